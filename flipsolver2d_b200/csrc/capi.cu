@@ -1,0 +1,527 @@
+// C ABI glue (include/fs2d.h): handle lifetime, state transfer and the stage entry points.
+#include <algorithm>
+#include <cstring>
+#include <new>
+
+#include "fs2d_internal.h"
+
+int pcgTileBlocks(const Ctx *ctx);
+
+namespace
+{
+struct GridDesc
+{
+    void **ptr;
+    int elemSize;
+    int64_t count;
+};
+
+GridDesc gridDesc(Ctx *c, int grid)
+{
+    switch (grid)
+    {
+    case FS2D_GRID_U: return {reinterpret_cast<void **>(&c->U), 4, c->NU};
+    case FS2D_GRID_V: return {reinterpret_cast<void **>(&c->V), 4, c->NV};
+    case FS2D_GRID_U_VALID: return {reinterpret_cast<void **>(&c->uValid), 1, c->NU};
+    case FS2D_GRID_V_VALID: return {reinterpret_cast<void **>(&c->vValid), 1, c->NV};
+    case FS2D_GRID_SAVED_U: return {reinterpret_cast<void **>(&c->savedU), 4, c->NU};
+    case FS2D_GRID_SAVED_V: return {reinterpret_cast<void **>(&c->savedV), 4, c->NV};
+    case FS2D_GRID_MATERIAL: return {reinterpret_cast<void **>(&c->material), 1, c->N};
+    case FS2D_GRID_FLUID_SDF: return {reinterpret_cast<void **>(&c->fluidSdf), 4, c->N};
+    case FS2D_GRID_SOLID_SDF: return {reinterpret_cast<void **>(&c->solidSdf), 4, c->N};
+    case FS2D_GRID_VISCOSITY: return {reinterpret_cast<void **>(&c->viscosity), 4, c->N};
+    case FS2D_GRID_DENSITY: return {reinterpret_cast<void **>(&c->density), 4, c->N};
+    case FS2D_GRID_COUNTS: return {reinterpret_cast<void **>(&c->counts), 4, c->N};
+    case FS2D_GRID_EMITTER_ID: return {reinterpret_cast<void **>(&c->emitterId), 4, c->N};
+    case FS2D_GRID_SOLID_ID: return {reinterpret_cast<void **>(&c->solidId), 4, c->N};
+    case FS2D_GRID_DIVERGENCE_CONTROL: return {reinterpret_cast<void **>(&c->divergenceControl), 4, c->N};
+    case FS2D_GRID_TEST: return {reinterpret_cast<void **>(&c->testGrid), 4, c->N};
+    case FS2D_GRID_KNOWN_CENTERED: return {reinterpret_cast<void **>(&c->knownCentered), 1, c->N};
+    case FS2D_GRID_TEMPERATURE: return {reinterpret_cast<void **>(&c->temperature), 4, c->N};
+    case FS2D_GRID_CONCENTRATION: return {reinterpret_cast<void **>(&c->concentration), 4, c->N};
+    case FS2D_GRID_FUEL: return {reinterpret_cast<void **>(&c->fuel), 4, c->N};
+    case FS2D_GRID_PRESSURE: return {reinterpret_cast<void **>(&c->x), 8, c->N};
+    case FS2D_GRID_RHS: return {reinterpret_cast<void **>(&c->rhs), 8, c->N};
+    case FS2D_GRID_SOURCE_SDF: return {reinterpret_cast<void **>(&c->sourceSdf), 4, c->N};
+    case FS2D_GRID_SOURCE_SDF_ID: return {reinterpret_cast<void **>(&c->sourceSdfId), 4, c->N};
+    case FS2D_GRID_ADVECTED_U: return {reinterpret_cast<void **>(&c->advU), 4, c->NU};
+    case FS2D_GRID_ADVECTED_V: return {reinterpret_cast<void **>(&c->advV), 4, c->NV};
+    case FS2D_GRID_ADVECTED_SDF: return {reinterpret_cast<void **>(&c->advSdf), 4, c->N};
+    case FS2D_GRID_ADVECTED_VISCOSITY: return {reinterpret_cast<void **>(&c->advViscosity), 4, c->N};
+    default: return {nullptr, 0, 0};
+    }
+}
+
+template <class T> int devAlloc(Ctx *ctx, T **p, int64_t count, int fillByte = 0)
+{
+    FS2D_CUDA(cudaMalloc(reinterpret_cast<void **>(p), static_cast<size_t>(std::max<int64_t>(count, 1)) * sizeof(T)));
+    FS2D_CUDA(cudaMemsetAsync(*p, fillByte, static_cast<size_t>(std::max<int64_t>(count, 1)) * sizeof(T), ctx->stream));
+    return FS2D_OK;
+}
+
+__global__ void fillFloatKernel(float *p, long long n, float v)
+{
+    for (long long k = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; k < n;
+         k += static_cast<long long>(gridDim.x) * blockDim.x)
+        p[k] = v;
+}
+
+__global__ void fillIntKernel(int32_t *p, long long n, int32_t v)
+{
+    for (long long k = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; k < n;
+         k += static_cast<long long>(gridDim.x) * blockDim.x)
+        p[k] = v;
+}
+
+int allocAll(Ctx *ctx)
+{
+    const int64_t N = ctx->N, NU = ctx->NU, NV = ctx->NV;
+    const bool smoke = ctx->p.sim_type == FS2D_SIM_SMOKE || ctx->p.sim_type == FS2D_SIM_FIRE;
+    const bool fire = ctx->p.sim_type == FS2D_SIM_FIRE;
+    const bool nb = ctx->p.sim_type == FS2D_SIM_NBFLIP;
+    FS2D_TRY(devAlloc(ctx, &ctx->U, NU));
+    FS2D_TRY(devAlloc(ctx, &ctx->V, NV));
+    FS2D_TRY(devAlloc(ctx, &ctx->savedU, NU));
+    FS2D_TRY(devAlloc(ctx, &ctx->savedV, NV));
+    FS2D_TRY(devAlloc(ctx, &ctx->uValid, NU));
+    FS2D_TRY(devAlloc(ctx, &ctx->vValid, NV));
+    FS2D_TRY(devAlloc(ctx, &ctx->material, N, FS2D_EMPTY));  // MaterialGrid init value (materialgrid.cpp:5-8)
+    FS2D_TRY(devAlloc(ctx, &ctx->fluidSdf, N));
+    FS2D_TRY(devAlloc(ctx, &ctx->solidSdf, N));
+    FS2D_TRY(devAlloc(ctx, &ctx->viscosity, N));
+    FS2D_TRY(devAlloc(ctx, &ctx->density, N));
+    FS2D_TRY(devAlloc(ctx, &ctx->counts, N));
+    FS2D_TRY(devAlloc(ctx, &ctx->emitterId, N, 0xFF));       // -1 (flipsolver2d.cpp:38-39)
+    FS2D_TRY(devAlloc(ctx, &ctx->solidId, N, 0xFF));
+    FS2D_TRY(devAlloc(ctx, &ctx->divergenceControl, N));
+    FS2D_TRY(devAlloc(ctx, &ctx->testGrid, N));
+    FS2D_TRY(devAlloc(ctx, &ctx->knownCentered, N));
+    if (smoke)
+    {
+        FS2D_TRY(devAlloc(ctx, &ctx->temperature, N));
+        FS2D_TRY(devAlloc(ctx, &ctx->concentration, N));
+        fillFloatKernel<<<ctx->smCount * 4, 256, 0, ctx->stream>>>(ctx->temperature, N, ctx->p.ambient_temperature);
+    }
+    if (fire) FS2D_TRY(devAlloc(ctx, &ctx->fuel, N));
+    if (nb)
+    {
+        FS2D_TRY(devAlloc(ctx, &ctx->sourceSdf, N));
+        FS2D_TRY(devAlloc(ctx, &ctx->sourceSdfId, N, 0xFF));
+        FS2D_TRY(devAlloc(ctx, &ctx->advU, NU));
+        FS2D_TRY(devAlloc(ctx, &ctx->advV, NV));
+        FS2D_TRY(devAlloc(ctx, &ctx->advSdf, N));
+        FS2D_TRY(devAlloc(ctx, &ctx->advViscosity, N));
+    }
+    const int64_t big = std::max(NU, NV);
+    FS2D_TRY(devAlloc(ctx, &ctx->scratchA, big));
+    FS2D_TRY(devAlloc(ctx, &ctx->scratchB, big));
+    FS2D_TRY(devAlloc(ctx, &ctx->scratchC, big));
+    FS2D_TRY(devAlloc(ctx, &ctx->markers, big));
+
+    FS2D_TRY(devAlloc(ctx, &ctx->rhs, N));
+    FS2D_TRY(devAlloc(ctx, &ctx->x, N));
+    FS2D_TRY(devAlloc(ctx, &ctx->r[0], N));
+    FS2D_TRY(devAlloc(ctx, &ctx->r[1], N));
+    FS2D_TRY(devAlloc(ctx, &ctx->s[0], N));
+    FS2D_TRY(devAlloc(ctx, &ctx->s[1], N));
+    FS2D_TRY(devAlloc(ctx, &ctx->q, N));
+    FS2D_TRY(devAlloc(ctx, &ctx->z, N));
+    FS2D_TRY(devAlloc(ctx, &ctx->rowInfo, N));
+    FS2D_TRY(devAlloc(ctx, &ctx->preInfo, N));
+    ctx->maxBlocks = std::max({pcgTileBlocks(ctx), ctx->smCount * 8, ctx->p.convergence_threads, 1024});
+    FS2D_TRY(devAlloc(ctx, &ctx->partials, 3 * static_cast<int64_t>(ctx->maxBlocks)));
+    FS2D_TRY(devAlloc(ctx, &ctx->scalars, 1));
+    ctx->traceCapacity = std::max(ctx->p.pcg_iter_limit, 16) + 8;
+    FS2D_TRY(devAlloc(ctx, &ctx->trace, 4 * static_cast<int64_t>(ctx->traceCapacity)));
+
+    FS2D_TRY(devAlloc(ctx, &ctx->cellStart, N + 1));
+    FS2D_TRY(devAlloc(ctx, &ctx->cellCursor, N + 1));
+    FS2D_TRY(devAlloc(ctx, &ctx->reseedOffset, N + 1));
+    FS2D_TRY(devAlloc(ctx, &ctx->scanBlock, divUp(N + 1, 1024) + 1024));
+    FS2D_TRY(devAlloc(ctx, &ctx->d_counter, 16));
+    FS2D_TRY(devAlloc(ctx, &ctx->d_fscratch, 4096));
+    for (int k = 0; k < 16; k++) FS2D_CUDA(cudaEventCreate(&ctx->ev[k]));
+    ctx->eventsReady = true;
+    FS2D_CUDA(cudaGetLastError());
+    return FS2D_OK;
+}
+
+void freeAll(Ctx *c)
+{
+    void *ptrs[] = {c->U, c->V, c->savedU, c->savedV, c->uValid, c->vValid, c->material, c->fluidSdf, c->solidSdf,
+                    c->viscosity, c->density, c->counts, c->emitterId, c->solidId, c->divergenceControl, c->testGrid,
+                    c->knownCentered, c->temperature, c->concentration, c->fuel, c->sourceSdf, c->sourceSdfId, c->advU,
+                    c->advV, c->advSdf, c->advViscosity, c->scratchA, c->scratchB, c->scratchC, c->markers, c->rhs, c->x,
+                    c->r[0], c->r[1], c->s[0], c->s[1], c->q, c->z, c->rowInfo, c->preInfo, c->partials, c->scalars,
+                    c->trace, c->rangeLast, c->dead, c->perm, c->cellStart, c->cellCursor, c->scanBlock, c->d_counter,
+                    c->d_fscratch, c->obstacleFriction, c->sources, c->reseedOffset};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    for (int b = 0; b < 2; b++)
+    {
+        if (c->pb[b].pos) cudaFree(c->pb[b].pos);
+        if (c->pb[b].vel) cudaFree(c->pb[b].vel);
+        if (c->pb[b].props) cudaFree(c->pb[b].props);
+        if (c->pb[b].key) cudaFree(c->pb[b].key);
+    }
+    if (c->eventsReady)
+        for (int k = 0; k < 16; k++) cudaEventDestroy(c->ev[k]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+}
+}  // namespace
+
+extern "C" {
+
+int fs2d_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int fs2d_create(const fs2d_params *params, fs2d_handle *out)
+{
+    if (!params || !out || params->size_i <= 0 || params->size_j <= 0 || params->num_properties < 0) return FS2D_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return FS2D_ERR_NO_DEVICE;  // no CPU fallback, by design
+    if (params->device < 0 || params->device >= n) return FS2D_ERR_ARG;
+    Ctx *ctx = new (std::nothrow) Ctx();
+    if (!ctx) return FS2D_ERR_ARG;
+    ctx->p = *params;
+    ctx->I = params->size_i;
+    ctx->J = params->size_j;
+    ctx->N = static_cast<int64_t>(ctx->I) * ctx->J;
+    ctx->NU = static_cast<int64_t>(ctx->I + 1) * ctx->J;
+    ctx->NV = static_cast<int64_t>(ctx->I) * (ctx->J + 1);
+    ctx->device = params->device;
+    ctx->stepDt = 0.f;
+    int rc = FS2D_OK;
+    do
+    {
+        if (cudaSetDevice(ctx->device) != cudaSuccess) { rc = FS2D_ERR_CUDA; break; }
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, ctx->device) != cudaSuccess) { rc = FS2D_ERR_CUDA; break; }
+        ctx->smCount = prop.multiProcessorCount;
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = FS2D_ERR_CUDA; break; }
+        rc = allocAll(ctx);
+        if (rc == FS2D_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = FS2D_ERR_CUDA;
+    } while (0);
+    if (rc != FS2D_OK)
+    {
+        fprintf(stderr, "fs2d_create failed: %s\n", ctx->lastError.c_str());
+        freeAll(ctx);
+        delete ctx;
+        return rc;
+    }
+    *out = ctx;
+    return FS2D_OK;
+}
+
+int fs2d_destroy(fs2d_handle h)
+{
+    if (!h) return FS2D_ERR_ARG;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    freeAll(h);
+    delete h;
+    return FS2D_OK;
+}
+
+const char *fs2d_last_error(fs2d_handle h) { return h ? h->lastError.c_str() : "null handle"; }
+
+int fs2d_synchronize(fs2d_handle ctx)
+{
+    if (!ctx) return FS2D_ERR_ARG;
+    FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FS2D_OK;
+}
+
+void *fs2d_stream(fs2d_handle h) { return h ? static_cast<void *>(h->stream) : nullptr; }
+
+int64_t fs2d_launch_count(fs2d_handle h) { return h ? h->launches : 0; }
+
+int64_t fs2d_grid_elements(fs2d_handle h, int grid) { return h ? gridDesc(h, grid).count : 0; }
+
+int fs2d_grid_element_size(int grid)
+{
+    Ctx dummy;
+    return gridDesc(&dummy, grid).elemSize;
+}
+
+void *fs2d_grid_device_ptr(fs2d_handle h, int grid)
+{
+    if (!h) return nullptr;
+    GridDesc d = gridDesc(h, grid);
+    return d.ptr ? *d.ptr : nullptr;
+}
+
+int fs2d_upload_grid(fs2d_handle ctx, int grid, const void *host_data, size_t bytes)
+{
+    if (!ctx || !host_data) return FS2D_ERR_ARG;
+    GridDesc d = gridDesc(ctx, grid);
+    if (!d.ptr || !*d.ptr || bytes != static_cast<size_t>(d.count) * d.elemSize)
+    {
+        ctx->lastError = "fs2d_upload_grid: unknown grid or size mismatch";
+        return FS2D_ERR_ARG;
+    }
+    FS2D_CUDA(cudaMemcpyAsync(*d.ptr, host_data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FS2D_OK;
+}
+
+int fs2d_download_grid(fs2d_handle ctx, int grid, void *host_data, size_t bytes)
+{
+    if (!ctx || !host_data) return FS2D_ERR_ARG;
+    GridDesc d = gridDesc(ctx, grid);
+    if (!d.ptr || !*d.ptr || bytes != static_cast<size_t>(d.count) * d.elemSize)
+    {
+        ctx->lastError = "fs2d_download_grid: unknown grid or size mismatch";
+        return FS2D_ERR_ARG;
+    }
+    FS2D_CUDA(cudaMemcpyAsync(host_data, *d.ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FS2D_OK;
+}
+
+int fs2d_set_obstacles(fs2d_handle ctx, int count, const float *host_friction)
+{
+    if (!ctx || count < 0 || (count > 0 && !host_friction)) return FS2D_ERR_ARG;
+    if (ctx->obstacleFriction) cudaFree(ctx->obstacleFriction);
+    ctx->obstacleFriction = nullptr;
+    ctx->numObstacles = count;
+    FS2D_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->obstacleFriction), sizeof(float) * std::max(count, 1)));
+    if (count > 0)
+        FS2D_CUDA(cudaMemcpy(ctx->obstacleFriction, host_friction, sizeof(float) * count, cudaMemcpyHostToDevice));
+    return FS2D_OK;
+}
+
+int fs2d_set_sources(fs2d_handle ctx, int count, const fs2d_source *host_sources)
+{
+    if (!ctx || count < 0 || (count > 0 && !host_sources)) return FS2D_ERR_ARG;
+    if (ctx->sources) cudaFree(ctx->sources);
+    ctx->sources = nullptr;
+    ctx->numSources = count;
+    ctx->hostSources.assign(host_sources, host_sources + count);
+    FS2D_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->sources), sizeof(fs2d_source) * std::max(count, 1)));
+    if (count > 0)
+        FS2D_CUDA(cudaMemcpy(ctx->sources, host_sources, sizeof(fs2d_source) * count, cudaMemcpyHostToDevice));
+    return FS2D_OK;
+}
+
+// ---------------------------------------------------------------- particles
+int64_t fs2d_particle_count(fs2d_handle h) { return h ? h->count : 0; }
+
+int fs2d_upload_particles(fs2d_handle ctx, int64_t count, const float *host_pos, const float *host_vel,
+                          const float *host_props)
+{
+    if (!ctx || count < 0) return FS2D_ERR_ARG;
+    ctx->count = 0;
+    ctx->sorted = false;
+    return fs2d_append_particles(ctx, count, host_pos, host_vel, host_props);
+}
+
+int fs2d_append_particles(fs2d_handle ctx, int64_t count, const float *host_pos, const float *host_vel,
+                          const float *host_props)
+{
+    if (!ctx || count < 0 || (count > 0 && !host_pos)) return FS2D_ERR_ARG;
+    if (count == 0) return FS2D_OK;
+    const int64_t base = ctx->count;
+    FS2D_TRY(particlesReserve(ctx, base + count));
+    ParticleBuffers &b = ctx->pb[ctx->cur];
+    FS2D_CUDA(cudaMemcpyAsync(b.pos + base, host_pos, sizeof(float2) * count, cudaMemcpyHostToDevice, ctx->stream));
+    if (host_vel)
+        FS2D_CUDA(cudaMemcpyAsync(b.vel + base, host_vel, sizeof(float2) * count, cudaMemcpyHostToDevice, ctx->stream));
+    else
+        FS2D_CUDA(cudaMemsetAsync(b.vel + base, 0, sizeof(float2) * count, ctx->stream));
+    for (int k = 0; k < ctx->p.num_properties; k++)
+    {
+        float *dst = b.props + static_cast<int64_t>(k) * b.capacity + base;
+        if (host_props)
+            FS2D_CUDA(cudaMemcpyAsync(dst, host_props + static_cast<int64_t>(k) * count, sizeof(float) * count,
+                                      cudaMemcpyHostToDevice, ctx->stream));
+        else
+            FS2D_CUDA(cudaMemsetAsync(dst, 0, sizeof(float) * count, ctx->stream));
+    }
+    FS2D_CUDA(cudaMemsetAsync(ctx->dead + base, 0, count, ctx->stream));
+    FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->count = base + count;
+    ctx->sorted = false;
+    return FS2D_OK;
+}
+
+int fs2d_download_particles(fs2d_handle ctx, float *host_pos, float *host_vel, float *host_props)
+{
+    if (!ctx) return FS2D_ERR_ARG;
+    const int64_t n = ctx->count;
+    if (n == 0) return FS2D_OK;
+    ParticleBuffers &b = ctx->pb[ctx->cur];
+    if (host_pos) FS2D_CUDA(cudaMemcpyAsync(host_pos, b.pos, sizeof(float2) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (host_vel) FS2D_CUDA(cudaMemcpyAsync(host_vel, b.vel, sizeof(float2) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (host_props)
+        for (int k = 0; k < ctx->p.num_properties; k++)
+            FS2D_CUDA(cudaMemcpyAsync(host_props + static_cast<int64_t>(k) * n, b.props + static_cast<int64_t>(k) * b.capacity,
+                                      sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FS2D_OK;
+}
+
+// ---------------------------------------------------------------- PCG
+int fs2d_pcg_solve(fs2d_handle ctx, const double *host_rhs, double *host_x, int iter_limit, double tol, int *iters)
+{
+    if (!ctx || !host_rhs || !host_x || iter_limit < 0) return FS2D_ERR_ARG;
+    const size_t bytes = static_cast<size_t>(ctx->N) * sizeof(double);
+    FS2D_CUDA(cudaMemcpyAsync(ctx->rhs, host_rhs, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    FS2D_TRY(pcgSolveDevice(ctx, iter_limit, tol));
+    FS2D_CUDA(cudaMemcpyAsync(host_x, ctx->x, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return fs2d_pcg_last_iterations(ctx, iters);
+}
+
+int fs2d_pcg_solve_device(fs2d_handle ctx, int iter_limit, double tol)
+{
+    if (!ctx || iter_limit < 0) return FS2D_ERR_ARG;
+    return pcgSolveDevice(ctx, iter_limit, tol);
+}
+
+int fs2d_pcg_last_iterations(fs2d_handle ctx, int *iters)
+{
+    if (!ctx) return FS2D_ERR_ARG;
+    PcgScalars sc;
+    FS2D_CUDA(cudaMemcpyAsync(&sc, ctx->scalars, sizeof(sc), cudaMemcpyDeviceToHost, ctx->stream));
+    FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->lastPcgIters = sc.result;
+    if (iters) *iters = sc.result;
+    return FS2D_OK;
+}
+
+int fs2d_pcg_trace(fs2d_handle ctx, double *host_trace, int max_iterations, int *written)
+{
+    if (!ctx || !host_trace || max_iterations < 0) return FS2D_ERR_ARG;
+    PcgScalars sc;
+    FS2D_CUDA(cudaMemcpyAsync(&sc, ctx->scalars, sizeof(sc), cudaMemcpyDeviceToHost, ctx->stream));
+    FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
+    int n = std::min({sc.iter, max_iterations, ctx->traceCapacity});
+    if (n > 0) FS2D_CUDA(cudaMemcpy(host_trace, ctx->trace, sizeof(double) * 4 * n, cudaMemcpyDeviceToHost));
+    if (written) *written = n;
+    return FS2D_OK;
+}
+
+int fs2d_spmv(fs2d_handle ctx, const double *host_in, double *host_out)
+{
+    if (!ctx || !host_in || !host_out) return FS2D_ERR_ARG;
+    return pcgSpmvHost(ctx, host_in, host_out, false);
+}
+
+int fs2d_precond_apply(fs2d_handle ctx, const double *host_in, double *host_out)
+{
+    if (!ctx || !host_in || !host_out) return FS2D_ERR_ARG;
+    return pcgSpmvHost(ctx, host_in, host_out, true);
+}
+
+int fs2d_download_matrix(fs2d_handle ctx, uint8_t *host_is_unit, uint8_t *host_mask, uint8_t *host_count,
+                         uint8_t *host_precond_counts)
+{
+    if (!ctx) return FS2D_ERR_ARG;
+    const size_t n = static_cast<size_t>(ctx->N);
+    std::vector<uint8_t> row(n);
+    std::vector<uint16_t> pre(n);
+    FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
+    FS2D_CUDA(cudaMemcpy(row.data(), ctx->rowInfo, n, cudaMemcpyDeviceToHost));
+    FS2D_CUDA(cudaMemcpy(pre.data(), ctx->preInfo, n * 2, cudaMemcpyDeviceToHost));
+    for (size_t k = 0; k < n; k++)
+    {
+        if (host_is_unit) host_is_unit[k] = (row[k] & FS2D_ROW_UNIT) ? 1 : 0;
+        if (host_mask) host_mask[k] = row[k] & 0xF;
+        if (host_count) host_count[k] = (row[k] >> 4) & 7;
+        if (host_precond_counts)
+            for (int d = 0; d < 4; d++) host_precond_counts[d * n + k] = (pre[k] >> (3 * d)) & 7;
+    }
+    return FS2D_OK;
+}
+
+// ---------------------------------------------------------------- stages
+int fs2d_set_step_dt(fs2d_handle h, float dt)
+{
+    if (!h) return FS2D_ERR_ARG;
+    h->stepDt = dt;
+    return FS2D_OK;
+}
+
+int fs2d_max_particle_velocity(fs2d_handle h, float *out) { return (h && out) ? particlesMaxVelocity(h, out) : FS2D_ERR_ARG; }
+
+int fs2d_advect(fs2d_handle h)
+{
+    if (!h) return FS2D_ERR_ARG;
+    FS2D_TRY(particlesAdvect(h));
+    if (h->p.parameter_handling == FS2D_PARAMS_GRID) FS2D_TRY(gridEulerAdvectParameters(h));  // flipsolver2d.cpp:157-160
+    return FS2D_OK;
+}
+
+int fs2d_build_matrix(fs2d_handle h) { return h ? gridBuildMatrix(h) : FS2D_ERR_ARG; }
+int fs2d_sort_particles(fs2d_handle h) { return h ? particlesSort(h) : FS2D_ERR_ARG; }
+int fs2d_update_density_grid(fs2d_handle h) { return h ? transferDensity(h) : FS2D_ERR_ARG; }
+int fs2d_density_rhs(fs2d_handle h) { return h ? gridDensityRhs(h) : FS2D_ERR_ARG; }
+
+int fs2d_density_correction(fs2d_handle h, int *iters)
+{
+    if (!h) return FS2D_ERR_ARG;
+    // densityCorrection (flipsolver2d.cpp:164-186)
+    FS2D_TRY(transferDensity(h));
+    FS2D_TRY(gridDensityRhs(h));
+    FS2D_TRY(pcgSolveDevice(h, h->p.pcg_iter_limit, h->p.project_tolerance));
+    int it = 0;
+    FS2D_TRY(fs2d_pcg_last_iterations(h, &it));
+    if (iters) *iters = it;
+    if (it >= h->p.pcg_iter_limit) return FS2D_OK;  // "Density solver solving failed!": result discarded (:179-182)
+    FS2D_TRY(particlesAdjustByDensity(h));
+    return FS2D_OK;
+}
+
+int fs2d_particle_to_grid(fs2d_handle h)
+{
+    if (!h) return FS2D_ERR_ARG;
+    FS2D_TRY(transferVelocity(h));                                                          // particleVelocityToGrid
+    if (h->p.parameter_handling != FS2D_PARAMS_GRID) FS2D_TRY(transferCentered(h));         // flipsolver2d.cpp:1216-1219
+    return FS2D_OK;
+}
+
+int fs2d_update_sdf(fs2d_handle h) { return h ? transferSdf(h) : FS2D_ERR_ARG; }
+int fs2d_update_materials(fs2d_handle h) { return h ? gridUpdateMaterials(h) : FS2D_ERR_ARG; }
+int fs2d_after_transfer(fs2d_handle h) { return h ? gridAfterTransfer(h) : FS2D_ERR_ARG; }
+int fs2d_extrapolate_velocity(fs2d_handle h, int radius) { return h ? gridExtrapolateVelocity(h, radius) : FS2D_ERR_ARG; }
+int fs2d_extrapolate_sdf_inside(fs2d_handle h) { return h ? gridExtrapolateSdf(h, true) : FS2D_ERR_ARG; }
+int fs2d_extrapolate_sdf_outside(fs2d_handle h) { return h ? gridExtrapolateSdf(h, false) : FS2D_ERR_ARG; }
+int fs2d_save_velocity(fs2d_handle h) { return h ? gridSaveVelocity(h) : FS2D_ERR_ARG; }
+int fs2d_apply_body_forces(fs2d_handle h) { return h ? gridBodyForces(h) : FS2D_ERR_ARG; }
+int fs2d_pressure_rhs(fs2d_handle h) { return h ? gridPressureRhs(h) : FS2D_ERR_ARG; }
+int fs2d_apply_pressure(fs2d_handle h) { return h ? gridApplyPressure(h) : FS2D_ERR_ARG; }
+
+int fs2d_project(fs2d_handle h, int *iters)
+{
+    if (!h) return FS2D_ERR_ARG;
+    // project (flipsolver2d.cpp:93-126)
+    FS2D_TRY(gridPressureRhs(h));
+    FS2D_TRY(pcgSolveDevice(h, h->p.pcg_iter_limit, h->p.project_tolerance));
+    FS2D_TRY(gridApplyPressure(h));
+    if (iters) FS2D_TRY(fs2d_pcg_last_iterations(h, iters));
+    return FS2D_OK;
+}
+
+int fs2d_velocity_from_solids(fs2d_handle h) { return h ? gridVelocityFromSolids(h) : FS2D_ERR_ARG; }
+int fs2d_apply_viscosity(fs2d_handle h, int *iters) { return h ? gridViscosity(h, iters) : FS2D_ERR_ARG; }
+int fs2d_particle_update(fs2d_handle h) { return h ? particlesUpdate(h) : FS2D_ERR_ARG; }
+int fs2d_count_particles(fs2d_handle h) { return h ? particlesCount(h) : FS2D_ERR_ARG; }
+int fs2d_reseed_plan(fs2d_handle h, int64_t *candidates) { return (h && candidates) ? particlesReseedPlan(h, candidates) : FS2D_ERR_ARG; }
+int fs2d_reseed_apply(fs2d_handle h, int64_t candidates, const float *host_uniform_xy)
+{
+    return h ? particlesReseedApply(h, candidates, host_uniform_xy) : FS2D_ERR_ARG;
+}
+
+int fs2d_nbflip_advect_grids(fs2d_handle h)
+{
+    if (!h) return FS2D_ERR_ARG;
+    FS2D_TRY(particlesPruneNarrowBand(h));
+    return gridNbflipAdvect(h);
+}
+
+}  // extern "C"

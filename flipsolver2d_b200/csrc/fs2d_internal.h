@@ -1,0 +1,187 @@
+// Internal state of one fs2d handle: every per-substep array lives on the device.
+// Layout notes are in DESIGN.md ("Data layout in HBM").
+#ifndef FS2D_INTERNAL_H
+#define FS2D_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/fs2d.h"
+
+#define FS2D_CUDA(call)                                                                             \
+    do                                                                                              \
+    {                                                                                               \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+        {                                                                                           \
+            char b__[512];                                                                          \
+            snprintf(b__, sizeof(b__), "%s:%d %s -> %s", __FILE__, __LINE__, #call,                 \
+                     cudaGetErrorString(e__));                                                      \
+            ctx->lastError = b__;                                                                   \
+            return FS2D_ERR_CUDA;                                                                   \
+        }                                                                                           \
+    } while (0)
+
+#define FS2D_TRY(expr)                  \
+    do                                  \
+    {                                   \
+        int rc__ = (expr);              \
+        if (rc__ != FS2D_OK) return rc__; \
+    } while (0)
+
+// Material predicates (materialgrid.h:15-20).
+__host__ __device__ inline bool matFluid(int8_t m) { return (m & 0x40) != 0; }
+__host__ __device__ inline bool matStrictFluid(int8_t m) { return m == 0x40; }
+__host__ __device__ inline bool matEmpty(int8_t m) { return (m & 0x10) != 0; }
+__host__ __device__ inline bool matSolid(int8_t m) { return (m & 0x20) != 0; }
+__host__ __device__ inline bool matSource(int8_t m) { return m == 0x41; }
+__host__ __device__ inline bool matSink(int8_t m) { return m == 0x12; }
+
+// Per-cell pressure-row byte (replaces IndexedPressureParameterUnit, pressuredata.h:97-151):
+// bit 7 = the cell has a matrix row, bits 4-6 = nonsolidNeighborCount (0..4),
+// bits 0-3 = fluidNeighborMask (I_NEG 1, I_POS 2, J_NEG 4, J_POS 8).
+#define FS2D_ROW_UNIT 0x80u
+// Per-cell preconditioner half-word (replaces IndexedIPPCoefficientUnit,
+// PressureIPPCoeficients.h:8-48): bit 15 = row exists, then four 3-bit fields with
+// nonsolidNeighborCount of the iNeg, iPos, jNeg, jPos neighbour (bits 0-2, 3-5, 6-8, 9-11).
+#define FS2D_PRE_UNIT 0x8000u
+
+struct PcgScalars
+{
+    double sigma;     // r.z of the current iteration
+    double alpha;     // step of the last executed iteration (pending x update)
+    double beta;
+    double err;
+    double gamma;
+    int iter;         // iterations completed
+    int done;         // 1 once converged / zero rhs
+    int result;       // value LinearSolver::solve returns
+    int pad;
+    unsigned int ticketA;
+    unsigned int ticketB;
+    unsigned int ticketC;
+    unsigned int pad2;
+};
+
+struct ParticleBuffers
+{
+    float2 *pos = nullptr;
+    float2 *vel = nullptr;
+    float *props = nullptr;      // [numProps][capacity]
+    uint32_t *key = nullptr;     // cell key at sort time
+    int64_t capacity = 0;
+};
+
+struct fs2d_context
+{
+    fs2d_params p;
+    int I = 0, J = 0;
+    int64_t N = 0, NU = 0, NV = 0;
+    int device = 0;
+    int smCount = 148;
+    cudaStream_t stream = nullptr;
+    std::string lastError;
+    int64_t launches = 0;
+    float stepDt = 0.f;
+
+    // ---- grids
+    float *U = nullptr, *V = nullptr, *savedU = nullptr, *savedV = nullptr;
+    uint8_t *uValid = nullptr, *vValid = nullptr;
+    int8_t *material = nullptr;
+    float *fluidSdf = nullptr, *solidSdf = nullptr, *viscosity = nullptr, *density = nullptr;
+    int32_t *counts = nullptr, *emitterId = nullptr, *solidId = nullptr;
+    float *divergenceControl = nullptr, *testGrid = nullptr;
+    uint8_t *knownCentered = nullptr;
+    float *temperature = nullptr, *concentration = nullptr, *fuel = nullptr;
+    float *sourceSdf = nullptr;
+    int32_t *sourceSdfId = nullptr;
+    float *advU = nullptr, *advV = nullptr, *advSdf = nullptr, *advViscosity = nullptr;
+    float *scratchA = nullptr, *scratchB = nullptr, *scratchC = nullptr;  // N+max(I,J)+1 floats each
+    int32_t *markers = nullptr;                                           // BFS layer markers, max(NU,NV)
+
+    // ---- PCG
+    double *rhs = nullptr, *x = nullptr, *r[2] = {nullptr, nullptr}, *s[2] = {nullptr, nullptr};
+    double *q = nullptr, *z = nullptr;
+    uint8_t *rowInfo = nullptr;       // N
+    uint16_t *preInfo = nullptr;      // N
+    double matrixScale = 0.0;
+    double *partials = nullptr;       // reduction scratch (3 * maxBlocks doubles)
+    int maxBlocks = 0;
+    PcgScalars *scalars = nullptr;    // device
+    double *trace = nullptr;          // device, 4 doubles per iteration
+    int traceCapacity = 0;
+    int64_t *rangeLast = nullptr;     // device, convergence_threads entries
+    int lastPcgIters = 0;
+
+    // ---- particles (double buffered for the sort)
+    ParticleBuffers pb[2];
+    int cur = 0;
+    int64_t count = 0;
+    uint8_t *dead = nullptr;          // capacity bytes
+    uint32_t *perm = nullptr;         // capacity
+    int32_t *cellStart = nullptr;     // N+1, valid after fs2d_sort_particles
+    int32_t *cellCursor = nullptr;    // N
+    int32_t *scanBlock = nullptr;     // scan scratch
+    bool sorted = false;
+    int64_t *d_counter = nullptr;     // device scalar scratch (8 int64)
+    float *d_fscratch = nullptr;      // device float scratch
+
+    // ---- scene tables
+    float *obstacleFriction = nullptr;
+    int numObstacles = 0;
+    fs2d_source *sources = nullptr;
+    int numSources = 0;
+    std::vector<fs2d_source> hostSources;
+
+    // ---- reseed plan
+    int32_t *reseedOffset = nullptr;  // N+1 exclusive scan of per-cell candidate counts
+    int64_t reseedCandidates = 0;
+
+    // ---- timing
+    cudaEvent_t ev[16];
+    bool eventsReady = false;
+};
+
+typedef fs2d_context Ctx;
+
+inline int divUp(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
+
+// pcg.cu
+int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol);
+int pcgSpmvHost(Ctx *ctx, const double *in, double *out, bool precond);
+// particles.cu
+int particlesReserve(Ctx *ctx, int64_t capacity);
+int particlesMaxVelocity(Ctx *ctx, float *out);
+int particlesAdvect(Ctx *ctx);
+int particlesSort(Ctx *ctx);
+int particlesUpdate(Ctx *ctx);
+int particlesCount(Ctx *ctx);
+int particlesAdjustByDensity(Ctx *ctx);
+int particlesReseedPlan(Ctx *ctx, int64_t *candidates);
+int particlesReseedApply(Ctx *ctx, int64_t candidates, const float *hostUniform);
+int particlesPruneNarrowBand(Ctx *ctx);
+// transfer.cu
+int transferVelocity(Ctx *ctx);
+int transferCentered(Ctx *ctx);
+int transferDensity(Ctx *ctx);
+int transferSdf(Ctx *ctx);
+// grid_ops.cu
+int gridBuildMatrix(Ctx *ctx);
+int gridUpdateMaterials(Ctx *ctx);
+int gridAfterTransfer(Ctx *ctx);
+int gridExtrapolateVelocity(Ctx *ctx, int radius);
+int gridExtrapolateSdf(Ctx *ctx, bool inside);
+int gridSaveVelocity(Ctx *ctx);
+int gridBodyForces(Ctx *ctx);
+int gridPressureRhs(Ctx *ctx);
+int gridDensityRhs(Ctx *ctx);
+int gridApplyPressure(Ctx *ctx);
+int gridVelocityFromSolids(Ctx *ctx);
+int gridEulerAdvectParameters(Ctx *ctx);
+int gridNbflipAdvect(Ctx *ctx);
+int gridViscosity(Ctx *ctx, int *iters);
+
+#endif

@@ -1,0 +1,543 @@
+// Kernel group 4: the pressure-projection PCG.
+//
+// Replaces LinearSolver::solve (linearsolver.cpp:25-73), IndexedPressureParameters::multiply
+// (pressuredata.h:132-238), IndexedIPPCoefficients::multiply (PressureIPPCoeficients.h:23-132)
+// and the VOps BLAS-1 passes (vmath.cpp:25-136) with two fused, bandwidth-bound kernels per
+// iteration plus device-resident scalars, so a solve never synchronises with the host:
+//
+//   K1(i):  s_i = z + beta*s_{i-1}          (addMul, linearsolver.cpp:68)
+//           x  += alpha_{i-1}*s_{i-1}       (deferred addMul of :51 -- s_{i-1} is in flight anyway)
+//           q   = A*s_i                     (:49)      gamma = q.s_i -> alpha_i (:50)
+//   K2(i):  r  -= alpha_i*q                 (:52)
+//           z   = M*r   sigma' = z.r        (:63-66)   err = max|r| (:53)
+//           last block decides convergence / beta (:59-69)
+//
+// Per iteration each kernel streams every vector it touches exactly once: K1 reads z, s, x
+// and writes s, q, x; K2 reads r, q and writes r, z -> 10 fp64 passes + 3 bytes of per-cell
+// row info = 83 B/cell (the reference makes 18 passes). Stencil neighbours come from a
+// shared-memory tile of the *derived* vector (s_i resp. the updated r), so the 5-point
+// operators never re-read HBM. Vectors stay fp64 like the reference's std::vector<double>
+// (linearsolver.h:15-20); arithmetic uses explicit non-contracted mul/add in the reference's
+// evaluation order so a single operator application is bit-identical to the strict oracle.
+#include "fs2d_internal.h"
+
+namespace
+{
+constexpr int TR = 16;        // tile rows
+constexpr int TC = 128;       // tile columns
+constexpr int NT = 256;       // threads per CTA
+constexpr int SW = TC + 2;    // shared row stride (doubles)
+
+enum Mode { MODE_K1 = 0, MODE_K2 = 1, MODE_APPLY_A = 2, MODE_APPLY_M = 3 };
+
+struct PcgArgs
+{
+    int I, J;
+    long long N;
+    int tilesJ;
+    double scale;
+    double pre[8];            // 1/(k*scale), k = 0..4 (getIPPCoefficients, flipsolver2d.cpp:924-927)
+    const uint8_t *rowInfo;
+    const uint16_t *preInfo;
+    const double *in0;        // K1: z      K2: r_in   APPLY: input vector
+    const double *in1;        // K1: s_old  K2: q
+    double *out0;             // K1: s_new  K2: r_out
+    double *out1;             // K1: q      K2: z      APPLY: output vector
+    double *x;                // K1 only
+    double *partials;
+    PcgScalars *sc;
+    double *trace;
+    int traceCapacity;
+    double tol;
+    int compat;               // 1: convergence decided by the range kernel
+};
+
+__device__ __forceinline__ double warpSum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ double warpMax(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Sum (or max) over the CTA; result valid in thread 0.
+template <bool IS_MAX> __device__ double blockReduce(double v, double *scratch /* >= 8 doubles */)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = IS_MAX ? warpMax(v) : warpSum(v);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    if (warp == 0)
+    {
+        v = (lane < (blockDim.x >> 5)) ? scratch[lane] : (IS_MAX ? 0.0 : 0.0);
+        v = IS_MAX ? warpMax(v) : warpSum(v);
+    }
+    return v;
+}
+
+// Deterministic final reduction by the last CTA: fixed assignment of partials to threads.
+template <bool IS_MAX> __device__ double finalReduce(const double *partials, int count, double *scratch)
+{
+    double v = 0.0;
+    for (int k = threadIdx.x; k < count; k += blockDim.x)
+    {
+        double p = __ldcg(partials + k);
+        v = IS_MAX ? fmax(v, p) : v + p;
+    }
+    return blockReduce<IS_MAX>(v, scratch);
+}
+
+// One row of A (IndexedPressureParameterUnit::multiply, pressuredata.h:132-146): centre,
+// iNeg, iPos, jNeg, jPos in that order, products and sums individually rounded.
+__device__ __forceinline__ double rowA(uint8_t info, double scale, double c, double im, double ip, double jm, double jp)
+{
+    if (!(info & FS2D_ROW_UNIT)) return c;  // identity row (pressuredata.h:227-236)
+    const double cnt = static_cast<double>((info >> 4) & 7u);
+    const double ns = -scale;
+    double acc = __dmul_rn(__dmul_rn(scale, cnt), c);
+    acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(ns, static_cast<double>(info & 1u)), im));
+    acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(ns, static_cast<double>((info >> 1) & 1u)), ip));
+    acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(ns, static_cast<double>((info >> 2) & 1u)), jm));
+    acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(ns, static_cast<double>((info >> 3) & 1u)), jp));
+    return acc;
+}
+
+// One row of M (IndexedIPPCoefficientUnit::multiply, PressureIPPCoeficients.h:23-40): centre,
+// jNeg, jPos, iNeg, iPos in that order.
+__device__ __forceinline__ double rowM(uint16_t info, const double *pre, double c, double im, double ip, double jm, double jp)
+{
+    if (!(info & FS2D_PRE_UNIT)) return c;
+    const double iNeg = pre[info & 7u], iPos = pre[(info >> 3) & 7u];
+    const double jNeg = pre[(info >> 6) & 7u], jPos = pre[(info >> 9) & 7u];
+    const double diag = __dadd_rn(__dadd_rn(1.0, __dmul_rn(iNeg, iNeg)), __dmul_rn(jNeg, jNeg));
+    double acc = __dmul_rn(diag, c);
+    acc = __dadd_rn(acc, __dmul_rn(jNeg, jm));
+    acc = __dadd_rn(acc, __dmul_rn(jPos, jp));
+    acc = __dadd_rn(acc, __dmul_rn(iNeg, im));
+    acc = __dadd_rn(acc, __dmul_rn(iPos, ip));
+    return acc;
+}
+
+template <int MODE> __global__ void __launch_bounds__(NT) pcgTileKernel(PcgArgs a)
+{
+    __shared__ double tile[(TR + 2) * SW];
+    __shared__ double red[8];
+    __shared__ double preTbl[8];
+    __shared__ int isLast;
+
+    if (MODE == MODE_K1 || MODE == MODE_K2)
+    {
+        if (a.sc->done) return;
+    }
+    const int tid = threadIdx.x;
+    if (MODE == MODE_K2 || MODE == MODE_APPLY_M)
+    {
+        if (tid < 8) preTbl[tid] = a.pre[tid];
+    }
+
+    const int ti = blockIdx.x / a.tilesJ, tj = blockIdx.x - ti * a.tilesJ;
+    const int i0 = ti * TR, j0 = tj * TC;
+    const long long J = a.J, N = a.N;
+
+    double coef = 0.0, alphaPrev = 0.0;
+    if (MODE == MODE_K1)
+    {
+        coef = a.sc->beta;
+        alphaPrev = a.sc->alpha;
+    }
+    else if (MODE == MODE_K2)
+    {
+        coef = a.sc->alpha;
+    }
+
+    // ---- load phase: derived vector into shared memory, by LINEAR index so that the
+    // j = 0 / J-1 neighbours wrap to the adjacent row exactly as the reference's
+    // linearIdxOfOffset(idx, 0, +-1) does (pressuredata.h:135-145).
+    // main body: (TR+2) rows x TC columns, each warp reads 32 consecutive doubles
+    for (int e = tid; e < (TR + 2) * TC; e += NT)
+    {
+        const int ar = e / TC, bc = e - ar * TC;  // ar 0..TR+1 (halo rows 0 and TR+1), bc 0..TC-1
+        const long long gi = i0 - 1 + ar, gj = j0 + bc;
+        const long long n = gi * J + gj;
+        double v = 0.0;
+        if (n >= 0 && n < N)
+        {
+            if (MODE == MODE_K1)
+            {
+                const double zv = a.in0[n], so = a.in1[n];
+                v = __dadd_rn(zv, __dmul_rn(so, coef));
+                if (ar >= 1 && ar <= TR && gi < a.I && gj < J)
+                {
+                    a.out0[n] = v;
+                    a.x[n] = __dadd_rn(a.x[n], __dmul_rn(so, alphaPrev));
+                }
+            }
+            else if (MODE == MODE_K2)
+            {
+                v = __dsub_rn(a.in0[n], __dmul_rn(a.in1[n], coef));
+                if (ar >= 1 && ar <= TR && gi < a.I && gj < J) a.out0[n] = v;
+            }
+            else
+            {
+                v = a.in0[n];
+            }
+        }
+        tile[ar * SW + bc + 1] = v;
+    }
+    // halo columns (left j0-1, right j0+TC) for the TR interior rows
+    if (tid < 2 * TR)
+    {
+        const int side = tid / TR, ar = 1 + (tid - side * TR);
+        const long long gi = i0 - 1 + ar, gj = side ? (j0 + TC) : (j0 - 1);
+        const long long n = gi * J + gj;
+        double v = 0.0;
+        if (n >= 0 && n < N)
+        {
+            if (MODE == MODE_K1)
+                v = __dadd_rn(a.in0[n], __dmul_rn(a.in1[n], coef));
+            else if (MODE == MODE_K2)
+                v = __dsub_rn(a.in0[n], __dmul_rn(a.in1[n], coef));
+            else
+                v = a.in0[n];
+        }
+        tile[ar * SW + (side ? TC + 1 : 0)] = v;
+    }
+    __syncthreads();
+
+    // ---- stencil phase: thread owns one column and marches TR/2 rows
+    const int bc = tid % TC, rg = tid / TC;  // rg 0..1
+    const long long gj = j0 + bc;
+    double accDot = 0.0, accMax = 0.0;
+    if (gj < J)
+    {
+#pragma unroll 4
+        for (int k = 0; k < TR / 2; k++)
+        {
+            const int ar = 1 + rg * (TR / 2) + k;
+            const long long gi = i0 - 1 + ar;
+            if (gi >= a.I) break;
+            const long long n = gi * J + gj;
+            const double *t = tile + ar * SW + bc + 1;
+            const double c = t[0], im = t[-SW], ip = t[SW], jm = t[-1], jp = t[1];
+            double o;
+            if (MODE == MODE_K1 || MODE == MODE_APPLY_A)
+                o = rowA(a.rowInfo[n], a.scale, c, im, ip, jm, jp);
+            else
+                o = rowM(a.preInfo[n], preTbl, c, im, ip, jm, jp);
+            a.out1[n] = o;
+            accDot += o * c;
+            accMax = fmax(accMax, fabs(c));
+        }
+    }
+    if (MODE == MODE_APPLY_A || MODE == MODE_APPLY_M) return;
+
+    // ---- reductions: per-CTA partials, finished by the last CTA in a fixed order
+    const int nb = gridDim.x;
+    double bs = blockReduce<false>(accDot, red);
+    double bm = 0.0;
+    if (MODE == MODE_K2) bm = blockReduce<true>(accMax, red);
+    if (tid == 0)
+    {
+        a.partials[blockIdx.x] = bs;
+        if (MODE == MODE_K2) a.partials[nb + blockIdx.x] = bm;
+        __threadfence();
+        unsigned int *ticket = (MODE == MODE_K1) ? &a.sc->ticketA : &a.sc->ticketB;
+        isLast = (atomicAdd(ticket, 1u) == static_cast<unsigned int>(nb - 1));
+    }
+    __syncthreads();
+    if (!isLast) return;
+    __threadfence();
+    double total = finalReduce<false>(a.partials, nb, red);
+    double emax = 0.0;
+    if (MODE == MODE_K2) emax = finalReduce<true>(a.partials + nb, nb, red);
+    if (tid == 0)
+    {
+        PcgScalars *sc = a.sc;
+        if (MODE == MODE_K1)
+        {
+            sc->gamma = total;
+            sc->alpha = sc->sigma / (total + 1e-8);  // linearsolver.cpp:50
+            sc->ticketA = 0;
+        }
+        else
+        {
+            sc->ticketB = 0;
+            sc->gamma = total;  // sigma' parked until the decision
+            sc->err = emax;
+            if (!a.compat)
+            {
+                const int it = sc->iter;
+                double beta = 0.0;
+                if (emax <= a.tol)  // linearsolver.cpp:59-61
+                {
+                    sc->done = 1;
+                    sc->result = it;
+                }
+                else
+                {
+                    beta = total / sc->sigma;  // :66-67
+                    sc->beta = beta;
+                    sc->sigma = total;
+                }
+                if (a.trace && it < a.traceCapacity)
+                {
+                    a.trace[4 * it + 0] = sc->alpha;
+                    a.trace[4 * it + 1] = beta;
+                    a.trace[4 * it + 2] = total;
+                    a.trace[4 * it + 3] = emax;
+                }
+                sc->iter = it + 1;
+            }
+        }
+    }
+}
+
+// Reference-compatible convergence value (vmath.cpp:100-136): for each ThreadPool range
+// the |r| of its LAST non-zero element (DBL_MIN when the range is all zero), then the max
+// over ranges. One CTA per range scans backwards and stops at the first chunk with a hit.
+__global__ void __launch_bounds__(NT) pcgRangeErrKernel(const double *r, long long N, int T, double *rangeVals,
+                                                        PcgScalars *sc, double tol, double *trace, int traceCapacity)
+{
+    __shared__ long long best;
+    __shared__ int isLast;
+    if (sc->done) return;
+    const int t = blockIdx.x;
+    // splitRange (threadpool.cpp:41-76) for N >= T: partSize = N/T, first N%T ranges one longer
+    const long long part = N / T, rem = N - part * T;
+    const long long start = t * part + (t < rem ? t : rem);
+    const long long end = start + part + (t < rem ? 1 : 0);
+    if (threadIdx.x == 0) best = -1;
+    __syncthreads();
+    for (long long hi = end; hi > start; hi -= 4 * NT)
+    {
+        long long local = -1;
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+        {
+            const long long idx = hi - 1 - (threadIdx.x + static_cast<long long>(u) * NT);
+            if (idx >= start && r[idx] != 0.0 && idx > local) local = idx;
+        }
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            long long other = __shfl_down_sync(0xffffffffu, local, o);
+            local = other > local ? other : local;
+        }
+        if ((threadIdx.x & 31) == 0 && local >= 0) atomicMax(&best, local);
+        __syncthreads();
+        if (best >= 0) break;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+    {
+        rangeVals[t] = best >= 0 ? fabs(r[best]) : 2.2250738585072014e-308;
+        __threadfence();
+        isLast = (atomicAdd(&sc->ticketC, 1u) == static_cast<unsigned int>(T - 1));
+    }
+    __syncthreads();
+    if (!isLast || threadIdx.x != 0) return;
+    __threadfence();
+    double err = 0.0;
+    for (int k = 0; k < T; k++)
+    {
+        const double v = __ldcg(rangeVals + k);
+        if (v > err) err = v;
+    }
+    sc->ticketC = 0;
+    const int it = sc->iter;
+    const double sigmaNew = sc->gamma;
+    double beta = 0.0;
+    const double trueMax = sc->err;
+    sc->err = err;
+    if (err <= tol)
+    {
+        sc->done = 1;
+        sc->result = it;
+    }
+    else
+    {
+        beta = sigmaNew / sc->sigma;
+        sc->beta = beta;
+        sc->sigma = sigmaNew;
+    }
+    if (trace && it < traceCapacity)
+    {
+        trace[4 * it + 0] = sc->alpha;
+        trace[4 * it + 1] = beta;
+        trace[4 * it + 2] = sigmaNew;
+        trace[4 * it + 3] = err;
+    }
+    (void)trueMax;
+    sc->iter = it + 1;
+}
+
+// result = 0; residual = aux = rhs; search = aux after the first K1 (linearsolver.cpp:32-46);
+// sigma = rhs.rhs; zero test of :33-35.
+__global__ void __launch_bounds__(NT) pcgInitKernel(const double *rhs, double *x, double *r0, double *z, double *s0,
+                                                    long long N, double *partials, PcgScalars *sc)
+{
+    __shared__ double red[8];
+    __shared__ int isLast;
+    double acc = 0.0, amax = 0.0;
+    for (long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x; n < N; n += static_cast<long long>(gridDim.x) * NT)
+    {
+        const double v = rhs[n];
+        x[n] = 0.0;
+        r0[n] = v;
+        z[n] = v;
+        s0[n] = 0.0;
+        acc += v * v;
+        amax = fmax(amax, fabs(v));
+    }
+    const int nb = gridDim.x;
+    double bs = blockReduce<false>(acc, red);
+    double bm = blockReduce<true>(amax, red);
+    if (threadIdx.x == 0)
+    {
+        partials[blockIdx.x] = bs;
+        partials[nb + blockIdx.x] = bm;
+        __threadfence();
+        isLast = (atomicAdd(&sc->ticketA, 1u) == static_cast<unsigned int>(nb - 1));
+    }
+    __syncthreads();
+    if (!isLast) return;
+    __threadfence();
+    double total = finalReduce<false>(partials, nb, red);
+    double emax = finalReduce<true>(partials + nb, nb, red);
+    if (threadIdx.x == 0)
+    {
+        sc->sigma = total;
+        sc->alpha = 0.0;
+        sc->beta = 0.0;
+        sc->gamma = 0.0;
+        sc->err = 0.0;
+        sc->iter = 0;
+        sc->result = 0;
+        sc->done = (emax > 1.0e-15) ? 0 : 1;  // VOps::isZero (vmath.cpp:47-58)
+        sc->ticketA = 0;
+        sc->ticketB = 0;
+        sc->ticketC = 0;
+    }
+}
+
+// Pending x += alpha*s of the last executed iteration, and the return value.
+__global__ void __launch_bounds__(NT) pcgFinalizeKernel(double *x, const double *sEven, const double *sOdd, long long N,
+                                                        PcgScalars *sc, int iterLimit)
+{
+    const int iters = sc->iter;
+    if (iters > 0)
+    {
+        const double alpha = sc->alpha;
+        const double *s = (iters & 1) ? sOdd : sEven;
+        for (long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x; n < N;
+             n += static_cast<long long>(gridDim.x) * NT)
+            x[n] = __dadd_rn(x[n], __dmul_rn(s[n], alpha));
+    }
+}
+
+__global__ void pcgResultKernel(PcgScalars *sc, int iterLimit)
+{
+    if (!sc->done) sc->result = iterLimit;
+    sc->done = 1;
+}
+
+PcgArgs baseArgs(Ctx *ctx)
+{
+    PcgArgs a;
+    a.I = ctx->I;
+    a.J = ctx->J;
+    a.N = ctx->N;
+    a.tilesJ = divUp(ctx->J, TC);
+    a.scale = ctx->matrixScale;
+    for (int k = 0; k < 8; k++) a.pre[k] = 1.0 / (static_cast<double>(k) * ctx->matrixScale);
+    a.rowInfo = ctx->rowInfo;
+    a.preInfo = ctx->preInfo;
+    a.in0 = a.in1 = nullptr;
+    a.out0 = a.out1 = a.x = nullptr;
+    a.partials = ctx->partials;
+    a.sc = ctx->scalars;
+    a.trace = ctx->trace;
+    a.traceCapacity = ctx->traceCapacity;
+    a.tol = 0.0;
+    a.compat = ctx->p.convergence_threads > 0 ? 1 : 0;
+    return a;
+}
+}  // namespace
+
+int pcgTileBlocks(const Ctx *ctx) { return divUp(ctx->I, TR) * divUp(ctx->J, TC); }
+
+int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
+{
+    const int blocks = pcgTileBlocks(ctx);
+    const int flat = ctx->smCount * 8;
+    if (blocks > ctx->maxBlocks || flat > ctx->maxBlocks)
+    {
+        ctx->lastError = "pcg: partials buffer too small";
+        return FS2D_ERR_STATE;
+    }
+    PcgArgs a = baseArgs(ctx);
+    a.tol = tol;
+    cudaStream_t st = ctx->stream;
+    const int T = ctx->p.convergence_threads;
+    if (T > 0 && ctx->N < T)
+    {
+        ctx->lastError = "pcg: convergence_threads larger than the cell count";
+        return FS2D_ERR_ARG;
+    }
+
+    pcgInitKernel<<<flat, NT, 0, st>>>(ctx->rhs, ctx->x, ctx->r[0], ctx->z, ctx->s[0], ctx->N, ctx->partials, ctx->scalars);
+    ctx->launches++;
+    for (int i = 0; i < iterLimit; i++)
+    {
+        PcgArgs k1 = a;
+        k1.in0 = ctx->z;
+        k1.in1 = ctx->s[i & 1];
+        k1.out0 = ctx->s[(i + 1) & 1];
+        k1.out1 = ctx->q;
+        k1.x = ctx->x;
+        pcgTileKernel<MODE_K1><<<blocks, NT, 0, st>>>(k1);
+        PcgArgs k2 = a;
+        k2.in0 = ctx->r[i & 1];
+        k2.in1 = ctx->q;
+        k2.out0 = ctx->r[(i + 1) & 1];
+        k2.out1 = ctx->z;
+        pcgTileKernel<MODE_K2><<<blocks, NT, 0, st>>>(k2);
+        ctx->launches += 2;
+        if (T > 0)
+        {
+            pcgRangeErrKernel<<<T, NT, 0, st>>>(ctx->r[(i + 1) & 1], ctx->N, T, ctx->partials + 2 * ctx->maxBlocks,
+                                               ctx->scalars, tol, ctx->trace, ctx->traceCapacity);
+            ctx->launches++;
+        }
+    }
+    pcgFinalizeKernel<<<flat, NT, 0, st>>>(ctx->x, ctx->s[0], ctx->s[1], ctx->N, ctx->scalars, iterLimit);
+    pcgResultKernel<<<1, 1, 0, st>>>(ctx->scalars, iterLimit);
+    ctx->launches += 2;
+    FS2D_CUDA(cudaGetLastError());
+    return FS2D_OK;
+}
+
+int pcgSpmvHost(Ctx *ctx, const double *in, double *out, bool precond)
+{
+    const size_t bytes = static_cast<size_t>(ctx->N) * sizeof(double);
+    FS2D_CUDA(cudaMemcpyAsync(ctx->z, in, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    PcgArgs a = baseArgs(ctx);
+    a.in0 = ctx->z;
+    a.out1 = ctx->q;
+    const int blocks = pcgTileBlocks(ctx);
+    if (precond)
+        pcgTileKernel<MODE_APPLY_M><<<blocks, NT, 0, ctx->stream>>>(a);
+    else
+        pcgTileKernel<MODE_APPLY_A><<<blocks, NT, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    FS2D_CUDA(cudaGetLastError());
+    FS2D_CUDA(cudaMemcpyAsync(out, ctx->q, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FS2D_OK;
+}

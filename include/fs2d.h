@@ -1,0 +1,250 @@
+/* fs2d.h -- C ABI of libfs2d_cuda.so: the B200 (sm_100a) implementation of the per-substep
+ * hot path of ArtNlk/FlipSolver2d.
+ *
+ * The reference has no FFI: its executables link the static C++ library FlipSolver2d and call
+ * methods on FlipSolver directly (AutoBench/CMakeLists.txt:33-35,
+ * AutoBench/benchmarkrunnerapplication.cpp:88-92). This header is the boundary a maintainer
+ * would bind instead: every entry point replaces one `protected` stage method (or one L1
+ * numerics class) of FlipSolver2dLib and is cited below as file:line relative to
+ * /root/reference/FlipSolver2dLib/. The host-side mirror of the reference classes
+ * (flipsolver2d_b200/host/) calls only these functions.
+ *
+ * Conventions
+ *   - all functions return FS2D_OK (0) or a negative error code and never throw;
+ *     fs2d_last_error() gives the text of the last failure on a handle;
+ *   - a handle owns one CUDA device, one stream and all device memory of one solver;
+ *     one host thread per handle (same contract as the reference: flipsolver2d.h:183,
+ *     "not thread-safe, single caller");
+ *   - dense grids are row-major exactly as the reference (linearindexable2d.h:30-37:
+ *     idx = i*sizeJ + j); U is (I+1) x J, V is I x (J+1)
+ *     (staggeredvelocitygrid.cpp:6-14); particle positions/velocities are in cell units;
+ *   - pointers named host_* are host memory (pageable or pinned); nothing in this ABI
+ *     takes a torch type.
+ */
+#ifndef FS2D_H
+#define FS2D_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FS2D_OK 0
+#define FS2D_ERR_CUDA -1
+#define FS2D_ERR_ARG -2
+#define FS2D_ERR_STATE -3
+#define FS2D_ERR_NO_DEVICE -4
+#define FS2D_ERR_COMM -5
+
+typedef struct fs2d_context *fs2d_handle;
+
+/* SimulationMethod (flipsolver2d.h:29) */
+enum fs2d_sim_type { FS2D_SIM_LIQUID = 0, FS2D_SIM_SMOKE = 1, FS2D_SIM_FIRE = 2, FS2D_SIM_NBFLIP = 3 };
+/* ParameterHandlingMethod (flipsolver2d.h:31) */
+enum fs2d_param_handling { FS2D_PARAMS_PARTICLE = 0, FS2D_PARAMS_HYBRID = 1, FS2D_PARAMS_GRID = 2 };
+/* FluidMaterial bit flags (materialgrid.h:6-20) */
+enum fs2d_material { FS2D_FLUID = 0x40, FS2D_SOURCE = 0x41, FS2D_SOLID = 0x20, FS2D_SINK = 0x12, FS2D_EMPTY = 0x10 };
+
+/* Device-resident grids addressable through fs2d_upload_grid / fs2d_download_grid.
+ * [dtype, element count]; N = I*J. */
+enum fs2d_grid
+{
+    FS2D_GRID_U = 0,                  /* f32 (I+1)*J  m_fluidVelocityGrid U      */
+    FS2D_GRID_V = 1,                  /* f32 I*(J+1)  m_fluidVelocityGrid V      */
+    FS2D_GRID_U_VALID = 2,            /* u8  (I+1)*J  uSampleValidityGrid        */
+    FS2D_GRID_V_VALID = 3,            /* u8  I*(J+1)  vSampleValidityGrid        */
+    FS2D_GRID_SAVED_U = 4,            /* f32 (I+1)*J  m_savedFluidVelocityGrid U */
+    FS2D_GRID_SAVED_V = 5,            /* f32 I*(J+1)  m_savedFluidVelocityGrid V */
+    FS2D_GRID_MATERIAL = 6,           /* i8  N        m_materialGrid             */
+    FS2D_GRID_FLUID_SDF = 7,          /* f32 N        m_fluidSdf                 */
+    FS2D_GRID_SOLID_SDF = 8,          /* f32 N        m_solidSdf                 */
+    FS2D_GRID_VISCOSITY = 9,          /* f32 N        m_viscosityGrid            */
+    FS2D_GRID_DENSITY = 10,           /* f32 N        m_densityGrid              */
+    FS2D_GRID_COUNTS = 11,            /* i32 N        m_fluidParticleCounts      */
+    FS2D_GRID_EMITTER_ID = 12,        /* i32 N        m_emitterId                */
+    FS2D_GRID_SOLID_ID = 13,          /* i32 N        m_solidId                  */
+    FS2D_GRID_DIVERGENCE_CONTROL = 14,/* f32 N        m_divergenceControl        */
+    FS2D_GRID_TEST = 15,              /* f32 N        m_testGrid                 */
+    FS2D_GRID_KNOWN_CENTERED = 16,    /* u8  N        m_knownCenteredParams      */
+    FS2D_GRID_TEMPERATURE = 17,       /* f32 N        FlipSmokeSolver::m_temperature        */
+    FS2D_GRID_CONCENTRATION = 18,     /* f32 N        FlipSmokeSolver::m_smokeConcentration */
+    FS2D_GRID_FUEL = 19,              /* f32 N        FlipFireSolver::m_fuel                */
+    FS2D_GRID_PRESSURE = 20,          /* f64 N        last PCG solution (project / density) */
+    FS2D_GRID_RHS = 21,               /* f64 N        last PCG right-hand side             */
+    FS2D_GRID_SOURCE_SDF = 22,        /* f32 N        min polygon sdf of all sources at (i*dx, j*dx)/dx (nbflipsolver.cpp:329-346) */
+    FS2D_GRID_SOURCE_SDF_ID = 23,     /* i32 N        argmin source of the above            */
+    FS2D_GRID_ADVECTED_U = 24,        /* f32 (I+1)*J  NBFlipSolver::m_advectedVelocity U    */
+    FS2D_GRID_ADVECTED_V = 25,        /* f32 I*(J+1)  NBFlipSolver::m_advectedVelocity V    */
+    FS2D_GRID_ADVECTED_SDF = 26,      /* f32 N        NBFlipSolver::m_advectedSdf           */
+    FS2D_GRID_ADVECTED_VISCOSITY = 27,/* f32 N        NBFlipSolver::m_advectedViscosity     */
+    FS2D_GRID_COUNT_
+};
+
+/* FlipSolverParameters (flipsolver2d.h:33-56) + Smoke/Fire parameters
+ * (flipsmokesolver.h:9-16, flipfiresolver.h:6-13) + the knobs that only exist here. */
+typedef struct fs2d_params
+{
+    int32_t size_i;               /* gridSizeI */
+    int32_t size_j;               /* gridSizeJ */
+    int32_t num_properties;       /* float property columns per particle (markerparticlesystem.h:120-126) */
+    int32_t particles_per_cell;
+    int32_t pcg_iter_limit;
+    int32_t sim_type;             /* enum fs2d_sim_type */
+    int32_t parameter_handling;   /* enum fs2d_param_handling */
+    int32_t viscosity_enabled;
+    /* Convergence test of LinearSolver::solve. The reference's VOps::maxAbs returns, per
+     * ThreadPool range, |r| of the LAST non-zero element (vmath.cpp:100-136), so its result
+     * depends on the thread count T. convergence_threads = T > 0 reproduces that test for a
+     * pool of T threads (splitRange, threadpool.cpp:41-76); 0 selects the true max-norm. */
+    int32_t convergence_threads;
+    int32_t device;               /* CUDA device ordinal */
+    int32_t viscosity_property;   /* property column indices, -1 when the solver has none */
+    int32_t temperature_property;
+    int32_t concentration_property;
+    int32_t fuel_property;
+    int32_t test_property;
+    int32_t reserved0;
+    double dx;
+    double fluid_density;
+    double project_tolerance;     /* m_projectTolerance (flipsolver2d.cpp:73) */
+    float gravity_x;              /* m_globalAcceleration */
+    float gravity_y;
+    float pic_ratio;
+    float particle_scale;
+    float ambient_temperature;    /* smoke */
+    float temperature_decay;
+    float concentration_decay;
+    float buoyancy_factor;
+    float soot_factor;
+    float ignition_temperature;   /* fire */
+    float burn_rate;
+    float smoke_proportion;
+    float heat_proportion;
+    float divergence_proportion;
+} fs2d_params;
+
+/* Emitter (emitter.h:6-47) fields the substep reads. */
+typedef struct fs2d_source
+{
+    float viscosity;
+    float temperature;
+    float concentration;
+    float fuel;
+    float divergence;
+    float velocity_x;
+    float velocity_y;
+    int32_t transfer_velocity;
+} fs2d_source;
+
+/* ---------------------------------------------------------------- lifetime */
+int fs2d_device_count(void);
+int fs2d_create(const fs2d_params *params, fs2d_handle *out);
+int fs2d_destroy(fs2d_handle h);
+const char *fs2d_last_error(fs2d_handle h);
+/* Blocks until all work queued on the handle's stream is done. */
+int fs2d_synchronize(fs2d_handle h);
+/* The handle's cudaStream_t (as void*) so callers can record events on it. */
+void *fs2d_stream(fs2d_handle h);
+/* Kernels launched on this handle since creation (bench.py's gpu_launches). */
+int64_t fs2d_launch_count(fs2d_handle h);
+
+/* ---------------------------------------------------------------- state transfer */
+int64_t fs2d_grid_elements(fs2d_handle h, int grid);
+int fs2d_grid_element_size(int grid);
+int fs2d_upload_grid(fs2d_handle h, int grid, const void *host_data, size_t bytes);
+int fs2d_download_grid(fs2d_handle h, int grid, void *host_data, size_t bytes);
+/* Device address of a grid (for callers that keep their own device buffers). */
+void *fs2d_grid_device_ptr(fs2d_handle h, int grid);
+
+/* Obstacle::friction() per solid id (obstacle.h:11) and the Emitter table. */
+int fs2d_set_obstacles(fs2d_handle h, int count, const float *host_friction);
+int fs2d_set_sources(fs2d_handle h, int count, const fs2d_source *host_sources);
+
+/* Replace / read back the marker particles (MarkerParticleSystem, markerparticlesystem.h:187-249).
+ * pos/vel: 2 floats per particle; props: property-major [num_properties][count].
+ * Download order is the device order: sorted by cell, stable inside a cell. */
+int64_t fs2d_particle_count(fs2d_handle h);
+int fs2d_upload_particles(fs2d_handle h, int64_t count, const float *host_pos, const float *host_vel,
+                          const float *host_props);
+int fs2d_download_particles(fs2d_handle h, float *host_pos, float *host_vel, float *host_props);
+/* Append particles (seedInitialFluid / reseedParticles callers, flipsolver2d.cpp:627-707). */
+int fs2d_append_particles(fs2d_handle h, int64_t count, const float *host_pos, const float *host_vel,
+                          const float *host_props);
+
+/* ---------------------------------------------------------------- PCG (kernel group 4) */
+/* LinearSolver::solve (linearsolver.cpp:25-73) on the system built by fs2d_build_matrix,
+ * with host vectors: rhs in, x out (N doubles each). *iters receives the reference's
+ * return value (0-based index of the converging iteration, or iter_limit). */
+int fs2d_pcg_solve(fs2d_handle h, const double *host_rhs, double *host_x, int iter_limit, double tol,
+                   int *iters);
+/* Same solve on device-resident vectors (FS2D_GRID_RHS -> FS2D_GRID_PRESSURE), no copies,
+ * no host synchronisation; the iteration count is fetched with fs2d_pcg_last_iterations. */
+int fs2d_pcg_solve_device(fs2d_handle h, int iter_limit, double tol);
+int fs2d_pcg_last_iterations(fs2d_handle h, int *iters);
+/* Trace of the last solve: per executed iteration alpha, beta, sigma, err (4 doubles). */
+int fs2d_pcg_trace(fs2d_handle h, double *host_trace, int max_iterations, int *written);
+/* IndexedPressureParameters::multiply (pressuredata.h:184-238) and
+ * IndexedIPPCoefficients::multiply (PressureIPPCoeficients.h:79-132) alone, host vectors. */
+int fs2d_spmv(fs2d_handle h, const double *host_in, double *host_out);
+int fs2d_precond_apply(fs2d_handle h, const double *host_in, double *host_out);
+/* Per-cell matrix export: is_unit/mask/count (1 byte each) and the four neighbour
+ * non-solid counts used by the preconditioner (iNeg, iPos, jNeg, jPos; 1 byte each plane). */
+int fs2d_download_matrix(fs2d_handle h, uint8_t *host_is_unit, uint8_t *host_mask, uint8_t *host_count,
+                         uint8_t *host_precond_counts);
+
+/* ---------------------------------------------------------------- substep stages */
+int fs2d_set_step_dt(fs2d_handle h, float dt);                 /* m_stepDt */
+/* maxParticleVelocity (flipsolver2d.cpp:1560-1574) */
+int fs2d_max_particle_velocity(fs2d_handle h, float *out);
+/* advect + advectThread (flipsolver2d.cpp:138-162,305-338): RK4, solid push-out, death flags;
+ * in GRID parameter mode also eulerAdvectParameters (flipsmokesolver.cpp:211-233). */
+int fs2d_advect(fs2d_handle h);
+/* getPressureProjectionMatrix + getIPPCoefficients (flipsolver2d.cpp:797-945;
+ * smoke: flipsmokesolver.cpp:354-507) */
+int fs2d_build_matrix(fs2d_handle h);
+/* pruneParticles + rebinParticles (flipsolver2d.cpp:353-359, markerparticlesystem.cpp:47-58):
+ * drop dead particles and counting-sort the rest by cell. */
+int fs2d_sort_particles(fs2d_handle h);
+/* densityCorrection (flipsolver2d.cpp:164-303). *iters = PCG iterations. */
+int fs2d_density_correction(fs2d_handle h, int *iters);
+int fs2d_update_density_grid(fs2d_handle h);                   /* updateDensityGrid :188-249 */
+int fs2d_density_rhs(fs2d_handle h);                           /* calcDensityCorrectionRhs :993-1011 -> FS2D_GRID_RHS */
+/* particleToGrid (flipsolver2d.cpp:1213-1220,1313-1431; smoke/nbflip centred params) */
+int fs2d_particle_to_grid(fs2d_handle h);
+int fs2d_update_sdf(fs2d_handle h);                            /* updateSdf :1243-1311 */
+int fs2d_update_materials(fs2d_handle h);                      /* updateMaterials :1053-1075 */
+int fs2d_after_transfer(fs2d_handle h);                        /* afterTransfer :390-410 (+smoke/fire/nbflip overrides) */
+int fs2d_extrapolate_velocity(fs2d_handle h, int radius);      /* StaggeredVelocityGrid::extrapolate, mathfuncs.cpp:152-215 */
+int fs2d_extrapolate_sdf_inside(fs2d_handle h);                /* extrapolateLevelsetInside :1433-1494 */
+int fs2d_extrapolate_sdf_outside(fs2d_handle h);               /* extrapolateLevelsetOutside :1496-1558 */
+int fs2d_save_velocity(fs2d_handle h);                         /* m_savedFluidVelocityGrid = m_fluidVelocityGrid :439 */
+int fs2d_apply_body_forces(fs2d_handle h);                     /* applyBodyForces :1222-1241; smoke :23-52 */
+int fs2d_pressure_rhs(fs2d_handle h);                          /* calcPressureRhs :962-991 -> FS2D_GRID_RHS */
+int fs2d_apply_pressure(fs2d_handle h);                        /* applyPressuresToVelocityField :1106-1193 <- FS2D_GRID_PRESSURE */
+int fs2d_project(fs2d_handle h, int *iters);                   /* project :93-126 */
+int fs2d_velocity_from_solids(fs2d_handle h);                  /* updateVelocityFromSolids :1077-1104 */
+int fs2d_apply_viscosity(fs2d_handle h, int *iters);           /* LightViscosityModel::apply, viscositymodel.cpp:4-162 */
+int fs2d_particle_update(fs2d_handle h);                       /* particleUpdate :361-388 (+smoke decay, fire combustion) */
+int fs2d_count_particles(fs2d_handle h);                       /* countParticles :1021-1051 */
+/* reseedParticles (flipsolver2d.cpp:627-680; nbflip nbflipsolver.cpp:118-201): the RNG stream
+ * (std::mt19937 + uniform_real_distribution<float>, flipsolver2d.cpp:1013-1019) stays on the
+ * host. fs2d_reseed_plan reports how many candidate particles will be drawn (two floats
+ * each, x then y, cells in row-major order); fs2d_reseed_apply consumes exactly that many. */
+int fs2d_reseed_plan(fs2d_handle h, int64_t *candidates);
+int fs2d_reseed_apply(fs2d_handle h, int64_t candidates, const float *host_uniform_xy);
+/* NBFlipSolver::pruneNarrowBand + semi-Lagrangian advection of U, V, sdf, viscosity
+ * (nbflipsolver.cpp:66-109,227-253) */
+int fs2d_nbflip_advect_grids(fs2d_handle h);
+
+/* One whole FlipSolver::step() (flipsolver2d.cpp:412-462) or NBFlipSolver::step()
+ * (nbflipsolver.cpp:26-64) for scenes without sources (no host RNG needed):
+ * stage_ms[12] receives the SolverStage timings (flipsolver2d.h:58-72) measured with
+ * CUDA events, iters[3] = pressure, density, viscosity iteration counts. Either may be NULL. */
+int fs2d_substep(fs2d_handle h, float dt, float *stage_ms, int *iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FS2D_H */

@@ -1,0 +1,89 @@
+"""Kernel group 4 parity: CUDA PCG (through the C ABI) vs the reference's own LinearSolver,
+IndexedPressureParameters and IndexedIPPCoefficients compiled into oracle/_ref (strict build)."""
+import numpy as np
+import pytest
+
+from conftest import ORACLE_THREADS
+from flipsolver2d_b200 import capi, scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_system(ref_mod, scene_dir, res, sim="flip", frames=0, dt=1.0 / 90.0):
+    """Reference solver advanced to the point where step() builds the matrix."""
+    path = scenes.write_scene(scenes.dam_break(res, sim), str(scene_dir / ("db%d_%s.json" % (res, sim))))
+    s = ref_mod.RefSolver(path, strict=True)
+    for _ in range(frames):
+        s.step_frame()
+    if frames == 0:
+        s.stage("FIRST_FRAME_INIT")
+    s.set_step_dt(dt)
+    s.stage("BUILD_MATRIX")
+    return s
+
+
+def _device_for(s, conv_threads=0, iter_limit=200):
+    p = s.params()
+    d = capi.Device(s.I, s.J, dx=p["dx"], fluid_density=p["fluidDensity"], pcg_iter_limit=iter_limit,
+                    convergence_threads=conv_threads, project_tolerance=p["projectTolerance"])
+    d.upload("MATERIAL", s.grid("MATERIAL"))
+    d.set_step_dt(p["stepDt"])
+    d.stage("build_matrix")
+    return d
+
+
+@pytest.mark.parametrize("res,frames", [(64, 0), (128, 2), (100, 1)])
+def test_matrix_rows_bit_exact(ref_mod, scene_dir, res, frames):
+    s = _ref_system(ref_mod, scene_dir, res, frames=frames)
+    d = _device_for(s)
+    rm, dm = s.matrix(), d.matrix()
+    assert np.array_equal(rm["is_unit"], dm["is_unit"])
+    assert np.array_equal(rm["mask"], dm["mask"])
+    assert np.array_equal(rm["count"], dm["count"])
+    unit = rm["is_unit"].astype(bool)
+    scale = rm["scale"]
+    with np.errstate(divide="ignore"):
+        coef = 1.0 / (dm["precond_counts"].astype(np.float64) * scale)
+    for k in range(4):
+        assert np.array_equal(coef[k][unit], rm["coef"][k][unit])
+
+
+@pytest.mark.parametrize("res,frames", [(64, 0), (128, 2), (100, 1)])
+def test_operators_bit_exact(ref_mod, scene_dir, res, frames):
+    s = _ref_system(ref_mod, scene_dir, res, frames=frames)
+    d = _device_for(s)
+    rng = np.random.default_rng(res)
+    v = rng.standard_normal(s.N)
+    assert np.array_equal(d.spmv(v), s.spmv(v))
+    assert np.array_equal(d.precond(v), s.precond(v))
+
+
+@pytest.mark.parametrize("res,frames,iters", [(64, 0, 10), (128, 2, 25), (256, 1, 40)])
+def test_fixed_iteration_solve(ref_mod, scene_dir, res, frames, iters):
+    """tol = 0 forces exactly `iters` iterations on both sides; compare the iterate."""
+    s = _ref_system(ref_mod, scene_dir, res, frames=frames)
+    d = _device_for(s)
+    rng = np.random.default_rng(7)
+    unit = s.matrix()["is_unit"].astype(bool)
+    rhs = np.where(unit, rng.standard_normal(s.N), 0.0)
+    xr, itr = s.pcg(rhs, iters, 0.0)
+    xd, itd = d.pcg_solve(rhs, iters, 0.0)
+    assert itr == itd == iters
+    rel = np.linalg.norm(xd - xr) / np.linalg.norm(xr)
+    # tolerance: 1e-9 relative L2 on the iterate (order of the dot-product sums differs)
+    assert rel < 1e-9, rel
+
+
+def test_zero_rhs_and_iteration_count_compat(ref_mod, scene_dir):
+    s = _ref_system(ref_mod, scene_dir, 256, frames=1, dt=1.0 / 30.0)  # scale 1.75: SPD regime
+    assert s.threads == ORACLE_THREADS
+    d = _device_for(s, conv_threads=ORACLE_THREADS, iter_limit=400)
+    x, it = d.pcg_solve(np.zeros(s.N), 50, 1e-6)
+    assert it == 0 and not x.any()
+    rhs = s.pressure_rhs()
+    xr, itr = s.pcg(rhs, 400, 1e-2)
+    xd, itd = d.pcg_solve(rhs, 400, 1e-2)
+    assert itr < 400, "expected a converging case"
+    assert itd == itr
+    rel = np.linalg.norm(xd - xr) / np.linalg.norm(xr)
+    assert rel < 1e-7, rel
