@@ -310,14 +310,29 @@ int fs2d_set_sources(fs2d_handle ctx, int count, const fs2d_source *host_sources
 }
 
 // ---------------------------------------------------------------- particles
-int64_t fs2d_particle_count(fs2d_handle h) { return h ? h->count : 0; }
+int64_t fs2d_particle_count(fs2d_handle h)
+{
+    if (!h) return 0;
+    int64_t n = 0;
+    if (particlesAliveCount(h, &n) != FS2D_OK) return -1;
+    return n;
+}
 
 int fs2d_upload_particles(fs2d_handle ctx, int64_t count, const float *host_pos, const float *host_vel,
                           const float *host_props)
 {
     if (!ctx || count < 0) return FS2D_ERR_ARG;
+    FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
+    FS2D_CUDA(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), ctx->stream));
     ctx->count = 0;
+    ctx->deadCount = 0;
+    ctx->killedDirty = false;
     ctx->sorted = false;
+    if (count == 0)
+    {
+        FS2D_CUDA(cudaMemsetAsync(ctx->cellStart, 0, sizeof(int32_t) * (ctx->N + 1), ctx->stream));
+        ctx->sorted = true;
+    }
     return fs2d_append_particles(ctx, count, host_pos, host_vel, host_props);
 }
 
@@ -353,6 +368,11 @@ int fs2d_append_particles(fs2d_handle ctx, int64_t count, const float *host_pos,
 int fs2d_download_particles(fs2d_handle ctx, float *host_pos, float *host_vel, float *host_props)
 {
     if (!ctx) return FS2D_ERR_ARG;
+    // dead-flagged particles (cap, sinks, narrow band) are dropped by the sort; do it now so the
+    // caller sees exactly fs2d_particle_count() records in device order
+    int64_t alive = 0;
+    FS2D_TRY(particlesAliveCount(ctx, &alive));
+    if (alive != ctx->count || !ctx->sorted) FS2D_TRY(particlesSort(ctx));
     const int64_t n = ctx->count;
     if (n == 0) return FS2D_OK;
     ParticleBuffers &b = ctx->pb[ctx->cur];
@@ -474,6 +494,10 @@ int fs2d_density_correction(fs2d_handle h, int *iters)
     if (iters) *iters = it;
     if (it >= h->p.pcg_iter_limit) return FS2D_OK;  // "Density solver solving failed!": result discarded (:179-182)
     FS2D_TRY(particlesAdjustByDensity(h));
+    // The reference leaves adjusted particles in their old bins ("adjusted not enough to require
+    // rebinning", flipsolver2d.cpp:427); the cell-sorted layout is re-keyed instead so that the
+    // gathers that follow see every particle in the cell its position says.
+    FS2D_TRY(particlesSort(h));
     return FS2D_OK;
 }
 
@@ -522,6 +546,12 @@ int fs2d_nbflip_advect_grids(fs2d_handle h)
     if (!h) return FS2D_ERR_ARG;
     FS2D_TRY(particlesPruneNarrowBand(h));
     return gridNbflipAdvect(h);
+}
+
+int fs2d_substep(fs2d_handle h, float dt, float *stage_ms, int *iters)
+{
+    if (!h) return FS2D_ERR_ARG;
+    return stepSubstep(h, dt, stage_ms, iters);
 }
 
 }  // extern "C"

@@ -126,6 +126,9 @@ struct fs2d_context
     int32_t *cellCursor = nullptr;    // N
     int32_t *scanBlock = nullptr;     // scan scratch
     bool sorted = false;
+    int64_t deadCount = 0;            // particles flagged dead since the last sort (host view)
+    bool killedDirty = false;         // d_counter[0] holds kills not yet folded into deadCount
+    bool smokeGridsAdvected = false;  // temperature/concentration/fuel replaced by advected grids (App. A-13)
     int64_t *d_counter = nullptr;     // device scalar scratch (8 int64)
     float *d_fscratch = nullptr;      // device float scratch
 
@@ -163,6 +166,7 @@ int particlesAdjustByDensity(Ctx *ctx);
 int particlesReseedPlan(Ctx *ctx, int64_t *candidates);
 int particlesReseedApply(Ctx *ctx, int64_t candidates, const float *hostUniform);
 int particlesPruneNarrowBand(Ctx *ctx);
+int particlesAliveCount(Ctx *ctx, int64_t *out);
 // transfer.cu
 int transferVelocity(Ctx *ctx);
 int transferCentered(Ctx *ctx);
@@ -183,5 +187,7 @@ int gridVelocityFromSolids(Ctx *ctx);
 int gridEulerAdvectParameters(Ctx *ctx);
 int gridNbflipAdvect(Ctx *ctx);
 int gridViscosity(Ctx *ctx, int *iters);
+// step.cu
+int stepSubstep(Ctx *ctx, float dt, float *stageMs, int *iters);
 
 #endif

@@ -2,8 +2,13 @@
 // (matrix rows, right-hand sides, pressure application) and group 5 (semi-Lagrangian
 // advection). All are one-thread-per-sample streaming kernels over the dense row-major
 // grids; each sample is read/written once, neighbours come from L1/L2.
+#include <algorithm>
+#include <cooperative_groups.h>
+
 #include "fs2d_internal.h"
 #include "fs2d_device.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace
 {
@@ -53,6 +58,411 @@ __global__ void __launch_bounds__(NT) buildMatrixKernel(const int8_t *__restrict
     }
     preInfo[n] = static_cast<uint16_t>(pre);
 }
+
+// ------------------------------------------------------------------ materials / sources
+// updateMaterials (flipsolver2d.cpp:1053-1075)
+__global__ void __launch_bounds__(NT) updateMaterialsKernel(const float *__restrict__ sdf, int8_t *__restrict__ mat, long long N)
+{
+    const long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    if (n >= N) return;
+    const int8_t m = mat[n];
+    if (sdf[n] < 0.f)
+    {
+        if (matEmpty(m)) mat[n] = FS2D_FLUID;
+    }
+    else if (matStrictFluid(m))
+    {
+        mat[n] = FS2D_EMPTY;
+    }
+}
+
+// afterTransfer: FlipSolver (flipsolver2d.cpp:390-410), smoke (flipsmokesolver.cpp:132-148), fire
+// (flipfiresolver.cpp:18-33). U(i,j)/V(i,j) of a SOURCE cell only belong to that cell, so this is race free.
+__global__ void __launch_bounds__(NT) afterTransferKernel(const int8_t *__restrict__ mat, const int32_t *__restrict__ emitterId,
+                                                          const fs2d_source *__restrict__ sources, int I, int J, double dx,
+                                                          float *__restrict__ viscosity, float *__restrict__ U,
+                                                          float *__restrict__ V, uint8_t *__restrict__ uValid,
+                                                          uint8_t *__restrict__ vValid, float *__restrict__ temperature,
+                                                          float *__restrict__ concentration, float *__restrict__ fuel)
+{
+    const long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    if (n >= static_cast<long long>(I) * J || !matSource(mat[n])) return;
+    const int i = static_cast<int>(n / J), j = static_cast<int>(n - static_cast<long long>(i) * J);
+    const fs2d_source s = sources[emitterId[n]];
+    viscosity[n] = s.viscosity;
+    if (s.transfer_velocity)
+    {
+        U[n] = static_cast<float>(static_cast<double>(s.velocity_x) / dx);
+        V[static_cast<long long>(i) * (J + 1) + j] = static_cast<float>(static_cast<double>(s.velocity_y) / dx);
+        uValid[n] = 1;
+        vValid[static_cast<long long>(i) * (J + 1) + j] = 1;
+    }
+    if (concentration) concentration[n] = s.concentration;
+    if (temperature) temperature[n] = s.temperature;
+    if (fuel) fuel[n] = s.fuel;
+}
+
+// ------------------------------------------------------------------ BFS extrapolation
+// simmath::breadthFirstExtrapolate (mathfuncs.cpp:152-215) as layer-synchronous sweeps: layer k
+// (8-neighbour BFS distance from the valid samples) averages, in a double, the neighbours of
+// smaller layer in the reference's neighbour order (linearindexable2d.h:69-78). Those are final
+// before layer k starts, so one in-place sweep per layer reproduces the queue order exactly.
+__global__ void __launch_bounds__(NT) bfsInitKernel(const uint8_t *__restrict__ uValid, const uint8_t *__restrict__ vValid,
+                                                    long long NU, long long NV, uint8_t *__restrict__ marker)
+{
+    const long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    if (n < NU)
+        marker[n] = uValid[n] ? 0 : 255;
+    else if (n < NU + NV)
+        marker[n] = vValid[n - NU] ? 0 : 255;
+}
+
+__device__ __forceinline__ void bfsLayerSample(float *__restrict__ g, uint8_t *__restrict__ valid, uint8_t *__restrict__ marker,
+                                               int sI, int sJ, long long n, int k)
+{
+    if (marker[n] != 255) return;
+    const int i = static_cast<int>(n / sJ), j = static_cast<int>(n - static_cast<long long>(i) * sJ);
+    bool hit = false;
+    double avg = 0.0;
+    int cnt = 0;
+#pragma unroll
+    for (int di = -1; di <= 1; di++)
+#pragma unroll
+        for (int dj = -1; dj <= 1; dj++)
+        {
+            if (di == 0 && dj == 0) continue;
+            const int ni = i + di, nj = j + dj;
+            if (ni < 0 || ni >= sI || nj < 0 || nj >= sJ) continue;
+            const long long nn = static_cast<long long>(ni) * sJ + nj;
+            const int m = marker[nn];
+            if (m == k - 1) hit = true;
+            if (m < k)
+            {
+                avg += static_cast<double>(g[nn]);
+                cnt++;
+            }
+        }
+    if (!hit) return;
+    g[n] = static_cast<float>(avg / cnt);
+    valid[n] = 1;
+    marker[n] = static_cast<uint8_t>(k);
+}
+
+__global__ void __launch_bounds__(NT) bfsLayerKernel(float *U, float *V, uint8_t *uValid, uint8_t *vValid, uint8_t *marker, int I,
+                                                     int J, int k)
+{
+    const long long NU = static_cast<long long>(I + 1) * J, NV = static_cast<long long>(I) * (J + 1);
+    const long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    if (n < NU)
+        bfsLayerSample(U, uValid, marker, I + 1, J, n, k);
+    else if (n < NU + NV)
+        bfsLayerSample(V, vValid, marker + NU, I, J + 1, n - NU, k);
+}
+
+// extrapolateLevelsetInside / Outside (flipsolver2d.cpp:1433-1558): same BFS with unbounded radius and
+// -1 / +1 per layer. One cooperative launch walks all layers; only the bounding box of the unmarked
+// cells is swept. bbox = {iMin, iMax, jMin, jMax}, flags[3] rotate so that a flag is never reset while
+// another CTA may still read it.
+__global__ void __launch_bounds__(NT) sdfMarkKernel(const float *__restrict__ sdf, int32_t *__restrict__ marker, int I, int J,
+                                                    int inside, float maxSdf, int *__restrict__ bbox)
+{
+    const long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    if (n >= static_cast<long long>(I) * J) return;
+    const float v = sdf[n];
+    const bool known = inside ? (v > 0.f) : (v < maxSdf);
+    marker[n] = known ? 0 : 0x7fffffff;
+    if (!known)
+    {
+        const int i = static_cast<int>(n / J), j = static_cast<int>(n - static_cast<long long>(i) * J);
+        atomicMin(bbox + 0, i);
+        atomicMax(bbox + 1, i);
+        atomicMin(bbox + 2, j);
+        atomicMax(bbox + 3, j);
+    }
+}
+
+__global__ void __launch_bounds__(NT) sdfExtrapolateKernel(float *sdf, int32_t *marker, int I, int J, float step,
+                                                           const int *__restrict__ bbox, int *flags)
+{
+    cg::grid_group grid = cg::this_grid();
+    const int i0 = bbox[0], i1 = bbox[1], j0 = bbox[2], j1 = bbox[3];
+    if (i1 < i0) return;  // nothing unmarked (uniform across the grid)
+    const long long w = j1 - j0 + 1, cells = w * (i1 - i0 + 1);
+    const long long stride = static_cast<long long>(gridDim.x) * NT;
+    for (int k = 1;; k++)
+    {
+        bool changed = false;
+        for (long long t = blockIdx.x * static_cast<long long>(NT) + threadIdx.x; t < cells; t += stride)
+        {
+            const int i = i0 + static_cast<int>(t / w), j = j0 + static_cast<int>(t % w);
+            const long long n = static_cast<long long>(i) * J + j;
+            if (marker[n] != 0x7fffffff) continue;
+            bool hit = false;
+            double avg = 0.0;
+            int cnt = 0;
+#pragma unroll
+            for (int di = -1; di <= 1; di++)
+#pragma unroll
+                for (int dj = -1; dj <= 1; dj++)
+                {
+                    if (di == 0 && dj == 0) continue;
+                    const int ni = i + di, nj = j + dj;
+                    if (ni < 0 || ni >= I || nj < 0 || nj >= J) continue;
+                    const long long nn = static_cast<long long>(ni) * J + nj;
+                    const int m = marker[nn];
+                    if (m == k - 1) hit = true;
+                    if (m < k)
+                    {
+                        avg += static_cast<double>(sdf[nn]);
+                        cnt++;
+                    }
+                }
+            if (!hit) continue;
+            sdf[n] = static_cast<float>(avg / cnt + static_cast<double>(step));
+            marker[n] = k;
+            changed = true;
+        }
+        if (changed) flags[k % 3] = 1;
+        if (blockIdx.x == 0 && threadIdx.x == 0) flags[(k + 1) % 3] = 0;
+        __threadfence();
+        grid.sync();
+        if (*reinterpret_cast<volatile int *>(flags + k % 3) == 0) break;
+    }
+}
+
+// ------------------------------------------------------------------ body forces
+// applyBodyForces (flipsolver2d.cpp:1222-1241): every U and V sample gets factor * g
+__global__ void __launch_bounds__(NT) bodyForceKernel(float *__restrict__ U, float *__restrict__ V, long long NU, long long NV,
+                                                      float addU, float addV)
+{
+    const long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    if (n < NU)
+        U[n] = faddr(U[n], addU);
+    else if (n < NU + NV)
+        V[n - NU] = faddr(V[n - NU], addV);
+}
+
+// FlipSmokeSolver::applyBodyForces (flipsmokesolver.cpp:23-52)
+__global__ void __launch_bounds__(NT) smokeBodyForceKernel(float *__restrict__ U, float *__restrict__ V, int I, int J,
+                                                           GridView temperature, GridView concentration, float sootWeight,
+                                                           float buoyancyInfluence, float ambient, float gx, float gy, float factor)
+{
+    const long long NU = static_cast<long long>(I + 1) * J, NV = static_cast<long long>(I) * (J + 1);
+    const long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    if (n < NU)
+    {
+        const int i = static_cast<int>(n / J), j = static_cast<int>(n - static_cast<long long>(i) * J);
+        const float x = static_cast<float>(i), y = faddr(static_cast<float>(j), 0.5f);
+        const float td = fsubr(gridLerp(temperature, x, y), ambient);
+        const float c = gridLerp(concentration, x, y);
+        const float a = fmulr(fmulr(fsubr(fmulr(sootWeight, c), fmulr(buoyancyInfluence, td)), gx), factor);
+        U[n] = faddr(U[n], a);
+    }
+    else if (n < NU + NV)
+    {
+        const long long m = n - NU;
+        const int i = static_cast<int>(m / (J + 1)), j = static_cast<int>(m - static_cast<long long>(i) * (J + 1));
+        const float x = faddr(static_cast<float>(i), 0.5f), y = static_cast<float>(j);
+        const float td = fsubr(gridLerp(temperature, x, y), ambient);
+        const float c = gridLerp(concentration, x, y);
+        const float a = fmulr(fmulr(fsubr(fmulr(sootWeight, c), fmulr(buoyancyInfluence, td)), gy), factor);
+        V[m] = faddr(V[m], a);
+    }
+}
+
+// ------------------------------------------------------------------ right-hand sides
+// calcPressureRhs (flipsolver2d.cpp:962-991; smoke: flipsmokesolver.cpp:73-102) with divergenceAt (:759-764)
+__global__ void __launch_bounds__(NT) pressureRhsKernel(const float *__restrict__ U, const float *__restrict__ V,
+                                                        const float *__restrict__ divCtl, const int8_t *__restrict__ mat, int I,
+                                                        int J, int smokeRows, double scale, double *__restrict__ rhs)
+{
+    const long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    if (n >= static_cast<long long>(I) * J) return;
+    const int i = static_cast<int>(n / J), j = static_cast<int>(n - static_cast<long long>(i) * J);
+    const int8_t m = mat[n];
+    const bool row = smokeRows ? !matSolid(m) : matFluid(m);
+    if (!row)
+    {
+        rhs[n] = 0.0;
+        return;
+    }
+    const float u0 = U[n], u1 = U[n + J];
+    const long long vn = static_cast<long long>(i) * (J + 1) + j;
+    const float v0 = V[vn], v1 = V[vn + 1];
+    const float div = faddr(fsubr(faddr(fsubr(u1, u0), v1), v0), divCtl[n]);
+    double val = __dmul_rn(-scale, static_cast<double>(div));
+    const double sIm = matSolid(matAt(mat, I, J, i - 1, j)) ? 1.0 : 0.0;
+    const double sIp = matSolid(matAt(mat, I, J, i + 1, j)) ? 1.0 : 0.0;
+    const double sJm = matSolid(matAt(mat, I, J, i, j - 1)) ? 1.0 : 0.0;
+    const double sJp = matSolid(matAt(mat, I, J, i, j + 1)) ? 1.0 : 0.0;
+    val = __dsub_rn(val, __dmul_rn(__dmul_rn(sIm, scale), static_cast<double>(u0)));
+    val = __dadd_rn(val, __dmul_rn(__dmul_rn(sIp, scale), static_cast<double>(u1)));
+    val = __dsub_rn(val, __dmul_rn(__dmul_rn(sJm, scale), static_cast<double>(v0)));
+    val = __dadd_rn(val, __dmul_rn(__dmul_rn(sJp, scale), static_cast<double>(v1)));
+    rhs[n] = val;
+}
+
+// calcDensityCorrectionRhs (flipsolver2d.cpp:993-1011)
+__global__ void __launch_bounds__(NT) densityRhsKernel(const float *__restrict__ density, const int8_t *__restrict__ mat,
+                                                       long long N, double scale, double restDensity, double *__restrict__ rhs)
+{
+    const long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    if (n >= N) return;
+    if (!matFluid(mat[n]))
+    {
+        rhs[n] = 0.0;
+        return;
+    }
+    double r = __ddiv_rn(static_cast<double>(density[n]), restDensity);
+    r = r < 0.5 ? 0.5 : (r > 1.5 ? 1.5 : r);
+    rhs[n] = __dmul_rn(scale, __dsub_rn(1.0, r));
+}
+
+// applyPressureThreadU/V (flipsolver2d.cpp:1133-1193; smoke: flipsmokesolver.cpp:262-322)
+__global__ void __launch_bounds__(NT) applyPressureKernel(const double *__restrict__ p, const int8_t *__restrict__ mat, int I,
+                                                          int J, int smokeRows, double scale, float *__restrict__ U,
+                                                          float *__restrict__ V, uint8_t *__restrict__ uValid,
+                                                          uint8_t *__restrict__ vValid, float *__restrict__ testGrid)
+{
+    const long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    if (n >= static_cast<long long>(I) * J) return;
+    const int i = static_cast<int>(n / J), j = static_cast<int>(n - static_cast<long long>(i) * J);
+    const double pc = p[n];
+    const int8_t mc = mat[n];
+    {
+        const int8_t mn = matAt(mat, I, J, i - 1, j);
+        const double pn = i > 0 ? p[n - J] : 0.0;
+        const bool active = smokeRows ? (!matSolid(mn) || !matSolid(mc)) : (matFluid(mn) || matFluid(mc));
+        if (active)
+        {
+            if (matSolid(mn) || matSolid(mc))
+                U[n] = 0.f;
+            else
+                U[n] = static_cast<float>(__dsub_rn(static_cast<double>(U[n]), __dmul_rn(scale, __dsub_rn(pc, pn))));
+        }
+        else
+        {
+            uValid[n] = 0;
+        }
+    }
+    {
+        const long long vn = static_cast<long long>(i) * (J + 1) + j;
+        const int8_t mn = matAt(mat, I, J, i, j - 1);
+        const double pn = j > 0 ? p[n - 1] : 0.0;
+        const bool active = smokeRows ? (!matSolid(mn) || !matSolid(mc)) : (matFluid(mn) || matFluid(mc));
+        if (active)
+        {
+            if (matSolid(mn) || matSolid(mc))
+                V[vn] = 0.f;
+            else
+                V[vn] = static_cast<float>(__dsub_rn(static_cast<double>(V[vn]), __dmul_rn(scale, __dsub_rn(pc, pn))));
+        }
+        else
+        {
+            vValid[vn] = 0;
+        }
+    }
+    if (testGrid) testGrid[n] = static_cast<float>(pc / 100.0);  // flipsmokesolver.cpp:247-250
+}
+
+// updateVelocityFromSolids (flipsolver2d.cpp:1077-1104) with validSolidNeighborIds (:766-786) and
+// u/vSampleAffectedBySolid (materialgrid.cpp:152-164)
+__global__ void __launch_bounds__(NT) solidFrictionKernel(const int32_t *__restrict__ solidId, const float *__restrict__ friction,
+                                                          const int8_t *__restrict__ mat, int I, int J, float *__restrict__ U,
+                                                          float *__restrict__ V)
+{
+    const long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    if (n >= static_cast<long long>(I) * J) return;
+    const int i = static_cast<int>(n / J), j = static_cast<int>(n - static_cast<long long>(i) * J);
+    float avg = 0.f;
+    int cnt = 0;
+    for (int di = -1; di <= 1; di++)
+        for (int dj = -1; dj <= 1; dj++)
+        {
+            const int ni = i + di, nj = j + dj;
+            if (ni < 0 || ni >= I || nj < 0 || nj >= J) continue;
+            const int id = solidId[static_cast<long long>(ni) * J + nj];
+            if (id != -1)
+            {
+                avg = faddr(avg, friction[id]);
+                cnt++;
+            }
+        }
+    if (cnt == 0) return;
+    avg = __fdiv_rn(avg, static_cast<float>(cnt));
+    const float keep = fsubr(1.f, avg);
+    auto S = [&](int a, int b) { return matSolid(matAt(mat, I, J, a, b)); };
+    if (S(i, j + 1) || S(i - 1, j + 1) || S(i, j) || S(i - 1, j) || S(i, j - 1) || S(i - 1, j - 1)) U[n] = fmulr(U[n], keep);
+    if (S(i + 1, j) || S(i + 1, j - 1) || S(i, j) || S(i, j - 1) || S(i - 1, j) || S(i - 1, j - 1))
+    {
+        const long long vn = static_cast<long long>(i) * (J + 1) + j;
+        V[vn] = fmulr(V[vn], keep);
+    }
+}
+
+// ------------------------------------------------------------------ semi-Lagrangian advection
+// eulerAdvectionThread (flipsolver2d.cpp:340-351): back-trace RK4(-dt) from the INTEGER sample index
+// (not the staggered sample position) and interpolate the input grid with its own offset / OOB policy.
+__global__ void __launch_bounds__(NT) eulerAdvectKernel(GridView in, VelocityView vel, float dt, float *__restrict__ out)
+{
+    const long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    if (n >= static_cast<long long>(in.sizeI) * in.sizeJ) return;
+    const int i = static_cast<int>(n / in.sizeJ), j = static_cast<int>(n - static_cast<long long>(i) * in.sizeJ);
+    const float2 prev = rk4(vel, make_float2(static_cast<float>(i), static_cast<float>(j)), -dt);
+    out[n] = gridLerp(in, prev.x, prev.y);
+}
+
+// NBFlipSolver::updateGridFromSources + combineLevelset (nbflipsolver.cpp:329-376)
+__global__ void __launch_bounds__(NT) nbSourcesLevelsetKernel(const float *__restrict__ sourceSdf, const int32_t *__restrict__ sourceId,
+                                                              const fs2d_source *__restrict__ sources,
+                                                              const float *__restrict__ advSdf, long long N,
+                                                              float *__restrict__ fluidSdf, float *__restrict__ viscosity,
+                                                              float *__restrict__ advViscosity)
+{
+    const long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    if (n >= N) return;
+    const float d = sourceSdf[n];
+    float f = fminf(d, fluidSdf[n]);
+    if (d < 0.f && sourceId[n] != -1)
+    {
+        const float v = sources[sourceId[n]].viscosity;
+        viscosity[n] = v;
+        advViscosity[n] = v;
+    }
+    fluidSdf[n] = fminf(faddr(advSdf[n], 1.f), f);
+}
+
+// combineVelocityGrid + combineCenteredGrids (nbflipsolver.cpp:378-427), rule nbCombine (nbflipsolver.h:53-63)
+__global__ void __launch_bounds__(NT) nbCombineKernel(GridView fluidSdf, int I, int J, const float *__restrict__ advU,
+                                                      const float *__restrict__ advV, const float *__restrict__ advViscosity,
+                                                      float *__restrict__ U, float *__restrict__ V, float *__restrict__ viscosity,
+                                                      float *__restrict__ testGrid, float band)
+{
+    const long long NU = static_cast<long long>(I + 1) * J, NV = static_cast<long long>(I) * (J + 1), N = static_cast<long long>(I) * J;
+    const long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    if (n < NU)
+    {
+        const int i = static_cast<int>(n / J), j = static_cast<int>(n - static_cast<long long>(i) * J);
+        const float sdf = gridLerp(fluidSdf, static_cast<float>(i), faddr(0.5f, static_cast<float>(j)));
+        if (!(sdf > band)) U[n] = advU[n];
+    }
+    else if (n < NU + NV)
+    {
+        const long long m = n - NU;
+        const int i = static_cast<int>(m / (J + 1)), j = static_cast<int>(m - static_cast<long long>(i) * (J + 1));
+        const float sdf = gridLerp(fluidSdf, faddr(0.5f, static_cast<float>(i)), static_cast<float>(j));
+        if (!(sdf > band)) V[m] = advV[m];
+    }
+    else if (n < NU + NV + N)
+    {
+        const long long m = n - NU - NV;
+        const int i = static_cast<int>(m / J), j = static_cast<int>(m - static_cast<long long>(i) * J);
+        // Vec3(0.5f + i, j + 0.5): the second component is evaluated in double and narrowed
+        const float sdf = gridLerp(fluidSdf, faddr(0.5f, static_cast<float>(i)), static_cast<float>(static_cast<double>(j) + 0.5));
+        if (!(sdf > band)) viscosity[m] = advViscosity[m];
+        testGrid[m] = viscosity[m];
+    }
+}
 }  // namespace
 
 int gridBuildMatrix(Ctx *ctx)
@@ -63,6 +473,190 @@ int gridBuildMatrix(Ctx *ctx)
     ctx->launches++;
     // scale = dt / (rho dx^2) (flipsolver2d.cpp:799), float dt promoted to double
     ctx->matrixScale = static_cast<double>(ctx->stepDt) / (ctx->p.fluid_density * ctx->p.dx * ctx->p.dx);
+    FS2D_CUDA(cudaGetLastError());
+    return FS2D_OK;
+}
+
+GridView solidSdfView(const Ctx *c);
+GridView fluidSdfView(const Ctx *c);
+GridView viscosityView(const Ctx *c);
+GridView temperatureView(const Ctx *c);
+GridView concentrationView(const Ctx *c);
+GridView fuelView(const Ctx *c);
+
+static bool isSmoke(const Ctx *ctx) { return ctx->p.sim_type == FS2D_SIM_SMOKE || ctx->p.sim_type == FS2D_SIM_FIRE; }
+
+int gridUpdateMaterials(Ctx *ctx)
+{
+    updateMaterialsKernel<<<divUp(ctx->N, NT), NT, 0, ctx->stream>>>(ctx->fluidSdf, ctx->material, ctx->N);
+    ctx->launches++;
+    FS2D_CUDA(cudaGetLastError());
+    return FS2D_OK;
+}
+
+int gridAfterTransfer(Ctx *ctx)
+{
+    cudaStream_t st = ctx->stream;
+    if (ctx->numSources > 0)
+    {
+        afterTransferKernel<<<divUp(ctx->N, NT), NT, 0, st>>>(ctx->material, ctx->emitterId, ctx->sources, ctx->I, ctx->J, ctx->p.dx,
+                                                            ctx->viscosity, ctx->U, ctx->V, ctx->uValid, ctx->vValid,
+                                                            isSmoke(ctx) ? ctx->temperature : nullptr,
+                                                            isSmoke(ctx) ? ctx->concentration : nullptr,
+                                                            ctx->p.sim_type == FS2D_SIM_FIRE ? ctx->fuel : nullptr);
+        ctx->launches++;
+    }
+    if (isSmoke(ctx)) FS2D_CUDA(cudaMemsetAsync(ctx->divergenceControl, 0, sizeof(float) * ctx->N, st));  // flipsmokesolver.cpp:135
+    if (ctx->p.sim_type == FS2D_SIM_NBFLIP)
+    {
+        // NBFlipSolver::afterTransfer (nbflipsolver.cpp:111-116)
+        nbSourcesLevelsetKernel<<<divUp(ctx->N, NT), NT, 0, st>>>(ctx->sourceSdf, ctx->sourceSdfId, ctx->sources, ctx->advSdf, ctx->N,
+                                                                ctx->fluidSdf, ctx->viscosity, ctx->advViscosity);
+        nbCombineKernel<<<divUp(ctx->NU + ctx->NV + ctx->N, NT), NT, 0, st>>>(fluidSdfView(ctx), ctx->I, ctx->J, ctx->advU, ctx->advV,
+                                                                            ctx->advViscosity, ctx->U, ctx->V, ctx->viscosity,
+                                                                            ctx->testGrid, -2.f);
+        ctx->launches += 2;
+    }
+    FS2D_CUDA(cudaGetLastError());
+    return FS2D_OK;
+}
+
+int gridExtrapolateVelocity(Ctx *ctx, int radius)
+{
+    uint8_t *marker = reinterpret_cast<uint8_t *>(ctx->markers);
+    const int blocks = divUp(ctx->NU + ctx->NV, NT);
+    bfsInitKernel<<<blocks, NT, 0, ctx->stream>>>(ctx->uValid, ctx->vValid, ctx->NU, ctx->NV, marker);
+    for (int k = 1; k <= radius + 1; k++)
+        bfsLayerKernel<<<blocks, NT, 0, ctx->stream>>>(ctx->U, ctx->V, ctx->uValid, ctx->vValid, marker, ctx->I, ctx->J, k);
+    ctx->launches += radius + 2;
+    FS2D_CUDA(cudaGetLastError());
+    return FS2D_OK;
+}
+
+int gridExtrapolateSdf(Ctx *ctx, bool inside)
+{
+    cudaStream_t st = ctx->stream;
+    int *bbox = reinterpret_cast<int *>(ctx->d_counter) + 8;  // 4 ints bbox + 3 ints flags
+    const int init[8] = {0x7fffffff, -1, 0x7fffffff, -1, 0, 0, 0, 0};
+    FS2D_CUDA(cudaMemcpyAsync(bbox, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    const float maxSdf = static_cast<float>(static_cast<size_t>(ctx->I) * static_cast<size_t>(ctx->J));
+    sdfMarkKernel<<<divUp(ctx->N, NT), NT, 0, st>>>(ctx->fluidSdf, ctx->markers, ctx->I, ctx->J, inside ? 1 : 0, maxSdf, bbox);
+    int perSm = 0;
+    FS2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, sdfExtrapolateKernel, NT, 0));
+    const int blocks = ctx->smCount * std::max(perSm, 1);
+    float *sdf = ctx->fluidSdf;
+    int32_t *markers = ctx->markers;
+    int I = ctx->I, J = ctx->J;
+    float step = inside ? -1.f : 1.f;
+    const int *cb = bbox;
+    int *flags = bbox + 4;
+    void *args[] = {&sdf, &markers, &I, &J, &step, &cb, &flags};
+    FS2D_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(sdfExtrapolateKernel), dim3(blocks), dim3(NT), args, 0, st));
+    ctx->launches += 2;
+    return FS2D_OK;
+}
+
+int gridSaveVelocity(Ctx *ctx)
+{
+    FS2D_CUDA(cudaMemcpyAsync(ctx->savedU, ctx->U, sizeof(float) * ctx->NU, cudaMemcpyDeviceToDevice, ctx->stream));
+    FS2D_CUDA(cudaMemcpyAsync(ctx->savedV, ctx->V, sizeof(float) * ctx->NV, cudaMemcpyDeviceToDevice, ctx->stream));
+    return FS2D_OK;
+}
+
+int gridBodyForces(Ctx *ctx)
+{
+    // const float factor = m_stepDt / m_dx (float / double, narrowed)
+    const float factor = static_cast<float>(static_cast<double>(ctx->stepDt) / ctx->p.dx);
+    const int blocks = divUp(ctx->NU + ctx->NV, NT);
+    if (isSmoke(ctx))
+    {
+        smokeBodyForceKernel<<<blocks, NT, 0, ctx->stream>>>(ctx->U, ctx->V, ctx->I, ctx->J, temperatureView(ctx), concentrationView(ctx),
+                                                            ctx->p.soot_factor, ctx->p.buoyancy_factor / ctx->p.ambient_temperature,
+                                                            ctx->p.ambient_temperature, ctx->p.gravity_x, ctx->p.gravity_y, factor);
+    }
+    else
+    {
+        bodyForceKernel<<<blocks, NT, 0, ctx->stream>>>(ctx->U, ctx->V, ctx->NU, ctx->NV, factor * ctx->p.gravity_x,
+                                                       factor * ctx->p.gravity_y);
+    }
+    ctx->launches++;
+    FS2D_CUDA(cudaGetLastError());
+    return FS2D_OK;
+}
+
+int gridPressureRhs(Ctx *ctx)
+{
+    const double scale = 1.f / ctx->p.dx;  // const double scale = 1.f/m_dx
+    pressureRhsKernel<<<divUp(ctx->N, NT), NT, 0, ctx->stream>>>(ctx->U, ctx->V, ctx->divergenceControl, ctx->material, ctx->I, ctx->J,
+                                                                isSmoke(ctx) ? 1 : 0, scale, ctx->rhs);
+    ctx->launches++;
+    FS2D_CUDA(cudaGetLastError());
+    return FS2D_OK;
+}
+
+int gridDensityRhs(Ctx *ctx)
+{
+    const double scale = 1.0 / ctx->stepDt;
+    densityRhsKernel<<<divUp(ctx->N, NT), NT, 0, ctx->stream>>>(ctx->density, ctx->material, ctx->N, scale, ctx->p.fluid_density, ctx->rhs);
+    ctx->launches++;
+    FS2D_CUDA(cudaGetLastError());
+    return FS2D_OK;
+}
+
+int gridApplyPressure(Ctx *ctx)
+{
+    const double scale = ctx->stepDt / (ctx->p.fluid_density * ctx->p.dx);
+    applyPressureKernel<<<divUp(ctx->N, NT), NT, 0, ctx->stream>>>(ctx->x, ctx->material, ctx->I, ctx->J, isSmoke(ctx) ? 1 : 0, scale,
+                                                                  ctx->U, ctx->V, ctx->uValid, ctx->vValid,
+                                                                  isSmoke(ctx) ? ctx->testGrid : nullptr);
+    ctx->launches++;
+    FS2D_CUDA(cudaGetLastError());
+    return FS2D_OK;
+}
+
+int gridVelocityFromSolids(Ctx *ctx)
+{
+    if (ctx->numObstacles == 0) return FS2D_OK;
+    solidFrictionKernel<<<divUp(ctx->N, NT), NT, 0, ctx->stream>>>(ctx->solidId, ctx->obstacleFriction, ctx->material, ctx->I, ctx->J,
+                                                                  ctx->U, ctx->V);
+    ctx->launches++;
+    FS2D_CUDA(cudaGetLastError());
+    return FS2D_OK;
+}
+
+// FlipSmokeSolver / FlipFireSolver::eulerAdvectParameters (flipsmokesolver.cpp:211-233, flipfiresolver.cpp:155-172)
+int gridEulerAdvectParameters(Ctx *ctx)
+{
+    if (!isSmoke(ctx)) return FS2D_OK;  // FlipSolver::eulerAdvectParameters is empty for water
+    const VelocityView vel = makeVelocityView(ctx->U, ctx->V, ctx->I, ctx->J);
+    const int blocks = divUp(ctx->N, NT);
+    eulerAdvectKernel<<<blocks, NT, 0, ctx->stream>>>(concentrationView(ctx), vel, ctx->stepDt, ctx->scratchA);
+    eulerAdvectKernel<<<blocks, NT, 0, ctx->stream>>>(temperatureView(ctx), vel, ctx->stepDt, ctx->scratchB);
+    ctx->launches += 2;
+    if (ctx->p.sim_type == FS2D_SIM_FIRE)
+    {
+        eulerAdvectKernel<<<blocks, NT, 0, ctx->stream>>>(fuelView(ctx), vel, ctx->stepDt, ctx->scratchC);
+        ctx->launches++;
+        std::swap(ctx->fuel, ctx->scratchC);
+    }
+    std::swap(ctx->concentration, ctx->scratchA);
+    std::swap(ctx->temperature, ctx->scratchB);
+    ctx->smokeGridsAdvected = true;  // the members now carry OOB_EXTEND and offset (1/2,1/2)
+    FS2D_CUDA(cudaGetLastError());
+    return FS2D_OK;
+}
+
+// NBFlipSolver::advect, the grid part (nbflipsolver.cpp:66-109)
+int gridNbflipAdvect(Ctx *ctx)
+{
+    if (ctx->p.sim_type != FS2D_SIM_NBFLIP) return FS2D_OK;
+    const VelocityView vel = makeVelocityView(ctx->U, ctx->V, ctx->I, ctx->J);
+    cudaStream_t st = ctx->stream;
+    eulerAdvectKernel<<<divUp(ctx->NU, NT), NT, 0, st>>>(vel.u, vel, ctx->stepDt, ctx->advU);
+    eulerAdvectKernel<<<divUp(ctx->NV, NT), NT, 0, st>>>(vel.v, vel, ctx->stepDt, ctx->advV);
+    eulerAdvectKernel<<<divUp(ctx->N, NT), NT, 0, st>>>(fluidSdfView(ctx), vel, ctx->stepDt, ctx->advSdf);
+    eulerAdvectKernel<<<divUp(ctx->N, NT), NT, 0, st>>>(viscosityView(ctx), vel, ctx->stepDt, ctx->advViscosity);
+    ctx->launches += 4;
     FS2D_CUDA(cudaGetLastError());
     return FS2D_OK;
 }

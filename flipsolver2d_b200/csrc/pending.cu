@@ -1,31 +1,4 @@
 // Temporary: stages not yet implemented report FS2D_ERR_STATE.
 #include "fs2d_internal.h"
 #define PENDING(sig) int sig { ctx->lastError = "stage not implemented yet"; return FS2D_ERR_STATE; }
-PENDING(particlesReserve(Ctx *ctx, int64_t))
-PENDING(particlesMaxVelocity(Ctx *ctx, float *))
-PENDING(particlesAdvect(Ctx *ctx))
-PENDING(particlesSort(Ctx *ctx))
-PENDING(particlesUpdate(Ctx *ctx))
-PENDING(particlesCount(Ctx *ctx))
-PENDING(particlesAdjustByDensity(Ctx *ctx))
-PENDING(particlesReseedPlan(Ctx *ctx, int64_t *))
-PENDING(particlesReseedApply(Ctx *ctx, int64_t, const float *))
-PENDING(particlesPruneNarrowBand(Ctx *ctx))
-PENDING(transferVelocity(Ctx *ctx))
-PENDING(transferCentered(Ctx *ctx))
-PENDING(transferDensity(Ctx *ctx))
-PENDING(transferSdf(Ctx *ctx))
-PENDING(gridUpdateMaterials(Ctx *ctx))
-PENDING(gridAfterTransfer(Ctx *ctx))
-PENDING(gridExtrapolateVelocity(Ctx *ctx, int))
-PENDING(gridExtrapolateSdf(Ctx *ctx, bool))
-PENDING(gridSaveVelocity(Ctx *ctx))
-PENDING(gridBodyForces(Ctx *ctx))
-PENDING(gridPressureRhs(Ctx *ctx))
-PENDING(gridDensityRhs(Ctx *ctx))
-PENDING(gridApplyPressure(Ctx *ctx))
-PENDING(gridVelocityFromSolids(Ctx *ctx))
-PENDING(gridEulerAdvectParameters(Ctx *ctx))
-PENDING(gridNbflipAdvect(Ctx *ctx))
 PENDING(gridViscosity(Ctx *ctx, int *))
-extern "C" int fs2d_substep(fs2d_handle ctx, float, float *, int *) { ctx->lastError = "not implemented"; return FS2D_ERR_STATE; }

@@ -1,0 +1,368 @@
+// Kernel group 2 (P2G) and the particle-reading part of group 3 (fluid SDF).
+//
+// The reference's P2G is a gather: every grid cell loops over all particles of the 3x3 block of
+// 3x3-cell bins around it and sums in storage order (flipsolver2d.cpp:1329-1377). With the
+// particles sorted by cell (particles.cu) the same gather needs only the cells inside the kernel
+// support, and each row of those cells is ONE contiguous particle range
+// [cellStart[r*J + j0], cellStart[r*J + j1 + 1]). A CTA owns a TILE_I x TILE_J tile of cells and
+// first stages the particle records of the tile plus its halo into shared memory (one coalesced
+// pass over the sorted arrays), then every thread gathers its cell from the staged records in a
+// fixed order -- no atomics, so the result is deterministic and independent of launch geometry.
+// When a tile's particles do not fit the staging buffer the threads read the same ranges
+// straight from global memory (L1/L2 hits), same order, same result.
+//
+// Weights are evaluated with the reference's expressions and thresholds (mathfuncs.cpp:32-43,
+// :100-116) using non-contracted float arithmetic; only the summation ORDER differs from the
+// reference (its in-bin order is history dependent), so sums agree to float rounding, not bitwise.
+#include <algorithm>
+#include <cfloat>
+
+#include "fs2d_device.cuh"
+#include "fs2d_internal.h"
+
+namespace
+{
+constexpr int TI = 8;          // tile rows (cells)
+constexpr int TJ = 32;         // tile columns (cells)
+constexpr int NT = TI * TJ;    // one thread per cell
+constexpr int STAGE = 6144;    // staged particle records per CTA (pos + 2 payload floats = 16 B each)
+
+struct TileStage
+{
+    float2 pos[STAGE];
+    float2 pay[STAGE];          // velocity, or (property, unused)
+    int rowBegin[TI + 4];       // global particle index where each staged row starts
+    int rowOffset[TI + 5];      // offset of each staged row inside pos/pay
+};
+constexpr size_t STAGE_BYTES = sizeof(TileStage);  // 96 KB + row tables: dynamic shared memory, 2 CTAs per SM
+
+// Stage rows [i0-haloLo, i0+TI-1+haloHi] x columns [j0-haloLo, j0+TJ-1+haloHi] of the sorted
+// particle arrays. Returns false (for the whole CTA) when the records do not fit.
+template <bool WITH_PAYLOAD2>
+__device__ bool stageTile(TileStage &s, const int32_t *__restrict__ cellStart, const float2 *__restrict__ pos,
+                          const float2 *__restrict__ pay2, const float *__restrict__ pay1, int I, int J, int i0, int j0,
+                          int haloLo, int haloHi)
+{
+    const int rows = TI + haloLo + haloHi;
+    __shared__ int total;
+    if (threadIdx.x == 0)
+    {
+        int acc = 0;
+        const int ja = max(j0 - haloLo, 0), jb = min(j0 + TJ - 1 + haloHi, J - 1);
+        for (int r = 0; r < rows; r++)
+        {
+            const int gi = i0 - haloLo + r;
+            int b = 0, e = 0;
+            if (gi >= 0 && gi < I && ja <= jb)
+            {
+                b = cellStart[static_cast<long long>(gi) * J + ja];
+                e = cellStart[static_cast<long long>(gi) * J + jb + 1];
+            }
+            s.rowBegin[r] = b;
+            s.rowOffset[r] = acc;
+            acc += e - b;
+        }
+        s.rowOffset[rows] = acc;
+        total = acc;
+    }
+    __syncthreads();
+    if (total > STAGE) return false;
+    for (int r = 0; r < rows; r++)
+    {
+        const int n = s.rowOffset[r + 1] - s.rowOffset[r];
+        const int gb = s.rowBegin[r], so = s.rowOffset[r];
+        for (int k = threadIdx.x; k < n; k += NT)
+        {
+            s.pos[so + k] = pos[gb + k];
+            if (WITH_PAYLOAD2)
+                s.pay[so + k] = pay2[gb + k];
+            else
+                s.pay[so + k] = make_float2(pay1 ? pay1[gb + k] : 0.f, 0.f);
+        }
+    }
+    __syncthreads();
+    return true;
+}
+
+// Iterate the particles of cells [ja..jb] of row gi, staged or global. F(pos, payload).
+template <bool WITH_PAYLOAD2, class F>
+__device__ __forceinline__ void forRowRange(const TileStage &s, bool staged, const int32_t *__restrict__ cellStart,
+                                            const float2 *__restrict__ pos, const float2 *__restrict__ pay2,
+                                            const float *__restrict__ pay1, int J, int gi, int ja, int jb, int stagedRow, F f)
+{
+    const int b = cellStart[static_cast<long long>(gi) * J + ja];
+    const int e = cellStart[static_cast<long long>(gi) * J + jb + 1];
+    if (staged)
+    {
+        const int shift = s.rowOffset[stagedRow] - s.rowBegin[stagedRow];
+        for (int k = b; k < e; k++) f(s.pos[k + shift], s.pay[k + shift]);
+    }
+    else
+    {
+        for (int k = b; k < e; k++)
+            f(pos[k], WITH_PAYLOAD2 ? pay2[k] : make_float2(pay1 ? pay1[k] : 0.f, 0.f));
+    }
+}
+
+// particleVelocityToGridThread (flipsolver2d.cpp:1329-1377). Cell (i,j) receives particles with
+// weightU > 1e-9 && weightV > 1e-9, i.e. floor(pos) within one cell of (i,j).
+__global__ void __launch_bounds__(NT) p2gVelocityKernel(const int32_t *__restrict__ cellStart, const float2 *__restrict__ pos,
+                                                        const float2 *__restrict__ vel, int I, int J, int tilesJ,
+                                                        float *__restrict__ U, float *__restrict__ V,
+                                                        uint8_t *__restrict__ uValid, uint8_t *__restrict__ vValid)
+{
+    extern __shared__ __align__(16) unsigned char stageRaw[];
+    TileStage &s = *reinterpret_cast<TileStage *>(stageRaw);
+    const int ti = blockIdx.x / tilesJ, tj = blockIdx.x - ti * tilesJ;
+    const int i0 = ti * TI, j0 = tj * TJ;
+    const bool staged = stageTile<true>(s, cellStart, pos, vel, nullptr, I, J, i0, j0, 1, 1);
+    const int li = threadIdx.x / TJ, lj = threadIdx.x - li * TJ;
+    const int i = i0 + li, j = j0 + lj;
+    if (i >= I || j >= J) return;
+    const float ci = static_cast<float>(i), cj = static_cast<float>(j);
+    const float cjh = faddr(cj, 0.5f), cih = faddr(ci, 0.5f);
+    float uW = 1e-10f, vW = 1e-10f, uAcc = 0.f, vAcc = 0.f;
+    bool any = false;
+    const int ja = max(j - 1, 0), jb = min(j + 1, J - 1);
+    for (int gi = max(i - 1, 0); gi <= min(i + 1, I - 1); gi++)
+    {
+        forRowRange<true>(s, staged, cellStart, pos, vel, nullptr, J, gi, ja, jb, gi - (i0 - 1),
+                          [&](float2 p, float2 v)
+                          {
+                              const float wU = quadraticBSpline(fsubr(p.x, ci), fsubr(p.y, cjh));
+                              const float wV = quadraticBSpline(fsubr(p.x, cih), fsubr(p.y, cj));
+                              if (wU > 1e-9f && wV > 1e-9f)
+                              {
+                                  uW = faddr(uW, wU);
+                                  uAcc = faddr(uAcc, fmulr(wU, v.x));
+                                  vW = faddr(vW, wV);
+                                  vAcc = faddr(vAcc, fmulr(wV, v.y));
+                                  any = true;
+                              }
+                          });
+    }
+    U[static_cast<long long>(i) * J + j] = __fdiv_rn(uAcc, uW);
+    uValid[static_cast<long long>(i) * J + j] = any ? 1 : 0;
+    V[static_cast<long long>(i) * (J + 1) + j] = __fdiv_rn(vAcc, vW);
+    vValid[static_cast<long long>(i) * (J + 1) + j] = any ? 1 : 0;
+}
+
+// centeredParamsToGridThread. MODE 0: water (flipsolver2d.cpp:1394-1431: threshold w > 1e-9, value
+// = sum/(1e-10 + sum w) always written). MODE 1: nbflip/smoke/fire (nbflipsolver.cpp:463-504,
+// flipsmokesolver.cpp:509-558: threshold |w| > 1e-6, divided only when known, grids pre-zeroed).
+// The support of B(px - i) spans cells i-2 .. i+1.
+template <int MODE>
+__global__ void __launch_bounds__(NT) p2gCenteredKernel(const int32_t *__restrict__ cellStart, const float2 *__restrict__ pos,
+                                                        const float *__restrict__ prop, int I, int J, int tilesJ,
+                                                        float *__restrict__ out, uint8_t *__restrict__ known)
+{
+    extern __shared__ __align__(16) unsigned char stageRaw[];
+    TileStage &s = *reinterpret_cast<TileStage *>(stageRaw);
+    const int ti = blockIdx.x / tilesJ, tj = blockIdx.x - ti * tilesJ;
+    const int i0 = ti * TI, j0 = tj * TJ;
+    const bool staged = stageTile<false>(s, cellStart, pos, nullptr, prop, I, J, i0, j0, 2, 1);
+    const int li = threadIdx.x / TJ, lj = threadIdx.x - li * TJ;
+    const int i = i0 + li, j = j0 + lj;
+    if (i >= I || j >= J) return;
+    const float ci = static_cast<float>(i), cj = static_cast<float>(j);
+    float wSum = 1e-10f, acc = 0.f;
+    bool any = false;
+    const int ja = max(j - 2, 0), jb = min(j + 1, J - 1);
+    for (int gi = max(i - 2, 0); gi <= min(i + 1, I - 1); gi++)
+    {
+        forRowRange<false>(s, staged, cellStart, pos, nullptr, prop, J, gi, ja, jb, gi - (i0 - 2),
+                           [&](float2 p, float2 v)
+                           {
+                               const float w = quadraticBSpline(fsubr(p.x, ci), fsubr(p.y, cj));
+                               const bool take = MODE == 0 ? (w > 1e-9f) : (fabsf(w) > 1e-6f);
+                               if (take)
+                               {
+                                   wSum = faddr(wSum, w);
+                                   acc = faddr(acc, fmulr(w, v.x));
+                                   any = true;
+                               }
+                           });
+    }
+    const long long n = static_cast<long long>(i) * J + j;
+    if (MODE == 0)
+        out[n] = __fdiv_rn(acc, wSum);
+    else
+        out[n] = any ? __fdiv_rn(acc, wSum) : 0.f;
+    if (known) known[n] = any ? 1 : 0;
+}
+
+// updateDensityGridThread (flipsolver2d.cpp:201-249)
+__global__ void __launch_bounds__(NT) densityKernel(const int32_t *__restrict__ cellStart, const float2 *__restrict__ pos,
+                                                    const int8_t *__restrict__ mat, int I, int J, int tilesJ, float particleMass,
+                                                    float cellVolume, float restDensity, float *__restrict__ density)
+{
+    extern __shared__ __align__(16) unsigned char stageRaw[];
+    TileStage &s = *reinterpret_cast<TileStage *>(stageRaw);
+    const int ti = blockIdx.x / tilesJ, tj = blockIdx.x - ti * tilesJ;
+    const int i0 = ti * TI, j0 = tj * TJ;
+    const bool staged = stageTile<false>(s, cellStart, pos, nullptr, nullptr, I, J, i0, j0, 1, 1);
+    const int li = threadIdx.x / TJ, lj = threadIdx.x - li * TJ;
+    const int i = i0 + li, j = j0 + lj;
+    if (i >= I || j >= J) return;
+    const float ci = static_cast<float>(i), cj = static_cast<float>(j);
+    float acc = 0.f;
+    const int ja = max(j - 1, 0), jb = min(j + 1, J - 1);
+    for (int gi = max(i - 1, 0); gi <= min(i + 1, I - 1); gi++)
+    {
+        forRowRange<false>(s, staged, cellStart, pos, nullptr, nullptr, J, gi, ja, jb, gi - (i0 - 1),
+                           [&](float2 p, float2)
+                           {
+                               const float w = bilinearHat(fsubr(fsubr(p.x, ci), 0.5f), fsubr(fsubr(p.y, cj), 0.5f));
+                               if (fabsf(w) > 1e-6f) acc = faddr(acc, fmulr(w, particleMass));
+                           });
+    }
+    float d = __fdiv_rn(acc, cellVolume);
+    if (matFluid(mat[static_cast<long long>(i) * J + j]) &&
+        (matEmpty(matAt(mat, I, J, i + 1, j)) || matEmpty(matAt(mat, I, J, i - 1, j)) || matEmpty(matAt(mat, I, J, i, j + 1)) ||
+         matEmpty(matAt(mat, I, J, i, j - 1))))
+        d = fminf(fmaxf(d, restDensity), FLT_MAX);
+    density[static_cast<long long>(i) * J + j] = d;
+}
+
+// updateSdfThread (flipsolver2d.cpp:1276-1311): min squared distance to the particles of the 3x3
+// block of BINS around the cell's bin (rows/columns 3*(b-1) .. 3*(b+1)+2), minus the particle radius.
+// The minimum is order independent, so rows are visited outwards from the cell's own row and the walk
+// stops once no remaining row can hold a closer particle -- the value is identical to the full scan.
+__global__ void __launch_bounds__(256) sdfKernel(const int32_t *__restrict__ cellStart, const float2 *__restrict__ pos, int I,
+                                                 int J, float radius, float *__restrict__ sdf)
+{
+    const long long n = blockIdx.x * 256ll + threadIdx.x;
+    if (n >= static_cast<long long>(I) * J) return;
+    const int i = static_cast<int>(n / J), j = static_cast<int>(n - static_cast<long long>(i) * J);
+    const int bi = i / 3, bj = j / 3;
+    const int iLo = max(3 * (bi - 1), 0), iHi = min(3 * (bi + 1) + 2, I - 1);
+    const int jLo = max(3 * (bj - 1), 0), jHi = min(3 * (bj + 1) + 2, J - 1);
+    const float cx = faddr(static_cast<float>(i), 0.5f), cy = faddr(static_cast<float>(j), 0.5f);
+    float best = FLT_MAX;
+    const int reach = max(i - iLo, iHi - i);
+    for (int d = 0; d <= reach; d++)
+    {
+        // every particle in a row at distance d is at least d - 1/2 away from the cell centre
+        const float lower = static_cast<float>(d) - 0.5f;
+        if (d > 0 && lower * lower >= best) break;
+        for (int sgn = 0; sgn < (d == 0 ? 1 : 2); sgn++)
+        {
+            const int gi = sgn == 0 ? i - d : i + d;
+            if (gi < iLo || gi > iHi) continue;
+            const int b = cellStart[static_cast<long long>(gi) * J + jLo];
+            const int e = cellStart[static_cast<long long>(gi) * J + jHi + 1];
+            for (int k = b; k < e; k++)
+            {
+                const float2 p = pos[k];
+                const float dx = fsubr(p.x, cx), dy = fsubr(p.y, cy);
+                const float d2 = faddr(fmulr(dx, dx), fmulr(dy, dy));
+                if (d2 < best) best = d2;
+            }
+        }
+    }
+    sdf[n] = fsubr(__fsqrt_rn(best), radius);
+}
+
+template <class K> void allowStage(K kernel)
+{
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(STAGE_BYTES));
+}
+
+int tileCount(const Ctx *ctx, int *tilesJ)
+{
+    *tilesJ = divUp(ctx->J, TJ);
+    return divUp(ctx->I, TI) * *tilesJ;
+}
+}  // namespace
+
+int particlesSort(Ctx *ctx);
+
+static int ensureSorted(Ctx *ctx)
+{
+    if (!ctx->sorted) return particlesSort(ctx);
+    return FS2D_OK;
+}
+
+int transferVelocity(Ctx *ctx)
+{
+    FS2D_TRY(ensureSorted(ctx));
+    cudaStream_t st = ctx->stream;
+    // fill(0)/fill(false) of all four arrays (flipsolver2d.cpp:1315-1318); row I of U and column J of V keep 0
+    FS2D_CUDA(cudaMemsetAsync(ctx->U + ctx->N, 0, sizeof(float) * (ctx->NU - ctx->N), st));
+    FS2D_CUDA(cudaMemsetAsync(ctx->uValid + ctx->N, 0, ctx->NU - ctx->N, st));
+    FS2D_CUDA(cudaMemsetAsync(ctx->V, 0, sizeof(float) * ctx->NV, st));
+    FS2D_CUDA(cudaMemsetAsync(ctx->vValid, 0, ctx->NV, st));
+    int tilesJ;
+    const int tiles = tileCount(ctx, &tilesJ);
+    ParticleBuffers &b = ctx->pb[ctx->cur];
+    allowStage(p2gVelocityKernel);
+    p2gVelocityKernel<<<tiles, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, b.vel, ctx->I, ctx->J, tilesJ, ctx->U, ctx->V, ctx->uValid,
+                                           ctx->vValid);
+    ctx->launches++;
+    FS2D_CUDA(cudaGetLastError());
+    return FS2D_OK;
+}
+
+int transferCentered(Ctx *ctx)
+{
+    FS2D_TRY(ensureSorted(ctx));
+    cudaStream_t st = ctx->stream;
+    int tilesJ;
+    const int tiles = tileCount(ctx, &tilesJ);
+    ParticleBuffers &b = ctx->pb[ctx->cur];
+    // m_divergenceControl.fill(0.f) in all three variants (flipsolver2d.cpp:1382, nbflipsolver.cpp:450,
+    // flipsmokesolver.cpp:60)
+    FS2D_CUDA(cudaMemsetAsync(ctx->divergenceControl, 0, sizeof(float) * ctx->N, st));
+    allowStage(p2gCenteredKernel<0>);
+    allowStage(p2gCenteredKernel<1>);
+    auto column = [&](int prop) -> const float * { return prop >= 0 ? b.props + static_cast<int64_t>(prop) * b.capacity : nullptr; };
+    switch (ctx->p.sim_type)
+    {
+    case FS2D_SIM_LIQUID:
+        p2gCenteredKernel<0><<<tiles, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, column(ctx->p.viscosity_property), ctx->I, ctx->J,
+                                                   tilesJ, ctx->viscosity, ctx->knownCentered);
+        ctx->launches++;
+        break;
+    case FS2D_SIM_NBFLIP:
+        p2gCenteredKernel<1><<<tiles, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, column(ctx->p.viscosity_property), ctx->I, ctx->J,
+                                                   tilesJ, ctx->viscosity, ctx->knownCentered);
+        ctx->launches++;
+        break;
+    default:  // smoke / fire: temperature and concentration (fire's fuel column has no P2G in the reference)
+        p2gCenteredKernel<1><<<tiles, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, column(ctx->p.temperature_property), ctx->I, ctx->J,
+                                                   tilesJ, ctx->temperature, ctx->knownCentered);
+        p2gCenteredKernel<1><<<tiles, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, column(ctx->p.concentration_property), ctx->I, ctx->J,
+                                                   tilesJ, ctx->concentration, nullptr);
+        ctx->launches += 2;
+        break;
+    }
+    FS2D_CUDA(cudaGetLastError());
+    return FS2D_OK;
+}
+
+int transferDensity(Ctx *ctx)
+{
+    FS2D_TRY(ensureSorted(ctx));
+    int tilesJ;
+    const int tiles = tileCount(ctx, &tilesJ);
+    // float cellVolume = dx*dx*dx; float particleMass = (rho * cellVolume) / float(ppc) (flipsolver2d.cpp:203-204)
+    const float cellVolume = static_cast<float>(ctx->p.dx * ctx->p.dx * ctx->p.dx);
+    const float particleMass =
+        static_cast<float>((ctx->p.fluid_density * cellVolume) / static_cast<float>(ctx->p.particles_per_cell));
+    allowStage(densityKernel);
+    densityKernel<<<tiles, NT, STAGE_BYTES, ctx->stream>>>(ctx->cellStart, ctx->pb[ctx->cur].pos, ctx->material, ctx->I, ctx->J, tilesJ,
+                                                particleMass, cellVolume, static_cast<float>(ctx->p.fluid_density), ctx->density);
+    ctx->launches++;
+    FS2D_CUDA(cudaGetLastError());
+    return FS2D_OK;
+}
+
+int transferSdf(Ctx *ctx)
+{
+    FS2D_TRY(ensureSorted(ctx));
+    sdfKernel<<<divUp(ctx->N, 256), 256, 0, ctx->stream>>>(ctx->cellStart, ctx->pb[ctx->cur].pos, ctx->I, ctx->J,
+                                                          ctx->p.particle_scale, ctx->fluidSdf);
+    ctx->launches++;
+    FS2D_CUDA(cudaGetLastError());
+    return FS2D_OK;
+}
