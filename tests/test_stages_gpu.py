@@ -43,9 +43,25 @@ def pair(request, ref_mod, scene_dir):
 
 
 def _sync(pair):
+    """Mirror the reference state into the device. The reference leaves particles that the density
+    correction pushed across a bin boundary in their OLD storage bin (flipsolver2d.cpp:427); the
+    cell-sorted device layout has no such state, so the reference's bins are normalised first
+    (ref_set_particles re-files every particle by position, same order)."""
     s, d, scene = pair
+    pos, vel, props, _ = s.particles()
+    s.set_particles(pos, vel, props)
     H.sync_state(s, d, scene["settings"]["simType"])
     return s, d
+
+
+def _mask_matches(ref_mask, dev_mask, expected):
+    """Device flags must equal the numpy restatement exactly. The reference's std::vector<bool> flags
+    lose updates at ThreadPool range boundaries (oracle/restate.py): it may only differ by a few
+    missing `true` bits."""
+    assert np.array_equal(dev_mask.astype(bool), expected)
+    lost = ref_mask.astype(bool) != expected
+    assert not np.any(ref_mask.astype(bool) & ~expected), "reference set a flag the rule does not"
+    assert lost.sum() <= 16, "too many differing flags for the vector<bool> race"
 
 
 def _particles_equal(s, d, exact=True):
@@ -83,6 +99,7 @@ def test_advect_and_sort(pair):
     assert np.all(np.diff(key) >= 0), "device particles are not sorted by cell"
     dbins = (np.floor(dpos[:, 0]).astype(np.int64) // 3) * binsJ + np.floor(dpos[:, 1]).astype(np.int64) // 3
     nb = ((s.I + 2) // 3) * binsJ
+    # particles the reference moved this stage were re-filed by position, the others were already
     assert np.array_equal(np.bincount(rbins, minlength=nb), np.bincount(dbins, minlength=nb))
 
 
@@ -90,9 +107,16 @@ def test_p2g(pair):
     s, d = _sync(pair)
     s.stage("P2G")
     d.stage("particle_to_grid")
-    assert np.array_equal(s.grid("U_VALID"), d.download("U_VALID"))
-    assert np.array_equal(s.grid("V_VALID"), d.download("V_VALID"))
-    assert np.array_equal(s.grid("KNOWN_CENTERED"), d.download("KNOWN_CENTERED"))
+    from oracle import restate
+    pos = s.particles()[0]
+    flags = restate.p2g_validity(pos, s.I, s.J)
+    uexp = np.zeros((s.I + 1, s.J), bool)
+    uexp[:s.I] = flags
+    vexp = np.zeros((s.I, s.J + 1), bool)
+    vexp[:, :s.J] = flags
+    _mask_matches(s.grid("U_VALID"), d.download("U_VALID"), uexp.ravel())
+    _mask_matches(s.grid("V_VALID"), d.download("V_VALID"), vexp.ravel())
+    _mask_matches(s.grid("KNOWN_CENTERED"), d.download("KNOWN_CENTERED"), restate.centered_known(pos, s.I, s.J).ravel())
     assert H.rel_l2(d.download("U"), s.grid("U")) < SUM_TOL
     assert H.rel_l2(d.download("V"), s.grid("V")) < SUM_TOL
     assert H.rel_l2(d.download("VISCOSITY"), s.grid("VISCOSITY")) < SUM_TOL
