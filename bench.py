@@ -1,0 +1,322 @@
+#!/usr/bin/env python3
+"""Headline benchmark: substeps/s of the FLIP dam-break scene at 4096^2 (BASELINE.json `metric`), one
+JSON line on stdout.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--res R] [--impl reference]
+
+A "step" is one CFL substep = one FlipSolver::step() (flipsolver2d.cpp:412-462), driven through the
+host mirror of the reference API (libfs2d_host.so: JsonSceneReader::loadJson -> stepSubstep), which
+calls the sm_100a kernels through the fs2d C ABI. All state is resident in HBM when the timed region
+starts (`value`); `e2e` repeats the measurement with the particle state crossing PCIe both ways every
+step (pinned host buffers -> fs2d_upload_particles, substep, fs2d_download_particles).
+
+`--impl reference` times the reference's own CPU implementation (oracle/_ref/libfs2d_ref.so = the
+unmodified reference sources with its Release flags) on the host cores, on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "substeps_per_s"
+UNIT = "substeps/s"
+REFERENCE_SAMPLE_RES = 1024
+
+
+def scene_for(res):
+    from flipsolver2d_b200 import scenes
+    return scenes.dam_break(res, "flip", ppc=8, pic_ratio=0.03, seed=0, max_substeps=10)
+
+
+def workload_name(res):
+    return "flip dam-break %dx%d, ppc 8, picRatio 0.03, pcgIterLimit 200 (default), seed 0" % (res, res)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=3)
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, n in enumerate(names):
+                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": float(self.rows[0][1]) if self.rows else None,
+                "power_w_max": max((float(r[2]) for r in self.rows if len(r) > 2), default=None),
+                "samples": len(self.rows), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "pcg_traffic.json")))["k1_dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+# --------------------------------------------------------------------------------------- reference arm
+def reference_substep(s):
+    """One iteration of FlipSolver::stepFrame's loop on the oracle (flipsolver2d.cpp:476-497)."""
+    st = reference_substep.state
+    p = reference_substep.params
+    vel = s.max_particle_velocity()
+    import numpy as np
+    f32 = np.float32
+    max_dt = f32(p["cfl"]) / (f32(vel) + f32(1e-15))
+    frame_dt = f32(p["frameDt"])
+    finished = False
+    if st["t"] + max_dt >= frame_dt or st["n"] == int(p["maxSubsteps"]) - 1:
+        max_dt = frame_dt - st["t"]
+        finished = True
+    elif st["t"] + f32(2.0) * max_dt >= frame_dt:
+        max_dt = f32(0.5) * (frame_dt - st["t"])
+    s.set_step_dt(float(max_dt))
+    s.stage("FULL_STEP")
+    st["t"] = f32(st["t"] + max_dt)
+    st["n"] += 1
+    if finished:
+        st["t"], st["n"] = f32(0.0), 0
+        s.bump_frame()
+
+
+def make_reference(res, tmp):
+    import numpy as np
+    from flipsolver2d_b200 import scenes
+    from oracle import ref
+    if not ref.available(strict=False):
+        raise RuntimeError("oracle/_ref/libfs2d_ref.so missing (run __graft_entry__.build() where /root/reference exists)")
+    path = scenes.write_scene(scene_for(res), os.path.join(tmp, "ref_%d.json" % res))
+    s = ref.RefSolver(path, strict=False, threads=None, quiet=True)
+    s.stage("FIRST_FRAME_INIT")
+    s.bump_frame()
+    reference_substep.state = {"t": np.float32(0.0), "n": 0}
+    reference_substep.params = s.params()
+    return s
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    tmp = tempfile.mkdtemp(prefix="fs2d_bench_")
+    res = REFERENCE_SAMPLE_RES
+    s = make_reference(res, tmp)
+    cores = s.threads
+    for _ in range(args.warmup):
+        reference_substep(s)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        reference_substep(s)
+    dt = time.perf_counter() - t0
+    scale = (res * res) / float(args.res * args.res)
+    value = args.steps / dt * scale
+    sample = ("%d substeps of the same scene at %dx%d on %d host threads (reference ThreadPool = all cores); rate x %.4f "
+              "(cell-count ratio) to express it at %dx%d -- favourable to the reference, whose rebin stage is superlinear"
+              % (args.steps, res, res, cores, scale, args.res, args.res))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3 / scale, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.res), "sample_resolution": res, "scale_to_workload": scale},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(args, tmp, budget_s=25.0):
+    """The reference's CPU path on this host, bounded: substeps of the 1024^2 scene for ~budget_s."""
+    res = REFERENCE_SAMPLE_RES
+    s = make_reference(res, tmp)
+    reference_substep(s)  # warm-up (first substep also pays first-touch allocation)
+    t0 = time.perf_counter()
+    n = 0
+    while n < 2 or (time.perf_counter() - t0 < budget_s and n < 12):
+        reference_substep(s)
+        n += 1
+    dt = time.perf_counter() - t0
+    scale = (res * res) / float(args.res * args.res)
+    out = {"value": n / dt * scale, "unit": UNIT, "cores": s.threads, "kind": "reference",
+           "sample": "%d substeps of the same scene at %dx%d (%.1f s, %.0f ms/substep), rate x %.4f (cell ratio) to express it "
+                     "at %dx%d; unmodified reference sources, flags -O3 -mavx2 -ffast-math, ThreadPool = all host threads"
+                     % (n, res, res, dt, dt / n * 1e3, scale, args.res, args.res)}
+    s.close()
+    return out
+
+
+# --------------------------------------------------------------------------------------- our arm
+def run_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from flipsolver2d_b200 import capi, host_api, scenes
+
+    if not torch.cuda.is_available() or capi.lib().fs2d_device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    tmp = tempfile.mkdtemp(prefix="fs2d_bench_")
+    res = args.res
+    path = scenes.write_scene(scene_for(res), os.path.join(tmp, "scene_%d.json" % res))
+    solver = host_api.Solver(path, quiet=True, device=local_rank)
+    solver.prepare()  # frame-0 rasterisation + seeding + upload: set-up, not timed
+    dev = solver.device(num_properties=2)
+    N = solver.N
+    stream = torch.cuda.ExternalStream(capi.lib().fs2d_stream(dev.h), device=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        dev.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- resident run
+    for _ in range(max(args.warmup, 3)):
+        solver.step_substep()
+    dev.pcg_profile(True)
+    launches0 = solver.kernel_launches()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms = timed(solver.step_substep, args.steps)
+    clocks = sampler.summary()
+    launches = solver.kernel_launches() - launches0
+    prof_ms, prof_n = dev.pcg_profile_read()
+    dev.pcg_profile(False)
+    stats = solver.stats()
+    particles = solver.particle_count()
+
+    # ---- end to end: particle state crosses PCIe both ways every step
+    P = particles
+    K = 2
+    cap = int(P * 1.25) + 1024
+    pos = torch.empty((cap, 2), dtype=torch.float32).pin_memory()
+    vel = torch.empty((cap, 2), dtype=torch.float32).pin_memory()
+    props = torch.empty((K * cap,), dtype=torch.float32).pin_memory()
+    L = capi.lib()
+    state = {"n": P, "h2d": 0, "d2h": 0}
+
+    def download():
+        n = int(L.fs2d_particle_count(dev.h))
+        assert n <= cap
+        rc = L.fs2d_download_particles(dev.h, pos.data_ptr(), vel.data_ptr(), props.data_ptr())
+        assert rc == 0
+        state["n"] = n
+        state["d2h"] += n * (16 + 4 * K)
+
+    def e2e_step():
+        n = state["n"]
+        rc = L.fs2d_upload_particles(dev.h, n, pos.data_ptr(), vel.data_ptr(), props.data_ptr())
+        assert rc == 0
+        state["h2d"] += n * (16 + 4 * K)
+        solver.step_substep()
+        download()
+
+    download()
+    e2e_step()  # warm-up of the path
+    state["h2d"] = state["d2h"] = 0
+    e2e_steps = args.steps
+    e2e_ms = timed(e2e_step, e2e_steps)
+    e2e = {"value": world * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": state["h2d"] // e2e_steps,
+           "d2h_bytes_per_step": state["d2h"] // e2e_steps,
+           "what": "per step: fs2d_upload_particles from pinned host buffers, FlipSolver::stepSubstep, fs2d_download_particles"}
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (PCG K1: s = z + beta s, x += alpha s, q = A s, q.s)
+    peak, peak_src = measured_peak()
+    k1_bytes = 49 * N  # R z,s,x + W s,q,x (6 fp64 passes) + 1 B row info per cell
+    k2_bytes = 34 * N  # R r,q + W r,z (4 fp64 passes) + 2 B preconditioner info per cell
+    k1_ms = prof_ms[0] / max(int(prof_n[0]), 1)
+    k2_ms = prof_ms[1] / max(int(prof_n[1]), 1)
+    achieved = k1_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "pcgTileKernel<K1>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                "bytes_per_launch": k1_bytes, "avg_launch_ms": k1_ms, "launches_timed": int(prof_n[0]),
+                "k2": {"kernel": "pcgTileKernel<K2>", "bytes_per_launch": k2_bytes, "avg_launch_ms": k2_ms,
+                       "achieved": k2_bytes / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else 0.0},
+                "pcg_share_of_step": (prof_ms[0] + prof_ms[1]) / ms if ms > 0 else None}
+    base = cpu_baseline(args, tmp) if world == 1 and not args.no_cpu_baseline else None
+    line = {"metric": METRIC, "value": world * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(res), "cells": N, "particles": particles,
+                       "l2": "every PCG vector (%d MB) and the particle arrays exceed the 126 MB L2" % (N * 8 // 2 ** 20),
+                       "parallelism": "1 GPU" if world == 1 else "%d independent replicas (one scene per GPU)" % world,
+                       "pcg_iterations_last_frame": {"pressure": stats["pressure_iters"], "density": stats["density_iters"]}},
+            "roofline": roofline, "cpu_baseline": base, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--res", type=int, default=4096)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -90,6 +90,7 @@ def lib():
         "fs2d_upload_grid": (i32, [H, i32, vp, C.c_size_t]),
         "fs2d_download_grid": (i32, [H, i32, vp, C.c_size_t]),
         "fs2d_grid_device_ptr": (vp, [H, i32]),
+        "fs2d_clear_grid": (i32, [H, i32]),
         "fs2d_set_obstacles": (i32, [H, i32, vp]),
         "fs2d_set_sources": (i32, [H, i32, vp]),
         "fs2d_particle_count": (i64, [H]),
@@ -100,6 +101,8 @@ def lib():
         "fs2d_pcg_solve_device": (i32, [H, i32, f64]),
         "fs2d_pcg_last_iterations": (i32, [H, C.POINTER(i32)]),
         "fs2d_pcg_trace": (i32, [H, vp, i32, C.POINTER(i32)]),
+        "fs2d_pcg_profile": (i32, [H, i32]),
+        "fs2d_pcg_profile_read": (i32, [H, vp, vp]),
         "fs2d_spmv": (i32, [H, vp, vp]),
         "fs2d_precond_apply": (i32, [H, vp, vp]),
         "fs2d_download_matrix": (i32, [H, vp, vp, vp, vp]),
@@ -177,9 +180,23 @@ class Device:
             raise Fs2dError("fs2d_create failed: %s (no CPU fallback exists)" % ERRORS.get(rc, rc))
         self.h = h
 
+    @classmethod
+    def borrow(cls, handle, size_i, size_j, num_properties=None):
+        """View of a handle owned by someone else (the C++ host solver)."""
+        d = cls.__new__(cls)
+        d.L = lib()
+        d.h = C.c_void_p(handle)
+        d.I, d.J = size_i, size_j
+        d.N = size_i * size_j
+        d.K = num_properties
+        d.params = None
+        d._borrowed = True
+        return d
+
     def close(self):
         if getattr(self, "h", None):
-            self.L.fs2d_destroy(self.h)
+            if not getattr(self, "_borrowed", False):
+                self.L.fs2d_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -257,6 +274,15 @@ class Device:
         n = C.c_int(0)
         self._ck(self.L.fs2d_pcg_trace(self.h, _p(buf), max_iterations, C.byref(n)), "pcg_trace")
         return buf[: n.value]
+
+    def pcg_profile(self, enable=True):
+        self._ck(self.L.fs2d_pcg_profile(self.h, 1 if enable else 0), "pcg_profile")
+
+    def pcg_profile_read(self):
+        ms = np.zeros(2, np.float64)
+        n = np.zeros(2, np.int64)
+        self._ck(self.L.fs2d_pcg_profile_read(self.h, _p(ms), _p(n)), "pcg_profile_read")
+        return ms, n
 
     def spmv(self, x):
         x = np.ascontiguousarray(x, np.float64)

@@ -166,6 +166,7 @@ void freeAll(Ctx *c)
     }
     if (c->eventsReady)
         for (int k = 0; k < 16; k++) cudaEventDestroy(c->ev[k]);
+    for (cudaEvent_t e : c->profEvents) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
 }
 }  // namespace
@@ -281,6 +282,19 @@ int fs2d_download_grid(fs2d_handle ctx, int grid, void *host_data, size_t bytes)
     }
     FS2D_CUDA(cudaMemcpyAsync(host_data, *d.ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FS2D_OK;
+}
+
+int fs2d_clear_grid(fs2d_handle ctx, int grid)
+{
+    if (!ctx) return FS2D_ERR_ARG;
+    GridDesc d = gridDesc(ctx, grid);
+    if (!d.ptr || !*d.ptr)
+    {
+        ctx->lastError = "fs2d_clear_grid: unknown grid";
+        return FS2D_ERR_ARG;
+    }
+    FS2D_CUDA(cudaMemsetAsync(*d.ptr, 0, static_cast<size_t>(d.count) * d.elemSize, ctx->stream));
     return FS2D_OK;
 }
 
@@ -423,6 +437,26 @@ int fs2d_pcg_trace(fs2d_handle ctx, double *host_trace, int max_iterations, int 
     int n = std::min({sc.iter, max_iterations, ctx->traceCapacity});
     if (n > 0) FS2D_CUDA(cudaMemcpy(host_trace, ctx->trace, sizeof(double) * 4 * n, cudaMemcpyDeviceToHost));
     if (written) *written = n;
+    return FS2D_OK;
+}
+
+int fs2d_pcg_profile(fs2d_handle ctx, int enable)
+{
+    if (!ctx) return FS2D_ERR_ARG;
+    ctx->profilePcg = enable != 0;
+    ctx->profMs[0] = ctx->profMs[1] = 0.0;
+    ctx->profLaunches[0] = ctx->profLaunches[1] = 0;
+    return FS2D_OK;
+}
+
+int fs2d_pcg_profile_read(fs2d_handle ctx, double *ms2, int64_t *launches2)
+{
+    if (!ctx || !ms2 || !launches2) return FS2D_ERR_ARG;
+    for (int k = 0; k < 2; k++)
+    {
+        ms2[k] = ctx->profMs[k];
+        launches2[k] = ctx->profLaunches[k];
+    }
     return FS2D_OK;
 }
 

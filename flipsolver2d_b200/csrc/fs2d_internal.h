@@ -115,6 +115,11 @@ struct fs2d_context
     int traceCapacity = 0;
     int64_t *rangeLast = nullptr;     // device, convergence_threads entries
     int lastPcgIters = 0;
+    // optional per-kernel timing of the PCG iteration kernels (fs2d_pcg_profile)
+    bool profilePcg = false;
+    std::vector<cudaEvent_t> profEvents;
+    double profMs[2] = {0.0, 0.0};        // accumulated device time of K1 / K2 launches
+    int64_t profLaunches[2] = {0, 0};
 
     // ---- particles (double buffered for the sort)
     ParticleBuffers pb[2];

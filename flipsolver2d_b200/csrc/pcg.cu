@@ -491,10 +491,19 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
         return FS2D_ERR_ARG;
     }
 
+    const bool prof = ctx->profilePcg;
+    if (prof)
+        while (static_cast<int>(ctx->profEvents.size()) < 2 * iterLimit + 1)
+        {
+            cudaEvent_t e;
+            FS2D_CUDA(cudaEventCreate(&e));
+            ctx->profEvents.push_back(e);
+        }
     pcgInitKernel<<<flat, NT, 0, st>>>(ctx->rhs, ctx->x, ctx->r[0], ctx->z, ctx->s[0], ctx->N, ctx->partials, ctx->scalars);
     ctx->launches++;
     for (int i = 0; i < iterLimit; i++)
     {
+        if (prof) cudaEventRecord(ctx->profEvents[2 * i], st);
         PcgArgs k1 = a;
         k1.in0 = ctx->z;
         k1.in1 = ctx->s[i & 1];
@@ -502,6 +511,7 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
         k1.out1 = ctx->q;
         k1.x = ctx->x;
         pcgTileKernel<MODE_K1><<<blocks, NT, 0, st>>>(k1);
+        if (prof) cudaEventRecord(ctx->profEvents[2 * i + 1], st);
         PcgArgs k2 = a;
         k2.in0 = ctx->r[i & 1];
         k2.in1 = ctx->q;
@@ -516,10 +526,29 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
             ctx->launches++;
         }
     }
+    if (prof && iterLimit > 0) cudaEventRecord(ctx->profEvents[2 * iterLimit], st);
     pcgFinalizeKernel<<<flat, NT, 0, st>>>(ctx->x, ctx->s[0], ctx->s[1], ctx->N, ctx->scalars, iterLimit);
     pcgResultKernel<<<1, 1, 0, st>>>(ctx->scalars, iterLimit);
     ctx->launches += 2;
     FS2D_CUDA(cudaGetLastError());
+    if (prof && iterLimit > 0)
+    {
+        // only iterations that did work count (after convergence the kernels return at once)
+        PcgScalars sc;
+        FS2D_CUDA(cudaMemcpyAsync(&sc, ctx->scalars, sizeof(sc), cudaMemcpyDeviceToHost, st));
+        FS2D_CUDA(cudaStreamSynchronize(st));
+        const int executed = sc.iter < iterLimit ? sc.iter : iterLimit;
+        for (int i = 0; i < executed; i++)
+        {
+            float a1 = 0.f, a2 = 0.f;
+            cudaEventElapsedTime(&a1, ctx->profEvents[2 * i], ctx->profEvents[2 * i + 1]);
+            cudaEventElapsedTime(&a2, ctx->profEvents[2 * i + 1], ctx->profEvents[2 * i + 2]);
+            ctx->profMs[0] += a1;
+            ctx->profMs[1] += a2;
+        }
+        ctx->profLaunches[0] += executed;
+        ctx->profLaunches[1] += executed;
+    }
     return FS2D_OK;
 }
 

@@ -155,6 +155,8 @@ int64_t fs2d_grid_elements(fs2d_handle h, int grid);
 int fs2d_grid_element_size(int grid);
 int fs2d_upload_grid(fs2d_handle h, int grid, const void *host_data, size_t bytes);
 int fs2d_download_grid(fs2d_handle h, int grid, void *host_data, size_t bytes);
+/* Grid2d::fill(0) on the device (e.g. m_testGrid.fill(0.f) at the top of stepFrame, flipsolver2d.cpp:470). */
+int fs2d_clear_grid(fs2d_handle h, int grid);
 /* Device address of a grid (for callers that keep their own device buffers). */
 void *fs2d_grid_device_ptr(fs2d_handle h, int grid);
 
@@ -185,6 +187,12 @@ int fs2d_pcg_solve_device(fs2d_handle h, int iter_limit, double tol);
 int fs2d_pcg_last_iterations(fs2d_handle h, int *iters);
 /* Trace of the last solve: per executed iteration alpha, beta, sigma, err (4 doubles). */
 int fs2d_pcg_trace(fs2d_handle h, double *host_trace, int max_iterations, int *written);
+/* Measurement aid: when enabled, every solve brackets its two iteration kernels (K1 = search update +
+ * A*s + dot, K2 = residual update + M*r + dot + max) with CUDA events on the handle's stream;
+ * fs2d_pcg_profile_read returns the accumulated device ms and launch counts {K1, K2} of the iterations
+ * that did work since the last fs2d_pcg_profile call. */
+int fs2d_pcg_profile(fs2d_handle h, int enable);
+int fs2d_pcg_profile_read(fs2d_handle h, double *ms2, int64_t *launches2);
 /* IndexedPressureParameters::multiply (pressuredata.h:184-238) and
  * IndexedIPPCoefficients::multiply (PressureIPPCoeficients.h:79-132) alone, host vectors. */
 int fs2d_spmv(fs2d_handle h, const double *host_in, double *host_out);

@@ -1,0 +1,57 @@
+/* fs2d_host.h -- C view of libfs2d_host.so, the C++ host mirror of the reference's solver API
+ * (flipsolver2d_b200/host/: JsonSceneReader, FlipSolver, NBFlipSolver, FlipSmokeSolver,
+ * FlipFireSolver, SolverStats -- same class and method names as FlipSolver2dLib/flipsolver2d.h:183-278
+ * and Utils/jsonscenereader.h:16). C++ applications (AutoBench, a viewer) link the classes directly;
+ * this shim exists for callers without a C++ toolchain (bench.py, tests) and replaces exactly the calls
+ * AutoBench makes: loadJson -> stepFrame -> timeStats (AutoBench/benchmarkrunnerapplication.cpp:74-97).
+ */
+#ifndef FS2D_HOST_H
+#define FS2D_HOST_H
+
+#include "fs2d.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *fs2dh_solver;
+
+/* process-wide switches; call before fs2dh_load_scene */
+void fs2dh_set_quiet(int quiet);                      /* silence the per-substep stdout lines (flipsolver2d.cpp:491) */
+void fs2dh_set_device(int ordinal);                   /* CUDA device of solvers created afterwards */
+void fs2dh_set_convergence_threads(int threads);      /* fs2d_params.convergence_threads */
+
+fs2dh_solver fs2dh_load_scene(const char *json_path); /* JsonSceneReader::loadJson; NULL on failure */
+void fs2dh_destroy(fs2dh_solver s);
+const char *fs2dh_last_error(fs2dh_solver s);
+
+/* Host-only half of frame 0: rasterise the scene polygons (updateSinks/Sources/Solids/InitialFluid,
+ * flipsolver2d.cpp:502-590) and draw the seed particles (seedInitialFluid :682-707). No GPU needed. */
+int fs2dh_prepare_host(fs2dh_solver s);
+int64_t fs2dh_seed_count(fs2dh_solver s);
+int fs2dh_seed_particles(fs2dh_solver s, float *pos, float *vel, float *props);
+/* Host copy of a scene grid (MATERIAL, SOLID_SDF, FLUID_SDF, VISCOSITY, SOLID_ID, EMITTER_ID, DIVERGENCE_CONTROL). */
+int fs2dh_host_grid(fs2dh_solver s, int grid, void *out);
+int fs2dh_prepare(fs2dh_solver s);                    /* frame-0 init (firstFrameInit) without stepping */
+int fs2dh_step_frame(fs2dh_solver s);                 /* FlipSolver::stepFrame */
+/* One CFL substep of the current frame (the body of stepFrame's loop, flipsolver2d.cpp:476-497);
+ * *frame_finished = 1 when it completed the frame. */
+int fs2dh_step_substep(fs2dh_solver s, int *frame_finished);
+/* timings12: ms per SolverStage; misc5: frameTime ms, substeps, pressure/density/viscosity iterations */
+int fs2dh_get_stats(fs2dh_solver s, float *timings12, float *misc5);
+
+int fs2dh_size_i(fs2dh_solver s);
+int fs2dh_size_j(fs2dh_solver s);
+int fs2dh_sim_type(fs2dh_solver s);
+int fs2dh_frame_number(fs2dh_solver s);
+int64_t fs2dh_particle_count(fs2dh_solver s);
+int64_t fs2dh_kernel_launches(fs2dh_solver s);
+
+fs2d_handle fs2dh_device(fs2dh_solver s);             /* the fs2d handle behind the solver (state download) */
+int fs2dh_material(fs2dh_solver s, int8_t *out);      /* materialGrid().data() */
+int64_t fs2dh_bin_sizes(fs2dh_solver s, int32_t *out, int64_t capacity); /* markerParticles().bins()[k].size() */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FS2D_HOST_H */

@@ -87,3 +87,25 @@ def test_zero_rhs_and_iteration_count_compat(ref_mod, scene_dir):
     assert itd == itr
     rel = np.linalg.norm(xd - xr) / np.linalg.norm(xr)
     assert rel < 1e-7, rel
+
+
+def test_golden_matviz_system_through_cuda(ref_mod, scene_dir):
+    """The reference's own dumped pressure system (tests/golden, see test_oracle_golden.py) through the
+    CUDA operator and solver: A*vout == vin to the printed digits, PCG(vin) == vout."""
+    import os
+    from test_oracle_golden import GOLDEN, golden_material
+    g = np.load(GOLDEN)
+    I, J = (int(v) for v in g["size"])
+    d = capi.Device(I, J, dx=50.0 / 64, fluid_density=0.5, pcg_iter_limit=2000)
+    d.upload("MATERIAL", golden_material(g))
+    d.set_step_dt(1.0 / 30.0)
+    d.stage("build_matrix")
+    m = d.matrix()
+    idx = g["index"]
+    assert np.array_equal(np.nonzero(m["is_unit"])[0], idx)
+    assert np.abs(0.109227 * m["count"][idx] - g["diag"]).max() < 1e-5
+    assert np.abs(d.spmv(g["vout"]) - g["vin"]).max() < 1e-4
+    x, iters = d.pcg_solve(g["vin"], 2000, 1e-6)
+    assert iters < 2000
+    assert np.abs(x - g["vout"]).max() < 1e-3 * np.abs(g["vout"]).max()
+    d.close()
