@@ -97,6 +97,8 @@ def lib():
         "fs2d_upload_particles": (i32, [H, i64, vp, vp, vp]),
         "fs2d_download_particles": (i32, [H, vp, vp, vp]),
         "fs2d_append_particles": (i32, [H, i64, vp, vp, vp]),
+        "fs2d_set_particle_storage_bins": (i32, [H, vp]),
+        "fs2d_get_particle_storage_bins": (i32, [H, vp]),
         "fs2d_pcg_solve": (i32, [H, vp, vp, i32, f64, C.POINTER(i32)]),
         "fs2d_pcg_solve_device": (i32, [H, i32, f64]),
         "fs2d_pcg_last_iterations": (i32, [H, C.POINTER(i32)]),
@@ -244,6 +246,15 @@ class Device:
         props = None if props is None else np.ascontiguousarray(props, np.float32)
         fn = self.L.fs2d_append_particles if append else self.L.fs2d_upload_particles
         self._ck(fn(self.h, pos.shape[0], _p(pos), _p(vel), _p(props)), "upload_particles")
+
+    def set_storage_bins(self, bins):
+        b = np.ascontiguousarray(bins, np.int32)
+        self._ck(self.L.fs2d_set_particle_storage_bins(self.h, _p(b)), "set_storage_bins")
+
+    def storage_bins(self):
+        out = np.zeros(self.particle_count(), np.int32)
+        self._ck(self.L.fs2d_get_particle_storage_bins(self.h, _p(out)), "storage_bins")
+        return out
 
     def download_particles(self):
         n = self.particle_count()

@@ -163,6 +163,7 @@ void freeAll(Ctx *c)
         if (c->pb[b].vel) cudaFree(c->pb[b].vel);
         if (c->pb[b].props) cudaFree(c->pb[b].props);
         if (c->pb[b].key) cudaFree(c->pb[b].key);
+        if (c->pb[b].mis) cudaFree(c->pb[b].mis);
     }
     if (c->eventsReady)
         for (int k = 0; k < 16; k++) cudaEventDestroy(c->ev[k]);
@@ -373,6 +374,7 @@ int fs2d_append_particles(fs2d_handle ctx, int64_t count, const float *host_pos,
             FS2D_CUDA(cudaMemsetAsync(dst, 0, sizeof(float) * count, ctx->stream));
     }
     FS2D_CUDA(cudaMemsetAsync(ctx->dead + base, 0, count, ctx->stream));
+    FS2D_CUDA(cudaMemsetAsync(b.mis + base, FS2D_MIS_HOME, count, ctx->stream));  // filed in the bin of its position
     FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->count = base + count;
     ctx->sorted = false;
@@ -398,6 +400,16 @@ int fs2d_download_particles(fs2d_handle ctx, float *host_pos, float *host_vel, f
                                       sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
     FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
     return FS2D_OK;
+}
+
+int fs2d_set_particle_storage_bins(fs2d_handle h, const int32_t *host_bins)
+{
+    return (h && host_bins) ? particlesSetStorageBins(h, host_bins) : FS2D_ERR_ARG;
+}
+
+int fs2d_get_particle_storage_bins(fs2d_handle h, int32_t *host_bins)
+{
+    return (h && host_bins) ? particlesGetStorageBins(h, host_bins) : FS2D_ERR_ARG;
 }
 
 // ---------------------------------------------------------------- PCG

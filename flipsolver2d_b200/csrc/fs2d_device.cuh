@@ -34,6 +34,28 @@ __device__ __forceinline__ unsigned int nonsolidCount(const int8_t *__restrict__
            (matSolid(matAt(mat, I, J, i, j - 1)) ? 0u : 1u) + (matSolid(matAt(mat, I, J, i, j + 1)) ? 0u : 1u);
 }
 
+// Bin of a position: gridToBinIdx(Vec3) truncates the coordinates to ssize_t, then divides by the bin
+// size 3 (markerparticlesystem.cpp:97-102,146-159).
+__device__ __forceinline__ int2 positionBin(float2 p) { return make_int2(static_cast<int>(p.x) / 3, static_cast<int>(p.y) / 3); }
+
+// Is a particle with storage code `mis` among the particles the reference visits for cell (ci, cj), i.e.
+// is its storage bin inside the 3x3 block of bins around the cell's bin (binsForGridCell,
+// markerparticlesystem.cpp:109-128)?
+__device__ __forceinline__ bool storageVisible(unsigned int mis, float2 p, int ci, int cj)
+{
+    if (mis == FS2D_MIS_LOST) return false;
+    const int2 pb = positionBin(p);
+    const int di = pb.x + static_cast<int>(mis / 5u) - 2 - ci / 3;
+    const int dj = pb.y + static_cast<int>(mis % 5u) - 2 - cj / 3;
+    return di >= -1 && di <= 1 && dj >= -1 && dj <= 1;
+}
+
+__device__ __forceinline__ unsigned int storageCode(int di, int dj)
+{
+    if (di < -2 || di > 2 || dj < -2 || dj > 2) return FS2D_MIS_LOST;
+    return static_cast<unsigned int>((di + 2) * 5 + (dj + 2));
+}
+
 // A float grid with the reference's out-of-bounds policy and sample offset.
 struct GridView
 {

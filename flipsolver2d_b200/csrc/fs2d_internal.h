@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -48,6 +49,14 @@ __host__ __device__ inline bool matSink(int8_t m) { return m == 0x12; }
 // PressureIPPCoeficients.h:8-48): bit 15 = row exists, then four 3-bit fields with
 // nonsolidNeighborCount of the iNeg, iPos, jNeg, jPos neighbour (bits 0-2, 3-5, 6-8, 9-11).
 #define FS2D_PRE_UNIT 0x8000u
+// Storage-bin code of a particle. The reference files a particle in a 3x3-cell bin and re-files it only
+// when ADVECTION moves it to another bin (flipsolver2d.cpp:317-336); the density correction moves
+// particles without re-filing them (:427), so a particle can sit in a bin that is not the bin of its
+// position. Gathers only see a particle through its storage bin and countParticles only counts
+// particles filed in the cell's own bin, so the offset (storage bin - position bin) per axis is kept:
+// code = (di+2)*5 + (dj+2); 12 = filed where it is; 255 = further than two bins away.
+#define FS2D_MIS_HOME 12
+#define FS2D_MIS_LOST 255
 
 struct PcgScalars
 {
@@ -72,6 +81,7 @@ struct ParticleBuffers
     float2 *vel = nullptr;
     float *props = nullptr;      // [numProps][capacity]
     uint32_t *key = nullptr;     // cell key at sort time
+    uint8_t *mis = nullptr;      // storage-bin offset code (FS2D_MIS_*), see particles.cu
     int64_t capacity = 0;
 };
 
@@ -116,6 +126,7 @@ struct fs2d_context
     int64_t *rangeLast = nullptr;     // device, convergence_threads entries
     int lastPcgIters = 0;
     // optional per-kernel timing of the PCG iteration kernels (fs2d_pcg_profile)
+    bool forceTileKernels = std::getenv("FS2D_PCG_TILE") != nullptr;  // A/B switch: plain tiled kernels
     bool profilePcg = false;
     std::vector<cudaEvent_t> profEvents;
     double profMs[2] = {0.0, 0.0};        // accumulated device time of K1 / K2 launches
@@ -172,6 +183,8 @@ int particlesReseedPlan(Ctx *ctx, int64_t *candidates);
 int particlesReseedApply(Ctx *ctx, int64_t candidates, const float *hostUniform);
 int particlesPruneNarrowBand(Ctx *ctx);
 int particlesAliveCount(Ctx *ctx, int64_t *out);
+int particlesSetStorageBins(Ctx *ctx, const int32_t *hostBins);
+int particlesGetStorageBins(Ctx *ctx, int32_t *hostBins);
 // transfer.cu
 int transferVelocity(Ctx *ctx);
 int transferCentered(Ctx *ctx);

@@ -201,9 +201,10 @@ __global__ void __launch_bounds__(NT) cellOrderKernel(const float2 *__restrict__
 __global__ void __launch_bounds__(NT) gatherKernel(const uint32_t *__restrict__ perm, long long alive,
                                                    const float2 *__restrict__ posIn, const float2 *__restrict__ velIn,
                                                    const float *__restrict__ propsIn, long long capIn,
-                                                   const uint32_t *__restrict__ keyIn, float2 *__restrict__ posOut,
-                                                   float2 *__restrict__ velOut, float *__restrict__ propsOut,
-                                                   long long capOut, uint32_t *__restrict__ keyOut, int numProps,
+                                                   const uint32_t *__restrict__ keyIn, const uint8_t *__restrict__ misIn,
+                                                   float2 *__restrict__ posOut, float2 *__restrict__ velOut,
+                                                   float *__restrict__ propsOut, long long capOut,
+                                                   uint32_t *__restrict__ keyOut, uint8_t *__restrict__ misOut, int numProps,
                                                    uint8_t *__restrict__ dead)
 {
     const long long s = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
@@ -212,6 +213,7 @@ __global__ void __launch_bounds__(NT) gatherKernel(const uint32_t *__restrict__ 
     posOut[s] = posIn[p];
     velOut[s] = velIn[p];
     keyOut[s] = keyIn[p];
+    misOut[s] = misIn[p];
     for (int k = 0; k < numProps; k++) propsOut[k * capOut + s] = propsIn[k * capIn + p];
     dead[s] = 0;
 }
@@ -273,13 +275,15 @@ __device__ float2 closestSurfacePoint(const GridView &sdf, float2 pos)
 }
 
 // advectThread (flipsolver2d.cpp:305-338)
-__global__ void __launch_bounds__(NT) advectKernel(float2 *__restrict__ pos, uint8_t *__restrict__ dead, long long count,
+__global__ void __launch_bounds__(NT) advectKernel(float2 *__restrict__ pos, uint8_t *__restrict__ dead,
+                                                   uint8_t *__restrict__ mis, long long count,
                                                    VelocityView vel, GridView solidSdf, const int8_t *__restrict__ mat,
                                                    int I, int J, float dt, unsigned long long *__restrict__ killed)
 {
     const long long p = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
     if (p >= count || dead[p]) return;
-    float2 x = rk4(vel, pos[p], dt);
+    const float2 before = pos[p];
+    float2 x = rk4(vel, before, dt);
     if (gridLerp(solidSdf, x.x, x.y) < 0.f) x = closestSurfacePoint(solidSdf, x);
     pos[p] = x;
     const float fi = floorf(x.x), fj = floorf(x.y);
@@ -288,7 +292,12 @@ __global__ void __launch_bounds__(NT) advectKernel(float2 *__restrict__ pos, uin
     {
         dead[p] = 1;
         atomicAdd(killed, 1ull);
+        return;
     }
+    // re-filed only when the bin of the POSITION changed (oldBinIdx is computed from the position, not
+    // from the bin the particle is stored in)
+    const int2 ob = positionBin(before), nb = positionBin(x);
+    if (ob.x != nb.x || ob.y != nb.y) mis[p] = FS2D_MIS_HOME;
 }
 
 // particleUpdate (flipsolver2d.cpp:361-388) + smoke decay (flipsmokesolver.cpp:104-130)
@@ -313,7 +322,7 @@ __global__ void __launch_bounds__(NT) particleUpdateKernel(const float2 *__restr
 
 // adjustParticlesByDensityThread (flipsolver2d.cpp:261-303)
 __global__ void __launch_bounds__(NT) densityAdjustKernel(float2 *__restrict__ pos, const uint8_t *__restrict__ dead,
-                                                          long long count, const double *__restrict__ pressure,
+                                                          uint8_t *__restrict__ mis, long long count, const double *__restrict__ pressure,
                                                           const int8_t *__restrict__ mat, int I, int J, float scale)
 {
     const long long p = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
@@ -334,26 +343,42 @@ __global__ void __launch_bounds__(NT) densityAdjustKernel(float2 *__restrict__ p
     float pI = P(iCorr + 1, j), pJ = P(i, jCorr + 1);
     if (matSolid(matAt(mat, I, J, iCorr + 1, j)) || matSolid(matAt(mat, I, J, iCorr, j))) pI = pCurI;
     if (matSolid(matAt(mat, I, J, i, jCorr + 1)) || matSolid(matAt(mat, I, J, i, jCorr))) pJ = pCurJ;
+    const int2 ob = positionBin(x);
     x.x = faddr(x.x, fmulr(fsubr(pI, pCurI), scale));
     x.y = faddr(x.y, fmulr(fsubr(pJ, pCurJ), scale));
     pos[p] = x;
+    // the particle stays filed where it was: keep (storage bin - position bin) up to date
+    const int2 nb = positionBin(x);
+    const unsigned int m = mis[p];
+    if ((ob.x != nb.x || ob.y != nb.y) && m != FS2D_MIS_LOST)
+        mis[p] = static_cast<uint8_t>(storageCode(static_cast<int>(m / 5u) - 2 + ob.x - nb.x, static_cast<int>(m % 5u) - 2 + ob.y - nb.y));
 }
 
 // countParticles (flipsolver2d.cpp:1021-1051): per-cell count, particles beyond 2*ppc die.
-__global__ void __launch_bounds__(NT) countCapKernel(const int32_t *__restrict__ cellStart, long long N, int cap,
-                                                     int32_t *__restrict__ counts, uint8_t *__restrict__ dead,
-                                                     unsigned long long *__restrict__ killed)
+__global__ void __launch_bounds__(NT) countCapKernel(const int32_t *__restrict__ cellStart, const uint8_t *__restrict__ mis,
+                                                     long long N, int cap, int32_t *__restrict__ counts,
+                                                     uint8_t *__restrict__ dead, unsigned long long *__restrict__ killed)
 {
     const long long c = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
     if (c >= N) return;
     const int32_t b = cellStart[c], e = cellStart[c + 1];
-    const int32_t n = e - b;
-    counts[c] = n < cap ? n : cap;
-    if (n > cap)
+    // only particles filed in this cell's own bin are seen by the reference's loop (binForGridIdx(i2d))
+    int32_t n = 0, over = 0;
+    for (int32_t s = b; s < e; s++)
     {
-        for (int32_t s = b + cap; s < e; s++) dead[s] = 1;
-        atomicAdd(killed, static_cast<unsigned long long>(n - cap));
+        if (mis[s] != FS2D_MIS_HOME) continue;
+        if (n >= cap)
+        {
+            dead[s] = 1;
+            over++;
+        }
+        else
+        {
+            n++;
+        }
     }
+    counts[c] = n;
+    if (over > 0) atomicAdd(killed, static_cast<unsigned long long>(over));
 }
 
 // pruneNarrowBand (nbflipsolver.cpp:227-253)
@@ -421,7 +446,8 @@ __global__ void __launch_bounds__(NT) reseedApplyKernel(const int32_t *__restric
                                                         GridView concentration, GridView fuel, ReseedArgs a,
                                                         float2 *__restrict__ pos, float2 *__restrict__ velOut,
                                                         float *__restrict__ props, long long cap, long long base,
-                                                        uint8_t *__restrict__ dead, unsigned long long *__restrict__ rejected)
+                                                        uint8_t *__restrict__ dead, uint8_t *__restrict__ mis,
+                                                        unsigned long long *__restrict__ rejected)
 {
     const long long c = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
     if (c >= N) return;
@@ -466,6 +492,7 @@ __global__ void __launch_bounds__(NT) reseedApplyKernel(const int32_t *__restric
         pos[slot] = x;
         velOut[slot] = v;
         dead[slot] = reject ? 1 : 0;
+        mis[slot] = FS2D_MIS_HOME;
         if (reject) atomicAdd(rejected, 1ull);
     }
 }
@@ -518,12 +545,15 @@ int particlesReserve(Ctx *ctx, int64_t capacity)
         FS2D_CUDA(cudaMalloc(reinterpret_cast<void **>(&nb.vel), sizeof(float2) * newCap));
         FS2D_CUDA(cudaMalloc(reinterpret_cast<void **>(&nb.props), sizeof(float) * newCap * std::max(K, 1)));
         FS2D_CUDA(cudaMalloc(reinterpret_cast<void **>(&nb.key), sizeof(uint32_t) * newCap));
+        FS2D_CUDA(cudaMalloc(reinterpret_cast<void **>(&nb.mis), newCap));
+        FS2D_CUDA(cudaMemset(nb.mis, FS2D_MIS_HOME, newCap));
         ParticleBuffers &ob = ctx->pb[b];
         if (b == ctx->cur && ctx->count > 0)
         {
             FS2D_CUDA(cudaMemcpy(nb.pos, ob.pos, sizeof(float2) * ctx->count, cudaMemcpyDeviceToDevice));
             FS2D_CUDA(cudaMemcpy(nb.vel, ob.vel, sizeof(float2) * ctx->count, cudaMemcpyDeviceToDevice));
             FS2D_CUDA(cudaMemcpy(nb.key, ob.key, sizeof(uint32_t) * ctx->count, cudaMemcpyDeviceToDevice));
+            FS2D_CUDA(cudaMemcpy(nb.mis, ob.mis, ctx->count, cudaMemcpyDeviceToDevice));
             for (int k = 0; k < K; k++)
                 FS2D_CUDA(cudaMemcpy(nb.props + k * newCap, ob.props + k * ob.capacity, sizeof(float) * ctx->count,
                                      cudaMemcpyDeviceToDevice));
@@ -532,6 +562,7 @@ int particlesReserve(Ctx *ctx, int64_t capacity)
         if (ob.vel) cudaFree(ob.vel);
         if (ob.props) cudaFree(ob.props);
         if (ob.key) cudaFree(ob.key);
+        if (ob.mis) cudaFree(ob.mis);
         ob = nb;
     }
     uint8_t *nd = nullptr;
@@ -577,7 +608,7 @@ int particlesMaxVelocity(Ctx *ctx, float *out)
 int particlesAdvect(Ctx *ctx)
 {
     if (ctx->count == 0) return FS2D_OK;
-    advectKernel<<<gridFor(ctx->count), NT, 0, ctx->stream>>>(ctx->pb[ctx->cur].pos, ctx->dead, ctx->count,
+    advectKernel<<<gridFor(ctx->count), NT, 0, ctx->stream>>>(ctx->pb[ctx->cur].pos, ctx->dead, ctx->pb[ctx->cur].mis, ctx->count,
                                                              makeVelocityView(ctx->U, ctx->V, ctx->I, ctx->J),
                                                              solidSdfView(ctx), ctx->material, ctx->I, ctx->J, ctx->stepDt,
                                                              reinterpret_cast<unsigned long long *>(ctx->d_counter));
@@ -613,8 +644,9 @@ int particlesSort(Ctx *ctx)
     FS2D_CUDA(cudaStreamSynchronize(st));
     if (alive > 0)
     {
-        gatherKernel<<<gridFor(alive), NT, 0, st>>>(ctx->perm, alive, in.pos, in.vel, in.props, in.capacity, in.key, out.pos,
-                                                    out.vel, out.props, out.capacity, out.key, ctx->p.num_properties, ctx->dead);
+        gatherKernel<<<gridFor(alive), NT, 0, st>>>(ctx->perm, alive, in.pos, in.vel, in.props, in.capacity, in.key, in.mis, out.pos,
+                                                    out.vel, out.props, out.capacity, out.key, out.mis, ctx->p.num_properties,
+                                                    ctx->dead);
         ctx->launches++;
     }
     FS2D_CUDA(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), st));
@@ -656,7 +688,7 @@ int particlesAdjustByDensity(Ctx *ctx)
     // (dt*dt) in float, denominator in double, result narrowed to float (flipsolver2d.cpp:263)
     const float scale = static_cast<float>(static_cast<double>(ctx->stepDt * ctx->stepDt) /
                                            (ctx->p.fluid_density * ctx->p.dx * ctx->p.dx));
-    densityAdjustKernel<<<gridFor(ctx->count), NT, 0, ctx->stream>>>(ctx->pb[ctx->cur].pos, ctx->dead, ctx->count, ctx->x,
+    densityAdjustKernel<<<gridFor(ctx->count), NT, 0, ctx->stream>>>(ctx->pb[ctx->cur].pos, ctx->dead, ctx->pb[ctx->cur].mis, ctx->count, ctx->x,
                                                                     ctx->material, ctx->I, ctx->J, scale);
     ctx->launches++;
     ctx->sorted = false;
@@ -667,8 +699,9 @@ int particlesAdjustByDensity(Ctx *ctx)
 int particlesCount(Ctx *ctx)
 {
     if (!ctx->sorted) FS2D_TRY(particlesSort(ctx));
-    countCapKernel<<<gridFor(ctx->N), NT, 0, ctx->stream>>>(ctx->cellStart, ctx->N, 2 * ctx->p.particles_per_cell, ctx->counts,
-                                                           ctx->dead, reinterpret_cast<unsigned long long *>(ctx->d_counter));
+    countCapKernel<<<gridFor(ctx->N), NT, 0, ctx->stream>>>(ctx->cellStart, ctx->pb[ctx->cur].mis, ctx->N,
+                                                           2 * ctx->p.particles_per_cell, ctx->counts, ctx->dead,
+                                                           reinterpret_cast<unsigned long long *>(ctx->d_counter));
     ctx->launches++;
     ctx->killedDirty = true;
     FS2D_CUDA(cudaGetLastError());
@@ -740,7 +773,7 @@ int particlesReseedApply(Ctx *ctx, int64_t candidates, const float *hostUniform)
         ctx->reseedOffset, ctx->N, du, ctx->material, ctx->emitterId, ctx->sources,
         makeVelocityView(ctx->U, ctx->V, ctx->I, ctx->J), fluidSdfView(ctx), viscosityView(ctx),
         smoke ? temperatureView(ctx) : none, smoke ? concentrationView(ctx) : none,
-        ctx->p.sim_type == FS2D_SIM_FIRE ? fuelView(ctx) : none, a, b.pos, b.vel, b.props, b.capacity, ctx->count, ctx->dead,
+        ctx->p.sim_type == FS2D_SIM_FIRE ? fuelView(ctx) : none, a, b.pos, b.vel, b.props, b.capacity, ctx->count, ctx->dead, b.mis,
         reinterpret_cast<unsigned long long *>(ctx->d_counter));
     ctx->launches++;
     FS2D_CUDA(cudaGetLastError());
@@ -750,5 +783,51 @@ int particlesReseedApply(Ctx *ctx, int64_t candidates, const float *hostUniform)
     ctx->killedDirty = true;
     ctx->sorted = false;
     ctx->reseedCandidates = 0;
+    return FS2D_OK;
+}
+
+namespace
+{
+__global__ void __launch_bounds__(NT) setStorageBinsKernel(const float2 *__restrict__ pos, const int32_t *__restrict__ bins,
+                                                           long long count, int binsJ, uint8_t *__restrict__ mis)
+{
+    const long long p = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    if (p >= count) return;
+    const int2 pb = positionBin(pos[p]);
+    const int sb = bins[p];
+    mis[p] = static_cast<uint8_t>(storageCode(sb / binsJ - pb.x, sb % binsJ - pb.y));
+}
+
+__global__ void __launch_bounds__(NT) getStorageBinsKernel(const float2 *__restrict__ pos, const uint8_t *__restrict__ mis,
+                                                           long long count, int binsJ, int32_t *__restrict__ bins)
+{
+    const long long p = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    if (p >= count) return;
+    const int2 pb = positionBin(pos[p]);
+    const unsigned int m = mis[p];
+    bins[p] = m == FS2D_MIS_LOST ? -1 : (pb.x + static_cast<int>(m / 5u) - 2) * binsJ + pb.y + static_cast<int>(m % 5u) - 2;
+}
+}  // namespace
+
+// Storage bin (linear index in the ceil(I/3) x ceil(J/3) bin grid) of every particle, in device order.
+int particlesSetStorageBins(Ctx *ctx, const int32_t *hostBins)
+{
+    if (ctx->count == 0) return FS2D_OK;
+    FS2D_CUDA(cudaMemcpyAsync(ctx->perm, hostBins, sizeof(int32_t) * ctx->count, cudaMemcpyHostToDevice, ctx->stream));
+    setStorageBinsKernel<<<gridFor(ctx->count), NT, 0, ctx->stream>>>(ctx->pb[ctx->cur].pos, reinterpret_cast<const int32_t *>(ctx->perm),
+                                                                     ctx->count, (ctx->J + 2) / 3, ctx->pb[ctx->cur].mis);
+    ctx->launches++;
+    FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FS2D_OK;
+}
+
+int particlesGetStorageBins(Ctx *ctx, int32_t *hostBins)
+{
+    if (ctx->count == 0) return FS2D_OK;
+    getStorageBinsKernel<<<gridFor(ctx->count), NT, 0, ctx->stream>>>(ctx->pb[ctx->cur].pos, ctx->pb[ctx->cur].mis, ctx->count,
+                                                                     (ctx->J + 2) / 3, reinterpret_cast<int32_t *>(ctx->perm));
+    ctx->launches++;
+    FS2D_CUDA(cudaMemcpyAsync(hostBins, ctx->perm, sizeof(int32_t) * ctx->count, cudaMemcpyDeviceToHost, ctx->stream));
+    FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
     return FS2D_OK;
 }

@@ -19,6 +19,8 @@
 // operators never re-read HBM. Vectors stay fp64 like the reference's std::vector<double>
 // (linearsolver.h:15-20); arithmetic uses explicit non-contracted mul/add in the reference's
 // evaluation order so a single operator application is bit-identical to the strict oracle.
+#include <algorithm>
+
 #include "fs2d_internal.h"
 
 namespace
@@ -123,6 +125,73 @@ __device__ __forceinline__ double rowM(uint16_t info, const double *pre, double 
     acc = __dadd_rn(acc, __dmul_rn(iNeg, im));
     acc = __dadd_rn(acc, __dmul_rn(iPos, ip));
     return acc;
+}
+
+
+// Per-CTA partial sums -> the last CTA to arrive reduces them in a fixed order and updates the
+// device-resident scalars (alpha after K1; sigma', err, convergence decision and beta after K2).
+template <int MODE>
+__device__ void finishReductions(const PcgArgs &a, double accDot, double accMax, double *red, int *isLastShared)
+{
+    const int tid = threadIdx.x;
+    const int nb = gridDim.x;
+    double bs = blockReduce<false>(accDot, red);
+    double bm = 0.0;
+    if (MODE == MODE_K2) bm = blockReduce<true>(accMax, red);
+    if (tid == 0)
+    {
+        a.partials[blockIdx.x] = bs;
+        if (MODE == MODE_K2) a.partials[nb + blockIdx.x] = bm;
+        __threadfence();
+        unsigned int *ticket = (MODE == MODE_K1) ? &a.sc->ticketA : &a.sc->ticketB;
+        *isLastShared = (atomicAdd(ticket, 1u) == static_cast<unsigned int>(nb - 1));
+    }
+    __syncthreads();
+    if (!*isLastShared) return;
+    __threadfence();
+    double total = finalReduce<false>(a.partials, nb, red);
+    double emax = 0.0;
+    if (MODE == MODE_K2) emax = finalReduce<true>(a.partials + nb, nb, red);
+    if (tid == 0)
+    {
+        PcgScalars *sc = a.sc;
+        if (MODE == MODE_K1)
+        {
+            sc->gamma = total;
+            sc->alpha = sc->sigma / (total + 1e-8);  // linearsolver.cpp:50
+            sc->ticketA = 0;
+        }
+        else
+        {
+            sc->ticketB = 0;
+            sc->gamma = total;  // sigma' parked until the decision
+            sc->err = emax;
+            if (!a.compat)
+            {
+                const int it = sc->iter;
+                double beta = 0.0;
+                if (emax <= a.tol)  // linearsolver.cpp:59-61
+                {
+                    sc->done = 1;
+                    sc->result = it;
+                }
+                else
+                {
+                    beta = total / sc->sigma;  // :66-67
+                    sc->beta = beta;
+                    sc->sigma = total;
+                }
+                if (a.trace && it < a.traceCapacity)
+                {
+                    a.trace[4 * it + 0] = sc->alpha;
+                    a.trace[4 * it + 1] = beta;
+                    a.trace[4 * it + 2] = total;
+                    a.trace[4 * it + 3] = emax;
+                }
+                sc->iter = it + 1;
+            }
+        }
+    }
 }
 
 template <int MODE> __global__ void __launch_bounds__(NT) pcgTileKernel(PcgArgs a)
@@ -239,64 +308,250 @@ template <int MODE> __global__ void __launch_bounds__(NT) pcgTileKernel(PcgArgs 
     if (MODE == MODE_APPLY_A || MODE == MODE_APPLY_M) return;
 
     // ---- reductions: per-CTA partials, finished by the last CTA in a fixed order
-    const int nb = gridDim.x;
-    double bs = blockReduce<false>(accDot, red);
-    double bm = 0.0;
-    if (MODE == MODE_K2) bm = blockReduce<true>(accMax, red);
-    if (tid == 0)
+    finishReductions<MODE>(a, accDot, accMax, red, &isLast);
+}
+
+
+// ------------------------------------------------------------------ pipelined iteration kernels
+// Same arithmetic as pcgTileKernel<K1/K2>, restructured for HBM throughput: a persistent grid (2 CTAs
+// per SM) walks the tiles; the raw input rows of the NEXT tile are fetched by the bulk-copy engine
+// (cp.async.bulk global->shared, completion on an mbarrier) while the threads compute the current one,
+// so bytes stay in flight during the stencil / store phases instead of only during a load phase.
+// Rows are fetched by LINEAR index (segment [gi*J + j0 - 2, +132) clipped to [0, N)), which keeps the
+// reference's wrap of the j = 0 / J-1 neighbours (pressuredata.h:135-145); needs J even for the 16-byte
+// alignment of the bulk copies (the host falls back to pcgTileKernel otherwise).
+constexpr int PSW = TC + 4;               // staged row: 2 pad + TC + 2 pad doubles (1056 B)
+constexpr int PROWS = TR + 2;
+constexpr int PTILE = PROWS * PSW;        // 2376 doubles per staged array
+constexpr int PSTAGES = 2;
+
+template <int MODE> struct PipeStage
+{
+    double a[PTILE];                      // K1: z -> s_new (in place)    K2: r -> r_new (in place)
+    double b[PTILE];                      // K1: s_old                    K2: q
+    double x[MODE == MODE_K1 ? TR * TC : 2];  // K1: x tile
+};
+
+template <int MODE> struct PipeSmem
+{
+    PipeStage<MODE> st[PSTAGES];
+    unsigned long long full[PSTAGES];
+    double red[8];
+    double preTbl[8];
+    int isLast;
+};
+
+__device__ __forceinline__ unsigned int smemAddr(const void *p) { return static_cast<unsigned int>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbarInit(unsigned long long *bar, unsigned int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbarArriveExpectTx(unsigned long long *bar, unsigned int bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbarWait(unsigned long long *bar, unsigned int parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "FS2D_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra FS2D_DONE;\n"
+        "bra FS2D_WAIT;\n"
+        "FS2D_DONE:\n"
+        "}\n" ::"r"(smemAddr(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ void bulkLoad(void *dstSmem, const void *srcGlobal, unsigned int bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(dstSmem)),
+                 "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void fenceProxyAsync() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Warp 0 fetches one tile: every lane owns whole rows. A row segment clipped by the ends of the vector is
+// zero-filled with ordinary stores (visible to the consumers through the __syncthreads that separates
+// the issue from the use of a stage).
+template <int MODE>
+__device__ __forceinline__ void pipeIssue(PipeStage<MODE> &st, unsigned long long *bar, const PcgArgs &a, int tile, int lane)
+{
+    const int ti = tile / a.tilesJ, tj = tile - ti * a.tilesJ;
+    const long long J = a.J, N = a.N;
+    const long long i0 = static_cast<long long>(ti) * TR, j0 = static_cast<long long>(tj) * TC;
+    // bytes this lane will request
+    unsigned int bytes = 0;
+    long long lo[2], hi[2];  // valid linear range of the (up to) two row kinds this lane handles
+    const int r = lane;      // PROWS = 18 <= 32: one halo-extended row per lane
+    long long segLo = 0, segHi = 0, xLo = 0, xHi = 0;
+    if (r < PROWS)
     {
-        a.partials[blockIdx.x] = bs;
-        if (MODE == MODE_K2) a.partials[nb + blockIdx.x] = bm;
-        __threadfence();
-        unsigned int *ticket = (MODE == MODE_K1) ? &a.sc->ticketA : &a.sc->ticketB;
-        isLast = (atomicAdd(ticket, 1u) == static_cast<unsigned int>(nb - 1));
-    }
-    __syncthreads();
-    if (!isLast) return;
-    __threadfence();
-    double total = finalReduce<false>(a.partials, nb, red);
-    double emax = 0.0;
-    if (MODE == MODE_K2) emax = finalReduce<true>(a.partials + nb, nb, red);
-    if (tid == 0)
-    {
-        PcgScalars *sc = a.sc;
-        if (MODE == MODE_K1)
+        const long long n0 = (i0 - 1 + r) * J + j0 - 2;
+        segLo = n0 < 0 ? 0 : n0;
+        segHi = n0 + PSW > N ? N : n0 + PSW;
+        if (segHi < segLo) segHi = segLo;
+        bytes += 2u * static_cast<unsigned int>(segHi - segLo) * 8u;
+        if (MODE == MODE_K1 && r >= 1 && r <= TR)
         {
-            sc->gamma = total;
-            sc->alpha = sc->sigma / (total + 1e-8);  // linearsolver.cpp:50
-            sc->ticketA = 0;
+            const long long m0 = (i0 - 1 + r) * J + j0;
+            xLo = m0 < 0 ? 0 : m0;
+            xHi = m0 + TC > N ? N : m0 + TC;
+            if (xHi < xLo) xHi = xLo;
+            bytes += static_cast<unsigned int>(xHi - xLo) * 8u;
         }
-        else
+    }
+    (void)lo;
+    (void)hi;
+    unsigned int total = bytes;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    if (lane == 0) mbarArriveExpectTx(bar, total);
+    __syncwarp();
+    if (r < PROWS)
+    {
+        const long long n0 = (i0 - 1 + r) * J + j0 - 2;
+        double *da = st.a + r * PSW, *db = st.b + r * PSW;
+        if (segHi - segLo < PSW)
         {
-            sc->ticketB = 0;
-            sc->gamma = total;  // sigma' parked until the decision
-            sc->err = emax;
-            if (!a.compat)
+            for (int c = 0; c < PSW; c++)
             {
-                const int it = sc->iter;
-                double beta = 0.0;
-                if (emax <= a.tol)  // linearsolver.cpp:59-61
+                const long long n = n0 + c;
+                if (n < segLo || n >= segHi)
                 {
-                    sc->done = 1;
-                    sc->result = it;
+                    da[c] = 0.0;
+                    db[c] = 0.0;
                 }
-                else
-                {
-                    beta = total / sc->sigma;  // :66-67
-                    sc->beta = beta;
-                    sc->sigma = total;
-                }
-                if (a.trace && it < a.traceCapacity)
-                {
-                    a.trace[4 * it + 0] = sc->alpha;
-                    a.trace[4 * it + 1] = beta;
-                    a.trace[4 * it + 2] = total;
-                    a.trace[4 * it + 3] = emax;
-                }
-                sc->iter = it + 1;
             }
         }
+        if (segHi > segLo)
+        {
+            const unsigned int nb = static_cast<unsigned int>(segHi - segLo) * 8u;
+            bulkLoad(da + (segLo - n0), a.in0 + segLo, nb, bar);
+            bulkLoad(db + (segLo - n0), a.in1 + segLo, nb, bar);
+        }
+        if (MODE == MODE_K1 && r >= 1 && r <= TR && xHi > xLo)
+        {
+            const long long m0 = (i0 - 1 + r) * J + j0;
+            bulkLoad(st.x + (r - 1) * TC + (xLo - m0), a.x + xLo, static_cast<unsigned int>(xHi - xLo) * 8u, bar);
+        }
     }
+}
+
+template <int MODE> __global__ void __launch_bounds__(NT, 2) pcgPipeKernel(PcgArgs a, int numTiles)
+{
+    extern __shared__ __align__(128) unsigned char pipeRaw[];
+    PipeSmem<MODE> &sm = *reinterpret_cast<PipeSmem<MODE> *>(pipeRaw);
+    if (a.sc->done) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (MODE == MODE_K2 && tid < 8) sm.preTbl[tid] = a.pre[tid];
+    if (tid == 0)
+    {
+#pragma unroll
+        for (int s = 0; s < PSTAGES; s++) mbarInit(&sm.full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fenceProxyAsync();
+    __syncthreads();
+
+    double coef = 0.0, alphaPrev = 0.0;
+    if (MODE == MODE_K1)
+    {
+        coef = a.sc->beta;
+        alphaPrev = a.sc->alpha;
+    }
+    else
+    {
+        coef = a.sc->alpha;
+    }
+    const long long J = a.J, N = a.N;
+    const int myTiles = (numTiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    if (warp == 0 && myTiles > 0) pipeIssue<MODE>(sm.st[0], &sm.full[0], a, blockIdx.x, lane);
+
+    double accDot = 0.0, accMax = 0.0;
+    const int bc = tid % TC, rg = tid / TC;  // stencil phase: one column, TR/2 rows per thread
+    for (int k = 0; k < myTiles; k++)
+    {
+        const int s = k & 1;
+        const unsigned int parity = static_cast<unsigned int>(k >> 1) & 1u;
+        const int tile = blockIdx.x + k * gridDim.x;
+        if (warp == 0 && k + 1 < myTiles) pipeIssue<MODE>(sm.st[s ^ 1], &sm.full[s ^ 1], a, tile + gridDim.x, lane);
+        const int ti = tile / a.tilesJ, tj = tile - ti * a.tilesJ;
+        const int i0 = ti * TR, j0 = tj * TC;
+        PipeStage<MODE> &st = sm.st[s];
+
+        // row info of this thread's cells: issued before the wait so the latency overlaps it
+        const long long gj = j0 + bc;
+        unsigned int info[TR / 2];
+#pragma unroll
+        for (int q = 0; q < TR / 2; q++)
+        {
+            const long long gi = i0 + rg * (TR / 2) + q;
+            info[q] = 0;
+            if (gi < a.I && gj < J)
+            {
+                const long long n = gi * J + gj;
+                info[q] = (MODE == MODE_K1) ? static_cast<unsigned int>(a.rowInfo[n]) : static_cast<unsigned int>(a.preInfo[n]);
+            }
+        }
+
+        mbarWait(&sm.full[s], parity);
+
+        // ---- phase 1: derived vector in place, interior written back (and x advanced in K1)
+        for (int e = tid; e < PTILE; e += NT)
+        {
+            const int ar = e / PSW, c = e - ar * PSW;
+            const double av = st.a[e], bv = st.b[e];
+            double v;
+            if (MODE == MODE_K1)
+                v = __dadd_rn(av, __dmul_rn(bv, coef));
+            else
+                v = __dsub_rn(av, __dmul_rn(bv, coef));
+            st.a[e] = v;
+            const long long gi = i0 - 1 + ar, gjj = j0 - 2 + c;
+            if (ar >= 1 && ar <= TR && c >= 2 && c < TC + 2 && gi < a.I && gjj < J)
+            {
+                const long long n = gi * J + gjj;
+                a.out0[n] = v;
+                if (MODE == MODE_K1) a.x[n] = __dadd_rn(st.x[(ar - 1) * TC + (c - 2)], __dmul_rn(bv, alphaPrev));
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 2: 5-point operator on the staged derived vector
+        if (gj < J)
+        {
+#pragma unroll
+            for (int q = 0; q < TR / 2; q++)
+            {
+                const int ar = 1 + rg * (TR / 2) + q;
+                const long long gi = i0 - 1 + ar;
+                if (gi < a.I)
+                {
+                    const long long n = gi * J + gj;
+                    const double *t = st.a + ar * PSW + bc + 2;
+                    const double c = t[0], im = t[-PSW], ip = t[PSW], jm = t[-1], jp = t[1];
+                    double o;
+                    if (MODE == MODE_K1)
+                        o = rowA(static_cast<uint8_t>(info[q]), a.scale, c, im, ip, jm, jp);
+                    else
+                        o = rowM(static_cast<uint16_t>(info[q]), sm.preTbl, c, im, ip, jm, jp);
+                    a.out1[n] = o;
+                    accDot += o * c;
+                    accMax = fmax(accMax, fabs(c));
+                }
+            }
+        }
+        fenceProxyAsync();   // generic writes to this stage are ordered before the next bulk copy into it
+        __syncthreads();
+    }
+    finishReductions<MODE>(a, accDot, accMax, sm.red, &sm.isLast);
 }
 
 // Reference-compatible convergence value (vmath.cpp:100-136): for each ThreadPool range
@@ -472,9 +727,18 @@ PcgArgs baseArgs(Ctx *ctx)
 
 int pcgTileBlocks(const Ctx *ctx) { return divUp(ctx->I, TR) * divUp(ctx->J, TC); }
 
+static bool pipeUsable(const Ctx *ctx) { return (ctx->J % 2) == 0 && !ctx->forceTileKernels; }
+
 int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
 {
     const int blocks = pcgTileBlocks(ctx);
+    const bool pipe = pipeUsable(ctx);
+    const int pipeBlocks = std::min(blocks, 2 * ctx->smCount);
+    if (pipe)
+    {
+        cudaFuncSetAttribute(pcgPipeKernel<MODE_K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(PipeSmem<MODE_K1>)));
+        cudaFuncSetAttribute(pcgPipeKernel<MODE_K2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(PipeSmem<MODE_K2>)));
+    }
     const int flat = ctx->smCount * 8;
     if (blocks > ctx->maxBlocks || flat > ctx->maxBlocks)
     {
@@ -510,14 +774,20 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
         k1.out0 = ctx->s[(i + 1) & 1];
         k1.out1 = ctx->q;
         k1.x = ctx->x;
-        pcgTileKernel<MODE_K1><<<blocks, NT, 0, st>>>(k1);
+        if (pipe)
+            pcgPipeKernel<MODE_K1><<<pipeBlocks, NT, sizeof(PipeSmem<MODE_K1>), st>>>(k1, blocks);
+        else
+            pcgTileKernel<MODE_K1><<<blocks, NT, 0, st>>>(k1);
         if (prof) cudaEventRecord(ctx->profEvents[2 * i + 1], st);
         PcgArgs k2 = a;
         k2.in0 = ctx->r[i & 1];
         k2.in1 = ctx->q;
         k2.out0 = ctx->r[(i + 1) & 1];
         k2.out1 = ctx->z;
-        pcgTileKernel<MODE_K2><<<blocks, NT, 0, st>>>(k2);
+        if (pipe)
+            pcgPipeKernel<MODE_K2><<<pipeBlocks, NT, sizeof(PipeSmem<MODE_K2>), st>>>(k2, blocks);
+        else
+            pcgTileKernel<MODE_K2><<<blocks, NT, 0, st>>>(k2);
         ctx->launches += 2;
         if (T > 0)
         {

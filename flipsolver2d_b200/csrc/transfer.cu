@@ -31,6 +31,7 @@ struct TileStage
 {
     float2 pos[STAGE];
     float2 pay[STAGE];          // velocity, or (property, unused)
+    unsigned char mis[STAGE];   // storage-bin code (FS2D_MIS_*)
     int rowBegin[TI + 4];       // global particle index where each staged row starts
     int rowOffset[TI + 5];      // offset of each staged row inside pos/pay
 };
@@ -40,8 +41,8 @@ constexpr size_t STAGE_BYTES = sizeof(TileStage);  // 96 KB + row tables: dynami
 // particle arrays. Returns false (for the whole CTA) when the records do not fit.
 template <bool WITH_PAYLOAD2>
 __device__ bool stageTile(TileStage &s, const int32_t *__restrict__ cellStart, const float2 *__restrict__ pos,
-                          const float2 *__restrict__ pay2, const float *__restrict__ pay1, int I, int J, int i0, int j0,
-                          int haloLo, int haloHi)
+                          const float2 *__restrict__ pay2, const float *__restrict__ pay1, const uint8_t *__restrict__ mis, int I,
+                          int J, int i0, int j0, int haloLo, int haloHi)
 {
     const int rows = TI + haloLo + haloHi;
     __shared__ int total;
@@ -74,6 +75,7 @@ __device__ bool stageTile(TileStage &s, const int32_t *__restrict__ cellStart, c
         for (int k = threadIdx.x; k < n; k += NT)
         {
             s.pos[so + k] = pos[gb + k];
+            s.mis[so + k] = mis[gb + k];
             if (WITH_PAYLOAD2)
                 s.pay[so + k] = pay2[gb + k];
             else
@@ -88,26 +90,41 @@ __device__ bool stageTile(TileStage &s, const int32_t *__restrict__ cellStart, c
 template <bool WITH_PAYLOAD2, class F>
 __device__ __forceinline__ void forRowRange(const TileStage &s, bool staged, const int32_t *__restrict__ cellStart,
                                             const float2 *__restrict__ pos, const float2 *__restrict__ pay2,
-                                            const float *__restrict__ pay1, int J, int gi, int ja, int jb, int stagedRow, F f)
+                                            const float *__restrict__ pay1, const uint8_t *__restrict__ mis, int J, int gi,
+                                            int ja, int jb, int stagedRow, int ci, int cj, F f)
 {
     const int b = cellStart[static_cast<long long>(gi) * J + ja];
     const int e = cellStart[static_cast<long long>(gi) * J + jb + 1];
+    // A particle filed in the bin of its position is always inside the 3x3 bins of a cell whose kernel
+    // support reaches it; only re-filed-late particles (FS2D_MIS_*) need the explicit bin test.
     if (staged)
     {
         const int shift = s.rowOffset[stagedRow] - s.rowBegin[stagedRow];
-        for (int k = b; k < e; k++) f(s.pos[k + shift], s.pay[k + shift]);
+        for (int k = b; k < e; k++)
+        {
+            const unsigned int m = s.mis[k + shift];
+            const float2 p = s.pos[k + shift];
+            if (m != FS2D_MIS_HOME && !storageVisible(m, p, ci, cj)) continue;
+            f(p, s.pay[k + shift]);
+        }
     }
     else
     {
         for (int k = b; k < e; k++)
-            f(pos[k], WITH_PAYLOAD2 ? pay2[k] : make_float2(pay1 ? pay1[k] : 0.f, 0.f));
+        {
+            const unsigned int m = mis[k];
+            const float2 p = pos[k];
+            if (m != FS2D_MIS_HOME && !storageVisible(m, p, ci, cj)) continue;
+            f(p, WITH_PAYLOAD2 ? pay2[k] : make_float2(pay1 ? pay1[k] : 0.f, 0.f));
+        }
     }
 }
 
 // particleVelocityToGridThread (flipsolver2d.cpp:1329-1377). Cell (i,j) receives particles with
 // weightU > 1e-9 && weightV > 1e-9, i.e. floor(pos) within one cell of (i,j).
 __global__ void __launch_bounds__(NT) p2gVelocityKernel(const int32_t *__restrict__ cellStart, const float2 *__restrict__ pos,
-                                                        const float2 *__restrict__ vel, int I, int J, int tilesJ,
+                                                        const float2 *__restrict__ vel, const uint8_t *__restrict__ mis, int I,
+                                                        int J, int tilesJ,
                                                         float *__restrict__ U, float *__restrict__ V,
                                                         uint8_t *__restrict__ uValid, uint8_t *__restrict__ vValid)
 {
@@ -115,7 +132,7 @@ __global__ void __launch_bounds__(NT) p2gVelocityKernel(const int32_t *__restric
     TileStage &s = *reinterpret_cast<TileStage *>(stageRaw);
     const int ti = blockIdx.x / tilesJ, tj = blockIdx.x - ti * tilesJ;
     const int i0 = ti * TI, j0 = tj * TJ;
-    const bool staged = stageTile<true>(s, cellStart, pos, vel, nullptr, I, J, i0, j0, 1, 1);
+    const bool staged = stageTile<true>(s, cellStart, pos, vel, nullptr, mis, I, J, i0, j0, 1, 1);
     const int li = threadIdx.x / TJ, lj = threadIdx.x - li * TJ;
     const int i = i0 + li, j = j0 + lj;
     if (i >= I || j >= J) return;
@@ -126,7 +143,7 @@ __global__ void __launch_bounds__(NT) p2gVelocityKernel(const int32_t *__restric
     const int ja = max(j - 1, 0), jb = min(j + 1, J - 1);
     for (int gi = max(i - 1, 0); gi <= min(i + 1, I - 1); gi++)
     {
-        forRowRange<true>(s, staged, cellStart, pos, vel, nullptr, J, gi, ja, jb, gi - (i0 - 1),
+        forRowRange<true>(s, staged, cellStart, pos, vel, nullptr, mis, J, gi, ja, jb, gi - (i0 - 1), i, j,
                           [&](float2 p, float2 v)
                           {
                               const float wU = quadraticBSpline(fsubr(p.x, ci), fsubr(p.y, cjh));
@@ -153,14 +170,15 @@ __global__ void __launch_bounds__(NT) p2gVelocityKernel(const int32_t *__restric
 // The support of B(px - i) spans cells i-2 .. i+1.
 template <int MODE>
 __global__ void __launch_bounds__(NT) p2gCenteredKernel(const int32_t *__restrict__ cellStart, const float2 *__restrict__ pos,
-                                                        const float *__restrict__ prop, int I, int J, int tilesJ,
+                                                        const float *__restrict__ prop, const uint8_t *__restrict__ mis, int I,
+                                                        int J, int tilesJ,
                                                         float *__restrict__ out, uint8_t *__restrict__ known)
 {
     extern __shared__ __align__(16) unsigned char stageRaw[];
     TileStage &s = *reinterpret_cast<TileStage *>(stageRaw);
     const int ti = blockIdx.x / tilesJ, tj = blockIdx.x - ti * tilesJ;
     const int i0 = ti * TI, j0 = tj * TJ;
-    const bool staged = stageTile<false>(s, cellStart, pos, nullptr, prop, I, J, i0, j0, 2, 1);
+    const bool staged = stageTile<false>(s, cellStart, pos, nullptr, prop, mis, I, J, i0, j0, 2, 1);
     const int li = threadIdx.x / TJ, lj = threadIdx.x - li * TJ;
     const int i = i0 + li, j = j0 + lj;
     if (i >= I || j >= J) return;
@@ -170,7 +188,7 @@ __global__ void __launch_bounds__(NT) p2gCenteredKernel(const int32_t *__restric
     const int ja = max(j - 2, 0), jb = min(j + 1, J - 1);
     for (int gi = max(i - 2, 0); gi <= min(i + 1, I - 1); gi++)
     {
-        forRowRange<false>(s, staged, cellStart, pos, nullptr, prop, J, gi, ja, jb, gi - (i0 - 2),
+        forRowRange<false>(s, staged, cellStart, pos, nullptr, prop, mis, J, gi, ja, jb, gi - (i0 - 2), i, j,
                            [&](float2 p, float2 v)
                            {
                                const float w = quadraticBSpline(fsubr(p.x, ci), fsubr(p.y, cj));
@@ -193,14 +211,15 @@ __global__ void __launch_bounds__(NT) p2gCenteredKernel(const int32_t *__restric
 
 // updateDensityGridThread (flipsolver2d.cpp:201-249)
 __global__ void __launch_bounds__(NT) densityKernel(const int32_t *__restrict__ cellStart, const float2 *__restrict__ pos,
-                                                    const int8_t *__restrict__ mat, int I, int J, int tilesJ, float particleMass,
+                                                    const uint8_t *__restrict__ mis, const int8_t *__restrict__ mat, int I, int J,
+                                                    int tilesJ, float particleMass,
                                                     float cellVolume, float restDensity, float *__restrict__ density)
 {
     extern __shared__ __align__(16) unsigned char stageRaw[];
     TileStage &s = *reinterpret_cast<TileStage *>(stageRaw);
     const int ti = blockIdx.x / tilesJ, tj = blockIdx.x - ti * tilesJ;
     const int i0 = ti * TI, j0 = tj * TJ;
-    const bool staged = stageTile<false>(s, cellStart, pos, nullptr, nullptr, I, J, i0, j0, 1, 1);
+    const bool staged = stageTile<false>(s, cellStart, pos, nullptr, nullptr, mis, I, J, i0, j0, 1, 1);
     const int li = threadIdx.x / TJ, lj = threadIdx.x - li * TJ;
     const int i = i0 + li, j = j0 + lj;
     if (i >= I || j >= J) return;
@@ -209,7 +228,7 @@ __global__ void __launch_bounds__(NT) densityKernel(const int32_t *__restrict__ 
     const int ja = max(j - 1, 0), jb = min(j + 1, J - 1);
     for (int gi = max(i - 1, 0); gi <= min(i + 1, I - 1); gi++)
     {
-        forRowRange<false>(s, staged, cellStart, pos, nullptr, nullptr, J, gi, ja, jb, gi - (i0 - 1),
+        forRowRange<false>(s, staged, cellStart, pos, nullptr, nullptr, mis, J, gi, ja, jb, gi - (i0 - 1), i, j,
                            [&](float2 p, float2)
                            {
                                const float w = bilinearHat(fsubr(fsubr(p.x, ci), 0.5f), fsubr(fsubr(p.y, cj), 0.5f));
@@ -224,36 +243,47 @@ __global__ void __launch_bounds__(NT) densityKernel(const int32_t *__restrict__ 
     density[static_cast<long long>(i) * J + j] = d;
 }
 
-// updateSdfThread (flipsolver2d.cpp:1276-1311): min squared distance to the particles of the 3x3
-// block of BINS around the cell's bin (rows/columns 3*(b-1) .. 3*(b+1)+2), minus the particle radius.
-// The minimum is order independent, so rows are visited outwards from the cell's own row and the walk
-// stops once no remaining row can hold a closer particle -- the value is identical to the full scan.
-__global__ void __launch_bounds__(256) sdfKernel(const int32_t *__restrict__ cellStart, const float2 *__restrict__ pos, int I,
-                                                 int J, float radius, float *__restrict__ sdf)
+// updateSdfThread (flipsolver2d.cpp:1276-1311): min squared distance to the particles FILED in the 3x3
+// block of bins around the cell's bin, minus the particle radius. The minimum is order independent, so
+// rows are visited outwards from the cell's own row and the walk stops once no remaining row can hold a
+// closer particle; columns are clipped the same way -- the value is identical to the full scan. A
+// particle can be filed one bin away from its position (FS2D_MIS_*), so positions are scanned over the
+// 5x5 bins around the cell and every candidate is tested against the reference's 3x3 bin window.
+__global__ void __launch_bounds__(256) sdfKernel(const int32_t *__restrict__ cellStart, const float2 *__restrict__ pos,
+                                                 const uint8_t *__restrict__ mis, int I, int J, float radius,
+                                                 float *__restrict__ sdf)
 {
     const long long n = blockIdx.x * 256ll + threadIdx.x;
     if (n >= static_cast<long long>(I) * J) return;
     const int i = static_cast<int>(n / J), j = static_cast<int>(n - static_cast<long long>(i) * J);
     const int bi = i / 3, bj = j / 3;
-    const int iLo = max(3 * (bi - 1), 0), iHi = min(3 * (bi + 1) + 2, I - 1);
-    const int jLo = max(3 * (bj - 1), 0), jHi = min(3 * (bj + 1) + 2, J - 1);
+    const int iLo = max(3 * (bi - 2), 0), iHi = min(3 * (bi + 2) + 2, I - 1);
+    const int jLo = max(3 * (bj - 2), 0), jHi = min(3 * (bj + 2) + 2, J - 1);
     const float cx = faddr(static_cast<float>(i), 0.5f), cy = faddr(static_cast<float>(j), 0.5f);
     float best = FLT_MAX;
     const int reach = max(i - iLo, iHi - i);
     for (int d = 0; d <= reach; d++)
     {
-        // every particle in a row at distance d is at least d - 1/2 away from the cell centre
+        // every particle in a row (column) at cell distance d is at least d - 1/2 away from the centre
         const float lower = static_cast<float>(d) - 0.5f;
         if (d > 0 && lower * lower >= best) break;
+        int ja = jLo, jb = jHi;
+        if (best < 64.f)
+        {
+            const int w = static_cast<int>(sqrtf(best) + 0.5f) + 1;
+            ja = max(jLo, j - w);
+            jb = min(jHi, j + w);
+        }
         for (int sgn = 0; sgn < (d == 0 ? 1 : 2); sgn++)
         {
             const int gi = sgn == 0 ? i - d : i + d;
             if (gi < iLo || gi > iHi) continue;
-            const int b = cellStart[static_cast<long long>(gi) * J + jLo];
-            const int e = cellStart[static_cast<long long>(gi) * J + jHi + 1];
+            const int b = cellStart[static_cast<long long>(gi) * J + ja];
+            const int e = cellStart[static_cast<long long>(gi) * J + jb + 1];
             for (int k = b; k < e; k++)
             {
                 const float2 p = pos[k];
+                if (!storageVisible(mis[k], p, i, j)) continue;
                 const float dx = fsubr(p.x, cx), dy = fsubr(p.y, cy);
                 const float d2 = faddr(fmulr(dx, dx), fmulr(dy, dy));
                 if (d2 < best) best = d2;
@@ -296,7 +326,7 @@ int transferVelocity(Ctx *ctx)
     const int tiles = tileCount(ctx, &tilesJ);
     ParticleBuffers &b = ctx->pb[ctx->cur];
     allowStage(p2gVelocityKernel);
-    p2gVelocityKernel<<<tiles, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, b.vel, ctx->I, ctx->J, tilesJ, ctx->U, ctx->V, ctx->uValid,
+    p2gVelocityKernel<<<tiles, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, b.vel, b.mis, ctx->I, ctx->J, tilesJ, ctx->U, ctx->V, ctx->uValid,
                                            ctx->vValid);
     ctx->launches++;
     FS2D_CUDA(cudaGetLastError());
@@ -319,19 +349,19 @@ int transferCentered(Ctx *ctx)
     switch (ctx->p.sim_type)
     {
     case FS2D_SIM_LIQUID:
-        p2gCenteredKernel<0><<<tiles, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, column(ctx->p.viscosity_property), ctx->I, ctx->J,
+        p2gCenteredKernel<0><<<tiles, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, column(ctx->p.viscosity_property), b.mis, ctx->I, ctx->J,
                                                    tilesJ, ctx->viscosity, ctx->knownCentered);
         ctx->launches++;
         break;
     case FS2D_SIM_NBFLIP:
-        p2gCenteredKernel<1><<<tiles, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, column(ctx->p.viscosity_property), ctx->I, ctx->J,
+        p2gCenteredKernel<1><<<tiles, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, column(ctx->p.viscosity_property), b.mis, ctx->I, ctx->J,
                                                    tilesJ, ctx->viscosity, ctx->knownCentered);
         ctx->launches++;
         break;
     default:  // smoke / fire: temperature and concentration (fire's fuel column has no P2G in the reference)
-        p2gCenteredKernel<1><<<tiles, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, column(ctx->p.temperature_property), ctx->I, ctx->J,
+        p2gCenteredKernel<1><<<tiles, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, column(ctx->p.temperature_property), b.mis, ctx->I, ctx->J,
                                                    tilesJ, ctx->temperature, ctx->knownCentered);
-        p2gCenteredKernel<1><<<tiles, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, column(ctx->p.concentration_property), ctx->I, ctx->J,
+        p2gCenteredKernel<1><<<tiles, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, column(ctx->p.concentration_property), b.mis, ctx->I, ctx->J,
                                                    tilesJ, ctx->concentration, nullptr);
         ctx->launches += 2;
         break;
@@ -350,7 +380,7 @@ int transferDensity(Ctx *ctx)
     const float particleMass =
         static_cast<float>((ctx->p.fluid_density * cellVolume) / static_cast<float>(ctx->p.particles_per_cell));
     allowStage(densityKernel);
-    densityKernel<<<tiles, NT, STAGE_BYTES, ctx->stream>>>(ctx->cellStart, ctx->pb[ctx->cur].pos, ctx->material, ctx->I, ctx->J, tilesJ,
+    densityKernel<<<tiles, NT, STAGE_BYTES, ctx->stream>>>(ctx->cellStart, ctx->pb[ctx->cur].pos, ctx->pb[ctx->cur].mis, ctx->material, ctx->I, ctx->J, tilesJ,
                                                 particleMass, cellVolume, static_cast<float>(ctx->p.fluid_density), ctx->density);
     ctx->launches++;
     FS2D_CUDA(cudaGetLastError());
@@ -360,7 +390,7 @@ int transferDensity(Ctx *ctx)
 int transferSdf(Ctx *ctx)
 {
     FS2D_TRY(ensureSorted(ctx));
-    sdfKernel<<<divUp(ctx->N, 256), 256, 0, ctx->stream>>>(ctx->cellStart, ctx->pb[ctx->cur].pos, ctx->I, ctx->J,
+    sdfKernel<<<divUp(ctx->N, 256), 256, 0, ctx->stream>>>(ctx->cellStart, ctx->pb[ctx->cur].pos, ctx->pb[ctx->cur].mis, ctx->I, ctx->J,
                                                           ctx->p.particle_scale, ctx->fluidSdf);
     ctx->launches++;
     FS2D_CUDA(cudaGetLastError());

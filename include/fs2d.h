@@ -171,6 +171,13 @@ int64_t fs2d_particle_count(fs2d_handle h);
 int fs2d_upload_particles(fs2d_handle h, int64_t count, const float *host_pos, const float *host_vel,
                           const float *host_props);
 int fs2d_download_particles(fs2d_handle h, float *host_pos, float *host_vel, float *host_props);
+/* The bin each particle is FILED in (linear index in the ceil(I/3) x ceil(J/3) ParticleBin grid,
+ * markerparticlesystem.cpp:12-13), in the order of the last upload / download. Uploads file every
+ * particle in the bin of its position (MarkerParticleSystem::binForGridPosition); the reference can
+ * hold particles elsewhere after a density correction (flipsolver2d.cpp:427) and its gathers and
+ * countParticles depend on it, so the state is settable. */
+int fs2d_set_particle_storage_bins(fs2d_handle h, const int32_t *host_bins);
+int fs2d_get_particle_storage_bins(fs2d_handle h, int32_t *host_bins);
 /* Append particles (seedInitialFluid / reseedParticles callers, flipsolver2d.cpp:627-707). */
 int fs2d_append_particles(fs2d_handle h, int64_t count, const float *host_pos, const float *host_vel,
                           const float *host_props);

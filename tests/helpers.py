@@ -84,8 +84,10 @@ def sync_state(s, d, sim="flip"):
             d.upload(g, s.grid(g))
     if sim == "fire":
         d.upload("FUEL", s.grid("FUEL"))
-    pos, vel, props, _ = s.particles()
+    pos, vel, props, bins = s.particles()
     d.upload_particles(pos, vel, props)
+    if len(pos):
+        d.set_storage_bins(bins)  # the reference may hold particles in a bin that is not their position's
     d.set_step_dt(s.params()["stepDt"])
 
 

@@ -6,6 +6,9 @@ import pytest
 from conftest import ORACLE_THREADS
 from flipsolver2d_b200 import capi, scenes
 
+import os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 pytestmark = pytest.mark.gpu
 
 
@@ -109,3 +112,39 @@ def test_golden_matviz_system_through_cuda(ref_mod, scene_dir):
     assert iters < 2000
     assert np.abs(x - g["vout"]).max() < 1e-3 * np.abs(g["vout"]).max()
     d.close()
+
+
+def test_iteration_count_compat_eight_threads(tmp_path):
+    """The reference's convergence value depends on its ThreadPool size (vmath.cpp:100-136); the suite
+    pins the oracle to one thread, so the T = 8 case runs in its own process."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import os, sys
+os.environ["FS2D_ORACLE_THREADS"] = "8"
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+import numpy as np
+from oracle import ref
+from flipsolver2d_b200 import capi, scenes
+path = scenes.write_scene(scenes.dam_break(256, "flip"), %r)
+s = ref.RefSolver(path, strict=True, threads=8)
+s.step_frame()
+s.set_step_dt(1.0 / 30.0)
+s.stage("BUILD_MATRIX")
+assert s.threads == 8
+p = s.params()
+d = capi.Device(s.I, s.J, dx=p["dx"], fluid_density=p["fluidDensity"], pcg_iter_limit=400, convergence_threads=8)
+d.upload("MATERIAL", s.grid("MATERIAL")); d.set_step_dt(p["stepDt"]); d.stage("build_matrix")
+rhs = s.pressure_rhs()
+xr, itr = s.pcg(rhs, 400, 1e-2)
+xd, itd = d.pcg_solve(rhs, 400, 1e-2)
+d1 = capi.Device(s.I, s.J, dx=p["dx"], fluid_density=p["fluidDensity"], pcg_iter_limit=400, convergence_threads=1)
+d1.upload("MATERIAL", s.grid("MATERIAL")); d1.set_step_dt(p["stepDt"]); d1.stage("build_matrix")
+_, it1 = d1.pcg_solve(rhs, 400, 1e-2)
+print("ITERS", itr, itd, it1, float(np.linalg.norm(xd - xr) / np.linalg.norm(xr)))
+assert itr < 400 and itd == itr
+""" % (ROOT, ROOT, str(tmp_path / "t8.json"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "ITERS" in r.stdout
