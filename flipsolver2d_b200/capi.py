@@ -103,6 +103,8 @@ def lib():
         "fs2d_pcg_solve_device": (i32, [H, i32, f64]),
         "fs2d_pcg_last_iterations": (i32, [H, C.POINTER(i32)]),
         "fs2d_pcg_trace": (i32, [H, vp, i32, C.POINTER(i32)]),
+        "fs2d_pcg_set_dense": (i32, [H, i32]),
+        "fs2d_pcg_active_cells": (i32, [H, C.POINTER(i64)]),
         "fs2d_pcg_profile": (i32, [H, i32]),
         "fs2d_pcg_profile_read": (i32, [H, vp, vp]),
         "fs2d_spmv": (i32, [H, vp, vp]),
@@ -285,6 +287,14 @@ class Device:
         n = C.c_int(0)
         self._ck(self.L.fs2d_pcg_trace(self.h, _p(buf), max_iterations, C.byref(n)), "pcg_trace")
         return buf[: n.value]
+
+    def pcg_set_dense(self, dense=True):
+        self._ck(self.L.fs2d_pcg_set_dense(self.h, 1 if dense else 0), "pcg_set_dense")
+
+    def pcg_active_cells(self):
+        n = C.c_int64(0)
+        self._ck(self.L.fs2d_pcg_active_cells(self.h, C.byref(n)), "pcg_active_cells")
+        return n.value
 
     def pcg_profile(self, enable=True):
         self._ck(self.L.fs2d_pcg_profile(self.h, 1 if enable else 0), "pcg_profile")

@@ -131,6 +131,9 @@ int allocAll(Ctx *ctx)
     ctx->maxBlocks = std::max({pcgTileBlocks(ctx), ctx->smCount * 8, ctx->p.convergence_threads, 1024});
     FS2D_TRY(devAlloc(ctx, &ctx->partials, 3 * static_cast<int64_t>(ctx->maxBlocks)));
     FS2D_TRY(devAlloc(ctx, &ctx->scalars, 1));
+    FS2D_TRY(devAlloc(ctx, &ctx->tileFlags, pcgTileBlocks(ctx)));
+    FS2D_TRY(devAlloc(ctx, &ctx->activeTiles, pcgTileBlocks(ctx)));
+    FS2D_TRY(devAlloc(ctx, &ctx->activeCount, 1));
     ctx->traceCapacity = std::max(ctx->p.pcg_iter_limit, 16) + 8;
     FS2D_TRY(devAlloc(ctx, &ctx->trace, 4 * static_cast<int64_t>(ctx->traceCapacity)));
 
@@ -154,7 +157,7 @@ void freeAll(Ctx *c)
                     c->advV, c->advSdf, c->advViscosity, c->scratchA, c->scratchB, c->scratchC, c->markers, c->rhs, c->x,
                     c->r[0], c->r[1], c->s[0], c->s[1], c->q, c->z, c->rowInfo, c->preInfo, c->partials, c->scalars,
                     c->trace, c->rangeLast, c->dead, c->perm, c->cellStart, c->cellCursor, c->scanBlock, c->d_counter,
-                    c->d_fscratch, c->obstacleFriction, c->sources, c->reseedOffset};
+                    c->d_fscratch, c->obstacleFriction, c->sources, c->reseedOffset, c->tileFlags, c->activeTiles, c->activeCount};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (int b = 0; b < 2; b++)
@@ -254,6 +257,7 @@ int fs2d_grid_element_size(int grid)
 void *fs2d_grid_device_ptr(fs2d_handle h, int grid)
 {
     if (!h) return nullptr;
+    if (grid == FS2D_GRID_FLUID_SDF && gridFlushSdf(h) != FS2D_OK) return nullptr;
     GridDesc d = gridDesc(h, grid);
     return d.ptr ? *d.ptr : nullptr;
 }
@@ -267,6 +271,7 @@ int fs2d_upload_grid(fs2d_handle ctx, int grid, const void *host_data, size_t by
         ctx->lastError = "fs2d_upload_grid: unknown grid or size mismatch";
         return FS2D_ERR_ARG;
     }
+    if (grid == FS2D_GRID_FLUID_SDF) ctx->sdfInsidePending = false;
     FS2D_CUDA(cudaMemcpyAsync(*d.ptr, host_data, bytes, cudaMemcpyHostToDevice, ctx->stream));
     FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
     return FS2D_OK;
@@ -281,6 +286,7 @@ int fs2d_download_grid(fs2d_handle ctx, int grid, void *host_data, size_t bytes)
         ctx->lastError = "fs2d_download_grid: unknown grid or size mismatch";
         return FS2D_ERR_ARG;
     }
+    if (grid == FS2D_GRID_FLUID_SDF) FS2D_TRY(gridFlushSdf(ctx));
     FS2D_CUDA(cudaMemcpyAsync(host_data, *d.ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
     return FS2D_OK;
@@ -449,6 +455,23 @@ int fs2d_pcg_trace(fs2d_handle ctx, double *host_trace, int max_iterations, int 
     int n = std::min({sc.iter, max_iterations, ctx->traceCapacity});
     if (n > 0) FS2D_CUDA(cudaMemcpy(host_trace, ctx->trace, sizeof(double) * 4 * n, cudaMemcpyDeviceToHost));
     if (written) *written = n;
+    return FS2D_OK;
+}
+
+int fs2d_pcg_set_dense(fs2d_handle ctx, int dense)
+{
+    if (!ctx) return FS2D_ERR_ARG;
+    ctx->densePcg = dense != 0;
+    return FS2D_OK;
+}
+
+int fs2d_pcg_active_cells(fs2d_handle ctx, int64_t *cells)
+{
+    if (!ctx || !cells) return FS2D_ERR_ARG;
+    int n = 0;
+    FS2D_CUDA(cudaMemcpyAsync(&n, ctx->activeCount, sizeof(n), cudaMemcpyDeviceToHost, ctx->stream));
+    FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
+    *cells = static_cast<int64_t>(n) * 16 * 128;
     return FS2D_OK;
 }
 

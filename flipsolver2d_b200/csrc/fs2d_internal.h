@@ -126,6 +126,8 @@ struct fs2d_context
     int64_t *rangeLast = nullptr;     // device, convergence_threads entries
     int lastPcgIters = 0;
     // optional per-kernel timing of the PCG iteration kernels (fs2d_pcg_profile)
+    bool densePcg = std::getenv("FS2D_PCG_DENSE") != nullptr;  // walk every tile, not only the active ones
+    int *tileFlags = nullptr, *activeTiles = nullptr, *activeCount = nullptr;
     bool forceTileKernels = std::getenv("FS2D_PCG_TILE") != nullptr;  // A/B switch: plain tiled kernels
     bool profilePcg = false;
     std::vector<cudaEvent_t> profEvents;
@@ -144,6 +146,8 @@ struct fs2d_context
     bool sorted = false;
     int64_t deadCount = 0;            // particles flagged dead since the last sort (host view)
     bool killedDirty = false;         // d_counter[0] holds kills not yet folded into deadCount
+    bool sdfInsidePending = false;    // extrapolateLevelsetInside deferred until the grid is read (grid_ops.cu)
+    bool eagerSdf = std::getenv("FS2D_EAGER_SDF") != nullptr;
     bool smokeGridsAdvected = false;  // temperature/concentration/fuel replaced by advected grids (App. A-13)
     int64_t *d_counter = nullptr;     // device scalar scratch (8 int64)
     float *d_fscratch = nullptr;      // device float scratch
@@ -196,6 +200,7 @@ int gridUpdateMaterials(Ctx *ctx);
 int gridAfterTransfer(Ctx *ctx);
 int gridExtrapolateVelocity(Ctx *ctx, int radius);
 int gridExtrapolateSdf(Ctx *ctx, bool inside);
+int gridFlushSdf(Ctx *ctx);
 int gridSaveVelocity(Ctx *ctx);
 int gridBodyForces(Ctx *ctx);
 int gridPressureRhs(Ctx *ctx);

@@ -107,14 +107,53 @@ __global__ void __launch_bounds__(NT) afterTransferKernel(const int8_t *__restri
 // (8-neighbour BFS distance from the valid samples) averages, in a double, the neighbours of
 // smaller layer in the reference's neighbour order (linearindexable2d.h:69-78). Those are final
 // before layer k starts, so one in-place sweep per layer reproduces the queue order exactly.
-__global__ void __launch_bounds__(NT) bfsInitKernel(const uint8_t *__restrict__ uValid, const uint8_t *__restrict__ vValid,
-                                                    long long NU, long long NV, uint8_t *__restrict__ marker)
+// Markers (0 = valid sample, 255 = unknown) and the bounding box {iMin, iMax, jMin, jMax} of the valid
+// samples of both grids: layers can only appear within radius+1 samples of it, so the layer sweeps are
+// restricted to that box instead of the whole grid.
+__global__ void __launch_bounds__(NT) bfsInitKernel(const uint8_t *__restrict__ uValid, const uint8_t *__restrict__ vValid, int I,
+                                                    int J, uint8_t *__restrict__ marker, int *__restrict__ bbox)
 {
+    const long long NU = static_cast<long long>(I + 1) * J, NV = static_cast<long long>(I) * (J + 1);
     const long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    int i = -1, j = -1;
     if (n < NU)
-        marker[n] = uValid[n] ? 0 : 255;
+    {
+        const bool v = uValid[n] != 0;
+        marker[n] = v ? 0 : 255;
+        if (v)
+        {
+            i = static_cast<int>(n / J);
+            j = static_cast<int>(n - static_cast<long long>(i) * J);
+        }
+    }
     else if (n < NU + NV)
-        marker[n] = vValid[n - NU] ? 0 : 255;
+    {
+        const long long m = n - NU;
+        const bool v = vValid[m] != 0;
+        marker[n] = v ? 0 : 255;
+        if (v)
+        {
+            i = static_cast<int>(m / (J + 1));
+            j = static_cast<int>(m - static_cast<long long>(i) * (J + 1));
+        }
+    }
+    // one atomic per warp and bound
+    int iMin = i < 0 ? 0x7fffffff : i, iMax = i, jMin = j < 0 ? 0x7fffffff : j, jMax = j;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        iMin = min(iMin, __shfl_xor_sync(0xffffffffu, iMin, o));
+        iMax = max(iMax, __shfl_xor_sync(0xffffffffu, iMax, o));
+        jMin = min(jMin, __shfl_xor_sync(0xffffffffu, jMin, o));
+        jMax = max(jMax, __shfl_xor_sync(0xffffffffu, jMax, o));
+    }
+    if ((threadIdx.x & 31) == 0 && iMax >= 0)
+    {
+        atomicMin(bbox + 0, iMin);
+        atomicMax(bbox + 1, iMax);
+        atomicMin(bbox + 2, jMin);
+        atomicMax(bbox + 3, jMax);
+    }
 }
 
 __device__ __forceinline__ void bfsLayerSample(float *__restrict__ g, uint8_t *__restrict__ valid, uint8_t *__restrict__ marker,
@@ -148,15 +187,25 @@ __device__ __forceinline__ void bfsLayerSample(float *__restrict__ g, uint8_t *_
     marker[n] = static_cast<uint8_t>(k);
 }
 
+// One layer over the box [i0, i0+h) x [j0, j0+w) of both sample grids (clipped to each grid's extent).
 __global__ void __launch_bounds__(NT) bfsLayerKernel(float *U, float *V, uint8_t *uValid, uint8_t *vValid, uint8_t *marker, int I,
-                                                     int J, int k)
+                                                     int J, int k, int i0, int j0, int h, int w)
 {
-    const long long NU = static_cast<long long>(I + 1) * J, NV = static_cast<long long>(I) * (J + 1);
-    const long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
-    if (n < NU)
-        bfsLayerSample(U, uValid, marker, I + 1, J, n, k);
-    else if (n < NU + NV)
-        bfsLayerSample(V, vValid, marker + NU, I, J + 1, n - NU, k);
+    const long long NU = static_cast<long long>(I + 1) * J;
+    const long long box = static_cast<long long>(h) * w;
+    const long long t = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    if (t >= 2 * box) return;
+    const bool second = t >= box;
+    const long long q = second ? t - box : t;
+    const int i = i0 + static_cast<int>(q / w), j = j0 + static_cast<int>(q % w);
+    if (!second)
+    {
+        if (i <= I && j < J) bfsLayerSample(U, uValid, marker, I + 1, J, static_cast<long long>(i) * J + j, k);
+    }
+    else if (i < I && j <= J)
+    {
+        bfsLayerSample(V, vValid, marker + NU, I, J + 1, static_cast<long long>(i) * (J + 1) + j, k);
+    }
 }
 
 // extrapolateLevelsetInside / Outside (flipsolver2d.cpp:1433-1558): same BFS with unbounded radius and
@@ -524,16 +573,53 @@ int gridAfterTransfer(Ctx *ctx)
 int gridExtrapolateVelocity(Ctx *ctx, int radius)
 {
     uint8_t *marker = reinterpret_cast<uint8_t *>(ctx->markers);
-    const int blocks = divUp(ctx->NU + ctx->NV, NT);
-    bfsInitKernel<<<blocks, NT, 0, ctx->stream>>>(ctx->uValid, ctx->vValid, ctx->NU, ctx->NV, marker);
+    cudaStream_t st = ctx->stream;
+    int *bbox = reinterpret_cast<int *>(ctx->d_counter) + 16;  // ints 16..19 of the scalar scratch
+    const int init[4] = {0x7fffffff, -1, 0x7fffffff, -1};
+    FS2D_CUDA(cudaMemcpyAsync(bbox, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    bfsInitKernel<<<divUp(ctx->NU + ctx->NV, NT), NT, 0, st>>>(ctx->uValid, ctx->vValid, ctx->I, ctx->J, marker, bbox);
+    ctx->launches++;
+    int box[4];
+    FS2D_CUDA(cudaMemcpyAsync(box, bbox, sizeof(box), cudaMemcpyDeviceToHost, st));
+    FS2D_CUDA(cudaStreamSynchronize(st));
+    if (box[1] < box[0]) return FS2D_OK;  // no valid sample anywhere: the BFS has no seed (mathfuncs.cpp:171-189)
+    const int grow = radius + 2;
+    const int i0 = std::max(box[0] - grow, 0), i1 = std::min(box[1] + grow, ctx->I);
+    const int j0 = std::max(box[2] - grow, 0), j1 = std::min(box[3] + grow, ctx->J);
+    const int h = i1 - i0 + 1, w = j1 - j0 + 1;
+    const int blocks = divUp(2ll * h * w, NT);
     for (int k = 1; k <= radius + 1; k++)
-        bfsLayerKernel<<<blocks, NT, 0, ctx->stream>>>(ctx->U, ctx->V, ctx->uValid, ctx->vValid, marker, ctx->I, ctx->J, k);
-    ctx->launches += radius + 2;
+        bfsLayerKernel<<<blocks, NT, 0, st>>>(ctx->U, ctx->V, ctx->uValid, ctx->vValid, marker, ctx->I, ctx->J, k, i0, j0, h, w);
+    ctx->launches += radius + 1;
     FS2D_CUDA(cudaGetLastError());
     return FS2D_OK;
 }
 
+int gridExtrapolateSdfNow(Ctx *ctx, bool inside);
+
+// extrapolateLevelsetInside only rewrites the level set BELOW the surface. Outside NBFlip nothing in the
+// substep reads those values (updateMaterials has already run, the next updateSdf overwrites them,
+// SURVEY section 7 "extrapolate-inside depth"), so the hundreds of dependent BFS layers are deferred until
+// somebody asks for the grid (fs2d_download_grid / fs2d_grid_device_ptr) -- same values, off the hot path.
+int gridFlushSdf(Ctx *ctx)
+{
+    if (!ctx->sdfInsidePending) return FS2D_OK;
+    ctx->sdfInsidePending = false;
+    return gridExtrapolateSdfNow(ctx, true);
+}
+
 int gridExtrapolateSdf(Ctx *ctx, bool inside)
+{
+    if (inside && ctx->p.sim_type != FS2D_SIM_NBFLIP && !ctx->eagerSdf)
+    {
+        ctx->sdfInsidePending = true;
+        return FS2D_OK;
+    }
+    FS2D_TRY(gridFlushSdf(ctx));
+    return gridExtrapolateSdfNow(ctx, inside);
+}
+
+int gridExtrapolateSdfNow(Ctx *ctx, bool inside)
 {
     cudaStream_t st = ctx->stream;
     int *bbox = reinterpret_cast<int *>(ctx->d_counter) + 8;  // 4 ints bbox + 3 ints flags

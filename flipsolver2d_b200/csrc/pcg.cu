@@ -52,6 +52,8 @@ struct PcgArgs
     int traceCapacity;
     double tol;
     int compat;               // 1: convergence decided by the range kernel
+    const int *activeTiles;   // ordered list of tiles that can hold non-zero entries (nullptr: all tiles)
+    const int *activeCount;
 };
 
 __device__ __forceinline__ double warpSum(double v)
@@ -470,9 +472,15 @@ template <int MODE> __global__ void __launch_bounds__(NT, 2) pcgPipeKernel(PcgAr
     {
         coef = a.sc->alpha;
     }
-    const long long J = a.J, N = a.N;
-    const int myTiles = (numTiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-    if (warp == 0 && myTiles > 0) pipeIssue<MODE>(sm.st[0], &sm.full[0], a, blockIdx.x, lane);
+    const long long J = a.J;
+    if (a.activeCount) numTiles = *a.activeCount;
+    int myTiles = (numTiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    if (myTiles < 0) myTiles = 0;
+    auto tileAt = [&](int k) -> int {
+        const int t = blockIdx.x + k * gridDim.x;
+        return a.activeTiles ? a.activeTiles[t] : t;
+    };
+    if (warp == 0 && myTiles > 0) pipeIssue<MODE>(sm.st[0], &sm.full[0], a, tileAt(0), lane);
 
     double accDot = 0.0, accMax = 0.0;
     const int bc = tid % TC, rg = tid / TC;  // stencil phase: one column, TR/2 rows per thread
@@ -480,8 +488,8 @@ template <int MODE> __global__ void __launch_bounds__(NT, 2) pcgPipeKernel(PcgAr
     {
         const int s = k & 1;
         const unsigned int parity = static_cast<unsigned int>(k >> 1) & 1u;
-        const int tile = blockIdx.x + k * gridDim.x;
-        if (warp == 0 && k + 1 < myTiles) pipeIssue<MODE>(sm.st[s ^ 1], &sm.full[s ^ 1], a, tile + gridDim.x, lane);
+        const int tile = tileAt(k);
+        if (warp == 0 && k + 1 < myTiles) pipeIssue<MODE>(sm.st[s ^ 1], &sm.full[s ^ 1], a, tileAt(k + 1), lane);
         const int ti = tile / a.tilesJ, tj = tile - ti * a.tilesJ;
         const int i0 = ti * TR, j0 = tj * TC;
         PipeStage<MODE> &st = sm.st[s];
@@ -632,10 +640,83 @@ __global__ void __launch_bounds__(NT) pcgRangeErrKernel(const double *r, long lo
     sc->iter = it + 1;
 }
 
+// ------------------------------------------------------------------ active tiles
+// A tile whose cells have no matrix row and a zero right-hand side stays identically zero in every PCG
+// vector for the whole solve (identity rows: q = s, z = r; r0 = rhs = 0), and contributes nothing to the
+// dot products or the max. Such tiles are skipped: the iteration kernels walk an ordered list of the
+// other ("active") tiles. Halo rows read from a skipped tile are the zeros pcgInitKernel put there.
+// In a dam-break scene ~9 % of the cells are fluid, so this removes ~90 % of the PCG traffic; the
+// iterates are the same numbers (only the grouping of the dot-product partials over CTAs changes).
+__global__ void __launch_bounds__(NT) pcgTileFlagKernel(const uint8_t *__restrict__ rowInfo, const double *__restrict__ rhs, int I, int J,
+                                                        int tilesJ, int *__restrict__ flags)
+{
+    __shared__ int any;
+    if (threadIdx.x == 0) any = 0;
+    __syncthreads();
+    const int ti = blockIdx.x / tilesJ, tj = blockIdx.x - ti * tilesJ;
+    const int i0 = ti * TR, j0 = tj * TC;
+    bool hit = false;
+    for (int e = threadIdx.x; e < TR * TC; e += NT)
+    {
+        const int i = i0 + e / TC, j = j0 + e % TC;
+        if (i < I && j < J)
+        {
+            const long long n = static_cast<long long>(i) * J + j;
+            if ((rowInfo[n] & FS2D_ROW_UNIT) || rhs[n] != 0.0) hit = true;
+        }
+    }
+    if (hit) any = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) flags[blockIdx.x] = any;
+}
+
+// Ordered compaction of the flagged tiles (a single CTA: there are only a few thousand tiles).
+__global__ void __launch_bounds__(1024) pcgTileCompactKernel(const int *__restrict__ flags, int tiles, int *__restrict__ list,
+                                                             int *__restrict__ count)
+{
+    __shared__ int warpSums[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < tiles; base += 1024)
+    {
+        const int idx = base + threadIdx.x;
+        const int v = idx < tiles ? flags[idx] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warpSums[warp] = incl;
+        __syncthreads();
+        if (warp == 0)
+        {
+            int w = warpSums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const int t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += t;
+            }
+            warpSums[lane] = w;
+        }
+        __syncthreads();
+        const int excl = incl - v + (warp > 0 ? warpSums[warp - 1] : 0) + carry;
+        if (v) list[excl] = idx;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = carry;
+}
+
 // result = 0; residual = aux = rhs; search = aux after the first K1 (linearsolver.cpp:32-46);
 // sigma = rhs.rhs; zero test of :33-35.
-__global__ void __launch_bounds__(NT) pcgInitKernel(const double *rhs, double *x, double *r0, double *z, double *s0,
-                                                    long long N, double *partials, PcgScalars *sc)
+__global__ void __launch_bounds__(NT) pcgInitKernel(const double *rhs, double *x, double *r0, double *z, double *s0, double *r1,
+                                                    double *s1, double *q, long long N, double *partials, PcgScalars *sc)
 {
     __shared__ double red[8];
     __shared__ int isLast;
@@ -647,6 +728,12 @@ __global__ void __launch_bounds__(NT) pcgInitKernel(const double *rhs, double *x
         r0[n] = v;
         z[n] = v;
         s0[n] = 0.0;
+        if (r1)  // active-tile mode: skipped tiles are never written again and must read as zero
+        {
+            r1[n] = 0.0;
+            s1[n] = 0.0;
+            q[n] = 0.0;
+        }
         acc += v * v;
         amax = fmax(amax, fabs(v));
     }
@@ -721,6 +808,8 @@ PcgArgs baseArgs(Ctx *ctx)
     a.traceCapacity = ctx->traceCapacity;
     a.tol = 0.0;
     a.compat = ctx->p.convergence_threads > 0 ? 1 : 0;
+    a.activeTiles = nullptr;
+    a.activeCount = nullptr;
     return a;
 }
 }  // namespace
@@ -763,8 +852,18 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
             FS2D_CUDA(cudaEventCreate(&e));
             ctx->profEvents.push_back(e);
         }
-    pcgInitKernel<<<flat, NT, 0, st>>>(ctx->rhs, ctx->x, ctx->r[0], ctx->z, ctx->s[0], ctx->N, ctx->partials, ctx->scalars);
+    const bool active = pipe && !ctx->densePcg;
+    pcgInitKernel<<<flat, NT, 0, st>>>(ctx->rhs, ctx->x, ctx->r[0], ctx->z, ctx->s[0], active ? ctx->r[1] : nullptr, ctx->s[1], ctx->q,
+                                       ctx->N, ctx->partials, ctx->scalars);
     ctx->launches++;
+    if (active)
+    {
+        pcgTileFlagKernel<<<blocks, NT, 0, st>>>(ctx->rowInfo, ctx->rhs, ctx->I, ctx->J, a.tilesJ, ctx->tileFlags);
+        pcgTileCompactKernel<<<1, 1024, 0, st>>>(ctx->tileFlags, blocks, ctx->activeTiles, ctx->activeCount);
+        ctx->launches += 2;
+        a.activeTiles = ctx->activeTiles;
+        a.activeCount = ctx->activeCount;
+    }
     for (int i = 0; i < iterLimit; i++)
     {
         if (prof) cudaEventRecord(ctx->profEvents[2 * i], st);

@@ -390,6 +390,7 @@ int transferDensity(Ctx *ctx)
 int transferSdf(Ctx *ctx)
 {
     FS2D_TRY(ensureSorted(ctx));
+    ctx->sdfInsidePending = false;  // the whole level set is rewritten below
     sdfKernel<<<divUp(ctx->N, 256), 256, 0, ctx->stream>>>(ctx->cellStart, ctx->pb[ctx->cur].pos, ctx->pb[ctx->cur].mis, ctx->I, ctx->J,
                                                           ctx->p.particle_scale, ctx->fluidSdf);
     ctx->launches++;

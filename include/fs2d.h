@@ -194,6 +194,12 @@ int fs2d_pcg_solve_device(fs2d_handle h, int iter_limit, double tol);
 int fs2d_pcg_last_iterations(fs2d_handle h, int *iters);
 /* Trace of the last solve: per executed iteration alpha, beta, sigma, err (4 doubles). */
 int fs2d_pcg_trace(fs2d_handle h, double *host_trace, int max_iterations, int *written);
+/* The iteration kernels skip 16x128-cell tiles that hold no matrix row and a zero right-hand side (every
+ * PCG vector is identically zero there for the whole solve). fs2d_pcg_set_dense(h, 1) makes them walk
+ * the whole grid instead (same iterates); fs2d_pcg_active_cells reports the cells covered by the tiles
+ * the last solve walked. */
+int fs2d_pcg_set_dense(fs2d_handle h, int dense);
+int fs2d_pcg_active_cells(fs2d_handle h, int64_t *cells);
 /* Measurement aid: when enabled, every solve brackets its two iteration kernels (K1 = search update +
  * A*s + dot, K2 = residual update + M*r + dot + max) with CUDA events on the handle's stream;
  * fs2d_pcg_profile_read returns the accumulated device ms and launch counts {K1, K2} of the iterations

@@ -77,6 +77,32 @@ def test_fixed_iteration_solve(ref_mod, scene_dir, res, frames, iters):
     assert rel < 1e-9, rel
 
 
+@pytest.mark.parametrize("res,frames,iters", [(256, 1, 40), (384, 0, 30)])
+def test_active_tile_walk_equals_dense_walk(ref_mod, scene_dir, res, frames, iters):
+    """The iteration kernels skip tiles without matrix rows and with a zero right-hand side; the iterate
+    must be the one the dense walk produces (only the grouping of the dot-product partials differs) and
+    fewer cells must be walked."""
+    s = _ref_system(ref_mod, scene_dir, res, frames=frames)
+    d = _device_for(s)
+    rng = np.random.default_rng(11)
+    unit = s.matrix()["is_unit"].astype(bool)
+    rhs = np.where(unit, rng.standard_normal(s.N), 0.0)
+    rhs[5 * s.J + 7] = 0.25  # a non-zero rhs on an identity row far from the fluid keeps its tile active
+    d.pcg_set_dense(False)
+    xa, ita = d.pcg_solve(rhs, iters, 0.0)
+    active = d.pcg_active_cells()
+    d.pcg_set_dense(True)
+    xd, itd = d.pcg_solve(rhs, iters, 0.0)
+    assert ita == itd == iters
+    assert 0 < active < s.N
+    assert np.linalg.norm(xa - xd) <= 1e-10 * np.linalg.norm(xd)
+    xr, _ = s.pcg(rhs, iters, 0.0)
+    assert np.linalg.norm(xa - xr) / np.linalg.norm(xr) < 1e-9
+    # untouched tiles hold exact zeros, the lone identity row its rhs (x = rhs after one step of identity)
+    assert not xa[~unit & (rhs == 0)].any()
+    d.close()
+
+
 def test_zero_rhs_and_iteration_count_compat(ref_mod, scene_dir):
     s = _ref_system(ref_mod, scene_dir, 256, frames=1, dt=1.0 / 30.0)  # scale 1.75: SPD regime (SURVEY App. A-3)
     assert s.threads == ORACLE_THREADS
