@@ -56,6 +56,8 @@ class Source(C.Structure):
                 ("velocity_y", C.c_float), ("transfer_velocity", C.c_int32)]
 
 
+SLAB_HANDLE_BYTES = 256
+
 _lib = None
 
 
@@ -138,6 +140,11 @@ def lib():
         "fs2d_reseed_apply": (i32, [H, i64, vp]),
         "fs2d_nbflip_advect_grids": (i32, [H]),
         "fs2d_substep": (i32, [H, f32, vp, vp]),
+        "fs2d_slab_configure": (i32, [H, i32, i32, i32]),
+        "fs2d_slab_export": (i32, [H, vp]),
+        "fs2d_slab_connect": (i32, [H, i32, vp]),
+        "fs2d_slab_rows": (i32, [H, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
+        "fs2d_slab_allgather": (i32, [H, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -358,8 +365,67 @@ class Device:
         self._ck(self.L.fs2d_substep(self.h, float(dt), _p(ms), _p(iters)), "substep")
         return ms, iters
 
+    # ---- row slabs over several GPUs (or several ranks on one GPU, for tests)
+    def slab_configure(self, rank, world, device_share=1):
+        self._ck(self.L.fs2d_slab_configure(self.h, int(rank), int(world), int(device_share)), "slab_configure")
+        self.rank, self.world = int(rank), int(world)
+
+    def slab_export(self):
+        buf = C.create_string_buffer(SLAB_HANDLE_BYTES)
+        self._ck(self.L.fs2d_slab_export(self.h, C.cast(buf, C.c_void_p)), "slab_export")
+        return bytes(buf.raw)
+
+    def slab_connect(self, peer_rank, blob):
+        buf = C.create_string_buffer(bytes(blob), SLAB_HANDLE_BYTES)
+        self._ck(self.L.fs2d_slab_connect(self.h, int(peer_rank), C.cast(buf, C.c_void_p)), "slab_connect")
+
+    def slab_rows(self):
+        a, b, h = C.c_int(0), C.c_int(0), C.c_int(0)
+        self._ck(self.L.fs2d_slab_rows(self.h, C.byref(a), C.byref(b), C.byref(h)), "slab_rows")
+        return a.value, b.value, h.value
+
+    def slab_allgather(self, values):
+        v = np.zeros(4, np.int64)
+        v[: len(values)] = values
+        out = np.zeros(4 * getattr(self, "world", 1), np.int64)
+        self._ck(self.L.fs2d_slab_allgather(self.h, _p(v), _p(out)), "slab_allgather")
+        return out.reshape(-1, 4)
+
     def synchronize(self):
         self._ck(self.L.fs2d_synchronize(self.h), "synchronize")
 
     def launch_count(self):
         return int(self.L.fs2d_launch_count(self.h))
+
+
+def connect_slabs(devices):
+    """Connect handles that live in THIS process (one per GPU, or several sharing a GPU in tests):
+    configure must have been called on each; every handle maps every other one."""
+    blobs = [d.slab_export() for d in devices]
+    for d in devices:
+        for r, blob in enumerate(blobs):
+            if r != d.rank:
+                d.slab_connect(r, blob)
+
+
+def run_ranks(fns):
+    """Run one callable per rank concurrently (ctypes releases the GIL inside the C calls; the ranks
+    spin on each other's device flags, so they must not be serialised). Returns the results in rank order."""
+    import threading
+    out, err = [None] * len(fns), [None] * len(fns)
+
+    def work(k):
+        try:
+            out[k] = fns[k]()
+        except BaseException as e:  # noqa: BLE001
+            err[k] = e
+
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(len(fns))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for e in err:
+        if e is not None:
+            raise e
+    return out

@@ -6,6 +6,7 @@
 #include "fs2d_internal.h"
 
 int pcgTileBlocks(const Ctx *ctx);
+void slabRelease(Ctx *ctx);
 
 namespace
 {
@@ -52,10 +53,30 @@ GridDesc gridDesc(Ctx *c, int grid)
     }
 }
 
-template <class T> int devAlloc(Ctx *ctx, T **p, int64_t count, int fillByte = 0)
+// Every dense array is carved from one allocation (the "symmetric heap"): same parameters -> same offsets
+// on every rank, so a peer that maps the heap through one IPC handle finds each array where its own is.
+struct HeapPlan
 {
-    FS2D_CUDA(cudaMalloc(reinterpret_cast<void **>(p), static_cast<size_t>(std::max<int64_t>(count, 1)) * sizeof(T)));
-    FS2D_CUDA(cudaMemsetAsync(*p, fillByte, static_cast<size_t>(std::max<int64_t>(count, 1)) * sizeof(T), ctx->stream));
+    struct Item
+    {
+        void **ptr;
+        size_t bytes;
+        int fill;
+    };
+    std::vector<Item> items;
+    size_t total = 0;
+    template <class T> void add(T **p, int64_t count, int fillByte = 0)
+    {
+        size_t bytes = static_cast<size_t>(std::max<int64_t>(count, 1)) * sizeof(T);
+        bytes = (bytes + 255) & ~static_cast<size_t>(255);
+        items.push_back({reinterpret_cast<void **>(p), bytes, fillByte});
+        total += bytes;
+    }
+};
+
+template <class T> int devAlloc(HeapPlan &plan, T **p, int64_t count, int fillByte = 0)
+{
+    plan.add(p, count, fillByte);
     return FS2D_OK;
 }
 
@@ -73,76 +94,91 @@ __global__ void fillIntKernel(int32_t *p, long long n, int32_t v)
         p[k] = v;
 }
 
-int allocAll(Ctx *ctx)
+int allocAll(Ctx *realCtx)
 {
+    HeapPlan plan;
+    HeapPlan *ctxPlan = &plan;
+    Ctx *ctx = realCtx;
     const int64_t N = ctx->N, NU = ctx->NU, NV = ctx->NV;
     const bool smoke = ctx->p.sim_type == FS2D_SIM_SMOKE || ctx->p.sim_type == FS2D_SIM_FIRE;
     const bool fire = ctx->p.sim_type == FS2D_SIM_FIRE;
     const bool nb = ctx->p.sim_type == FS2D_SIM_NBFLIP;
-    FS2D_TRY(devAlloc(ctx, &ctx->U, NU));
-    FS2D_TRY(devAlloc(ctx, &ctx->V, NV));
-    FS2D_TRY(devAlloc(ctx, &ctx->savedU, NU));
-    FS2D_TRY(devAlloc(ctx, &ctx->savedV, NV));
-    FS2D_TRY(devAlloc(ctx, &ctx->uValid, NU));
-    FS2D_TRY(devAlloc(ctx, &ctx->vValid, NV));
-    FS2D_TRY(devAlloc(ctx, &ctx->material, N, FS2D_EMPTY));  // MaterialGrid init value (materialgrid.cpp:5-8)
-    FS2D_TRY(devAlloc(ctx, &ctx->fluidSdf, N));
-    FS2D_TRY(devAlloc(ctx, &ctx->solidSdf, N));
-    FS2D_TRY(devAlloc(ctx, &ctx->viscosity, N));
-    FS2D_TRY(devAlloc(ctx, &ctx->density, N));
-    FS2D_TRY(devAlloc(ctx, &ctx->counts, N));
-    FS2D_TRY(devAlloc(ctx, &ctx->emitterId, N, 0xFF));       // -1 (flipsolver2d.cpp:38-39)
-    FS2D_TRY(devAlloc(ctx, &ctx->solidId, N, 0xFF));
-    FS2D_TRY(devAlloc(ctx, &ctx->divergenceControl, N));
-    FS2D_TRY(devAlloc(ctx, &ctx->testGrid, N));
-    FS2D_TRY(devAlloc(ctx, &ctx->knownCentered, N));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->U, NU));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->V, NV));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->savedU, NU));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->savedV, NV));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->uValid, NU));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->vValid, NV));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->material, N, FS2D_EMPTY));  // MaterialGrid init value (materialgrid.cpp:5-8)
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->fluidSdf, N));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->solidSdf, N));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->viscosity, N));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->density, N));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->counts, N));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->emitterId, N, 0xFF));       // -1 (flipsolver2d.cpp:38-39)
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->solidId, N, 0xFF));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->divergenceControl, N));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->testGrid, N));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->knownCentered, N));
     if (smoke)
     {
-        FS2D_TRY(devAlloc(ctx, &ctx->temperature, N));
-        FS2D_TRY(devAlloc(ctx, &ctx->concentration, N));
-        fillFloatKernel<<<ctx->smCount * 4, 256, 0, ctx->stream>>>(ctx->temperature, N, ctx->p.ambient_temperature);
+        FS2D_TRY(devAlloc(*ctxPlan, &ctx->temperature, N));
+        FS2D_TRY(devAlloc(*ctxPlan, &ctx->concentration, N));
     }
-    if (fire) FS2D_TRY(devAlloc(ctx, &ctx->fuel, N));
+    if (fire) FS2D_TRY(devAlloc(*ctxPlan, &ctx->fuel, N));
     if (nb)
     {
-        FS2D_TRY(devAlloc(ctx, &ctx->sourceSdf, N));
-        FS2D_TRY(devAlloc(ctx, &ctx->sourceSdfId, N, 0xFF));
-        FS2D_TRY(devAlloc(ctx, &ctx->advU, NU));
-        FS2D_TRY(devAlloc(ctx, &ctx->advV, NV));
-        FS2D_TRY(devAlloc(ctx, &ctx->advSdf, N));
-        FS2D_TRY(devAlloc(ctx, &ctx->advViscosity, N));
+        FS2D_TRY(devAlloc(*ctxPlan, &ctx->sourceSdf, N));
+        FS2D_TRY(devAlloc(*ctxPlan, &ctx->sourceSdfId, N, 0xFF));
+        FS2D_TRY(devAlloc(*ctxPlan, &ctx->advU, NU));
+        FS2D_TRY(devAlloc(*ctxPlan, &ctx->advV, NV));
+        FS2D_TRY(devAlloc(*ctxPlan, &ctx->advSdf, N));
+        FS2D_TRY(devAlloc(*ctxPlan, &ctx->advViscosity, N));
     }
     const int64_t big = std::max(NU, NV);
-    FS2D_TRY(devAlloc(ctx, &ctx->scratchA, big));
-    FS2D_TRY(devAlloc(ctx, &ctx->scratchB, big));
-    FS2D_TRY(devAlloc(ctx, &ctx->scratchC, big));
-    FS2D_TRY(devAlloc(ctx, &ctx->markers, big));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->scratchA, big));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->scratchB, big));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->scratchC, big));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->markers, big));
 
-    FS2D_TRY(devAlloc(ctx, &ctx->rhs, N));
-    FS2D_TRY(devAlloc(ctx, &ctx->x, N));
-    FS2D_TRY(devAlloc(ctx, &ctx->r[0], N));
-    FS2D_TRY(devAlloc(ctx, &ctx->r[1], N));
-    FS2D_TRY(devAlloc(ctx, &ctx->s[0], N));
-    FS2D_TRY(devAlloc(ctx, &ctx->s[1], N));
-    FS2D_TRY(devAlloc(ctx, &ctx->q, N));
-    FS2D_TRY(devAlloc(ctx, &ctx->z, N));
-    FS2D_TRY(devAlloc(ctx, &ctx->rowInfo, N));
-    FS2D_TRY(devAlloc(ctx, &ctx->preInfo, N));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->rhs, N));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->x, N));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->r[0], N));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->r[1], N));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->s[0], N));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->s[1], N));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->q, N));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->z, N));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->rowInfo, N));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->preInfo, N));
     ctx->maxBlocks = std::max({pcgTileBlocks(ctx), ctx->smCount * 8, ctx->p.convergence_threads, 1024});
-    FS2D_TRY(devAlloc(ctx, &ctx->partials, 3 * static_cast<int64_t>(ctx->maxBlocks)));
-    FS2D_TRY(devAlloc(ctx, &ctx->scalars, 1));
-    FS2D_TRY(devAlloc(ctx, &ctx->tileFlags, pcgTileBlocks(ctx)));
-    FS2D_TRY(devAlloc(ctx, &ctx->activeTiles, pcgTileBlocks(ctx)));
-    FS2D_TRY(devAlloc(ctx, &ctx->activeCount, 1));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->partials, 3 * static_cast<int64_t>(ctx->maxBlocks)));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->scalars, 1));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->tileFlags, pcgTileBlocks(ctx)));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->activeTiles, pcgTileBlocks(ctx)));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->activeCount, 1));
     ctx->traceCapacity = std::max(ctx->p.pcg_iter_limit, 16) + 8;
-    FS2D_TRY(devAlloc(ctx, &ctx->trace, 4 * static_cast<int64_t>(ctx->traceCapacity)));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->trace, 4 * static_cast<int64_t>(ctx->traceCapacity)));
 
-    FS2D_TRY(devAlloc(ctx, &ctx->cellStart, N + 1));
-    FS2D_TRY(devAlloc(ctx, &ctx->cellCursor, N + 1));
-    FS2D_TRY(devAlloc(ctx, &ctx->reseedOffset, N + 1));
-    FS2D_TRY(devAlloc(ctx, &ctx->scanBlock, divUp(N + 1, 1024) + 1024));
-    FS2D_TRY(devAlloc(ctx, &ctx->d_counter, 16));
-    FS2D_TRY(devAlloc(ctx, &ctx->d_fscratch, 4096));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->cellStart, N + 1));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->cellCursor, N + 1));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->reseedOffset, N + 1));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->scanBlock, divUp(N + 1, 1024) + 1024));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->d_counter, 16));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->d_fscratch, 4096));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->mail, 1));
+    FS2D_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->heap), plan.total));
+    ctx->heapBytes = plan.total;
+    {
+        size_t off = 0;
+        for (const HeapPlan::Item &it : plan.items)
+        {
+            *it.ptr = ctx->heap + off;
+            FS2D_CUDA(cudaMemsetAsync(ctx->heap + off, it.fill, it.bytes, ctx->stream));
+            off += it.bytes;
+        }
+    }
+    if (smoke) fillFloatKernel<<<ctx->smCount * 4, 256, 0, ctx->stream>>>(ctx->temperature, N, ctx->p.ambient_temperature);
     for (int k = 0; k < 16; k++) FS2D_CUDA(cudaEventCreate(&ctx->ev[k]));
     ctx->eventsReady = true;
     FS2D_CUDA(cudaGetLastError());
@@ -151,13 +187,9 @@ int allocAll(Ctx *ctx)
 
 void freeAll(Ctx *c)
 {
-    void *ptrs[] = {c->U, c->V, c->savedU, c->savedV, c->uValid, c->vValid, c->material, c->fluidSdf, c->solidSdf,
-                    c->viscosity, c->density, c->counts, c->emitterId, c->solidId, c->divergenceControl, c->testGrid,
-                    c->knownCentered, c->temperature, c->concentration, c->fuel, c->sourceSdf, c->sourceSdfId, c->advU,
-                    c->advV, c->advSdf, c->advViscosity, c->scratchA, c->scratchB, c->scratchC, c->markers, c->rhs, c->x,
-                    c->r[0], c->r[1], c->s[0], c->s[1], c->q, c->z, c->rowInfo, c->preInfo, c->partials, c->scalars,
-                    c->trace, c->rangeLast, c->dead, c->perm, c->cellStart, c->cellCursor, c->scanBlock, c->d_counter,
-                    c->d_fscratch, c->obstacleFriction, c->sources, c->reseedOffset, c->tileFlags, c->activeTiles, c->activeCount};
+    slabRelease(c);
+    if (c->heap) cudaFree(c->heap);  // every dense array lives inside the heap
+    void *ptrs[] = {c->rangeLast, c->dead, c->perm, c->obstacleFriction, c->sources, c->reseedUniform};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (int b = 0; b < 2; b++)
@@ -349,11 +381,14 @@ int fs2d_upload_particles(fs2d_handle ctx, int64_t count, const float *host_pos,
     ctx->deadCount = 0;
     ctx->killedDirty = false;
     ctx->sorted = false;
+    ctx->slab.ghostCount = 0;  // slab mode: the caller uploads the particles this rank owns
+    ctx->slab.ownedBegin = ctx->slab.ownedEnd = 0;
     if (count == 0)
     {
         FS2D_CUDA(cudaMemsetAsync(ctx->cellStart, 0, sizeof(int32_t) * (ctx->N + 1), ctx->stream));
         ctx->sorted = true;
     }
+    if (ctx->slab.enabled && ctx->slab.world > 1) FS2D_TRY(particlesReserve(ctx, count + 2 * ctx->slab.xchgCapacity));
     return fs2d_append_particles(ctx, count, host_pos, host_vel, host_props);
 }
 
@@ -363,7 +398,10 @@ int fs2d_append_particles(fs2d_handle ctx, int64_t count, const float *host_pos,
     if (!ctx || count < 0 || (count > 0 && !host_pos)) return FS2D_ERR_ARG;
     if (count == 0) return FS2D_OK;
     const int64_t base = ctx->count;
-    FS2D_TRY(particlesReserve(ctx, base + count));
+    // slab mode: room for the ghosts and migrants of the neighbours up front, so that no exchange has to grow the
+    // buffers (cudaFree synchronises the device, which must not happen while a peer spins on this rank)
+    const int64_t slack = (ctx->slab.enabled && ctx->slab.world > 1) ? 2 * ctx->slab.xchgCapacity : 0;
+    FS2D_TRY(particlesReserve(ctx, base + count + slack));
     ParticleBuffers &b = ctx->pb[ctx->cur];
     FS2D_CUDA(cudaMemcpyAsync(b.pos + base, host_pos, sizeof(float2) * count, cudaMemcpyHostToDevice, ctx->stream));
     if (host_vel)
@@ -381,6 +419,7 @@ int fs2d_append_particles(fs2d_handle ctx, int64_t count, const float *host_pos,
     }
     FS2D_CUDA(cudaMemsetAsync(ctx->dead + base, 0, count, ctx->stream));
     FS2D_CUDA(cudaMemsetAsync(b.mis + base, FS2D_MIS_HOME, count, ctx->stream));  // filed in the bin of its position
+    FS2D_TRY(particlesKeyRange(ctx, base, base + count));
     FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->count = base + count;
     ctx->sorted = false;
@@ -394,15 +433,18 @@ int fs2d_download_particles(fs2d_handle ctx, float *host_pos, float *host_vel, f
     // caller sees exactly fs2d_particle_count() records in device order
     int64_t alive = 0;
     FS2D_TRY(particlesAliveCount(ctx, &alive));
-    if (alive != ctx->count || !ctx->sorted) FS2D_TRY(particlesSort(ctx));
-    const int64_t n = ctx->count;
+    const bool slab = ctx->slab.enabled && ctx->slab.world > 1;
+    if (alive != ctx->count - ctx->slab.ghostCount || !ctx->sorted) FS2D_TRY(particlesSort(ctx));
+    // slab mode: only the particles this rank owns (the sorted arrays also hold ghost copies of the neighbours')
+    const int64_t first = slab ? ctx->slab.ownedBegin : 0;
+    const int64_t n = slab ? ctx->slab.ownedEnd - ctx->slab.ownedBegin : ctx->count;
     if (n == 0) return FS2D_OK;
     ParticleBuffers &b = ctx->pb[ctx->cur];
-    if (host_pos) FS2D_CUDA(cudaMemcpyAsync(host_pos, b.pos, sizeof(float2) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    if (host_vel) FS2D_CUDA(cudaMemcpyAsync(host_vel, b.vel, sizeof(float2) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (host_pos) FS2D_CUDA(cudaMemcpyAsync(host_pos, b.pos + first, sizeof(float2) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (host_vel) FS2D_CUDA(cudaMemcpyAsync(host_vel, b.vel + first, sizeof(float2) * n, cudaMemcpyDeviceToHost, ctx->stream));
     if (host_props)
         for (int k = 0; k < ctx->p.num_properties; k++)
-            FS2D_CUDA(cudaMemcpyAsync(host_props + static_cast<int64_t>(k) * n, b.props + static_cast<int64_t>(k) * b.capacity,
+            FS2D_CUDA(cudaMemcpyAsync(host_props + static_cast<int64_t>(k) * n, b.props + static_cast<int64_t>(k) * b.capacity + first,
                                       sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
     FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
     return FS2D_OK;
@@ -547,7 +589,7 @@ int fs2d_advect(fs2d_handle h)
 }
 
 int fs2d_build_matrix(fs2d_handle h) { return h ? gridBuildMatrix(h) : FS2D_ERR_ARG; }
-int fs2d_sort_particles(fs2d_handle h) { return h ? particlesSort(h) : FS2D_ERR_ARG; }
+int fs2d_sort_particles(fs2d_handle h) { return h ? particlesRebin(h) : FS2D_ERR_ARG; }
 int fs2d_update_density_grid(fs2d_handle h) { return h ? transferDensity(h) : FS2D_ERR_ARG; }
 int fs2d_density_rhs(fs2d_handle h) { return h ? gridDensityRhs(h) : FS2D_ERR_ARG; }
 
@@ -562,11 +604,12 @@ int fs2d_density_correction(fs2d_handle h, int *iters)
     FS2D_TRY(fs2d_pcg_last_iterations(h, &it));
     if (iters) *iters = it;
     if (it >= h->p.pcg_iter_limit) return FS2D_OK;  // "Density solver solving failed!": result discarded (:179-182)
+    FS2D_TRY(slabExchangePressure(h));               // slab mode: the gradient reads p one row outside the slab
     FS2D_TRY(particlesAdjustByDensity(h));
     // The reference leaves adjusted particles in their old bins ("adjusted not enough to require
     // rebinning", flipsolver2d.cpp:427); the cell-sorted layout is re-keyed instead so that the
     // gathers that follow see every particle in the cell its position says.
-    FS2D_TRY(particlesSort(h));
+    FS2D_TRY(particlesRebin(h));
     return FS2D_OK;
 }
 
@@ -595,6 +638,7 @@ int fs2d_project(fs2d_handle h, int *iters)
     // project (flipsolver2d.cpp:93-126)
     FS2D_TRY(gridPressureRhs(h));
     FS2D_TRY(pcgSolveDevice(h, h->p.pcg_iter_limit, h->p.project_tolerance));
+    FS2D_TRY(slabExchangePressure(h));  // slab mode: U(i,j) needs p(i-1,j) of the row neighbour
     FS2D_TRY(gridApplyPressure(h));
     if (iters) FS2D_TRY(fs2d_pcg_last_iterations(h, iters));
     return FS2D_OK;

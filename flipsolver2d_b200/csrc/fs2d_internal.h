@@ -75,6 +75,67 @@ struct PcgScalars
     unsigned int pad2;
 };
 
+// ------------------------------------------------------------------ row-slab decomposition (slab.cu)
+// One process (or one handle) per GPU owns the cell rows [rowBegin, rowEnd); every dense array keeps the
+// GLOBAL size and indexing, a rank computes its own rows plus what it needs of the halo, and ranks talk
+// through peer-mapped device memory only: data is PUSHED into the peer's copy of an array and announced
+// with a tag the peer spins on in its own memory (1.2 us one way over NVLink, profiles/r1e_ipc_probe*).
+#define FS2D_MAX_RANKS 8
+#define FS2D_PCG_RING 16
+
+struct SlabPcgSlot
+{
+    double v0, v1;             // partial dot product, partial max
+    unsigned long long tag;    // (solve sequence << 20) + phase + 1, written after the payload
+    unsigned long long pad;
+};
+
+struct SlabGatherSlot
+{
+    long long v[4];
+    unsigned long long tag;
+    unsigned long long pad[3];
+};
+
+struct SlabMail
+{
+    SlabPcgSlot pcg[FS2D_PCG_RING][FS2D_MAX_RANKS];  // written by every rank (slot [.][writer])
+    unsigned long long ready[2];   // [0] written by the lower neighbour (rank-1), [1] by the upper: "I am done reading
+                                   //     what exchange #seq overwrites"
+    unsigned long long data[2];    // "my data of exchange #seq has landed in your memory"
+    long long counts[2][4];        // particle exchange: records pushed by neighbour [from] {owned, ghosts}
+    SlabGatherSlot gather[2][FS2D_MAX_RANKS];      // double buffered by the parity of the gather sequence
+    int error;                     // set when a spin loop timed out
+    int pad[3];
+};
+
+struct SlabField                   // one dense array taking part in a halo exchange
+{
+    unsigned long long offset;     // byte offset inside the symmetric heap
+    unsigned long long rowBytes;   // bytes per grid row
+};
+
+struct SlabState
+{
+    bool enabled = false;
+    int rank = 0, world = 1, share = 1;
+    int rowBegin = 0, rowEnd = 0;          // owned cell rows
+    int halo = 32;                         // rows kept valid on either side after a halo exchange
+    int ghost = 12;                        // rows of neighbour particles mirrored as ghosts
+    unsigned char *peerHeap[FS2D_MAX_RANKS] = {};   // mapped base address of every rank's heap (own: local)
+    unsigned char *peerXchg[FS2D_MAX_RANKS] = {};   // mapped particle receive buffers
+    bool peerMapped[FS2D_MAX_RANKS] = {};           // opened through cudaIpcOpenMemHandle (to be closed)
+    unsigned long long seq = 0;            // generic exchange sequence (same on every rank)
+    unsigned long long gatherSeq = 0;
+    unsigned long long solveSeq = 0;
+    unsigned char *xchg = nullptr;         // local particle exchange buffers: send[2], recv[2]
+    size_t xchgBytes = 0;
+    int64_t xchgCapacity = 0;              // records per buffer
+    int64_t ghostCount = 0;                // ghost records inside the particle arrays (host view)
+    int64_t ownedBegin = 0, ownedEnd = 0;  // owned range of the sorted particle arrays
+    int connected = 0;
+};
+
 struct ParticleBuffers
 {
     float2 *pos = nullptr;
@@ -162,6 +223,15 @@ struct fs2d_context
     // ---- reseed plan
     int32_t *reseedOffset = nullptr;  // N+1 exclusive scan of per-cell candidate counts
     int64_t reseedCandidates = 0;
+    float *reseedUniform = nullptr;   // device copy of the host-drawn jitter
+    int64_t reseedUniformCapacity = 0;
+
+    // ---- symmetric heap: every dense array above is carved from ONE allocation so that a peer can map it
+    // with a single IPC handle and address the same array at the same offset
+    unsigned char *heap = nullptr;
+    size_t heapBytes = 0;
+    SlabMail *mail = nullptr;         // inside the heap
+    SlabState slab;
 
     // ---- timing
     cudaEvent_t ev[16];
@@ -177,9 +247,11 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol);
 int pcgSpmvHost(Ctx *ctx, const double *in, double *out, bool precond);
 // particles.cu
 int particlesReserve(Ctx *ctx, int64_t capacity);
+int particlesKeyRange(Ctx *ctx, int64_t begin, int64_t end);
 int particlesMaxVelocity(Ctx *ctx, float *out);
 int particlesAdvect(Ctx *ctx);
 int particlesSort(Ctx *ctx);
+int particlesRebin(Ctx *ctx);
 int particlesUpdate(Ctx *ctx);
 int particlesCount(Ctx *ctx);
 int particlesAdjustByDensity(Ctx *ctx);
@@ -210,6 +282,16 @@ int gridVelocityFromSolids(Ctx *ctx);
 int gridEulerAdvectParameters(Ctx *ctx);
 int gridNbflipAdvect(Ctx *ctx);
 int gridViscosity(Ctx *ctx, int *iters);
+// slab.cu
+struct SlabRows { int lo, hi; };                       // half-open cell-row range
+SlabRows slabOwn(const Ctx *ctx);                      // owned rows (whole grid without slabs)
+SlabRows slabExt(const Ctx *ctx, int k);               // owned rows grown by k, clipped to the grid
+int slabExchangeFields(Ctx *ctx, const void *const *arrays, const size_t *rowBytes, int count);
+int slabExchangeVelocity(Ctx *ctx, bool withMaterial);
+int slabExchangePressure(Ctx *ctx);
+int slabExchangeParticles(Ctx *ctx);
+int slabAllGather(Ctx *ctx, const long long v[4], long long *out /* world x 4 */);
+int slabCheckError(Ctx *ctx);
 // step.cu
 int stepSubstep(Ctx *ctx, float dt, float *stageMs, int *iters);
 

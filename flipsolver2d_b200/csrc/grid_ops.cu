@@ -14,15 +14,24 @@ namespace
 {
 constexpr int NT = 256;
 
+// Linear cell range of a row range (slab mode restricts every sweep to the rows a rank needs).
+struct CellRange
+{
+    long long begin, end;
+    long long count() const { return end > begin ? end - begin : 0; }
+};
+inline CellRange cellRange(const Ctx *ctx, SlabRows r) { return {static_cast<long long>(r.lo) * ctx->J, static_cast<long long>(r.hi) * ctx->J}; }
+
 // ------------------------------------------------------------------ matrix rows
 // getPressureProjectionMatrix (flipsolver2d.cpp:797-887; smoke flipsmokesolver.cpp:354-444)
 // and getIPPCoefficients (flipsolver2d.cpp:889-945) as per-cell bit fields.
 __global__ void __launch_bounds__(NT) buildMatrixKernel(const int8_t *__restrict__ mat, int I, int J, int smokeRows,
-                                                        uint8_t *__restrict__ rowInfo, uint16_t *__restrict__ preInfo)
+                                                        uint8_t *__restrict__ rowInfo, uint16_t *__restrict__ preInfo,
+                                                        long long nBegin, long long nEnd)
 {
     const long long N = static_cast<long long>(I) * J;
-    const long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
-    if (n >= N) return;
+    const long long n = nBegin + blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    if (n >= nEnd) return;
     const int i = static_cast<int>(n / J), j = static_cast<int>(n - static_cast<long long>(i) * J);
     const int8_t m = mat[n];
     const bool hasRow = smokeRows ? !matSolid(m) : matFluid(m);
@@ -61,9 +70,10 @@ __global__ void __launch_bounds__(NT) buildMatrixKernel(const int8_t *__restrict
 
 // ------------------------------------------------------------------ materials / sources
 // updateMaterials (flipsolver2d.cpp:1053-1075)
-__global__ void __launch_bounds__(NT) updateMaterialsKernel(const float *__restrict__ sdf, int8_t *__restrict__ mat, long long N)
+__global__ void __launch_bounds__(NT) updateMaterialsKernel(const float *__restrict__ sdf, int8_t *__restrict__ mat, long long nBegin,
+                                                            long long N)
 {
-    const long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    const long long n = nBegin + blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
     if (n >= N) return;
     const int8_t m = mat[n];
     if (sdf[n] < 0.f)
@@ -83,10 +93,11 @@ __global__ void __launch_bounds__(NT) afterTransferKernel(const int8_t *__restri
                                                           float *__restrict__ viscosity, float *__restrict__ U,
                                                           float *__restrict__ V, uint8_t *__restrict__ uValid,
                                                           uint8_t *__restrict__ vValid, float *__restrict__ temperature,
-                                                          float *__restrict__ concentration, float *__restrict__ fuel)
+                                                          float *__restrict__ concentration, float *__restrict__ fuel,
+                                                          long long nBegin, long long nEnd)
 {
-    const long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
-    if (n >= static_cast<long long>(I) * J || !matSource(mat[n])) return;
+    const long long n = nBegin + blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    if (n >= nEnd || !matSource(mat[n])) return;
     const int i = static_cast<int>(n / J), j = static_cast<int>(n - static_cast<long long>(i) * J);
     const fs2d_source s = sources[emitterId[n]];
     viscosity[n] = s.viscosity;
@@ -110,14 +121,18 @@ __global__ void __launch_bounds__(NT) afterTransferKernel(const int8_t *__restri
 // Markers (0 = valid sample, 255 = unknown) and the bounding box {iMin, iMax, jMin, jMax} of the valid
 // samples of both grids: layers can only appear within radius+1 samples of it, so the layer sweeps are
 // restricted to that box instead of the whole grid.
+// Rows [rowLo, rowHiU) of U and [rowLo, rowHiV) of V are swept (the whole grids without slabs).
 __global__ void __launch_bounds__(NT) bfsInitKernel(const uint8_t *__restrict__ uValid, const uint8_t *__restrict__ vValid, int I,
-                                                    int J, uint8_t *__restrict__ marker, int *__restrict__ bbox)
+                                                    int J, uint8_t *__restrict__ marker, int *__restrict__ bbox, int rowLo, int rowHiU,
+                                                    int rowHiV)
 {
-    const long long NU = static_cast<long long>(I + 1) * J, NV = static_cast<long long>(I) * (J + 1);
-    const long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    const long long NU = static_cast<long long>(I + 1) * J;
+    const long long cntU = static_cast<long long>(rowHiU - rowLo) * J, cntV = static_cast<long long>(rowHiV - rowLo) * (J + 1);
+    const long long t = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
     int i = -1, j = -1;
-    if (n < NU)
+    if (t < cntU)
     {
+        const long long n = static_cast<long long>(rowLo) * J + t;
         const bool v = uValid[n] != 0;
         marker[n] = v ? 0 : 255;
         if (v)
@@ -126,9 +141,10 @@ __global__ void __launch_bounds__(NT) bfsInitKernel(const uint8_t *__restrict__ 
             j = static_cast<int>(n - static_cast<long long>(i) * J);
         }
     }
-    else if (n < NU + NV)
+    else if (t < cntU + cntV)
     {
-        const long long m = n - NU;
+        const long long m = static_cast<long long>(rowLo) * (J + 1) + (t - cntU);
+        const long long n = NU + m;
         const bool v = vValid[m] != 0;
         marker[n] = v ? 0 : 255;
         if (v)
@@ -281,14 +297,15 @@ __global__ void __launch_bounds__(NT) sdfExtrapolateKernel(float *sdf, int32_t *
 
 // ------------------------------------------------------------------ body forces
 // applyBodyForces (flipsolver2d.cpp:1222-1241): every U and V sample gets factor * g
-__global__ void __launch_bounds__(NT) bodyForceKernel(float *__restrict__ U, float *__restrict__ V, long long NU, long long NV,
-                                                      float addU, float addV)
+// U samples [uBegin, uBegin + NU) and V samples [vBegin, vBegin + NV) (whole grids without slabs)
+__global__ void __launch_bounds__(NT) bodyForceKernel(float *__restrict__ U, float *__restrict__ V, long long uBegin, long long NU,
+                                                      long long vBegin, long long NV, float addU, float addV)
 {
     const long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
     if (n < NU)
-        U[n] = faddr(U[n], addU);
+        U[uBegin + n] = faddr(U[uBegin + n], addU);
     else if (n < NU + NV)
-        V[n - NU] = faddr(V[n - NU], addV);
+        V[vBegin + n - NU] = faddr(V[vBegin + n - NU], addV);
 }
 
 // FlipSmokeSolver::applyBodyForces (flipsmokesolver.cpp:23-52)
@@ -323,10 +340,11 @@ __global__ void __launch_bounds__(NT) smokeBodyForceKernel(float *__restrict__ U
 // calcPressureRhs (flipsolver2d.cpp:962-991; smoke: flipsmokesolver.cpp:73-102) with divergenceAt (:759-764)
 __global__ void __launch_bounds__(NT) pressureRhsKernel(const float *__restrict__ U, const float *__restrict__ V,
                                                         const float *__restrict__ divCtl, const int8_t *__restrict__ mat, int I,
-                                                        int J, int smokeRows, double scale, double *__restrict__ rhs)
+                                                        int J, int smokeRows, double scale, double *__restrict__ rhs, long long nBegin,
+                                                        long long nEnd)
 {
-    const long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
-    if (n >= static_cast<long long>(I) * J) return;
+    const long long n = nBegin + blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    if (n >= nEnd) return;
     const int i = static_cast<int>(n / J), j = static_cast<int>(n - static_cast<long long>(i) * J);
     const int8_t m = mat[n];
     const bool row = smokeRows ? !matSolid(m) : matFluid(m);
@@ -353,9 +371,10 @@ __global__ void __launch_bounds__(NT) pressureRhsKernel(const float *__restrict_
 
 // calcDensityCorrectionRhs (flipsolver2d.cpp:993-1011)
 __global__ void __launch_bounds__(NT) densityRhsKernel(const float *__restrict__ density, const int8_t *__restrict__ mat,
-                                                       long long N, double scale, double restDensity, double *__restrict__ rhs)
+                                                       long long nBegin, long long N, double scale, double restDensity,
+                                                       double *__restrict__ rhs)
 {
-    const long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    const long long n = nBegin + blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
     if (n >= N) return;
     if (!matFluid(mat[n]))
     {
@@ -371,10 +390,11 @@ __global__ void __launch_bounds__(NT) densityRhsKernel(const float *__restrict__
 __global__ void __launch_bounds__(NT) applyPressureKernel(const double *__restrict__ p, const int8_t *__restrict__ mat, int I,
                                                           int J, int smokeRows, double scale, float *__restrict__ U,
                                                           float *__restrict__ V, uint8_t *__restrict__ uValid,
-                                                          uint8_t *__restrict__ vValid, float *__restrict__ testGrid)
+                                                          uint8_t *__restrict__ vValid, float *__restrict__ testGrid, long long nBegin,
+                                                          long long nEnd)
 {
-    const long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
-    if (n >= static_cast<long long>(I) * J) return;
+    const long long n = nBegin + blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    if (n >= nEnd) return;
     const int i = static_cast<int>(n / J), j = static_cast<int>(n - static_cast<long long>(i) * J);
     const double pc = p[n];
     const int8_t mc = mat[n];
@@ -418,10 +438,10 @@ __global__ void __launch_bounds__(NT) applyPressureKernel(const double *__restri
 // u/vSampleAffectedBySolid (materialgrid.cpp:152-164)
 __global__ void __launch_bounds__(NT) solidFrictionKernel(const int32_t *__restrict__ solidId, const float *__restrict__ friction,
                                                           const int8_t *__restrict__ mat, int I, int J, float *__restrict__ U,
-                                                          float *__restrict__ V)
+                                                          float *__restrict__ V, long long nBegin, long long nEnd)
 {
-    const long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
-    if (n >= static_cast<long long>(I) * J) return;
+    const long long n = nBegin + blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    if (n >= nEnd) return;
     const int i = static_cast<int>(n / J), j = static_cast<int>(n - static_cast<long long>(i) * J);
     float avg = 0.f;
     int cnt = 0;
@@ -517,8 +537,9 @@ __global__ void __launch_bounds__(NT) nbCombineKernel(GridView fluidSdf, int I, 
 int gridBuildMatrix(Ctx *ctx)
 {
     const int smokeRows = (ctx->p.sim_type == FS2D_SIM_SMOKE || ctx->p.sim_type == FS2D_SIM_FIRE) ? 1 : 0;
-    buildMatrixKernel<<<divUp(ctx->N, NT), NT, 0, ctx->stream>>>(ctx->material, ctx->I, ctx->J, smokeRows, ctx->rowInfo,
-                                                                  ctx->preInfo);
+    const CellRange cr = cellRange(ctx, slabOwn(ctx));
+    buildMatrixKernel<<<divUp(cr.count(), NT), NT, 0, ctx->stream>>>(ctx->material, ctx->I, ctx->J, smokeRows, ctx->rowInfo,
+                                                                      ctx->preInfo, cr.begin, cr.end);
     ctx->launches++;
     // scale = dt / (rho dx^2) (flipsolver2d.cpp:799), float dt promoted to double
     ctx->matrixScale = static_cast<double>(ctx->stepDt) / (ctx->p.fluid_density * ctx->p.dx * ctx->p.dx);
@@ -535,9 +556,18 @@ GridView fuelView(const Ctx *c);
 
 static bool isSmoke(const Ctx *ctx) { return ctx->p.sim_type == FS2D_SIM_SMOKE || ctx->p.sim_type == FS2D_SIM_FIRE; }
 
+static int slabUnsupported(Ctx *ctx, const char *what)
+{
+    if (!ctx->slab.enabled || ctx->slab.world == 1) return FS2D_OK;
+    ctx->lastError = std::string(what) + " is not slab-aware yet (only FS2D_SIM_LIQUID without viscosity runs on several GPUs)";
+    return FS2D_ERR_STATE;
+}
+
+
 int gridUpdateMaterials(Ctx *ctx)
 {
-    updateMaterialsKernel<<<divUp(ctx->N, NT), NT, 0, ctx->stream>>>(ctx->fluidSdf, ctx->material, ctx->N);
+    const CellRange cr = cellRange(ctx, slabOwn(ctx));
+    updateMaterialsKernel<<<divUp(cr.count(), NT), NT, 0, ctx->stream>>>(ctx->fluidSdf, ctx->material, cr.begin, cr.end);
     ctx->launches++;
     FS2D_CUDA(cudaGetLastError());
     return FS2D_OK;
@@ -548,11 +578,12 @@ int gridAfterTransfer(Ctx *ctx)
     cudaStream_t st = ctx->stream;
     if (ctx->numSources > 0)
     {
-        afterTransferKernel<<<divUp(ctx->N, NT), NT, 0, st>>>(ctx->material, ctx->emitterId, ctx->sources, ctx->I, ctx->J, ctx->p.dx,
-                                                            ctx->viscosity, ctx->U, ctx->V, ctx->uValid, ctx->vValid,
-                                                            isSmoke(ctx) ? ctx->temperature : nullptr,
-                                                            isSmoke(ctx) ? ctx->concentration : nullptr,
-                                                            ctx->p.sim_type == FS2D_SIM_FIRE ? ctx->fuel : nullptr);
+        const CellRange cr = cellRange(ctx, slabOwn(ctx));
+        afterTransferKernel<<<divUp(cr.count(), NT), NT, 0, st>>>(ctx->material, ctx->emitterId, ctx->sources, ctx->I, ctx->J, ctx->p.dx,
+                                                                ctx->viscosity, ctx->U, ctx->V, ctx->uValid, ctx->vValid,
+                                                                isSmoke(ctx) ? ctx->temperature : nullptr,
+                                                                isSmoke(ctx) ? ctx->concentration : nullptr,
+                                                                ctx->p.sim_type == FS2D_SIM_FIRE ? ctx->fuel : nullptr, cr.begin, cr.end);
         ctx->launches++;
     }
     if (isSmoke(ctx)) FS2D_CUDA(cudaMemsetAsync(ctx->divergenceControl, 0, sizeof(float) * ctx->N, st));  // flipsmokesolver.cpp:135
@@ -572,19 +603,28 @@ int gridAfterTransfer(Ctx *ctx)
 
 int gridExtrapolateVelocity(Ctx *ctx, int radius)
 {
+    // slab mode: both call sites of a substep (after the transfer, after the projection) follow stages that
+    // rewrote U / V / validity / material on the owned rows only -> refresh the halo copies first
+    FS2D_TRY(slabExchangeVelocity(ctx, true));
     uint8_t *marker = reinterpret_cast<uint8_t *>(ctx->markers);
     cudaStream_t st = ctx->stream;
     int *bbox = reinterpret_cast<int *>(ctx->d_counter) + 16;  // ints 16..19 of the scalar scratch
     const int init[4] = {0x7fffffff, -1, 0x7fffffff, -1};
     FS2D_CUDA(cudaMemcpyAsync(bbox, init, sizeof(init), cudaMemcpyHostToDevice, st));
-    bfsInitKernel<<<divUp(ctx->NU + ctx->NV, NT), NT, 0, st>>>(ctx->uValid, ctx->vValid, ctx->I, ctx->J, marker, bbox);
+    // slab mode: the sweep covers the owned rows plus the exchanged halo. Values on the outer halo rows lack
+    // their outside neighbours; that error moves one row per layer, so after radius+1 layers the owned rows and
+    // the inner halo - (radius+2) rows are exact.
+    const SlabRows reg = slabExt(ctx, ctx->slab.halo);
+    const int rowHiU = reg.hi == ctx->I ? ctx->I + 1 : reg.hi;
+    bfsInitKernel<<<divUp(static_cast<long long>(rowHiU - reg.lo) * ctx->J + static_cast<long long>(reg.hi - reg.lo) * (ctx->J + 1), NT), NT, 0,
+                    st>>>(ctx->uValid, ctx->vValid, ctx->I, ctx->J, marker, bbox, reg.lo, rowHiU, reg.hi);
     ctx->launches++;
     int box[4];
     FS2D_CUDA(cudaMemcpyAsync(box, bbox, sizeof(box), cudaMemcpyDeviceToHost, st));
     FS2D_CUDA(cudaStreamSynchronize(st));
     if (box[1] < box[0]) return FS2D_OK;  // no valid sample anywhere: the BFS has no seed (mathfuncs.cpp:171-189)
     const int grow = radius + 2;
-    const int i0 = std::max(box[0] - grow, 0), i1 = std::min(box[1] + grow, ctx->I);
+    const int i0 = std::max({box[0] - grow, 0, reg.lo}), i1 = std::min({box[1] + grow, ctx->I, rowHiU - 1});
     const int j0 = std::max(box[2] - grow, 0), j1 = std::min(box[3] + grow, ctx->J);
     const int h = i1 - i0 + 1, w = j1 - j0 + 1;
     const int blocks = divUp(2ll * h * w, NT);
@@ -621,6 +661,7 @@ int gridExtrapolateSdf(Ctx *ctx, bool inside)
 
 int gridExtrapolateSdfNow(Ctx *ctx, bool inside)
 {
+    FS2D_TRY(slabUnsupported(ctx, "extrapolateLevelset"));
     cudaStream_t st = ctx->stream;
     int *bbox = reinterpret_cast<int *>(ctx->d_counter) + 8;  // 4 ints bbox + 3 ints flags
     const int init[8] = {0x7fffffff, -1, 0x7fffffff, -1, 0, 0, 0, 0};
@@ -644,8 +685,13 @@ int gridExtrapolateSdfNow(Ctx *ctx, bool inside)
 
 int gridSaveVelocity(Ctx *ctx)
 {
-    FS2D_CUDA(cudaMemcpyAsync(ctx->savedU, ctx->U, sizeof(float) * ctx->NU, cudaMemcpyDeviceToDevice, ctx->stream));
-    FS2D_CUDA(cudaMemcpyAsync(ctx->savedV, ctx->V, sizeof(float) * ctx->NV, cudaMemcpyDeviceToDevice, ctx->stream));
+    const SlabRows reg = slabExt(ctx, ctx->slab.halo);
+    const int rowHiU = reg.hi == ctx->I ? ctx->I + 1 : reg.hi;
+    const size_t uOff = static_cast<size_t>(reg.lo) * ctx->J, vOff = static_cast<size_t>(reg.lo) * (ctx->J + 1);
+    FS2D_CUDA(cudaMemcpyAsync(ctx->savedU + uOff, ctx->U + uOff, sizeof(float) * static_cast<size_t>(rowHiU - reg.lo) * ctx->J,
+                              cudaMemcpyDeviceToDevice, ctx->stream));
+    FS2D_CUDA(cudaMemcpyAsync(ctx->savedV + vOff, ctx->V + vOff, sizeof(float) * static_cast<size_t>(reg.hi - reg.lo) * (ctx->J + 1),
+                              cudaMemcpyDeviceToDevice, ctx->stream));
     return FS2D_OK;
 }
 
@@ -656,14 +702,20 @@ int gridBodyForces(Ctx *ctx)
     const int blocks = divUp(ctx->NU + ctx->NV, NT);
     if (isSmoke(ctx))
     {
+        FS2D_TRY(slabUnsupported(ctx, "FlipSmokeSolver::applyBodyForces"));
         smokeBodyForceKernel<<<blocks, NT, 0, ctx->stream>>>(ctx->U, ctx->V, ctx->I, ctx->J, temperatureView(ctx), concentrationView(ctx),
                                                             ctx->p.soot_factor, ctx->p.buoyancy_factor / ctx->p.ambient_temperature,
                                                             ctx->p.ambient_temperature, ctx->p.gravity_x, ctx->p.gravity_y, factor);
     }
     else
     {
-        bodyForceKernel<<<blocks, NT, 0, ctx->stream>>>(ctx->U, ctx->V, ctx->NU, ctx->NV, factor * ctx->p.gravity_x,
-                                                       factor * ctx->p.gravity_y);
+        // slab mode: every sample a rank holds a valid copy of (owned rows + exchanged halo) gets the force once
+        const SlabRows reg = slabExt(ctx, ctx->slab.halo);
+        const int rowHiU = reg.hi == ctx->I ? ctx->I + 1 : reg.hi;
+        const long long uBegin = static_cast<long long>(reg.lo) * ctx->J, nu = static_cast<long long>(rowHiU - reg.lo) * ctx->J;
+        const long long vBegin = static_cast<long long>(reg.lo) * (ctx->J + 1), nv = static_cast<long long>(reg.hi - reg.lo) * (ctx->J + 1);
+        bodyForceKernel<<<divUp(nu + nv, NT), NT, 0, ctx->stream>>>(ctx->U, ctx->V, uBegin, nu, vBegin, nv, factor * ctx->p.gravity_x,
+                                                                   factor * ctx->p.gravity_y);
     }
     ctx->launches++;
     FS2D_CUDA(cudaGetLastError());
@@ -673,8 +725,9 @@ int gridBodyForces(Ctx *ctx)
 int gridPressureRhs(Ctx *ctx)
 {
     const double scale = 1.f / ctx->p.dx;  // const double scale = 1.f/m_dx
-    pressureRhsKernel<<<divUp(ctx->N, NT), NT, 0, ctx->stream>>>(ctx->U, ctx->V, ctx->divergenceControl, ctx->material, ctx->I, ctx->J,
-                                                                isSmoke(ctx) ? 1 : 0, scale, ctx->rhs);
+    const CellRange cr = cellRange(ctx, slabExt(ctx, 1));  // + one halo row: r0 = rhs there feeds the slab PCG
+    pressureRhsKernel<<<divUp(cr.count(), NT), NT, 0, ctx->stream>>>(ctx->U, ctx->V, ctx->divergenceControl, ctx->material, ctx->I, ctx->J,
+                                                                    isSmoke(ctx) ? 1 : 0, scale, ctx->rhs, cr.begin, cr.end);
     ctx->launches++;
     FS2D_CUDA(cudaGetLastError());
     return FS2D_OK;
@@ -683,7 +736,9 @@ int gridPressureRhs(Ctx *ctx)
 int gridDensityRhs(Ctx *ctx)
 {
     const double scale = 1.0 / ctx->stepDt;
-    densityRhsKernel<<<divUp(ctx->N, NT), NT, 0, ctx->stream>>>(ctx->density, ctx->material, ctx->N, scale, ctx->p.fluid_density, ctx->rhs);
+    const CellRange cr = cellRange(ctx, slabExt(ctx, 1));
+    densityRhsKernel<<<divUp(cr.count(), NT), NT, 0, ctx->stream>>>(ctx->density, ctx->material, cr.begin, cr.end, scale, ctx->p.fluid_density,
+                                                                   ctx->rhs);
     ctx->launches++;
     FS2D_CUDA(cudaGetLastError());
     return FS2D_OK;
@@ -692,9 +747,10 @@ int gridDensityRhs(Ctx *ctx)
 int gridApplyPressure(Ctx *ctx)
 {
     const double scale = ctx->stepDt / (ctx->p.fluid_density * ctx->p.dx);
-    applyPressureKernel<<<divUp(ctx->N, NT), NT, 0, ctx->stream>>>(ctx->x, ctx->material, ctx->I, ctx->J, isSmoke(ctx) ? 1 : 0, scale,
-                                                                  ctx->U, ctx->V, ctx->uValid, ctx->vValid,
-                                                                  isSmoke(ctx) ? ctx->testGrid : nullptr);
+    const CellRange cr = cellRange(ctx, slabOwn(ctx));
+    applyPressureKernel<<<divUp(cr.count(), NT), NT, 0, ctx->stream>>>(ctx->x, ctx->material, ctx->I, ctx->J, isSmoke(ctx) ? 1 : 0, scale,
+                                                                      ctx->U, ctx->V, ctx->uValid, ctx->vValid,
+                                                                      isSmoke(ctx) ? ctx->testGrid : nullptr, cr.begin, cr.end);
     ctx->launches++;
     FS2D_CUDA(cudaGetLastError());
     return FS2D_OK;
@@ -703,8 +759,9 @@ int gridApplyPressure(Ctx *ctx)
 int gridVelocityFromSolids(Ctx *ctx)
 {
     if (ctx->numObstacles == 0) return FS2D_OK;
-    solidFrictionKernel<<<divUp(ctx->N, NT), NT, 0, ctx->stream>>>(ctx->solidId, ctx->obstacleFriction, ctx->material, ctx->I, ctx->J,
-                                                                  ctx->U, ctx->V);
+    const CellRange cr = cellRange(ctx, slabOwn(ctx));
+    solidFrictionKernel<<<divUp(cr.count(), NT), NT, 0, ctx->stream>>>(ctx->solidId, ctx->obstacleFriction, ctx->material, ctx->I, ctx->J,
+                                                                      ctx->U, ctx->V, cr.begin, cr.end);
     ctx->launches++;
     FS2D_CUDA(cudaGetLastError());
     return FS2D_OK;
@@ -714,6 +771,7 @@ int gridVelocityFromSolids(Ctx *ctx)
 int gridEulerAdvectParameters(Ctx *ctx)
 {
     if (!isSmoke(ctx)) return FS2D_OK;  // FlipSolver::eulerAdvectParameters is empty for water
+    FS2D_TRY(slabUnsupported(ctx, "eulerAdvectParameters"));
     const VelocityView vel = makeVelocityView(ctx->U, ctx->V, ctx->I, ctx->J);
     const int blocks = divUp(ctx->N, NT);
     eulerAdvectKernel<<<blocks, NT, 0, ctx->stream>>>(concentrationView(ctx), vel, ctx->stepDt, ctx->scratchA);
@@ -736,6 +794,7 @@ int gridEulerAdvectParameters(Ctx *ctx)
 int gridNbflipAdvect(Ctx *ctx)
 {
     if (ctx->p.sim_type != FS2D_SIM_NBFLIP) return FS2D_OK;
+    FS2D_TRY(slabUnsupported(ctx, "NBFlipSolver::advect"));
     const VelocityView vel = makeVelocityView(ctx->U, ctx->V, ctx->I, ctx->J);
     cudaStream_t st = ctx->stream;
     eulerAdvectKernel<<<divUp(ctx->NU, NT), NT, 0, st>>>(vel.u, vel, ctx->stepDt, ctx->advU);

@@ -141,9 +141,27 @@ __device__ __forceinline__ uint32_t cellKey(float2 p, int I, int J)
     return static_cast<uint32_t>(i) * static_cast<uint32_t>(J) + static_cast<uint32_t>(j);
 }
 
+// Slab mode: a rank updates only the particles it OWNS -- those whose cell row at the last sort (key / J) lies in
+// its rows; the others are ghost copies of a neighbour's particles. own.key == nullptr: everything is owned.
+struct OwnedRows
+{
+    const uint32_t *key;
+    uint32_t J;
+    int rowBegin, rowEnd;
+};
+__device__ __forceinline__ bool ownedParticle(const OwnedRows &o, long long p)
+{
+    if (!o.key) return true;
+    const int r = static_cast<int>(o.key[p] / o.J);
+    return r >= o.rowBegin && r < o.rowEnd;
+}
+
+__global__ void __launch_bounds__(NT) cellKeyKernel(const float2 *__restrict__ pos, long long begin, long long end, int I, int J,
+                                                    uint32_t *__restrict__ key);
+
 __global__ void __launch_bounds__(NT) histogramKernel(const float2 *__restrict__ pos, const uint8_t *__restrict__ dead,
-                                                      long long count, int I, int J, uint32_t *__restrict__ key,
-                                                      int32_t *__restrict__ cellCount)
+                                                      long long count, int I, int J, uint32_t cLo, uint32_t cHi,
+                                                      uint32_t *__restrict__ key, int32_t *__restrict__ cellCount)
 {
     const long long p = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
     if (p >= count) return;
@@ -153,6 +171,11 @@ __global__ void __launch_bounds__(NT) histogramKernel(const float2 *__restrict__
         return;
     }
     const uint32_t c = cellKey(pos[p], I, J);
+    if (c < cLo || c >= cHi)  // slab mode: outside the rows this rank keeps (cannot happen after a particle exchange)
+    {
+        key[p] = 0xFFFFFFFFu;
+        return;
+    }
     key[p] = c;
     atomicAdd(cellCount + c, 1);
 }
@@ -180,9 +203,9 @@ __device__ __forceinline__ bool particleLess(const float2 *__restrict__ pos, uin
 // Canonical order inside each cell: ascending (x, y, old index). One thread per cell; cells hold
 // O(particlesPerCell) entries so an insertion sort on the permutation is enough.
 __global__ void __launch_bounds__(NT) cellOrderKernel(const float2 *__restrict__ pos, const int32_t *__restrict__ cellStart,
-                                                      long long N, uint32_t *__restrict__ perm)
+                                                      long long cBegin, long long N, uint32_t *__restrict__ perm)
 {
-    const long long c = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    const long long c = cBegin + blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
     if (c >= N) return;
     const int32_t b = cellStart[c], e = cellStart[c + 1];
     for (int32_t a = b + 1; a < e; a++)
@@ -218,16 +241,23 @@ __global__ void __launch_bounds__(NT) gatherKernel(const uint32_t *__restrict__ 
     dead[s] = 0;
 }
 
+__global__ void __launch_bounds__(NT) cellKeyKernel(const float2 *__restrict__ pos, long long begin, long long end, int I, int J,
+                                                    uint32_t *__restrict__ key)
+{
+    const long long p = begin + blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    if (p < end) key[p] = cellKey(pos[p], I, J);
+}
+
 // ------------------------------------------------------------------ CFL velocity
 // maxParticleVelocity (flipsolver2d.cpp:1560-1574): max of vx*vx + vy*vy, initial value FLT_MIN.
 __global__ void __launch_bounds__(NT) maxVelocityKernel(const float2 *__restrict__ vel, const uint8_t *__restrict__ dead,
-                                                        long long count, unsigned int *__restrict__ outBits)
+                                                        long long count, OwnedRows own, unsigned int *__restrict__ outBits)
 {
     float m = 0.f;
     for (long long p = blockIdx.x * static_cast<long long>(NT) + threadIdx.x; p < count;
          p += static_cast<long long>(gridDim.x) * NT)
     {
-        if (dead[p]) continue;
+        if (dead[p] || !ownedParticle(own, p)) continue;
         const float2 v = vel[p];
         const float s = faddr(fmulr(v.x, v.x), fmulr(v.y, v.y));
         m = fmaxf(m, s);
@@ -278,10 +308,10 @@ __device__ float2 closestSurfacePoint(const GridView &sdf, float2 pos)
 __global__ void __launch_bounds__(NT) advectKernel(float2 *__restrict__ pos, uint8_t *__restrict__ dead,
                                                    uint8_t *__restrict__ mis, long long count,
                                                    VelocityView vel, GridView solidSdf, const int8_t *__restrict__ mat,
-                                                   int I, int J, float dt, unsigned long long *__restrict__ killed)
+                                                   int I, int J, float dt, OwnedRows own, unsigned long long *__restrict__ killed)
 {
     const long long p = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
-    if (p >= count || dead[p]) return;
+    if (p >= count || dead[p] || !ownedParticle(own, p)) return;
     const float2 before = pos[p];
     float2 x = rk4(vel, before, dt);
     if (gridLerp(solidSdf, x.x, x.y) < 0.f) x = closestSurfacePoint(solidSdf, x);
@@ -305,10 +335,10 @@ __global__ void __launch_bounds__(NT) particleUpdateKernel(const float2 *__restr
                                                            const uint8_t *__restrict__ dead, long long count,
                                                            VelocityView cur, VelocityView saved, float pic,
                                                            float *__restrict__ temperature, float *__restrict__ concentration,
-                                                           float ambient, float tempFactor, float concFactor)
+                                                           float ambient, float tempFactor, float concFactor, OwnedRows own)
 {
     const long long p = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
-    if (p >= count || dead[p]) return;
+    if (p >= count || dead[p] || !ownedParticle(own, p)) return;
     const float2 x = pos[p];
     const float2 oldV = velocityAt(saved, x.x, x.y);
     const float2 newV = velocityAt(cur, x.x, x.y);
@@ -323,10 +353,10 @@ __global__ void __launch_bounds__(NT) particleUpdateKernel(const float2 *__restr
 // adjustParticlesByDensityThread (flipsolver2d.cpp:261-303)
 __global__ void __launch_bounds__(NT) densityAdjustKernel(float2 *__restrict__ pos, const uint8_t *__restrict__ dead,
                                                           uint8_t *__restrict__ mis, long long count, const double *__restrict__ pressure,
-                                                          const int8_t *__restrict__ mat, int I, int J, float scale)
+                                                          const int8_t *__restrict__ mat, int I, int J, float scale, OwnedRows own)
 {
     const long long p = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
-    if (p >= count || dead[p]) return;
+    if (p >= count || dead[p] || !ownedParticle(own, p)) return;
     float2 x = pos[p];
     const int iCorr = clampi(static_cast<int>(fsubr(x.x, 0.5f)), 0, I);
     const int jCorr = clampi(static_cast<int>(fsubr(x.y, 0.5f)), 0, J);
@@ -356,10 +386,10 @@ __global__ void __launch_bounds__(NT) densityAdjustKernel(float2 *__restrict__ p
 
 // countParticles (flipsolver2d.cpp:1021-1051): per-cell count, particles beyond 2*ppc die.
 __global__ void __launch_bounds__(NT) countCapKernel(const int32_t *__restrict__ cellStart, const uint8_t *__restrict__ mis,
-                                                     long long N, int cap, int32_t *__restrict__ counts,
+                                                     long long cBegin, long long N, int cap, int32_t *__restrict__ counts,
                                                      uint8_t *__restrict__ dead, unsigned long long *__restrict__ killed)
 {
-    const long long c = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    const long long c = cBegin + blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
     if (c >= N) return;
     const int32_t b = cellStart[c], e = cellStart[c + 1];
     // only particles filed in this cell's own bin are seen by the reference's loop (binForGridIdx(i2d))
@@ -407,10 +437,11 @@ __global__ void __launch_bounds__(NT) pruneBandKernel(const float2 *__restrict__
 // Candidate count per cell. Water/smoke/fire: SOURCE cells short of ppc/2 (flipsolver2d.cpp:632-667,
 // flipsmokesolver.cpp:155-176). NBFlip: SOURCE or band cells short of ppc (nbflipsolver.cpp:143-160).
 __global__ void __launch_bounds__(NT) reseedPlanKernel(const int8_t *__restrict__ mat, const int32_t *__restrict__ counts,
-                                                       const float *__restrict__ fluidSdf, long long N, int ppc, int nbflip,
-                                                       float narrowBand, float resamplingBand, int32_t *__restrict__ want)
+                                                       const float *__restrict__ fluidSdf, long long cBegin, long long N, int ppc,
+                                                       int nbflip, float narrowBand, float resamplingBand,
+                                                       int32_t *__restrict__ want)
 {
-    const long long c = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    const long long c = cBegin + blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
     if (c > N) return;
     int32_t w = 0;
     if (c < N)
@@ -447,9 +478,10 @@ __global__ void __launch_bounds__(NT) reseedApplyKernel(const int32_t *__restric
                                                         float2 *__restrict__ pos, float2 *__restrict__ velOut,
                                                         float *__restrict__ props, long long cap, long long base,
                                                         uint8_t *__restrict__ dead, uint8_t *__restrict__ mis,
+                                                        uint32_t *__restrict__ key, long long cBegin,
                                                         unsigned long long *__restrict__ rejected)
 {
-    const long long c = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    const long long c = cBegin + blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
     if (c >= N) return;
     const int32_t b = offset[c], e = offset[c + 1];
     if (e == b) return;
@@ -493,6 +525,7 @@ __global__ void __launch_bounds__(NT) reseedApplyKernel(const int32_t *__restric
         velOut[slot] = v;
         dead[slot] = reject ? 1 : 0;
         mis[slot] = FS2D_MIS_HOME;
+        key[slot] = static_cast<uint32_t>(c);
         if (reject) atomicAdd(rejected, 1ull);
     }
 }
@@ -529,6 +562,27 @@ GridView fuelView(const Ctx *c)
 {
     return c->smokeGridsAdvected ? makeView(c->fuel, c->I, c->J, 0.5f, 0.5f, FS2D_OOB_EXTEND)
                                  : makeView(c->fuel, c->I, c->J, 0.f, 0.f, FS2D_OOB_CONST, 0.f);
+}
+
+static OwnedRows ownedRows(const Ctx *ctx)
+{
+    OwnedRows o;
+    const bool slab = ctx->slab.enabled && ctx->slab.world > 1;
+    o.key = slab ? ctx->pb[ctx->cur].key : nullptr;
+    o.J = static_cast<uint32_t>(ctx->J);
+    o.rowBegin = ctx->slab.rowBegin;
+    o.rowEnd = ctx->slab.rowEnd;
+    return o;
+}
+
+// Cell keys of particles [begin, end) of the current buffer (uploads and appends; the sort recomputes them).
+int particlesKeyRange(Ctx *ctx, int64_t begin, int64_t end)
+{
+    if (end <= begin) return FS2D_OK;
+    cellKeyKernel<<<gridFor(end - begin), NT, 0, ctx->stream>>>(ctx->pb[ctx->cur].pos, begin, end, ctx->I, ctx->J, ctx->pb[ctx->cur].key);
+    ctx->launches++;
+    FS2D_CUDA(cudaGetLastError());
+    return FS2D_OK;
 }
 
 int particlesReserve(Ctx *ctx, int64_t capacity)
@@ -581,7 +635,7 @@ int particlesReserve(Ctx *ctx, int64_t capacity)
 int particlesAliveCount(Ctx *ctx, int64_t *out)
 {
     FS2D_TRY(fetchKilled(ctx));
-    *out = ctx->count - ctx->deadCount;
+    *out = ctx->count - ctx->deadCount - ctx->slab.ghostCount;  // slab mode: ghost copies belong to a neighbour
     return FS2D_OK;
 }
 
@@ -593,12 +647,19 @@ int particlesMaxVelocity(Ctx *ctx, float *out)
     if (ctx->count > 0)
     {
         const int blocks = std::min(gridFor(ctx->count), ctx->smCount * 16);
-        maxVelocityKernel<<<blocks, NT, 0, ctx->stream>>>(ctx->pb[ctx->cur].vel, ctx->dead, ctx->count, bits);
+        maxVelocityKernel<<<blocks, NT, 0, ctx->stream>>>(ctx->pb[ctx->cur].vel, ctx->dead, ctx->count, ownedRows(ctx), bits);
         ctx->launches++;
     }
     unsigned int r = 0;
     FS2D_CUDA(cudaMemcpyAsync(&r, bits, sizeof(r), cudaMemcpyDeviceToHost, ctx->stream));
     FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->slab.enabled && ctx->slab.world > 1)
+    {
+        // the CFL step is global: max over ranks (non-negative floats order as their bit patterns)
+        long long v[4] = {static_cast<long long>(r), 0, 0, 0}, all[4 * FS2D_MAX_RANKS];
+        FS2D_TRY(slabAllGather(ctx, v, all));
+        for (int k = 0; k < ctx->slab.world; k++) r = std::max(r, static_cast<unsigned int>(all[4 * k]));
+    }
     float sq;
     memcpy(&sq, &r, sizeof(sq));
     *out = sqrtf(sq);
@@ -610,7 +671,7 @@ int particlesAdvect(Ctx *ctx)
     if (ctx->count == 0) return FS2D_OK;
     advectKernel<<<gridFor(ctx->count), NT, 0, ctx->stream>>>(ctx->pb[ctx->cur].pos, ctx->dead, ctx->pb[ctx->cur].mis, ctx->count,
                                                              makeVelocityView(ctx->U, ctx->V, ctx->I, ctx->J),
-                                                             solidSdfView(ctx), ctx->material, ctx->I, ctx->J, ctx->stepDt,
+                                                             solidSdfView(ctx), ctx->material, ctx->I, ctx->J, ctx->stepDt, ownedRows(ctx),
                                                              reinterpret_cast<unsigned long long *>(ctx->d_counter));
     ctx->launches++;
     ctx->killedDirty = true;
@@ -619,26 +680,39 @@ int particlesAdvect(Ctx *ctx)
     return FS2D_OK;
 }
 
+// Local counting sort of everything in the particle arrays (in slab mode: owned particles and ghosts). Cells
+// outside the rows [rows.lo, rows.hi) hold no particle, so the histogram / scan / order passes only cover those.
 int particlesSort(Ctx *ctx)
 {
-    const int64_t N = ctx->N;
+    const bool slab = ctx->slab.enabled && ctx->slab.world > 1;
+    const SlabRows rows = slab ? slabExt(ctx, ctx->slab.ghost) : SlabRows{0, ctx->I};
+    const int64_t cLo = static_cast<int64_t>(rows.lo) * ctx->J, cHi = static_cast<int64_t>(rows.hi) * ctx->J;
+    const int64_t cells = cHi - cLo;
     cudaStream_t st = ctx->stream;
-    FS2D_CUDA(cudaMemsetAsync(ctx->cellCursor, 0, sizeof(int32_t) * (N + 1), st));
+    FS2D_CUDA(cudaMemsetAsync(ctx->cellCursor + cLo, 0, sizeof(int32_t) * (cells + 1), st));
     ParticleBuffers &in = ctx->pb[ctx->cur];
     ParticleBuffers &out = ctx->pb[ctx->cur ^ 1];
     if (ctx->count > 0)
     {
-        histogramKernel<<<gridFor(ctx->count), NT, 0, st>>>(in.pos, ctx->dead, ctx->count, ctx->I, ctx->J, in.key, ctx->cellCursor);
+        histogramKernel<<<gridFor(ctx->count), NT, 0, st>>>(in.pos, ctx->dead, ctx->count, ctx->I, ctx->J, static_cast<uint32_t>(cLo),
+                                                            static_cast<uint32_t>(cHi), in.key, ctx->cellCursor);
         ctx->launches++;
     }
-    exclusiveScan(ctx, ctx->cellCursor, ctx->cellStart, N + 1);
-    int32_t alive = 0;
-    FS2D_CUDA(cudaMemcpyAsync(&alive, ctx->cellStart + N, sizeof(alive), cudaMemcpyDeviceToHost, st));
-    FS2D_CUDA(cudaMemsetAsync(ctx->cellCursor, 0, sizeof(int32_t) * (N + 1), st));
+    exclusiveScan(ctx, ctx->cellCursor + cLo, ctx->cellStart + cLo, cells + 1);
+    int32_t alive = 0, ownedRange[2] = {0, 0};
+    FS2D_CUDA(cudaMemcpyAsync(&alive, ctx->cellStart + cHi, sizeof(alive), cudaMemcpyDeviceToHost, st));
+    if (slab)
+    {
+        FS2D_CUDA(cudaMemcpyAsync(&ownedRange[0], ctx->cellStart + static_cast<int64_t>(ctx->slab.rowBegin) * ctx->J, sizeof(int32_t),
+                                  cudaMemcpyDeviceToHost, st));
+        FS2D_CUDA(cudaMemcpyAsync(&ownedRange[1], ctx->cellStart + static_cast<int64_t>(ctx->slab.rowEnd) * ctx->J, sizeof(int32_t),
+                                  cudaMemcpyDeviceToHost, st));
+    }
+    FS2D_CUDA(cudaMemsetAsync(ctx->cellCursor + cLo, 0, sizeof(int32_t) * (cells + 1), st));
     if (ctx->count > 0)
     {
         scatterKernel<<<gridFor(ctx->count), NT, 0, st>>>(in.key, ctx->count, ctx->cellStart, ctx->cellCursor, ctx->perm);
-        cellOrderKernel<<<gridFor(N), NT, 0, st>>>(in.pos, ctx->cellStart, N, ctx->perm);
+        cellOrderKernel<<<gridFor(cells), NT, 0, st>>>(in.pos, ctx->cellStart, cLo, cHi, ctx->perm);
         ctx->launches += 2;
     }
     FS2D_CUDA(cudaStreamSynchronize(st));
@@ -655,8 +729,22 @@ int particlesSort(Ctx *ctx)
     ctx->deadCount = 0;
     ctx->killedDirty = false;
     ctx->sorted = true;
+    if (slab)
+    {
+        ctx->slab.ownedBegin = ownedRange[0];
+        ctx->slab.ownedEnd = ownedRange[1];
+        ctx->slab.ghostCount = alive - (ownedRange[1] - ownedRange[0]);
+    }
     FS2D_CUDA(cudaGetLastError());
     return FS2D_OK;
+}
+
+// pruneParticles + rebinParticles; in slab mode preceded by the exchange of migrants and ghosts with the row
+// neighbours (collective: every rank calls it at the same points of the substep).
+int particlesRebin(Ctx *ctx)
+{
+    FS2D_TRY(slabExchangeParticles(ctx));
+    return particlesSort(ctx);
 }
 
 int particlesUpdate(Ctx *ctx)
@@ -676,7 +764,8 @@ int particlesUpdate(Ctx *ctx)
     }
     particleUpdateKernel<<<gridFor(ctx->count), NT, 0, ctx->stream>>>(
         b.pos, b.vel, ctx->dead, ctx->count, makeVelocityView(ctx->U, ctx->V, ctx->I, ctx->J),
-        makeVelocityView(ctx->savedU, ctx->savedV, ctx->I, ctx->J), ctx->p.pic_ratio, t, c, ctx->p.ambient_temperature, tf, cf);
+        makeVelocityView(ctx->savedU, ctx->savedV, ctx->I, ctx->J), ctx->p.pic_ratio, t, c, ctx->p.ambient_temperature, tf, cf,
+        ownedRows(ctx));
     ctx->launches++;
     FS2D_CUDA(cudaGetLastError());
     return FS2D_OK;
@@ -689,7 +778,7 @@ int particlesAdjustByDensity(Ctx *ctx)
     const float scale = static_cast<float>(static_cast<double>(ctx->stepDt * ctx->stepDt) /
                                            (ctx->p.fluid_density * ctx->p.dx * ctx->p.dx));
     densityAdjustKernel<<<gridFor(ctx->count), NT, 0, ctx->stream>>>(ctx->pb[ctx->cur].pos, ctx->dead, ctx->pb[ctx->cur].mis, ctx->count, ctx->x,
-                                                                    ctx->material, ctx->I, ctx->J, scale);
+                                                                    ctx->material, ctx->I, ctx->J, scale, ownedRows(ctx));
     ctx->launches++;
     ctx->sorted = false;
     FS2D_CUDA(cudaGetLastError());
@@ -699,7 +788,9 @@ int particlesAdjustByDensity(Ctx *ctx)
 int particlesCount(Ctx *ctx)
 {
     if (!ctx->sorted) FS2D_TRY(particlesSort(ctx));
-    countCapKernel<<<gridFor(ctx->N), NT, 0, ctx->stream>>>(ctx->cellStart, ctx->pb[ctx->cur].mis, ctx->N,
+    const SlabRows own = slabOwn(ctx);
+    const int64_t cLo = static_cast<int64_t>(own.lo) * ctx->J, cHi = static_cast<int64_t>(own.hi) * ctx->J;
+    countCapKernel<<<gridFor(cHi - cLo), NT, 0, ctx->stream>>>(ctx->cellStart, ctx->pb[ctx->cur].mis, cLo, cHi,
                                                            2 * ctx->p.particles_per_cell, ctx->counts, ctx->dead,
                                                            reinterpret_cast<unsigned long long *>(ctx->d_counter));
     ctx->launches++;
@@ -724,12 +815,16 @@ int particlesPruneNarrowBand(Ctx *ctx)
 int particlesReseedPlan(Ctx *ctx, int64_t *candidates)
 {
     const int nb = ctx->p.sim_type == FS2D_SIM_NBFLIP ? 1 : 0;
-    reseedPlanKernel<<<gridFor(ctx->N + 1), NT, 0, ctx->stream>>>(ctx->material, ctx->counts, ctx->fluidSdf, ctx->N,
-                                                                 ctx->p.particles_per_cell, nb, -3.f, -1.f, ctx->reseedOffset);
+    // slab mode: every rank plans its own rows; the host mirror strings the ranks' draws together in rank order,
+    // which IS the reference's row-major cell order
+    const SlabRows own = slabOwn(ctx);
+    const int64_t cLo = static_cast<int64_t>(own.lo) * ctx->J, cHi = static_cast<int64_t>(own.hi) * ctx->J;
+    reseedPlanKernel<<<gridFor(cHi - cLo + 1), NT, 0, ctx->stream>>>(ctx->material, ctx->counts, ctx->fluidSdf, cLo, cHi,
+                                                                    ctx->p.particles_per_cell, nb, -3.f, -1.f, ctx->reseedOffset);
     ctx->launches++;
-    exclusiveScan(ctx, ctx->reseedOffset, ctx->reseedOffset, ctx->N + 1);
+    exclusiveScan(ctx, ctx->reseedOffset + cLo, ctx->reseedOffset + cLo, cHi - cLo + 1);
     int32_t total = 0;
-    FS2D_CUDA(cudaMemcpyAsync(&total, ctx->reseedOffset + ctx->N, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
+    FS2D_CUDA(cudaMemcpyAsync(&total, ctx->reseedOffset + cHi, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
     FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->reseedCandidates = total;
     *candidates = total;
@@ -751,8 +846,14 @@ int particlesReseedApply(Ctx *ctx, int64_t candidates, const float *hostUniform)
         return FS2D_ERR_STATE;
     }
     FS2D_TRY(particlesReserve(ctx, ctx->count + candidates));
-    float *du = nullptr;
-    FS2D_CUDA(cudaMalloc(reinterpret_cast<void **>(&du), sizeof(float) * 2 * candidates));
+    if (2 * candidates > ctx->reseedUniformCapacity)  // persistent: cudaFree synchronises the device, keep it off the step path
+    {
+        if (ctx->reseedUniform) cudaFree(ctx->reseedUniform);
+        ctx->reseedUniform = nullptr;
+        ctx->reseedUniformCapacity = std::max<int64_t>(4 * candidates, 1 << 16);
+        FS2D_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->reseedUniform), sizeof(float) * ctx->reseedUniformCapacity));
+    }
+    float *du = ctx->reseedUniform;
     FS2D_CUDA(cudaMemcpyAsync(du, hostUniform, sizeof(float) * 2 * candidates, cudaMemcpyHostToDevice, ctx->stream));
     ParticleBuffers &b = ctx->pb[ctx->cur];
     ReseedArgs a;
@@ -769,16 +870,17 @@ int particlesReseedApply(Ctx *ctx, int64_t candidates, const float *hostUniform)
     a.resamplingBand = -1.f;
     const bool smoke = ctx->p.sim_type == FS2D_SIM_SMOKE || ctx->p.sim_type == FS2D_SIM_FIRE;
     GridView none = makeView(nullptr, 1, 1, 0.f, 0.f);
-    reseedApplyKernel<<<gridFor(ctx->N), NT, 0, ctx->stream>>>(
-        ctx->reseedOffset, ctx->N, du, ctx->material, ctx->emitterId, ctx->sources,
+    const SlabRows own = slabOwn(ctx);
+    const int64_t cLo = static_cast<int64_t>(own.lo) * ctx->J, cHi = static_cast<int64_t>(own.hi) * ctx->J;
+    reseedApplyKernel<<<gridFor(cHi - cLo), NT, 0, ctx->stream>>>(
+        ctx->reseedOffset, cHi, du, ctx->material, ctx->emitterId, ctx->sources,
         makeVelocityView(ctx->U, ctx->V, ctx->I, ctx->J), fluidSdfView(ctx), viscosityView(ctx),
         smoke ? temperatureView(ctx) : none, smoke ? concentrationView(ctx) : none,
         ctx->p.sim_type == FS2D_SIM_FIRE ? fuelView(ctx) : none, a, b.pos, b.vel, b.props, b.capacity, ctx->count, ctx->dead, b.mis,
-        reinterpret_cast<unsigned long long *>(ctx->d_counter));
+        b.key, cLo, reinterpret_cast<unsigned long long *>(ctx->d_counter));
     ctx->launches++;
     FS2D_CUDA(cudaGetLastError());
     FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(du);
     ctx->count += candidates;
     ctx->killedDirty = true;
     ctx->sorted = false;

@@ -20,6 +20,7 @@
 // (linearsolver.h:15-20); arithmetic uses explicit non-contracted mul/add in the reference's
 // evaluation order so a single operator application is bit-identical to the strict oracle.
 #include <algorithm>
+#include <cstring>
 
 #include "fs2d_internal.h"
 
@@ -54,6 +55,85 @@ struct PcgArgs
     int compat;               // 1: convergence decided by the range kernel
     const int *activeTiles;   // ordered list of tiles that can hold non-zero entries (nullptr: all tiles)
     const int *activeCount;
+};
+
+// Slab mode (several GPUs, slab.cu): the two reductions of an iteration become all-reduces and the operators need
+// one halo row from each row neighbour. Both ride on the iteration kernels themselves:
+//   * the last CTA of a kernel PUSHES its rank's partial sums into a mail slot of every rank (peer-mapped
+//     store + tag), and every CTA of the NEXT kernel starts by waiting for the tags in its own memory and adding
+//     the partials in rank order -- every CTA of every rank derives bit-identical alpha / beta / err;
+//   * the CTAs that own a slab-boundary row store their q (K1) or z (K2) values of that row straight into the
+//     neighbour's array as well; the tag that carries the partial sum also publishes those rows.
+// The derived vectors s and r are kept up to date on the halo rows redundantly (same inputs, same beta/alpha
+// -> same bits as on the owner). Phase p of a solve: 0 = init, 2i+1 = K1(i), 2i+2 = K2(i); slot (p & 7) of the
+// half of the ring selected by the parity of the solve.
+struct MgArgs
+{
+    int rank, world;
+    int rowBegin, rowEnd;                 // owned cell rows
+    int tileBase;                         // first owned tile (dense walk)
+    int phase;                            // phase this kernel PRODUCES
+    int iter;                             // iteration index i
+    int ringBase;                         // 0 or 8
+    unsigned long long solveTag;          // solve sequence << 20
+    SlabMail *mail;
+    SlabMail *peerMail[FS2D_MAX_RANKS];
+    double *loOut1, *hiOut1;              // the row neighbours' copies of out1 (nullptr at the domain ends)
+    int iterLimit;
+};
+
+constexpr long long MG_SPIN_LIMIT = 8000000000ll;
+
+// Sum (v0) and max (v1) over ranks of the partials published for `phase`; spins until every rank's tag is there.
+__device__ __forceinline__ bool mgCollect(const MgArgs &m, int phase, bool wait, double *sum, double *mx)
+{
+    const unsigned long long want = m.solveTag + static_cast<unsigned long long>(phase) + 1ull;
+    double s = 0.0, x = 0.0;
+    for (int r = 0; r < m.world; r++)
+    {
+        const SlabPcgSlot *slot = &m.mail->pcg[m.ringBase + (phase & 7)][r];
+        if (wait)
+        {
+            const volatile unsigned long long *tag = &slot->tag;
+            const long long t0 = clock64();
+            while (*tag != want)
+            {
+                if (clock64() - t0 > MG_SPIN_LIMIT)
+                {
+                    m.mail->error = 1;
+                    return false;
+                }
+            }
+            __threadfence_system();
+        }
+        const double v0 = *reinterpret_cast<const volatile double *>(&slot->v0);
+        const double v1 = *reinterpret_cast<const volatile double *>(&slot->v1);
+        s += v0;
+        x = fmax(x, v1);
+    }
+    *sum = s;
+    *mx = x;
+    return true;
+}
+
+// Publish this rank's partials for m.phase in every rank's mail (threads 0..world-1 of the last CTA).
+__device__ __forceinline__ void mgPublish(const MgArgs &m, double v0, double v1)
+{
+    const int r = threadIdx.x;
+    if (r < m.world)
+    {
+        SlabPcgSlot *slot = &m.peerMail[r]->pcg[m.ringBase + (m.phase & 7)][m.rank];
+        *reinterpret_cast<volatile double *>(&slot->v0) = v0;
+        *reinterpret_cast<volatile double *>(&slot->v1) = v1;
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long *>(&slot->tag) = m.solveTag + static_cast<unsigned long long>(m.phase) + 1ull;
+    }
+}
+
+struct MgScalars
+{
+    double coef, alphaPrev;
+    int done;
 };
 
 __device__ __forceinline__ double warpSum(double v)
@@ -133,7 +213,7 @@ __device__ __forceinline__ double rowM(uint16_t info, const double *pre, double 
 // Per-CTA partial sums -> the last CTA to arrive reduces them in a fixed order and updates the
 // device-resident scalars (alpha after K1; sigma', err, convergence decision and beta after K2).
 template <int MODE>
-__device__ void finishReductions(const PcgArgs &a, double accDot, double accMax, double *red, int *isLastShared)
+__device__ void finishReductions(const PcgArgs &a, double accDot, double accMax, double *red, int *isLastShared, const MgArgs *mg = nullptr)
 {
     const int tid = threadIdx.x;
     const int nb = gridDim.x;
@@ -144,7 +224,10 @@ __device__ void finishReductions(const PcgArgs &a, double accDot, double accMax,
     {
         a.partials[blockIdx.x] = bs;
         if (MODE == MODE_K2) a.partials[nb + blockIdx.x] = bm;
-        __threadfence();
+        if (mg)
+            __threadfence_system();  // also orders this CTA's halo-row stores into the neighbours' arrays
+        else
+            __threadfence();
         unsigned int *ticket = (MODE == MODE_K1) ? &a.sc->ticketA : &a.sc->ticketB;
         *isLastShared = (atomicAdd(ticket, 1u) == static_cast<unsigned int>(nb - 1));
     }
@@ -154,6 +237,23 @@ __device__ void finishReductions(const PcgArgs &a, double accDot, double accMax,
     double total = finalReduce<false>(a.partials, nb, red);
     double emax = 0.0;
     if (MODE == MODE_K2) emax = finalReduce<true>(a.partials + nb, nb, red);
+    if (mg)
+    {
+        // slab mode: the scalars are derived by the consumers (mgPrologue); only publish the partials
+        __shared__ double pub[2];
+        if (tid == 0)
+        {
+            pub[0] = total;
+            pub[1] = emax;
+            if (MODE == MODE_K1)
+                a.sc->ticketA = 0;
+            else
+                a.sc->ticketB = 0;
+        }
+        __syncthreads();
+        mgPublish(*mg, pub[0], pub[1]);
+        return;
+    }
     if (tid == 0)
     {
         PcgScalars *sc = a.sc;
@@ -446,11 +546,103 @@ __device__ __forceinline__ void pipeIssue(PipeStage<MODE> &st, unsigned long lon
     }
 }
 
-template <int MODE> __global__ void __launch_bounds__(NT, 2) pcgPipeKernel(PcgArgs a, int numTiles)
+// Slab mode: thread 0 of every CTA waits for the partials of the previous phase from all ranks and derives the
+// scalars of this kernel; block 0 keeps the bookkeeping (iteration count, trace, convergence) in PcgScalars.
+template <int MODE> __device__ void mgPrologue(const PcgArgs &a, const MgArgs &m, MgScalars *out)
+{
+    MgScalars r;
+    r.coef = 0.0;
+    r.alphaPrev = 0.0;
+    r.done = 0;
+    const int i = m.iter;
+    double sA = 0.0, mA = 0.0, sB = 0.0, sC = 0.0, dummy = 0.0;
+    if (MODE == MODE_K1)
+    {
+        // waits for phase 2i: init (i = 0) or K2(i-1)
+        if (!mgCollect(m, 2 * i, true, &sA, &mA))
+        {
+            r.done = 1;
+            a.sc->done = 1;  // a lost peer: let the remaining launches of this solve fall through
+        }
+        if (i == 0)
+        {
+            if (!(mA > 1.0e-15)) r.done = 1;  // VOps::isZero (vmath.cpp:47-58): x = 0, zero iterations
+            if (blockIdx.x == 0)
+            {
+                PcgScalars *sc = a.sc;
+                sc->sigma = sA;
+                sc->alpha = sc->beta = sc->gamma = sc->err = 0.0;
+                sc->iter = 0;
+                sc->result = 0;
+                if (r.done) sc->done = 1;
+            }
+        }
+        else
+        {
+            mgCollect(m, 2 * i - 1, false, &sB, &dummy);  // gamma_{i-1}
+            mgCollect(m, 2 * i - 2, false, &sC, &dummy);  // sigma_{i-1}
+            r.alphaPrev = sC / (sB + 1e-8);                // linearsolver.cpp:50
+            double beta = 0.0;
+            if (mA <= a.tol)                               // :59-61
+                r.done = 1;
+            else
+                beta = sA / sC;                            // :66-67
+            r.coef = beta;
+            if (blockIdx.x == 0)
+            {
+                PcgScalars *sc = a.sc;
+                const int it = i - 1;
+                sc->alpha = r.alphaPrev;
+                sc->gamma = sA;
+                sc->err = mA;
+                if (r.done)
+                {
+                    sc->done = 1;
+                    sc->result = it;
+                }
+                else
+                {
+                    sc->beta = beta;
+                    sc->sigma = sA;
+                }
+                if (a.trace && it < a.traceCapacity)
+                {
+                    a.trace[4 * it + 0] = r.alphaPrev;
+                    a.trace[4 * it + 1] = beta;
+                    a.trace[4 * it + 2] = sA;
+                    a.trace[4 * it + 3] = mA;
+                }
+                sc->iter = i;
+            }
+        }
+    }
+    else
+    {
+        // K2(i) waits for phase 2i+1 (gamma_i); sigma_i was published in phase 2i
+        if (!mgCollect(m, 2 * i + 1, true, &sB, &dummy))
+        {
+            r.done = 1;
+            a.sc->done = 1;
+        }
+        mgCollect(m, 2 * i, false, &sC, &dummy);
+        r.coef = sC / (sB + 1e-8);
+    }
+    *out = r;
+}
+
+template <int MODE, bool MG> __global__ void __launch_bounds__(NT, 2) pcgPipeKernel(PcgArgs a, int numTiles, MgArgs mg)
 {
     extern __shared__ __align__(128) unsigned char pipeRaw[];
     PipeSmem<MODE> &sm = *reinterpret_cast<PipeSmem<MODE> *>(pipeRaw);
     if (a.sc->done) return;
+    __shared__ MgScalars mgs;
+    if (MG)
+    {
+        if (threadIdx.x == 0) mgPrologue<MODE>(a, mg, &mgs);
+        __syncthreads();
+        if (mgs.done) return;
+        asm volatile("fence.proxy.async;" ::: "memory");  // halo rows written by a peer are read by bulk copies below
+    }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (MODE == MODE_K2 && tid < 8) sm.preTbl[tid] = a.pre[tid];
     if (tid == 0)
@@ -463,7 +655,12 @@ template <int MODE> __global__ void __launch_bounds__(NT, 2) pcgPipeKernel(PcgAr
     __syncthreads();
 
     double coef = 0.0, alphaPrev = 0.0;
-    if (MODE == MODE_K1)
+    if (MG)
+    {
+        coef = mgs.coef;
+        alphaPrev = mgs.alphaPrev;
+    }
+    else if (MODE == MODE_K1)
     {
         coef = a.sc->beta;
         alphaPrev = a.sc->alpha;
@@ -478,7 +675,7 @@ template <int MODE> __global__ void __launch_bounds__(NT, 2) pcgPipeKernel(PcgAr
     if (myTiles < 0) myTiles = 0;
     auto tileAt = [&](int k) -> int {
         const int t = blockIdx.x + k * gridDim.x;
-        return a.activeTiles ? a.activeTiles[t] : t;
+        return a.activeTiles ? a.activeTiles[t] : (MG ? mg.tileBase + t : t);
     };
     if (warp == 0 && myTiles > 0) pipeIssue<MODE>(sm.st[0], &sm.full[0], a, tileAt(0), lane);
 
@@ -529,6 +726,11 @@ template <int MODE> __global__ void __launch_bounds__(NT, 2) pcgPipeKernel(PcgAr
                 a.out0[n] = v;
                 if (MODE == MODE_K1) a.x[n] = __dadd_rn(st.x[(ar - 1) * TC + (c - 2)], __dmul_rn(bv, alphaPrev));
             }
+            else if (MG && c >= 2 && c < TC + 2 && gjj < J && ((ar == 0 && gi == mg.rowBegin - 1 && gi >= 0) || (gi == mg.rowEnd && gi < a.I && ar <= TR + 1)))
+            {
+                // halo row of the slab: the derived vector is kept current here too (the owner computes the same bits)
+                a.out0[gi * J + gjj] = v;
+            }
         }
         __syncthreads();
 
@@ -551,6 +753,11 @@ template <int MODE> __global__ void __launch_bounds__(NT, 2) pcgPipeKernel(PcgAr
                     else
                         o = rowM(static_cast<uint16_t>(info[q]), sm.preTbl, c, im, ip, jm, jp);
                     a.out1[n] = o;
+                    if (MG)
+                    {
+                        if (gi == mg.rowBegin && mg.loOut1) mg.loOut1[n] = o;
+                        if (gi == mg.rowEnd - 1 && mg.hiOut1) mg.hiOut1[n] = o;
+                    }
                     accDot += o * c;
                     accMax = fmax(accMax, fabs(c));
                 }
@@ -559,7 +766,7 @@ template <int MODE> __global__ void __launch_bounds__(NT, 2) pcgPipeKernel(PcgAr
         fenceProxyAsync();   // generic writes to this stage are ordered before the next bulk copy into it
         __syncthreads();
     }
-    finishReductions<MODE>(a, accDot, accMax, sm.red, &sm.isLast);
+    finishReductions<MODE>(a, accDot, accMax, sm.red, &sm.isLast, MG ? &mg : nullptr);
 }
 
 // Reference-compatible convergence value (vmath.cpp:100-136): for each ThreadPool range
@@ -648,12 +855,13 @@ __global__ void __launch_bounds__(NT) pcgRangeErrKernel(const double *r, long lo
 // In a dam-break scene ~9 % of the cells are fluid, so this removes ~90 % of the PCG traffic; the
 // iterates are the same numbers (only the grouping of the dot-product partials over CTAs changes).
 __global__ void __launch_bounds__(NT) pcgTileFlagKernel(const uint8_t *__restrict__ rowInfo, const double *__restrict__ rhs, int I, int J,
-                                                        int tilesJ, int *__restrict__ flags)
+                                                        int tilesJ, int tileBase, int *__restrict__ flags)
 {
     __shared__ int any;
     if (threadIdx.x == 0) any = 0;
     __syncthreads();
-    const int ti = blockIdx.x / tilesJ, tj = blockIdx.x - ti * tilesJ;
+    const int tile = tileBase + blockIdx.x;
+    const int ti = tile / tilesJ, tj = tile - ti * tilesJ;
     const int i0 = ti * TR, j0 = tj * TC;
     bool hit = false;
     for (int e = threadIdx.x; e < TR * TC; e += NT)
@@ -671,8 +879,8 @@ __global__ void __launch_bounds__(NT) pcgTileFlagKernel(const uint8_t *__restric
 }
 
 // Ordered compaction of the flagged tiles (a single CTA: there are only a few thousand tiles).
-__global__ void __launch_bounds__(1024) pcgTileCompactKernel(const int *__restrict__ flags, int tiles, int *__restrict__ list,
-                                                             int *__restrict__ count)
+__global__ void __launch_bounds__(1024) pcgTileCompactKernel(const int *__restrict__ flags, int tiles, int tileBase,
+                                                             int *__restrict__ list, int *__restrict__ count)
 {
     __shared__ int warpSums[32];
     __shared__ int carry;
@@ -705,7 +913,7 @@ __global__ void __launch_bounds__(1024) pcgTileCompactKernel(const int *__restri
         }
         __syncthreads();
         const int excl = incl - v + (warp > 0 ? warpSums[warp - 1] : 0) + carry;
-        if (v) list[excl] = idx;
+        if (v) list[excl] = tileBase + idx;
         __syncthreads();
         if (threadIdx.x == 1023) carry = excl + v;
         __syncthreads();
@@ -715,13 +923,18 @@ __global__ void __launch_bounds__(1024) pcgTileCompactKernel(const int *__restri
 
 // result = 0; residual = aux = rhs; search = aux after the first K1 (linearsolver.cpp:32-46);
 // sigma = rhs.rhs; zero test of :33-35.
+// Slab mode: the walk covers the owned rows plus one halo row each side [nLo, nHi) (the halo rows of r0 = z = rhs
+// come from the locally computed halo of the right-hand side); only owned cells [oLo, oHi) enter the sums, and
+// the last CTA publishes them as phase 0 instead of writing the scalars.
+template <bool MG>
 __global__ void __launch_bounds__(NT) pcgInitKernel(const double *rhs, double *x, double *r0, double *z, double *s0, double *r1,
-                                                    double *s1, double *q, long long N, double *partials, PcgScalars *sc)
+                                                    double *s1, double *q, long long N, double *partials, PcgScalars *sc,
+                                                    long long nLo, long long oLo, long long oHi, MgArgs mg)
 {
     __shared__ double red[8];
     __shared__ int isLast;
     double acc = 0.0, amax = 0.0;
-    for (long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x; n < N; n += static_cast<long long>(gridDim.x) * NT)
+    for (long long n = nLo + blockIdx.x * static_cast<long long>(NT) + threadIdx.x; n < N; n += static_cast<long long>(gridDim.x) * NT)
     {
         const double v = rhs[n];
         x[n] = 0.0;
@@ -734,6 +947,7 @@ __global__ void __launch_bounds__(NT) pcgInitKernel(const double *rhs, double *x
             s1[n] = 0.0;
             q[n] = 0.0;
         }
+        if (MG && (n < oLo || n >= oHi)) continue;
         acc += v * v;
         amax = fmax(amax, fabs(v));
     }
@@ -752,6 +966,24 @@ __global__ void __launch_bounds__(NT) pcgInitKernel(const double *rhs, double *x
     __threadfence();
     double total = finalReduce<false>(partials, nb, red);
     double emax = finalReduce<true>(partials + nb, nb, red);
+    if (MG)
+    {
+        __shared__ double pub[2];
+        if (threadIdx.x == 0)
+        {
+            pub[0] = total;
+            pub[1] = emax;
+            sc->done = 0;
+            sc->iter = 0;
+            sc->result = 0;
+            sc->ticketA = 0;
+            sc->ticketB = 0;
+            sc->ticketC = 0;
+        }
+        __syncthreads();
+        mgPublish(mg, pub[0], pub[1]);
+        return;
+    }
     if (threadIdx.x == 0)
     {
         sc->sigma = total;
@@ -769,7 +1001,7 @@ __global__ void __launch_bounds__(NT) pcgInitKernel(const double *rhs, double *x
 }
 
 // Pending x += alpha*s of the last executed iteration, and the return value.
-__global__ void __launch_bounds__(NT) pcgFinalizeKernel(double *x, const double *sEven, const double *sOdd, long long N,
+__global__ void __launch_bounds__(NT) pcgFinalizeKernel(double *x, const double *sEven, const double *sOdd, long long nLo, long long N,
                                                         PcgScalars *sc, int iterLimit)
 {
     const int iters = sc->iter;
@@ -777,7 +1009,7 @@ __global__ void __launch_bounds__(NT) pcgFinalizeKernel(double *x, const double 
     {
         const double alpha = sc->alpha;
         const double *s = (iters & 1) ? sOdd : sEven;
-        for (long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x; n < N;
+        for (long long n = nLo + blockIdx.x * static_cast<long long>(NT) + threadIdx.x; n < N;
              n += static_cast<long long>(gridDim.x) * NT)
             x[n] = __dadd_rn(x[n], __dmul_rn(s[n], alpha));
     }
@@ -786,6 +1018,44 @@ __global__ void __launch_bounds__(NT) pcgFinalizeKernel(double *x, const double 
 __global__ void pcgResultKernel(PcgScalars *sc, int iterLimit)
 {
     if (!sc->done) sc->result = iterLimit;
+    sc->done = 1;
+}
+
+// Slab mode, after the last K2: wait for its partials (one thread, so that no grid-sized kernel ever spins), close
+// the bookkeeping of the last iteration and leave alpha / iter for the pending x update of pcgFinalizeKernel.
+__global__ void pcgMgCloseKernel(PcgArgs a, MgArgs mg)
+{
+    PcgScalars *sc = a.sc;
+    const int L = mg.iterLimit - 1;
+    if (!sc->done && mg.iterLimit > 0)
+    {
+        double sA = 0.0, mA = 0.0, sB = 0.0, sC = 0.0, dummy = 0.0;
+        mgCollect(mg, 2 * L + 2, true, &sA, &mA);
+        mgCollect(mg, 2 * L + 1, false, &sB, &dummy);
+        mgCollect(mg, 2 * L, false, &sC, &dummy);
+        const double alpha = sC / (sB + 1e-8);
+        double beta = 0.0;
+        sc->alpha = alpha;
+        sc->gamma = sA;
+        sc->err = mA;
+        if (mA <= a.tol)
+            sc->result = L;
+        else
+        {
+            sc->result = mg.iterLimit;
+            beta = sA / sC;
+            sc->beta = beta;
+            sc->sigma = sA;
+        }
+        if (a.trace && L < a.traceCapacity)
+        {
+            a.trace[4 * L + 0] = alpha;
+            a.trace[4 * L + 1] = beta;
+            a.trace[4 * L + 2] = sA;
+            a.trace[4 * L + 3] = mA;
+        }
+        sc->iter = mg.iterLimit;
+    }
     sc->done = 1;
 }
 
@@ -820,16 +1090,33 @@ static bool pipeUsable(const Ctx *ctx) { return (ctx->J % 2) == 0 && !ctx->force
 
 int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
 {
-    const int blocks = pcgTileBlocks(ctx);
+    const bool mgOn = ctx->slab.enabled && ctx->slab.world > 1;
+    const int tilesJ = divUp(ctx->J, TC);
+    int blocks = pcgTileBlocks(ctx);  // tiles this rank walks
+    int tileBase = 0;
+    if (mgOn)
+    {
+        const int t0 = ctx->slab.rowBegin / TR, t1 = divUp(ctx->slab.rowEnd, TR);
+        tileBase = t0 * tilesJ;
+        blocks = (t1 - t0) * tilesJ;
+    }
     const bool pipe = pipeUsable(ctx);
-    const int pipeBlocks = std::min(blocks, 2 * ctx->smCount);
+    if (mgOn && (!pipe || ctx->p.convergence_threads > 0))
+    {
+        ctx->lastError = "pcg: slab mode needs the pipelined kernels (even gridSizeJ) and convergence_threads = 0";
+        return FS2D_ERR_STATE;
+    }
+    const int share = mgOn ? ctx->slab.share : 1;
+    const int pipeBlocks = std::max(1, std::min(blocks, 2 * ctx->smCount / share));
     if (pipe)
     {
-        cudaFuncSetAttribute(pcgPipeKernel<MODE_K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(PipeSmem<MODE_K1>)));
-        cudaFuncSetAttribute(pcgPipeKernel<MODE_K2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(PipeSmem<MODE_K2>)));
+        cudaFuncSetAttribute(pcgPipeKernel<MODE_K1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(PipeSmem<MODE_K1>)));
+        cudaFuncSetAttribute(pcgPipeKernel<MODE_K2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(PipeSmem<MODE_K2>)));
+        cudaFuncSetAttribute(pcgPipeKernel<MODE_K1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(PipeSmem<MODE_K1>)));
+        cudaFuncSetAttribute(pcgPipeKernel<MODE_K2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(PipeSmem<MODE_K2>)));
     }
-    const int flat = ctx->smCount * 8;
-    if (blocks > ctx->maxBlocks || flat > ctx->maxBlocks)
+    const int flat = std::max(1, ctx->smCount * 8 / share);
+    if (pcgTileBlocks(ctx) > ctx->maxBlocks || flat > ctx->maxBlocks)
     {
         ctx->lastError = "pcg: partials buffer too small";
         return FS2D_ERR_STATE;
@@ -844,6 +1131,40 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
         return FS2D_ERR_ARG;
     }
 
+    MgArgs mg;
+    memset(&mg, 0, sizeof(mg));
+    long long nLo = 0, nHi = ctx->N, oLo = 0, oHi = ctx->N;
+    auto peerOf = [&](int r, double *p) -> double * {
+        if (r < 0 || r >= ctx->slab.world) return nullptr;
+        return reinterpret_cast<double *>(ctx->slab.peerHeap[r] + (reinterpret_cast<unsigned char *>(p) - ctx->heap));
+    };
+    if (mgOn)
+    {
+        SlabState &sl = ctx->slab;
+        if (sl.connected != sl.world - 1)
+        {
+            ctx->lastError = "pcg: slab peers are not connected";
+            return FS2D_ERR_COMM;
+        }
+        sl.solveSeq++;
+        mg.rank = sl.rank;
+        mg.world = sl.world;
+        mg.rowBegin = sl.rowBegin;
+        mg.rowEnd = sl.rowEnd;
+        mg.tileBase = tileBase;
+        mg.ringBase = static_cast<int>(sl.solveSeq & 1ull) * 8;
+        mg.solveTag = sl.solveSeq << 20;
+        mg.mail = ctx->mail;
+        for (int r = 0; r < sl.world; r++)
+            mg.peerMail[r] = reinterpret_cast<SlabMail *>(sl.peerHeap[r] + (reinterpret_cast<unsigned char *>(ctx->mail) - ctx->heap));
+        mg.iterLimit = iterLimit;
+        const SlabRows ext = slabExt(ctx, 1);
+        nLo = static_cast<long long>(ext.lo) * ctx->J;
+        nHi = static_cast<long long>(ext.hi) * ctx->J;
+        oLo = static_cast<long long>(sl.rowBegin) * ctx->J;
+        oHi = static_cast<long long>(sl.rowEnd) * ctx->J;
+    }
+
     const bool prof = ctx->profilePcg;
     if (prof)
         while (static_cast<int>(ctx->profEvents.size()) < 2 * iterLimit + 1)
@@ -853,13 +1174,22 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
             ctx->profEvents.push_back(e);
         }
     const bool active = pipe && !ctx->densePcg;
-    pcgInitKernel<<<flat, NT, 0, st>>>(ctx->rhs, ctx->x, ctx->r[0], ctx->z, ctx->s[0], active ? ctx->r[1] : nullptr, ctx->s[1], ctx->q,
-                                       ctx->N, ctx->partials, ctx->scalars);
+    if (mgOn)
+    {
+        mg.phase = 0;
+        pcgInitKernel<true><<<flat, NT, 0, st>>>(ctx->rhs, ctx->x, ctx->r[0], ctx->z, ctx->s[0], active ? ctx->r[1] : nullptr, ctx->s[1], ctx->q,
+                                                 nHi, ctx->partials, ctx->scalars, nLo, oLo, oHi, mg);
+    }
+    else
+    {
+        pcgInitKernel<false><<<flat, NT, 0, st>>>(ctx->rhs, ctx->x, ctx->r[0], ctx->z, ctx->s[0], active ? ctx->r[1] : nullptr, ctx->s[1],
+                                                  ctx->q, ctx->N, ctx->partials, ctx->scalars, 0, 0, ctx->N, mg);
+    }
     ctx->launches++;
     if (active)
     {
-        pcgTileFlagKernel<<<blocks, NT, 0, st>>>(ctx->rowInfo, ctx->rhs, ctx->I, ctx->J, a.tilesJ, ctx->tileFlags);
-        pcgTileCompactKernel<<<1, 1024, 0, st>>>(ctx->tileFlags, blocks, ctx->activeTiles, ctx->activeCount);
+        pcgTileFlagKernel<<<blocks, NT, 0, st>>>(ctx->rowInfo, ctx->rhs, ctx->I, ctx->J, a.tilesJ, tileBase, ctx->tileFlags);
+        pcgTileCompactKernel<<<1, 1024, 0, st>>>(ctx->tileFlags, blocks, tileBase, ctx->activeTiles, ctx->activeCount);
         ctx->launches += 2;
         a.activeTiles = ctx->activeTiles;
         a.activeCount = ctx->activeCount;
@@ -873,8 +1203,16 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
         k1.out0 = ctx->s[(i + 1) & 1];
         k1.out1 = ctx->q;
         k1.x = ctx->x;
-        if (pipe)
-            pcgPipeKernel<MODE_K1><<<pipeBlocks, NT, sizeof(PipeSmem<MODE_K1>), st>>>(k1, blocks);
+        if (mgOn)
+        {
+            mg.iter = i;
+            mg.phase = 2 * i + 1;
+            mg.loOut1 = peerOf(mg.rank - 1, ctx->q);
+            mg.hiOut1 = peerOf(mg.rank + 1, ctx->q);
+            pcgPipeKernel<MODE_K1, true><<<pipeBlocks, NT, sizeof(PipeSmem<MODE_K1>), st>>>(k1, blocks, mg);
+        }
+        else if (pipe)
+            pcgPipeKernel<MODE_K1, false><<<pipeBlocks, NT, sizeof(PipeSmem<MODE_K1>), st>>>(k1, blocks, mg);
         else
             pcgTileKernel<MODE_K1><<<blocks, NT, 0, st>>>(k1);
         if (prof) cudaEventRecord(ctx->profEvents[2 * i + 1], st);
@@ -883,8 +1221,15 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
         k2.in1 = ctx->q;
         k2.out0 = ctx->r[(i + 1) & 1];
         k2.out1 = ctx->z;
-        if (pipe)
-            pcgPipeKernel<MODE_K2><<<pipeBlocks, NT, sizeof(PipeSmem<MODE_K2>), st>>>(k2, blocks);
+        if (mgOn)
+        {
+            mg.phase = 2 * i + 2;
+            mg.loOut1 = peerOf(mg.rank - 1, ctx->z);
+            mg.hiOut1 = peerOf(mg.rank + 1, ctx->z);
+            pcgPipeKernel<MODE_K2, true><<<pipeBlocks, NT, sizeof(PipeSmem<MODE_K2>), st>>>(k2, blocks, mg);
+        }
+        else if (pipe)
+            pcgPipeKernel<MODE_K2, false><<<pipeBlocks, NT, sizeof(PipeSmem<MODE_K2>), st>>>(k2, blocks, mg);
         else
             pcgTileKernel<MODE_K2><<<blocks, NT, 0, st>>>(k2);
         ctx->launches += 2;
@@ -896,8 +1241,16 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
         }
     }
     if (prof && iterLimit > 0) cudaEventRecord(ctx->profEvents[2 * iterLimit], st);
-    pcgFinalizeKernel<<<flat, NT, 0, st>>>(ctx->x, ctx->s[0], ctx->s[1], ctx->N, ctx->scalars, iterLimit);
-    pcgResultKernel<<<1, 1, 0, st>>>(ctx->scalars, iterLimit);
+    if (mgOn)
+    {
+        pcgMgCloseKernel<<<1, 1, 0, st>>>(a, mg);
+        pcgFinalizeKernel<<<flat, NT, 0, st>>>(ctx->x, ctx->s[0], ctx->s[1], oLo, oHi, ctx->scalars, iterLimit);
+    }
+    else
+    {
+        pcgFinalizeKernel<<<flat, NT, 0, st>>>(ctx->x, ctx->s[0], ctx->s[1], 0, ctx->N, ctx->scalars, iterLimit);
+        pcgResultKernel<<<1, 1, 0, st>>>(ctx->scalars, iterLimit);
+    }
     ctx->launches += 2;
     FS2D_CUDA(cudaGetLastError());
     if (prof && iterLimit > 0)

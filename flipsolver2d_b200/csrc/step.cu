@@ -57,6 +57,7 @@ int projectStage(Ctx *ctx, int *iters)
 {
     FS2D_TRY(gridPressureRhs(ctx));
     FS2D_TRY(pcgSolveDevice(ctx, ctx->p.pcg_iter_limit, ctx->p.project_tolerance));
+    FS2D_TRY(slabExchangePressure(ctx));
     FS2D_TRY(gridApplyPressure(ctx));
     if (iters) FS2D_TRY(fs2d_pcg_last_iterations(ctx, iters));
     return FS2D_OK;
@@ -68,7 +69,7 @@ int stepFlip(Ctx *ctx, StageClock &clk, int *iters)
     clk.end(ADVECTION);
     FS2D_TRY(gridBuildMatrix(ctx));
     clk.end(DECOMPOSITION);
-    FS2D_TRY(particlesSort(ctx));
+    FS2D_TRY(particlesRebin(ctx));
     clk.end(PARTICLE_REBIN);
     if (!ctx->p.viscosity_enabled)
     {
@@ -108,7 +109,7 @@ int stepNbflip(Ctx *ctx, StageClock &clk, int *iters)
     FS2D_TRY(fs2d_advect(ctx));
     FS2D_TRY(fs2d_nbflip_advect_grids(ctx));
     clk.end(ADVECTION);
-    FS2D_TRY(particlesSort(ctx));
+    FS2D_TRY(particlesRebin(ctx));
     clk.end(PARTICLE_REBIN);
     FS2D_TRY(fs2d_particle_to_grid(ctx));
     FS2D_TRY(gridExtrapolateVelocity(ctx, 10));

@@ -124,13 +124,14 @@ __device__ __forceinline__ void forRowRange(const TileStage &s, bool staged, con
 // weightU > 1e-9 && weightV > 1e-9, i.e. floor(pos) within one cell of (i,j).
 __global__ void __launch_bounds__(NT) p2gVelocityKernel(const int32_t *__restrict__ cellStart, const float2 *__restrict__ pos,
                                                         const float2 *__restrict__ vel, const uint8_t *__restrict__ mis, int I,
-                                                        int J, int tilesJ,
+                                                        int J, int tilesJ, int tileBase,
                                                         float *__restrict__ U, float *__restrict__ V,
                                                         uint8_t *__restrict__ uValid, uint8_t *__restrict__ vValid)
 {
     extern __shared__ __align__(16) unsigned char stageRaw[];
     TileStage &s = *reinterpret_cast<TileStage *>(stageRaw);
-    const int ti = blockIdx.x / tilesJ, tj = blockIdx.x - ti * tilesJ;
+    const int tile = tileBase + blockIdx.x;
+    const int ti = tile / tilesJ, tj = tile - ti * tilesJ;
     const int i0 = ti * TI, j0 = tj * TJ;
     const bool staged = stageTile<true>(s, cellStart, pos, vel, nullptr, mis, I, J, i0, j0, 1, 1);
     const int li = threadIdx.x / TJ, lj = threadIdx.x - li * TJ;
@@ -171,12 +172,13 @@ __global__ void __launch_bounds__(NT) p2gVelocityKernel(const int32_t *__restric
 template <int MODE>
 __global__ void __launch_bounds__(NT) p2gCenteredKernel(const int32_t *__restrict__ cellStart, const float2 *__restrict__ pos,
                                                         const float *__restrict__ prop, const uint8_t *__restrict__ mis, int I,
-                                                        int J, int tilesJ,
+                                                        int J, int tilesJ, int tileBase,
                                                         float *__restrict__ out, uint8_t *__restrict__ known)
 {
     extern __shared__ __align__(16) unsigned char stageRaw[];
     TileStage &s = *reinterpret_cast<TileStage *>(stageRaw);
-    const int ti = blockIdx.x / tilesJ, tj = blockIdx.x - ti * tilesJ;
+    const int tile = tileBase + blockIdx.x;
+    const int ti = tile / tilesJ, tj = tile - ti * tilesJ;
     const int i0 = ti * TI, j0 = tj * TJ;
     const bool staged = stageTile<false>(s, cellStart, pos, nullptr, prop, mis, I, J, i0, j0, 2, 1);
     const int li = threadIdx.x / TJ, lj = threadIdx.x - li * TJ;
@@ -212,12 +214,13 @@ __global__ void __launch_bounds__(NT) p2gCenteredKernel(const int32_t *__restric
 // updateDensityGridThread (flipsolver2d.cpp:201-249)
 __global__ void __launch_bounds__(NT) densityKernel(const int32_t *__restrict__ cellStart, const float2 *__restrict__ pos,
                                                     const uint8_t *__restrict__ mis, const int8_t *__restrict__ mat, int I, int J,
-                                                    int tilesJ, float particleMass,
+                                                    int tilesJ, int tileBase, float particleMass,
                                                     float cellVolume, float restDensity, float *__restrict__ density)
 {
     extern __shared__ __align__(16) unsigned char stageRaw[];
     TileStage &s = *reinterpret_cast<TileStage *>(stageRaw);
-    const int ti = blockIdx.x / tilesJ, tj = blockIdx.x - ti * tilesJ;
+    const int tile = tileBase + blockIdx.x;
+    const int ti = tile / tilesJ, tj = tile - ti * tilesJ;
     const int i0 = ti * TI, j0 = tj * TJ;
     const bool staged = stageTile<false>(s, cellStart, pos, nullptr, nullptr, mis, I, J, i0, j0, 1, 1);
     const int li = threadIdx.x / TJ, lj = threadIdx.x - li * TJ;
@@ -251,10 +254,10 @@ __global__ void __launch_bounds__(NT) densityKernel(const int32_t *__restrict__ 
 // 5x5 bins around the cell and every candidate is tested against the reference's 3x3 bin window.
 __global__ void __launch_bounds__(256) sdfKernel(const int32_t *__restrict__ cellStart, const float2 *__restrict__ pos,
                                                  const uint8_t *__restrict__ mis, int I, int J, float radius,
-                                                 float *__restrict__ sdf)
+                                                 float *__restrict__ sdf, long long nBegin, long long nEnd)
 {
-    const long long n = blockIdx.x * 256ll + threadIdx.x;
-    if (n >= static_cast<long long>(I) * J) return;
+    const long long n = nBegin + blockIdx.x * 256ll + threadIdx.x;
+    if (n >= nEnd) return;
     const int i = static_cast<int>(n / J), j = static_cast<int>(n - static_cast<long long>(i) * J);
     const int bi = i / 3, bj = j / 3;
     const int iLo = max(3 * (bi - 2), 0), iHi = min(3 * (bi + 2) + 2, I - 1);
@@ -298,10 +301,13 @@ template <class K> void allowStage(K kernel)
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(STAGE_BYTES));
 }
 
-int tileCount(const Ctx *ctx, int *tilesJ)
+// Tiles covering the rows `r` (slab boundaries are multiples of 16, hence of TI); *tileBase = first tile.
+int tileCount(const Ctx *ctx, SlabRows r, int *tilesJ, int *tileBase)
 {
     *tilesJ = divUp(ctx->J, TJ);
-    return divUp(ctx->I, TI) * *tilesJ;
+    const int t0 = r.lo / TI, t1 = divUp(r.hi, TI);
+    *tileBase = t0 * *tilesJ;
+    return (t1 - t0) * *tilesJ;
 }
 }  // namespace
 
@@ -320,14 +326,16 @@ int transferVelocity(Ctx *ctx)
     // fill(0)/fill(false) of all four arrays (flipsolver2d.cpp:1315-1318); row I of U and column J of V keep 0
     FS2D_CUDA(cudaMemsetAsync(ctx->U + ctx->N, 0, sizeof(float) * (ctx->NU - ctx->N), st));
     FS2D_CUDA(cudaMemsetAsync(ctx->uValid + ctx->N, 0, ctx->NU - ctx->N, st));
-    FS2D_CUDA(cudaMemsetAsync(ctx->V, 0, sizeof(float) * ctx->NV, st));
-    FS2D_CUDA(cudaMemsetAsync(ctx->vValid, 0, ctx->NV, st));
-    int tilesJ;
-    const int tiles = tileCount(ctx, &tilesJ);
+    const SlabRows own = slabOwn(ctx);
+    const size_t vOff = static_cast<size_t>(own.lo) * (ctx->J + 1), vCnt = static_cast<size_t>(own.hi - own.lo) * (ctx->J + 1);
+    FS2D_CUDA(cudaMemsetAsync(ctx->V + vOff, 0, sizeof(float) * vCnt, st));
+    FS2D_CUDA(cudaMemsetAsync(ctx->vValid + vOff, 0, vCnt, st));
+    int tilesJ, tileBase;
+    const int tiles = tileCount(ctx, own, &tilesJ, &tileBase);
     ParticleBuffers &b = ctx->pb[ctx->cur];
     allowStage(p2gVelocityKernel);
-    p2gVelocityKernel<<<tiles, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, b.vel, b.mis, ctx->I, ctx->J, tilesJ, ctx->U, ctx->V, ctx->uValid,
-                                           ctx->vValid);
+    p2gVelocityKernel<<<tiles, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, b.vel, b.mis, ctx->I, ctx->J, tilesJ, tileBase, ctx->U, ctx->V,
+                                                      ctx->uValid, ctx->vValid);
     ctx->launches++;
     FS2D_CUDA(cudaGetLastError());
     return FS2D_OK;
@@ -337,12 +345,15 @@ int transferCentered(Ctx *ctx)
 {
     FS2D_TRY(ensureSorted(ctx));
     cudaStream_t st = ctx->stream;
-    int tilesJ;
-    const int tiles = tileCount(ctx, &tilesJ);
+    int tilesJ, tileBase;
+    const SlabRows own = slabOwn(ctx);
+    const int tiles = tileCount(ctx, own, &tilesJ, &tileBase);
     ParticleBuffers &b = ctx->pb[ctx->cur];
     // m_divergenceControl.fill(0.f) in all three variants (flipsolver2d.cpp:1382, nbflipsolver.cpp:450,
-    // flipsmokesolver.cpp:60)
-    FS2D_CUDA(cudaMemsetAsync(ctx->divergenceControl, 0, sizeof(float) * ctx->N, st));
+    // flipsmokesolver.cpp:60); slab mode clears the rows the right-hand side is evaluated on
+    const SlabRows e1 = slabExt(ctx, 1);
+    FS2D_CUDA(cudaMemsetAsync(ctx->divergenceControl + static_cast<size_t>(e1.lo) * ctx->J, 0,
+                              sizeof(float) * static_cast<size_t>(e1.hi - e1.lo) * ctx->J, st));
     allowStage(p2gCenteredKernel<0>);
     allowStage(p2gCenteredKernel<1>);
     auto column = [&](int prop) -> const float * { return prop >= 0 ? b.props + static_cast<int64_t>(prop) * b.capacity : nullptr; };
@@ -350,19 +361,19 @@ int transferCentered(Ctx *ctx)
     {
     case FS2D_SIM_LIQUID:
         p2gCenteredKernel<0><<<tiles, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, column(ctx->p.viscosity_property), b.mis, ctx->I, ctx->J,
-                                                   tilesJ, ctx->viscosity, ctx->knownCentered);
+                                                   tilesJ, tileBase, ctx->viscosity, ctx->knownCentered);
         ctx->launches++;
         break;
     case FS2D_SIM_NBFLIP:
         p2gCenteredKernel<1><<<tiles, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, column(ctx->p.viscosity_property), b.mis, ctx->I, ctx->J,
-                                                   tilesJ, ctx->viscosity, ctx->knownCentered);
+                                                   tilesJ, tileBase, ctx->viscosity, ctx->knownCentered);
         ctx->launches++;
         break;
     default:  // smoke / fire: temperature and concentration (fire's fuel column has no P2G in the reference)
         p2gCenteredKernel<1><<<tiles, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, column(ctx->p.temperature_property), b.mis, ctx->I, ctx->J,
-                                                   tilesJ, ctx->temperature, ctx->knownCentered);
+                                                   tilesJ, tileBase, ctx->temperature, ctx->knownCentered);
         p2gCenteredKernel<1><<<tiles, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, column(ctx->p.concentration_property), b.mis, ctx->I, ctx->J,
-                                                   tilesJ, ctx->concentration, nullptr);
+                                                   tilesJ, tileBase, ctx->concentration, nullptr);
         ctx->launches += 2;
         break;
     }
@@ -373,15 +384,17 @@ int transferCentered(Ctx *ctx)
 int transferDensity(Ctx *ctx)
 {
     FS2D_TRY(ensureSorted(ctx));
-    int tilesJ;
-    const int tiles = tileCount(ctx, &tilesJ);
+    int tilesJ, tileBase;
+    // slab mode: one extra tile row each side, the density right-hand side needs one halo row (ghost particles
+    // reach 12 rows, the tile halo needs 9)
+    const int tiles = tileCount(ctx, slabExt(ctx, ctx->slab.enabled ? TI : 0), &tilesJ, &tileBase);
     // float cellVolume = dx*dx*dx; float particleMass = (rho * cellVolume) / float(ppc) (flipsolver2d.cpp:203-204)
     const float cellVolume = static_cast<float>(ctx->p.dx * ctx->p.dx * ctx->p.dx);
     const float particleMass =
         static_cast<float>((ctx->p.fluid_density * cellVolume) / static_cast<float>(ctx->p.particles_per_cell));
     allowStage(densityKernel);
     densityKernel<<<tiles, NT, STAGE_BYTES, ctx->stream>>>(ctx->cellStart, ctx->pb[ctx->cur].pos, ctx->pb[ctx->cur].mis, ctx->material, ctx->I, ctx->J, tilesJ,
-                                                particleMass, cellVolume, static_cast<float>(ctx->p.fluid_density), ctx->density);
+                                                tileBase, particleMass, cellVolume, static_cast<float>(ctx->p.fluid_density), ctx->density);
     ctx->launches++;
     FS2D_CUDA(cudaGetLastError());
     return FS2D_OK;
@@ -391,8 +404,10 @@ int transferSdf(Ctx *ctx)
 {
     FS2D_TRY(ensureSorted(ctx));
     ctx->sdfInsidePending = false;  // the whole level set is rewritten below
-    sdfKernel<<<divUp(ctx->N, 256), 256, 0, ctx->stream>>>(ctx->cellStart, ctx->pb[ctx->cur].pos, ctx->pb[ctx->cur].mis, ctx->I, ctx->J,
-                                                          ctx->p.particle_scale, ctx->fluidSdf);
+    const SlabRows own = slabOwn(ctx);
+    const long long nBegin = static_cast<long long>(own.lo) * ctx->J, nEnd = static_cast<long long>(own.hi) * ctx->J;
+    sdfKernel<<<divUp(nEnd - nBegin, 256), 256, 0, ctx->stream>>>(ctx->cellStart, ctx->pb[ctx->cur].pos, ctx->pb[ctx->cur].mis, ctx->I, ctx->J,
+                                                                 ctx->p.particle_scale, ctx->fluidSdf, nBegin, nEnd);
     ctx->launches++;
     FS2D_CUDA(cudaGetLastError());
     return FS2D_OK;

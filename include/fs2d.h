@@ -265,6 +265,26 @@ int fs2d_nbflip_advect_grids(fs2d_handle h);
  * CUDA events, iters[3] = pressure, density, viscosity iteration counts. Either may be NULL. */
 int fs2d_substep(fs2d_handle h, float dt, float *stage_ms, int *iters);
 
+/* ---------------------------------------------------------------- row slabs over several GPUs
+ * The reference is single-node shared-memory; its ThreadPool splits every grid loop into row ranges
+ * (threadpool.cpp:41-76). Here the same split is done across GPUs: one handle per GPU owns the cell rows
+ * [row_begin, row_end) (multiples of 16) of the global grid, and the handles exchange halo rows, migrating
+ * particles and reduction partials through peer-mapped device memory. Call order on every rank:
+ *   fs2d_create -> fs2d_slab_configure -> fs2d_slab_export (send the blob to the other ranks by any means:
+ *   torch.distributed, MPI, a file) -> fs2d_slab_connect for every other rank -> upload the scene (full
+ *   grids on every rank, only the rank's OWN particles) -> stage calls, the same sequence on every rank.
+ * device_share = how many ranks run on the same GPU (1 in production; > 1 lets a single GPU host several
+ * ranks for testing, with the persistent kernels sized so that all ranks stay co-resident).
+ * Only FS2D_SIM_LIQUID without viscosity is slab-aware so far; other solvers report FS2D_ERR_STATE. */
+#define FS2D_SLAB_HANDLE_BYTES 256
+int fs2d_slab_configure(fs2d_handle h, int rank, int world, int device_share);
+int fs2d_slab_export(fs2d_handle h, void *handle_out /* FS2D_SLAB_HANDLE_BYTES */);
+int fs2d_slab_connect(fs2d_handle h, int peer_rank, const void *handle);
+int fs2d_slab_rows(fs2d_handle h, int *row_begin, int *row_end, int *halo_rows);
+/* All-gather of four int64 per rank (CFL max velocity, reseed candidate counts, particle totals):
+ * out receives world x 4 values in rank order. Collective: every rank must call it. */
+int fs2d_slab_allgather(fs2d_handle h, const int64_t value[4], int64_t *out);
+
 #ifdef __cplusplus
 }
 #endif

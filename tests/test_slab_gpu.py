@@ -1,0 +1,165 @@
+"""Row-slab decomposition: several ranks -- here several handles sharing ONE GPU, each on its own
+host thread, talking through the same peer-memory mailboxes a multi-GPU run uses -- must reproduce the
+single-handle result: integer grids exactly, floating-point fields to the rounding of the regrouped
+dot-product partials (the only arithmetic that depends on the decomposition)."""
+import numpy as np
+import pytest
+
+import helpers as H
+from flipsolver2d_b200 import capi, scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def _scene(res):
+    sc = scenes.dam_break(res, "flip")
+    sc["settings"]["density"] = 0.02
+    return sc
+
+
+def _slab_devices(s, scene, world, **over):
+    devs = []
+    for r in range(world):
+        d = H.make_device(s, scene, **over)
+        d.slab_configure(r, world, device_share=world)
+        devs.append(d)
+    capi.connect_slabs(devs)
+    return devs
+
+
+def _sync_slab(s, d):
+    for g in H.STATE_GRIDS:
+        d.upload(g, s.grid(g))
+    pos, vel, props, bins = s.particles()
+    lo, hi, _ = d.slab_rows()
+    own = (np.floor(pos[:, 0]) >= lo) & (np.floor(pos[:, 0]) < hi)
+    d.upload_particles(pos[own], vel[own], props[:, own])
+    if own.any():
+        d.set_storage_bins(bins[own])
+    d.set_step_dt(s.params()["stepDt"])
+    return int(own.sum())
+
+
+def _assemble(devs, name, J, per_row):
+    """Rows every rank owns, stitched together (per_row = elements per grid row of this array)."""
+    out = None
+    for d in devs:
+        a = d.download(name)
+        if out is None:
+            out = np.zeros_like(a)
+        lo, hi, _ = d.slab_rows()
+        hi_e = hi
+        if name in ("U", "U_VALID", "SAVED_U") and d.rank == d.world - 1:
+            hi_e = hi + 1  # the extra U row belongs to the last slab
+        out[lo * per_row: hi_e * per_row] = a[lo * per_row: hi_e * per_row]
+    return out
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("dense", [False, True])
+def test_slab_pcg_matches_single_handle(ref_mod, scene_dir, world, dense):
+    scene = _scene(128)
+    s = H.make_ref(ref_mod, scene, scene_dir / "slabpcg.json")
+    s.stage("FIRST_FRAME_INIT")
+    s.set_step_dt(1.0 / 60.0)
+    mat = s.grid("MATERIAL")
+    rng = np.random.default_rng(7)
+
+    def prep(d):
+        d.upload("MATERIAL", mat)
+        d.set_step_dt(1.0 / 60.0)
+        d.stage("build_matrix")
+        d.pcg_set_dense(dense)
+
+    single = H.make_device(s, scene)
+    prep(single)
+    unit = single.matrix()["is_unit"].astype(bool)
+    rhs = np.where(unit, rng.standard_normal(s.N), 0.0)
+    cases = [(40, 0.0), (200, 1e-6)]
+    want = [single.pcg_solve(rhs, it, tol) for it, tol in cases]
+    trace1 = single.pcg_trace()
+    devs = _slab_devices(s, scene, world)
+    for d in devs:
+        prep(d)
+    J = s.J
+    for (it, tol), (x1, n1) in zip(cases, want):
+        res = capi.run_ranks([lambda d=d: d.pcg_solve(rhs, it, tol) for d in devs])
+        x = np.zeros_like(x1)
+        for d, (xr, nr) in zip(devs, res):
+            lo, hi, _ = d.slab_rows()
+            x[lo * J: hi * J] = xr[lo * J: hi * J]
+            assert nr == n1, (nr, n1)
+        assert H.rel_l2(x, x1) < 1e-9, H.rel_l2(x, x1)
+    tr = devs[0].pcg_trace()
+    assert len(tr) == len(trace1)
+    assert np.allclose(tr, trace1, rtol=1e-7, atol=0)
+    for d in devs:
+        d.close()
+    single.close()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_slab_substeps_match_single_handle(ref_mod, scene_dir, world):
+    scene = _scene(128)
+    s = H.make_ref(ref_mod, scene, scene_dir / "slabstep.json")
+    s.stage("FIRST_FRAME_INIT")
+    s.bump_frame()
+    dt = 1.0 / 60.0
+    steps = 6
+    single = H.make_device(s, scene)
+    H.sync_state(s, single)
+    for _ in range(steps):
+        single.substep(dt)
+    devs = _slab_devices(s, scene, world)
+    assert sum(_sync_slab(s, d) for d in devs) == s.particle_count()
+
+    def run(d):
+        its = []
+        for _ in range(steps):
+            its.append(d.substep(dt)[1].copy())
+        return its
+
+    iters = capi.run_ranks([lambda d=d: run(d) for d in devs])
+    for r in range(1, world):
+        assert all(np.array_equal(a, b) for a, b in zip(iters[0], iters[r]))  # every rank sees the same PCG
+    I, J = s.I, s.J
+    assert np.array_equal(_assemble(devs, "MATERIAL", J, J), single.download("MATERIAL"))
+    assert np.array_equal(_assemble(devs, "COUNTS", J, J), single.download("COUNTS"))
+    assert np.array_equal(_assemble(devs, "U_VALID", J, J), single.download("U_VALID"))
+    for name, per_row in (("U", J), ("V", J + 1), ("PRESSURE", J), ("FLUID_SDF", J)):
+        a, b = _assemble(devs, name, J, per_row), single.download(name)
+        assert H.rel_l2(a, b) < 1e-7, (name, H.rel_l2(a, b))
+    assert sum(d.particle_count() for d in devs) == single.particle_count()
+    parts = [d.download_particles() for d in devs]
+    pos = np.concatenate([p[0] for p in parts])
+    vel = np.concatenate([p[1] for p in parts])
+    p1, v1, _ = single.download_particles()
+    # ranks hold consecutive row ranges and each is sorted by cell -> the concatenation is the global order
+    assert pos.shape == p1.shape
+    assert np.max(np.abs(pos - p1)) < 1e-5
+    assert H.rel_l2(vel, v1) < 1e-6
+    moved = sum(1 for d, p in zip(devs, parts) if len(p[0]))
+    assert moved >= 2  # the fluid really spans more than one slab
+    for d in devs:
+        d.close()
+    single.close()
+
+
+def test_slab_allgather_and_errors(ref_mod, scene_dir):
+    scene = _scene(128)
+    s = H.make_ref(ref_mod, scene, scene_dir / "slabmisc.json")
+    s.stage("FIRST_FRAME_INIT")
+    devs = _slab_devices(s, scene, 2)
+    got = capi.run_ranks([lambda d=d: d.slab_allgather([10 + d.rank, -d.rank]) for d in devs])
+    for g in got:
+        assert g[:, 0].tolist() == [10, 11] and g[:, 1].tolist() == [0, -1]
+    # a slab thinner than the halo, or a second configure, is refused
+    d = H.make_device(s, scene)
+    with pytest.raises(capi.Fs2dError):
+        d.slab_configure(0, 8)
+    d.slab_configure(0, 1)
+    with pytest.raises(capi.Fs2dError):
+        d.slab_configure(0, 1)
+    d.close()
+    for d in devs:
+        d.close()
