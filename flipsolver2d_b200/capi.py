@@ -145,6 +145,7 @@ def lib():
         "fs2d_slab_connect": (i32, [H, i32, vp]),
         "fs2d_slab_rows": (i32, [H, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
         "fs2d_slab_allgather": (i32, [H, vp, vp]),
+        "fs2d_slab_gather_grid": (i32, [H, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -390,6 +391,10 @@ class Device:
         out = np.zeros(4 * getattr(self, "world", 1), np.int64)
         self._ck(self.L.fs2d_slab_allgather(self.h, _p(v), _p(out)), "slab_allgather")
         return out.reshape(-1, 4)
+
+    def slab_gather(self, name):
+        """Collective: afterwards every rank holds all rows of the grid (and the lazily extrapolated FLUID_SDF)."""
+        self._ck(self.L.fs2d_slab_gather_grid(self.h, GRID[name][0]), "slab_gather " + name)
 
     def synchronize(self):
         self._ck(self.L.fs2d_synchronize(self.h), "synchronize")

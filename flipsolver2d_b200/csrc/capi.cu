@@ -3,6 +3,8 @@
 #include <cstring>
 #include <new>
 
+#include <cstdlib>
+
 #include "fs2d_internal.h"
 
 int pcgTileBlocks(const Ctx *ctx);
@@ -207,6 +209,13 @@ void freeAll(Ctx *c)
 }
 }  // namespace
 
+// Kernels of several ranks may wait for each other on the device (slab.cu, pcg.cu). CUDA's default lazy module
+// loading synchronises the context at the first use of a kernel, which deadlocks (until the spin limit) when that
+// first use happens on one host thread while a kernel of the same context spins for a launch another host thread
+// has not made yet. Ask for eager loading before the driver is initialised; fs2d_slab_configure additionally
+// touches the kernels that only exist in slab mode.
+__attribute__((constructor)) static void fs2dEagerModuleLoading() { setenv("CUDA_MODULE_LOADING", "EAGER", 0); }
+
 extern "C" {
 
 int fs2d_device_count(void)
@@ -319,8 +328,26 @@ int fs2d_download_grid(fs2d_handle ctx, int grid, void *host_data, size_t bytes)
         return FS2D_ERR_ARG;
     }
     if (grid == FS2D_GRID_FLUID_SDF) FS2D_TRY(gridFlushSdf(ctx));
-    FS2D_CUDA(cudaMemcpyAsync(host_data, *d.ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    FS2D_CUDA(fs2dCopyToHost(ctx, host_data, *d.ptr, bytes));
     FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FS2D_OK;
+}
+
+int fs2d_slab_gather_grid(fs2d_handle ctx, int grid)
+{
+    if (!ctx) return FS2D_ERR_ARG;
+    GridDesc d = gridDesc(ctx, grid);
+    if (!d.ptr || !*d.ptr)
+    {
+        ctx->lastError = "fs2d_slab_gather_grid: unknown grid";
+        return FS2D_ERR_ARG;
+    }
+    if (!ctx->slab.enabled || ctx->slab.world == 1) return grid == FS2D_GRID_FLUID_SDF ? gridFlushSdf(ctx) : FS2D_OK;
+    const bool uLike = grid == FS2D_GRID_U || grid == FS2D_GRID_U_VALID || grid == FS2D_GRID_SAVED_U || grid == FS2D_GRID_ADVECTED_U;
+    const bool vLike = grid == FS2D_GRID_V || grid == FS2D_GRID_V_VALID || grid == FS2D_GRID_SAVED_V || grid == FS2D_GRID_ADVECTED_V;
+    const size_t rowBytes = static_cast<size_t>(d.elemSize) * (vLike ? ctx->J + 1 : ctx->J);
+    FS2D_TRY(slabGatherRows(ctx, *d.ptr, rowBytes, uLike ? ctx->I + 1 : ctx->I));
+    if (grid == FS2D_GRID_FLUID_SDF) FS2D_TRY(gridFlushSdfGathered(ctx));
     return FS2D_OK;
 }
 
@@ -440,12 +467,12 @@ int fs2d_download_particles(fs2d_handle ctx, float *host_pos, float *host_vel, f
     const int64_t n = slab ? ctx->slab.ownedEnd - ctx->slab.ownedBegin : ctx->count;
     if (n == 0) return FS2D_OK;
     ParticleBuffers &b = ctx->pb[ctx->cur];
-    if (host_pos) FS2D_CUDA(cudaMemcpyAsync(host_pos, b.pos + first, sizeof(float2) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    if (host_vel) FS2D_CUDA(cudaMemcpyAsync(host_vel, b.vel + first, sizeof(float2) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (host_pos) FS2D_CUDA(fs2dCopyToHost(ctx, host_pos, b.pos + first, sizeof(float2) * n));
+    if (host_vel) FS2D_CUDA(fs2dCopyToHost(ctx, host_vel, b.vel + first, sizeof(float2) * n));
     if (host_props)
         for (int k = 0; k < ctx->p.num_properties; k++)
-            FS2D_CUDA(cudaMemcpyAsync(host_props + static_cast<int64_t>(k) * n, b.props + static_cast<int64_t>(k) * b.capacity + first,
-                                      sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+            FS2D_CUDA(fs2dCopyToHost(ctx, host_props + static_cast<int64_t>(k) * n, b.props + static_cast<int64_t>(k) * b.capacity + first,
+                                      sizeof(float) * n));
     FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
     return FS2D_OK;
 }
@@ -467,7 +494,7 @@ int fs2d_pcg_solve(fs2d_handle ctx, const double *host_rhs, double *host_x, int 
     const size_t bytes = static_cast<size_t>(ctx->N) * sizeof(double);
     FS2D_CUDA(cudaMemcpyAsync(ctx->rhs, host_rhs, bytes, cudaMemcpyHostToDevice, ctx->stream));
     FS2D_TRY(pcgSolveDevice(ctx, iter_limit, tol));
-    FS2D_CUDA(cudaMemcpyAsync(host_x, ctx->x, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    FS2D_CUDA(fs2dCopyToHost(ctx, host_x, ctx->x, bytes));
     return fs2d_pcg_last_iterations(ctx, iters);
 }
 
@@ -481,7 +508,7 @@ int fs2d_pcg_last_iterations(fs2d_handle ctx, int *iters)
 {
     if (!ctx) return FS2D_ERR_ARG;
     PcgScalars sc;
-    FS2D_CUDA(cudaMemcpyAsync(&sc, ctx->scalars, sizeof(sc), cudaMemcpyDeviceToHost, ctx->stream));
+    FS2D_CUDA(fs2dCopyToHost(ctx, &sc, ctx->scalars, sizeof(sc)));
     FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->lastPcgIters = sc.result;
     if (iters) *iters = sc.result;
@@ -492,10 +519,10 @@ int fs2d_pcg_trace(fs2d_handle ctx, double *host_trace, int max_iterations, int 
 {
     if (!ctx || !host_trace || max_iterations < 0) return FS2D_ERR_ARG;
     PcgScalars sc;
-    FS2D_CUDA(cudaMemcpyAsync(&sc, ctx->scalars, sizeof(sc), cudaMemcpyDeviceToHost, ctx->stream));
+    FS2D_CUDA(fs2dCopyToHost(ctx, &sc, ctx->scalars, sizeof(sc)));
     FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
     int n = std::min({sc.iter, max_iterations, ctx->traceCapacity});
-    if (n > 0) FS2D_CUDA(cudaMemcpy(host_trace, ctx->trace, sizeof(double) * 4 * n, cudaMemcpyDeviceToHost));
+    if (n > 0) FS2D_CUDA(fs2dCopyToHost(ctx, host_trace, ctx->trace, sizeof(double) * 4 * n));
     if (written) *written = n;
     return FS2D_OK;
 }
@@ -511,7 +538,7 @@ int fs2d_pcg_active_cells(fs2d_handle ctx, int64_t *cells)
 {
     if (!ctx || !cells) return FS2D_ERR_ARG;
     int n = 0;
-    FS2D_CUDA(cudaMemcpyAsync(&n, ctx->activeCount, sizeof(n), cudaMemcpyDeviceToHost, ctx->stream));
+    FS2D_CUDA(fs2dCopyToHost(ctx, &n, ctx->activeCount, sizeof(n)));
     FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
     *cells = static_cast<int64_t>(n) * 16 * 128;
     return FS2D_OK;
@@ -557,8 +584,8 @@ int fs2d_download_matrix(fs2d_handle ctx, uint8_t *host_is_unit, uint8_t *host_m
     std::vector<uint8_t> row(n);
     std::vector<uint16_t> pre(n);
     FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
-    FS2D_CUDA(cudaMemcpy(row.data(), ctx->rowInfo, n, cudaMemcpyDeviceToHost));
-    FS2D_CUDA(cudaMemcpy(pre.data(), ctx->preInfo, n * 2, cudaMemcpyDeviceToHost));
+    FS2D_CUDA(fs2dCopyToHost(ctx, row.data(), ctx->rowInfo, n));
+    FS2D_CUDA(fs2dCopyToHost(ctx, pre.data(), ctx->preInfo, n * 2));
     for (size_t k = 0; k < n; k++)
     {
         if (host_is_unit) host_is_unit[k] = (row[k] & FS2D_ROW_UNIT) ? 1 : 0;

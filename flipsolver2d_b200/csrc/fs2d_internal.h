@@ -273,6 +273,7 @@ int gridAfterTransfer(Ctx *ctx);
 int gridExtrapolateVelocity(Ctx *ctx, int radius);
 int gridExtrapolateSdf(Ctx *ctx, bool inside);
 int gridFlushSdf(Ctx *ctx);
+int gridFlushSdfGathered(Ctx *ctx);   // after every rank pushed its rows of the level set to every other rank
 int gridSaveVelocity(Ctx *ctx);
 int gridBodyForces(Ctx *ctx);
 int gridPressureRhs(Ctx *ctx);
@@ -282,6 +283,19 @@ int gridVelocityFromSolids(Ctx *ctx);
 int gridEulerAdvectParameters(Ctx *ctx);
 int gridNbflipAdvect(Ctx *ctx);
 int gridViscosity(Ctx *ctx, int *iters);
+// Device -> host copy into pageable memory: wait for the stream FIRST. cudaMemcpyAsync towards pageable memory blocks
+// inside the driver until the preceding work of the stream has finished, and other host threads cannot launch
+// meanwhile -- fatal when the preceding work is a kernel waiting for a launch of another rank that shares this
+// process (slab tests run several ranks on one GPU). cudaStreamSynchronize waits without that side effect.
+inline cudaError_t fs2dCopyToHost(Ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(ctx->stream);
+}
+
 // slab.cu
 struct SlabRows { int lo, hi; };                       // half-open cell-row range
 SlabRows slabOwn(const Ctx *ctx);                      // owned rows (whole grid without slabs)
@@ -292,6 +306,8 @@ int slabExchangePressure(Ctx *ctx);
 int slabExchangeParticles(Ctx *ctx);
 int slabAllGather(Ctx *ctx, const long long v[4], long long *out /* world x 4 */);
 int slabCheckError(Ctx *ctx);
+int slabGatherRows(Ctx *ctx, void *array, size_t rowBytes, int rowsTotal);  // collective: own rows -> every rank
+void pcgPreloadSlabKernels();           // pcg.cu
 // step.cu
 int stepSubstep(Ctx *ctx, float dt, float *stageMs, int *iters);
 

@@ -620,7 +620,7 @@ int gridExtrapolateVelocity(Ctx *ctx, int radius)
                     st>>>(ctx->uValid, ctx->vValid, ctx->I, ctx->J, marker, bbox, reg.lo, rowHiU, reg.hi);
     ctx->launches++;
     int box[4];
-    FS2D_CUDA(cudaMemcpyAsync(box, bbox, sizeof(box), cudaMemcpyDeviceToHost, st));
+    FS2D_CUDA(fs2dCopyToHost(ctx, box, bbox, sizeof(box)));
     FS2D_CUDA(cudaStreamSynchronize(st));
     if (box[1] < box[0]) return FS2D_OK;  // no valid sample anywhere: the BFS has no seed (mathfuncs.cpp:171-189)
     const int grow = radius + 2;
@@ -635,7 +635,7 @@ int gridExtrapolateVelocity(Ctx *ctx, int radius)
     return FS2D_OK;
 }
 
-int gridExtrapolateSdfNow(Ctx *ctx, bool inside);
+int gridExtrapolateSdfNow(Ctx *ctx, bool inside, bool wholeGridHeld = false);
 
 // extrapolateLevelsetInside only rewrites the level set BELOW the surface. Outside NBFlip nothing in the
 // substep reads those values (updateMaterials has already run, the next updateSdf overwrites them,
@@ -644,8 +644,23 @@ int gridExtrapolateSdfNow(Ctx *ctx, bool inside);
 int gridFlushSdf(Ctx *ctx)
 {
     if (!ctx->sdfInsidePending) return FS2D_OK;
+    if (ctx->slab.enabled && ctx->slab.world > 1)
+    {
+        // the BFS has unbounded radius: it needs every rank's rows, which only a collective call can bring here
+        ctx->lastError = "the fluid level set below the surface is computed lazily and needs all slabs: call "
+                         "fs2d_slab_gather_grid(FS2D_GRID_FLUID_SDF) on every rank first";
+        return FS2D_ERR_STATE;
+    }
     ctx->sdfInsidePending = false;
     return gridExtrapolateSdfNow(ctx, true);
+}
+
+// After fs2d_slab_gather_grid(FS2D_GRID_FLUID_SDF): every rank holds all rows and runs the deferred BFS on the whole grid.
+int gridFlushSdfGathered(Ctx *ctx)
+{
+    if (!ctx->sdfInsidePending) return FS2D_OK;
+    ctx->sdfInsidePending = false;
+    return gridExtrapolateSdfNow(ctx, true, true);
 }
 
 int gridExtrapolateSdf(Ctx *ctx, bool inside)
@@ -659,9 +674,9 @@ int gridExtrapolateSdf(Ctx *ctx, bool inside)
     return gridExtrapolateSdfNow(ctx, inside);
 }
 
-int gridExtrapolateSdfNow(Ctx *ctx, bool inside)
+int gridExtrapolateSdfNow(Ctx *ctx, bool inside, bool wholeGridHeld)
 {
-    FS2D_TRY(slabUnsupported(ctx, "extrapolateLevelset"));
+    if (!wholeGridHeld) FS2D_TRY(slabUnsupported(ctx, "extrapolateLevelset"));
     cudaStream_t st = ctx->stream;
     int *bbox = reinterpret_cast<int *>(ctx->d_counter) + 8;  // 4 ints bbox + 3 ints flags
     const int init[8] = {0x7fffffff, -1, 0x7fffffff, -1, 0, 0, 0, 0};

@@ -534,7 +534,7 @@ int fetchKilled(Ctx *ctx)
 {
     if (!ctx->killedDirty) return FS2D_OK;
     unsigned long long k = 0;
-    FS2D_CUDA(cudaMemcpyAsync(&k, ctx->d_counter, sizeof(k), cudaMemcpyDeviceToHost, ctx->stream));
+    FS2D_CUDA(fs2dCopyToHost(ctx, &k, ctx->d_counter, sizeof(k)));
     FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
     FS2D_CUDA(cudaMemsetAsync(ctx->d_counter, 0, sizeof(k), ctx->stream));
     ctx->deadCount += static_cast<int64_t>(k);
@@ -590,43 +590,46 @@ int particlesReserve(Ctx *ctx, int64_t capacity)
     if (capacity <= ctx->pb[0].capacity) return FS2D_OK;
     const int64_t newCap = std::max<int64_t>(capacity + capacity / 4, 1024);
     const int K = ctx->p.num_properties;
-    FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
+    // Stream-ordered allocation and copies: growing the buffers never synchronises the device (another rank sharing
+    // this GPU may have a kernel waiting for this rank's next launch) and never touches the legacy default stream.
+    cudaStream_t st = ctx->stream;
+    auto alloc = [&](void **p, size_t bytes) { return cudaMallocAsync(p, bytes, st); };
     for (int b = 0; b < 2; b++)
     {
         ParticleBuffers nb;
         nb.capacity = newCap;
-        FS2D_CUDA(cudaMalloc(reinterpret_cast<void **>(&nb.pos), sizeof(float2) * newCap));
-        FS2D_CUDA(cudaMalloc(reinterpret_cast<void **>(&nb.vel), sizeof(float2) * newCap));
-        FS2D_CUDA(cudaMalloc(reinterpret_cast<void **>(&nb.props), sizeof(float) * newCap * std::max(K, 1)));
-        FS2D_CUDA(cudaMalloc(reinterpret_cast<void **>(&nb.key), sizeof(uint32_t) * newCap));
-        FS2D_CUDA(cudaMalloc(reinterpret_cast<void **>(&nb.mis), newCap));
-        FS2D_CUDA(cudaMemset(nb.mis, FS2D_MIS_HOME, newCap));
+        FS2D_CUDA(alloc(reinterpret_cast<void **>(&nb.pos), sizeof(float2) * newCap));
+        FS2D_CUDA(alloc(reinterpret_cast<void **>(&nb.vel), sizeof(float2) * newCap));
+        FS2D_CUDA(alloc(reinterpret_cast<void **>(&nb.props), sizeof(float) * newCap * std::max(K, 1)));
+        FS2D_CUDA(alloc(reinterpret_cast<void **>(&nb.key), sizeof(uint32_t) * newCap));
+        FS2D_CUDA(alloc(reinterpret_cast<void **>(&nb.mis), newCap));
+        FS2D_CUDA(cudaMemsetAsync(nb.mis, FS2D_MIS_HOME, newCap, st));
         ParticleBuffers &ob = ctx->pb[b];
         if (b == ctx->cur && ctx->count > 0)
         {
-            FS2D_CUDA(cudaMemcpy(nb.pos, ob.pos, sizeof(float2) * ctx->count, cudaMemcpyDeviceToDevice));
-            FS2D_CUDA(cudaMemcpy(nb.vel, ob.vel, sizeof(float2) * ctx->count, cudaMemcpyDeviceToDevice));
-            FS2D_CUDA(cudaMemcpy(nb.key, ob.key, sizeof(uint32_t) * ctx->count, cudaMemcpyDeviceToDevice));
-            FS2D_CUDA(cudaMemcpy(nb.mis, ob.mis, ctx->count, cudaMemcpyDeviceToDevice));
+            FS2D_CUDA(cudaMemcpyAsync(nb.pos, ob.pos, sizeof(float2) * ctx->count, cudaMemcpyDeviceToDevice, st));
+            FS2D_CUDA(cudaMemcpyAsync(nb.vel, ob.vel, sizeof(float2) * ctx->count, cudaMemcpyDeviceToDevice, st));
+            FS2D_CUDA(cudaMemcpyAsync(nb.key, ob.key, sizeof(uint32_t) * ctx->count, cudaMemcpyDeviceToDevice, st));
+            FS2D_CUDA(cudaMemcpyAsync(nb.mis, ob.mis, ctx->count, cudaMemcpyDeviceToDevice, st));
             for (int k = 0; k < K; k++)
-                FS2D_CUDA(cudaMemcpy(nb.props + k * newCap, ob.props + k * ob.capacity, sizeof(float) * ctx->count,
-                                     cudaMemcpyDeviceToDevice));
+                FS2D_CUDA(cudaMemcpyAsync(nb.props + k * newCap, ob.props + k * ob.capacity, sizeof(float) * ctx->count,
+                                          cudaMemcpyDeviceToDevice, st));
         }
-        if (ob.pos) cudaFree(ob.pos);
-        if (ob.vel) cudaFree(ob.vel);
-        if (ob.props) cudaFree(ob.props);
-        if (ob.key) cudaFree(ob.key);
-        if (ob.mis) cudaFree(ob.mis);
+        if (ob.pos) cudaFreeAsync(ob.pos, st);
+        if (ob.vel) cudaFreeAsync(ob.vel, st);
+        if (ob.props) cudaFreeAsync(ob.props, st);
+        if (ob.key) cudaFreeAsync(ob.key, st);
+        if (ob.mis) cudaFreeAsync(ob.mis, st);
         ob = nb;
     }
     uint8_t *nd = nullptr;
     uint32_t *np = nullptr;
-    FS2D_CUDA(cudaMalloc(reinterpret_cast<void **>(&nd), newCap));
-    FS2D_CUDA(cudaMemset(nd, 0, newCap));
-    FS2D_CUDA(cudaMalloc(reinterpret_cast<void **>(&np), sizeof(uint32_t) * newCap));
-    if (ctx->dead && ctx->count > 0) FS2D_CUDA(cudaMemcpy(nd, ctx->dead, ctx->count, cudaMemcpyDeviceToDevice));
-    if (ctx->dead) cudaFree(ctx->dead);
-    if (ctx->perm) cudaFree(ctx->perm);
+    FS2D_CUDA(alloc(reinterpret_cast<void **>(&nd), newCap));
+    FS2D_CUDA(cudaMemsetAsync(nd, 0, newCap, st));
+    FS2D_CUDA(alloc(reinterpret_cast<void **>(&np), sizeof(uint32_t) * newCap));
+    if (ctx->dead && ctx->count > 0) FS2D_CUDA(cudaMemcpyAsync(nd, ctx->dead, ctx->count, cudaMemcpyDeviceToDevice, st));
+    if (ctx->dead) cudaFreeAsync(ctx->dead, st);
+    if (ctx->perm) cudaFreeAsync(ctx->perm, st);
     ctx->dead = nd;
     ctx->perm = np;
     return FS2D_OK;
@@ -651,7 +654,7 @@ int particlesMaxVelocity(Ctx *ctx, float *out)
         ctx->launches++;
     }
     unsigned int r = 0;
-    FS2D_CUDA(cudaMemcpyAsync(&r, bits, sizeof(r), cudaMemcpyDeviceToHost, ctx->stream));
+    FS2D_CUDA(fs2dCopyToHost(ctx, &r, bits, sizeof(r)));
     FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
     if (ctx->slab.enabled && ctx->slab.world > 1)
     {
@@ -700,13 +703,11 @@ int particlesSort(Ctx *ctx)
     }
     exclusiveScan(ctx, ctx->cellCursor + cLo, ctx->cellStart + cLo, cells + 1);
     int32_t alive = 0, ownedRange[2] = {0, 0};
-    FS2D_CUDA(cudaMemcpyAsync(&alive, ctx->cellStart + cHi, sizeof(alive), cudaMemcpyDeviceToHost, st));
+    FS2D_CUDA(fs2dCopyToHost(ctx, &alive, ctx->cellStart + cHi, sizeof(alive)));
     if (slab)
     {
-        FS2D_CUDA(cudaMemcpyAsync(&ownedRange[0], ctx->cellStart + static_cast<int64_t>(ctx->slab.rowBegin) * ctx->J, sizeof(int32_t),
-                                  cudaMemcpyDeviceToHost, st));
-        FS2D_CUDA(cudaMemcpyAsync(&ownedRange[1], ctx->cellStart + static_cast<int64_t>(ctx->slab.rowEnd) * ctx->J, sizeof(int32_t),
-                                  cudaMemcpyDeviceToHost, st));
+        FS2D_CUDA(fs2dCopyToHost(ctx, &ownedRange[0], ctx->cellStart + static_cast<int64_t>(ctx->slab.rowBegin) * ctx->J, sizeof(int32_t)));
+        FS2D_CUDA(fs2dCopyToHost(ctx, &ownedRange[1], ctx->cellStart + static_cast<int64_t>(ctx->slab.rowEnd) * ctx->J, sizeof(int32_t)));
     }
     FS2D_CUDA(cudaMemsetAsync(ctx->cellCursor + cLo, 0, sizeof(int32_t) * (cells + 1), st));
     if (ctx->count > 0)
@@ -824,7 +825,7 @@ int particlesReseedPlan(Ctx *ctx, int64_t *candidates)
     ctx->launches++;
     exclusiveScan(ctx, ctx->reseedOffset + cLo, ctx->reseedOffset + cLo, cHi - cLo + 1);
     int32_t total = 0;
-    FS2D_CUDA(cudaMemcpyAsync(&total, ctx->reseedOffset + cHi, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
+    FS2D_CUDA(fs2dCopyToHost(ctx, &total, ctx->reseedOffset + cHi, sizeof(total)));
     FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->reseedCandidates = total;
     *candidates = total;
@@ -929,7 +930,7 @@ int particlesGetStorageBins(Ctx *ctx, int32_t *hostBins)
     getStorageBinsKernel<<<gridFor(ctx->count), NT, 0, ctx->stream>>>(ctx->pb[ctx->cur].pos, ctx->pb[ctx->cur].mis, ctx->count,
                                                                      (ctx->J + 2) / 3, reinterpret_cast<int32_t *>(ctx->perm));
     ctx->launches++;
-    FS2D_CUDA(cudaMemcpyAsync(hostBins, ctx->perm, sizeof(int32_t) * ctx->count, cudaMemcpyDeviceToHost, ctx->stream));
+    FS2D_CUDA(fs2dCopyToHost(ctx, hostBins, ctx->perm, sizeof(int32_t) * ctx->count));
     FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
     return FS2D_OK;
 }

@@ -1084,6 +1084,20 @@ PcgArgs baseArgs(Ctx *ctx)
 }
 }  // namespace
 
+// Force the module loader to resolve the kernels that only run in slab mode (see capi.cu on lazy loading).
+void pcgPreloadSlabKernels()
+{
+    cudaFuncAttributes at;
+    cudaFuncGetAttributes(&at, pcgInitKernel<true>);
+    cudaFuncGetAttributes(&at, pcgPipeKernel<MODE_K1, true>);
+    cudaFuncGetAttributes(&at, pcgPipeKernel<MODE_K2, true>);
+    cudaFuncGetAttributes(&at, pcgMgCloseKernel);
+    cudaFuncGetAttributes(&at, pcgFinalizeKernel);
+    cudaFuncGetAttributes(&at, pcgTileFlagKernel);
+    cudaFuncGetAttributes(&at, pcgTileCompactKernel);
+    cudaGetLastError();
+}
+
 int pcgTileBlocks(const Ctx *ctx) { return divUp(ctx->I, TR) * divUp(ctx->J, TC); }
 
 static bool pipeUsable(const Ctx *ctx) { return (ctx->J % 2) == 0 && !ctx->forceTileKernels; }
@@ -1257,7 +1271,7 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
     {
         // only iterations that did work count (after convergence the kernels return at once)
         PcgScalars sc;
-        FS2D_CUDA(cudaMemcpyAsync(&sc, ctx->scalars, sizeof(sc), cudaMemcpyDeviceToHost, st));
+        FS2D_CUDA(fs2dCopyToHost(ctx, &sc, ctx->scalars, sizeof(sc)));
         FS2D_CUDA(cudaStreamSynchronize(st));
         const int executed = sc.iter < iterLimit ? sc.iter : iterLimit;
         for (int i = 0; i < executed; i++)
@@ -1288,7 +1302,7 @@ int pcgSpmvHost(Ctx *ctx, const double *in, double *out, bool precond)
         pcgTileKernel<MODE_APPLY_A><<<blocks, NT, 0, ctx->stream>>>(a);
     ctx->launches++;
     FS2D_CUDA(cudaGetLastError());
-    FS2D_CUDA(cudaMemcpyAsync(out, ctx->q, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    FS2D_CUDA(fs2dCopyToHost(ctx, out, ctx->q, bytes));
     FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
     return FS2D_OK;
 }

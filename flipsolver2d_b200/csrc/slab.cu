@@ -308,6 +308,22 @@ __global__ void slabGatherKernel(GatherArgs a)
     }
 }
 
+// ---------------------------------------------------------------- all-gather of the rows of one dense array
+struct GatherRowsArgs
+{
+    unsigned char *heap;
+    unsigned char *peerHeap[FS2D_MAX_RANKS];
+    int rank, world;
+    unsigned long long offset, bytesBegin, bytes;
+};
+
+__global__ void __launch_bounds__(256) slabGatherRowsKernel(GatherRowsArgs a)
+{
+    for (int r = 0; r < a.world; r++)
+        if (r != a.rank) copyBytes16(a.peerHeap[r] + a.offset + a.bytesBegin, a.heap + a.offset + a.bytesBegin, a.bytes);
+    __threadfence_system();
+}
+
 SlabMail *peerMailOf(Ctx *ctx, int r)
 {
     if (r < 0 || r >= ctx->slab.world) return nullptr;
@@ -362,7 +378,7 @@ int slabCheckError(Ctx *ctx)
 {
     if (!ctx->slab.enabled) return FS2D_OK;
     int err = 0;
-    FS2D_CUDA(cudaMemcpyAsync(&err, &ctx->mail->error, sizeof(err), cudaMemcpyDeviceToHost, ctx->stream));
+    FS2D_CUDA(fs2dCopyToHost(ctx, &err, &ctx->mail->error, sizeof(err)));
     FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
     if (err)
     {
@@ -460,8 +476,8 @@ int slabExchangeParticles(Ctx *ctx)
         FS2D_CUDA(cudaGetLastError());
         long long counts[2][4];
         unsigned long long overflow = 0;
-        FS2D_CUDA(cudaMemcpyAsync(counts, ctx->mail->counts, sizeof(counts), cudaMemcpyDeviceToHost, st));
-        FS2D_CUDA(cudaMemcpyAsync(&overflow, counters + 2, sizeof(overflow), cudaMemcpyDeviceToHost, st));
+        FS2D_CUDA(fs2dCopyToHost(ctx, counts, ctx->mail->counts, sizeof(counts)));
+        FS2D_CUDA(fs2dCopyToHost(ctx, &overflow, counters + 2, sizeof(overflow)));
         FS2D_CUDA(cudaStreamSynchronize(st));
         if (overflow)
         {
@@ -512,7 +528,7 @@ int slabAllGather(Ctx *ctx, const long long v[4], long long *out)
     ctx->launches++;
     FS2D_CUDA(cudaGetLastError());
     SlabGatherSlot slots[FS2D_MAX_RANKS];
-    FS2D_CUDA(cudaMemcpyAsync(slots, ctx->mail->gather[a.seq & 1ull], sizeof(slots), cudaMemcpyDeviceToHost, ctx->stream));
+    FS2D_CUDA(fs2dCopyToHost(ctx, slots, ctx->mail->gather[a.seq & 1ull], sizeof(slots)));
     FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int r = 0; r < s.world; r++)
     {
@@ -523,6 +539,33 @@ int slabAllGather(Ctx *ctx, const long long v[4], long long *out)
         }
         for (int k = 0; k < 4; k++) out[4 * r + k] = slots[r].v[k];
     }
+    return FS2D_OK;
+}
+
+// Every rank pushes the rows it owns of `array` into every other rank's copy. Bracketed by two all-gathers (host
+// synchronous): nobody is overwritten before it has finished what it was doing, nobody reads before all pushes landed.
+int slabGatherRows(Ctx *ctx, void *array, size_t rowBytes, int rowsTotal)
+{
+    SlabState &s = ctx->slab;
+    if (!s.enabled || s.world == 1) return FS2D_OK;
+    FS2D_TRY(requireConnected(ctx));
+    const long long zero[4] = {0, 0, 0, 0};
+    long long all[4 * FS2D_MAX_RANKS];
+    FS2D_TRY(slabAllGather(ctx, zero, all));
+    GatherRowsArgs a;
+    a.heap = ctx->heap;
+    for (int r = 0; r < FS2D_MAX_RANKS; r++) a.peerHeap[r] = r < s.world ? s.peerHeap[r] : nullptr;
+    a.rank = s.rank;
+    a.world = s.world;
+    a.offset = static_cast<unsigned long long>(static_cast<unsigned char *>(array) - ctx->heap);
+    const int rowEnd = s.rank == s.world - 1 ? rowsTotal : s.rowEnd;  // the extra U row belongs to the last slab
+    a.bytesBegin = static_cast<unsigned long long>(s.rowBegin) * rowBytes;
+    a.bytes = static_cast<unsigned long long>(rowEnd - s.rowBegin) * rowBytes;
+    const int blocks = std::max(1, ctx->smCount / s.share);
+    slabGatherRowsKernel<<<blocks, 256, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    FS2D_CUDA(cudaGetLastError());
+    FS2D_TRY(slabAllGather(ctx, zero, all));
     return FS2D_OK;
 }
 
@@ -558,6 +601,17 @@ int fs2d_slab_configure(fs2d_handle ctx, int rank, int world, int device_share)
     s.xchgBytes = 4 * recordBufferBytes(s.xchgCapacity, ctx->p.num_properties);
     FS2D_CUDA(cudaMalloc(reinterpret_cast<void **>(&s.xchg), s.xchgBytes));
     FS2D_CUDA(cudaMemset(s.xchg, 0, s.xchgBytes));
+    {
+        cudaFuncAttributes at;
+        cudaFuncGetAttributes(&at, slabHaloKernel);
+        cudaFuncGetAttributes(&at, slabClassifyKernel);
+        cudaFuncGetAttributes(&at, slabParticleKernel);
+        cudaFuncGetAttributes(&at, slabAppendKernel);
+        cudaFuncGetAttributes(&at, slabGatherKernel);
+        cudaFuncGetAttributes(&at, slabGatherRowsKernel);
+        cudaGetLastError();
+        pcgPreloadSlabKernels();
+    }
     s.peerHeap[rank] = ctx->heap;
     s.peerXchg[rank] = s.xchg;
     s.connected = 0;

@@ -284,6 +284,12 @@ int fs2d_slab_rows(fs2d_handle h, int *row_begin, int *row_end, int *halo_rows);
 /* All-gather of four int64 per rank (CFL max velocity, reseed candidate counts, particle totals):
  * out receives world x 4 values in rank order. Collective: every rank must call it. */
 int fs2d_slab_allgather(fs2d_handle h, const int64_t value[4], int64_t *out);
+/* Collective: every rank pushes the rows it owns of `grid` into every other rank's copy, so that afterwards
+ * fs2d_download_grid returns the whole grid on any rank (the host accessors of the reference -- fluidSdf(),
+ * materialGrid(), fluidVelocityGrid(), flipsolver2d.h:222-236 -- read whole grids). For FS2D_GRID_FLUID_SDF this is
+ * also where the deferred extrapolateLevelsetInside (flipsolver2d.cpp:1433-1494) runs: its BFS has unbounded radius
+ * and needs all slabs; without slabs the call only flushes that deferred pass. */
+int fs2d_slab_gather_grid(fs2d_handle h, int grid);
 
 #ifdef __cplusplus
 }
