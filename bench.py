@@ -189,7 +189,7 @@ def run_ours(args, rank, world, local_rank):
 
     from flipsolver2d_b200 import capi, host_api, scenes
 
-    if not torch.cuda.is_available() or capi.lib().fs2d_device_count() < 1:
+    if capi.lib().fs2d_device_count() < 1 or not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -197,11 +197,33 @@ def run_ours(args, rank, world, local_rank):
 
     tmp = tempfile.mkdtemp(prefix="fs2d_bench_")
     res = args.res
-    path = scenes.write_scene(scene_for(res), os.path.join(tmp, "scene_%d.json" % res))
-    solver = host_api.Solver(path, quiet=True, device=local_rank)
+    path = scenes.write_scene(scene_for(res), os.path.join(tmp, "scene_%d_r%d.json" % (res, rank)))
+    # N > 1: ONE scene decomposed into row slabs, one rank per GPU (strong scaling). The ranks exchange halo rows,
+    # migrating particles and the PCG reduction partials through peer-mapped device memory (CUDA IPC over NVLink);
+    # torch.distributed only carries the 256-byte IPC blobs at start-up and the timing reduction.
+    solver = host_api.Solver(path, quiet=True, device=local_rank, slab=(rank, world) if world > 1 else None)
+    if world > 1:
+        blob = torch.frombuffer(bytearray(solver.slab_export()), dtype=torch.uint8).cuda()
+        blobs = [torch.empty_like(blob) for _ in range(world)]
+        dist.all_gather(blobs, blob)
+        for r in range(world):
+            if r != rank:
+                solver.slab_connect(r, bytes(blobs[r].cpu().numpy().tobytes()))
+        dist.barrier()
     solver.prepare()  # frame-0 rasterisation + seeding + upload: set-up, not timed
     dev = solver.device(num_properties=2)
     N = solver.N
+    rows_lo, rows_hi = (0, solver.I)
+    if world > 1:
+        rows_lo, rows_hi, _ = dev.slab_rows()
+    own_cells = (rows_hi - rows_lo) * solver.J
+
+    def total(v):
+        if world == 1:
+            return v
+        t = torch.tensor([float(v)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        return type(v)(t.item())
     stream = torch.cuda.ExternalStream(capi.lib().fs2d_stream(dev.h), device=torch.device("cuda", local_rank))
 
     def barrier():
@@ -232,12 +254,14 @@ def run_ours(args, rank, world, local_rank):
     sampler.start()
     ms = timed(solver.step_substep, args.steps)
     clocks = sampler.summary()
-    launches = solver.kernel_launches() - launches0
+    launches = total(solver.kernel_launches() - launches0)
     prof_ms, prof_n = dev.pcg_profile_read()
     dev.pcg_profile(False)
     stats = solver.stats()
-    particles = solver.particle_count()
-    active_cells = dev.pcg_active_cells()
+    particles = solver.particle_count()          # this rank's
+    particles_all = total(particles)
+    active_cells = dev.pcg_active_cells()        # this rank's
+    active_cells_all = total(int(active_cells))
 
     # ---- the same substeps with the PCG kernels walking the WHOLE grid (fs2d_pcg_set_dense): every vector
     # pass streams 128 MB from HBM, which is the configuration the HBM roofline of SURVEY 8(d) is defined on
@@ -253,7 +277,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- end to end: particle state crosses PCIe both ways every step
     P = particles
     K = 2
-    cap = int(P * 1.25) + 1024
+    cap = int((particles_all if world > 1 else P) * 1.25) + 1024  # slabs: particles migrate between ranks
     pos = torch.empty((cap, 2), dtype=torch.float32).pin_memory()
     vel = torch.empty((cap, 2), dtype=torch.float32).pin_memory()
     props = torch.empty((K * cap,), dtype=torch.float32).pin_memory()
@@ -281,9 +305,10 @@ def run_ours(args, rank, world, local_rank):
     state["h2d"] = state["d2h"] = 0
     e2e_steps = args.steps
     e2e_ms = timed(e2e_step, e2e_steps)
-    e2e = {"value": world * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": state["h2d"] // e2e_steps,
-           "d2h_bytes_per_step": state["d2h"] // e2e_steps,
-           "what": "per step: fs2d_upload_particles from pinned host buffers, FlipSolver::stepSubstep, fs2d_download_particles"}
+    e2e = {"value": e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": total(state["h2d"]) // e2e_steps,
+           "d2h_bytes_per_step": total(state["d2h"]) // e2e_steps,
+           "what": "per step: fs2d_upload_particles from pinned host buffers, FlipSolver::stepSubstep, fs2d_download_particles"
+                   + (" (every rank moves the particles of its slab; bytes summed over ranks)" if world > 1 else "")}
 
     if rank != 0:
         return
@@ -302,17 +327,19 @@ def run_ours(args, rank, world, local_rank):
                 "k2": {"kernel": "pcgPipeKernel<K2>", "bytes_per_launch": k2_bytes, "avg_launch_ms": k2_ms,
                        "launches_timed": int(p_n[1]), "achieved": k2_bytes / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else 0.0}}
 
-    dense = kernel_roofline(dprof_ms, dprof_n, N)
+    dense = kernel_roofline(dprof_ms, dprof_n, own_cells)
     act = kernel_roofline(prof_ms, prof_n, active_cells)
     roofline = {"bound": "hbm", "kernel": "pcgPipeKernel<K1>", "achieved": dense["k1"]["achieved"], "peak": peak, "unit": "GB/s",
                 "frac": dense["k1"]["achieved"] / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
                 "bytes_per_launch": dense["k1"]["bytes_per_launch"], "avg_launch_ms": dense["k1"]["avg_launch_ms"],
                 "launches_timed": dense["k1"]["launches_timed"],
                 "measured_in": "second timed region of this run: the same %d substeps with fs2d_pcg_set_dense(1), i.e. the "
-                               "kernels walk all %d cells and every vector pass comes from HBM" % (args.steps, N),
+                               "kernels walk all %d cells%s and every vector pass comes from HBM" %
+                               (args.steps, own_cells, " of rank 0's slab (launch time includes waiting for the peers' "
+                                "reduction partials and halo rows, which ride on these kernels)" if world > 1 else ""),
                 "k2": dict(dense["k2"], frac=dense["k2"]["achieved"] / peak),
                 "pcg_share_of_step": (dprof_ms[0] + dprof_ms[1]) / dense_ms if dense_ms > 0 else None,
-                "dense_walk": {"value": world * args.steps / (dense_ms * 1e-3), "unit": UNIT, "ms_per_step": dense_ms / args.steps},
+                "dense_walk": {"value": args.steps / (dense_ms * 1e-3), "unit": UNIT, "ms_per_step": dense_ms / args.steps},
                 "active_tile_walk": dict(act, pcg_share_of_step=(prof_ms[0] + prof_ms[1]) / ms if ms > 0 else None,
                                          note="default mode (timed region of `value`): tiles without matrix rows are skipped; "
                                               "the %d walked cells x 7 vectors fit the 126 MB L2, so these GB/s are not an HBM "
@@ -320,14 +347,18 @@ def run_ours(args, rank, world, local_rank):
     per = max(stats["substeps"], 1)
     stage_ms = {name: round(float(stats["timings"][k]) / per, 3) for k, name in enumerate(host_api.STAGES)}
     base = cpu_baseline(args, tmp) if world == 1 and not args.no_cpu_baseline else None
-    line = {"metric": METRIC, "value": world * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+    line = {"metric": METRIC, "value": args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak" if world == 1 else "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(res), "cells": N, "particles": particles,
-                       "l2": "every PCG vector (%d MB) and the particle arrays exceed the 126 MB L2" % (N * 8 // 2 ** 20),
-                       "parallelism": "1 GPU" if world == 1 else "%d independent replicas (one scene per GPU)" % world,
+            "config": {"workload": workload_name(res), "cells": N, "particles": particles_all,
+                       "l2": "every PCG vector (%d MB%s) and the particle arrays exceed the 126 MB L2"
+                             % (own_cells * 8 // 2 ** 20, " per rank" if world > 1 else ""),
+                       "parallelism": "1 GPU" if world == 1 else
+                       "%d row slabs of one scene, one rank per GPU; halo rows, particle migration and the PCG all-reduces "
+                       "go through peer-mapped memory (CUDA IPC over NVLink), fused into the iteration kernels" % world,
                        "pcg_iterations_last_frame": {"pressure": stats["pressure_iters"], "density": stats["density_iters"]},
-                       "pcg_walk": "active tiles (%d of %d cells)" % (active_cells, N),
+                       "pcg_walk": "active tiles (%d of %d cells)" % (active_cells_all, N),
                        "stage_ms_per_substep_last_frame": stage_ms},
             "roofline": roofline, "cpu_baseline": base, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
     print(json.dumps(line), flush=True)

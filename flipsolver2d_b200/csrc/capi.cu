@@ -527,6 +527,14 @@ int fs2d_pcg_trace(fs2d_handle ctx, double *host_trace, int max_iterations, int 
     return FS2D_OK;
 }
 
+// Debug aid, not part of the ABI header: copies the FS2D_MG_DEBUG&8 timeline (1024 x 8 globaltimer stamps) out.
+int fs2d_debug_mg_timeline(fs2d_handle ctx, unsigned long long *host_out)
+{
+    if (!ctx || !host_out || !ctx->mgTimeline) return FS2D_ERR_STATE;
+    FS2D_CUDA(fs2dCopyToHost(ctx, host_out, ctx->mgTimeline, 1024 * 8 * sizeof(unsigned long long)));
+    return FS2D_OK;
+}
+
 int fs2d_pcg_set_dense(fs2d_handle ctx, int dense)
 {
     if (!ctx) return FS2D_ERR_ARG;

@@ -20,6 +20,7 @@
 // (linearsolver.h:15-20); arithmetic uses explicit non-contracted mul/add in the reference's
 // evaluation order so a single operator application is bit-identical to the strict oracle.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "fs2d_internal.h"
@@ -80,6 +81,10 @@ struct MgArgs
     SlabMail *peerMail[FS2D_MAX_RANKS];
     double *loOut1, *hiOut1;              // the row neighbours' copies of out1 (nullptr at the domain ends)
     int iterLimit;
+    unsigned long long *timeline;         // debug: 8 globaltimer stamps per phase (nullptr normally)
+    int debug;                            // FS2D_MG_DEBUG bit mask (timing experiments only; results are wrong when set):
+                                          // 1 = do not wait for the peers' partials, 2 = no halo-row stores into the peers,
+                                          // 4 = device-scope instead of system-scope fence in every CTA
 };
 
 constexpr long long MG_SPIN_LIMIT = 8000000000ll;
@@ -92,7 +97,7 @@ __device__ __forceinline__ bool mgCollect(const MgArgs &m, int phase, bool wait,
     for (int r = 0; r < m.world; r++)
     {
         const SlabPcgSlot *slot = &m.mail->pcg[m.ringBase + (phase & 7)][r];
-        if (wait)
+        if (wait && !((m.debug & 1) && phase > 0))
         {
             const volatile unsigned long long *tag = &slot->tag;
             const long long t0 = clock64();
@@ -128,6 +133,18 @@ __device__ __forceinline__ void mgPublish(const MgArgs &m, double v0, double v1)
         __threadfence_system();
         *reinterpret_cast<volatile unsigned long long *>(&slot->tag) = m.solveTag + static_cast<unsigned long long>(m.phase) + 1ull;
     }
+}
+
+__device__ __forceinline__ unsigned long long globalTimerNs()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ void mgStamp(const MgArgs *m, int point)
+{
+    if (m && m->timeline) m->timeline[(m->phase & 1023) * 8 + point] = globalTimerNs();
 }
 
 struct MgScalars
@@ -224,7 +241,7 @@ __device__ void finishReductions(const PcgArgs &a, double accDot, double accMax,
     {
         a.partials[blockIdx.x] = bs;
         if (MODE == MODE_K2) a.partials[nb + blockIdx.x] = bm;
-        if (mg)
+        if (mg && !(mg->debug & 4))
             __threadfence_system();  // also orders this CTA's halo-row stores into the neighbours' arrays
         else
             __threadfence();
@@ -233,6 +250,7 @@ __device__ void finishReductions(const PcgArgs &a, double accDot, double accMax,
     }
     __syncthreads();
     if (!*isLastShared) return;
+    if (tid == 0) mgStamp(mg, 3);
     __threadfence();
     double total = finalReduce<false>(a.partials, nb, red);
     double emax = 0.0;
@@ -251,7 +269,9 @@ __device__ void finishReductions(const PcgArgs &a, double accDot, double accMax,
                 a.sc->ticketB = 0;
         }
         __syncthreads();
+        if (tid == 0) mgStamp(mg, 4);
         mgPublish(*mg, pub[0], pub[1]);
+        if (tid == 0) mgStamp(mg, 5);
         return;
     }
     if (tid == 0)
@@ -638,7 +658,9 @@ template <int MODE, bool MG> __global__ void __launch_bounds__(NT, 2) pcgPipeKer
     __shared__ MgScalars mgs;
     if (MG)
     {
+        if (threadIdx.x == 0 && blockIdx.x == 0) mgStamp(&mg, 0);
         if (threadIdx.x == 0) mgPrologue<MODE>(a, mg, &mgs);
+        if (threadIdx.x == 0 && blockIdx.x == 0) mgStamp(&mg, 1);
         __syncthreads();
         if (mgs.done) return;
         asm volatile("fence.proxy.async;" ::: "memory");  // halo rows written by a peer are read by bulk copies below
@@ -753,7 +775,7 @@ template <int MODE, bool MG> __global__ void __launch_bounds__(NT, 2) pcgPipeKer
                     else
                         o = rowM(static_cast<uint16_t>(info[q]), sm.preTbl, c, im, ip, jm, jp);
                     a.out1[n] = o;
-                    if (MG)
+                    if (MG && !(mg.debug & 2))
                     {
                         if (gi == mg.rowBegin && mg.loOut1) mg.loOut1[n] = o;
                         if (gi == mg.rowEnd - 1 && mg.hiOut1) mg.hiOut1[n] = o;
@@ -766,6 +788,7 @@ template <int MODE, bool MG> __global__ void __launch_bounds__(NT, 2) pcgPipeKer
         fenceProxyAsync();   // generic writes to this stage are ordered before the next bulk copy into it
         __syncthreads();
     }
+    if (MG && threadIdx.x == 0 && blockIdx.x == 0) mgStamp(&mg, 2);
     finishReductions<MODE>(a, accDot, accMax, sm.red, &sm.isLast, MG ? &mg : nullptr);
 }
 
@@ -1172,6 +1195,16 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
         for (int r = 0; r < sl.world; r++)
             mg.peerMail[r] = reinterpret_cast<SlabMail *>(sl.peerHeap[r] + (reinterpret_cast<unsigned char *>(ctx->mail) - ctx->heap));
         mg.iterLimit = iterLimit;
+        static const int mgDebug = std::getenv("FS2D_MG_DEBUG") ? std::atoi(std::getenv("FS2D_MG_DEBUG")) : 0;
+        mg.debug = mgDebug;
+        if (mgDebug & 8)
+        {
+            // timeline dump: 1024 phases x 8 stamps, allocated once per process, printed by tools/mg_probe.py
+            static unsigned long long *tl = nullptr;
+            if (!tl) cudaMalloc(reinterpret_cast<void **>(&tl), 1024 * 8 * sizeof(unsigned long long));
+            mg.timeline = tl;
+            ctx->mgTimeline = tl;
+        }
         const SlabRows ext = slabExt(ctx, 1);
         nLo = static_cast<long long>(ext.lo) * ctx->J;
         nHi = static_cast<long long>(ext.hi) * ctx->J;

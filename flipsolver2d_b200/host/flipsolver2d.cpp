@@ -1,5 +1,6 @@
 #include "flipsolver2d.h"
 
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
@@ -12,6 +13,7 @@ namespace
 bool g_quiet = std::getenv("FS2D_QUIET") != nullptr;
 int g_device = std::getenv("FS2D_DEVICE") ? std::atoi(std::getenv("FS2D_DEVICE")) : 0;
 int g_convergenceThreads = std::getenv("FS2D_CONVERGENCE_THREADS") ? std::atoi(std::getenv("FS2D_CONVERGENCE_THREADS")) : 0;
+int g_slabRank = 0, g_slabWorld = 1, g_slabShare = 1;
 
 // Frame-0 rasterisation runs once on the host; rows are independent.
 template <class F> void parallelRows(ssize_t rows, F f)
@@ -31,6 +33,12 @@ template <class F> void parallelRows(ssize_t rows, F f)
 void FlipSolver::setQuiet(bool q) { g_quiet = q; }
 void FlipSolver::setDevice(int ordinal) { g_device = ordinal; }
 void FlipSolver::setConvergenceThreads(int t) { g_convergenceThreads = t; }
+void FlipSolver::setSlab(int rank, int world, int deviceShare)
+{
+    g_slabRank = rank;
+    g_slabWorld = world;
+    g_slabShare = deviceShare;
+}
 
 FlipSolver::FlipSolver(const FlipSolverParameters *p)
     : LinearIndexable2d(p->gridSizeI, p->gridSizeJ), m_randEngine(p->seed), m_markerParticles(p->gridSizeI, p->gridSizeJ, 3),
@@ -106,8 +114,27 @@ fs2d_handle FlipSolver::device()
         if (rc != FS2D_OK)
             throw std::runtime_error("fs2d_create failed (" + std::to_string(rc) +
                                      "): this solver needs a CUDA device, there is no CPU path");
+        if (g_slabWorld > 1)
+        {
+            m_slabRank = g_slabRank;
+            m_slabWorld = g_slabWorld;
+            check(fs2d_slab_configure(m_device, m_slabRank, m_slabWorld, g_slabShare), "fs2d_slab_configure");
+        }
     }
     return m_device;
+}
+
+void FlipSolver::slabExport(void *blob) { check(fs2d_slab_export(device(), blob), "fs2d_slab_export"); }
+void FlipSolver::slabConnect(int peerRank, const void *blob) { check(fs2d_slab_connect(device(), peerRank, blob), "fs2d_slab_connect"); }
+
+size_t FlipSolver::globalParticleCount()
+{
+    if (m_slabWorld == 1) return particleCount();
+    int64_t v[4] = {static_cast<int64_t>(particleCount()), 0, 0, 0}, all[4 * 8];
+    check(fs2d_slab_allgather(device(), v, all), "fs2d_slab_allgather");
+    size_t total = 0;
+    for (int r = 0; r < m_slabWorld; r++) total += static_cast<size_t>(all[4 * r]);
+    return total;
 }
 
 int64_t FlipSolver::kernelLaunches() { return m_device ? fs2d_launch_count(m_device) : 0; }
@@ -289,8 +316,26 @@ void FlipSolver::reseedParticles()
 {
     int64_t candidates = 0;
     check(fs2d_reseed_plan(device(), &candidates), "fs2d_reseed_plan");
-    if (candidates == 0) return;
     static std::uniform_real_distribution<float> dist(0.f, 1.f);
+    if (m_slabWorld > 1)
+    {
+        // every rank plans its own rows; the draws of all ranks strung together in rank order are the reference's
+        // row-major stream, so each rank draws the whole frame's stream (same seed everywhere) and uses its slice
+        int64_t v[4] = {candidates, 0, 0, 0}, all[4 * 8];
+        check(fs2d_slab_allgather(device(), v, all), "fs2d_slab_allgather");
+        int64_t before = 0, total = 0;
+        for (int r = 0; r < m_slabWorld; r++)
+        {
+            if (r < m_slabRank) before += all[4 * r];
+            total += all[4 * r];
+        }
+        if (total == 0) return;
+        std::vector<float> u(static_cast<size_t>(2 * total));
+        for (float &x : u) x = dist(m_randEngine);
+        check(fs2d_reseed_apply(device(), candidates, u.data() + 2 * before), "fs2d_reseed_apply");
+        return;
+    }
+    if (candidates == 0) return;
     std::vector<float> u(static_cast<size_t>(2 * candidates));
     for (float &v : u) v = dist(m_randEngine);
     check(fs2d_reseed_apply(device(), candidates, u.data()), "fs2d_reseed_apply");
@@ -415,6 +460,29 @@ void FlipSolver::seedInitialFluid()
 
 void FlipSolver::uploadSeed()
 {
+    fs2d_handle h = device();
+    if (m_slabWorld > 1)
+    {
+        // every rank seeded the whole scene (same mt19937 stream); keep the particles whose cell row is ours
+        int lo = 0, hi = 0;
+        check(fs2d_slab_rows(h, &lo, &hi, nullptr), "fs2d_slab_rows");
+        size_t kept = 0;
+        const size_t all = m_seedPos.size() / 2;
+        for (size_t p = 0; p < all; p++)
+        {
+            const int row = static_cast<int>(std::floor(m_seedPos[2 * p]));
+            if (row < lo || row >= hi) continue;
+            m_seedPos[2 * kept] = m_seedPos[2 * p];
+            m_seedPos[2 * kept + 1] = m_seedPos[2 * p + 1];
+            m_seedVel[2 * kept] = m_seedVel[2 * p];
+            m_seedVel[2 * kept + 1] = m_seedVel[2 * p + 1];
+            for (auto &c : m_seedProps) c[kept] = c[p];
+            kept++;
+        }
+        m_seedPos.resize(2 * kept);
+        m_seedVel.resize(2 * kept);
+        for (auto &c : m_seedProps) c.resize(kept);
+    }
     const size_t n = m_seedPos.size() / 2;
     std::vector<float> props;
     for (auto &c : m_seedProps) props.insert(props.end(), c.begin(), c.end());
@@ -478,6 +546,7 @@ void FlipSolver::firstFrameInit()
 void FlipSolver::fetchGrid(int grid, void *dst, size_t bytes) const
 {
     if (!m_device || m_gridEpoch[grid] == m_mirrorEpoch) return;
+    if (m_slabWorld > 1) check(fs2d_slab_gather_grid(m_device, grid), "fs2d_slab_gather_grid");  // collective
     check(fs2d_download_grid(m_device, grid, dst, bytes), "fs2d_download_grid");
     m_gridEpoch[grid] = m_mirrorEpoch;
 }

@@ -190,6 +190,18 @@ public:
     // pool of T threads (vmath.cpp:100-136), 0 = true max-norm (env FS2D_CONVERGENCE_THREADS).
     static void setConvergenceThreads(int t);
     int64_t kernelLaunches();
+    // Row slabs over several GPUs (include/fs2d.h "row slabs"; the reference's ThreadPool splits the same loops over
+    // row ranges, threadpool.cpp:41-76): one process -- one solver -- per GPU, every rank loads the SAME scene.
+    // setSlab before the solver touches the device; then exchange the 256-byte blobs (slabExport -> every other
+    // rank's slabConnect, by any transport) before prepare()/stepFrame(). In slab mode stepFrame(), the grid
+    // accessors (which gather all rows) and globalParticleCount() are collective: every rank must call them.
+    // markerParticles() / particleCount() return the rank's own particles.
+    static void setSlab(int rank, int world, int deviceShare = 1);
+    void slabExport(void *blob /* FS2D_SLAB_HANDLE_BYTES */);
+    void slabConnect(int peerRank, const void *blob);
+    int slabRank() const { return m_slabRank; }
+    int slabWorld() const { return m_slabWorld; }
+    size_t globalParticleCount();
 
 protected:
     virtual fs2d_params deviceParameters() const;
@@ -282,6 +294,7 @@ protected:
     size_t m_viscosityPropertyIndex = static_cast<size_t>(-1);
 
     fs2d_handle m_device = nullptr;
+    int m_slabRank = 0, m_slabWorld = 1;
 };
 
 #endif

@@ -40,6 +40,28 @@ void fs2dh_set_quiet(int quiet) { FlipSolver::setQuiet(quiet != 0); }
 void fs2dh_set_device(int ordinal) { FlipSolver::setDevice(ordinal); }
 void fs2dh_set_convergence_threads(int threads) { FlipSolver::setConvergenceThreads(threads); }
 
+void fs2dh_set_slab(int rank, int world, int device_share) { FlipSolver::setSlab(rank, world, device_share); }
+
+int fs2dh_slab_export(fs2dh_solver s, void *blob)
+{
+    Holder *h = static_cast<Holder *>(s);
+    return guarded(h, [&]() { h->solver->slabExport(blob); });
+}
+
+int fs2dh_slab_connect(fs2dh_solver s, int peer_rank, const void *blob)
+{
+    Holder *h = static_cast<Holder *>(s);
+    return guarded(h, [&]() { h->solver->slabConnect(peer_rank, blob); });
+}
+
+int64_t fs2dh_global_particle_count(fs2dh_solver s)
+{
+    Holder *h = static_cast<Holder *>(s);
+    int64_t n = -1;
+    guarded(h, [&]() { n = static_cast<int64_t>(h->solver->globalParticleCount()); });
+    return n;
+}
+
 fs2dh_solver fs2dh_load_scene(const char *json_path)
 {
     if (!json_path) return nullptr;

@@ -34,6 +34,10 @@ def lib():
         "fs2dh_set_quiet": (None, [i32]),
         "fs2dh_set_device": (None, [i32]),
         "fs2dh_set_convergence_threads": (None, [i32]),
+        "fs2dh_set_slab": (None, [i32, i32, i32]),
+        "fs2dh_slab_export": (i32, [vp, vp]),
+        "fs2dh_slab_connect": (i32, [vp, i32, vp]),
+        "fs2dh_global_particle_count": (i64, [vp]),
         "fs2dh_load_scene": (vp, [C.c_char_p]),
         "fs2dh_destroy": (None, [vp]),
         "fs2dh_last_error": (C.c_char_p, [vp]),
@@ -63,6 +67,15 @@ def lib():
     return L
 
 
+def connect_slabs(solvers):
+    """Connect Solver objects living in THIS process (tests: several ranks on one GPU)."""
+    blobs = [s.slab_export() for s in solvers]
+    for s in solvers:
+        for r, blob in enumerate(blobs):
+            if r != s.rank:
+                s.slab_connect(r, blob)
+
+
 STAGES = ["ADVECTION", "DECOMPOSITION", "DENSITY", "PARTICLE_REBIN", "PARTICLE_TO_GRID", "GRID_UPDATE", "AFTER_TRANSFER",
           "PRESSURE", "VISCOSITY", "REPRESSURE", "PARTICLE_UPDATE", "PARTICLE_RESEED"]
 
@@ -74,17 +87,45 @@ def _p(a):
 class Solver:
     """JsonSceneReader::loadJson + FlipSolver::stepFrame through the C shim."""
 
-    def __init__(self, json_path, quiet=True, device=0, convergence_threads=0):
+    def __init__(self, json_path, quiet=True, device=0, convergence_threads=0, slab=None):
+        """slab = (rank, world[, device_share]): this solver owns one row slab of the scene (one process per GPU;
+        device_share > 1 only for tests that run several ranks on one GPU). The device handle is created here so
+        that the process-wide slab setting cannot leak into a solver made later."""
         self.L = lib()
         self.L.fs2dh_set_quiet(1 if quiet else 0)
         self.L.fs2dh_set_device(int(device))
         self.L.fs2dh_set_convergence_threads(int(convergence_threads))
+        self.rank, self.world = 0, 1
+        if slab is not None:
+            self.rank, self.world = int(slab[0]), int(slab[1])
+            self.L.fs2dh_set_slab(self.rank, self.world, int(slab[2]) if len(slab) > 2 else 1)
+        else:
+            self.L.fs2dh_set_slab(0, 1, 1)
         self.h = self.L.fs2dh_load_scene(str(json_path).encode())
         if not self.h:
             raise RuntimeError("JsonSceneReader::loadJson failed for %s" % json_path)
         self.I = self.L.fs2dh_size_i(self.h)
         self.J = self.L.fs2dh_size_j(self.h)
         self.N = self.I * self.J
+        if slab is not None:
+            if not self.L.fs2dh_device(self.h):
+                raise capi.Fs2dError("no device: %s" % self.L.fs2dh_last_error(self.h).decode())
+            self.L.fs2dh_set_slab(0, 1, 1)
+
+    def slab_export(self):
+        buf = C.create_string_buffer(capi.SLAB_HANDLE_BYTES)
+        self._ck(self.L.fs2dh_slab_export(self.h, C.cast(buf, C.c_void_p)), "slab_export")
+        return bytes(buf.raw)
+
+    def slab_connect(self, peer_rank, blob):
+        buf = C.create_string_buffer(bytes(blob), capi.SLAB_HANDLE_BYTES)
+        self._ck(self.L.fs2dh_slab_connect(self.h, int(peer_rank), C.cast(buf, C.c_void_p)), "slab_connect")
+
+    def global_particle_count(self):
+        n = int(self.L.fs2dh_global_particle_count(self.h))
+        if n < 0:
+            raise capi.Fs2dError("global_particle_count: %s" % self.L.fs2dh_last_error(self.h).decode())
+        return n
 
     def close(self):
         if getattr(self, "h", None):

@@ -21,6 +21,15 @@ void fs2dh_set_quiet(int quiet);                      /* silence the per-substep
 void fs2dh_set_device(int ordinal);                   /* CUDA device of solvers created afterwards */
 void fs2dh_set_convergence_threads(int threads);      /* fs2d_params.convergence_threads */
 
+/* Row slabs over several GPUs (fs2d.h "row slabs"): one process and one solver per GPU, all loading the same scene.
+ * fs2dh_set_slab applies to solvers whose device is created afterwards; exchange the FS2D_SLAB_HANDLE_BYTES blobs of
+ * fs2dh_slab_export between the ranks and hand each to fs2dh_slab_connect before fs2dh_prepare / stepping. Stepping,
+ * fs2dh_material and fs2dh_global_particle_count are then collective. */
+void fs2dh_set_slab(int rank, int world, int device_share);
+int fs2dh_slab_export(fs2dh_solver s, void *blob);
+int fs2dh_slab_connect(fs2dh_solver s, int peer_rank, const void *blob);
+int64_t fs2dh_global_particle_count(fs2dh_solver s);
+
 fs2dh_solver fs2dh_load_scene(const char *json_path); /* JsonSceneReader::loadJson; NULL on failure */
 void fs2dh_destroy(fs2dh_solver s);
 const char *fs2dh_last_error(fs2dh_solver s);

@@ -161,6 +161,47 @@ def test_slab_substeps_match_single_handle(ref_mod, scene_dir, world):
     single.close()
 
 
+@pytest.mark.parametrize("kind", ["falling", "source_sink"])
+def test_host_solver_slabs_match_single_solver(scene_dir, kind):
+    """The C++ host mirror (JsonSceneReader -> FlipSolver::stepFrame) with one solver per slab: seed partition, CFL
+    all-gather, reseed stream stitched over the ranks, collective grid accessors."""
+    from flipsolver2d_b200 import host_api
+    world = 2
+    if kind == "falling":
+        scene = _scene(128, falling=True)
+    else:
+        scene = scenes.source_sink(96, "flip")  # emitter (host RNG reseeding every substep) + sink + sloped solid
+        scene["settings"]["density"] = 0.02
+    path = scenes.write_scene(scene, str(scene_dir / ("hostslab_%s.json" % kind)))
+    frames = 3
+    single = host_api.Solver(path, quiet=True)
+    for _ in range(frames):
+        single.step_frame()
+    solvers = [host_api.Solver(path, quiet=True, slab=(r, world, world)) for r in range(world)]
+    host_api.connect_slabs(solvers)
+
+    def run(s):
+        for _ in range(frames):
+            s.step_frame()
+        return s.stats()
+
+    stats = capi.run_ranks([lambda s=s: run(s) for s in solvers])
+    want = single.stats()
+    for st in stats:
+        assert st["substeps"] == want["substeps"]
+        assert st["pressure_iters"] == want["pressure_iters"] and st["density_iters"] == want["density_iters"]
+    mats = capi.run_ranks([lambda s=s: s.material() for s in solvers])  # collective accessor: gathers all rows
+    for m in mats:
+        assert np.array_equal(m, single.material())
+    counts = capi.run_ranks([lambda s=s: s.global_particle_count() for s in solvers])
+    assert counts == [single.particle_count()] * world
+    assert sum(s.particle_count() for s in solvers) == single.particle_count()
+    assert min(s.particle_count() for s in solvers) > 0
+    for s in solvers:
+        s.close()
+    single.close()
+
+
 def test_slab_allgather_and_errors(ref_mod, scene_dir):
     scene = _scene(128)
     s = H.make_ref(ref_mod, scene, scene_dir / "slabmisc.json")
