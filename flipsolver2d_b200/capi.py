@@ -140,6 +140,8 @@ def lib():
         "fs2d_reseed_apply": (i32, [H, i64, vp]),
         "fs2d_nbflip_advect_grids": (i32, [H]),
         "fs2d_substep": (i32, [H, f32, vp, vp]),
+        "fs2d_pcg_set_stepwise": (i32, [H, i32]),
+        "fs2d_pcg_profile_solves": (i32, [H, vp, vp]),
         "fs2d_slab_configure": (i32, [H, i32, i32, i32]),
         "fs2d_slab_export": (i32, [H, vp]),
         "fs2d_slab_connect": (i32, [H, i32, vp]),
@@ -306,6 +308,15 @@ class Device:
 
     def pcg_profile(self, enable=True):
         self._ck(self.L.fs2d_pcg_profile(self.h, 1 if enable else 0), "pcg_profile")
+
+    def pcg_set_stepwise(self, stepwise=True):
+        self._ck(self.L.fs2d_pcg_set_stepwise(self.h, 1 if stepwise else 0), "pcg_set_stepwise")
+
+    def pcg_profile_solves(self):
+        ms = np.zeros(1, np.float64)
+        n = np.zeros(1, np.int64)
+        self._ck(self.L.fs2d_pcg_profile_solves(self.h, _p(ms), _p(n)), "pcg_profile_solves")
+        return float(ms[0]), int(n[0])
 
     def pcg_profile_read(self):
         ms = np.zeros(2, np.float64)

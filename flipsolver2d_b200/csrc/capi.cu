@@ -558,6 +558,23 @@ int fs2d_pcg_profile(fs2d_handle ctx, int enable)
     ctx->profilePcg = enable != 0;
     ctx->profMs[0] = ctx->profMs[1] = 0.0;
     ctx->profLaunches[0] = ctx->profLaunches[1] = 0;
+    ctx->profSolveMs = 0.0;
+    ctx->profSolves = 0;
+    return FS2D_OK;
+}
+
+int fs2d_pcg_profile_solves(fs2d_handle ctx, double *ms, int64_t *solves)
+{
+    if (!ctx || !ms || !solves) return FS2D_ERR_ARG;
+    *ms = ctx->profSolveMs;
+    *solves = ctx->profSolves;
+    return FS2D_OK;
+}
+
+int fs2d_pcg_set_stepwise(fs2d_handle ctx, int stepwise)
+{
+    if (!ctx) return FS2D_ERR_ARG;
+    ctx->stepwisePcg = stepwise != 0;
     return FS2D_OK;
 }
 

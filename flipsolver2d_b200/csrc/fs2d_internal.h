@@ -72,7 +72,10 @@ struct PcgScalars
     unsigned int ticketA;
     unsigned int ticketB;
     unsigned int ticketC;
-    unsigned int pad2;
+    unsigned int ticketS;           // whole-solve kernel: monotonic barrier arrivals
+    unsigned long long phaseNs[2];  // whole-solve kernel: device time spent in the K1 / K2 phases (globaltimer, CTA 0)
+    unsigned int phaseLaunches;     // iterations those times cover
+    unsigned int pad3;
 };
 
 // ------------------------------------------------------------------ row-slab decomposition (slab.cu)
@@ -90,6 +93,14 @@ struct SlabPcgSlot
     unsigned long long pad;
 };
 
+// Whole-solve kernel: a reduction result travels as four self-validating 8-byte words {32 data bits, 32-bit tag}
+// (the layout NCCL's LL protocol uses): 8-byte stores are atomic, so the reader needs no fence between payload and
+// flag -- it polls until all four words carry the tag it expects.
+struct SlabLLSlot
+{
+    unsigned long long w[4];   // v0 low, v0 high, v1 low, v1 high
+};
+
 struct SlabGatherSlot
 {
     long long v[4];
@@ -100,6 +111,7 @@ struct SlabGatherSlot
 struct SlabMail
 {
     SlabPcgSlot pcg[FS2D_PCG_RING][FS2D_MAX_RANKS];  // written by every rank (slot [.][writer])
+    SlabLLSlot ll[FS2D_PCG_RING][FS2D_MAX_RANKS];    // the same ring for the whole-solve kernel
     unsigned long long ready[2];   // [0] written by the lower neighbour (rank-1), [1] by the upper: "I am done reading
                                    //     what exchange #seq overwrites"
     unsigned long long data[2];    // "my data of exchange #seq has landed in your memory"
@@ -191,7 +203,10 @@ struct fs2d_context
     bool densePcg = std::getenv("FS2D_PCG_DENSE") != nullptr;  // walk every tile, not only the active ones
     int *tileFlags = nullptr, *activeTiles = nullptr, *activeCount = nullptr;
     bool forceTileKernels = std::getenv("FS2D_PCG_TILE") != nullptr;  // A/B switch: plain tiled kernels
+    bool stepwisePcg = std::getenv("FS2D_PCG_STEPWISE") != nullptr;  // A/B switch: two kernels per iteration instead of the whole-solve kernel
     bool profilePcg = false;
+    double profSolveMs = 0.0;             // whole-solve kernel: accumulated launch durations and their number
+    int64_t profSolves = 0;
     std::vector<cudaEvent_t> profEvents;
     double profMs[2] = {0.0, 0.0};        // accumulated device time of K1 / K2 launches
     int64_t profLaunches[2] = {0, 0};

@@ -122,18 +122,20 @@ __device__ __forceinline__ bool mgCollect(const MgArgs &m, int phase, bool wait,
 }
 
 // Publish this rank's partials for m.phase in every rank's mail (threads 0..world-1 of the last CTA).
-__device__ __forceinline__ void mgPublish(const MgArgs &m, double v0, double v1)
+__device__ __forceinline__ void mgPublishPhase(const MgArgs &m, int phase, double v0, double v1)
 {
     const int r = threadIdx.x;
     if (r < m.world)
     {
-        SlabPcgSlot *slot = &m.peerMail[r]->pcg[m.ringBase + (m.phase & 7)][m.rank];
+        SlabPcgSlot *slot = &m.peerMail[r]->pcg[m.ringBase + (phase & 7)][m.rank];
         *reinterpret_cast<volatile double *>(&slot->v0) = v0;
         *reinterpret_cast<volatile double *>(&slot->v1) = v1;
         __threadfence_system();
-        *reinterpret_cast<volatile unsigned long long *>(&slot->tag) = m.solveTag + static_cast<unsigned long long>(m.phase) + 1ull;
+        *reinterpret_cast<volatile unsigned long long *>(&slot->tag) = m.solveTag + static_cast<unsigned long long>(phase) + 1ull;
     }
 }
+
+__device__ __forceinline__ void mgPublish(const MgArgs &m, double v0, double v1) { mgPublishPhase(m, m.phase, v0, v1); }
 
 __device__ __forceinline__ unsigned long long globalTimerNs()
 {
@@ -503,7 +505,18 @@ __device__ __forceinline__ void fenceProxyAsync() { asm volatile("fence.proxy.as
 // zero-filled with ordinary stores (visible to the consumers through the __syncthreads that separates
 // the issue from the use of a stage).
 template <int MODE>
+__device__ __forceinline__ void pipeIssueV(PipeStage<MODE> &st, unsigned long long *bar, const PcgArgs &a, const double *in0,
+                                          const double *in1, const double *xv, int tile, int lane);
+
+template <int MODE>
 __device__ __forceinline__ void pipeIssue(PipeStage<MODE> &st, unsigned long long *bar, const PcgArgs &a, int tile, int lane)
+{
+    pipeIssueV<MODE>(st, bar, a, a.in0, a.in1, a.x, tile, lane);
+}
+
+template <int MODE>
+__device__ __forceinline__ void pipeIssueV(PipeStage<MODE> &st, unsigned long long *bar, const PcgArgs &a, const double *in0,
+                                          const double *in1, const double *xv, int tile, int lane)
 {
     const int ti = tile / a.tilesJ, tj = tile - ti * a.tilesJ;
     const long long J = a.J, N = a.N;
@@ -555,13 +568,13 @@ __device__ __forceinline__ void pipeIssue(PipeStage<MODE> &st, unsigned long lon
         if (segHi > segLo)
         {
             const unsigned int nb = static_cast<unsigned int>(segHi - segLo) * 8u;
-            bulkLoad(da + (segLo - n0), a.in0 + segLo, nb, bar);
-            bulkLoad(db + (segLo - n0), a.in1 + segLo, nb, bar);
+            bulkLoad(da + (segLo - n0), in0 + segLo, nb, bar);
+            bulkLoad(db + (segLo - n0), in1 + segLo, nb, bar);
         }
         if (MODE == MODE_K1 && r >= 1 && r <= TR && xHi > xLo)
         {
             const long long m0 = (i0 - 1 + r) * J + j0;
-            bulkLoad(st.x + (r - 1) * TC + (xLo - m0), a.x + xLo, static_cast<unsigned int>(xHi - xLo) * 8u, bar);
+            bulkLoad(st.x + (r - 1) * TC + (xLo - m0), xv + xLo, static_cast<unsigned int>(xHi - xLo) * 8u, bar);
         }
     }
 }
@@ -790,6 +803,390 @@ template <int MODE, bool MG> __global__ void __launch_bounds__(NT, 2) pcgPipeKer
     }
     if (MG && threadIdx.x == 0 && blockIdx.x == 0) mgStamp(&mg, 2);
     finishReductions<MODE>(a, accDot, accMax, sm.red, &sm.isLast, MG ? &mg : nullptr);
+}
+
+// ------------------------------------------------------------------ whole-solve kernel
+// One persistent, cooperatively launched kernel runs ALL iterations of a solve. The two kernel boundaries per
+// iteration of the pipelined path (launch gap + cold pipeline + last-CTA reduction, ~10 us each on one GPU, ~20 us
+// with peers) become two grid-wide barriers that carry the reductions:
+//   every CTA: block partial -> partials[cta], arrive on a monotonic ticket;
+//   the last CTA to arrive reduces the partials in a fixed order and PUBLISHES the rank's sum / max into the mail slot
+//   of every rank (its own included; peers through peer-mapped memory), tagged with the phase;
+//   every CTA of every rank waits for the tags of all ranks in its OWN memory and adds the values in rank order.
+// So the all-reduce across GPUs is the barrier itself (one NVLink hop), every CTA everywhere derives bit-identical
+// alpha / beta / err, and the scalars never leave registers. Tiles are assigned to CTAs statically; the tile walk
+// (bulk-copy pipeline, in-place derived vector, 5-point operator from shared memory) is the one of pcgPipeKernel.
+// Phase numbering, mail ring and halo-row pushes are those of the slab path above (phase 0 = pcgInitKernel<true>).
+__device__ __forceinline__ unsigned int llTag(const MgArgs &m, int phase)
+{
+    return static_cast<unsigned int>((m.solveTag >> 4) + static_cast<unsigned long long>(phase) + 1ull);  // solveSeq * 65536 + phase + 1
+}
+
+// Threads 0 .. 4*world-1 of the calling CTA store one word each into rank (t >> 2)'s mail.
+template <bool MG> __device__ __forceinline__ void llPublish(const MgArgs &m, int phase, double v0, double v1)
+{
+    const int t = threadIdx.x;
+    if (t < 4 * m.world)
+    {
+        const int r = t >> 2, word = t & 3;
+        const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(word < 2 ? v0 : v1));
+        const unsigned long long half = (word & 1) ? (bits >> 32) : (bits & 0xffffffffull);
+        unsigned long long *dst = &m.peerMail[r]->ll[m.ringBase + (phase & 7)][m.rank].w[word];
+        // everything this rank wrote before the barrier (tile outputs; halo rows pushed into the neighbours) is ordered
+        // before the word the consumers wait for
+        if (MG)
+            __threadfence_system();
+        else
+            __threadfence();
+        *reinterpret_cast<volatile unsigned long long *>(dst) = half | (static_cast<unsigned long long>(llTag(m, phase)) << 32);
+    }
+}
+
+// Warp 0 of the calling CTA: lane l < 4*world polls word (l & 3) of rank (l >> 2) in this rank's OWN mail; then the
+// values are combined in rank order (identical bits in every CTA of every rank). Returns false on a lost peer.
+template <bool MG> __device__ __forceinline__ bool llCollect(const MgArgs &m, int phase, double *sum, double *mx)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned int want = llTag(m, phase);
+    unsigned long long w = 0;
+    bool ok = true;
+    if (lane < 4 * m.world)
+    {
+        const unsigned long long *src = &m.mail->ll[m.ringBase + (phase & 7)][lane >> 2].w[lane & 3];
+        const long long t0 = clock64();
+        for (;;)
+        {
+            if (MG)
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
+            else
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
+            if (static_cast<unsigned int>(w >> 32) == want) break;
+            if (clock64() - t0 > MG_SPIN_LIMIT)
+            {
+                ok = false;
+                m.mail->error = 1;
+                break;
+            }
+        }
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    double s = 0.0, x = 0.0;
+    for (int r = 0; r < m.world; r++)
+    {
+        const unsigned long long a0 = __shfl_sync(0xffffffffu, w, 4 * r), a1 = __shfl_sync(0xffffffffu, w, 4 * r + 1);
+        const unsigned long long b0 = __shfl_sync(0xffffffffu, w, 4 * r + 2), b1 = __shfl_sync(0xffffffffu, w, 4 * r + 3);
+        s += __longlong_as_double(static_cast<long long>((a0 & 0xffffffffull) | (a1 << 32)));
+        x = fmax(x, __longlong_as_double(static_cast<long long>((b0 & 0xffffffffull) | (b1 << 32))));
+    }
+    *sum = s;
+    *mx = x;
+    return ok;
+}
+
+// Sum and max over the CTA in one pass (same operation order as blockReduce); result valid in thread 0.
+__device__ __forceinline__ void blockReduce2(double &s, double &m, double *scratch /* >= 16 doubles */)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    s = warpSum(s);
+    m = warpMax(m);
+    __syncthreads();
+    if (lane == 0)
+    {
+        scratch[warp] = s;
+        scratch[8 + warp] = m;
+    }
+    __syncthreads();
+    if (warp == 0)
+    {
+        s = (lane < (blockDim.x >> 5)) ? scratch[lane] : 0.0;
+        m = (lane < (blockDim.x >> 5)) ? scratch[8 + lane] : 0.0;
+        s = warpSum(s);
+        m = warpMax(m);
+    }
+}
+
+struct SolveSmem
+{
+    PipeStage<MODE_K1> st[PSTAGES];       // phase B views each stage as a (smaller) PipeStage<MODE_K2>
+    unsigned long long full[PSTAGES];
+    double red[16];
+    double preTbl[8];
+    double pub[2];
+    double bc[2];
+    int isLast;
+    int ok;
+};
+
+struct SolveArgs
+{
+    PcgArgs a;                            // operator tables, partials, scalars, trace, tol, active-tile list
+    double *z, *q, *x, *s[2], *r[2];
+    double *loQ, *hiQ, *loZ, *hiZ;        // the row neighbours' copies of q and z (slab mode)
+    int numTiles;                         // tiles of the dense walk (active walk: *a.activeCount)
+    int iterLimit;
+    unsigned int *ticket;                 // zeroed before the launch
+};
+
+template <int MODE, bool MG>
+__device__ __forceinline__ void pipeWalk(PipeStage<MODE> *st0, PipeStage<MODE> *st1, unsigned long long *full, const double *preTbl,
+                                         const PcgArgs &a, const MgArgs &mg, const double *__restrict__ in0,
+                                         const double *__restrict__ in1, double *__restrict__ out0, double *__restrict__ out1,
+                                         double *__restrict__ xv, double *loOut1, double *hiOut1, double coef, double alphaPrev,
+                                         int numTiles, unsigned int &use0, unsigned int &use1, double &accDot, double &accMax)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long J = a.J;
+    int myTiles = (numTiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    if (myTiles < 0) myTiles = 0;
+    auto tileAt = [&](int k) -> int {
+        const int t = blockIdx.x + k * gridDim.x;
+        return a.activeTiles ? a.activeTiles[t] : (MG ? mg.tileBase + t : t);
+    };
+    if (warp == 0 && myTiles > 0) pipeIssueV<MODE>(*st0, &full[0], a, in0, in1, xv, tileAt(0), lane);
+    const int bc = tid % TC, rg = tid / TC;
+    for (int k = 0; k < myTiles; k++)
+    {
+        const int s = k & 1;
+        const unsigned int parity = (s ? use1 : use0) & 1u;
+        if (s)
+            use1++;
+        else
+            use0++;
+        const int tile = tileAt(k);
+        if (warp == 0 && k + 1 < myTiles) pipeIssueV<MODE>(s ? *st0 : *st1, &full[s ^ 1], a, in0, in1, xv, tileAt(k + 1), lane);
+        const int ti = tile / a.tilesJ, tj = tile - ti * a.tilesJ;
+        const int i0 = ti * TR, j0 = tj * TC;
+        PipeStage<MODE> &st = s ? *st1 : *st0;
+        const long long gj = j0 + bc;
+        unsigned int info[TR / 2];
+#pragma unroll
+        for (int q = 0; q < TR / 2; q++)
+        {
+            const long long gi = i0 + rg * (TR / 2) + q;
+            info[q] = 0;
+            if (gi < a.I && gj < J)
+            {
+                const long long n = gi * J + gj;
+                info[q] = (MODE == MODE_K1) ? static_cast<unsigned int>(a.rowInfo[n]) : static_cast<unsigned int>(a.preInfo[n]);
+            }
+        }
+        mbarWait(&full[s], parity);
+        for (int e = tid; e < PTILE; e += NT)
+        {
+            const int ar = e / PSW, c = e - ar * PSW;
+            const double av = st.a[e], bv = st.b[e];
+            double v;
+            if (MODE == MODE_K1)
+                v = __dadd_rn(av, __dmul_rn(bv, coef));
+            else
+                v = __dsub_rn(av, __dmul_rn(bv, coef));
+            st.a[e] = v;
+            const long long gi = i0 - 1 + ar, gjj = j0 - 2 + c;
+            if (ar >= 1 && ar <= TR && c >= 2 && c < TC + 2 && gi < a.I && gjj < J)
+            {
+                const long long n = gi * J + gjj;
+                out0[n] = v;
+                if (MODE == MODE_K1) xv[n] = __dadd_rn(st.x[(ar - 1) * TC + (c - 2)], __dmul_rn(bv, alphaPrev));
+            }
+            else if (MG && c >= 2 && c < TC + 2 && gjj < J && ((ar == 0 && gi == mg.rowBegin - 1 && gi >= 0) || (gi == mg.rowEnd && gi < a.I && ar <= TR + 1)))
+            {
+                out0[gi * J + gjj] = v;  // halo row of the slab, kept current redundantly (same bits as on the owner)
+            }
+        }
+        __syncthreads();
+        if (gj < J)
+        {
+#pragma unroll
+            for (int q = 0; q < TR / 2; q++)
+            {
+                const int ar = 1 + rg * (TR / 2) + q;
+                const long long gi = i0 - 1 + ar;
+                if (gi < a.I)
+                {
+                    const long long n = gi * J + gj;
+                    const double *t = st.a + ar * PSW + bc + 2;
+                    const double c = t[0], im = t[-PSW], ip = t[PSW], jm = t[-1], jp = t[1];
+                    double o;
+                    if (MODE == MODE_K1)
+                        o = rowA(static_cast<uint8_t>(info[q]), a.scale, c, im, ip, jm, jp);
+                    else
+                        o = rowM(static_cast<uint16_t>(info[q]), preTbl, c, im, ip, jm, jp);
+                    out1[n] = o;
+                    if (MG)
+                    {
+                        if (gi == mg.rowBegin && loOut1) loOut1[n] = o;
+                        if (gi == mg.rowEnd - 1 && hiOut1) hiOut1[n] = o;
+                    }
+                    accDot += o * c;
+                    accMax = fmax(accMax, fabs(c));
+                }
+            }
+        }
+        fenceProxyAsync();
+        __syncthreads();
+    }
+}
+
+// Grid-wide (and, with slabs, machine-wide) barrier that all-reduces (v0: sum, v1: max). Returns false when a peer
+// did not answer within the spin limit.
+template <bool MG>
+__device__ __forceinline__ bool solveBarrier(const SolveArgs &g, const MgArgs &m, int phase, unsigned int barrierIndex, double v0,
+                                             double v1, SolveSmem &sm, double *sum, double *mx)
+{
+    const int tid = threadIdx.x;
+    const unsigned int nb = gridDim.x;
+    blockReduce2(v0, v1, sm.red);
+    if (tid == 0)
+    {
+        g.a.partials[blockIdx.x] = v0;
+        g.a.partials[nb + blockIdx.x] = v1;
+        if (MG)
+            __threadfence_system();  // also orders this CTA's halo-row stores into the neighbours' arrays
+        else
+            __threadfence();
+        sm.isLast = (atomicAdd(g.ticket, 1u) == (barrierIndex + 1u) * nb - 1u);
+    }
+    __syncthreads();
+    if (sm.isLast)
+    {
+        // fixed assignment of partials to threads, then the fixed block tree: deterministic, same order as finalReduce
+        double ts = 0.0, tm = 0.0;
+        for (unsigned int k = tid; k < nb; k += blockDim.x)
+        {
+            ts += __ldcg(g.a.partials + k);
+            tm = fmax(tm, __ldcg(g.a.partials + nb + k));
+        }
+        blockReduce2(ts, tm, sm.red);
+        if (tid == 0)
+        {
+            sm.pub[0] = ts;
+            sm.pub[1] = tm;
+        }
+        __syncthreads();
+        llPublish<MG>(m, phase, sm.pub[0], sm.pub[1]);
+    }
+    if (tid < 32)
+    {
+        double s = 0.0, x = 0.0;
+        const bool ok = llCollect<MG>(m, phase, &s, &x);
+        if (tid == 0)
+        {
+            sm.ok = ok ? 1 : 0;
+            sm.bc[0] = s;
+            sm.bc[1] = x;
+        }
+    }
+    __syncthreads();
+    *sum = sm.bc[0];
+    *mx = sm.bc[1];
+    asm volatile("fence.proxy.async;" ::: "memory");  // what other CTAs / peers wrote is read by bulk copies next
+    return sm.ok != 0;
+}
+
+template <bool MG> __global__ void __launch_bounds__(NT, 2) pcgSolveKernel(SolveArgs g, MgArgs mg)
+{
+    extern __shared__ __align__(128) unsigned char solveRaw[];
+    SolveSmem &sm = *reinterpret_cast<SolveSmem *>(solveRaw);
+    const int tid = threadIdx.x;
+    const bool scribe = blockIdx.x == 0 && tid == 0;  // keeps PcgScalars / the trace for the host
+    PcgScalars *sc = g.a.sc;
+    if (tid < 8) sm.preTbl[tid] = g.a.pre[tid];
+    if (tid == 0)
+    {
+#pragma unroll
+        for (int s = 0; s < PSTAGES; s++) mbarInit(&sm.full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        double s0 = 0.0, m0 = 0.0;
+        sm.ok = mgCollect(mg, 0, true, &s0, &m0) ? 1 : 0;  // phase 0: rhs.rhs and max|rhs| from pcgInitKernel<true>
+        sm.bc[0] = s0;
+        sm.bc[1] = m0;
+    }
+    fenceProxyAsync();
+    __syncthreads();
+    asm volatile("fence.proxy.async;" ::: "memory");
+    double sigma = sm.bc[0];
+    const double max0 = sm.bc[1];
+    const bool lost0 = sm.ok == 0;
+    __syncthreads();
+    if (lost0 || !(max0 > 1.0e-15))  // a lost peer, or VOps::isZero (vmath.cpp:47-58): x = 0, zero iterations
+    {
+        if (scribe)
+        {
+            sc->sigma = sigma;
+            sc->alpha = sc->beta = sc->gamma = sc->err = 0.0;
+            sc->iter = 0;
+            sc->result = 0;
+            sc->done = 1;
+        }
+        return;
+    }
+    const int numTiles = g.a.activeCount ? *g.a.activeCount : g.numTiles;
+    PipeStage<MODE_K1> *a0 = &sm.st[0], *a1 = &sm.st[1];
+    PipeStage<MODE_K2> *b0 = reinterpret_cast<PipeStage<MODE_K2> *>(&sm.st[0]), *b1 = reinterpret_cast<PipeStage<MODE_K2> *>(&sm.st[1]);
+    unsigned int use0 = 0, use1 = 0, bar = 0;
+    double alpha = 0.0, beta = 0.0, alphaPrev = 0.0, gamma = 0.0, err = 0.0;
+    int result = g.iterLimit, executed = 0;
+    unsigned long long tA = 0, tB = 0, t0 = scribe ? globalTimerNs() : 0ull;
+    for (int i = 0; i < g.iterLimit; i++)
+    {
+        // K1(i): s_i = z + beta s_{i-1}; x += alpha_{i-1} s_{i-1}; q = A s_i; gamma = q.s_i
+        double accDot = 0.0, accMax = 0.0, unused = 0.0;
+        pipeWalk<MODE_K1, MG>(a0, a1, sm.full, sm.preTbl, g.a, mg, g.z, g.s[i & 1], g.s[(i + 1) & 1], g.q, g.x, g.loQ, g.hiQ, beta,
+                              alphaPrev, numTiles, use0, use1, accDot, accMax);
+        if (!solveBarrier<MG>(g, mg, 2 * i + 1, bar++, accDot, 0.0, sm, &gamma, &unused)) break;
+        alpha = sigma / (gamma + 1e-8);  // linearsolver.cpp:50
+        if (scribe)
+        {
+            const unsigned long long t = globalTimerNs();
+            tA += t - t0;
+            t0 = t;
+        }
+        // K2(i): r -= alpha q; z = M r; sigma' = z.r; err = max|r|
+        accDot = 0.0;
+        accMax = 0.0;
+        pipeWalk<MODE_K2, MG>(b0, b1, sm.full, sm.preTbl, g.a, mg, g.r[i & 1], g.q, g.r[(i + 1) & 1], g.z, nullptr, g.loZ, g.hiZ, alpha, 0.0,
+                              numTiles, use0, use1, accDot, accMax);
+        double sigmaNew = 0.0;
+        if (!solveBarrier<MG>(g, mg, 2 * i + 2, bar++, accDot, accMax, sm, &sigmaNew, &err)) break;
+        executed = i + 1;
+        const bool converged = err <= g.a.tol;  // linearsolver.cpp:59-61
+        const double betaNew = converged ? 0.0 : sigmaNew / sigma;  // :66-67
+        if (scribe)
+        {
+            const unsigned long long t = globalTimerNs();
+            tB += t - t0;
+            t0 = t;
+            if (g.a.trace && i < g.a.traceCapacity)
+            {
+                g.a.trace[4 * i + 0] = alpha;
+                g.a.trace[4 * i + 1] = betaNew;
+                g.a.trace[4 * i + 2] = sigmaNew;
+                g.a.trace[4 * i + 3] = err;
+            }
+        }
+        if (converged)
+        {
+            result = i;
+            break;
+        }
+        beta = betaNew;
+        sigma = sigmaNew;
+        alphaPrev = alpha;
+    }
+    if (scribe)
+    {
+        sc->alpha = alpha;  // pending x += alpha s of the last executed iteration (pcgFinalizeKernel)
+        sc->beta = beta;
+        sc->sigma = sigma;
+        sc->gamma = gamma;
+        sc->err = err;
+        sc->iter = executed;
+        sc->result = result;
+        sc->done = 1;
+        sc->phaseNs[0] += tA;
+        sc->phaseNs[1] += tB;
+        sc->phaseLaunches += static_cast<unsigned int>(executed);
+    }
 }
 
 // Reference-compatible convergence value (vmath.cpp:100-136): for each ThreadPool range
@@ -1115,6 +1512,8 @@ void pcgPreloadSlabKernels()
     cudaFuncGetAttributes(&at, pcgPipeKernel<MODE_K1, true>);
     cudaFuncGetAttributes(&at, pcgPipeKernel<MODE_K2, true>);
     cudaFuncGetAttributes(&at, pcgMgCloseKernel);
+    cudaFuncGetAttributes(&at, pcgSolveKernel<true>);
+    cudaFuncGetAttributes(&at, pcgSolveKernel<false>);
     cudaFuncGetAttributes(&at, pcgFinalizeKernel);
     cudaFuncGetAttributes(&at, pcgTileFlagKernel);
     cudaFuncGetAttributes(&at, pcgTileCompactKernel);
@@ -1168,9 +1567,27 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
         return FS2D_ERR_ARG;
     }
 
+    // The whole-solve kernel (one cooperative launch for all iterations) is the default; the per-iteration kernels
+    // remain for odd gridSizeJ, the reference-compatible convergence test, and as the A/B baseline (FS2D_PCG_STEPWISE).
+    const bool whole = pipe && T == 0 && !ctx->stepwisePcg;
     MgArgs mg;
     memset(&mg, 0, sizeof(mg));
     long long nLo = 0, nHi = ctx->N, oLo = 0, oHi = ctx->N;
+    if (whole && !mgOn)
+    {
+        // one rank: the barrier of the whole-solve kernel still goes through the (local) mail ring
+        SlabState &sl = ctx->slab;
+        sl.solveSeq++;
+        mg.rank = 0;
+        mg.world = 1;
+        mg.rowBegin = 0;
+        mg.rowEnd = ctx->I;
+        mg.ringBase = static_cast<int>(sl.solveSeq & 1ull) * 8;
+        mg.solveTag = sl.solveSeq << 20;
+        mg.mail = ctx->mail;
+        mg.peerMail[0] = ctx->mail;
+        mg.iterLimit = iterLimit;
+    }
     auto peerOf = [&](int r, double *p) -> double * {
         if (r < 0 || r >= ctx->slab.world) return nullptr;
         return reinterpret_cast<double *>(ctx->slab.peerHeap[r] + (reinterpret_cast<unsigned char *>(p) - ctx->heap));
@@ -1221,7 +1638,7 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
             ctx->profEvents.push_back(e);
         }
     const bool active = pipe && !ctx->densePcg;
-    if (mgOn)
+    if (mgOn || whole)
     {
         mg.phase = 0;
         pcgInitKernel<true><<<flat, NT, 0, st>>>(ctx->rhs, ctx->x, ctx->r[0], ctx->z, ctx->s[0], active ? ctx->r[1] : nullptr, ctx->s[1], ctx->q,
@@ -1240,6 +1657,66 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
         ctx->launches += 2;
         a.activeTiles = ctx->activeTiles;
         a.activeCount = ctx->activeCount;
+    }
+    if (whole)
+    {
+        SolveArgs g;
+        g.a = a;
+        g.z = ctx->z;
+        g.q = ctx->q;
+        g.x = ctx->x;
+        g.s[0] = ctx->s[0];
+        g.s[1] = ctx->s[1];
+        g.r[0] = ctx->r[0];
+        g.r[1] = ctx->r[1];
+        g.loQ = mgOn ? peerOf(mg.rank - 1, ctx->q) : nullptr;
+        g.hiQ = mgOn ? peerOf(mg.rank + 1, ctx->q) : nullptr;
+        g.loZ = mgOn ? peerOf(mg.rank - 1, ctx->z) : nullptr;
+        g.hiZ = mgOn ? peerOf(mg.rank + 1, ctx->z) : nullptr;
+        g.numTiles = blocks;
+        g.iterLimit = iterLimit;
+        g.ticket = &ctx->scalars->ticketS;
+        FS2D_CUDA(cudaMemsetAsync(g.ticket, 0, sizeof(unsigned int), st));
+        if (prof)
+        {
+            FS2D_CUDA(cudaMemsetAsync(ctx->scalars->phaseNs, 0, 2 * sizeof(unsigned long long) + sizeof(unsigned int), st));
+            cudaEventRecord(ctx->profEvents[0], st);
+        }
+        void *args[] = {&g, &mg};
+        const size_t smem = sizeof(SolveSmem);
+        if (mgOn)
+        {
+            cudaFuncSetAttribute(pcgSolveKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            FS2D_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(pcgSolveKernel<true>), dim3(pipeBlocks), dim3(NT), args, smem, st));
+        }
+        else
+        {
+            cudaFuncSetAttribute(pcgSolveKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            FS2D_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(pcgSolveKernel<false>), dim3(pipeBlocks), dim3(NT), args, smem, st));
+        }
+        ctx->launches++;
+        if (prof) cudaEventRecord(ctx->profEvents[1], st);
+        pcgFinalizeKernel<<<flat, NT, 0, st>>>(ctx->x, ctx->s[0], ctx->s[1], oLo, oHi, ctx->scalars, iterLimit);
+        ctx->launches++;
+        FS2D_CUDA(cudaGetLastError());
+        if (prof)
+        {
+            PcgScalars sc;
+            FS2D_CUDA(fs2dCopyToHost(ctx, &sc, ctx->scalars, sizeof(sc)));
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ctx->profEvents[0], ctx->profEvents[1]);
+            // K1 / K2 split of the launch by the device-side phase clocks (CTA 0, globaltimer); the launch total is
+            // what the CUDA events saw
+            const double pa = static_cast<double>(sc.phaseNs[0]), pb = static_cast<double>(sc.phaseNs[1]);
+            const double tot = pa + pb > 0.0 ? pa + pb : 1.0;
+            ctx->profMs[0] += ms * pa / tot;
+            ctx->profMs[1] += ms * pb / tot;
+            ctx->profLaunches[0] += sc.iter;
+            ctx->profLaunches[1] += sc.iter;
+            ctx->profSolveMs += ms;
+            ctx->profSolves++;
+        }
+        return FS2D_OK;
     }
     for (int i = 0; i < iterLimit; i++)
     {

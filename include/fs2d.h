@@ -206,6 +206,13 @@ int fs2d_pcg_active_cells(fs2d_handle h, int64_t *cells);
  * that did work since the last fs2d_pcg_profile call. */
 int fs2d_pcg_profile(fs2d_handle h, int enable);
 int fs2d_pcg_profile_read(fs2d_handle h, double *ms2, int64_t *launches2);
+/* A solve is ONE cooperative launch (pcgSolveKernel: all iterations, the two reductions of an iteration carried by
+ * grid-wide barriers) unless gridSizeJ is odd or convergence_threads > 0. fs2d_pcg_set_stepwise(h, 1) selects the
+ * two-kernels-per-iteration path instead (same iterates; the A/B baseline). With profiling enabled
+ * fs2d_pcg_profile_solves returns the accumulated duration (CUDA events) and number of whole-solve launches, and
+ * fs2d_pcg_profile_read splits that time into the K1 / K2 phases by the kernel's own phase clocks. */
+int fs2d_pcg_set_stepwise(fs2d_handle h, int stepwise);
+int fs2d_pcg_profile_solves(fs2d_handle h, double *ms, int64_t *solves);
 /* IndexedPressureParameters::multiply (pressuredata.h:184-238) and
  * IndexedIPPCoefficients::multiply (PressureIPPCoeficients.h:79-132) alone, host vectors. */
 int fs2d_spmv(fs2d_handle h, const double *host_in, double *host_out);

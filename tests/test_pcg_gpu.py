@@ -174,3 +174,28 @@ assert itr < 400 and itd == itr
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "ITERS" in r.stdout
+
+
+@pytest.mark.parametrize("dense", [False, True])
+def test_whole_solve_kernel_equals_stepwise_kernels(ref_mod, scene_dir, dense):
+    """The default solve is ONE cooperative launch (pcgSolveKernel); the two-kernels-per-iteration path does the same
+    arithmetic with the same tile -> CTA assignment and reduction order, so iterates agree to the last bit."""
+    s = _ref_system(ref_mod, scene_dir, 192, dt=1.0 / 2000.0)  # small matrix scale: the solve converges within the cap
+    d = _device_for(s, iter_limit=400)
+    d.pcg_set_dense(dense)
+    unit = d.matrix()["is_unit"].astype(bool)
+    rng = np.random.default_rng(11)
+    rhs = np.where(unit, rng.standard_normal(s.N), 0.0)
+    for limit, tol in ((37, 0.0), (300, 1e-7), (5, 1e30), (0, 0.0)):
+        d.pcg_set_stepwise(True)
+        x_step, n_step = d.pcg_solve(rhs, limit, tol)
+        t_step = d.pcg_trace().copy()
+        d.pcg_set_stepwise(False)
+        x_whole, n_whole = d.pcg_solve(rhs, limit, tol)
+        t_whole = d.pcg_trace().copy()
+        assert n_whole == n_step
+        assert np.array_equal(t_whole, t_step)
+        assert np.array_equal(x_whole, x_step)
+    x0, n0 = d.pcg_solve(np.zeros(s.N), 50, 0.0)  # VOps::isZero: no iterations
+    assert n0 == 0 and not x0.any()
+    d.close()
