@@ -143,6 +143,7 @@ def lib():
         "fs2d_pcg_set_stepwise": (i32, [H, i32]),
         "fs2d_pcg_profile_solves": (i32, [H, vp, vp]),
         "fs2d_slab_configure": (i32, [H, i32, i32, i32]),
+        "fs2d_slab_configure_rows": (i32, [H, i32, i32, i32, vp]),
         "fs2d_slab_export": (i32, [H, vp]),
         "fs2d_slab_connect": (i32, [H, i32, vp]),
         "fs2d_slab_rows": (i32, [H, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
@@ -378,8 +379,13 @@ class Device:
         return ms, iters
 
     # ---- row slabs over several GPUs (or several ranks on one GPU, for tests)
-    def slab_configure(self, rank, world, device_share=1):
-        self._ck(self.L.fs2d_slab_configure(self.h, int(rank), int(world), int(device_share)), "slab_configure")
+    def slab_configure(self, rank, world, device_share=1, row_bounds=None):
+        if row_bounds is None:
+            self._ck(self.L.fs2d_slab_configure(self.h, int(rank), int(world), int(device_share)), "slab_configure")
+        else:
+            b = np.ascontiguousarray(row_bounds, np.int32)
+            assert b.size == world + 1
+            self._ck(self.L.fs2d_slab_configure_rows(self.h, int(rank), int(world), int(device_share), _p(b)), "slab_configure_rows")
         self.rank, self.world = int(rank), int(world)
 
     def slab_export(self):

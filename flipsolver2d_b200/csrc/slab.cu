@@ -573,7 +573,17 @@ extern "C" {
 
 int fs2d_slab_configure(fs2d_handle ctx, int rank, int world, int device_share)
 {
-    if (!ctx || world < 1 || world > FS2D_MAX_RANKS || rank < 0 || rank >= world || device_share < 1) return FS2D_ERR_ARG;
+    if (!ctx || world < 1 || world > FS2D_MAX_RANKS) return FS2D_ERR_ARG;
+    // equal numbers of 16-row tile rows per rank
+    int32_t bounds[FS2D_MAX_RANKS + 1];
+    const int tileRows = divUp(ctx->I, 16);
+    for (int r = 0; r <= world; r++) bounds[r] = std::min(ctx->I, 16 * static_cast<int>(static_cast<long long>(r) * tileRows / world));
+    return fs2d_slab_configure_rows(ctx, rank, world, device_share, bounds);
+}
+
+int fs2d_slab_configure_rows(fs2d_handle ctx, int rank, int world, int device_share, const int32_t *row_bounds)
+{
+    if (!ctx || !row_bounds || world < 1 || world > FS2D_MAX_RANKS || rank < 0 || rank >= world || device_share < 1) return FS2D_ERR_ARG;
     SlabState &s = ctx->slab;
     if (s.enabled)
     {
@@ -585,17 +595,25 @@ int fs2d_slab_configure(fs2d_handle ctx, int rank, int world, int device_share)
         ctx->lastError = "fs2d_slab_configure: needs an even gridSizeJ and convergence_threads = 0 (true max-norm test)";
         return FS2D_ERR_ARG;
     }
-    const int tileRows = divUp(ctx->I, 16);
+    if (row_bounds[0] != 0 || row_bounds[world] != ctx->I)
+    {
+        ctx->lastError = "fs2d_slab_configure_rows: the boundaries must start at 0 and end at gridSizeI";
+        return FS2D_ERR_ARG;
+    }
+    for (int r = 0; r < world; r++)
+    {
+        const bool aligned = r == 0 || row_bounds[r] % 16 == 0;
+        if (!aligned || row_bounds[r + 1] <= row_bounds[r] || (world > 1 && row_bounds[r + 1] - row_bounds[r] < s.halo))
+        {
+            ctx->lastError = "fs2d_slab_configure: slab boundaries must be multiples of 16 and a slab must hold at least 32 rows";
+            return FS2D_ERR_ARG;
+        }
+    }
     s.rank = rank;
     s.world = world;
     s.share = device_share;
-    s.rowBegin = 16 * static_cast<int>(static_cast<long long>(rank) * tileRows / world);
-    s.rowEnd = std::min(ctx->I, 16 * static_cast<int>(static_cast<long long>(rank + 1) * tileRows / world));
-    if (world > 1 && s.rowEnd - s.rowBegin < s.halo)
-    {
-        ctx->lastError = "fs2d_slab_configure: a slab must hold at least 32 rows";
-        return FS2D_ERR_ARG;
-    }
+    s.rowBegin = row_bounds[rank];
+    s.rowEnd = row_bounds[rank + 1];
     // migrants (CFL <= 5 cells -> a few rows) + ghost rows, every cell at the 2*ppc cap
     s.xchgCapacity = std::max<int64_t>(static_cast<int64_t>(ctx->J) * (s.ghost + 8) * 2 * std::max(ctx->p.particles_per_cell, 1), 1 << 16);
     s.xchgBytes = 4 * recordBufferBytes(s.xchgCapacity, ctx->p.num_properties);

@@ -118,10 +118,61 @@ fs2d_handle FlipSolver::device()
         {
             m_slabRank = g_slabRank;
             m_slabWorld = g_slabWorld;
-            check(fs2d_slab_configure(m_device, m_slabRank, m_slabWorld, g_slabShare), "fs2d_slab_configure");
+            const std::vector<int32_t> bounds = slabBounds(m_slabWorld);
+            check(fs2d_slab_configure_rows(m_device, m_slabRank, m_slabWorld, g_slabShare, bounds.data()), "fs2d_slab_configure_rows");
         }
     }
     return m_device;
+}
+
+// Slab boundaries balanced by work instead of by rows: the seed particles per 16-row tile row (every rank seeds the
+// whole scene with the same stream, so every rank computes the same table) plus a small cost per row for the dense
+// grid passes. In a dam break the fluid fills the lower half of the tank only: equal row counts would leave half of
+// the GPUs without a single particle or matrix row.
+std::vector<int32_t> FlipSolver::slabBounds(int world)
+{
+    prepareHost();
+    const int tileRows = static_cast<int>((m_sizeI + 15) / 16);
+    std::vector<double> w(static_cast<size_t>(tileRows), 0.0);
+    const size_t n = m_seedPos.size() / 2;
+    for (size_t p = 0; p < n; p++)
+    {
+        int t = static_cast<int>(std::floor(m_seedPos[2 * p])) / 16;
+        t = std::max(0, std::min(tileRows - 1, t));
+        w[static_cast<size_t>(t)] += 1.0;
+    }
+    const double base = std::max(1.0, 0.02 * static_cast<double>(n) / tileRows);
+    double total = 0.0;
+    for (double &x : w)
+    {
+        x += base;
+        total += x;
+    }
+    std::vector<int32_t> b(static_cast<size_t>(world) + 1, 0);
+    const int minTiles = 2;  // a slab holds at least 32 rows (the halo width)
+    if (tileRows < minTiles * world) throw std::runtime_error("the grid has too few rows for this many slabs");
+    double prefix = 0.0;
+    int t = 0;
+    for (int r = 1; r < world; r++)
+    {
+        const double target = total * r / world;
+        while (t < tileRows && prefix + w[static_cast<size_t>(t)] <= target)
+        {
+            prefix += w[static_cast<size_t>(t)];
+            t++;
+        }
+        int cut = t;
+        cut = std::max(cut, b[static_cast<size_t>(r) - 1] / 16 + minTiles);
+        cut = std::min(cut, tileRows - minTiles * (world - r));
+        while (t < cut)
+        {
+            prefix += w[static_cast<size_t>(t)];
+            t++;
+        }
+        b[static_cast<size_t>(r)] = 16 * cut;
+    }
+    b[static_cast<size_t>(world)] = static_cast<int32_t>(m_sizeI);
+    return b;
 }
 
 void FlipSolver::slabExport(void *blob) { check(fs2d_slab_export(device(), blob), "fs2d_slab_export"); }

@@ -202,6 +202,7 @@ public:
     int slabRank() const { return m_slabRank; }
     int slabWorld() const { return m_slabWorld; }
     size_t globalParticleCount();
+    std::vector<int32_t> slabBounds(int world);  // row boundaries balanced by seed particles per tile row
 
 protected:
     virtual fs2d_params deviceParameters() const;

@@ -285,6 +285,10 @@ int fs2d_substep(fs2d_handle h, float dt, float *stage_ms, int *iters);
  * Only FS2D_SIM_LIQUID without viscosity is slab-aware so far; other solvers report FS2D_ERR_STATE. */
 #define FS2D_SLAB_HANDLE_BYTES 256
 int fs2d_slab_configure(fs2d_handle h, int rank, int world, int device_share);
+/* The same with explicit slab boundaries: row_bounds[world + 1], row_bounds[0] = 0, row_bounds[world] = gridSizeI,
+ * the others multiples of 16, every slab at least 32 rows. Lets the caller balance the slabs by work (particles,
+ * fluid cells) instead of by rows: in a dam break most rows hold no fluid. Every rank must pass the same table. */
+int fs2d_slab_configure_rows(fs2d_handle h, int rank, int world, int device_share, const int32_t *row_bounds);
 int fs2d_slab_export(fs2d_handle h, void *handle_out /* FS2D_SLAB_HANDLE_BYTES */);
 int fs2d_slab_connect(fs2d_handle h, int peer_rank, const void *handle);
 int fs2d_slab_rows(fs2d_handle h, int *row_begin, int *row_end, int *halo_rows);

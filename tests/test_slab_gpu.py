@@ -21,11 +21,11 @@ def _scene(res, falling=False):
     return sc
 
 
-def _slab_devices(s, scene, world, **over):
+def _slab_devices(s, scene, world, row_bounds=None, **over):
     devs = []
     for r in range(world):
         d = H.make_device(s, scene, **over)
-        d.slab_configure(r, world, device_share=world)
+        d.slab_configure(r, world, device_share=world, row_bounds=row_bounds)
         devs.append(d)
     capi.connect_slabs(devs)
     return devs
@@ -102,8 +102,8 @@ def test_slab_pcg_matches_single_handle(ref_mod, scene_dir, world, dense):
     single.close()
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_slab_substeps_match_single_handle(ref_mod, scene_dir, world):
+@pytest.mark.parametrize("world,bounds", [(2, None), (4, None), (2, (0, 48, 128)), (2, (0, 96, 128)), (3, (0, 32, 80, 128))])
+def test_slab_substeps_match_single_handle(ref_mod, scene_dir, world, bounds):
     scene = _scene(128, falling=True)
     s = H.make_ref(ref_mod, scene, scene_dir / "slabstep.json")
     s.stage("FIRST_FRAME_INIT")
@@ -114,7 +114,7 @@ def test_slab_substeps_match_single_handle(ref_mod, scene_dir, world):
     H.sync_state(s, single)
     for _ in range(steps):
         single.substep(dt)
-    devs = _slab_devices(s, scene, world)
+    devs = _slab_devices(s, scene, world, row_bounds=bounds)  # None: equal row counts; else work-balanced style cuts
     assert sum(_sync_slab(s, d) for d in devs) == s.particle_count()
 
     def run(d):
