@@ -195,6 +195,7 @@ struct fs2d_context
     int maxBlocks = 0;
     PcgScalars *scalars = nullptr;    // device
     double *trace = nullptr;          // device, 4 doubles per iteration
+    void *viscScalars = nullptr;      // device scalars of the viscosity CG (viscosity.cu), allocated on first use
     unsigned long long *mgTimeline = nullptr;  // debug (FS2D_MG_DEBUG & 8): globaltimer stamps of the slab PCG kernels
     int traceCapacity = 0;
     int64_t *rangeLast = nullptr;     // device, convergence_threads entries

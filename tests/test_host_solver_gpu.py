@@ -73,3 +73,47 @@ def test_smoke_scene_steps(ref_mod, scene_dir):
     assert np.array_equal(d.download("MATERIAL"), s.grid("MATERIAL"))
     h.close()
     s.close()
+
+
+@pytest.mark.parametrize("sim,visc", [("nbflip", False), ("nbflip", True), ("flip", True)])
+def test_nbflip_and_viscous_frames_match_reference(ref_mod, scene_dir, sim, visc):
+    """BASELINE config 4 at test size: narrow-band FLIP (semi-Lagrangian grids, band prune / combine) and the implicit
+    viscosity stage with the re-projection that follows it, frame loop against the reference's own stepFrame."""
+    scene = _low_density(scenes.dam_break(64, sim, viscosity_enabled=visc))
+    path = scene_dir / ("hostgpu_%s_%d.json" % (sim, int(visc)))
+    s = H.make_ref(ref_mod, scene, path)
+    h = host_api.Solver(str(path), convergence_threads=s.threads)
+    for f in range(3):
+        s.step_frame()
+        h.step_frame()
+        rs, hs = s.stats(), h.stats()
+        assert hs["substeps"] == rs["substeps"], (f, hs, rs)
+        if visc:
+            assert hs["viscosity_iters"] == rs["viscosity_iters"] and rs["viscosity_iters"] > 0, (f, hs, rs)
+    d = h.device(num_properties=2)
+    assert abs(h.particle_count() - s.particle_count()) <= max(2, s.particle_count() // 500)
+    assert H.rel_l2(d.download("U"), s.grid("U")) < 1e-3
+    assert H.rel_l2(d.download("V"), s.grid("V")) < 1e-3
+    assert np.mean(d.download("MATERIAL") != s.grid("MATERIAL")) < 5e-3
+    h.close()
+    s.close()
+
+
+@pytest.mark.parametrize("sim,handling", [("smoke", "grid"), ("smoke", "particle"), ("fire", "particle"), ("fire", "grid")])
+def test_smoke_fire_frames_match_reference(ref_mod, scene_dir, sim, handling):
+    """BASELINE config 3 at test size: smoke with grid-advected temperature / soot (and the fire subclass)."""
+    scene = scenes.smoke_test(64, parameter_handling=handling, sim_type=sim)
+    path = scene_dir / ("hostgpu_%s_%s.json" % (sim, handling))
+    s = H.make_ref(ref_mod, scene, path)
+    h = host_api.Solver(str(path), convergence_threads=s.threads)
+    for _ in range(3):
+        s.step_frame()
+        h.step_frame()
+    d = h.device(num_properties=3 if sim == "smoke" else 4)
+    assert h.particle_count() == s.particle_count()
+    assert np.array_equal(d.download("MATERIAL"), s.grid("MATERIAL"))
+    assert H.rel_l2(d.download("U"), s.grid("U")) < 1e-3
+    assert H.rel_l2(d.download("TEMPERATURE"), s.grid("TEMPERATURE")) < 1e-3
+    assert H.rel_l2(d.download("CONCENTRATION"), s.grid("CONCENTRATION")) < 1e-3
+    h.close()
+    s.close()

@@ -250,3 +250,81 @@ def test_project_stage(pair):
     assert H.rel_l2(d.download("V"), s.grid("V")) < 1e-5
     assert np.array_equal(s.grid("U_VALID"), d.download("U_VALID"))
     d.close()
+
+
+def _viscosity_cg_numpy(mat, mu, field, dt, rho):
+    """numpy restatement of the system Eigen::ConjugateGradient<.., Upper> sees (SURVEY appendix D) and of Eigen
+    3.4.0's conjugate_gradient loop; returns (solution / rho, iterations())."""
+    solid = (mat & 0x20) != 0
+    mu = mu.astype(np.float64)
+    d = np.where(solid, 1.0, 1.0 + 4.0 * (mu * dt))
+
+    def upper(n_solid, n_mu, m_solid, m_mu):
+        return np.where(~n_solid, n_mu * dt, np.where(~m_solid, m_mu * dt, 0.0))
+
+    ej = upper(solid[:, :-1], mu[:, :-1], solid[:, 1:], mu[:, 1:])
+    ei = upper(solid[:-1, :], mu[:-1, :], solid[1:, :], mu[1:, :])
+
+    def apply(v):
+        y = d * v
+        y[:, :-1] += ej * v[:, 1:]
+        y[:, 1:] += ej * v[:, :-1]
+        y[:-1, :] += ei * v[1:, :]
+        y[1:, :] += ei * v[:-1, :]
+        return y
+
+    b = (np.float32(rho) * field.astype(np.float32)).astype(np.float64)
+    x = np.zeros_like(b)
+    r = b.copy()
+    n2 = float((b * b).sum())
+    if n2 == 0.0:
+        return x, 0
+    thr = max(1e-4 * 1e-4 * n2, np.finfo(np.float64).tiny)
+    p = r / d
+    abs_new = float((r * p).sum())
+    it = 0
+    while it < 2 * b.size:
+        t = apply(p)
+        alpha = abs_new / float((p * t).sum())
+        x += alpha * p
+        r -= alpha * t
+        if float((r * r).sum()) < thr:
+            break
+        z = r / d
+        abs_old, abs_new = abs_new, float((r * z).sum())
+        p = z + (abs_new / abs_old) * p
+        it += 1
+    return x / np.float64(np.float32(rho)), it
+
+
+@pytest.mark.parametrize("sim,res,frames", [("flip", 64, 3), ("nbflip", 64, 2), ("flip", 96, 1)])
+def test_viscosity_stage(ref_mod, scene_dir, sim, res, frames):
+    """LightViscosityModel::apply (viscositymodel.cpp:4-162) = Eigen 3.4.0 Jacobi-CG on the matrix getMatrix assembles.
+    Eigen is not in the reference tree: the oracle runs the reference's own assembly against oracle/shim/Eigen, which
+    restates Eigen's conjugate_gradient (parity unpinned). Velocities to the rounding of the
+    regrouped dot products against the oracle; iteration count against the numpy restatement of the same system (the
+    reference only keeps the per-frame maximum, flipsolver2d.h:125-128)."""
+    scene = scenes.dam_break(res, sim, viscosity_enabled=True, fluid_viscosity=10)
+    scene["settings"]["density"] = 0.02
+    s, d = _pair(ref_mod, scene_dir, scene, "visc_%s_%d_f%d" % (sim, res, frames), frames, dt=1.0 / 120.0)
+    H.sync_state(s, d, sim)
+    I, J = s.I, s.J
+    p = s.params()
+    u0, v0 = s.grid("U").copy(), s.grid("V").copy()
+    mat, mu = s.grid("MATERIAL").reshape(I, J), s.grid("VISCOSITY").reshape(I, J)
+    dt32 = float(np.float32(p["stepDt"]))
+    _, it_u = _viscosity_cg_numpy(mat, mu, u0[:I * J].reshape(I, J), dt32, p["fluidDensity"])
+    xv, it_v = _viscosity_cg_numpy(mat, mu, v0.reshape(I, J + 1)[:, :J], dt32, p["fluidDensity"])
+    s.stage("VISCOSITY")
+    it_dev = d.stage_iters("apply_viscosity")
+    assert it_dev == it_v and it_v > 0, (it_dev, it_u, it_v)  # apply() returns the V solve's iterations()
+    ur, vr = s.grid("U"), s.grid("V")
+    ud, vd = d.download("U"), d.download("V")
+    assert H.rel_l2(ur, u0) > 1e-3  # the stage really changes the field
+    assert H.rel_l2(ud, ur) < 1e-6, H.rel_l2(ud, ur)
+    assert H.rel_l2(vd, vr) < 1e-6, H.rel_l2(vd, vr)
+    assert H.rel_l2(vd.reshape(I, J + 1)[:, :J], xv) < 1e-6
+    assert np.array_equal(ud[I * J:], u0[I * J:])          # U's last row is not part of the system
+    assert np.array_equal(vd.reshape(I, J + 1)[:, J], v0.reshape(I, J + 1)[:, J])  # nor V's last column
+    d.close()
+    s.close()
