@@ -748,9 +748,82 @@ int particlesRebin(Ctx *ctx)
     return particlesSort(ctx);
 }
 
+// FlipFireSolver::combustionUpdate (flipfiresolver.cpp:35-106), run after particleUpdate (:149-153). Above the ignition
+// temperature a particle (PARTICLE mode) or a cell (GRID / HYBRID mode) burns min(dt * burnRate, fuel) and turns it into
+// soot and heat. particleCombustionUpdateThread ignores the range it is handed and walks every bin (:58-86), so the
+// reference burns every particle once per ThreadPool range, i.e. T times per substep for a pool of T threads;
+// `repeats` reproduces that (convergence_threads = T; 1 when the knob is 0).
+__global__ void __launch_bounds__(NT) particleCombustionKernel(float *__restrict__ temperature, float *__restrict__ concentration,
+                                                               float *__restrict__ fuel, int64_t count, float ignition, float burn,
+                                                               float smokeProportion, float heatProportion, int repeats)
+{
+    const int64_t p = blockIdx.x * static_cast<int64_t>(NT) + threadIdx.x;
+    if (p >= count) return;
+    float t = temperature[p], c = concentration[p], f = fuel[p];
+    for (int k = 0; k < repeats; k++)
+    {
+        if (t > ignition && f > 0.f)
+        {
+            const float burnt = fminf(burn, f);
+            f = __fsub_rn(f, burnt);
+            c = __fadd_rn(c, __fmul_rn(smokeProportion, burnt));
+            t = __fadd_rn(t, __fmul_rn(heatProportion, burnt));
+        }
+    }
+    temperature[p] = t;
+    concentration[p] = c;
+    fuel[p] = f;
+}
+
+__global__ void __launch_bounds__(NT) gridCombustionKernel(float *__restrict__ temperature, float *__restrict__ concentration,
+                                                           float *__restrict__ fuel, float *__restrict__ testGrid, int64_t n,
+                                                           float ignition, float burn, float smokeProportion, float heatProportion)
+{
+    const int64_t k = blockIdx.x * static_cast<int64_t>(NT) + threadIdx.x;
+    if (k >= n) return;
+    const float t = temperature[k], f = fuel[k];
+    if (t > ignition && f > 0.f)
+    {
+        const float burnt = fminf(burn, f);
+        const float left = __fsub_rn(f, burnt);
+        fuel[k] = left;
+        testGrid[k] = left;
+        concentration[k] = __fadd_rn(concentration[k], __fmul_rn(smokeProportion, burnt));
+        temperature[k] = __fadd_rn(t, __fmul_rn(heatProportion, burnt));
+    }
+}
+
+static int combustionUpdate(Ctx *ctx)
+{
+    const float burn = ctx->stepDt * ctx->p.burn_rate;  // m_stepDt * m_burnRate (float)
+    if (ctx->p.parameter_handling == FS2D_PARAMS_PARTICLE)
+    {
+        if (ctx->count == 0) return FS2D_OK;
+        if (ctx->p.temperature_property < 0 || ctx->p.concentration_property < 0 || ctx->p.fuel_property < 0)
+        {
+            ctx->lastError = "fire: temperature / concentration / fuel property columns are not set";
+            return FS2D_ERR_STATE;
+        }
+        ParticleBuffers &b = ctx->pb[ctx->cur];
+        particleCombustionKernel<<<gridFor(ctx->count), NT, 0, ctx->stream>>>(
+            b.props + ctx->p.temperature_property * b.capacity, b.props + ctx->p.concentration_property * b.capacity,
+            b.props + ctx->p.fuel_property * b.capacity, ctx->count, ctx->p.ignition_temperature, burn, ctx->p.smoke_proportion,
+            ctx->p.heat_proportion, std::max(1, ctx->p.convergence_threads));
+    }
+    else
+    {
+        gridCombustionKernel<<<gridFor(ctx->N), NT, 0, ctx->stream>>>(ctx->temperature, ctx->concentration, ctx->fuel, ctx->testGrid, ctx->N,
+                                                                      ctx->p.ignition_temperature, burn, ctx->p.smoke_proportion,
+                                                                      ctx->p.heat_proportion);
+    }
+    ctx->launches++;
+    FS2D_CUDA(cudaGetLastError());
+    return FS2D_OK;
+}
+
 int particlesUpdate(Ctx *ctx)
 {
-    if (ctx->count == 0) return FS2D_OK;
+    if (ctx->count == 0) return ctx->p.sim_type == FS2D_SIM_FIRE ? combustionUpdate(ctx) : FS2D_OK;
     const bool smoke = ctx->p.sim_type == FS2D_SIM_SMOKE || ctx->p.sim_type == FS2D_SIM_FIRE;
     ParticleBuffers &b = ctx->pb[ctx->cur];
     float *t = nullptr, *c = nullptr;
@@ -769,6 +842,7 @@ int particlesUpdate(Ctx *ctx)
         ownedRows(ctx));
     ctx->launches++;
     FS2D_CUDA(cudaGetLastError());
+    if (ctx->p.sim_type == FS2D_SIM_FIRE) FS2D_TRY(combustionUpdate(ctx));
     return FS2D_OK;
 }
 

@@ -115,5 +115,11 @@ def test_smoke_fire_frames_match_reference(ref_mod, scene_dir, sim, handling):
     assert H.rel_l2(d.download("U"), s.grid("U")) < 1e-3
     assert H.rel_l2(d.download("TEMPERATURE"), s.grid("TEMPERATURE")) < 1e-3
     assert H.rel_l2(d.download("CONCENTRATION"), s.grid("CONCENTRATION")) < 1e-3
+    if sim == "fire":
+        # FlipFireSolver::combustionUpdate (flipfiresolver.cpp:35-106): fuel burnt into soot and heat
+        assert H.rel_l2(d.download("FUEL"), s.grid("FUEL")) < 1e-3
+        pr = s.particles()[2]
+        pd = d.download_particles()[2]
+        assert abs(float(pr[3].sum()) - float(pd[3].sum())) <= 1e-3 * max(1.0, abs(float(pr[3].sum())))  # fuel column
     h.close()
     s.close()
