@@ -89,7 +89,7 @@ def measured_peak():
 def ncu_traffic():
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "pcg_traffic.json")))["k1_dram_bytes_per_launch"]
+        return json.load(open(os.path.join(ROOT, "profiles", "pcg_traffic.json")))["solve_dram_bytes_per_launch"]
     except Exception:
         return None
 
@@ -256,6 +256,7 @@ def run_ours(args, rank, world, local_rank):
     clocks = sampler.summary()
     launches = total(solver.kernel_launches() - launches0)
     prof_ms, prof_n = dev.pcg_profile_read()
+    solve_ms, solve_n = dev.pcg_profile_solves()
     dev.pcg_profile(False)
     stats = solver.stats()
     particles = solver.particle_count()          # this rank's
@@ -270,6 +271,7 @@ def run_ours(args, rank, world, local_rank):
     dev.pcg_profile(True)
     dense_ms = timed(solver.step_substep, args.steps)
     dprof_ms, dprof_n = dev.pcg_profile_read()
+    dsolve_ms, dsolve_n = dev.pcg_profile_solves()
     dev.pcg_profile(False)
     dev.pcg_set_dense(False)
     solver.step_substep()
@@ -312,35 +314,46 @@ def run_ours(args, rank, world, local_rank):
 
     if rank != 0:
         return
-    # ---- roofline of the PCG iteration kernels (K1: s = z + beta s, x += alpha s, q = A s, q.s; K2: r -= alpha q,
-    # z = M r, z.r, max|r|). Algorithmic bytes per cell: K1 = R z,s,x + W s,q,x (6 fp64 passes) + 1 B row info = 49;
-    # K2 = R r,q + W r,z (4 fp64 passes) + 2 B preconditioner info = 34.
+    # ---- roofline of the dominant kernel, pcgSolveKernel: ONE cooperative launch per PCG solve runs all iterations
+    # (two solves per substep: density correction + pressure projection). Per iteration and cell it moves, in its K1
+    # phase (s = z + beta s, x += alpha s, q = A s, q.s) R z,s,x + W s,q,x + 1 B row info = 49 B and in its K2 phase
+    # (r -= alpha q, z = M r, z.r, max|r|) R r,q + W r,z + 2 B preconditioner info = 34 B: 83 B.
+    # Launch durations come from CUDA events around every launch on the solver's stream (fs2d_pcg_profile_solves);
+    # the K1 / K2 split of a launch from the kernel's own phase clocks (%globaltimer in CTA 0).
     peak, peak_src = measured_peak()
 
-    def kernel_roofline(p_ms, p_n, cells):
+    def solve_roofline(p_ms, p_n, s_ms, s_n, cells):
+        launches = max(int(s_n), 1)
+        iters = int(p_n[0]) / launches
+        launch_ms = s_ms / launches
+        bytes_per_launch = 83.0 * cells * iters
         k1_ms = p_ms[0] / max(int(p_n[0]), 1)
         k2_ms = p_ms[1] / max(int(p_n[1]), 1)
-        k1_bytes, k2_bytes = 49 * cells, 34 * cells
-        return {"cells_per_launch": int(cells),
-                "k1": {"kernel": "pcgPipeKernel<K1>", "bytes_per_launch": k1_bytes, "avg_launch_ms": k1_ms,
-                       "launches_timed": int(p_n[0]), "achieved": k1_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else 0.0},
-                "k2": {"kernel": "pcgPipeKernel<K2>", "bytes_per_launch": k2_bytes, "avg_launch_ms": k2_ms,
-                       "launches_timed": int(p_n[1]), "achieved": k2_bytes / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else 0.0}}
+        return {"cells_per_launch": int(cells), "iterations_per_launch": iters, "bytes_per_launch": bytes_per_launch,
+                "avg_launch_ms": launch_ms, "launches_timed": int(s_n),
+                "achieved": bytes_per_launch / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else 0.0,
+                "k1_phase": {"bytes_per_iteration": 49 * cells, "avg_ms": k1_ms,
+                             "achieved": 49 * cells / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else 0.0},
+                "k2_phase": {"bytes_per_iteration": 34 * cells, "avg_ms": k2_ms,
+                             "achieved": 34 * cells / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else 0.0}}
 
-    dense = kernel_roofline(dprof_ms, dprof_n, own_cells)
-    act = kernel_roofline(prof_ms, prof_n, active_cells)
-    roofline = {"bound": "hbm", "kernel": "pcgPipeKernel<K1>", "achieved": dense["k1"]["achieved"], "peak": peak, "unit": "GB/s",
-                "frac": dense["k1"]["achieved"] / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
-                "bytes_per_launch": dense["k1"]["bytes_per_launch"], "avg_launch_ms": dense["k1"]["avg_launch_ms"],
-                "launches_timed": dense["k1"]["launches_timed"],
+    dense = solve_roofline(dprof_ms, dprof_n, dsolve_ms, dsolve_n, own_cells)
+    act = solve_roofline(prof_ms, prof_n, solve_ms, solve_n, active_cells)
+    for r in (dense, act):
+        for k in ("k1_phase", "k2_phase"):
+            r[k]["frac"] = r[k]["achieved"] / peak
+    roofline = {"bound": "hbm", "kernel": "pcgSolveKernel", "achieved": dense["achieved"], "peak": peak, "unit": "GB/s",
+                "frac": dense["achieved"] / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                "bytes_per_launch": dense["bytes_per_launch"], "avg_launch_ms": dense["avg_launch_ms"],
+                "launches_timed": dense["launches_timed"], "iterations_per_launch": dense["iterations_per_launch"],
+                "k1_phase": dense["k1_phase"], "k2_phase": dense["k2_phase"],
                 "measured_in": "second timed region of this run: the same %d substeps with fs2d_pcg_set_dense(1), i.e. the "
-                               "kernels walk all %d cells%s and every vector pass comes from HBM" %
-                               (args.steps, own_cells, " of rank 0's slab (launch time includes waiting for the peers' "
-                                "reduction partials and halo rows, which ride on these kernels)" if world > 1 else ""),
-                "k2": dict(dense["k2"], frac=dense["k2"]["achieved"] / peak),
-                "pcg_share_of_step": (dprof_ms[0] + dprof_ms[1]) / dense_ms if dense_ms > 0 else None,
+                               "kernel walks all %d cells%s and every vector pass comes from HBM" %
+                               (args.steps, own_cells, " of rank 0's slab (the launch includes the cross-GPU barriers that "
+                                "carry the all-reduces and the halo rows)" if world > 1 else ""),
+                "pcg_share_of_step": dsolve_ms / dense_ms if dense_ms > 0 else None,
                 "dense_walk": {"value": args.steps / (dense_ms * 1e-3), "unit": UNIT, "ms_per_step": dense_ms / args.steps},
-                "active_tile_walk": dict(act, pcg_share_of_step=(prof_ms[0] + prof_ms[1]) / ms if ms > 0 else None,
+                "active_tile_walk": dict(act, pcg_share_of_step=solve_ms / ms if ms > 0 else None,
                                          note="default mode (timed region of `value`): tiles without matrix rows are skipped; "
                                               "the %d walked cells x 7 vectors fit the 126 MB L2, so these GB/s are not an HBM "
                                               "figure" % active_cells)}
@@ -356,7 +369,8 @@ def run_ours(args, rank, world, local_rank):
                              % (own_cells * 8 // 2 ** 20, " per rank" if world > 1 else ""),
                        "parallelism": "1 GPU" if world == 1 else
                        "%d row slabs of one scene, one rank per GPU; halo rows, particle migration and the PCG all-reduces "
-                       "go through peer-mapped memory (CUDA IPC over NVLink), fused into the iteration kernels" % world,
+                       "go through peer-mapped memory (CUDA IPC over NVLink); the all-reduces are the grid barriers of the whole-solve "
+                       "kernel; slab boundaries balanced by particles per tile row" % world,
                        "pcg_iterations_last_frame": {"pressure": stats["pressure_iters"], "density": stats["density_iters"]},
                        "pcg_walk": "active tiles (%d of %d cells)" % (active_cells_all, N),
                        "stage_ms_per_substep_last_frame": stage_ms},
