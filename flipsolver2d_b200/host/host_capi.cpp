@@ -54,6 +54,15 @@ int fs2dh_slab_connect(fs2dh_solver s, int peer_rank, const void *blob)
     return guarded(h, [&]() { h->solver->slabConnect(peer_rank, blob); });
 }
 
+int fs2dh_slab_bounds(fs2dh_solver s, int world, int32_t *row_bounds)
+{
+    Holder *h = static_cast<Holder *>(s);
+    return guarded(h, [&]() {
+        const std::vector<int32_t> b = h->solver->slabBounds(world);
+        for (size_t k = 0; k < b.size(); k++) row_bounds[k] = b[k];
+    });
+}
+
 int64_t fs2dh_global_particle_count(fs2dh_solver s)
 {
     Holder *h = static_cast<Holder *>(s);

@@ -38,6 +38,7 @@ def lib():
         "fs2dh_slab_export": (i32, [vp, vp]),
         "fs2dh_slab_connect": (i32, [vp, i32, vp]),
         "fs2dh_global_particle_count": (i64, [vp]),
+        "fs2dh_slab_bounds": (i32, [vp, i32, vp]),
         "fs2dh_load_scene": (vp, [C.c_char_p]),
         "fs2dh_destroy": (None, [vp]),
         "fs2dh_last_error": (C.c_char_p, [vp]),
@@ -120,6 +121,11 @@ class Solver:
     def slab_connect(self, peer_rank, blob):
         buf = C.create_string_buffer(bytes(blob), capi.SLAB_HANDLE_BYTES)
         self._ck(self.L.fs2dh_slab_connect(self.h, int(peer_rank), C.cast(buf, C.c_void_p)), "slab_connect")
+
+    def slab_bounds(self, world):
+        out = np.zeros(world + 1, np.int32)
+        self._ck(self.L.fs2dh_slab_bounds(self.h, int(world), _p(out)), "slab_bounds")
+        return out
 
     def global_particle_count(self):
         n = int(self.L.fs2dh_global_particle_count(self.h))

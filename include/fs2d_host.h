@@ -29,6 +29,9 @@ void fs2dh_set_slab(int rank, int world, int device_share);
 int fs2dh_slab_export(fs2dh_solver s, void *blob);
 int fs2dh_slab_connect(fs2dh_solver s, int peer_rank, const void *blob);
 int64_t fs2dh_global_particle_count(fs2dh_solver s);
+/* The slab boundaries the solver would use for `world` ranks (world + 1 rows, balanced by seed particles per
+ * 16-row tile row; host only, no GPU needed). Every rank computes the same table from the same scene. */
+int fs2dh_slab_bounds(fs2dh_solver s, int world, int32_t *row_bounds);
 
 fs2dh_solver fs2dh_load_scene(const char *json_path); /* JsonSceneReader::loadJson; NULL on failure */
 void fs2dh_destroy(fs2dh_solver s);
