@@ -205,6 +205,9 @@ struct fs2d_context
     int *tileFlags = nullptr, *activeTiles = nullptr, *activeCount = nullptr;
     bool forceTileKernels = std::getenv("FS2D_PCG_TILE") != nullptr;  // A/B switch: plain tiled kernels
     bool stepwisePcg = std::getenv("FS2D_PCG_STEPWISE") != nullptr;  // A/B switch: two kernels per iteration instead of the whole-solve kernel
+    bool rowCopyPcg = std::getenv("FS2D_PCG_ROWCOPY") != nullptr;    // A/B switch: per-row bulk copies instead of tensor copies
+    void *solveMaps = nullptr;            // host copy of the tensor maps of the Krylov vectors (pcg.cu)
+    bool solveMapsTried = false, solveMapsOk = false;
     bool profilePcg = false;
     double profSolveMs = 0.0;             // whole-solve kernel: accumulated launch durations and their number
     int64_t profSolves = 0;

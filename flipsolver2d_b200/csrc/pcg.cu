@@ -19,6 +19,8 @@
 // operators never re-read HBM. Vectors stay fp64 like the reference's std::vector<double>
 // (linearsolver.h:15-20); arithmetic uses explicit non-contracted mul/add in the reference's
 // evaluation order so a single operator application is bit-identical to the strict oracle.
+#include <cuda.h>
+
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -147,6 +149,11 @@ __device__ __forceinline__ unsigned long long globalTimerNs()
 __device__ __forceinline__ void mgStamp(const MgArgs *m, int point)
 {
     if (m && m->timeline) m->timeline[(m->phase & 1023) * 8 + point] = globalTimerNs();
+}
+
+__device__ __forceinline__ void mgStampAt(const MgArgs &m, int phase, int point)
+{
+    if (m.timeline) m.timeline[(phase & 1023) * 8 + point] = globalTimerNs();
 }
 
 struct MgScalars
@@ -447,12 +454,13 @@ template <int MODE> __global__ void __launch_bounds__(NT) pcgTileKernel(PcgArgs 
 constexpr int PSW = TC + 4;               // staged row: 2 pad + TC + 2 pad doubles (1056 B)
 constexpr int PROWS = TR + 2;
 constexpr int PTILE = PROWS * PSW;        // 2376 doubles per staged array
+constexpr int PTILE_PAD = (PTILE + 15) / 16 * 16;  // arrays padded to 128 bytes: tensor copies need 128-byte aligned targets
 constexpr int PSTAGES = 2;
 
 template <int MODE> struct PipeStage
 {
-    double a[PTILE];                      // K1: z -> s_new (in place)    K2: r -> r_new (in place)
-    double b[PTILE];                      // K1: s_old                    K2: q
+    double a[PTILE_PAD];                  // K1: z -> s_new (in place)    K2: r -> r_new (in place)
+    double b[PTILE_PAD];                  // K1: s_old                    K2: q
     double x[MODE == MODE_K1 ? TR * TC : 2];  // K1: x tile
 };
 
@@ -905,6 +913,39 @@ __device__ __forceinline__ void blockReduce2(double &s, double &m, double *scrat
     }
 }
 
+// Tensor maps of the Krylov vectors seen as I x J matrices of doubles: one cp.async.bulk.tensor.2d (SASS UTMALDG)
+// brings a whole halo-extended tile -- 18 rows of 132 doubles -- instead of 18 row copies, and out-of-range rows /
+// columns arrive as zeros. (The row copies of pcgPipeKernel cost ~50 TMA instructions per tile; at 2 us per tile and
+// SM that instruction stream is what bounded the K2 phase and the start of every phase.)
+enum { TM_Z = 0, TM_Q, TM_S0, TM_S1, TM_R0, TM_R1, TM_X, TM_COUNT };
+
+struct SolveMaps
+{
+    CUtensorMap m[TM_COUNT];
+};
+
+__device__ __forceinline__ void tmaLoad2D(void *dstSmem, const CUtensorMap *map, int col, int row, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smemAddr(dstSmem)),
+                 "l"(reinterpret_cast<unsigned long long>(map)), "r"(smemAddr(bar)), "r"(col), "r"(row)
+                 : "memory");
+}
+
+// One thread fetches one tile: the two halo-extended input boxes (and the x tile in K1).
+template <int MODE>
+__device__ __forceinline__ void pipeIssueT(PipeStage<MODE> &st, unsigned long long *bar, const CUtensorMap *in0, const CUtensorMap *in1,
+                                          const CUtensorMap *xm, int tilesJ, int tile)
+{
+    const int ti = tile / tilesJ, tj = tile - ti * tilesJ;
+    const int i0 = ti * TR, j0 = tj * TC;
+    constexpr unsigned int boxBytes = PTILE * 8u, xBytes = TR * TC * 8u;
+    mbarArriveExpectTx(bar, 2u * boxBytes + (MODE == MODE_K1 ? xBytes : 0u));
+    tmaLoad2D(st.a, in0, j0 - 2, i0 - 1, bar);
+    tmaLoad2D(st.b, in1, j0 - 2, i0 - 1, bar);
+    if (MODE == MODE_K1) tmaLoad2D(st.x, xm, j0, i0, bar);
+}
+
 struct SolveSmem
 {
     PipeStage<MODE_K1> st[PSTAGES];       // phase B views each stage as a (smaller) PipeStage<MODE_K2>
@@ -932,17 +973,29 @@ __device__ __forceinline__ void pipeWalk(PipeStage<MODE> *st0, PipeStage<MODE> *
                                          const PcgArgs &a, const MgArgs &mg, const double *__restrict__ in0,
                                          const double *__restrict__ in1, double *__restrict__ out0, double *__restrict__ out1,
                                          double *__restrict__ xv, double *loOut1, double *hiOut1, double coef, double alphaPrev,
-                                         int numTiles, unsigned int &use0, unsigned int &use1, double &accDot, double &accMax)
+                                         int numTiles, unsigned int &use0, unsigned int &use1, double &accDot, double &accMax,
+                                         int phase = 0, const CUtensorMap *tm0 = nullptr, const CUtensorMap *tm1 = nullptr,
+                                         const CUtensorMap *tmx = nullptr)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long J = a.J;
+    if (blockIdx.x == 0 && tid == 0) mgStampAt(mg, phase, 0);
     int myTiles = (numTiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
     if (myTiles < 0) myTiles = 0;
     auto tileAt = [&](int k) -> int {
         const int t = blockIdx.x + k * gridDim.x;
         return a.activeTiles ? a.activeTiles[t] : (MG ? mg.tileBase + t : t);
     };
-    if (warp == 0 && myTiles > 0) pipeIssueV<MODE>(*st0, &full[0], a, in0, in1, xv, tileAt(0), lane);
+    const bool tensor = tm0 != nullptr;
+    if (myTiles > 0)
+    {
+        if (tensor)
+        {
+            if (tid == 0) pipeIssueT<MODE>(*st0, &full[0], tm0, tm1, tmx, a.tilesJ, tileAt(0));
+        }
+        else if (warp == 0)
+            pipeIssueV<MODE>(*st0, &full[0], a, in0, in1, xv, tileAt(0), lane);
+    }
     const int bc = tid % TC, rg = tid / TC;
     for (int k = 0; k < myTiles; k++)
     {
@@ -953,11 +1006,38 @@ __device__ __forceinline__ void pipeWalk(PipeStage<MODE> *st0, PipeStage<MODE> *
         else
             use0++;
         const int tile = tileAt(k);
-        if (warp == 0 && k + 1 < myTiles) pipeIssueV<MODE>(s ? *st0 : *st1, &full[s ^ 1], a, in0, in1, xv, tileAt(k + 1), lane);
+        if (k + 1 < myTiles)
+        {
+            if (tensor)
+            {
+                if (tid == 0) pipeIssueT<MODE>(s ? *st0 : *st1, &full[s ^ 1], tm0, tm1, tmx, a.tilesJ, tileAt(k + 1));
+            }
+            else if (warp == 0)
+                pipeIssueV<MODE>(s ? *st0 : *st1, &full[s ^ 1], a, in0, in1, xv, tileAt(k + 1), lane);
+        }
         const int ti = tile / a.tilesJ, tj = tile - ti * a.tilesJ;
         const int i0 = ti * TR, j0 = tj * TC;
         PipeStage<MODE> &st = s ? *st1 : *st0;
         const long long gj = j0 + bc;
+        // Tensor copies zero-fill what lies outside the I x J matrix; the reference's operators address the j = -1 /
+        // j = J neighbours by LINEAR index, i.e. the last / first element of the adjacent row (pressuredata.h:135-145).
+        // Threads 0..15 (left edge tiles) and 16..31 (right edge tiles) fetch those values while the tile is in flight.
+        const bool leftEdge = tensor && tj == 0, rightEdge = tensor && j0 + TC >= a.J;
+        double wrapA = 0.0, wrapB = 0.0;
+        int wrapAt = -1;
+        if ((leftEdge && tid < TR) || (rightEdge && tid >= TR && tid < 2 * TR))
+        {
+            const int ar = 1 + (tid & (TR - 1));
+            const long long gi = i0 - 1 + ar;
+            const bool left = tid < TR;
+            const long long n = left ? gi * J - 1 : gi * J + J;
+            wrapAt = ar * PSW + (left ? 1 : static_cast<int>(J - j0) + 2);
+            if (n >= 0 && n < a.N && gi < a.I)
+            {
+                wrapA = in0[n];
+                wrapB = in1[n];
+            }
+        }
         unsigned int info[TR / 2];
 #pragma unroll
         for (int q = 0; q < TR / 2; q++)
@@ -971,6 +1051,16 @@ __device__ __forceinline__ void pipeWalk(PipeStage<MODE> *st0, PipeStage<MODE> *
             }
         }
         mbarWait(&full[s], parity);
+        if (k == 0 && blockIdx.x == 0 && tid == 0) mgStampAt(mg, phase, 1);
+        if (leftEdge || rightEdge)
+        {
+            if (wrapAt >= 0)
+            {
+                st.a[wrapAt] = wrapA;
+                st.b[wrapAt] = wrapB;
+            }
+            __syncthreads();
+        }
         for (int e = tid; e < PTILE; e += NT)
         {
             const int ar = e / PSW, c = e - ar * PSW;
@@ -1035,6 +1125,7 @@ __device__ __forceinline__ bool solveBarrier(const SolveArgs &g, const MgArgs &m
 {
     const int tid = threadIdx.x;
     const unsigned int nb = gridDim.x;
+    if (blockIdx.x == 0 && tid == 0) mgStampAt(m, phase, 2);
     blockReduce2(v0, v1, sm.red);
     if (tid == 0)
     {
@@ -1045,10 +1136,12 @@ __device__ __forceinline__ bool solveBarrier(const SolveArgs &g, const MgArgs &m
         else
             __threadfence();
         sm.isLast = (atomicAdd(g.ticket, 1u) == (barrierIndex + 1u) * nb - 1u);
+        if (blockIdx.x == 0) mgStampAt(m, phase, 3);
     }
     __syncthreads();
     if (sm.isLast)
     {
+        if (tid == 0) mgStampAt(m, phase, 4);
         // fixed assignment of partials to threads, then the fixed block tree: deterministic, same order as finalReduce
         double ts = 0.0, tm = 0.0;
         for (unsigned int k = tid; k < nb; k += blockDim.x)
@@ -1064,6 +1157,7 @@ __device__ __forceinline__ bool solveBarrier(const SolveArgs &g, const MgArgs &m
         }
         __syncthreads();
         llPublish<MG>(m, phase, sm.pub[0], sm.pub[1]);
+        if (tid == 0) mgStampAt(m, phase, 5);
     }
     if (tid < 32)
     {
@@ -1080,10 +1174,12 @@ __device__ __forceinline__ bool solveBarrier(const SolveArgs &g, const MgArgs &m
     *sum = sm.bc[0];
     *mx = sm.bc[1];
     asm volatile("fence.proxy.async;" ::: "memory");  // what other CTAs / peers wrote is read by bulk copies next
+    if (blockIdx.x == 0 && tid == 0) mgStampAt(m, phase, 6);
     return sm.ok != 0;
 }
 
-template <bool MG> __global__ void __launch_bounds__(NT, 2) pcgSolveKernel(SolveArgs g, MgArgs mg)
+template <bool MG>
+__global__ void __launch_bounds__(NT, 2) pcgSolveKernel(SolveArgs g, MgArgs mg, const __grid_constant__ SolveMaps tm, int useTensor)
 {
     extern __shared__ __align__(128) unsigned char solveRaw[];
     SolveSmem &sm = *reinterpret_cast<SolveSmem *>(solveRaw);
@@ -1132,7 +1228,8 @@ template <bool MG> __global__ void __launch_bounds__(NT, 2) pcgSolveKernel(Solve
         // K1(i): s_i = z + beta s_{i-1}; x += alpha_{i-1} s_{i-1}; q = A s_i; gamma = q.s_i
         double accDot = 0.0, accMax = 0.0, unused = 0.0;
         pipeWalk<MODE_K1, MG>(a0, a1, sm.full, sm.preTbl, g.a, mg, g.z, g.s[i & 1], g.s[(i + 1) & 1], g.q, g.x, g.loQ, g.hiQ, beta,
-                              alphaPrev, numTiles, use0, use1, accDot, accMax);
+                              alphaPrev, numTiles, use0, use1, accDot, accMax, 2 * i + 1, useTensor ? &tm.m[TM_Z] : nullptr,
+                              &tm.m[TM_S0 + (i & 1)], &tm.m[TM_X]);
         if (!solveBarrier<MG>(g, mg, 2 * i + 1, bar++, accDot, 0.0, sm, &gamma, &unused)) break;
         alpha = sigma / (gamma + 1e-8);  // linearsolver.cpp:50
         if (scribe)
@@ -1145,7 +1242,8 @@ template <bool MG> __global__ void __launch_bounds__(NT, 2) pcgSolveKernel(Solve
         accDot = 0.0;
         accMax = 0.0;
         pipeWalk<MODE_K2, MG>(b0, b1, sm.full, sm.preTbl, g.a, mg, g.r[i & 1], g.q, g.r[(i + 1) & 1], g.z, nullptr, g.loZ, g.hiZ, alpha, 0.0,
-                              numTiles, use0, use1, accDot, accMax);
+                              numTiles, use0, use1, accDot, accMax, 2 * i + 2, useTensor ? &tm.m[TM_R0 + (i & 1)] : nullptr, &tm.m[TM_Q],
+                              nullptr);
         double sigmaNew = 0.0;
         if (!solveBarrier<MG>(g, mg, 2 * i + 2, bar++, accDot, accMax, sm, &sigmaNew, &err)) break;
         executed = i + 1;
@@ -1520,6 +1618,41 @@ void pcgPreloadSlabKernels()
     cudaGetLastError();
 }
 
+// Tensor maps for the whole-solve kernel, encoded once per handle (the vectors never move). The driver entry point is
+// fetched through the runtime, so the library still links against cudart only.
+static bool buildSolveMaps(Ctx *ctx, SolveMaps *out)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess)
+    {
+        cudaGetLastError();
+        return false;
+    }
+    EncodeFn encode = reinterpret_cast<EncodeFn>(fn);
+    double *vec[TM_COUNT] = {ctx->z, ctx->q, ctx->s[0], ctx->s[1], ctx->r[0], ctx->r[1], ctx->x};
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(ctx->J), static_cast<cuuint64_t>(ctx->I)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ctx->J) * sizeof(double)};
+    const cuuint32_t elem[2] = {1, 1};
+    const int promo = std::getenv("FS2D_PCG_L2PROMO") ? std::atoi(std::getenv("FS2D_PCG_L2PROMO")) : 256;
+    const CUtensorMapL2promotion l2promo = promo >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                           : promo >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                           : promo >= 64  ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                                          : CU_TENSOR_MAP_L2_PROMOTION_NONE;
+    for (int k = 0; k < TM_COUNT; k++)
+    {
+        const cuuint32_t box[2] = {static_cast<cuuint32_t>(k == TM_X ? TC : PSW), static_cast<cuuint32_t>(k == TM_X ? TR : PROWS)};
+        if (encode(&out->m[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, vec[k], dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, l2promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    return true;
+}
+
 int pcgTileBlocks(const Ctx *ctx) { return divUp(ctx->I, TR) * divUp(ctx->J, TC); }
 
 static bool pipeUsable(const Ctx *ctx) { return (ctx->J % 2) == 0 && !ctx->forceTileKernels; }
@@ -1587,6 +1720,14 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
         mg.mail = ctx->mail;
         mg.peerMail[0] = ctx->mail;
         mg.iterLimit = iterLimit;
+        static const int dbg1 = std::getenv("FS2D_MG_DEBUG") ? std::atoi(std::getenv("FS2D_MG_DEBUG")) : 0;
+        if (dbg1 & 8)
+        {
+            static unsigned long long *tl1 = nullptr;
+            if (!tl1) cudaMalloc(reinterpret_cast<void **>(&tl1), 1024 * 8 * sizeof(unsigned long long));
+            mg.timeline = tl1;
+            ctx->mgTimeline = tl1;
+        }
     }
     auto peerOf = [&](int r, double *p) -> double * {
         if (r < 0 || r >= ctx->slab.world) return nullptr;
@@ -1682,7 +1823,17 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
             FS2D_CUDA(cudaMemsetAsync(ctx->scalars->phaseNs, 0, 2 * sizeof(unsigned long long) + sizeof(unsigned int), st));
             cudaEventRecord(ctx->profEvents[0], st);
         }
-        void *args[] = {&g, &mg};
+        if (!ctx->solveMapsTried)
+        {
+            ctx->solveMapsTried = true;
+            ctx->solveMaps = std::malloc(sizeof(SolveMaps));
+            ctx->solveMapsOk = ctx->solveMaps && !ctx->rowCopyPcg && buildSolveMaps(ctx, static_cast<SolveMaps *>(ctx->solveMaps));
+        }
+        SolveMaps maps;
+        memset(&maps, 0, sizeof(maps));
+        int useTensor = ctx->solveMapsOk ? 1 : 0;
+        if (useTensor) maps = *static_cast<SolveMaps *>(ctx->solveMaps);
+        void *args[] = {&g, &mg, &maps, &useTensor};
         const size_t smem = sizeof(SolveSmem);
         if (mgOn)
         {

@@ -80,27 +80,28 @@ for dense in (True, False):
     t2 = time.perf_counter()
     out["noprof_" + ("dense" if dense else "active")] = {"host_enqueue_us_per_iter": 1e6 * (t1 - t0) / (200 * solves),
                                                          "total_us_per_iter": 1e6 * (t2 - t0) / (200 * solves)}
-if int(os.environ.get("FS2D_MG_DEBUG", "0")) & 8 and world > 1:
+if int(os.environ.get("FS2D_MG_DEBUG", "0")) & 8:
+    # whole-solve kernel timeline (CTA 0 + the last-arriving CTA, globaltimer ns): per phase
+    # 0 walk start, 1 first tile landed, 2 walk end, 3 CTA 0 arrived, 4 last CTA arrived, 5 published, 6 CTA 0 released
     import ctypes as C
     L = capi.lib()
+    L.fs2d_debug_mg_timeline.argtypes = [C.c_void_p, C.c_void_p]
     for dense in (True, False):
         d.pcg_set_dense(dense)
         d.pcg_solve_device(200, 0.0)
         d.synchronize()
         tl = np.zeros((1024, 8), np.uint64)
-        L.fs2d_debug_mg_timeline.argtypes = [C.c_void_p, C.c_void_p]
-        rc = L.fs2d_debug_mg_timeline(d.h, tl.ctypes.data_as(C.c_void_p))
-        t = tl[100:300].astype(np.int64)  # phases 100..299: K1 odd, K2 even
+        L.fs2d_debug_mg_timeline(d.h, tl.ctypes.data_as(C.c_void_p))
+        t = tl[101:301].astype(np.int64)  # phases 101..300: K1 odd, K2 even
         rows = {}
-        for name, sel in (("k1", t[1::2]), ("k2", t[0::2])):
-            nxt0 = np.roll(t[:, 0], -1)
-            rows[name] = {"prologue_us": float(np.mean(sel[:, 1] - sel[:, 0])) / 1e3,
-                          "body_block0_us": float(np.mean(sel[:, 2] - sel[:, 1])) / 1e3,
-                          "to_last_cta_us": float(np.mean(sel[:, 3] - sel[:, 2])) / 1e3,
-                          "final_reduce_us": float(np.mean(sel[:, 4] - sel[:, 3])) / 1e3,
-                          "publish_us": float(np.mean(sel[:, 5] - sel[:, 4])) / 1e3}
-        gaps = (t[1:, 0] - t[:-1, 5]) / 1e3   # end of publish -> first stamp of the next kernel
-        rows["gap_publish_to_next_start_us"] = float(np.mean(gaps))
+        for name, sel in (("k1", t[0::2]), ("k2", t[1::2])):
+            rows[name] = {"first_tile_us": float(np.mean(sel[:, 1] - sel[:, 0])) / 1e3,
+                          "walk_rest_us": float(np.mean(sel[:, 2] - sel[:, 1])) / 1e3,
+                          "cta0_reduce_arrive_us": float(np.mean(sel[:, 3] - sel[:, 2])) / 1e3,
+                          "wait_for_last_cta_us": float(np.mean(sel[:, 4] - sel[:, 3])) / 1e3,
+                          "final_reduce_publish_us": float(np.mean(sel[:, 5] - sel[:, 4])) / 1e3,
+                          "release_us": float(np.mean(sel[:, 6] - sel[:, 5])) / 1e3,
+                          "phase_us": float(np.mean(sel[:, 6] - sel[:, 0])) / 1e3}
         rows["phase_period_us"] = float(np.mean(np.diff(t[:, 0]))) / 1e3
         out["timeline_" + ("dense" if dense else "active")] = rows
 print(json.dumps(out), flush=True)
