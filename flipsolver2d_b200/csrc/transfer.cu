@@ -38,36 +38,47 @@ struct TileStage
 constexpr size_t STAGE_BYTES = sizeof(TileStage);  // 96 KB + row tables: dynamic shared memory, 2 CTAs per SM
 
 // Stage rows [i0-haloLo, i0+TI-1+haloHi] x columns [j0-haloLo, j0+TJ-1+haloHi] of the sorted
-// particle arrays. Returns false (for the whole CTA) when the records do not fit.
+// particle arrays. Returns (for the whole CTA) 1 = staged, 0 = the records do not fit (read them from global memory),
+// 2 = there is no particle at all in the tile and its halo.
 template <bool WITH_PAYLOAD2>
-__device__ bool stageTile(TileStage &s, const int32_t *__restrict__ cellStart, const float2 *__restrict__ pos,
+__device__ int stageTile(TileStage &s, const int32_t *__restrict__ cellStart, const float2 *__restrict__ pos,
                           const float2 *__restrict__ pay2, const float *__restrict__ pay1, const uint8_t *__restrict__ mis, int I,
                           int J, int i0, int j0, int haloLo, int haloHi)
 {
     const int rows = TI + haloLo + haloHi;
     __shared__ int total;
+    // one thread per staged row fetches its particle range (the loads run in parallel: with one CTA per 8 x 32 cells
+    // and 91 % of the tiles empty in a dam break, a serial walk over the row table dominated the whole kernel)
+    if (threadIdx.x < rows)
+    {
+        const int r = threadIdx.x;
+        const int ja = max(j0 - haloLo, 0), jb = min(j0 + TJ - 1 + haloHi, J - 1);
+        const int gi = i0 - haloLo + r;
+        int b = 0, e = 0;
+        if (gi >= 0 && gi < I && ja <= jb)
+        {
+            b = cellStart[static_cast<long long>(gi) * J + ja];
+            e = cellStart[static_cast<long long>(gi) * J + jb + 1];
+        }
+        s.rowBegin[r] = b;
+        s.rowOffset[r] = e - b;
+    }
+    __syncthreads();
     if (threadIdx.x == 0)
     {
         int acc = 0;
-        const int ja = max(j0 - haloLo, 0), jb = min(j0 + TJ - 1 + haloHi, J - 1);
         for (int r = 0; r < rows; r++)
         {
-            const int gi = i0 - haloLo + r;
-            int b = 0, e = 0;
-            if (gi >= 0 && gi < I && ja <= jb)
-            {
-                b = cellStart[static_cast<long long>(gi) * J + ja];
-                e = cellStart[static_cast<long long>(gi) * J + jb + 1];
-            }
-            s.rowBegin[r] = b;
+            const int c = s.rowOffset[r];
             s.rowOffset[r] = acc;
-            acc += e - b;
+            acc += c;
         }
         s.rowOffset[rows] = acc;
         total = acc;
     }
     __syncthreads();
-    if (total > STAGE) return false;
+    if (total == 0) return 2;  // nothing within reach of this tile: the callers write their "no particle" values
+    if (total > STAGE) return 0;
     for (int r = 0; r < rows; r++)
     {
         const int n = s.rowOffset[r + 1] - s.rowOffset[r];
@@ -83,7 +94,7 @@ __device__ bool stageTile(TileStage &s, const int32_t *__restrict__ cellStart, c
         }
     }
     __syncthreads();
-    return true;
+    return 1;
 }
 
 // Iterate the particles of cells [ja..jb] of row gi, staged or global. F(pos, payload).
@@ -133,7 +144,8 @@ __global__ void __launch_bounds__(NT) p2gVelocityKernel(const int32_t *__restric
     const int tile = tileBase + blockIdx.x;
     const int ti = tile / tilesJ, tj = tile - ti * tilesJ;
     const int i0 = ti * TI, j0 = tj * TJ;
-    const bool staged = stageTile<true>(s, cellStart, pos, vel, nullptr, mis, I, J, i0, j0, 1, 1);
+    const int stageMode = stageTile<true>(s, cellStart, pos, vel, nullptr, mis, I, J, i0, j0, 1, 1);
+    const bool staged = stageMode != 0, empty = stageMode == 2;
     const int li = threadIdx.x / TJ, lj = threadIdx.x - li * TJ;
     const int i = i0 + li, j = j0 + lj;
     if (i >= I || j >= J) return;
@@ -142,7 +154,7 @@ __global__ void __launch_bounds__(NT) p2gVelocityKernel(const int32_t *__restric
     float uW = 1e-10f, vW = 1e-10f, uAcc = 0.f, vAcc = 0.f;
     bool any = false;
     const int ja = max(j - 1, 0), jb = min(j + 1, J - 1);
-    for (int gi = max(i - 1, 0); gi <= min(i + 1, I - 1); gi++)
+    for (int gi = max(i - 1, 0); !empty && gi <= min(i + 1, I - 1); gi++)
     {
         forRowRange<true>(s, staged, cellStart, pos, vel, nullptr, mis, J, gi, ja, jb, gi - (i0 - 1), i, j,
                           [&](float2 p, float2 v)
@@ -180,7 +192,8 @@ __global__ void __launch_bounds__(NT) p2gCenteredKernel(const int32_t *__restric
     const int tile = tileBase + blockIdx.x;
     const int ti = tile / tilesJ, tj = tile - ti * tilesJ;
     const int i0 = ti * TI, j0 = tj * TJ;
-    const bool staged = stageTile<false>(s, cellStart, pos, nullptr, prop, mis, I, J, i0, j0, 2, 1);
+    const int stageMode = stageTile<false>(s, cellStart, pos, nullptr, prop, mis, I, J, i0, j0, 2, 1);
+    const bool staged = stageMode != 0, empty = stageMode == 2;
     const int li = threadIdx.x / TJ, lj = threadIdx.x - li * TJ;
     const int i = i0 + li, j = j0 + lj;
     if (i >= I || j >= J) return;
@@ -188,7 +201,7 @@ __global__ void __launch_bounds__(NT) p2gCenteredKernel(const int32_t *__restric
     float wSum = 1e-10f, acc = 0.f;
     bool any = false;
     const int ja = max(j - 2, 0), jb = min(j + 1, J - 1);
-    for (int gi = max(i - 2, 0); gi <= min(i + 1, I - 1); gi++)
+    for (int gi = max(i - 2, 0); !empty && gi <= min(i + 1, I - 1); gi++)
     {
         forRowRange<false>(s, staged, cellStart, pos, nullptr, prop, mis, J, gi, ja, jb, gi - (i0 - 2), i, j,
                            [&](float2 p, float2 v)
@@ -222,14 +235,15 @@ __global__ void __launch_bounds__(NT) densityKernel(const int32_t *__restrict__ 
     const int tile = tileBase + blockIdx.x;
     const int ti = tile / tilesJ, tj = tile - ti * tilesJ;
     const int i0 = ti * TI, j0 = tj * TJ;
-    const bool staged = stageTile<false>(s, cellStart, pos, nullptr, nullptr, mis, I, J, i0, j0, 1, 1);
+    const int stageMode = stageTile<false>(s, cellStart, pos, nullptr, nullptr, mis, I, J, i0, j0, 1, 1);
+    const bool staged = stageMode != 0, empty = stageMode == 2;
     const int li = threadIdx.x / TJ, lj = threadIdx.x - li * TJ;
     const int i = i0 + li, j = j0 + lj;
     if (i >= I || j >= J) return;
     const float ci = static_cast<float>(i), cj = static_cast<float>(j);
     float acc = 0.f;
     const int ja = max(j - 1, 0), jb = min(j + 1, J - 1);
-    for (int gi = max(i - 1, 0); gi <= min(i + 1, I - 1); gi++)
+    for (int gi = max(i - 1, 0); !empty && gi <= min(i + 1, I - 1); gi++)
     {
         forRowRange<false>(s, staged, cellStart, pos, nullptr, nullptr, mis, J, gi, ja, jb, gi - (i0 - 1), i, j,
                            [&](float2 p, float2)
@@ -257,13 +271,31 @@ __global__ void __launch_bounds__(256) sdfKernel(const int32_t *__restrict__ cel
                                                  float *__restrict__ sdf, long long nBegin, long long nEnd)
 {
     const long long n = nBegin + blockIdx.x * 256ll + threadIdx.x;
-    if (n >= nEnd) return;
-    const int i = static_cast<int>(n / J), j = static_cast<int>(n - static_cast<long long>(i) * J);
+    const bool valid = n < nEnd;
+    const long long nc = valid ? n : nEnd - 1;
+    const int i = static_cast<int>(nc / J), j = static_cast<int>(nc - static_cast<long long>(i) * J);
     const int bi = i / 3, bj = j / 3;
     const int iLo = max(3 * (bi - 2), 0), iHi = min(3 * (bi + 2) + 2, I - 1);
     const int jLo = max(3 * (bj - 2), 0), jHi = min(3 * (bj + 2) + 2, J - 1);
     const float cx = faddr(static_cast<float>(i), 0.5f), cy = faddr(static_cast<float>(j), 0.5f);
     float best = FLT_MAX;
+    {
+        // Most of the grid is far from any particle (91 % of the cells in the dam break). The warp counts, with one
+        // row per lane, the particles inside the union of its 32 search windows; when there is none every cell of the
+        // warp gets the "no particle" value without walking its own window.
+        const unsigned int all = 0xffffffffu;
+        const int wiLo = __reduce_min_sync(all, iLo), wiHi = __reduce_max_sync(all, iHi);
+        const int wjLo = __reduce_min_sync(all, jLo), wjHi = __reduce_max_sync(all, jHi);
+        int cnt = 0;
+        for (int gi = wiLo + static_cast<int>(threadIdx.x & 31u); gi <= wiHi; gi += 32)
+            cnt += cellStart[static_cast<long long>(gi) * J + wjHi + 1] - cellStart[static_cast<long long>(gi) * J + wjLo];
+        if (__reduce_add_sync(all, cnt) == 0)
+        {
+            if (valid) sdf[n] = fsubr(__fsqrt_rn(best), radius);
+            return;
+        }
+    }
+    if (!valid) return;
     const int reach = max(i - iLo, iHi - i);
     for (int d = 0; d <= reach; d++)
     {
