@@ -224,45 +224,61 @@ __global__ void __launch_bounds__(NT) bfsLayerKernel(float *U, float *V, uint8_t
     }
 }
 
-// extrapolateLevelsetInside / Outside (flipsolver2d.cpp:1433-1558): same BFS with unbounded radius and
-// -1 / +1 per layer. One cooperative launch walks all layers; only the bounding box of the unmarked
-// cells is swept. bbox = {iMin, iMax, jMin, jMax}, flags[3] rotate so that a flag is never reset while
-// another CTA may still read it.
-__global__ void __launch_bounds__(NT) sdfMarkKernel(const float *__restrict__ sdf, int32_t *__restrict__ marker, int I, int J,
-                                                    int inside, float maxSdf, int *__restrict__ bbox)
+// extrapolateLevelsetInside / Outside (flipsolver2d.cpp:1433-1558): same BFS with unbounded radius and -1 / +1 per
+// layer: a cell of layer k takes the mean (double) of its 8-neighbours in lower layers plus the step. Layers are
+// processed one after the other (their values depend on the previous layer) but each cell is visited ONCE: layer k is a
+// list of cells; processing a cell claims its still unmarked neighbours for layer k + 1 (atomicCAS on the marker) and
+// appends them to the list. One cooperative launch walks all layers with one grid-wide barrier per layer -- at 4096^2
+// the level set has thousands of layers; sweeping the bounding box of the unmarked cells once per layer, as the first
+// version did, cost 0.5 s per nbflip substep. The value of a cell does not depend on the order inside its layer
+// (SURVEY appendix A-9), so the arbitrary list order is harmless: results are bit-identical to the reference.
+// queue: one slot per cell; ctl[0] = tail (cells appended so far).
+__global__ void __launch_bounds__(NT) sdfMarkKernel(const float *__restrict__ sdf, int32_t *__restrict__ marker, long long N, int inside,
+                                                    float maxSdf)
 {
     const long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
-    if (n >= static_cast<long long>(I) * J) return;
+    if (n >= N) return;
     const float v = sdf[n];
     const bool known = inside ? (v > 0.f) : (v < maxSdf);
     marker[n] = known ? 0 : 0x7fffffff;
-    if (!known)
-    {
-        const int i = static_cast<int>(n / J), j = static_cast<int>(n - static_cast<long long>(i) * J);
-        atomicMin(bbox + 0, i);
-        atomicMax(bbox + 1, i);
-        atomicMin(bbox + 2, j);
-        atomicMax(bbox + 3, j);
-    }
 }
 
-__global__ void __launch_bounds__(NT) sdfExtrapolateKernel(float *sdf, int32_t *marker, int I, int J, float step,
-                                                           const int *__restrict__ bbox, int *flags)
+// layer 1: unmarked cells with a known 8-neighbour (flipsolver2d.cpp:1450-1468)
+__global__ void __launch_bounds__(NT) sdfFirstLayerKernel(int32_t *__restrict__ marker, int I, int J, int32_t *__restrict__ queue,
+                                                          unsigned int *__restrict__ ctl)
+{
+    const long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    if (n >= static_cast<long long>(I) * J) return;
+    if (marker[n] == 0) return;
+    const int i = static_cast<int>(n / J), j = static_cast<int>(n - static_cast<long long>(i) * J);
+    bool hit = false;
+#pragma unroll
+    for (int di = -1; di <= 1; di++)
+#pragma unroll
+        for (int dj = -1; dj <= 1; dj++)
+        {
+            const int ni = i + di, nj = j + dj;
+            if ((di == 0 && dj == 0) || ni < 0 || ni >= I || nj < 0 || nj >= J) continue;
+            if (marker[static_cast<long long>(ni) * J + nj] == 0) hit = true;
+        }
+    if (!hit) return;
+    // neighbours only test for == 0 in this kernel, so writing 1 here cannot change what another thread decides
+    marker[n] = 1;
+    queue[atomicAdd(ctl, 1u)] = static_cast<int32_t>(n);
+}
+
+__global__ void __launch_bounds__(NT) sdfExtrapolateKernel(float *sdf, int32_t *marker, int I, int J, float step, int32_t *queue,
+                                                           unsigned int *ctl)
 {
     cg::grid_group grid = cg::this_grid();
-    const int i0 = bbox[0], i1 = bbox[1], j0 = bbox[2], j1 = bbox[3];
-    if (i1 < i0) return;  // nothing unmarked (uniform across the grid)
-    const long long w = j1 - j0 + 1, cells = w * (i1 - i0 + 1);
-    const long long stride = static_cast<long long>(gridDim.x) * NT;
-    for (int k = 1;; k++)
+    const unsigned int stride = gridDim.x * NT;
+    unsigned int begin = 0, end = *reinterpret_cast<volatile unsigned int *>(ctl);
+    for (int k = 1; begin < end; k++)
     {
-        bool changed = false;
-        for (long long t = blockIdx.x * static_cast<long long>(NT) + threadIdx.x; t < cells; t += stride)
+        for (unsigned int t = begin + blockIdx.x * NT + threadIdx.x; t < end; t += stride)
         {
-            const int i = i0 + static_cast<int>(t / w), j = j0 + static_cast<int>(t % w);
-            const long long n = static_cast<long long>(i) * J + j;
-            if (marker[n] != 0x7fffffff) continue;
-            bool hit = false;
+            const long long n = queue[t];
+            const int i = static_cast<int>(n / J), j = static_cast<int>(n - static_cast<long long>(i) * J);
             double avg = 0.0;
             int cnt = 0;
 #pragma unroll
@@ -270,28 +286,32 @@ __global__ void __launch_bounds__(NT) sdfExtrapolateKernel(float *sdf, int32_t *
 #pragma unroll
                 for (int dj = -1; dj <= 1; dj++)
                 {
-                    if (di == 0 && dj == 0) continue;
                     const int ni = i + di, nj = j + dj;
-                    if (ni < 0 || ni >= I || nj < 0 || nj >= J) continue;
+                    if ((di == 0 && dj == 0) || ni < 0 || ni >= I || nj < 0 || nj >= J) continue;
                     const long long nn = static_cast<long long>(ni) * J + nj;
-                    const int m = marker[nn];
-                    if (m == k - 1) hit = true;
+                    int m = marker[nn];
+                    if (m == 0x7fffffff)
+                    {
+                        // claim the unmarked neighbour for the next layer; exactly one claimant appends it
+                        m = atomicCAS(marker + nn, 0x7fffffff, k + 1);
+                        if (m == 0x7fffffff)
+                        {
+                            queue[atomicAdd(ctl, 1u)] = static_cast<int32_t>(nn);
+                            m = k + 1;
+                        }
+                    }
                     if (m < k)
                     {
-                        avg += static_cast<double>(sdf[nn]);
+                        avg += static_cast<double>(sdf[nn]);  // a lower layer: final since the last barrier
                         cnt++;
                     }
                 }
-            if (!hit) continue;
             sdf[n] = static_cast<float>(avg / cnt + static_cast<double>(step));
-            marker[n] = k;
-            changed = true;
         }
-        if (changed) flags[k % 3] = 1;
-        if (blockIdx.x == 0 && threadIdx.x == 0) flags[(k + 1) % 3] = 0;
         __threadfence();
         grid.sync();
-        if (*reinterpret_cast<volatile int *>(flags + k % 3) == 0) break;
+        begin = end;
+        end = *reinterpret_cast<volatile unsigned int *>(ctl);
     }
 }
 
@@ -678,22 +698,28 @@ int gridExtrapolateSdfNow(Ctx *ctx, bool inside, bool wholeGridHeld)
 {
     if (!wholeGridHeld) FS2D_TRY(slabUnsupported(ctx, "extrapolateLevelset"));
     cudaStream_t st = ctx->stream;
-    int *bbox = reinterpret_cast<int *>(ctx->d_counter) + 8;  // 4 ints bbox + 3 ints flags
-    const int init[8] = {0x7fffffff, -1, 0x7fffffff, -1, 0, 0, 0, 0};
-    FS2D_CUDA(cudaMemcpyAsync(bbox, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    if (!ctx->bfsQueue)
+    {
+        FS2D_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->bfsQueue), sizeof(int32_t) * static_cast<size_t>(ctx->N)));
+        FS2D_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->bfsCtl), 64));
+    }
+    FS2D_CUDA(cudaMemsetAsync(ctx->bfsCtl, 0, 64, st));
     const float maxSdf = static_cast<float>(static_cast<size_t>(ctx->I) * static_cast<size_t>(ctx->J));
-    sdfMarkKernel<<<divUp(ctx->N, NT), NT, 0, st>>>(ctx->fluidSdf, ctx->markers, ctx->I, ctx->J, inside ? 1 : 0, maxSdf, bbox);
+    sdfMarkKernel<<<divUp(ctx->N, NT), NT, 0, st>>>(ctx->fluidSdf, ctx->markers, ctx->N, inside ? 1 : 0, maxSdf);
+    sdfFirstLayerKernel<<<divUp(ctx->N, NT), NT, 0, st>>>(ctx->markers, ctx->I, ctx->J, ctx->bfsQueue, ctx->bfsCtl);
+    // a modest grid: the frontier of a layer is a few thousand cells, and the barrier gets cheaper with fewer CTAs
     int perSm = 0;
     FS2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, sdfExtrapolateKernel, NT, 0));
-    const int blocks = ctx->smCount * std::max(perSm, 1);
+    const int blocks = ctx->smCount * std::min(std::max(perSm, 1), 2);
     float *sdf = ctx->fluidSdf;
     int32_t *markers = ctx->markers;
     int I = ctx->I, J = ctx->J;
     float step = inside ? -1.f : 1.f;
-    const int *cb = bbox;
-    int *flags = bbox + 4;
-    void *args[] = {&sdf, &markers, &I, &J, &step, &cb, &flags};
+    int32_t *queue = ctx->bfsQueue;
+    unsigned int *ctl = ctx->bfsCtl;
+    void *args[] = {&sdf, &markers, &I, &J, &step, &queue, &ctl};
     FS2D_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(sdfExtrapolateKernel), dim3(blocks), dim3(NT), args, 0, st));
+    ctx->launches++;
     ctx->launches += 2;
     return FS2D_OK;
 }
