@@ -485,6 +485,16 @@ __device__ __forceinline__ void mbarArriveExpectTx(unsigned long long *bar, unsi
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
 }
 
+__device__ __forceinline__ void mbarExpectTx(unsigned long long *bar, unsigned int bytes)  // more bytes expected, no arrival
+{
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbarArrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smemAddr(bar)) : "memory");
+}
+
 __device__ __forceinline__ void mbarWait(unsigned long long *bar, unsigned int parity)
 {
     asm volatile(
@@ -946,6 +956,31 @@ __device__ __forceinline__ void pipeIssueT(PipeStage<MODE> &st, unsigned long lo
     if (MODE == MODE_K1) tmaLoad2D(st.x, xm, j0, i0, bar);
 }
 
+// The first tile of a phase in two halves. EARLY (issued BEFORE the barrier that ends the previous phase, so that it
+// overlaps the barrier): the operands the previous phase did not write -- K1: s_old and x (written a whole iteration
+// ago), K2: r_old. LATE (after the barrier): the vector the previous phase produced -- K1: z, K2: q. The early half only
+// raises the transaction count; the single arrival of the stage comes with the late half.
+template <int MODE>
+__device__ __forceinline__ void pipeIssueEarly(PipeStage<MODE> &st, unsigned long long *bar, const CUtensorMap *early, const CUtensorMap *xm,
+                                              int tilesJ, int tile)
+{
+    const int ti = tile / tilesJ, tj = tile - ti * tilesJ;
+    const int i0 = ti * TR, j0 = tj * TC;
+    constexpr unsigned int boxBytes = PTILE * 8u, xBytes = TR * TC * 8u;
+    mbarExpectTx(bar, boxBytes + (MODE == MODE_K1 ? xBytes : 0u));
+    tmaLoad2D(MODE == MODE_K1 ? st.b : st.a, early, j0 - 2, i0 - 1, bar);
+    if (MODE == MODE_K1) tmaLoad2D(st.x, xm, j0, i0, bar);
+}
+
+template <int MODE>
+__device__ __forceinline__ void pipeIssueLate(PipeStage<MODE> &st, unsigned long long *bar, const CUtensorMap *late, int tilesJ, int tile)
+{
+    const int ti = tile / tilesJ, tj = tile - ti * tilesJ;
+    const int i0 = ti * TR, j0 = tj * TC;
+    mbarArriveExpectTx(bar, PTILE * 8u);
+    tmaLoad2D(MODE == MODE_K1 ? st.a : st.b, late, j0 - 2, i0 - 1, bar);
+}
+
 struct SolveSmem
 {
     PipeStage<MODE_K1> st[PSTAGES];       // phase B views each stage as a (smaller) PipeStage<MODE_K2>
@@ -975,7 +1010,7 @@ __device__ __forceinline__ void pipeWalk(PipeStage<MODE> *st0, PipeStage<MODE> *
                                          double *__restrict__ xv, double *loOut1, double *hiOut1, double coef, double alphaPrev,
                                          int numTiles, unsigned int &use0, unsigned int &use1, double &accDot, double &accMax,
                                          int phase = 0, const CUtensorMap *tm0 = nullptr, const CUtensorMap *tm1 = nullptr,
-                                         const CUtensorMap *tmx = nullptr)
+                                         const CUtensorMap *tmx = nullptr, bool earlyIssued = false)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long J = a.J;
@@ -991,7 +1026,13 @@ __device__ __forceinline__ void pipeWalk(PipeStage<MODE> *st0, PipeStage<MODE> *
     {
         if (tensor)
         {
-            if (tid == 0) pipeIssueT<MODE>(*st0, &full[0], tm0, tm1, tmx, a.tilesJ, tileAt(0));
+            if (tid == 0)
+            {
+                if (earlyIssued)
+                    pipeIssueLate<MODE>(*st0, &full[0], MODE == MODE_K1 ? tm0 : tm1, a.tilesJ, tileAt(0));
+                else
+                    pipeIssueT<MODE>(*st0, &full[0], tm0, tm1, tmx, a.tilesJ, tileAt(0));
+            }
         }
         else if (warp == 0)
             pipeIssueV<MODE>(*st0, &full[0], a, in0, in1, xv, tileAt(0), lane);
@@ -1223,13 +1264,20 @@ __global__ void __launch_bounds__(NT, 2) pcgSolveKernel(SolveArgs g, MgArgs mg, 
     double alpha = 0.0, beta = 0.0, alphaPrev = 0.0, gamma = 0.0, err = 0.0;
     int result = g.iterLimit, executed = 0;
     unsigned long long tA = 0, tB = 0, t0 = scribe ? globalTimerNs() : 0ull;
+    // first tile of this CTA (the one every walk starts with) and whether its early half is in flight
+    const bool hasTile = static_cast<int>(blockIdx.x) < numTiles;
+    const int firstTile = !hasTile ? 0 : (g.a.activeTiles ? g.a.activeTiles[blockIdx.x] : (MG ? mg.tileBase + static_cast<int>(blockIdx.x) : static_cast<int>(blockIdx.x)));
+    const bool canEarly = useTensor && hasTile;
+    bool early = false;
     for (int i = 0; i < g.iterLimit; i++)
     {
         // K1(i): s_i = z + beta s_{i-1}; x += alpha_{i-1} s_{i-1}; q = A s_i; gamma = q.s_i
         double accDot = 0.0, accMax = 0.0, unused = 0.0;
         pipeWalk<MODE_K1, MG>(a0, a1, sm.full, sm.preTbl, g.a, mg, g.z, g.s[i & 1], g.s[(i + 1) & 1], g.q, g.x, g.loQ, g.hiQ, beta,
                               alphaPrev, numTiles, use0, use1, accDot, accMax, 2 * i + 1, useTensor ? &tm.m[TM_Z] : nullptr,
-                              &tm.m[TM_S0 + (i & 1)], &tm.m[TM_X]);
+                              &tm.m[TM_S0 + (i & 1)], &tm.m[TM_X], early);
+        early = canEarly;  // r_old of K2(i) was written an iteration ago: fetch it while the barrier runs
+        if (early && tid == 0) pipeIssueEarly<MODE_K2>(*b0, &sm.full[0], &tm.m[TM_R0 + (i & 1)], nullptr, g.a.tilesJ, firstTile);
         if (!solveBarrier<MG>(g, mg, 2 * i + 1, bar++, accDot, 0.0, sm, &gamma, &unused)) break;
         alpha = sigma / (gamma + 1e-8);  // linearsolver.cpp:50
         if (scribe)
@@ -1243,7 +1291,10 @@ __global__ void __launch_bounds__(NT, 2) pcgSolveKernel(SolveArgs g, MgArgs mg, 
         accMax = 0.0;
         pipeWalk<MODE_K2, MG>(b0, b1, sm.full, sm.preTbl, g.a, mg, g.r[i & 1], g.q, g.r[(i + 1) & 1], g.z, nullptr, g.loZ, g.hiZ, alpha, 0.0,
                               numTiles, use0, use1, accDot, accMax, 2 * i + 2, useTensor ? &tm.m[TM_R0 + (i & 1)] : nullptr, &tm.m[TM_Q],
-                              nullptr);
+                              nullptr, early);
+        early = canEarly && i + 1 < g.iterLimit;  // s_old and x of K1(i+1), unless this was the last iteration
+        if (early && tid == 0)
+            pipeIssueEarly<MODE_K1>(*a0, &sm.full[0], &tm.m[TM_S0 + ((i + 1) & 1)], &tm.m[TM_X], g.a.tilesJ, firstTile);
         double sigmaNew = 0.0;
         if (!solveBarrier<MG>(g, mg, 2 * i + 2, bar++, accDot, accMax, sm, &sigmaNew, &err)) break;
         executed = i + 1;
@@ -1270,6 +1321,14 @@ __global__ void __launch_bounds__(NT, 2) pcgSolveKernel(SolveArgs g, MgArgs mg, 
         beta = betaNew;
         sigma = sigmaNew;
         alphaPrev = alpha;
+        if (i + 1 >= g.iterLimit) early = false;
+    }
+    if (early)
+    {
+        // left the loop with the early half of a first tile in flight (convergence, or a lost peer): complete the
+        // stage before the CTA gives its shared memory back
+        if (tid == 0) mbarArrive(&sm.full[0]);
+        mbarWait(&sm.full[0], use0 & 1u);
     }
     if (scribe)
     {
