@@ -30,13 +30,17 @@ UNIT = "substeps/s"
 REFERENCE_SAMPLE_RES = 1024
 
 
+DENSE_FILL = False  # --fill dense: the near-full tank of BASELINE config 5 (~400 M particles at 8192^2)
+
+
 def scene_for(res):
     from flipsolver2d_b200 import scenes
-    return scenes.dam_break(res, "flip", ppc=8, pic_ratio=0.03, seed=0, max_substeps=10)
+    return scenes.dam_break(res, "flip", ppc=8, pic_ratio=0.03, seed=0, max_substeps=10, dense_fill=DENSE_FILL)
 
 
 def workload_name(res):
-    return "flip dam-break %dx%d, ppc 8, picRatio 0.03, pcgIterLimit 200 (default), seed 0" % (res, res)
+    return "flip dam-break %dx%d%s, ppc 8, picRatio 0.03, pcgIterLimit 200 (default), seed 0" % (
+        res, res, " (near-full tank: fluid block (5,3)-(47,47) of the 50x50 domain)" if DENSE_FILL else "")
 
 
 class ClockSampler(threading.Thread):
@@ -279,7 +283,11 @@ def run_ours(args, rank, world, local_rank):
     # ---- end to end: particle state crosses PCIe both ways every step
     P = particles
     K = 2
-    cap = int((particles_all if world > 1 else P) * 1.25) + 1024  # slabs: particles migrate between ranks
+    cap = int(P * 1.25) + 1024
+    if world > 1:
+        cap = int(P * 1.5) + 2_000_000  # slabs: particles migrate between ranks (a few rows per step at CFL 5)
+    if args.no_e2e:
+        cap = 16
     pos = torch.empty((cap, 2), dtype=torch.float32).pin_memory()
     vel = torch.empty((cap, 2), dtype=torch.float32).pin_memory()
     props = torch.empty((K * cap,), dtype=torch.float32).pin_memory()
@@ -302,15 +310,17 @@ def run_ours(args, rank, world, local_rank):
         solver.step_substep()
         download()
 
-    download()
-    e2e_step()  # warm-up of the path
-    state["h2d"] = state["d2h"] = 0
-    e2e_steps = args.steps
-    e2e_ms = timed(e2e_step, e2e_steps)
-    e2e = {"value": e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": total(state["h2d"]) // e2e_steps,
-           "d2h_bytes_per_step": total(state["d2h"]) // e2e_steps,
-           "what": "per step: fs2d_upload_particles from pinned host buffers, FlipSolver::stepSubstep, fs2d_download_particles"
-                   + (" (every rank moves the particles of its slab; bytes summed over ranks)" if world > 1 else "")}
+    e2e = None
+    if not args.no_e2e:
+        download()
+        e2e_step()  # warm-up of the path
+        state["h2d"] = state["d2h"] = 0
+        e2e_steps = args.steps
+        e2e_ms = timed(e2e_step, e2e_steps)
+        e2e = {"value": e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": total(state["h2d"]) // e2e_steps,
+               "d2h_bytes_per_step": total(state["d2h"]) // e2e_steps,
+               "what": "per step: fs2d_upload_particles from pinned host buffers, FlipSolver::stepSubstep, fs2d_download_particles"
+                       + (" (every rank moves the particles of its slab; bytes summed over ranks)" if world > 1 else "")}
 
     if rank != 0:
         return
@@ -386,7 +396,11 @@ def main():
     ap.add_argument("--res", type=int, default=4096)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fill", default="reference", choices=["reference", "dense"])
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end region (very large particle counts)")
     args = ap.parse_args()
+    global DENSE_FILL
+    DENSE_FILL = args.fill == "dense"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -193,6 +193,7 @@ void freeAll(Ctx *c)
     if (c->heap) cudaFree(c->heap);  // every dense array lives inside the heap
     if (c->viscScalars) cudaFree(c->viscScalars);
     if (c->bfsQueue) cudaFree(c->bfsQueue);
+    if (c->p2gTileList) cudaFree(c->p2gTileList);
     if (c->bfsCtl) cudaFree(c->bfsCtl);
     if (c->solveMaps) std::free(c->solveMaps);
     void *ptrs[] = {c->rangeLast, c->dead, c->perm, c->obstacleFriction, c->sources, c->reseedUniform};

@@ -195,6 +195,7 @@ struct fs2d_context
     int maxBlocks = 0;
     PcgScalars *scalars = nullptr;    // device
     double *trace = nullptr;          // device, 4 doubles per iteration
+    int *p2gTileList = nullptr;       // [0] = count, [1..] = tiles with particles in reach (transfer.cu), allocated on first use
     int32_t *bfsQueue = nullptr;      // level-set BFS: cells in layer order (one slot per cell), allocated on first use
     unsigned int *bfsCtl = nullptr;   // level-set BFS: [0] = queue tail
     void *viscScalars = nullptr;      // device scalars of the viscosity CG (viscosity.cu), allocated on first use

@@ -1168,6 +1168,49 @@ __device__ __forceinline__ bool solveBarrier(const SolveArgs &g, const MgArgs &m
     const unsigned int nb = gridDim.x;
     if (blockIdx.x == 0 && tid == 0) mgStampAt(m, phase, 2);
     blockReduce2(v0, v1, sm.red);
+    if (!MG)
+    {
+        // One GPU: no publication step. Every CTA waits for the ticket to reach this barrier's target and then sums the
+        // partials itself, all in the same fixed order -> identical bits in every CTA, one L2 round trip less than
+        // "last CTA reduces and publishes". The partials are double-buffered by barrier parity: a CTA can run at most
+        // one barrier ahead of the slowest reader.
+        double *part = g.a.partials + (barrierIndex & 1u) * 2u * nb;
+        if (tid == 0)
+        {
+            part[blockIdx.x] = v0;
+            part[nb + blockIdx.x] = v1;
+            __threadfence();
+            atomicAdd(g.ticket, 1u);
+            if (blockIdx.x == 0) mgStampAt(m, phase, 3);
+            const unsigned int target = (barrierIndex + 1u) * nb;
+            unsigned int seen;
+            do
+            {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(g.ticket) : "memory");
+            } while (seen < target);
+            if (blockIdx.x == 0) mgStampAt(m, phase, 4);
+        }
+        __syncthreads();
+        double ts = 0.0, tm = 0.0;
+        for (unsigned int k = tid; k < nb; k += blockDim.x)
+        {
+            ts += __ldcg(part + k);
+            tm = fmax(tm, __ldcg(part + nb + k));
+        }
+        blockReduce2(ts, tm, sm.red);
+        if (tid == 0)
+        {
+            sm.bc[0] = ts;
+            sm.bc[1] = tm;
+            if (blockIdx.x == 0) mgStampAt(m, phase, 5);
+        }
+        __syncthreads();
+        *sum = sm.bc[0];
+        *mx = sm.bc[1];
+        asm volatile("fence.proxy.async;" ::: "memory");  // what other CTAs wrote is read by bulk copies next
+        if (blockIdx.x == 0 && tid == 0) mgStampAt(m, phase, 6);
+        return true;
+    }
     if (tid == 0)
     {
         g.a.partials[blockIdx.x] = v0;

@@ -135,46 +135,54 @@ __device__ __forceinline__ void forRowRange(const TileStage &s, bool staged, con
 // weightU > 1e-9 && weightV > 1e-9, i.e. floor(pos) within one cell of (i,j).
 __global__ void __launch_bounds__(NT) p2gVelocityKernel(const int32_t *__restrict__ cellStart, const float2 *__restrict__ pos,
                                                         const float2 *__restrict__ vel, const uint8_t *__restrict__ mis, int I,
-                                                        int J, int tilesJ, int tileBase,
+                                                        int J, int tilesJ, const int *__restrict__ tileList,
+                                                        const int *__restrict__ tileCount,
                                                         float *__restrict__ U, float *__restrict__ V,
                                                         uint8_t *__restrict__ uValid, uint8_t *__restrict__ vValid)
 {
     extern __shared__ __align__(16) unsigned char stageRaw[];
     TileStage &s = *reinterpret_cast<TileStage *>(stageRaw);
-    const int tile = tileBase + blockIdx.x;
-    const int ti = tile / tilesJ, tj = tile - ti * tilesJ;
-    const int i0 = ti * TI, j0 = tj * TJ;
-    const int stageMode = stageTile<true>(s, cellStart, pos, vel, nullptr, mis, I, J, i0, j0, 1, 1);
-    const bool staged = stageMode != 0, empty = stageMode == 2;
-    const int li = threadIdx.x / TJ, lj = threadIdx.x - li * TJ;
-    const int i = i0 + li, j = j0 + lj;
-    if (i >= I || j >= J) return;
-    const float ci = static_cast<float>(i), cj = static_cast<float>(j);
-    const float cjh = faddr(cj, 0.5f), cih = faddr(ci, 0.5f);
-    float uW = 1e-10f, vW = 1e-10f, uAcc = 0.f, vAcc = 0.f;
-    bool any = false;
-    const int ja = max(j - 1, 0), jb = min(j + 1, J - 1);
-    for (int gi = max(i - 1, 0); !empty && gi <= min(i + 1, I - 1); gi++)
+    const int count = *tileCount;
+    for (int t = blockIdx.x; t < count; t += gridDim.x)  // persistent CTAs walk the tiles that have particles in reach
     {
-        forRowRange<true>(s, staged, cellStart, pos, vel, nullptr, mis, J, gi, ja, jb, gi - (i0 - 1), i, j,
-                          [&](float2 p, float2 v)
-                          {
-                              const float wU = quadraticBSpline(fsubr(p.x, ci), fsubr(p.y, cjh));
-                              const float wV = quadraticBSpline(fsubr(p.x, cih), fsubr(p.y, cj));
-                              if (wU > 1e-9f && wV > 1e-9f)
-                              {
-                                  uW = faddr(uW, wU);
-                                  uAcc = faddr(uAcc, fmulr(wU, v.x));
-                                  vW = faddr(vW, wV);
-                                  vAcc = faddr(vAcc, fmulr(wV, v.y));
-                                  any = true;
-                              }
-                          });
+        const int tile = tileList[t];
+        const int ti = tile / tilesJ, tj = tile - ti * tilesJ;
+        const int i0 = ti * TI, j0 = tj * TJ;
+        const int stageMode = stageTile<true>(s, cellStart, pos, vel, nullptr, mis, I, J, i0, j0, 1, 1);
+        const bool staged = stageMode != 0, empty = stageMode == 2;
+        const int li = threadIdx.x / TJ, lj = threadIdx.x - li * TJ;
+        const int i = i0 + li, j = j0 + lj;
+        if (i < I && j < J)
+        {
+            const float ci = static_cast<float>(i), cj = static_cast<float>(j);
+            const float cjh = faddr(cj, 0.5f), cih = faddr(ci, 0.5f);
+            float uW = 1e-10f, vW = 1e-10f, uAcc = 0.f, vAcc = 0.f;
+            bool any = false;
+            const int ja = max(j - 1, 0), jb = min(j + 1, J - 1);
+            for (int gi = max(i - 1, 0); !empty && gi <= min(i + 1, I - 1); gi++)
+            {
+                forRowRange<true>(s, staged, cellStart, pos, vel, nullptr, mis, J, gi, ja, jb, gi - (i0 - 1), i, j,
+                                  [&](float2 p, float2 v)
+                                  {
+                                      const float wU = quadraticBSpline(fsubr(p.x, ci), fsubr(p.y, cjh));
+                                      const float wV = quadraticBSpline(fsubr(p.x, cih), fsubr(p.y, cj));
+                                      if (wU > 1e-9f && wV > 1e-9f)
+                                      {
+                                          uW = faddr(uW, wU);
+                                          uAcc = faddr(uAcc, fmulr(wU, v.x));
+                                          vW = faddr(vW, wV);
+                                          vAcc = faddr(vAcc, fmulr(wV, v.y));
+                                          any = true;
+                                      }
+                                  });
+            }
+            U[static_cast<long long>(i) * J + j] = __fdiv_rn(uAcc, uW);
+            uValid[static_cast<long long>(i) * J + j] = any ? 1 : 0;
+            V[static_cast<long long>(i) * (J + 1) + j] = __fdiv_rn(vAcc, vW);
+            vValid[static_cast<long long>(i) * (J + 1) + j] = any ? 1 : 0;
+        }
+        __syncthreads();  // the stage is rewritten for the next tile
     }
-    U[static_cast<long long>(i) * J + j] = __fdiv_rn(uAcc, uW);
-    uValid[static_cast<long long>(i) * J + j] = any ? 1 : 0;
-    V[static_cast<long long>(i) * (J + 1) + j] = __fdiv_rn(vAcc, vW);
-    vValid[static_cast<long long>(i) * (J + 1) + j] = any ? 1 : 0;
 }
 
 // centeredParamsToGridThread. MODE 0: water (flipsolver2d.cpp:1394-1431: threshold w > 1e-9, value
@@ -184,44 +192,73 @@ __global__ void __launch_bounds__(NT) p2gVelocityKernel(const int32_t *__restric
 template <int MODE>
 __global__ void __launch_bounds__(NT) p2gCenteredKernel(const int32_t *__restrict__ cellStart, const float2 *__restrict__ pos,
                                                         const float *__restrict__ prop, const uint8_t *__restrict__ mis, int I,
-                                                        int J, int tilesJ, int tileBase,
+                                                        int J, int tilesJ, const int *__restrict__ tileList,
+                                                        const int *__restrict__ tileCount,
                                                         float *__restrict__ out, uint8_t *__restrict__ known)
 {
     extern __shared__ __align__(16) unsigned char stageRaw[];
     TileStage &s = *reinterpret_cast<TileStage *>(stageRaw);
-    const int tile = tileBase + blockIdx.x;
+    const int count = *tileCount;
+    for (int t = blockIdx.x; t < count; t += gridDim.x)
+    {
+        const int tile = tileList[t];
+        const int ti = tile / tilesJ, tj = tile - ti * tilesJ;
+        const int i0 = ti * TI, j0 = tj * TJ;
+        const int stageMode = stageTile<false>(s, cellStart, pos, nullptr, prop, mis, I, J, i0, j0, 2, 1);
+        const bool staged = stageMode != 0, empty = stageMode == 2;
+        const int li = threadIdx.x / TJ, lj = threadIdx.x - li * TJ;
+        const int i = i0 + li, j = j0 + lj;
+        if (i < I && j < J)
+        {
+            const float ci = static_cast<float>(i), cj = static_cast<float>(j);
+            float wSum = 1e-10f, acc = 0.f;
+            bool any = false;
+            const int ja = max(j - 2, 0), jb = min(j + 1, J - 1);
+            for (int gi = max(i - 2, 0); !empty && gi <= min(i + 1, I - 1); gi++)
+            {
+                forRowRange<false>(s, staged, cellStart, pos, nullptr, prop, mis, J, gi, ja, jb, gi - (i0 - 2), i, j,
+                                   [&](float2 p, float2 v)
+                                   {
+                                       const float w = quadraticBSpline(fsubr(p.x, ci), fsubr(p.y, cj));
+                                       const bool take = MODE == 0 ? (w > 1e-9f) : (fabsf(w) > 1e-6f);
+                                       if (take)
+                                       {
+                                           wSum = faddr(wSum, w);
+                                           acc = faddr(acc, fmulr(w, v.x));
+                                           any = true;
+                                       }
+                                   });
+            }
+            const long long n = static_cast<long long>(i) * J + j;
+            if (MODE == 0)
+                out[n] = __fdiv_rn(acc, wSum);
+            else
+                out[n] = any ? __fdiv_rn(acc, wSum) : 0.f;
+            if (known) known[n] = any ? 1 : 0;
+        }
+        __syncthreads();
+    }
+}
+
+// The tiles a P2G kernel has to visit: those with at least one particle inside the tile grown by the widest kernel
+// support (2 cells up/left, 1 down/right). Everything else keeps the cleared value -- "no particle in reach" is 0 for
+// the velocity samples, their validity flags and the centred parameters alike (uAcc / 1e-10 = 0, known = false). One
+// warp per tile; the list order is arbitrary (tiles are independent and each cell's sum has a fixed order).
+__global__ void __launch_bounds__(256) p2gTileListKernel(const int32_t *__restrict__ cellStart, int I, int J, int tilesJ, int tileBase,
+                                                         int tiles, int *__restrict__ list, int *__restrict__ count)
+{
+    const int w = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (w >= tiles) return;
+    const int tile = tileBase + w;
     const int ti = tile / tilesJ, tj = tile - ti * tilesJ;
     const int i0 = ti * TI, j0 = tj * TJ;
-    const int stageMode = stageTile<false>(s, cellStart, pos, nullptr, prop, mis, I, J, i0, j0, 2, 1);
-    const bool staged = stageMode != 0, empty = stageMode == 2;
-    const int li = threadIdx.x / TJ, lj = threadIdx.x - li * TJ;
-    const int i = i0 + li, j = j0 + lj;
-    if (i >= I || j >= J) return;
-    const float ci = static_cast<float>(i), cj = static_cast<float>(j);
-    float wSum = 1e-10f, acc = 0.f;
-    bool any = false;
-    const int ja = max(j - 2, 0), jb = min(j + 1, J - 1);
-    for (int gi = max(i - 2, 0); !empty && gi <= min(i + 1, I - 1); gi++)
-    {
-        forRowRange<false>(s, staged, cellStart, pos, nullptr, prop, mis, J, gi, ja, jb, gi - (i0 - 2), i, j,
-                           [&](float2 p, float2 v)
-                           {
-                               const float w = quadraticBSpline(fsubr(p.x, ci), fsubr(p.y, cj));
-                               const bool take = MODE == 0 ? (w > 1e-9f) : (fabsf(w) > 1e-6f);
-                               if (take)
-                               {
-                                   wSum = faddr(wSum, w);
-                                   acc = faddr(acc, fmulr(w, v.x));
-                                   any = true;
-                               }
-                           });
-    }
-    const long long n = static_cast<long long>(i) * J + j;
-    if (MODE == 0)
-        out[n] = __fdiv_rn(acc, wSum);
-    else
-        out[n] = any ? __fdiv_rn(acc, wSum) : 0.f;
-    if (known) known[n] = any ? 1 : 0;
+    const int ja = max(j0 - 2, 0), jb = min(j0 + TJ, J - 1);
+    int n = 0;
+    const int gi = i0 - 2 + lane;
+    if (lane < TI + 3 && gi >= 0 && gi < I && ja <= jb)
+        n = cellStart[static_cast<long long>(gi) * J + jb + 1] - cellStart[static_cast<long long>(gi) * J + ja];
+    n = __reduce_add_sync(0xffffffffu, n);
+    if (lane == 0 && n > 0) list[atomicAdd(count, 1)] = tile;
 }
 
 // updateDensityGridThread (flipsolver2d.cpp:201-249)
@@ -345,6 +382,24 @@ int tileCount(const Ctx *ctx, SlabRows r, int *tilesJ, int *tileBase)
 
 int particlesSort(Ctx *ctx);
 
+// Builds the list of tiles with particles in reach for the rows `r`; returns the persistent grid size to launch.
+static int buildTileList(Ctx *ctx, SlabRows r, int *tilesJ)
+{
+    int tileBase = 0;
+    const int tiles = tileCount(ctx, r, tilesJ, &tileBase);
+    if (!ctx->p2gTileList)
+    {
+        const int all = divUp(ctx->I, TI) * divUp(ctx->J, TJ);
+        if (cudaMalloc(reinterpret_cast<void **>(&ctx->p2gTileList), sizeof(int) * (static_cast<size_t>(all) + 1)) != cudaSuccess) return -1;
+    }
+    int *count = ctx->p2gTileList, *list = ctx->p2gTileList + 1;
+    cudaMemsetAsync(count, 0, sizeof(int), ctx->stream);
+    p2gTileListKernel<<<divUp(tiles, 8), 256, 0, ctx->stream>>>(ctx->cellStart, ctx->I, ctx->J, *tilesJ, tileBase, tiles, list, count);
+    ctx->launches++;
+    (void)list;
+    return std::max(1, std::min(tiles, 2 * ctx->smCount));
+}
+
 static int ensureSorted(Ctx *ctx)
 {
     if (!ctx->sorted) return particlesSort(ctx);
@@ -362,12 +417,17 @@ int transferVelocity(Ctx *ctx)
     const size_t vOff = static_cast<size_t>(own.lo) * (ctx->J + 1), vCnt = static_cast<size_t>(own.hi - own.lo) * (ctx->J + 1);
     FS2D_CUDA(cudaMemsetAsync(ctx->V + vOff, 0, sizeof(float) * vCnt, st));
     FS2D_CUDA(cudaMemsetAsync(ctx->vValid + vOff, 0, vCnt, st));
-    int tilesJ, tileBase;
-    const int tiles = tileCount(ctx, own, &tilesJ, &tileBase);
+    // the owned rows of U and its flags: cells no particle reaches keep this 0 (the kernel only visits the other tiles)
+    const size_t uOff = static_cast<size_t>(own.lo) * ctx->J, uCnt = static_cast<size_t>(own.hi - own.lo) * ctx->J;
+    FS2D_CUDA(cudaMemsetAsync(ctx->U + uOff, 0, sizeof(float) * uCnt, st));
+    FS2D_CUDA(cudaMemsetAsync(ctx->uValid + uOff, 0, uCnt, st));
+    int tilesJ;
+    const int grid = buildTileList(ctx, own, &tilesJ);
+    if (grid < 0) return FS2D_ERR_CUDA;
     ParticleBuffers &b = ctx->pb[ctx->cur];
     allowStage(p2gVelocityKernel);
-    p2gVelocityKernel<<<tiles, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, b.vel, b.mis, ctx->I, ctx->J, tilesJ, tileBase, ctx->U, ctx->V,
-                                                      ctx->uValid, ctx->vValid);
+    p2gVelocityKernel<<<grid, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, b.vel, b.mis, ctx->I, ctx->J, tilesJ, ctx->p2gTileList + 1,
+                                                     ctx->p2gTileList, ctx->U, ctx->V, ctx->uValid, ctx->vValid);
     ctx->launches++;
     FS2D_CUDA(cudaGetLastError());
     return FS2D_OK;
@@ -377,35 +437,45 @@ int transferCentered(Ctx *ctx)
 {
     FS2D_TRY(ensureSorted(ctx));
     cudaStream_t st = ctx->stream;
-    int tilesJ, tileBase;
     const SlabRows own = slabOwn(ctx);
-    const int tiles = tileCount(ctx, own, &tilesJ, &tileBase);
+    int tilesJ;
+    const int grid = buildTileList(ctx, own, &tilesJ);
+    if (grid < 0) return FS2D_ERR_CUDA;
+    const int *tl = ctx->p2gTileList + 1, *tc = ctx->p2gTileList;
     ParticleBuffers &b = ctx->pb[ctx->cur];
     // m_divergenceControl.fill(0.f) in all three variants (flipsolver2d.cpp:1382, nbflipsolver.cpp:450,
     // flipsmokesolver.cpp:60); slab mode clears the rows the right-hand side is evaluated on
     const SlabRows e1 = slabExt(ctx, 1);
     FS2D_CUDA(cudaMemsetAsync(ctx->divergenceControl + static_cast<size_t>(e1.lo) * ctx->J, 0,
                               sizeof(float) * static_cast<size_t>(e1.hi - e1.lo) * ctx->J, st));
+    // cells no particle reaches: value 0, not known (the kernels only visit tiles with particles in reach)
+    const size_t cOff = static_cast<size_t>(own.lo) * ctx->J, cCnt = static_cast<size_t>(own.hi - own.lo) * ctx->J;
+    auto clear = [&](float *grid) { return cudaMemsetAsync(grid + cOff, 0, sizeof(float) * cCnt, st); };
+    FS2D_CUDA(cudaMemsetAsync(ctx->knownCentered + cOff, 0, cCnt, st));
     allowStage(p2gCenteredKernel<0>);
     allowStage(p2gCenteredKernel<1>);
     auto column = [&](int prop) -> const float * { return prop >= 0 ? b.props + static_cast<int64_t>(prop) * b.capacity : nullptr; };
     switch (ctx->p.sim_type)
     {
     case FS2D_SIM_LIQUID:
-        p2gCenteredKernel<0><<<tiles, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, column(ctx->p.viscosity_property), b.mis, ctx->I, ctx->J,
-                                                   tilesJ, tileBase, ctx->viscosity, ctx->knownCentered);
+        FS2D_CUDA(clear(ctx->viscosity));
+        p2gCenteredKernel<0><<<grid, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, column(ctx->p.viscosity_property), b.mis, ctx->I, ctx->J,
+                                                  tilesJ, tl, tc, ctx->viscosity, ctx->knownCentered);
         ctx->launches++;
         break;
     case FS2D_SIM_NBFLIP:
-        p2gCenteredKernel<1><<<tiles, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, column(ctx->p.viscosity_property), b.mis, ctx->I, ctx->J,
-                                                   tilesJ, tileBase, ctx->viscosity, ctx->knownCentered);
+        FS2D_CUDA(clear(ctx->viscosity));
+        p2gCenteredKernel<1><<<grid, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, column(ctx->p.viscosity_property), b.mis, ctx->I, ctx->J,
+                                                  tilesJ, tl, tc, ctx->viscosity, ctx->knownCentered);
         ctx->launches++;
         break;
     default:  // smoke / fire: temperature and concentration (fire's fuel column has no P2G in the reference)
-        p2gCenteredKernel<1><<<tiles, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, column(ctx->p.temperature_property), b.mis, ctx->I, ctx->J,
-                                                   tilesJ, tileBase, ctx->temperature, ctx->knownCentered);
-        p2gCenteredKernel<1><<<tiles, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, column(ctx->p.concentration_property), b.mis, ctx->I, ctx->J,
-                                                   tilesJ, tileBase, ctx->concentration, nullptr);
+        FS2D_CUDA(clear(ctx->temperature));
+        FS2D_CUDA(clear(ctx->concentration));
+        p2gCenteredKernel<1><<<grid, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, column(ctx->p.temperature_property), b.mis, ctx->I, ctx->J,
+                                                  tilesJ, tl, tc, ctx->temperature, ctx->knownCentered);
+        p2gCenteredKernel<1><<<grid, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, column(ctx->p.concentration_property), b.mis, ctx->I, ctx->J,
+                                                  tilesJ, tl, tc, ctx->concentration, nullptr);
         ctx->launches += 2;
         break;
     }

@@ -125,23 +125,30 @@ fs2d_handle FlipSolver::device()
     return m_device;
 }
 
-// Slab boundaries balanced by work instead of by rows: the seed particles per 16-row tile row (every rank seeds the
-// whole scene with the same stream, so every rank computes the same table) plus a small cost per row for the dense
-// grid passes. In a dam break the fluid fills the lower half of the tank only: equal row counts would leave half of
+// Slab boundaries balanced by work instead of by rows: the seed particles per 16-row tile row (every rank rasterises
+// the same scene, so every rank computes the same table) plus a small cost per row for the dense grid passes. In a dam break the fluid fills the lower half of the tank only: equal row counts would leave half of
 // the GPUs without a single particle or matrix row.
 std::vector<int32_t> FlipSolver::slabBounds(int world)
 {
     prepareHost();
+    return slabBoundsFromMaterial(world);
+}
+
+// seedInitialFluid puts exactly particlesPerCell particles into every strict-FLUID cell (flipsolver2d.cpp:682-707), so the
+// work per tile row is known from the rasterised material grid alone -- before (and without) drawing a single particle.
+std::vector<int32_t> FlipSolver::slabBoundsFromMaterial(int world) const
+{
     const int tileRows = static_cast<int>((m_sizeI + 15) / 16);
     std::vector<double> w(static_cast<size_t>(tileRows), 0.0);
-    const size_t n = m_seedPos.size() / 2;
-    for (size_t p = 0; p < n; p++)
+    double n = 0.0;
+    for (ssize_t i = 0; i < m_sizeI; i++)
     {
-        int t = static_cast<int>(std::floor(m_seedPos[2 * p])) / 16;
-        t = std::max(0, std::min(tileRows - 1, t));
-        w[static_cast<size_t>(t)] += 1.0;
+        size_t fluid = 0;
+        for (ssize_t j = 0; j < m_sizeJ; j++) fluid += m_materialGrid.isStrictFluid(i, j) ? 1 : 0;
+        w[static_cast<size_t>(i / 16)] += static_cast<double>(fluid) * m_particlesPerCell;
+        n += static_cast<double>(fluid) * m_particlesPerCell;
     }
-    const double base = std::max(1.0, 0.02 * static_cast<double>(n) / tileRows);
+    const double base = std::max(1.0, 0.02 * n / tileRows);
     double total = 0.0;
     for (double &x : w)
     {
@@ -490,6 +497,16 @@ void FlipSolver::updateInitialFluid()
 void FlipSolver::seedInitialFluid()
 {
     m_seedProps.assign(m_markerParticles.propertyCount(), std::vector<float>());
+    // Row slabs: every rank draws the WHOLE mt19937 stream (the jitter of a particle depends on all particles before
+    // it) but keeps only the particles of its own rows -- at 8192^2 with a full tank that is 50 M instead of 400 M
+    // records of host memory per rank.
+    int rowLo = 0, rowHi = static_cast<int>(m_sizeI);
+    if (g_slabWorld > 1)
+    {
+        const std::vector<int32_t> b = slabBoundsFromMaterial(g_slabWorld);
+        rowLo = b[static_cast<size_t>(g_slabRank)];
+        rowHi = b[static_cast<size_t>(g_slabRank) + 1];
+    }
     for (ssize_t i = 0; i < m_sizeI; i++)
         for (ssize_t j = 0; j < m_sizeJ; j++)
         {
@@ -497,6 +514,8 @@ void FlipSolver::seedInitialFluid()
             for (int p = 0; p < m_particlesPerCell; p++)
             {
                 const Vec3 pos = jitteredPosInCell(i, j);
+                const int row = static_cast<int>(std::floor(pos.x()));  // the cell row the device files it under
+                if (row < rowLo || row >= rowHi) continue;
                 const Vec3 velocity = m_fluidVelocityGrid.velocityAt(pos);
                 const float viscosity = m_viscosityGrid.interpolateAt(pos);
                 m_seedPos.push_back(pos.x());

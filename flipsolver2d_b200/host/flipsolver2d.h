@@ -203,6 +203,7 @@ public:
     int slabWorld() const { return m_slabWorld; }
     size_t globalParticleCount();
     std::vector<int32_t> slabBounds(int world);  // row boundaries balanced by seed particles per tile row
+    std::vector<int32_t> slabBoundsFromMaterial(int world) const;
 
 protected:
     virtual fs2d_params deviceParameters() const;
