@@ -262,39 +262,62 @@ __global__ void __launch_bounds__(256) p2gTileListKernel(const int32_t *__restri
 }
 
 // updateDensityGridThread (flipsolver2d.cpp:201-249)
-__global__ void __launch_bounds__(NT) densityKernel(const int32_t *__restrict__ cellStart, const float2 *__restrict__ pos,
-                                                    const uint8_t *__restrict__ mis, const int8_t *__restrict__ mat, int I, int J,
-                                                    int tilesJ, int tileBase, float particleMass,
-                                                    float cellVolume, float restDensity, float *__restrict__ density)
+// The value a cell without any particle in reach gets: 0 / cellVolume, clamped up to the rest density when the cell is
+// FLUID and touches an EMPTY cell (flipsolver2d.cpp:236-247).
+__device__ __forceinline__ float densityClamp(const int8_t *__restrict__ mat, int I, int J, int i, int j, float d, float restDensity)
 {
-    extern __shared__ __align__(16) unsigned char stageRaw[];
-    TileStage &s = *reinterpret_cast<TileStage *>(stageRaw);
-    const int tile = tileBase + blockIdx.x;
-    const int ti = tile / tilesJ, tj = tile - ti * tilesJ;
-    const int i0 = ti * TI, j0 = tj * TJ;
-    const int stageMode = stageTile<false>(s, cellStart, pos, nullptr, nullptr, mis, I, J, i0, j0, 1, 1);
-    const bool staged = stageMode != 0, empty = stageMode == 2;
-    const int li = threadIdx.x / TJ, lj = threadIdx.x - li * TJ;
-    const int i = i0 + li, j = j0 + lj;
-    if (i >= I || j >= J) return;
-    const float ci = static_cast<float>(i), cj = static_cast<float>(j);
-    float acc = 0.f;
-    const int ja = max(j - 1, 0), jb = min(j + 1, J - 1);
-    for (int gi = max(i - 1, 0); !empty && gi <= min(i + 1, I - 1); gi++)
-    {
-        forRowRange<false>(s, staged, cellStart, pos, nullptr, nullptr, mis, J, gi, ja, jb, gi - (i0 - 1), i, j,
-                           [&](float2 p, float2)
-                           {
-                               const float w = bilinearHat(fsubr(fsubr(p.x, ci), 0.5f), fsubr(fsubr(p.y, cj), 0.5f));
-                               if (fabsf(w) > 1e-6f) acc = faddr(acc, fmulr(w, particleMass));
-                           });
-    }
-    float d = __fdiv_rn(acc, cellVolume);
     if (matFluid(mat[static_cast<long long>(i) * J + j]) &&
         (matEmpty(matAt(mat, I, J, i + 1, j)) || matEmpty(matAt(mat, I, J, i - 1, j)) || matEmpty(matAt(mat, I, J, i, j + 1)) ||
          matEmpty(matAt(mat, I, J, i, j - 1))))
         d = fminf(fmaxf(d, restDensity), FLT_MAX);
-    density[static_cast<long long>(i) * J + j] = d;
+    return d;
+}
+
+// all cells of [nBegin, nEnd): the "no particle in reach" value; the tiles with particles overwrite theirs afterwards
+__global__ void __launch_bounds__(256) densityBackgroundKernel(const int8_t *__restrict__ mat, int I, int J, float cellVolume, float restDensity,
+                                                               float *__restrict__ density, long long nBegin, long long nEnd)
+{
+    const long long n = nBegin + blockIdx.x * 256ll + threadIdx.x;
+    if (n >= nEnd) return;
+    const int i = static_cast<int>(n / J), j = static_cast<int>(n - static_cast<long long>(i) * J);
+    density[n] = densityClamp(mat, I, J, i, j, __fdiv_rn(0.f, cellVolume), restDensity);
+}
+
+__global__ void __launch_bounds__(NT) densityKernel(const int32_t *__restrict__ cellStart, const float2 *__restrict__ pos,
+                                                    const uint8_t *__restrict__ mis, const int8_t *__restrict__ mat, int I, int J,
+                                                    int tilesJ, const int *__restrict__ tileList, const int *__restrict__ tileCount,
+                                                    float particleMass, float cellVolume, float restDensity, float *__restrict__ density)
+{
+    extern __shared__ __align__(16) unsigned char stageRaw[];
+    TileStage &s = *reinterpret_cast<TileStage *>(stageRaw);
+    const int count = *tileCount;
+    for (int t = blockIdx.x; t < count; t += gridDim.x)
+    {
+        const int tile = tileList[t];
+        const int ti = tile / tilesJ, tj = tile - ti * tilesJ;
+        const int i0 = ti * TI, j0 = tj * TJ;
+        const int stageMode = stageTile<false>(s, cellStart, pos, nullptr, nullptr, mis, I, J, i0, j0, 1, 1);
+        const bool staged = stageMode != 0, empty = stageMode == 2;
+        const int li = threadIdx.x / TJ, lj = threadIdx.x - li * TJ;
+        const int i = i0 + li, j = j0 + lj;
+        if (i < I && j < J)
+        {
+            const float ci = static_cast<float>(i), cj = static_cast<float>(j);
+            float acc = 0.f;
+            const int ja = max(j - 1, 0), jb = min(j + 1, J - 1);
+            for (int gi = max(i - 1, 0); !empty && gi <= min(i + 1, I - 1); gi++)
+            {
+                forRowRange<false>(s, staged, cellStart, pos, nullptr, nullptr, mis, J, gi, ja, jb, gi - (i0 - 1), i, j,
+                                   [&](float2 p, float2)
+                                   {
+                                       const float w = bilinearHat(fsubr(fsubr(p.x, ci), 0.5f), fsubr(fsubr(p.y, cj), 0.5f));
+                                       if (fabsf(w) > 1e-6f) acc = faddr(acc, fmulr(w, particleMass));
+                                   });
+            }
+            density[static_cast<long long>(i) * J + j] = densityClamp(mat, I, J, i, j, __fdiv_rn(acc, cellVolume), restDensity);
+        }
+        __syncthreads();
+    }
 }
 
 // updateSdfThread (flipsolver2d.cpp:1276-1311): min squared distance to the particles FILED in the 3x3
@@ -486,17 +509,25 @@ int transferCentered(Ctx *ctx)
 int transferDensity(Ctx *ctx)
 {
     FS2D_TRY(ensureSorted(ctx));
-    int tilesJ, tileBase;
     // slab mode: one extra tile row each side, the density right-hand side needs one halo row (ghost particles
     // reach 12 rows, the tile halo needs 9)
-    const int tiles = tileCount(ctx, slabExt(ctx, ctx->slab.enabled ? TI : 0), &tilesJ, &tileBase);
+    const SlabRows rows = slabExt(ctx, ctx->slab.enabled ? TI : 0);
+    int tilesJ;
+    const int grid = buildTileList(ctx, rows, &tilesJ);
+    if (grid < 0) return FS2D_ERR_CUDA;
     // float cellVolume = dx*dx*dx; float particleMass = (rho * cellVolume) / float(ppc) (flipsolver2d.cpp:203-204)
     const float cellVolume = static_cast<float>(ctx->p.dx * ctx->p.dx * ctx->p.dx);
     const float particleMass =
         static_cast<float>((ctx->p.fluid_density * cellVolume) / static_cast<float>(ctx->p.particles_per_cell));
+    const int rLo = (rows.lo / TI) * TI, rHi = std::min(ctx->I, divUp(rows.hi, TI) * TI);
+    const long long nBegin = static_cast<long long>(rLo) * ctx->J, nEnd = static_cast<long long>(rHi) * ctx->J;
+    densityBackgroundKernel<<<divUp(nEnd - nBegin, 256), 256, 0, ctx->stream>>>(ctx->material, ctx->I, ctx->J, cellVolume,
+                                                                               static_cast<float>(ctx->p.fluid_density), ctx->density, nBegin, nEnd);
     allowStage(densityKernel);
-    densityKernel<<<tiles, NT, STAGE_BYTES, ctx->stream>>>(ctx->cellStart, ctx->pb[ctx->cur].pos, ctx->pb[ctx->cur].mis, ctx->material, ctx->I, ctx->J, tilesJ,
-                                                tileBase, particleMass, cellVolume, static_cast<float>(ctx->p.fluid_density), ctx->density);
+    densityKernel<<<grid, NT, STAGE_BYTES, ctx->stream>>>(ctx->cellStart, ctx->pb[ctx->cur].pos, ctx->pb[ctx->cur].mis, ctx->material, ctx->I, ctx->J,
+                                                         tilesJ, ctx->p2gTileList + 1, ctx->p2gTileList, particleMass, cellVolume,
+                                                         static_cast<float>(ctx->p.fluid_density), ctx->density);
+    ctx->launches++;
     ctx->launches++;
     FS2D_CUDA(cudaGetLastError());
     return FS2D_OK;
