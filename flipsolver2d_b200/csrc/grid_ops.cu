@@ -165,12 +165,31 @@ __global__ void __launch_bounds__(NT) bfsInitKernel(const uint8_t *__restrict__ 
         jMin = min(jMin, __shfl_xor_sync(0xffffffffu, jMin, o));
         jMax = max(jMax, __shfl_xor_sync(0xffffffffu, jMax, o));
     }
+    // warps -> CTA in shared memory, then one global atomic per CTA and bound (hundreds of thousands of warp-level
+    // atomics on four addresses were most of this kernel's time)
+    __shared__ int box[4];
+    if (threadIdx.x == 0)
+    {
+        box[0] = 0x7fffffff;
+        box[1] = -1;
+        box[2] = 0x7fffffff;
+        box[3] = -1;
+    }
+    __syncthreads();
     if ((threadIdx.x & 31) == 0 && iMax >= 0)
     {
-        atomicMin(bbox + 0, iMin);
-        atomicMax(bbox + 1, iMax);
-        atomicMin(bbox + 2, jMin);
-        atomicMax(bbox + 3, jMax);
+        atomicMin(box + 0, iMin);
+        atomicMax(box + 1, iMax);
+        atomicMin(box + 2, jMin);
+        atomicMax(box + 3, jMax);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && box[1] >= 0)
+    {
+        atomicMin(bbox + 0, box[0]);
+        atomicMax(bbox + 1, box[1]);
+        atomicMin(bbox + 2, box[2]);
+        atomicMax(bbox + 3, box[3]);
     }
 }
 
