@@ -1,9 +1,9 @@
 // Autobench: headless scene benchmark with the reference's command line
 // (AutoBench/benchmarkrunnerapplication.cpp:14-48): -i <scene.json | directory of *.json>
 // -o <output directory> -s <frames per scene, default 60>. For every scene it loads the JSON through
-// JsonSceneReader, calls stepFrame() and records SolverStats per frame. The reference writes
-// Stats.xlsx through OpenXLSX (not available here); this driver writes one CSV per run with the same
-// 18 columns (AutoBench/benchruntable.h:28-49), one block per scene.
+// JsonSceneReader, calls stepFrame() and records SolverStats per frame, then writes <output>/Stats.xlsx
+// -- one worksheet per scene, the 18 columns of AutoBench/benchruntable.h:28-49 (benchruntable.h here:
+// a dependency-free xlsx writer, OpenXLSX is not available) -- and the same table as Stats.csv.
 #include <filesystem>
 #include <fstream>
 #include <iostream>
@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 
+#include "../benchruntable.h"
 #include "../jsonscenereader.h"
 
 namespace fs = std::filesystem;
@@ -21,10 +22,6 @@ static std::string option(int argc, char **argv, const std::string &name)
         if (name == argv[k]) return argv[k + 1];
     return "";
 }
-
-static const char *kColumns[] = {"Step",          "Substeps",       "Frame time",   "Advection",     "Decomposition", "Density",
-                                 "Particle rebin", "Particle to grid", "Grid update", "After transfer", "Pressure",      "Viscosity",
-                                 "Repressure",    "Particle update", "Particle reseed", "Pressure iters", "Density iters", "Viscosity iters"};
 
 struct SceneRun
 {
@@ -85,18 +82,27 @@ int main(int argc, char **argv)
         return 1;
     }
 
+    BenchRunTable table;
+    table.setOutputFile(output / "Stats.xlsx");
+    for (const SceneRun &run : runs)
+    {
+        for (const SolverStats &st : run.frames) table.addStepTiming(st);
+        table.finishScene(run.name);
+    }
+    if (!table.save()) std::cerr << "Autobench: cannot write " << (output / "Stats.xlsx").string() << std::endl;
+
     std::ofstream csv(output / "Stats.csv");
     for (const SceneRun &run : runs)
     {
         double totalMs = 0.0;
         long substeps = 0;
         csv << "# scene," << run.name << ",cells," << run.cells << ",particles," << run.particles << "\n";
-        for (size_t c = 0; c < 18; c++) csv << kColumns[c] << (c + 1 < 18 ? "," : "\n");
+        for (int c = 0; c < 18; c++) csv << BenchRunTable::getColumnHeader(c) << (c + 1 < 18 ? "," : "\n");
         for (size_t f = 0; f < run.frames.size(); f++)
         {
             const SolverStats &s = run.frames[f];
             const SolverStats::StageTimings t = s.timings();
-            csv << f << "," << s.substepCount() << "," << s.frameTime();
+            csv << f + 1 << "," << s.substepCount() << "," << s.frameTime();
             for (float v : t) csv << "," << v;
             csv << "," << s.pressureIterations() << "," << s.densityIterations() << "," << s.viscosityIterations() << "\n";
             totalMs += s.frameTime();

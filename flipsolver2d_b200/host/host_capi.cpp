@@ -7,6 +7,7 @@
 #include <string>
 
 #include "../../include/fs2d_host.h"
+#include "benchruntable.h"
 #include "jsonscenereader.h"
 
 namespace
@@ -52,6 +53,25 @@ int fs2dh_slab_connect(fs2dh_solver s, int peer_rank, const void *blob)
 {
     Holder *h = static_cast<Holder *>(s);
     return guarded(h, [&]() { h->solver->slabConnect(peer_rank, blob); });
+}
+
+int fs2dh_write_stats_xlsx(const char *path, int scenes, const char *const *scene_names, const int *rows_per_scene, const double *rows18)
+{
+    if (!path || scenes < 0 || (scenes > 0 && (!scene_names || !rows_per_scene || !rows18))) return FS2D_ERR_ARG;
+    BenchRunTable table;
+    table.setOutputFile(path);
+    const double *r = rows18;
+    for (int k = 0; k < scenes; k++)
+    {
+        for (int f = 0; f < rows_per_scene[k]; f++, r += BenchRunTable::TABLE_COLUMN_COUNT)
+        {
+            BenchRunTable::Row row{};
+            for (int c = 0; c < BenchRunTable::TABLE_COLUMN_COUNT; c++) row[static_cast<size_t>(c)] = r[c];
+            table.addRow(row);
+        }
+        table.finishScene(scene_names[k]);
+    }
+    return table.save() ? FS2D_OK : FS2D_ERR_STATE;
 }
 
 int fs2dh_slab_bounds(fs2dh_solver s, int world, int32_t *row_bounds)

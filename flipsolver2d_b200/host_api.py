@@ -39,6 +39,7 @@ def lib():
         "fs2dh_slab_connect": (i32, [vp, i32, vp]),
         "fs2dh_global_particle_count": (i64, [vp]),
         "fs2dh_slab_bounds": (i32, [vp, i32, vp]),
+        "fs2dh_write_stats_xlsx": (i32, [C.c_char_p, i32, vp, vp, vp]),
         "fs2dh_load_scene": (vp, [C.c_char_p]),
         "fs2dh_destroy": (None, [vp]),
         "fs2dh_last_error": (C.c_char_p, [vp]),
@@ -66,6 +67,19 @@ def lib():
         fn.argtypes = args
     _lib = L
     return L
+
+
+def write_stats_xlsx(path, scenes):
+    """scenes: {name: array of shape (frames, 18)} -> Stats.xlsx as AutoBench's BenchRunTable::save lays it out."""
+    L = lib()
+    names = list(scenes.keys())
+    arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+    counts = np.array([len(scenes[n]) for n in names], np.int32)
+    rows = np.ascontiguousarray(np.concatenate([np.asarray(scenes[n], np.float64).reshape(-1, 18) for n in names])
+                                if names else np.zeros((0, 18)), np.float64)
+    rc = L.fs2dh_write_stats_xlsx(str(path).encode(), len(names), C.cast(arr, C.c_void_p), _p(counts), _p(rows))
+    if rc != 0:
+        raise capi.Fs2dError("write_stats_xlsx failed (%d)" % rc)
 
 
 def connect_slabs(solvers):

@@ -63,6 +63,11 @@ fs2d_handle fs2dh_device(fs2dh_solver s);             /* the fs2d handle behind 
 int fs2dh_material(fs2dh_solver s, int8_t *out);      /* materialGrid().data() */
 int64_t fs2dh_bin_sizes(fs2dh_solver s, int32_t *out, int64_t capacity); /* markerParticles().bins()[k].size() */
 
+/* BenchRunTable::save (AutoBench/benchruntable.cpp:15-48): Stats.xlsx with one worksheet per scene and the 18 columns of
+ * AutoBench/benchruntable.h:28-49, written without OpenXLSX. rows18 = all rows of all scenes back to back, 18 doubles
+ * each, in the order of the TableColumn enum; no GPU needed. The Autobench driver fills the same table from SolverStats. */
+int fs2dh_write_stats_xlsx(const char *path, int scenes, const char *const *scene_names, const int *rows_per_scene, const double *rows18);
+
 #ifdef __cplusplus
 }
 #endif
