@@ -199,3 +199,41 @@ def test_whole_solve_kernel_equals_stepwise_kernels(ref_mod, scene_dir, dense):
     x0, n0 = d.pcg_solve(np.zeros(s.N), 50, 0.0)  # VOps::isZero: no iterations
     assert n0 == 0 and not x0.any()
     d.close()
+
+
+def test_linear_index_wrap_columns_without_walls(ref_mod, scene_dir):
+    """A tank without side walls: FLUID cells in columns 0 and J-1 have their j-1 / j+1 "neighbour" bit set (the material
+    grid extends its border, materialgrid.cpp:5-8) and the reference's operators then read the LINEAR neighbours idx-1 /
+    idx+1, i.e. the last / first element of the adjacent row (pressuredata.h:135-145). The whole-solve kernel loads its
+    tiles with tensor copies, which zero-fill outside the matrix, and patches exactly those wrap columns by hand; the
+    stepwise kernels load row segments by linear index. Both must reproduce the reference's iterates."""
+    scene = scenes.dam_break(96, "flip")
+    scene["solver"]["objects"] = [o for o in scene["solver"]["objects"] if o["type"] != "solid"]
+    scene["solver"]["objects"][-1]["verts"] = [[20, 0], [20, 50], [45, 50], [45, 0]]  # fluid across the full width
+    path = scenes.write_scene(scene, str(scene_dir / "nowalls.json"))
+    s = ref_mod.RefSolver(path, strict=True)
+    s.stage("FIRST_FRAME_INIT")
+    s.set_step_dt(1.0 / 2000.0)
+    s.stage("BUILD_MATRIX")
+    d = _device_for(s, iter_limit=60)
+    rm = s.matrix()
+    unit = rm["is_unit"].astype(bool).reshape(s.I, s.J)
+    assert unit[:, 0].any() and unit[:, -1].any()            # rows exist in the first and the last column ...
+    mask = rm["mask"].reshape(s.I, s.J)
+    assert (mask[unit[:, 0], 0] & 4).any() and (mask[unit[:, -1], -1] & 8).any()  # ... with the wrap neighbours switched on
+    rng = np.random.default_rng(3)
+    rhs = np.where(unit.ravel(), rng.standard_normal(s.N), 0.0)
+    v = rng.standard_normal(s.N)
+    assert np.array_equal(d.spmv(v), s.spmv(v))
+    for dense in (True, False):
+        d.pcg_set_dense(dense)
+        xr, nr = s.pcg(rhs, 25, 0.0)
+        d.pcg_set_stepwise(True)
+        x_step, n_step = d.pcg_solve(rhs, 25, 0.0)
+        d.pcg_set_stepwise(False)
+        x_whole, n_whole = d.pcg_solve(rhs, 25, 0.0)
+        assert n_step == n_whole == nr == 25
+        assert np.array_equal(x_whole, x_step)
+        assert np.linalg.norm(x_whole - xr) / np.linalg.norm(xr) < 1e-9
+    d.close()
+    s.close()
