@@ -1004,7 +1004,7 @@ struct SolveArgs
 };
 
 template <int MODE, bool MG>
-__device__ __forceinline__ void pipeWalk(PipeStage<MODE> *st0, PipeStage<MODE> *st1, unsigned long long *full, const double *preTbl,
+__device__ __forceinline__ bool pipeWalk(PipeStage<MODE> *st0, PipeStage<MODE> *st1, unsigned long long *full, const double *preTbl,
                                          const PcgArgs &a, const MgArgs &mg, const double *__restrict__ in0,
                                          const double *__restrict__ in1, double *__restrict__ out0, double *__restrict__ out1,
                                          double *__restrict__ xv, double *loOut1, double *hiOut1, double coef, double alphaPrev,
@@ -1022,6 +1022,7 @@ __device__ __forceinline__ void pipeWalk(PipeStage<MODE> *st0, PipeStage<MODE> *
         return a.activeTiles ? a.activeTiles[t] : (MG ? mg.tileBase + t : t);
     };
     const bool tensor = tm0 != nullptr;
+    bool remote = false;  // (uniform over the CTA) one of its tiles holds a slab-boundary row pushed into a neighbour
     if (myTiles > 0)
     {
         if (tensor)
@@ -1060,6 +1061,8 @@ __device__ __forceinline__ void pipeWalk(PipeStage<MODE> *st0, PipeStage<MODE> *
         const int i0 = ti * TR, j0 = tj * TC;
         PipeStage<MODE> &st = s ? *st1 : *st0;
         const long long gj = j0 + bc;
+        if (MG)
+            remote = remote || (loOut1 && mg.rowBegin >= i0 && mg.rowBegin < i0 + TR) || (hiOut1 && mg.rowEnd - 1 >= i0 && mg.rowEnd - 1 < i0 + TR);
         // Tensor copies zero-fill what lies outside the I x J matrix; the reference's operators address the j = -1 /
         // j = J neighbours by LINEAR index, i.e. the last / first element of the adjacent row (pressuredata.h:135-145).
         // Threads 0..15 (left edge tiles) and 16..31 (right edge tiles) fetch those values while the tile is in flight.
@@ -1156,13 +1159,14 @@ __device__ __forceinline__ void pipeWalk(PipeStage<MODE> *st0, PipeStage<MODE> *
         fenceProxyAsync();
         __syncthreads();
     }
+    return remote;
 }
 
 // Grid-wide (and, with slabs, machine-wide) barrier that all-reduces (v0: sum, v1: max). Returns false when a peer
 // did not answer within the spin limit.
 template <bool MG>
 __device__ __forceinline__ bool solveBarrier(const SolveArgs &g, const MgArgs &m, int phase, unsigned int barrierIndex, double v0,
-                                             double v1, SolveSmem &sm, double *sum, double *mx)
+                                             double v1, SolveSmem &sm, double *sum, double *mx, bool remoteStores = true)
 {
     const int tid = threadIdx.x;
     const unsigned int nb = gridDim.x;
@@ -1215,8 +1219,11 @@ __device__ __forceinline__ bool solveBarrier(const SolveArgs &g, const MgArgs &m
     {
         g.a.partials[blockIdx.x] = v0;
         g.a.partials[nb + blockIdx.x] = v1;
-        if (MG)
-            __threadfence_system();  // also orders this CTA's halo-row stores into the neighbours' arrays
+        // A CTA that pushed a halo row into a neighbour's array orders those stores at system scope before it arrives
+        // (the publication by the last CTA then covers them); for everybody else the data only has to be visible on this
+        // GPU. A system-scope fence behind a tile's worth of stores costs 3-5 us, a device-scope one ~1 us.
+        if (MG && remoteStores)
+            __threadfence_system();
         else
             __threadfence();
         sm.isLast = (atomicAdd(g.ticket, 1u) == (barrierIndex + 1u) * nb - 1u);
@@ -1316,12 +1323,12 @@ __global__ void __launch_bounds__(NT, 2) pcgSolveKernel(SolveArgs g, MgArgs mg, 
     {
         // K1(i): s_i = z + beta s_{i-1}; x += alpha_{i-1} s_{i-1}; q = A s_i; gamma = q.s_i
         double accDot = 0.0, accMax = 0.0, unused = 0.0;
-        pipeWalk<MODE_K1, MG>(a0, a1, sm.full, sm.preTbl, g.a, mg, g.z, g.s[i & 1], g.s[(i + 1) & 1], g.q, g.x, g.loQ, g.hiQ, beta,
+        const bool remoteA = pipeWalk<MODE_K1, MG>(a0, a1, sm.full, sm.preTbl, g.a, mg, g.z, g.s[i & 1], g.s[(i + 1) & 1], g.q, g.x, g.loQ, g.hiQ, beta,
                               alphaPrev, numTiles, use0, use1, accDot, accMax, 2 * i + 1, useTensor ? &tm.m[TM_Z] : nullptr,
                               &tm.m[TM_S0 + (i & 1)], &tm.m[TM_X], early);
         early = canEarly;  // r_old of K2(i) was written an iteration ago: fetch it while the barrier runs
         if (early && tid == 0) pipeIssueEarly<MODE_K2>(*b0, &sm.full[0], &tm.m[TM_R0 + (i & 1)], nullptr, g.a.tilesJ, firstTile);
-        if (!solveBarrier<MG>(g, mg, 2 * i + 1, bar++, accDot, 0.0, sm, &gamma, &unused)) break;
+        if (!solveBarrier<MG>(g, mg, 2 * i + 1, bar++, accDot, 0.0, sm, &gamma, &unused, remoteA)) break;
         alpha = sigma / (gamma + 1e-8);  // linearsolver.cpp:50
         if (scribe)
         {
@@ -1332,14 +1339,14 @@ __global__ void __launch_bounds__(NT, 2) pcgSolveKernel(SolveArgs g, MgArgs mg, 
         // K2(i): r -= alpha q; z = M r; sigma' = z.r; err = max|r|
         accDot = 0.0;
         accMax = 0.0;
-        pipeWalk<MODE_K2, MG>(b0, b1, sm.full, sm.preTbl, g.a, mg, g.r[i & 1], g.q, g.r[(i + 1) & 1], g.z, nullptr, g.loZ, g.hiZ, alpha, 0.0,
+        const bool remoteB = pipeWalk<MODE_K2, MG>(b0, b1, sm.full, sm.preTbl, g.a, mg, g.r[i & 1], g.q, g.r[(i + 1) & 1], g.z, nullptr, g.loZ, g.hiZ, alpha, 0.0,
                               numTiles, use0, use1, accDot, accMax, 2 * i + 2, useTensor ? &tm.m[TM_R0 + (i & 1)] : nullptr, &tm.m[TM_Q],
                               nullptr, early);
         early = canEarly && i + 1 < g.iterLimit;  // s_old and x of K1(i+1), unless this was the last iteration
         if (early && tid == 0)
             pipeIssueEarly<MODE_K1>(*a0, &sm.full[0], &tm.m[TM_S0 + ((i + 1) & 1)], &tm.m[TM_X], g.a.tilesJ, firstTile);
         double sigmaNew = 0.0;
-        if (!solveBarrier<MG>(g, mg, 2 * i + 2, bar++, accDot, accMax, sm, &sigmaNew, &err)) break;
+        if (!solveBarrier<MG>(g, mg, 2 * i + 2, bar++, accDot, accMax, sm, &sigmaNew, &err, remoteB)) break;
         executed = i + 1;
         const bool converged = err <= g.a.tol;  // linearsolver.cpp:59-61
         const double betaNew = converged ? 0.0 : sigmaNew / sigma;  // :66-67
