@@ -1105,41 +1105,59 @@ __device__ __forceinline__ bool pipeWalk(PipeStage<MODE> *st0, PipeStage<MODE> *
             }
             __syncthreads();
         }
-        for (int e = tid; e < PTILE; e += NT)
+        // phase 1, two elements per thread and step: the staged rows hold an even number of doubles, the interior
+        // starts at an even column and J is even, so a pair never straddles a row, the interior or the matrix edge;
+        // 16-byte shared and global accesses halve the instruction count of this phase
+        for (int e = 2 * tid; e < PTILE; e += 2 * NT)
         {
             const int ar = e / PSW, c = e - ar * PSW;
-            const double av = st.a[e], bv = st.b[e];
-            double v;
+            const double2 av = *reinterpret_cast<const double2 *>(st.a + e), bv = *reinterpret_cast<const double2 *>(st.b + e);
+            double2 v;
             if (MODE == MODE_K1)
-                v = __dadd_rn(av, __dmul_rn(bv, coef));
+            {
+                v.x = __dadd_rn(av.x, __dmul_rn(bv.x, coef));
+                v.y = __dadd_rn(av.y, __dmul_rn(bv.y, coef));
+            }
             else
-                v = __dsub_rn(av, __dmul_rn(bv, coef));
-            st.a[e] = v;
+            {
+                v.x = __dsub_rn(av.x, __dmul_rn(bv.x, coef));
+                v.y = __dsub_rn(av.y, __dmul_rn(bv.y, coef));
+            }
+            *reinterpret_cast<double2 *>(st.a + e) = v;
             const long long gi = i0 - 1 + ar, gjj = j0 - 2 + c;
             if (ar >= 1 && ar <= TR && c >= 2 && c < TC + 2 && gi < a.I && gjj < J)
             {
                 const long long n = gi * J + gjj;
-                out0[n] = v;
-                if (MODE == MODE_K1) xv[n] = __dadd_rn(st.x[(ar - 1) * TC + (c - 2)], __dmul_rn(bv, alphaPrev));
+                *reinterpret_cast<double2 *>(out0 + n) = v;
+                if (MODE == MODE_K1)
+                {
+                    const double2 xo = *reinterpret_cast<const double2 *>(st.x + (ar - 1) * TC + (c - 2));
+                    double2 xn;
+                    xn.x = __dadd_rn(xo.x, __dmul_rn(bv.x, alphaPrev));
+                    xn.y = __dadd_rn(xo.y, __dmul_rn(bv.y, alphaPrev));
+                    *reinterpret_cast<double2 *>(xv + n) = xn;
+                }
             }
             else if (MG && c >= 2 && c < TC + 2 && gjj < J && ((ar == 0 && gi == mg.rowBegin - 1 && gi >= 0) || (gi == mg.rowEnd && gi < a.I && ar <= TR + 1)))
             {
-                out0[gi * J + gjj] = v;  // halo row of the slab, kept current redundantly (same bits as on the owner)
+                *reinterpret_cast<double2 *>(out0 + gi * J + gjj) = v;  // halo row of the slab, kept current redundantly (same bits as on the owner)
             }
         }
         __syncthreads();
         if (gj < J)
         {
+            // phase 2: the thread walks down its column; the vertical neighbours slide through registers
+            const double *t = st.a + (1 + rg * (TR / 2)) * PSW + bc + 2;
+            double im = t[-PSW], c = t[0];
 #pragma unroll
             for (int q = 0; q < TR / 2; q++)
             {
                 const int ar = 1 + rg * (TR / 2) + q;
                 const long long gi = i0 - 1 + ar;
+                const double ip = t[PSW], jm = t[-1], jp = t[1];
                 if (gi < a.I)
                 {
                     const long long n = gi * J + gj;
-                    const double *t = st.a + ar * PSW + bc + 2;
-                    const double c = t[0], im = t[-PSW], ip = t[PSW], jm = t[-1], jp = t[1];
                     double o;
                     if (MODE == MODE_K1)
                         o = rowA(static_cast<uint8_t>(info[q]), a.scale, c, im, ip, jm, jp);
@@ -1154,6 +1172,9 @@ __device__ __forceinline__ bool pipeWalk(PipeStage<MODE> *st0, PipeStage<MODE> *
                     accDot += o * c;
                     accMax = fmax(accMax, fabs(c));
                 }
+                im = c;
+                c = ip;
+                t += PSW;
             }
         }
         fenceProxyAsync();
