@@ -2,23 +2,31 @@
 //
 // Replaces LinearSolver::solve (linearsolver.cpp:25-73), IndexedPressureParameters::multiply
 // (pressuredata.h:132-238), IndexedIPPCoefficients::multiply (PressureIPPCoeficients.h:23-132)
-// and the VOps BLAS-1 passes (vmath.cpp:25-136) with two fused, bandwidth-bound kernels per
-// iteration plus device-resident scalars, so a solve never synchronises with the host:
+// and the VOps BLAS-1 passes (vmath.cpp:25-136) with two fused, bandwidth-bound phases per
+// iteration and scalars that never leave the device:
 //
 //   K1(i):  s_i = z + beta*s_{i-1}          (addMul, linearsolver.cpp:68)
 //           x  += alpha_{i-1}*s_{i-1}       (deferred addMul of :51 -- s_{i-1} is in flight anyway)
 //           q   = A*s_i                     (:49)      gamma = q.s_i -> alpha_i (:50)
 //   K2(i):  r  -= alpha_i*q                 (:52)
 //           z   = M*r   sigma' = z.r        (:63-66)   err = max|r| (:53)
-//           last block decides convergence / beta (:59-69)
+//           convergence / beta (:59-69)
 //
-// Per iteration each kernel streams every vector it touches exactly once: K1 reads z, s, x
+// Per iteration each phase streams every vector it touches exactly once: K1 reads z, s, x
 // and writes s, q, x; K2 reads r, q and writes r, z -> 10 fp64 passes + 3 bytes of per-cell
 // row info = 83 B/cell (the reference makes 18 passes). Stencil neighbours come from a
 // shared-memory tile of the *derived* vector (s_i resp. the updated r), so the 5-point
 // operators never re-read HBM. Vectors stay fp64 like the reference's std::vector<double>
 // (linearsolver.h:15-20); arithmetic uses explicit non-contracted mul/add in the reference's
 // evaluation order so a single operator application is bit-identical to the strict oracle.
+//
+// Three generations of the same arithmetic live here (all produce bit-identical iterates):
+//   pcgSolveKernel   the default: ONE persistent cooperative launch per solve, tensor-map TMA tile loads, the two
+//                    reductions of an iteration carried by in-kernel grid barriers (which, with row slabs, ARE the
+//                    all-reduce across GPUs) -- see "whole-solve kernel" below;
+//   pcgPipeKernel    two launches per iteration with a bulk-copy pipeline; still used for the reference-compatible
+//                    convergence test (convergence_threads > 0) and as the A/B baseline (fs2d_pcg_set_stepwise);
+//   pcgTileKernel    plain tiles, for odd gridSizeJ and the stand-alone operator applications.
 #include <cuda.h>
 
 #include <algorithm>
