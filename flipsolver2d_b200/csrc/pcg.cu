@@ -950,6 +950,7 @@ struct SolveMaps
 struct WalkHints
 {
     unsigned long long in0, in1, x, out0, out1;
+    unsigned long long xStore = 0;  // policy of the x store when it differs from the x load (0: same as x)
 };
 
 __device__ __forceinline__ unsigned long long policyEvictFirst()
@@ -1075,7 +1076,7 @@ __device__ __forceinline__ bool pipeWalk(PipeStage<MODE> *st0, PipeStage<MODE> *
                                          double *__restrict__ xv, double *loOut1, double *hiOut1, double coef, double alphaPrev,
                                          int numTiles, unsigned int &use0, unsigned int &use1, double &accDot, double &accMax,
                                          int phase = 0, const CUtensorMap *tm0 = nullptr, const CUtensorMap *tm1 = nullptr,
-                                         const CUtensorMap *tmx = nullptr, bool earlyIssued = false, WalkHints h = WalkHints{0, 0, 0, 0, 0})
+                                         const CUtensorMap *tmx = nullptr, bool earlyIssued = false, WalkHints h = WalkHints{0, 0, 0, 0, 0, 0})
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long J = a.J;
@@ -1200,7 +1201,7 @@ __device__ __forceinline__ bool pipeWalk(PipeStage<MODE> *st0, PipeStage<MODE> *
                     double2 xn;
                     xn.x = __dadd_rn(xo.x, __dmul_rn(bv.x, alphaPrev));
                     xn.y = __dadd_rn(xo.y, __dmul_rn(bv.y, alphaPrev));
-                    storeHint2(xv + n, xn, h.x);
+                    storeHint2(xv + n, xn, h.xStore ? h.xStore : h.x);
                 }
             }
             else if (MG && c >= 2 && c < TC + 2 && gjj < J && ((ar == 0 && gi == mg.rowBegin - 1 && gi >= 0) || (gi == mg.rowEnd && gi < a.I && ar <= TR + 1)))
@@ -1410,15 +1411,21 @@ __global__ void __launch_bounds__(NT, 2) pcgSolveKernel(SolveArgs g, MgArgs mg, 
     const unsigned long long hx = (hintMask & 1) ? pf : 0ull;                               // x
     const unsigned long long hqz = (hintMask & 2) ? pl : 0ull;                              // q and z
     const unsigned long long hsr = (hintMask & 4) ? pf : ((hintMask & 8) ? pl : 0ull);      // s and r
-    const WalkHints hA = {hqz, hsr, hx, hsr, hqz};  // K1: in0 = z, in1 = s_old, x, out0 = s_new, out1 = q
-    const WalkHints hB = {hsr, hqz, 0ull, hsr, hqz};  // K2: in0 = r_old, in1 = q, out0 = r_new, out1 = z
+    // bit 16: every element is written once and read once per iteration, so every load is a LAST use (evict-first) and
+    // every store will be read exactly once (evict-last); x loads / stores follow bit 32 (0: like the rest, 1: streaming)
+    const bool lastUse = (hintMask & 16) != 0;
+    const unsigned long long hxs = (hintMask & 32) ? pf : pl;
+    const WalkHints hA = lastUse ? WalkHints{pf, pf, pf, pl, pl} : WalkHints{hqz, hsr, hx, hsr, hqz};  // K1: in0 = z, in1 = s_old, x, out0 = s_new, out1 = q
+    const WalkHints hB = lastUse ? WalkHints{pf, pf, 0ull, pl, pl} : WalkHints{hsr, hqz, 0ull, hsr, hqz};  // K2: in0 = r_old, in1 = q, out0 = r_new, out1 = z
+    WalkHints hA2 = hA;
+    hA2.xStore = lastUse ? hxs : 0ull;
     for (int i = 0; i < g.iterLimit; i++)
     {
         // K1(i): s_i = z + beta s_{i-1}; x += alpha_{i-1} s_{i-1}; q = A s_i; gamma = q.s_i
         double accDot = 0.0, accMax = 0.0, unused = 0.0;
         const bool remoteA = pipeWalk<MODE_K1, MG>(a0, a1, sm.full, sm.preTbl, g.a, mg, g.z, g.s[i & 1], g.s[(i + 1) & 1], g.q, g.x, g.loQ, g.hiQ, beta,
                               alphaPrev, numTiles, use0, use1, accDot, accMax, 2 * i + 1, (useTensor & 1) ? &tm.m[TM_Z] : nullptr,
-                              &tm.m[TM_S0 + (i & 1)], &tm.m[TM_X], early, hA);
+                              &tm.m[TM_S0 + (i & 1)], &tm.m[TM_X], early, hA2);
         early = canEarly;  // r_old of K2(i) was written an iteration ago: fetch it while the barrier runs
         if (early && tid == 0) pipeIssueEarly<MODE_K2>(*b0, &sm.full[0], &tm.m[TM_R0 + (i & 1)], nullptr, g.a.tilesJ, firstTile, hB);
         if (!solveBarrier<MG>(g, mg, 2 * i + 1, bar++, accDot, 0.0, sm, &gamma, &unused, remoteA)) break;
