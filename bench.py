@@ -257,7 +257,6 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     sampler.start()
     ms = timed(solver.step_substep, args.steps)
-    clocks = sampler.summary()
     launches = total(solver.kernel_launches() - launches0)
     prof_ms, prof_n = dev.pcg_profile_read()
     solve_ms, solve_n = dev.pcg_profile_solves()
@@ -276,6 +275,7 @@ def run_ours(args, rank, world, local_rank):
     dense_ms = timed(solver.step_substep, args.steps)
     dprof_ms, dprof_n = dev.pcg_profile_read()
     dsolve_ms, dsolve_n = dev.pcg_profile_solves()
+    clocks = sampler.summary()  # sampled across both timed regions (active-tile walk and dense walk)
     dev.pcg_profile(False)
     dev.pcg_set_dense(False)
     solver.step_substep()
@@ -322,6 +322,9 @@ def run_ours(args, rank, world, local_rank):
                "what": "per step: fs2d_upload_particles from pinned host buffers, FlipSolver::stepSubstep, fs2d_download_particles"
                        + (" (every rank moves the particles of its slab; bytes summed over ranks)" if world > 1 else "")}
 
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     # ---- roofline of the dominant kernel, pcgSolveKernel: ONE cooperative launch per PCG solve runs all iterations
