@@ -39,7 +39,7 @@ class Params(C.Structure):
         ("parameter_handling", C.c_int32), ("viscosity_enabled", C.c_int32),
         ("convergence_threads", C.c_int32), ("device", C.c_int32), ("viscosity_property", C.c_int32),
         ("temperature_property", C.c_int32), ("concentration_property", C.c_int32),
-        ("fuel_property", C.c_int32), ("test_property", C.c_int32), ("reserved0", C.c_int32),
+        ("fuel_property", C.c_int32), ("test_property", C.c_int32), ("heavy_viscosity", C.c_int32),
         ("dx", C.c_double), ("fluid_density", C.c_double), ("project_tolerance", C.c_double),
         ("gravity_x", C.c_float), ("gravity_y", C.c_float), ("pic_ratio", C.c_float),
         ("particle_scale", C.c_float), ("ambient_temperature", C.c_float),

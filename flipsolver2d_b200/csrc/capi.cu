@@ -192,6 +192,7 @@ void freeAll(Ctx *c)
     slabRelease(c);
     if (c->heap) cudaFree(c->heap);  // every dense array lives inside the heap
     if (c->viscScalars) cudaFree(c->viscScalars);
+    if (c->heavyBuf) cudaFree(c->heavyBuf);
     if (c->bfsQueue) cudaFree(c->bfsQueue);
     if (c->p2gTileList) cudaFree(c->p2gTileList);
     if (c->bfsCtl) cudaFree(c->bfsCtl);

@@ -198,6 +198,7 @@ struct fs2d_context
     int *p2gTileList = nullptr;       // [0] = count, [1..] = tiles with particles in reach (transfer.cu), allocated on first use
     int32_t *bfsQueue = nullptr;      // level-set BFS: cells in layer order (one slot per cell), allocated on first use
     unsigned int *bfsCtl = nullptr;   // level-set BFS: [0] = queue tail
+    void *heavyBuf = nullptr;         // heavy viscosity model: diag, x, r, p, tmp, z over all U and V samples + corner viscosities
     void *viscScalars = nullptr;      // device scalars of the viscosity CG (viscosity.cu), allocated on first use
     unsigned long long *mgTimeline = nullptr;  // debug (FS2D_MG_DEBUG & 8): globaltimer stamps of the slab PCG kernels
     int traceCapacity = 0;

@@ -25,6 +25,7 @@
 #include <cfloat>
 #include <cmath>
 
+#include "fs2d_device.cuh"
 #include "fs2d_internal.h"
 
 namespace
@@ -250,6 +251,228 @@ __global__ void __launch_bounds__(NT) viscWriteBackKernel(ViscArgs a, float *__r
         field[i * fieldStride + j] = static_cast<float>(a.x[n] / static_cast<double>(density));
     }
 }
+
+// ------------------------------------------------------------------ HeavyViscosityModel (viscositymodel.cpp:164-470)
+// One coupled system over all U and all V samples (n = (I+1)J + I(J+1) unknowns, U block first). getMatrix accumulates
+// (+=) a non-symmetric matrix; Eigen's ConjugateGradient<.., Upper> reads the diagonal and the strict upper triangle and
+// mirrors it, so the operator every solve sees is S = D + triu(A) + triu(A)^T. With
+//     T(a,b) = scaleTwoDt * viscosity.getAt(a,b)                 scaleTwoDt = 2 dt / dx^2      (float arithmetic)
+//     C(a,b) = scaleTwoDx * viscosity.interpolateAt(a-1/2, b-1/2) scaleTwoDx = dt / (2 dx^2)
+// and uval / vval = "the sample exists", the strict upper entries are (viscositymodel.cpp:232-385)
+//   row U(i,j): U(i+1,j): -T(i,j) | if U(i,j+1),V(i,j+1),V(i-1,j+1) exist: U(i,j+1): -C(i,j+1), V(i,j+1): -C(i,j+1),
+//               V(i-1,j+1): +C(i,j+1) | if U(i,j-1),V(i,j),V(i-1,j) exist: V(i,j): +C(i,j), V(i-1,j): -C(i,j)
+//   row V(i,j): V(i,j+1): -T(i,j) | if U(i+1,j),V(i+1,j-1),V(i+1,j) exist: V(i+1,j): -C(i+1,j)
+// (every V-row entry that points into the U block -- including the one the reference addresses with a V index,
+// :364,377-379 -- lies below the diagonal and is never read). The diagonal takes every += in code order. The formulas
+// below were checked entry by entry against a scipy assembly of the reference's loops, which in turn reproduces the
+// oracle's result bit for bit (tests/test_stages_gpu.py::test_heavy_viscosity_stage).
+struct HeavyArgs
+{
+    const float *mu;       // viscosity grid (I x J, OOB_EXTEND, sample offset 1/2)
+    const float *corner;   // C(a,b), (I+2) x (J+2)
+    int I, J;
+    long long NU, n;
+    float s2dt, rho;
+    double *diag, *x, *r, *p, *tmp, *z;
+    double *partials;
+    ViscScalars *sc;
+    long long maxIters;
+};
+
+__device__ __forceinline__ bool uval(const HeavyArgs &a, int i, int j) { return i >= 0 && i <= a.I && j >= 0 && j < a.J; }
+__device__ __forceinline__ bool vval(const HeavyArgs &a, int i, int j) { return i >= 0 && i < a.I && j >= 0 && j <= a.J; }
+__device__ __forceinline__ double heavyT(const HeavyArgs &a, int i, int j)
+{
+    i = i < 0 ? 0 : (i > a.I - 1 ? a.I - 1 : i);
+    j = j < 0 ? 0 : (j > a.J - 1 ? a.J - 1 : j);
+    return static_cast<double>(__fmul_rn(a.s2dt, a.mu[static_cast<long long>(i) * a.J + j]));
+}
+__device__ __forceinline__ double heavyC(const HeavyArgs &a, int i, int j) { return static_cast<double>(a.corner[static_cast<long long>(i) * (a.J + 2) + j]); }
+
+__global__ void __launch_bounds__(NT) heavyCornerKernel(GridView visc, int I, int J, float s2dx, float *__restrict__ corner)
+{
+    const long long t = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    if (t >= static_cast<long long>(I + 2) * (J + 2)) return;
+    const int a = static_cast<int>(t / (J + 2)), b = static_cast<int>(t - static_cast<long long>(a) * (J + 2));
+    corner[t] = __fmul_rn(s2dx, gridLerp(visc, __fsub_rn(static_cast<float>(a), 0.5f), __fsub_rn(static_cast<float>(b), 0.5f)));
+}
+
+__device__ __forceinline__ double heavyDiag(const HeavyArgs &a, long long row)
+{
+    double d = static_cast<double>(a.rho);
+    if (row < a.NU)
+    {
+        const int i = static_cast<int>(row / a.J), j = static_cast<int>(row - static_cast<long long>(i) * a.J);
+        if (uval(a, i - 1, j)) d += heavyT(a, i - 1, j);
+        if (uval(a, i + 1, j)) d += heavyT(a, i, j);
+        if (uval(a, i, j - 1) && vval(a, i, j) && vval(a, i - 1, j)) d += heavyC(a, i, j);
+        if (uval(a, i, j + 1) && vval(a, i, j + 1) && vval(a, i - 1, j + 1)) d += heavyC(a, i, j + 1);
+    }
+    else
+    {
+        const long long m = row - a.NU;
+        const int i = static_cast<int>(m / (a.J + 1)), j = static_cast<int>(m - static_cast<long long>(i) * (a.J + 1));
+        if (vval(a, i, j - 1)) d += heavyT(a, i, j - 1);
+        if (vval(a, i, j + 1)) d += heavyT(a, i, j);
+        if (uval(a, i, j) && uval(a, i, j - 1) && vval(a, i - 1, j)) d += heavyC(a, i, j);
+        if (uval(a, i + 1, j) && vval(a, i + 1, j - 1) && vval(a, i + 1, j)) d += heavyC(a, i + 1, j);
+    }
+    return d;
+}
+
+// (S v)[row]: diagonal, the row's own strict upper entries, and the entries other rows hold in this column
+__device__ __forceinline__ double heavyApplyRow(const HeavyArgs &a, const double *__restrict__ v, long long row)
+{
+    const long long J = a.J, J1 = a.J + 1;
+    const double *vU = v, *vV = v + a.NU;
+    double y = a.diag[row] * v[row];
+    if (row < a.NU)
+    {
+        const int i = static_cast<int>(row / J), j = static_cast<int>(row - static_cast<long long>(i) * J);
+        const bool jm = uval(a, i, j - 1) && vval(a, i, j) && vval(a, i - 1, j);
+        const bool jp = uval(a, i, j + 1) && vval(a, i, j + 1) && vval(a, i - 1, j + 1);
+        if (uval(a, i + 1, j)) y += -heavyT(a, i, j) * vU[(i + 1) * J + j];
+        if (jp)
+        {
+            const double c = heavyC(a, i, j + 1);
+            y += -c * vU[i * J + j + 1];
+            y += -c * vV[i * J1 + j + 1];
+            y += c * vV[(i - 1) * J1 + j + 1];
+        }
+        if (jm)
+        {
+            const double c = heavyC(a, i, j);
+            y += c * vV[i * J1 + j];
+            y += -c * vV[(i - 1) * J1 + j];
+        }
+        if (uval(a, i - 1, j)) y += -heavyT(a, i - 1, j) * vU[(i - 1) * J + j];  // U(i-1,j) -> U(i,j)
+        if (jm) y += -heavyC(a, i, j) * vU[i * J + j - 1];                       // U(i,j-1) -> U(i,j), same existence test
+    }
+    else
+    {
+        const long long m = row - a.NU;
+        const int i = static_cast<int>(m / J1), j = static_cast<int>(m - static_cast<long long>(i) * J1);
+        if (vval(a, i, j + 1)) y += -heavyT(a, i, j) * vV[i * J1 + j + 1];
+        if (uval(a, i + 1, j) && vval(a, i + 1, j - 1) && vval(a, i + 1, j)) y += -heavyC(a, i + 1, j) * vV[(i + 1) * J1 + j];
+        if (vval(a, i, j - 1)) y += -heavyT(a, i, j - 1) * vV[i * J1 + j - 1];                                   // V(i,j-1)
+        if (vval(a, i - 1, j) && uval(a, i, j) && vval(a, i, j - 1)) y += -heavyC(a, i, j) * vV[(i - 1) * J1 + j];  // V(i-1,j)
+        if (uval(a, i, j) && uval(a, i, j - 1) && vval(a, i - 1, j)) y += heavyC(a, i, j) * vU[i * J + j];                    // U(i,j)
+        if (uval(a, i + 1, j) && uval(a, i + 1, j - 1) && vval(a, i + 1, j)) y += -heavyC(a, i + 1, j) * vU[(i + 1) * J + j]; // U(i+1,j)
+        if (uval(a, i, j - 1) && uval(a, i, j) && vval(a, i - 1, j)) y += -heavyC(a, i, j) * vU[i * J + j - 1];               // U(i,j-1)
+        if (uval(a, i + 1, j - 1) && uval(a, i + 1, j) && vval(a, i + 1, j)) y += heavyC(a, i + 1, j) * vU[(i + 1) * J + j - 1];  // U(i+1,j-1)
+    }
+    return y;
+}
+
+// getRhs (viscositymodel.cpp:400-432): rhs = density * velocity (float product) for every U and V sample; then the
+// start of Eigen's conjugate_gradient as in viscInitKernel
+__global__ void __launch_bounds__(NT) heavyInitKernel(HeavyArgs a, const float *__restrict__ U, const float *__restrict__ V)
+{
+    __shared__ double scratch[16];
+    __shared__ int isLast;
+    double s0 = 0.0, s1 = 0.0;
+    for (long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x; n < a.n; n += static_cast<long long>(gridDim.x) * NT)
+    {
+        const double b = static_cast<double>(__fmul_rn(a.rho, n < a.NU ? U[n] : V[n - a.NU]));
+        const double d = heavyDiag(a, n);
+        a.diag[n] = d;
+        a.x[n] = 0.0;
+        a.r[n] = b;
+        const double p = b * (1.0 / d);
+        a.p[n] = p;
+        s0 += b * b;
+        s1 += b * p;
+    }
+    if (!gridSum2(s0, s1, a.partials, &a.sc->ticket, scratch, &isLast)) return;
+    if (threadIdx.x == 0)
+    {
+        ViscScalars *sc = a.sc;
+        sc->rhsNorm2 = s0;
+        sc->threshold = fmax(1e-4 * 1e-4 * s0, DBL_MIN);
+        sc->absNew = s1;
+        sc->resNorm2 = s0;
+        sc->alpha = sc->beta = sc->pAp = 0.0;
+        sc->iter = 0;
+        sc->applied = 0;
+        sc->done = (s0 == 0.0 || s0 < sc->threshold) ? 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(NT) heavyApplyKernel(HeavyArgs a)
+{
+    __shared__ double scratch[16];
+    __shared__ int isLast;
+    if (a.sc->done) return;
+    double s0 = 0.0, s1 = 0.0;
+    for (long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x; n < a.n; n += static_cast<long long>(gridDim.x) * NT)
+    {
+        const double y = heavyApplyRow(a, a.p, n);
+        a.tmp[n] = y;
+        s0 += a.p[n] * y;
+    }
+    if (!gridSum2(s0, s1, a.partials, &a.sc->ticket, scratch, &isLast)) return;
+    if (threadIdx.x == 0)
+    {
+        a.sc->pAp = s0;
+        a.sc->alpha = a.sc->absNew / s0;
+    }
+}
+
+__global__ void __launch_bounds__(NT) heavyUpdateKernel(HeavyArgs a)
+{
+    __shared__ double scratch[16];
+    __shared__ int isLast;
+    if (a.sc->done) return;
+    const double alpha = a.sc->alpha;
+    double s0 = 0.0, s1 = 0.0;
+    for (long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x; n < a.n; n += static_cast<long long>(gridDim.x) * NT)
+    {
+        a.x[n] += alpha * a.p[n];
+        const double r = a.r[n] - alpha * a.tmp[n];
+        a.r[n] = r;
+        const double z = r * (1.0 / a.diag[n]);
+        a.z[n] = z;
+        s0 += r * r;
+        s1 += r * z;
+    }
+    if (!gridSum2(s0, s1, a.partials, &a.sc->ticket, scratch, &isLast)) return;
+    if (threadIdx.x == 0)
+    {
+        ViscScalars *sc = a.sc;
+        sc->resNorm2 = s0;
+        sc->applied++;
+        if (s0 < sc->threshold)
+            sc->done = 1;
+        else
+        {
+            sc->beta = s1 / sc->absNew;
+            sc->absNew = s1;
+            sc->iter++;
+            if (sc->iter >= a.maxIters) sc->done = 1;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(NT) heavyDirectionKernel(HeavyArgs a)
+{
+    if (a.sc->done) return;
+    const double beta = a.sc->beta;
+    for (long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x; n < a.n; n += static_cast<long long>(gridDim.x) * NT)
+        a.p[n] = a.z[n] + beta * a.p[n];
+}
+
+// applyResult (viscositymodel.cpp:434-470): every U and V sample takes the solution (no division by the density)
+__global__ void __launch_bounds__(NT) heavyWriteBackKernel(HeavyArgs a, float *__restrict__ U, float *__restrict__ V)
+{
+    for (long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x; n < a.n; n += static_cast<long long>(gridDim.x) * NT)
+    {
+        const float v = static_cast<float>(a.x[n]);
+        if (n < a.NU)
+            U[n] = v;
+        else
+            V[n - a.NU] = v;
+    }
+}
 }  // namespace
 
 // One Eigen-style solve for `field` (U: stride J; V: stride J + 1). *iters = Eigen's iterations(); returns
@@ -281,6 +504,75 @@ static int viscSolve(Ctx *ctx, ViscArgs &a, float *field, int stride, float dens
     return FS2D_OK;
 }
 
+GridView viscosityView(const Ctx *c);
+
+// HeavyViscosityModel::apply (viscositymodel.cpp:164-200)
+static int gridViscosityHeavy(Ctx *ctx, int *iters)
+{
+    cudaStream_t st = ctx->stream;
+    const long long n = ctx->NU + ctx->NV;
+    const long long cornerCount = static_cast<long long>(ctx->I + 2) * (ctx->J + 2);
+    if (!ctx->heavyBuf)
+    {
+        const size_t bytes = sizeof(double) * 6 * static_cast<size_t>(n) + sizeof(float) * static_cast<size_t>(cornerCount) + 256;
+        FS2D_CUDA(cudaMalloc(&ctx->heavyBuf, bytes));
+    }
+    if (!ctx->viscScalars) FS2D_CUDA(cudaMalloc(&ctx->viscScalars, 256));
+    FS2D_CUDA(cudaMemsetAsync(ctx->viscScalars, 0, 256, st));
+    double *base = static_cast<double *>(ctx->heavyBuf);
+    HeavyArgs a;
+    a.mu = ctx->viscosity;
+    a.I = ctx->I;
+    a.J = ctx->J;
+    a.NU = ctx->NU;
+    a.n = n;
+    a.diag = base;
+    a.x = base + n;
+    a.r = base + 2 * n;
+    a.p = base + 3 * n;
+    a.tmp = base + 4 * n;
+    a.z = base + 5 * n;
+    float *corner = reinterpret_cast<float *>(base + 6 * n);
+    a.corner = corner;
+    a.partials = ctx->partials;
+    a.sc = static_cast<ViscScalars *>(ctx->viscScalars);
+    a.maxIters = 2 * n;
+    // apply(..., float dt, float dx, float density): scaleTwoDt = 2*dt / (dx*dx), scaleTwoDx = dt / (2*dx*dx) in float
+    const float dt = ctx->stepDt, dx = static_cast<float>(ctx->p.dx);
+    a.rho = static_cast<float>(ctx->p.fluid_density);
+    a.s2dt = 2 * dt / (dx * dx);
+    const float s2dx = dt / (2 * dx * dx);
+    const int blocks = std::min<long long>(divUp(n, NT), static_cast<long long>(ctx->smCount) * 8);
+    heavyCornerKernel<<<divUp(cornerCount, NT), NT, 0, st>>>(viscosityView(ctx), ctx->I, ctx->J, s2dx, corner);
+    heavyInitKernel<<<blocks, NT, 0, st>>>(a, ctx->U, ctx->V);
+    ctx->launches += 2;
+    ViscScalars sc;
+    for (;;)
+    {
+        for (int k = 0; k < 8; k++)
+        {
+            heavyApplyKernel<<<blocks, NT, 0, st>>>(a);
+            heavyUpdateKernel<<<blocks, NT, 0, st>>>(a);
+            heavyDirectionKernel<<<blocks, NT, 0, st>>>(a);
+        }
+        ctx->launches += 24;
+        FS2D_CUDA(cudaGetLastError());
+        FS2D_CUDA(fs2dCopyToHost(ctx, &sc, a.sc, sizeof(sc)));
+        if (sc.done) break;
+    }
+    const double err = sc.rhsNorm2 > 0.0 ? std::sqrt(sc.resNorm2 / sc.rhsNorm2) : 0.0;
+    if (sc.rhsNorm2 > 0.0 && !(err <= 1e-4))
+    {
+        if (iters) *iters = -1;  // "Viscosity solver U solving failed!": nothing is applied
+        return FS2D_OK;
+    }
+    heavyWriteBackKernel<<<blocks, NT, 0, st>>>(a, ctx->U, ctx->V);
+    ctx->launches++;
+    FS2D_CUDA(cudaGetLastError());
+    if (iters) *iters = sc.iter;
+    return FS2D_OK;
+}
+
 int gridViscosity(Ctx *ctx, int *iters)
 {
     if (ctx->slab.enabled && ctx->slab.world > 1)
@@ -288,6 +580,7 @@ int gridViscosity(Ctx *ctx, int *iters)
         ctx->lastError = "applyViscosity is not slab-aware yet (only FS2D_SIM_LIQUID without viscosity runs on several GPUs)";
         return FS2D_ERR_STATE;
     }
+    if (ctx->p.heavy_viscosity) return gridViscosityHeavy(ctx, iters);
     if (!ctx->viscScalars) FS2D_CUDA(cudaMalloc(&ctx->viscScalars, 256));
     FS2D_CUDA(cudaMemsetAsync(ctx->viscScalars, 0, 256, ctx->stream));
     ViscArgs a;

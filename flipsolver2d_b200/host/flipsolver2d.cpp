@@ -57,7 +57,7 @@ FlipSolver::FlipSolver(const FlipSolverParameters *p)
 {
     m_testValuePropertyIndex = m_markerParticles.addParticleProperty<float>();
     m_projectTolerance = m_viscosityEnabled ? 1e-6 : 1e-2;  // flipsolver2d.cpp:73
-    if (p->useHeavyViscosity) std::cout << "heavy viscosity model is not available on the GPU path; using the light model" << std::endl;
+    m_useHeavyViscosity = p->useHeavyViscosity;  // flipsolver2d.cpp:77-85
 }
 
 FlipSolver::~FlipSolver()
@@ -88,6 +88,7 @@ fs2d_params FlipSolver::deviceParameters() const
     q.sim_type = m_simulationMethod;
     q.parameter_handling = m_parameterHandlingMethod;
     q.viscosity_enabled = m_viscosityEnabled ? 1 : 0;
+    q.heavy_viscosity = m_useHeavyViscosity ? 1 : 0;
     q.convergence_threads = g_convergenceThreads;
     q.device = g_device;
     q.viscosity_property = m_viscosityPropertyIndex == static_cast<size_t>(-1) ? -1 : static_cast<int32_t>(m_viscosityPropertyIndex);

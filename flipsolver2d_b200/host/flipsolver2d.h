@@ -288,6 +288,7 @@ protected:
     float m_domainSizeI, m_domainSizeJ, m_sceneScale;
     double m_projectTolerance;
     bool m_viscosityEnabled;
+    bool m_useHeavyViscosity = false;
     SimulationMethod m_simulationMethod;
     ParameterHandlingMethod m_parameterHandlingMethod;
     SolverStats m_stats;

@@ -105,7 +105,7 @@ typedef struct fs2d_params
     int32_t concentration_property;
     int32_t fuel_property;
     int32_t test_property;
-    int32_t reserved0;
+    int32_t heavy_viscosity;      /* useHeavyViscosity (flipsolver2d.cpp:77-85): HeavyViscosityModel instead of the light one */
     double dx;
     double fluid_density;
     double project_tolerance;     /* m_projectTolerance (flipsolver2d.cpp:73) */
@@ -253,7 +253,7 @@ int fs2d_pressure_rhs(fs2d_handle h);                          /* calcPressureRh
 int fs2d_apply_pressure(fs2d_handle h);                        /* applyPressuresToVelocityField :1106-1193 <- FS2D_GRID_PRESSURE */
 int fs2d_project(fs2d_handle h, int *iters);                   /* project :93-126 */
 int fs2d_velocity_from_solids(fs2d_handle h);                  /* updateVelocityFromSolids :1077-1104 */
-int fs2d_apply_viscosity(fs2d_handle h, int *iters);           /* LightViscosityModel::apply, viscositymodel.cpp:4-162 */
+int fs2d_apply_viscosity(fs2d_handle h, int *iters);           /* Light / HeavyViscosityModel::apply, viscositymodel.cpp:4-162,164-470 */
 int fs2d_particle_update(fs2d_handle h);                       /* particleUpdate :361-388 (+smoke decay, fire combustion) */
 int fs2d_count_particles(fs2d_handle h);                       /* countParticles :1021-1051 */
 /* reseedParticles (flipsolver2d.cpp:627-680; nbflip nbflipsolver.cpp:118-201): the RNG stream

@@ -75,12 +75,14 @@ def test_smoke_scene_steps(ref_mod, scene_dir):
     s.close()
 
 
-@pytest.mark.parametrize("sim,visc", [("nbflip", False), ("nbflip", True), ("flip", True)])
+@pytest.mark.parametrize("sim,visc", [("nbflip", False), ("nbflip", True), ("flip", True), ("flip", "heavy")])
 def test_nbflip_and_viscous_frames_match_reference(ref_mod, scene_dir, sim, visc):
     """BASELINE config 4 at test size: narrow-band FLIP (semi-Lagrangian grids, band prune / combine) and the implicit
     viscosity stage with the re-projection that follows it, frame loop against the reference's own stepFrame."""
-    scene = _low_density(scenes.dam_break(64, sim, viscosity_enabled=visc))
-    path = scene_dir / ("hostgpu_%s_%d.json" % (sim, int(visc)))
+    scene = _low_density(scenes.dam_break(64, sim, viscosity_enabled=bool(visc)))
+    if visc == "heavy":
+        scene["settings"]["heavyViscosity"] = True  # HeavyViscosityModel (viscositymodel.cpp:164-470) through JsonSceneReader
+    path = scene_dir / ("hostgpu_%s_%s.json" % (sim, visc))
     s = H.make_ref(ref_mod, scene, path)
     h = host_api.Solver(str(path), convergence_threads=s.threads)
     for f in range(3):

@@ -328,3 +328,110 @@ def test_viscosity_stage(ref_mod, scene_dir, sim, res, frames):
     assert np.array_equal(vd.reshape(I, J + 1)[:, J], v0.reshape(I, J + 1)[:, J])  # nor V's last column
     d.close()
     s.close()
+
+
+def _heavy_viscosity_numpy(visc, u, v, dt, dx, rho):
+    """scipy restatement of HeavyViscosityModel::getMatrix (viscositymodel.cpp:202-398, including the column the
+    reference addresses with a V index) + Eigen's Upper view + conjugate_gradient; returns (U, V, iterations())."""
+    import scipy.sparse as sp
+    f32 = np.float32
+    I, J = visc.shape
+    NU, NV = (I + 1) * J, I * (J + 1)
+    dt, dx, rho = f32(dt), f32(dx), f32(rho)
+    s2dt, s2dx = f32(f32(2) * dt / (dx * dx)), f32(dt / (f32(2) * dx * dx))
+
+    def get_at(a, b):
+        return visc[np.clip(a, 0, I - 1), np.clip(b, 0, J - 1)]
+
+    def lerp_at(x, y):  # Grid2d::lerp (grid2d.h:187-216) with the sample offset (1/2, 1/2) of the viscosity grid
+        i = np.clip((x + f32(0.5)).astype(f32), f32(0), f32(I - 1)).astype(f32)
+        j = np.clip((y + f32(0.5)).astype(f32), f32(0), f32(J - 1)).astype(f32)
+        ci, cj = np.floor(i).astype(np.int64), np.floor(j).astype(np.int64)
+        fi, fj = (i - np.floor(i)).astype(f32), (j - np.floor(j)).astype(f32)
+        i2, j2 = np.where(fi >= 0.5, ci + 1, ci - 1), np.where(fj >= 0.5, cj + 1, cj - 1)
+        il = np.where(fi < 0.5, f32(0.5) - fi, fi - f32(0.5)).astype(f32)
+        jl = np.where(fj < 0.5, f32(0.5) - fj, fj - f32(0.5)).astype(f32)
+        mix = lambda a, b, f: (a * (f32(1) - f) + b * f).astype(f32)
+        return mix(mix(get_at(ci, cj), get_at(i2, cj), il), mix(get_at(ci, j2), get_at(i2, j2), il), jl)
+
+    uidx, vidx = (lambda i, j: i * J + j), (lambda i, j: NU + i * (J + 1) + j)
+    uval = lambda i, j: (i >= 0) & (i <= I) & (j >= 0) & (j < J)
+    vval = lambda i, j: (i >= 0) & (i < I) & (j >= 0) & (j <= J)
+    rows, cols, vals = [], [], []
+
+    def add(r, c, val, m):
+        rows.append(r[m]); cols.append(c[m]); vals.append(val[m].astype(np.float64))
+
+    ii, jj = [a.ravel() for a in np.meshgrid(np.arange(I + 1), np.arange(J), indexing="ij")]
+    ur = uidx(ii, jj)
+    add(ur, ur, np.full(ii.shape, rho, f32), np.ones_like(ii, bool))
+    m = uval(ii - 1, jj); t = (s2dt * get_at(ii - 1, jj)).astype(f32); add(ur, uidx(ii - 1, jj), -t, m); add(ur, ur, t, m)
+    m = uval(ii + 1, jj); t = (s2dt * get_at(ii, jj)).astype(f32); add(ur, uidx(ii + 1, jj), -t, m); add(ur, ur, t, m)
+    m = uval(ii, jj - 1) & vval(ii, jj) & vval(ii - 1, jj)
+    lv = (s2dx * lerp_at(ii.astype(f32) - f32(0.5), jj.astype(f32) - f32(0.5))).astype(f32)
+    add(ur, uidx(ii, jj - 1), -lv, m); add(ur, vidx(ii, jj), lv, m); add(ur, vidx(ii - 1, jj), -lv, m); add(ur, ur, lv, m)
+    m = uval(ii, jj + 1) & vval(ii, jj + 1) & vval(ii - 1, jj + 1)
+    lv = (s2dx * lerp_at(ii.astype(f32) - f32(0.5), jj.astype(f32) + f32(0.5))).astype(f32)
+    add(ur, uidx(ii, jj + 1), -lv, m); add(ur, vidx(ii, jj + 1), -lv, m); add(ur, vidx(ii - 1, jj + 1), lv, m); add(ur, ur, lv, m)
+    ii, jj = [a.ravel() for a in np.meshgrid(np.arange(I), np.arange(J + 1), indexing="ij")]
+    vr = vidx(ii, jj)
+    add(vr, vr, np.full(ii.shape, rho, f32), np.ones_like(ii, bool))
+    m = vval(ii, jj - 1); t = (s2dt * get_at(ii, jj - 1)).astype(f32); add(vr, vidx(ii, jj - 1), -t, m); add(vr, vr, t, m)
+    m = vval(ii, jj + 1); t = (s2dt * get_at(ii, jj)).astype(f32); add(vr, vidx(ii, jj + 1), -t, m); add(vr, vr, t, m)
+    m = uval(ii, jj) & uval(ii, jj - 1) & vval(ii - 1, jj)
+    lv = (s2dx * lerp_at(ii.astype(f32) - f32(0.5), jj.astype(f32) - f32(0.5))).astype(f32)
+    add(vr, uidx(ii, jj), lv, m); add(vr, uidx(ii, jj - 1), -lv, m); add(vr, vidx(ii - 1, jj), -lv, m); add(vr, vr, lv, m)
+    m = uval(ii + 1, jj) & vval(ii + 1, jj - 1) & vval(ii + 1, jj)
+    lv = (s2dx * lerp_at(ii.astype(f32) + f32(0.5), jj.astype(f32) - f32(0.5))).astype(f32)
+    add(vr, uidx(ii + 1, jj), -lv, m); add(vr, (ii + 1) * (J + 1) + (jj - 1), lv, m); add(vr, vidx(ii + 1, jj), -lv, m); add(vr, vr, lv, m)
+    n = NU + NV
+    A = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n)).tocsr()
+    upper, d = sp.triu(A, 1).tocsr(), A.diagonal()
+    apply = lambda x: d * x + upper @ x + upper.T @ x
+    b = np.concatenate([(rho * u.astype(f32)).astype(f32), (rho * v.astype(f32)).astype(f32)]).astype(np.float64)
+    x, r = np.zeros_like(b), b.copy()
+    n2 = float(b @ b)
+    thr = max(1e-4 * 1e-4 * n2, np.finfo(np.float64).tiny)
+    p = r / d
+    abs_new, it = float(r @ p), 0
+    while it < 2 * n:
+        t = apply(p)
+        alpha = abs_new / float(p @ t)
+        x += alpha * p
+        r -= alpha * t
+        if float(r @ r) < thr:
+            break
+        z = r / d
+        abs_old, abs_new = abs_new, float(r @ z)
+        p = z + (abs_new / abs_old) * p
+        it += 1
+    return x[:NU].astype(f32), x[NU:].astype(f32), it
+
+
+@pytest.mark.parametrize("res,frames", [(48, 2), (64, 1)])
+def test_heavy_viscosity_stage(ref_mod, scene_dir, res, frames):
+    """HeavyViscosityModel::apply (viscositymodel.cpp:164-470, `"heavyViscosity": true`): the coupled U+V system as Eigen's
+    Upper view sees it, matrix-free on the device. Against the oracle (reference assembly + Eigen shim: parity unpinned)
+    and against the scipy restatement of the reference's loops, which also gives the iteration count of this one call."""
+    scene = scenes.dam_break(res, "flip", viscosity_enabled=True, fluid_viscosity=10)
+    scene["settings"]["density"] = 0.02
+    scene["settings"]["heavyViscosity"] = True
+    s, d = _pair(ref_mod, scene_dir, scene, "heavy_%d_f%d" % (res, frames), frames, dt=1.0 / 120.0)
+    d.close()
+    d = H.make_device(s, scene, heavy_viscosity=1)
+    H.sync_state(s, d, "flip")
+    I, J = s.I, s.J
+    p = s.params()
+    u0, v0 = s.grid("U").copy(), s.grid("V").copy()
+    un, vn, it_np = _heavy_viscosity_numpy(s.grid("VISCOSITY").reshape(I, J), u0, v0, p["stepDt"], p["dx"], p["fluidDensity"])
+    s.stage("VISCOSITY")
+    it_dev = d.stage_iters("apply_viscosity")
+    ur, vr = s.grid("U"), s.grid("V")
+    ud, vd = d.download("U"), d.download("V")
+    assert H.rel_l2(ur, u0) > 1e-3                      # the stage really changes the field
+    assert np.array_equal(un, ur) and np.array_equal(vn, vr)   # the restatement IS the oracle's result, bit for bit
+    assert it_dev == it_np and it_np > 0, (it_dev, it_np)
+    assert H.rel_l2(ud, ur) < 1e-6, H.rel_l2(ud, ur)
+    assert H.rel_l2(vd, vr) < 1e-6, H.rel_l2(vd, vr)
+    d.close()
+    s.close()
