@@ -435,3 +435,23 @@ def test_heavy_viscosity_stage(ref_mod, scene_dir, res, frames):
     assert H.rel_l2(vd, vr) < 1e-6, H.rel_l2(vd, vr)
     d.close()
     s.close()
+
+
+@pytest.mark.parametrize("model", ["light", "heavy"])
+def test_viscosity_stage_against_golden_vectors(model):
+    """The CUDA viscosity stage on the committed golden inputs (tests/golden/viscosity_systems.npz, produced by the
+    reference's own assembly; no oracle involved at run time)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "viscosity_systems.npz"))
+    I, J = int(g[model + "_I"]), int(g[model + "_J"])
+    d = capi.Device(I, J, dx=float(g[model + "_dx"]), fluid_density=float(g[model + "_density"]), viscosity_enabled=1,
+                    heavy_viscosity=1 if model == "heavy" else 0)
+    d.upload("MATERIAL", g[model + "_material"])
+    d.upload("VISCOSITY", g[model + "_viscosity"])
+    d.upload("U", g[model + "_u0"])
+    d.upload("V", g[model + "_v0"])
+    d.set_step_dt(float(g[model + "_dt"]))
+    assert d.stage_iters("apply_viscosity") > 0
+    assert H.rel_l2(d.download("U"), g[model + "_u1"]) < 1e-6
+    assert H.rel_l2(d.download("V"), g[model + "_v1"]) < 1e-6
+    d.close()
