@@ -280,33 +280,36 @@ def run_ours(args, rank, world, local_rank):
     dev.pcg_set_dense(False)
     solver.step_substep()
 
-    # ---- end to end: particle state crosses PCIe both ways every step
+    # ---- end to end: the particle state crosses PCIe both ways every step, through the packed C-ABI calls (one copy per
+    # direction; lossless: the storage-bin byte travels with the records, tests/test_substep_gpu.py proves the round trip
+    # is the identity on the solver state)
     P = particles
     K = 2
+    rec = 16 + 4 * K + 1
     cap = int(P * 1.25) + 1024
     if world > 1:
         cap = int(P * 1.5) + 2_000_000  # slabs: particles migrate between ranks (a few rows per step at CFL 5)
     if args.no_e2e:
         cap = 16
-    pos = torch.empty((cap, 2), dtype=torch.float32).pin_memory()
-    vel = torch.empty((cap, 2), dtype=torch.float32).pin_memory()
-    props = torch.empty((K * cap,), dtype=torch.float32).pin_memory()
+    hostbuf = torch.empty((cap * rec,), dtype=torch.uint8).pin_memory()
     L = capi.lib()
-    state = {"n": P, "h2d": 0, "d2h": 0}
+    import ctypes
+    state = {"n": P, "h2d": 0, "d2h": 0, "n_min": P, "n_max": P}
 
     def download():
-        n = int(L.fs2d_particle_count(dev.h))
-        assert n <= cap
-        rc = L.fs2d_download_particles(dev.h, pos.data_ptr(), vel.data_ptr(), props.data_ptr())
-        assert rc == 0
-        state["n"] = n
-        state["d2h"] += n * (16 + 4 * K)
+        n = ctypes.c_int64(0)
+        rc = L.fs2d_download_particles_packed(dev.h, hostbuf.data_ptr(), hostbuf.numel(), ctypes.byref(n))
+        assert rc == 0, dev.L.fs2d_last_error(dev.h)
+        state["n"] = n.value
+        state["n_min"] = min(state["n_min"], n.value)
+        state["n_max"] = max(state["n_max"], n.value)
+        state["d2h"] += n.value * rec
 
     def e2e_step():
         n = state["n"]
-        rc = L.fs2d_upload_particles(dev.h, n, pos.data_ptr(), vel.data_ptr(), props.data_ptr())
-        assert rc == 0
-        state["h2d"] += n * (16 + 4 * K)
+        rc = L.fs2d_upload_particles_packed(dev.h, hostbuf.data_ptr(), n)
+        assert rc == 0, dev.L.fs2d_last_error(dev.h)
+        state["h2d"] += n * rec
         solver.step_substep()
         download()
 
@@ -315,11 +318,14 @@ def run_ours(args, rank, world, local_rank):
         download()
         e2e_step()  # warm-up of the path
         state["h2d"] = state["d2h"] = 0
+        state["n_min"] = state["n_max"] = n_start = state["n"]
         e2e_steps = args.steps
         e2e_ms = timed(e2e_step, e2e_steps)
         e2e = {"value": e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": total(state["h2d"]) // e2e_steps,
-               "d2h_bytes_per_step": total(state["d2h"]) // e2e_steps,
-               "what": "per step: fs2d_upload_particles from pinned host buffers, FlipSolver::stepSubstep, fs2d_download_particles"
+               "d2h_bytes_per_step": total(state["d2h"]) // e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+               "particles_start": total(n_start), "particles_end": total(state["n"]), "bytes_per_particle": rec,
+               "what": "per step: fs2d_upload_particles_packed from a pinned host buffer, FlipSolver::stepSubstep, "
+                       "fs2d_download_particles_packed into it (positions, velocities, %d property columns, storage-bin byte)" % K
                        + (" (every rank moves the particles of its slab; bytes summed over ranks)" if world > 1 else "")}
 
     if world > 1:

@@ -99,6 +99,9 @@ def lib():
         "fs2d_upload_particles": (i32, [H, i64, vp, vp, vp]),
         "fs2d_download_particles": (i32, [H, vp, vp, vp]),
         "fs2d_append_particles": (i32, [H, i64, vp, vp, vp]),
+        "fs2d_packed_particle_bytes": (C.c_size_t, [H, i64]),
+        "fs2d_download_particles_packed": (i32, [H, vp, C.c_size_t, C.POINTER(i64)]),
+        "fs2d_upload_particles_packed": (i32, [H, vp, i64]),
         "fs2d_set_particle_storage_bins": (i32, [H, vp]),
         "fs2d_get_particle_storage_bins": (i32, [H, vp]),
         "fs2d_pcg_solve": (i32, [H, vp, vp, i32, f64, C.POINTER(i32)]),
@@ -142,6 +145,8 @@ def lib():
         "fs2d_substep": (i32, [H, f32, vp, vp]),
         "fs2d_pcg_set_stepwise": (i32, [H, i32]),
         "fs2d_pcg_profile_solves": (i32, [H, vp, vp]),
+        "fs2d_pcg_set_grid_limit": (i32, [H, i32]),
+        "fs2d_pcg_set_tile_kernels": (i32, [H, i32]),
         "fs2d_slab_configure": (i32, [H, i32, i32, i32]),
         "fs2d_slab_configure_rows": (i32, [H, i32, i32, i32, vp]),
         "fs2d_slab_export": (i32, [H, vp]),
@@ -277,6 +282,18 @@ class Device:
         self._ck(self.L.fs2d_download_particles(self.h, _p(pos), _p(vel), _p(props)), "download_particles")
         return pos, vel, props
 
+    def download_packed(self, buf=None):
+        """Packed particle state (pos | vel | props | storage byte) into `buf` (uint8 numpy array; allocated when
+        None). Returns (buf, count)."""
+        if buf is None:
+            buf = np.zeros(int(self.L.fs2d_packed_particle_bytes(self.h, self.particle_count())) + 64, np.uint8)
+        n = C.c_int64(0)
+        self._ck(self.L.fs2d_download_particles_packed(self.h, _p(buf), buf.nbytes, C.byref(n)), "download_packed")
+        return buf, n.value
+
+    def upload_packed(self, buf, count):
+        self._ck(self.L.fs2d_upload_particles_packed(self.h, _p(buf), int(count)), "upload_packed")
+
     # ---- PCG
     def pcg_solve(self, rhs, iter_limit, tol):
         rhs = np.ascontiguousarray(rhs, np.float64)
@@ -312,6 +329,12 @@ class Device:
 
     def pcg_set_stepwise(self, stepwise=True):
         self._ck(self.L.fs2d_pcg_set_stepwise(self.h, 1 if stepwise else 0), "pcg_set_stepwise")
+
+    def pcg_set_grid_limit(self, max_ctas=0):
+        self._ck(self.L.fs2d_pcg_set_grid_limit(self.h, int(max_ctas)), "pcg_set_grid_limit")
+
+    def pcg_set_tile_kernels(self, tile=True):
+        self._ck(self.L.fs2d_pcg_set_tile_kernels(self.h, 1 if tile else 0), "pcg_set_tile_kernels")
 
     def pcg_profile_solves(self):
         ms = np.zeros(1, np.float64)

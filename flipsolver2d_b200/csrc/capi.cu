@@ -197,7 +197,7 @@ void freeAll(Ctx *c)
     if (c->p2gTileList) cudaFree(c->p2gTileList);
     if (c->bfsCtl) cudaFree(c->bfsCtl);
     if (c->solveMaps) std::free(c->solveMaps);
-    void *ptrs[] = {c->rangeLast, c->dead, c->perm, c->obstacleFriction, c->sources, c->reseedUniform};
+    void *ptrs[] = {c->rangeLast, c->dead, c->perm, c->obstacleFriction, c->sources, c->reseedUniform, c->stage};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (int b = 0; b < 2; b++)
@@ -483,6 +483,88 @@ int fs2d_download_particles(fs2d_handle ctx, float *host_pos, float *host_vel, f
     return FS2D_OK;
 }
 
+// ---- packed particle state: ONE copy per direction, lossless (the storage-bin byte travels with the record)
+static int stageReserve(Ctx *ctx, size_t bytes)
+{
+    if (bytes <= ctx->stageBytes) return FS2D_OK;
+    FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->stage) cudaFree(ctx->stage);
+    ctx->stage = nullptr;
+    ctx->stageBytes = 0;
+    const size_t want = bytes + bytes / 4 + 4096;
+    FS2D_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->stage), want));
+    ctx->stageBytes = want;
+    return FS2D_OK;
+}
+
+size_t fs2d_packed_particle_bytes(fs2d_handle ctx, int64_t count)
+{
+    if (!ctx || count < 0) return 0;
+    return static_cast<size_t>(count) * (16u + 4u * static_cast<size_t>(ctx->p.num_properties) + 1u);
+}
+
+int fs2d_download_particles_packed(fs2d_handle ctx, void *host_buf, size_t capacity_bytes, int64_t *count)
+{
+    if (!ctx || !host_buf || !count) return FS2D_ERR_ARG;
+    int64_t alive = 0;
+    FS2D_TRY(particlesAliveCount(ctx, &alive));
+    const bool slab = ctx->slab.enabled && ctx->slab.world > 1;
+    if (alive != ctx->count - ctx->slab.ghostCount || !ctx->sorted) FS2D_TRY(particlesSort(ctx));
+    const int64_t first = slab ? ctx->slab.ownedBegin : 0;
+    const int64_t n = slab ? ctx->slab.ownedEnd - ctx->slab.ownedBegin : ctx->count;
+    *count = n;
+    const size_t bytes = fs2d_packed_particle_bytes(ctx, n);
+    if (bytes > capacity_bytes)
+    {
+        ctx->lastError = "fs2d_download_particles_packed: host buffer too small";
+        return FS2D_ERR_ARG;
+    }
+    if (n == 0) return FS2D_OK;
+    FS2D_TRY(stageReserve(ctx, bytes));
+    const ParticleBuffers &b = ctx->pb[ctx->cur];
+    const int K = ctx->p.num_properties;
+    cudaStream_t st = ctx->stream;
+    unsigned char *d = ctx->stage;
+    FS2D_CUDA(cudaMemcpyAsync(d, b.pos + first, 8u * n, cudaMemcpyDeviceToDevice, st));
+    FS2D_CUDA(cudaMemcpyAsync(d + 8u * n, b.vel + first, 8u * n, cudaMemcpyDeviceToDevice, st));
+    for (int k = 0; k < K; k++)
+        FS2D_CUDA(cudaMemcpyAsync(d + (16u + 4u * k) * n, b.props + static_cast<int64_t>(k) * b.capacity + first, 4u * n,
+                                  cudaMemcpyDeviceToDevice, st));
+    FS2D_CUDA(cudaMemcpyAsync(d + (16u + 4u * K) * n, b.mis + first, static_cast<size_t>(n), cudaMemcpyDeviceToDevice, st));
+    FS2D_CUDA(cudaMemcpyAsync(host_buf, d, bytes, cudaMemcpyDeviceToHost, st));
+    FS2D_CUDA(cudaStreamSynchronize(st));
+    return FS2D_OK;
+}
+
+int fs2d_upload_particles_packed(fs2d_handle ctx, const void *host_buf, int64_t count)
+{
+    if (!ctx || count < 0 || (count > 0 && !host_buf)) return FS2D_ERR_ARG;
+    FS2D_TRY(fs2d_upload_particles(ctx, 0, nullptr, nullptr, nullptr));  // resets the particle state
+    if (count == 0) return FS2D_OK;
+    const bool slab = ctx->slab.enabled && ctx->slab.world > 1;
+    FS2D_TRY(particlesReserve(ctx, count + (slab ? 2 * ctx->slab.xchgCapacity : 0)));
+    const size_t bytes = fs2d_packed_particle_bytes(ctx, count);
+    FS2D_TRY(stageReserve(ctx, bytes));
+    ParticleBuffers &b = ctx->pb[ctx->cur];
+    const int K = ctx->p.num_properties;
+    const size_t n = static_cast<size_t>(count);
+    cudaStream_t st = ctx->stream;
+    unsigned char *d = ctx->stage;
+    FS2D_CUDA(cudaMemcpyAsync(d, host_buf, bytes, cudaMemcpyHostToDevice, st));
+    FS2D_CUDA(cudaMemcpyAsync(b.pos, d, 8u * n, cudaMemcpyDeviceToDevice, st));
+    FS2D_CUDA(cudaMemcpyAsync(b.vel, d + 8u * n, 8u * n, cudaMemcpyDeviceToDevice, st));
+    for (int k = 0; k < K; k++)
+        FS2D_CUDA(cudaMemcpyAsync(b.props + static_cast<int64_t>(k) * b.capacity, d + (16u + 4u * k) * n, 4u * n, cudaMemcpyDeviceToDevice, st));
+    FS2D_CUDA(cudaMemcpyAsync(b.mis, d + (16u + 4u * K) * n, n, cudaMemcpyDeviceToDevice, st));
+    FS2D_CUDA(cudaMemsetAsync(ctx->dead, 0, n, st));
+    ctx->count = count;
+    ctx->sorted = false;
+    FS2D_TRY(particlesKeyRange(ctx, 0, count));
+    // the host buffer may be reused as soon as this returns
+    FS2D_CUDA(cudaStreamSynchronize(st));
+    return FS2D_OK;
+}
+
 int fs2d_set_particle_storage_bins(fs2d_handle h, const int32_t *host_bins)
 {
     return (h && host_bins) ? particlesSetStorageBins(h, host_bins) : FS2D_ERR_ARG;
@@ -518,7 +600,7 @@ int fs2d_pcg_last_iterations(fs2d_handle ctx, int *iters)
     FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->lastPcgIters = sc.result;
     if (iters) *iters = sc.result;
-    return FS2D_OK;
+    return slabCheckError(ctx);  // slab mode: a barrier of the solve that gave up on a peer (host is synchronised here anyway)
 }
 
 int fs2d_pcg_trace(fs2d_handle ctx, double *host_trace, int max_iterations, int *written)
@@ -581,6 +663,20 @@ int fs2d_pcg_set_stepwise(fs2d_handle ctx, int stepwise)
 {
     if (!ctx) return FS2D_ERR_ARG;
     ctx->stepwisePcg = stepwise != 0;
+    return FS2D_OK;
+}
+
+int fs2d_pcg_set_grid_limit(fs2d_handle ctx, int max_ctas)
+{
+    if (!ctx || max_ctas < 0) return FS2D_ERR_ARG;
+    ctx->pcgGridLimit = max_ctas;
+    return FS2D_OK;
+}
+
+int fs2d_pcg_set_tile_kernels(fs2d_handle ctx, int tile)
+{
+    if (!ctx) return FS2D_ERR_ARG;
+    ctx->forceTileKernels = tile != 0;
     return FS2D_OK;
 }
 

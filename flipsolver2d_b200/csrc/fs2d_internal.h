@@ -210,6 +210,10 @@ struct fs2d_context
     bool forceTileKernels = std::getenv("FS2D_PCG_TILE") != nullptr;  // A/B switch: plain tiled kernels
     bool stepwisePcg = std::getenv("FS2D_PCG_STEPWISE") != nullptr;  // A/B switch: two kernels per iteration instead of the whole-solve kernel
     bool rowCopyPcg = std::getenv("FS2D_PCG_ROWCOPY") != nullptr;    // A/B switch: per-row bulk copies instead of tensor copies
+    // test knob (fs2d_pcg_set_grid_limit / FS2D_PCG_GRID): cap on the CTAs of the persistent PCG grids, so that a small
+    // grid already gives every CTA several tiles to walk (the pipelined k >= 1 path the 4096^2 runs live on); 0 = no cap
+    int pcgGridLimit = std::getenv("FS2D_PCG_GRID") ? std::atoi(std::getenv("FS2D_PCG_GRID")) : 0;
+    int pcgOccupancy = 0;                 // CTAs of pcgSolveKernel one SM holds (occupancy query, cached)
     void *solveMaps = nullptr;            // host copy of the tensor maps of the Krylov vectors (pcg.cu)
     bool solveMapsTried = false, solveMapsOk = false;
     bool profilePcg = false;
@@ -236,6 +240,9 @@ struct fs2d_context
     bool smokeGridsAdvected = false;  // temperature/concentration/fuel replaced by advected grids (App. A-13)
     int64_t *d_counter = nullptr;     // device scalar scratch (8 int64)
     float *d_fscratch = nullptr;      // device float scratch
+
+    unsigned char *stage = nullptr;   // device staging buffer of the packed particle transfers (capi.cu)
+    size_t stageBytes = 0;
 
     // ---- scene tables
     float *obstacleFriction = nullptr;

@@ -467,6 +467,7 @@ struct ReseedArgs
     int simType;
     int viscosityProp, temperatureProp, concentrationProp, fuelProp, testProp;
     float narrowBand, resamplingBand;
+    int numSources;
 };
 
 __global__ void __launch_bounds__(NT) reseedApplyKernel(const int32_t *__restrict__ offset, long long N,
@@ -487,7 +488,10 @@ __global__ void __launch_bounds__(NT) reseedApplyKernel(const int32_t *__restric
     if (e == b) return;
     const int i = static_cast<int>(c / a.J), j = static_cast<int>(c - static_cast<long long>(i) * a.J);
     const bool src = matSource(mat[c]);
-    const int em = emitterId[c];
+    // a SOURCE cell without a (valid) emitter -- a material grid uploaded through the C ABI without its emitter grid --
+    // behaves like an emitter with zero velocity / viscosity instead of indexing the table out of bounds
+    const int emRaw = emitterId[c];
+    const int em = (emRaw >= 0 && emRaw < a.numSources) ? emRaw : -1;
     for (int32_t k = b; k < e; k++)
     {
         // jitteredPosInCell (flipsolver2d.cpp:1013-1019): x drawn first, then y
@@ -507,10 +511,10 @@ __global__ void __launch_bounds__(NT) reseedApplyKernel(const int32_t *__restric
         }
         else
         {
-            if (sources[em].transfer_velocity) v = velocityAt(vel, x.x, x.y);
+            if (em != -1 && sources[em].transfer_velocity) v = velocityAt(vel, x.x, x.y);
             if (a.simType == FS2D_SIM_LIQUID)
             {
-                if (a.viscosityProp >= 0) props[a.viscosityProp * cap + slot] = sources[em].viscosity;
+                if (a.viscosityProp >= 0) props[a.viscosityProp * cap + slot] = em != -1 ? sources[em].viscosity : 0.f;
             }
             else
             {
@@ -943,6 +947,7 @@ int particlesReseedApply(Ctx *ctx, int64_t candidates, const float *hostUniform)
     a.testProp = ctx->p.test_property;
     a.narrowBand = -3.f;
     a.resamplingBand = -1.f;
+    a.numSources = ctx->numSources;
     const bool smoke = ctx->p.sim_type == FS2D_SIM_SMOKE || ctx->p.sim_type == FS2D_SIM_FIRE;
     GridView none = makeView(nullptr, 1, 1, 0.f, 0.f);
     const SlabRows own = slabOwn(ctx);

@@ -1885,7 +1885,22 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
         return FS2D_ERR_STATE;
     }
     const int share = mgOn ? ctx->slab.share : 1;
-    const int pipeBlocks = std::max(1, std::min(blocks, 2 * ctx->smCount / share));
+    // CTAs of the persistent grids: what the device can hold co-resident (a cooperative launch refuses more; queried
+    // once, for the kernel with the larger footprint), split between the ranks that share the GPU, capped by the
+    // number of tiles and by the test knob.
+    if (pipe && ctx->pcgOccupancy == 0)
+    {
+        int perSm = 0;
+        cudaFuncSetAttribute(pcgSolveKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(SolveSmem)));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, pcgSolveKernel<true>, NT, sizeof(SolveSmem)) != cudaSuccess || perSm < 1)
+        {
+            cudaGetLastError();
+            perSm = 1;
+        }
+        ctx->pcgOccupancy = std::min(perSm, 2);
+    }
+    int pipeBlocks = std::max(1, std::min(blocks, std::max(1, ctx->pcgOccupancy) * ctx->smCount / share));
+    if (ctx->pcgGridLimit > 0) pipeBlocks = std::min(pipeBlocks, ctx->pcgGridLimit);
     if (pipe)
     {
         cudaFuncSetAttribute(pcgPipeKernel<MODE_K1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(PipeSmem<MODE_K1>)));
@@ -2056,7 +2071,16 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
         else
         {
             cudaFuncSetAttribute(pcgSolveKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-            FS2D_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(pcgSolveKernel<false>), dim3(pipeBlocks), dim3(NT), args, smem, st));
+            const cudaError_t le = cudaLaunchCooperativeKernel(reinterpret_cast<void *>(pcgSolveKernel<false>), dim3(pipeBlocks), dim3(NT), args, smem, st);
+            if (le == cudaErrorCooperativeLaunchTooLarge)
+            {
+                // the device cannot hold the grid co-resident right now (other resident work, MPS): the stepwise kernels
+                // need no co-residency and produce the same iterates
+                cudaGetLastError();
+                ctx->stepwisePcg = true;
+                return pcgSolveDevice(ctx, iterLimit, tol);
+            }
+            FS2D_CUDA(le);
         }
         ctx->launches++;
         if (prof) cudaEventRecord(ctx->profEvents[1], st);

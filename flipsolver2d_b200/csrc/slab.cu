@@ -374,9 +374,10 @@ void slabRelease(Ctx *ctx)
     s.enabled = false;
 }
 
+// Sticky: once a peer was given up on, this rank's halos are stale and every later check fails too.
 int slabCheckError(Ctx *ctx)
 {
-    if (!ctx->slab.enabled) return FS2D_OK;
+    if (!ctx->slab.enabled || ctx->slab.world == 1) return FS2D_OK;
     int err = 0;
     FS2D_CUDA(fs2dCopyToHost(ctx, &err, &ctx->mail->error, sizeof(err)));
     FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -479,6 +480,9 @@ int slabExchangeParticles(Ctx *ctx)
         FS2D_CUDA(fs2dCopyToHost(ctx, counts, ctx->mail->counts, sizeof(counts)));
         FS2D_CUDA(fs2dCopyToHost(ctx, &overflow, counters + 2, sizeof(overflow)));
         FS2D_CUDA(cudaStreamSynchronize(st));
+        // the host is synchronised here anyway: a spin loop of any slab kernel since the last check that gave up on a
+        // peer (halo exchange, particle exchange, PCG barrier) is reported now instead of stepping on with stale halos
+        FS2D_TRY(slabCheckError(ctx));
         if (overflow)
         {
             ctx->lastError = "slab: particle exchange buffer overflow";
@@ -530,6 +534,7 @@ int slabAllGather(Ctx *ctx, const long long v[4], long long *out)
     SlabGatherSlot slots[FS2D_MAX_RANKS];
     FS2D_CUDA(fs2dCopyToHost(ctx, slots, ctx->mail->gather[a.seq & 1ull], sizeof(slots)));
     FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
+    FS2D_TRY(slabCheckError(ctx));
     for (int r = 0; r < s.world; r++)
     {
         if (slots[r].tag != a.seq)

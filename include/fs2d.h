@@ -178,6 +178,18 @@ int fs2d_download_particles(fs2d_handle h, float *host_pos, float *host_vel, flo
  * countParticles depend on it, so the state is settable. */
 int fs2d_set_particle_storage_bins(fs2d_handle h, const int32_t *host_bins);
 int fs2d_get_particle_storage_bins(fs2d_handle h, int32_t *host_bins);
+/* Packed particle state, ONE copy per direction and lossless: the device order, positions, velocities, property
+ * columns AND the storage-bin byte of every particle, so that download -> upload is the identity on the solver state
+ * (a plain fs2d_upload_particles re-files every particle at home, which changes what countParticles and the gathers
+ * see once a density correction has pushed particles across bin boundaries). Also the particle half of a state
+ * dump / restore (the grids go through fs2d_download_grid / fs2d_upload_grid). Layout for n particles, K property
+ * columns: float2 pos[n] | float2 vel[n] | float props[K][n] | uint8 storage[n]; storage = (di+2)*5 + (dj+2) with
+ * (di, dj) = bin the particle is filed in minus bin of its position (markerparticlesystem.cpp:146-159), 12 = at home,
+ * 255 = further than two bins away. fs2d_packed_particle_bytes(h, n) = n * (16 + 4K + 1). Pinned host buffers make
+ * the copies run at PCIe speed; the calls return when the host buffer may be reused / read. */
+size_t fs2d_packed_particle_bytes(fs2d_handle h, int64_t count);
+int fs2d_download_particles_packed(fs2d_handle h, void *host_buf, size_t capacity_bytes, int64_t *count);
+int fs2d_upload_particles_packed(fs2d_handle h, const void *host_buf, int64_t count);
 /* Append particles (seedInitialFluid / reseedParticles callers, flipsolver2d.cpp:627-707). */
 int fs2d_append_particles(fs2d_handle h, int64_t count, const float *host_pos, const float *host_vel,
                           const float *host_props);
@@ -213,6 +225,13 @@ int fs2d_pcg_profile_read(fs2d_handle h, double *ms2, int64_t *launches2);
  * fs2d_pcg_profile_read splits that time into the K1 / K2 phases by the kernel's own phase clocks. */
 int fs2d_pcg_set_stepwise(fs2d_handle h, int stepwise);
 int fs2d_pcg_profile_solves(fs2d_handle h, double *ms, int64_t *solves);
+/* Test knobs. fs2d_pcg_set_grid_limit caps the CTAs of the persistent PCG grids (0 = no cap; env FS2D_PCG_GRID sets the
+ * default) so that a small grid already makes every CTA walk several tiles through the double-buffered TMA pipeline --
+ * the code path the 4096^2 runs live on (28 tiles per CTA). fs2d_pcg_set_tile_kernels(h, 1) selects the plain tiled
+ * kernels (one CTA per tile, no pipeline; what odd gridSizeJ uses) as a third, independent evaluation of the same
+ * arithmetic. Iterates are the same numbers in every mode; only the grouping of the dot-product partials changes. */
+int fs2d_pcg_set_grid_limit(fs2d_handle h, int max_ctas);
+int fs2d_pcg_set_tile_kernels(fs2d_handle h, int tile);
 /* IndexedPressureParameters::multiply (pressuredata.h:184-238) and
  * IndexedIPPCoefficients::multiply (PressureIPPCoeficients.h:79-132) alone, host vectors. */
 int fs2d_spmv(fs2d_handle h, const double *host_in, double *host_out);

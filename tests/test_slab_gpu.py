@@ -220,3 +220,28 @@ def test_slab_allgather_and_errors(ref_mod, scene_dir):
     d.close()
     for d in devs:
         d.close()
+
+
+def test_withheld_rank_is_reported_not_ignored(ref_mod, scene_dir):
+    """A peer that never shows up: the kernels of the waiting rank give up after their spin limit (~4 s) and flag
+    SlabMail::error; the host must turn that into FS2D_ERR_COMM at its next synchronisation point instead of stepping
+    on with stale halo rows, and keep reporting it (this rank's halos are stale for good)."""
+    scene = _scene(128)
+    s = H.make_ref(ref_mod, scene, scene_dir / "slablost.json")
+    s.stage("FIRST_FRAME_INIT")
+    s.set_step_dt(1.0 / 60.0)
+    devs = _slab_devices(s, scene, 2)
+    for d in devs:
+        d.upload("MATERIAL", s.grid("MATERIAL"))
+        d.set_step_dt(1.0 / 60.0)
+        d.stage("build_matrix")
+    rng = np.random.default_rng(1)
+    unit = devs[0].matrix()["is_unit"].astype(bool)
+    rhs = np.where(unit, rng.standard_normal(s.N), 0.0)
+    with pytest.raises(capi.Fs2dError, match="communication"):
+        devs[0].pcg_solve(rhs, 10, 0.0)      # rank 1 never calls
+    with pytest.raises(capi.Fs2dError, match="communication"):
+        devs[0].slab_allgather([1, 2])
+    for d in devs:
+        d.close()
+    s.close()

@@ -245,7 +245,7 @@ def test_project_stage(pair):
     d.stage("build_matrix")
     s.stage("PROJECT")
     it = d.stage_iters("project")
-    assert it == s.stats()["pressure_iters"] or True  # stats are per frame; compared in the trajectory test
+    assert 0 <= it <= int(s.params()["pcgIterLimit"])  # SolverStats keeps per-frame maxima; counts are compared in the frame tests
     assert H.rel_l2(d.download("U"), s.grid("U")) < 1e-5
     assert H.rel_l2(d.download("V"), s.grid("V")) < 1e-5
     assert np.array_equal(s.grid("U_VALID"), d.download("U_VALID"))
@@ -455,3 +455,113 @@ def test_viscosity_stage_against_golden_vectors(model):
     assert H.rel_l2(d.download("U"), g[model + "_u1"]) < 1e-6
     assert H.rel_l2(d.download("V"), g[model + "_v1"]) < 1e-6
     d.close()
+
+
+def test_full_stage_sweep_1024(ref_mod, scene_dir):
+    """BASELINE config 2 (flip dam break 1024^2, density 0.5, 739 640 particles): one substep from rest through the
+    reference's step(), then the SECOND substep stage by stage in the order of FlipSolver::step()
+    (flipsolver2d.cpp:412-462) on both sides. At this size every persistent kernel walks several tiles per CTA (PCG:
+    512 tiles; P2G / density tile lists; the frontier BFS runs hundreds of layers). Integer / order-free outputs
+    bit-exact; float sums to SUM_TOL; after a stage with a float tolerance the device is re-synchronised so that the
+    following bit-exact comparisons stay meaningful."""
+    scene = scenes.dam_break(1024, "flip")
+    s = H.make_ref(ref_mod, scene, scene_dir / "sweep1024.json")
+    s.stage("FIRST_FRAME_INIT")
+    s.bump_frame()
+    dt = 1.0 / 300.0
+    s.set_step_dt(dt)
+    s.stage("FULL_STEP")
+    d = H.make_device(s, scene, conv_threads=s.threads)
+    H.sync_state(s, d)
+    P0 = s.particle_count()
+    assert P0 > 700000
+
+    def grids_equal(*names):
+        for g in names:
+            assert np.array_equal(s.grid(g), d.download(g)), g
+
+    # advect + prune/rebin
+    s.stage("ADVECT")
+    s.stage("PRUNE_REBIN")
+    d.stage("advect")
+    d.stage("sort_particles")
+    assert d.particle_count() == s.particle_count()
+    _particles_equal(s, d)
+    # matrix
+    s.stage("BUILD_MATRIX")
+    d.stage("build_matrix")
+    rm, dm = s.matrix(), d.matrix()
+    for k in ("is_unit", "mask", "count"):
+        assert np.array_equal(rm[k], dm[k]), k
+    # density correction: 200 capped iterations of a non-converging PCG, then the particle push
+    s.stage("UPDATE_DENSITY_GRID")
+    _, it_ref = s.pcg(s.density_rhs(), int(s.params()["pcgIterLimit"]), s.params()["projectTolerance"])  # flipsolver2d.cpp:164-186
+    s.stage("DENSITY_CORRECTION")
+    it = d.stage_iters("density_correction")
+    assert it == it_ref, (it, it_ref)
+    assert H.rel_l2(d.download("DENSITY"), s.grid("DENSITY")) < SUM_TOL
+    rp, dp, _, _ = _particles_equal(s, d, exact=False)
+    assert H.max_abs(dp, rp) < 1e-4, H.max_abs(dp, rp)   # positions in cell units, |pos| up to 1024 (float ulp 6e-5)
+    H.sync_state(s, d)
+    # particle to grid
+    s.stage("P2G")
+    d.stage("particle_to_grid")
+    for g in ("U", "V", "VISCOSITY"):
+        assert H.rel_l2(d.download(g), s.grid(g)) < SUM_TOL, g
+    from oracle import restate
+    flags = restate.p2g_validity(s.particles()[0], s.I, s.J)
+    uexp = np.zeros((s.I + 1, s.J), bool)
+    uexp[:s.I] = flags
+    _mask_matches(s.grid("U_VALID"), d.download("U_VALID"), uexp.ravel())
+    H.sync_state(s, d)
+    # level set, materials
+    s.stage("UPDATE_SDF")
+    d.stage("update_sdf")
+    grids_equal("FLUID_SDF")
+    s.stage("UPDATE_MATERIALS")
+    d.stage("update_materials")
+    grids_equal("MATERIAL")
+    s.stage("AFTER_TRANSFER")
+    d.stage("after_transfer")
+    s.stage("EXTRAPOLATE_SDF_IN")
+    d.stage("extrapolate_sdf_inside")
+    grids_equal("FLUID_SDF")
+    s.stage("EXTRAPOLATE_VEL")
+    d.stage("extrapolate_velocity", 10)
+    grids_equal("U_VALID", "V_VALID", "U", "V")
+    s.stage("SAVE_VELOCITY")
+    s.stage("BODY_FORCES")
+    d.stage("save_velocity")
+    d.stage("apply_body_forces")
+    grids_equal("SAVED_U", "SAVED_V", "U", "V")
+    # projection: rhs bit-exact, then 200 capped iterations and the pressure gradient
+    d.stage("pressure_rhs")
+    rhs = s.pressure_rhs()
+    assert np.array_equal(rhs, d.download("RHS"))
+    # the reference's own return value for this system (LinearSolver::solve is a pure function of matrix and rhs). With
+    # one ThreadPool worker VOps::maxAbs is |r| of the LAST non-zero element (vmath.cpp:100-136), so the loop can stop
+    # long before the residual is small (here at iteration 88 with max|r| ~ 5); convergence_threads reproduces it
+    _, it_ref = s.pcg(rhs, int(s.params()["pcgIterLimit"]), s.params()["projectTolerance"])
+    u0 = s.grid("U").copy()
+    s.stage("PROJECT")
+    it = d.stage_iters("project")
+    assert it == it_ref, (it, it_ref)
+    assert H.rel_l2(u0, s.grid("U")) > 1e-3   # the stage really changes the field
+    assert H.rel_l2(d.download("U"), s.grid("U")) < 1e-5
+    assert H.rel_l2(d.download("V"), s.grid("V")) < 1e-5
+    H.sync_state(s, d)
+    s.stage("VELOCITY_FROM_SOLIDS")
+    d.stage("velocity_from_solids")
+    s.stage("EXTRAPOLATE_VEL")
+    d.stage("extrapolate_velocity", 10)
+    grids_equal("U", "V", "U_VALID", "V_VALID")
+    s.stage("PARTICLE_UPDATE")
+    d.stage("particle_update")
+    _particles_equal(s, d)
+    s.stage("COUNT_PARTICLES")
+    d.stage("count_particles")
+    grids_equal("COUNTS")
+    assert d.particle_count() == s.particle_count()
+    assert d.max_particle_velocity() == s.max_particle_velocity()
+    d.close()
+    s.close()

@@ -69,3 +69,44 @@ def test_substep_is_deterministic(ref_mod, scene_dir):
         d.close()
     for a, b in zip(*outs):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("res,density", [(96, 0.5), (128, 0.02)])
+def test_packed_round_trip_equals_resident_stepping(ref_mod, scene_dir, res, density):
+    """bench.py's end-to-end region moves the particle state host <-> device around every substep
+    (fs2d_download_particles_packed / fs2d_upload_particles_packed). That round trip must be the identity on the
+    solver state: stepping with it is bit-identical to stepping resident, and no particle is lost. At the BASELINE
+    density 0.5 the density correction pushes particles across bin boundaries, so the storage-bin byte matters: the
+    plain fs2d_upload_particles (which re-files every particle at home) is shown to change the particle count."""
+    scene = scenes.dam_break(res, "flip")
+    scene["settings"]["density"] = density
+    s = H.make_ref(ref_mod, scene, scene_dir / ("rt%d.json" % res))
+    s.stage("FIRST_FRAME_INIT")
+    s.bump_frame()
+    devs = [H.make_device(s, scene) for _ in range(3)]
+    for d in devs:
+        H.sync_state(s, d)
+    resident, packed, plain = devs
+    dt = 1.0 / 60.0
+    steps = 8
+    counts = []
+    for k in range(steps):
+        resident.substep(dt)
+        buf, n = packed.download_packed()
+        assert n == packed.particle_count()
+        packed.upload_packed(buf, n)
+        packed.substep(dt)
+        pos, vel, props = plain.download_particles()
+        plain.upload_particles(pos, vel, props)
+        plain.substep(dt)
+        counts.append((resident.particle_count(), packed.particle_count(), plain.particle_count()))
+    print("particle counts (resident, packed round trip, plain round trip):", counts)
+    assert resident.particle_count() == packed.particle_count()
+    for a, b in zip(resident.download_particles(), packed.download_particles()):
+        assert np.array_equal(a, b)
+    for g in ("U", "V", "MATERIAL", "COUNTS", "PRESSURE"):
+        assert np.array_equal(resident.download(g), packed.download(g)), g
+    assert np.array_equal(resident.storage_bins(), packed.storage_bins())
+    for d in devs:
+        d.close()
+    s.close()
