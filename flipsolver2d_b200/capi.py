@@ -147,6 +147,7 @@ def lib():
         "fs2d_pcg_profile_solves": (i32, [H, vp, vp]),
         "fs2d_pcg_set_grid_limit": (i32, [H, i32]),
         "fs2d_pcg_set_tile_kernels": (i32, [H, i32]),
+        "fs2d_pcg_set_resident": (i32, [H, i32]),
         "fs2d_slab_configure": (i32, [H, i32, i32, i32]),
         "fs2d_slab_configure_rows": (i32, [H, i32, i32, i32, vp]),
         "fs2d_slab_export": (i32, [H, vp]),
@@ -332,6 +333,9 @@ class Device:
 
     def pcg_set_grid_limit(self, max_ctas=0):
         self._ck(self.L.fs2d_pcg_set_grid_limit(self.h, int(max_ctas)), "pcg_set_grid_limit")
+
+    def pcg_set_resident(self, resident=True):
+        self._ck(self.L.fs2d_pcg_set_resident(self.h, 1 if resident else 0), "pcg_set_resident")
 
     def pcg_set_tile_kernels(self, tile=True):
         self._ck(self.L.fs2d_pcg_set_tile_kernels(self.h, 1 if tile else 0), "pcg_set_tile_kernels")

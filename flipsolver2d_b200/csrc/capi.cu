@@ -673,6 +673,13 @@ int fs2d_pcg_set_grid_limit(fs2d_handle ctx, int max_ctas)
     return FS2D_OK;
 }
 
+int fs2d_pcg_set_resident(fs2d_handle ctx, int resident)
+{
+    if (!ctx) return FS2D_ERR_ARG;
+    ctx->residentPcg = resident != 0;
+    return FS2D_OK;
+}
+
 int fs2d_pcg_set_tile_kernels(fs2d_handle ctx, int tile)
 {
     if (!ctx) return FS2D_ERR_ARG;

@@ -1364,6 +1364,7 @@ __global__ void __launch_bounds__(NT, 2) pcgSolveKernel(SolveArgs g, MgArgs mg, 
     const int tid = threadIdx.x;
     const bool scribe = blockIdx.x == 0 && tid == 0;  // keeps PcgScalars / the trace for the host
     PcgScalars *sc = g.a.sc;
+    if (sc->pad) return;  // pcgResidentKernel (launched just before) took this solve
     if (tid < 8) sm.preTbl[tid] = g.a.pre[tid];
     if (tid == 0)
     {
@@ -1483,6 +1484,458 @@ __global__ void __launch_bounds__(NT, 2) pcgSolveKernel(SolveArgs g, MgArgs mg, 
     if (scribe)
     {
         sc->alpha = alpha;  // pending x += alpha s of the last executed iteration (pcgFinalizeKernel)
+        sc->beta = beta;
+        sc->sigma = sigma;
+        sc->gamma = gamma;
+        sc->err = err;
+        sc->iter = executed;
+        sc->result = result;
+        sc->done = 1;
+        sc->phaseNs[0] += tA;
+        sc->phaseNs[1] += tB;
+        sc->phaseLaunches += static_cast<unsigned int>(executed);
+    }
+}
+
+// ------------------------------------------------------------------ resident whole-solve kernel
+// When the active set is small -- at most RES_TPC tiles per SM: every grid <= 2048^2 with a dam-break fill, and every
+// rank of a 4096^2 run over >= 2 GPUs -- the Krylov vectors never leave the SMs. A CTA (512 threads, one per SM) owns
+// up to RES_TPC tiles for the WHOLE solve and keeps, per tile, in shared memory: the halo-extended search vector s and
+// residual r (18 x 132 doubles each) and the interior of the vector that travels between the two phases (z into K1, q
+// into K2; 16 x 128); the solution x accumulates in registers (4 cells per thread and tile). Per phase a tile then only
+//   * writes its 16 x 128 q (K1) or z (K2) to the global array -- the only thing neighbours need --, and
+//   * after the barrier reads the 288 ring values of its neighbours' z / q back (L2, ld.cg) to advance s / r on its halo
+//     ring redundantly (same inputs, same scalars -> same bits as on the owner; what the slab path already does for the
+//     halo rows of a rank),
+// i.e. ~18 KB of L2 traffic instead of the 100 KB a streamed tile moves, and no load pipeline to start: a phase is the
+// barrier plus ~1 us of shared-memory arithmetic. Arithmetic, barrier protocol (phases, tags, mail ring), halo-row pushes
+// into the row neighbours' q / z and convergence logic are those of pcgSolveKernel, so a rank running this kernel
+// interoperates with a rank streaming its tiles. x is written once, at the end (pending alpha * s included).
+constexpr int RNT = 512;          // threads per CTA
+constexpr int RES_TPC = 4;        // tiles a CTA can hold
+constexpr int RES_CELLS = TR * TC / RNT;  // interior cells per thread and tile (4)
+
+struct ResTile
+{
+    double S[PTILE_PAD];
+    double R[PTILE_PAD];
+    double T[TR * TC];
+};
+
+struct ResSmem
+{
+    ResTile t[RES_TPC];
+    double red[32];
+    double preTbl[8];
+    double pub[2];
+    double bc[2];
+    int isLast;
+    int ok;
+};
+
+__device__ __forceinline__ void blockReduce2W16(double &s, double &m, double *scratch /* >= 32 doubles */)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    s = warpSum(s);
+    m = warpMax(m);
+    __syncthreads();
+    if (lane == 0)
+    {
+        scratch[warp] = s;
+        scratch[16 + warp] = m;
+    }
+    __syncthreads();
+    if (warp == 0)
+    {
+        s = (lane < (RNT >> 5)) ? scratch[lane] : 0.0;
+        m = (lane < (RNT >> 5)) ? scratch[16 + lane] : 0.0;
+        s = warpSum(s);
+        m = warpMax(m);
+    }
+}
+
+// solveBarrier for `nb` participating CTAs of RNT threads (same protocol; see there).
+template <bool MG>
+__device__ __forceinline__ bool resBarrier(const SolveArgs &g, const MgArgs &m, int phase, unsigned int barrierIndex, unsigned int nb,
+                                           double v0, double v1, ResSmem &sm, double *sum, double *mx, bool remoteStores)
+{
+    const int tid = threadIdx.x;
+    blockReduce2W16(v0, v1, sm.red);
+    if (!MG)
+    {
+        double *part = g.a.partials + (barrierIndex & 1u) * 2u * nb;
+        if (tid == 0)
+        {
+            part[blockIdx.x] = v0;
+            part[nb + blockIdx.x] = v1;
+            __threadfence();
+            atomicAdd(g.ticket, 1u);
+            const unsigned int target = (barrierIndex + 1u) * nb;
+            unsigned int seen;
+            do
+            {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(g.ticket) : "memory");
+            } while (seen < target);
+        }
+        __syncthreads();
+        double ts = 0.0, tm = 0.0;
+        for (unsigned int k = tid; k < nb; k += RNT)
+        {
+            ts += __ldcg(part + k);
+            tm = fmax(tm, __ldcg(part + nb + k));
+        }
+        blockReduce2W16(ts, tm, sm.red);
+        if (tid == 0)
+        {
+            sm.bc[0] = ts;
+            sm.bc[1] = tm;
+        }
+        __syncthreads();
+        *sum = sm.bc[0];
+        *mx = sm.bc[1];
+        return true;
+    }
+    if (tid == 0)
+    {
+        g.a.partials[blockIdx.x] = v0;
+        g.a.partials[nb + blockIdx.x] = v1;
+        if (remoteStores)
+            __threadfence_system();
+        else
+            __threadfence();
+        sm.isLast = (atomicAdd(g.ticket, 1u) == (barrierIndex + 1u) * nb - 1u);
+    }
+    __syncthreads();
+    if (sm.isLast)
+    {
+        double ts = 0.0, tm = 0.0;
+        for (unsigned int k = tid; k < nb; k += RNT)
+        {
+            ts += __ldcg(g.a.partials + k);
+            tm = fmax(tm, __ldcg(g.a.partials + nb + k));
+        }
+        blockReduce2W16(ts, tm, sm.red);
+        if (tid == 0)
+        {
+            sm.pub[0] = ts;
+            sm.pub[1] = tm;
+        }
+        __syncthreads();
+        llPublish<MG>(m, phase, sm.pub[0], sm.pub[1]);
+    }
+    if (tid < 32)
+    {
+        double s = 0.0, x = 0.0;
+        const bool ok = llCollect<MG>(m, phase, &s, &x);
+        if (tid == 0)
+        {
+            sm.ok = ok ? 1 : 0;
+            sm.bc[0] = s;
+            sm.bc[1] = x;
+        }
+    }
+    __syncthreads();
+    *sum = sm.bc[0];
+    *mx = sm.bc[1];
+    return sm.ok != 0;
+}
+
+// Ring cell `tid` (< 288) of a tile: position inside the halo-extended 18 x 132 array and the LINEAR global index of the
+// value (the reference addresses the j = -1 / j = J neighbours by linear index: pressuredata.h:135-145); n = -1 when the
+// value lies outside the vector (reads as zero).
+__device__ __forceinline__ void resRingCell(int tid, int i0, int j0, int I, long long J, long long N, int *pos, long long *n)
+{
+    *pos = -1;
+    *n = -1;
+    if (tid < 2 * TC)
+    {
+        const int bottom = tid >= TC ? 1 : 0, col = tid - bottom * TC;
+        const long long gi = bottom ? i0 + TR : i0 - 1, gj = j0 + col;
+        if (gj < J)
+        {
+            *pos = (bottom ? TR + 1 : 0) * PSW + col + 2;
+            if (gi >= 0 && gi < I) *n = gi * J + gj;
+        }
+    }
+    else if (tid < 2 * TC + 2 * TR)
+    {
+        const int e = tid - 2 * TC, right = e >= TR ? 1 : 0, ar = 1 + (e - right * TR);
+        const long long gi = i0 - 1 + ar;
+        const long long span = J - j0;                                        // valid columns of this tile (<= TC for edge tiles)
+        const int c = right ? static_cast<int>(span < TC ? span : TC) + 2 : 1;  // right neighbour of the last valid column
+        const long long gj = j0 - 2 + c;
+        *pos = ar * PSW + c;
+        const long long lin = gi * J + gj;
+        if (gi < I && lin >= 0 && lin < N) *n = lin;
+    }
+}
+
+template <bool MG> __global__ void __launch_bounds__(RNT, 1) pcgResidentKernel(SolveArgs g, MgArgs mg)
+{
+    extern __shared__ __align__(128) unsigned char resRaw[];
+    ResSmem &sm = *reinterpret_cast<ResSmem *>(resRaw);
+    const int tid = threadIdx.x;
+    PcgScalars *sc = g.a.sc;
+    const int count = *g.a.activeCount;
+    const unsigned int P = static_cast<unsigned int>(min(static_cast<int>(gridDim.x), count));  // participating CTAs
+    if (count > RES_TPC * static_cast<int>(gridDim.x) || count <= 0)
+        return;  // too many tiles to hold (or nothing to do): PcgScalars::pad stays 0 and the streaming kernel runs
+    if (blockIdx.x >= P) return;
+    const bool scribe = blockIdx.x == 0 && tid == 0;
+    if (scribe) sc->pad = 1;  // tells the streaming kernel and pcgFinalizeKernel that this solve is done here
+    if (tid < 8) sm.preTbl[tid] = g.a.pre[tid];
+    if (tid == 0)
+    {
+        double s0 = 0.0, m0 = 0.0;
+        sm.ok = mgCollect(mg, 0, true, &s0, &m0) ? 1 : 0;  // phase 0: rhs.rhs and max|rhs| from pcgInitKernel<true>
+        sm.bc[0] = s0;
+        sm.bc[1] = m0;
+    }
+    __syncthreads();
+    double sigma = sm.bc[0];
+    const double max0 = sm.bc[1];
+    const bool lost0 = sm.ok == 0;
+    __syncthreads();
+    if (lost0 || !(max0 > 1.0e-15))  // a lost peer, or VOps::isZero (vmath.cpp:47-58): x = 0 (pcgInitKernel), zero iterations
+    {
+        if (scribe)
+        {
+            sc->sigma = sigma;
+            sc->alpha = sc->beta = sc->gamma = sc->err = 0.0;
+            sc->iter = 0;
+            sc->result = 0;
+            sc->done = 1;
+        }
+        return;
+    }
+    const int I = g.a.I;
+    const long long J = g.a.J, N = g.a.N;
+    const int myTiles = (count - static_cast<int>(blockIdx.x) + static_cast<int>(P) - 1) / static_cast<int>(P);
+    const int lr = tid >> 7, lc = tid & (TC - 1);  // this thread's interior cells of a tile: rows lr + 4k, column lc
+
+    // ---- per-tile constants in registers: origin, ring cell, operator bytes of the thread's cells
+    int ti0[RES_TPC], tj0[RES_TPC], ringPos[RES_TPC];
+    long long ringN[RES_TPC];
+    unsigned int rowBits[RES_TPC];             // 4 x rowInfo byte
+    unsigned int validBits[RES_TPC];           // bit k: cell k of this thread lies inside the matrix
+    unsigned long long preBits[RES_TPC];       // 4 x preInfo half-word
+    double xacc[RES_TPC][RES_CELLS];
+    bool remote = false;                       // (uniform over the CTA) a tile holds a slab-boundary row pushed to a neighbour
+#pragma unroll
+    for (int t = 0; t < RES_TPC; t++)
+    {
+        ti0[t] = tj0[t] = 0;
+        ringPos[t] = -1;
+        ringN[t] = -1;
+        rowBits[t] = 0;
+        preBits[t] = 0;
+        validBits[t] = 0;
+#pragma unroll
+        for (int k = 0; k < RES_CELLS; k++) xacc[t][k] = 0.0;
+        if (t < myTiles)
+        {
+            const int tile = g.a.activeTiles[blockIdx.x + t * P];
+            const int ti = tile / g.a.tilesJ, tj = tile - ti * g.a.tilesJ;
+            ti0[t] = ti * TR;
+            tj0[t] = tj * TC;
+            resRingCell(tid, ti0[t], tj0[t], I, J, N, &ringPos[t], &ringN[t]);
+            if (MG)
+                remote = remote || (g.loQ && mg.rowBegin >= ti0[t] && mg.rowBegin < ti0[t] + TR) ||
+                         (g.hiQ && mg.rowEnd - 1 >= ti0[t] && mg.rowEnd - 1 < ti0[t] + TR);
+            // s = 0, r = rhs on the halo-extended tile (r0 = z0 = rhs, linearsolver.cpp:32-46), T = z0 interior
+            ResTile &rt = sm.t[t];
+            for (int e = tid; e < PTILE; e += RNT)
+            {
+                const int ar = e / PSW, c = e - ar * PSW;
+                const long long gi = ti0[t] - 1 + ar, gj = tj0[t] - 2 + c;
+                double v = 0.0;
+                if (gi >= 0 && gi < I && gj >= -1 && gj <= J)
+                {
+                    const long long n = gi * J + gj;
+                    if (n >= 0 && n < N) v = g.z[n];  // pcgInitKernel left z = rhs; linear index: wrap columns included
+                }
+                rt.S[e] = 0.0;
+                rt.R[e] = v;
+            }
+#pragma unroll
+            for (int k = 0; k < RES_CELLS; k++)
+            {
+                const int row = lr + 4 * k;
+                const long long gi = ti0[t] + row, gj = tj0[t] + lc;
+                double v = 0.0;
+                if (gi < I && gj < J)
+                {
+                    const long long n = gi * J + gj;
+                    v = g.z[n];
+                    validBits[t] |= 1u << k;
+                    rowBits[t] |= static_cast<unsigned int>(g.a.rowInfo[n]) << (8 * k);
+                    preBits[t] |= static_cast<unsigned long long>(g.a.preInfo[n]) << (16 * k);
+                }
+                rt.T[row * TC + lc] = v;
+            }
+        }
+    }
+    __syncthreads();
+
+    unsigned int bar = 0;
+    double alpha = 0.0, beta = 0.0, alphaPrev = 0.0, gamma = 0.0, err = 0.0;
+    int result = g.iterLimit, executed = 0;
+    unsigned long long tA = 0, tB = 0, t0 = scribe ? globalTimerNs() : 0ull;
+    for (int i = 0; i < g.iterLimit; i++)
+    {
+        // ---- K1(i): s = z + beta s (interior from T, ring from the neighbours' z); x += alpha_{i-1} s_{i-1}; q = A s; gamma = q.s
+        double accDot = 0.0, accMax = 0.0, unused = 0.0;
+        double ringV[RES_TPC];
+#pragma unroll
+        for (int t = 0; t < RES_TPC; t++) ringV[t] = (t < myTiles && ringN[t] >= 0) ? __ldcg(g.z + ringN[t]) : 0.0;
+#pragma unroll
+        for (int t = 0; t < RES_TPC; t++)
+            if (t < myTiles)
+            {
+                ResTile &rt = sm.t[t];
+#pragma unroll
+                for (int k = 0; k < RES_CELLS; k++)
+                {
+                    // cells outside the matrix stay zero; in an edge tile the slot right of the last valid column is the
+                    // ring cell (wrap neighbour) and belongs to the ring thread
+                    if (!((validBits[t] >> k) & 1u)) continue;
+                    const int row = lr + 4 * k, p = (row + 1) * PSW + lc + 2;
+                    const double so = rt.S[p];
+                    rt.S[p] = __dadd_rn(rt.T[row * TC + lc], __dmul_rn(so, beta));
+                    xacc[t][k] = __dadd_rn(xacc[t][k], __dmul_rn(so, alphaPrev));
+                }
+                if (ringPos[t] >= 0) rt.S[ringPos[t]] = __dadd_rn(ringV[t], __dmul_rn(rt.S[ringPos[t]], beta));
+            }
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < RES_TPC; t++)
+            if (t < myTiles)
+            {
+                ResTile &rt = sm.t[t];
+#pragma unroll
+                for (int k = 0; k < RES_CELLS; k++)
+                {
+                    const int row = lr + 4 * k, p = (row + 1) * PSW + lc + 2;
+                    const long long gi = ti0[t] + row, gj = tj0[t] + lc;
+                    if (gi < I && gj < J)
+                    {
+                        const long long n = gi * J + gj;
+                        const double c = rt.S[p];
+                        const double o = rowA(static_cast<uint8_t>(rowBits[t] >> (8 * k)), g.a.scale, c, rt.S[p - PSW], rt.S[p + PSW], rt.S[p - 1], rt.S[p + 1]);
+                        rt.T[row * TC + lc] = o;
+                        g.q[n] = o;
+                        if (MG)
+                        {
+                            if (gi == mg.rowBegin && g.loQ) g.loQ[n] = o;
+                            if (gi == mg.rowEnd - 1 && g.hiQ) g.hiQ[n] = o;
+                        }
+                        accDot += o * c;
+                    }
+                }
+            }
+        if (!resBarrier<MG>(g, mg, 2 * i + 1, bar++, P, accDot, 0.0, sm, &gamma, &unused, remote)) break;
+        alpha = sigma / (gamma + 1e-8);  // linearsolver.cpp:50
+        if (scribe)
+        {
+            const unsigned long long t = globalTimerNs();
+            tA += t - t0;
+            t0 = t;
+        }
+        // ---- K2(i): r -= alpha q (interior from T, ring from the neighbours' q); z = M r; sigma' = z.r; err = max|r|
+        accDot = 0.0;
+#pragma unroll
+        for (int t = 0; t < RES_TPC; t++) ringV[t] = (t < myTiles && ringN[t] >= 0) ? __ldcg(g.q + ringN[t]) : 0.0;
+#pragma unroll
+        for (int t = 0; t < RES_TPC; t++)
+            if (t < myTiles)
+            {
+                ResTile &rt = sm.t[t];
+#pragma unroll
+                for (int k = 0; k < RES_CELLS; k++)
+                {
+                    if (!((validBits[t] >> k) & 1u)) continue;
+                    const int row = lr + 4 * k, p = (row + 1) * PSW + lc + 2;
+                    rt.R[p] = __dsub_rn(rt.R[p], __dmul_rn(rt.T[row * TC + lc], alpha));
+                }
+                if (ringPos[t] >= 0) rt.R[ringPos[t]] = __dsub_rn(rt.R[ringPos[t]], __dmul_rn(ringV[t], alpha));
+            }
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < RES_TPC; t++)
+            if (t < myTiles)
+            {
+                ResTile &rt = sm.t[t];
+#pragma unroll
+                for (int k = 0; k < RES_CELLS; k++)
+                {
+                    const int row = lr + 4 * k, p = (row + 1) * PSW + lc + 2;
+                    const long long gi = ti0[t] + row, gj = tj0[t] + lc;
+                    if (gi < I && gj < J)
+                    {
+                        const long long n = gi * J + gj;
+                        const double c = rt.R[p];
+                        const double o = rowM(static_cast<uint16_t>(preBits[t] >> (16 * k)), sm.preTbl, c, rt.R[p - PSW], rt.R[p + PSW], rt.R[p - 1], rt.R[p + 1]);
+                        rt.T[row * TC + lc] = o;
+                        g.z[n] = o;
+                        if (MG)
+                        {
+                            if (gi == mg.rowBegin && g.loZ) g.loZ[n] = o;
+                            if (gi == mg.rowEnd - 1 && g.hiZ) g.hiZ[n] = o;
+                        }
+                        accDot += o * c;
+                        accMax = fmax(accMax, fabs(c));
+                    }
+                }
+            }
+        double sigmaNew = 0.0;
+        if (!resBarrier<MG>(g, mg, 2 * i + 2, bar++, P, accDot, accMax, sm, &sigmaNew, &err, remote)) break;
+        executed = i + 1;
+        const bool converged = err <= g.a.tol;                      // linearsolver.cpp:59-61
+        const double betaNew = converged ? 0.0 : sigmaNew / sigma;  // :66-67
+        if (scribe)
+        {
+            const unsigned long long t = globalTimerNs();
+            tB += t - t0;
+            t0 = t;
+            if (g.a.trace && i < g.a.traceCapacity)
+            {
+                g.a.trace[4 * i + 0] = alpha;
+                g.a.trace[4 * i + 1] = betaNew;
+                g.a.trace[4 * i + 2] = sigmaNew;
+                g.a.trace[4 * i + 3] = err;
+            }
+        }
+        if (converged)
+        {
+            result = i;
+            break;
+        }
+        beta = betaNew;
+        sigma = sigmaNew;
+        alphaPrev = alpha;
+    }
+    // ---- x = accumulated steps + the pending alpha * s of the last executed iteration (linearsolver.cpp:51)
+#pragma unroll
+    for (int t = 0; t < RES_TPC; t++)
+        if (t < myTiles)
+        {
+            ResTile &rt = sm.t[t];
+#pragma unroll
+            for (int k = 0; k < RES_CELLS; k++)
+            {
+                const int row = lr + 4 * k, p = (row + 1) * PSW + lc + 2;
+                const long long gi = ti0[t] + row, gj = tj0[t] + lc;
+                if (gi < I && gj < J)
+                {
+                    double xv = xacc[t][k];
+                    if (executed > 0) xv = __dadd_rn(xv, __dmul_rn(rt.S[p], alpha));
+                    g.x[gi * J + gj] = xv;
+                }
+            }
+        }
+    if (scribe)
+    {
+        sc->alpha = alpha;
         sc->beta = beta;
         sc->sigma = sigma;
         sc->gamma = gamma;
@@ -1732,7 +2185,7 @@ __global__ void __launch_bounds__(NT) pcgFinalizeKernel(double *x, const double 
                                                         PcgScalars *sc, int iterLimit)
 {
     const int iters = sc->iter;
-    if (iters > 0)
+    if (iters > 0 && !sc->pad)  // pad: the resident kernel wrote the finished x itself
     {
         const double alpha = sc->alpha;
         const double *s = (iters & 1) ? sOdd : sEven;
@@ -1821,6 +2274,8 @@ void pcgPreloadSlabKernels()
     cudaFuncGetAttributes(&at, pcgMgCloseKernel);
     cudaFuncGetAttributes(&at, pcgSolveKernel<true>);
     cudaFuncGetAttributes(&at, pcgSolveKernel<false>);
+    cudaFuncGetAttributes(&at, pcgResidentKernel<true>);
+    cudaFuncGetAttributes(&at, pcgResidentKernel<false>);
     cudaFuncGetAttributes(&at, pcgFinalizeKernel);
     cudaFuncGetAttributes(&at, pcgTileFlagKernel);
     cudaFuncGetAttributes(&at, pcgTileCompactKernel);
@@ -2003,6 +2458,7 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
             ctx->profEvents.push_back(e);
         }
     const bool active = pipe && !ctx->densePcg;
+    FS2D_CUDA(cudaMemsetAsync(&ctx->scalars->pad, 0, sizeof(int), st));  // set by pcgResidentKernel when it takes the solve
     if (mgOn || whole)
     {
         mg.phase = 0;
@@ -2061,6 +2517,33 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
         static const int hintEnv = std::getenv("FS2D_PCG_HINTS") ? std::atoi(std::getenv("FS2D_PCG_HINTS")) : -1;
         const int hintMask = hintEnv >= 0 ? hintEnv : 7;  // measured at 4096^2: 19.7 -> 18.2 us per phase with x, s, r evict-first and q, z evict-last
         if (useTensor && active) useTensor |= hintMask << 8;
+        if (active && ctx->residentPcg)
+        {
+            // small active sets stay in shared memory for the whole solve (pcgResidentKernel decides on the device,
+            // from the tile count, whether it can hold them; if not it returns at once and the streaming kernel runs)
+            int resBlocks = std::max(1, ctx->smCount / share);
+            if (ctx->pcgGridLimit > 0) resBlocks = std::min(resBlocks, ctx->pcgGridLimit);
+            void *rargs[] = {&g, &mg};
+            const size_t rsmem = sizeof(ResSmem);
+            cudaError_t re;
+            if (mgOn)
+            {
+                cudaFuncSetAttribute(pcgResidentKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rsmem));
+                re = cudaLaunchCooperativeKernel(reinterpret_cast<void *>(pcgResidentKernel<true>), dim3(resBlocks), dim3(RNT), rargs, rsmem, st);
+            }
+            else
+            {
+                cudaFuncSetAttribute(pcgResidentKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rsmem));
+                re = cudaLaunchCooperativeKernel(reinterpret_cast<void *>(pcgResidentKernel<false>), dim3(resBlocks), dim3(RNT), rargs, rsmem, st);
+            }
+            if (re == cudaErrorCooperativeLaunchTooLarge)
+                cudaGetLastError();  // the device is shared: the streaming kernel (or its stepwise fallback) takes the solve
+            else
+            {
+                FS2D_CUDA(re);
+                ctx->launches++;
+            }
+        }
         void *args[] = {&g, &mg, &maps, &useTensor};
         const size_t smem = sizeof(SolveSmem);
         if (mgOn)

@@ -231,6 +231,11 @@ int fs2d_pcg_profile_solves(fs2d_handle h, double *ms, int64_t *solves);
  * kernels (one CTA per tile, no pipeline; what odd gridSizeJ uses) as a third, independent evaluation of the same
  * arithmetic. Iterates are the same numbers in every mode; only the grouping of the dot-product partials changes. */
 int fs2d_pcg_set_grid_limit(fs2d_handle h, int max_ctas);
+/* Active-tile solves whose tiles fit the shared memory of the SMs (<= 4 tiles of 16x128 per SM) run in
+ * pcgResidentKernel: s, r and the inter-phase vector stay in shared memory for the whole solve, x in registers, only
+ * halo values cross L2. fs2d_pcg_set_resident(h, 0) forces the streaming kernel (A/B switch; env FS2D_PCG_RESIDENT=0).
+ * Same iterates up to the grouping of the dot-product partials. */
+int fs2d_pcg_set_resident(fs2d_handle h, int resident);
 int fs2d_pcg_set_tile_kernels(fs2d_handle h, int tile);
 /* IndexedPressureParameters::multiply (pressuredata.h:184-238) and
  * IndexedIPPCoefficients::multiply (PressureIPPCoeficients.h:79-132) alone, host vectors. */

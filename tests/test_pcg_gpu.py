@@ -183,6 +183,7 @@ def test_whole_solve_kernel_equals_stepwise_kernels(ref_mod, scene_dir, dense):
     s = _ref_system(ref_mod, scene_dir, 192, dt=1.0 / 2000.0)  # small matrix scale: the solve converges within the cap
     d = _device_for(s, iter_limit=400)
     d.pcg_set_dense(dense)
+    d.pcg_set_resident(False)  # the streaming whole-solve kernel; pcgResidentKernel groups the partials differently
     unit = d.matrix()["is_unit"].astype(bool)
     rng = np.random.default_rng(11)
     rhs = np.where(unit, rng.standard_normal(s.N), 0.0)
@@ -227,6 +228,7 @@ def test_linear_index_wrap_columns_without_walls(ref_mod, scene_dir):
     assert np.array_equal(d.spmv(v), s.spmv(v))
     for dense in (True, False):
         d.pcg_set_dense(dense)
+        d.pcg_set_resident(False)
         xr, nr = s.pcg(rhs, 25, 0.0)
         d.pcg_set_stepwise(True)
         x_step, n_step = d.pcg_solve(rhs, 25, 0.0)
@@ -235,5 +237,11 @@ def test_linear_index_wrap_columns_without_walls(ref_mod, scene_dir):
         assert n_step == n_whole == nr == 25
         assert np.array_equal(x_whole, x_step)
         assert np.linalg.norm(x_whole - xr) / np.linalg.norm(xr) < 1e-9
+        if not dense:
+            # the resident kernel reads the wrap neighbours as ring cells by linear index
+            d.pcg_set_resident(True)
+            x_res, n_res = d.pcg_solve(rhs, 25, 0.0)
+            assert n_res == 25
+            assert np.linalg.norm(x_res - xr) / np.linalg.norm(xr) < 1e-9
     d.close()
     s.close()

@@ -57,6 +57,9 @@ def _modes(d, rhs, iters, tol=0.0):
     out = {}
     d.pcg_set_tile_kernels(False)
     d.pcg_set_stepwise(False)
+    d.pcg_set_resident(True)   # active walk with few enough tiles: pcgResidentKernel (vectors stay in shared memory)
+    out["resident"] = d.pcg_solve(rhs, iters, tol) + (d.pcg_trace().copy(),)
+    d.pcg_set_resident(False)  # the streaming whole-solve kernel
     out["whole"] = d.pcg_solve(rhs, iters, tol) + (d.pcg_trace().copy(),)
     d.pcg_set_stepwise(True)
     out["stepwise"] = d.pcg_solve(rhs, iters, tol) + (d.pcg_trace().copy(),)
@@ -64,6 +67,7 @@ def _modes(d, rhs, iters, tol=0.0):
     d.pcg_set_tile_kernels(True)
     out["tile"] = d.pcg_solve(rhs, iters, tol) + (d.pcg_trace().copy(),)
     d.pcg_set_tile_kernels(False)
+    d.pcg_set_resident(True)
     return out
 
 
@@ -104,8 +108,10 @@ def test_shrunk_grid_walks_many_tiles_per_cta(sys256, limit, dense):
     assert np.array_equal(m["whole"][2], m["stepwise"][2])
     # the plain tile kernels group the partials per tile: same numbers up to that regrouping
     assert H.rel_l2(m["tile"][0], m["whole"][0]) < 1e-11
+    assert H.rel_l2(m["resident"][0], m["whole"][0]) < 1e-11
     if not dense:
         assert not m["whole"][0][~unit & (rhs == 0)].any()  # skipped tiles hold exact zeros
+        assert not m["resident"][0][~unit & (rhs == 0)].any()
 
 
 def test_shrunk_grid_converging_solve_and_zero_rhs(sys256):
@@ -169,15 +175,21 @@ def test_flip_1024_against_reference(sys1024, limit):
     for dense in (True, False):
         d.pcg_set_dense(dense)
         d.pcg_set_stepwise(False)
+        d.pcg_set_resident(False)
         xw, nw = d.pcg_solve(rhs, iters, 0.0)
         d.pcg_set_stepwise(True)
         xs, ns = d.pcg_solve(rhs, iters, 0.0)
         d.pcg_set_stepwise(False)
+        d.pcg_set_resident(True)
         assert nw == ns == iters
         assert np.array_equal(xw, xs)
         assert H.rel_l2(xw, xr) < TOL, (dense, H.rel_l2(xw, xr))
         if not dense:
             assert d.pcg_active_cells() < s.N // 4
+            # ~60 active tiles: with the full grid the resident kernel holds one tile per CTA, with 37 CTAs two
+            xres, nres = d.pcg_solve(rhs, iters, 0.0)
+            assert nres == iters and H.rel_l2(xres, xr) < TOL, H.rel_l2(xres, xr)
+            assert H.rel_l2(xres, xw) < 1e-11
     # the real right-hand side of the scene (hydrostatic column at rest): body forces, then calcPressureRhs
     s.stage("BODY_FORCES")
     rhs2 = s.pressure_rhs()
@@ -213,7 +225,7 @@ def test_smoke_2048_rows_against_reference(sys2048, limit):
 
 
 @pytest.mark.parametrize("world,limit", [(2, 3), (4, 2), (2, 0)])
-@pytest.mark.parametrize("dense", [True, False], ids=["dense", "active"])
+@pytest.mark.parametrize("dense", [True, False, None], ids=["dense", "active", "resident"])
 def test_slab_solve_with_many_tiles_per_cta(ref_mod, scene_dir, world, limit, dense):
     """pcgSolveKernel<MG = true> (row slabs; here the ranks share one GPU) with 3 - 8 tiles per CTA: the halo rows
     pushed into the neighbour, the machine-wide barrier and the pipelined walk together, against the reference."""
@@ -234,11 +246,12 @@ def test_slab_solve_with_many_tiles_per_cta(ref_mod, scene_dir, world, limit, de
         d.upload("MATERIAL", mat)
         d.set_step_dt(1.0 / 60.0)
         d.stage("build_matrix")
-        d.pcg_set_dense(dense)
+        d.pcg_set_dense(bool(dense))
+        d.pcg_set_resident(dense is None)  # None: active walk through pcgResidentKernel<MG> (1 - 4 resident tiles per CTA)
         d.pcg_set_grid_limit(limit)
     J = s.J
     outs = {}
-    for stepwise in (False, True):
+    for stepwise in ((False,) if dense is None else (False, True)):
         for d in devs:
             d.pcg_set_stepwise(stepwise)
         res = capi.run_ranks([lambda d=d: d.pcg_solve(rhs, iters, 0.0) for d in devs])
@@ -249,7 +262,8 @@ def test_slab_solve_with_many_tiles_per_cta(ref_mod, scene_dir, world, limit, de
             assert nd == iters
         outs[stepwise] = x
         assert H.rel_l2(x, xr) < TOL, (stepwise, H.rel_l2(x, xr))
-    assert np.array_equal(outs[False], outs[True])
+    if dense is not None:
+        assert np.array_equal(outs[False], outs[True])
     for d in devs:
         d.close()
     s.close()
