@@ -139,34 +139,65 @@ def make_reference(res, tmp):
 
 
 def run_reference(args, rank, world):
+    """The reference's own CPU implementation (oracle/_ref/libfs2d_ref.so: unmodified sources, Release flags, ThreadPool =
+    all host threads) on the SAME scene at the SAME resolution as our arm. A 4096^2 substep costs the reference 30 - 200 s
+    (SURVEY section 6), so `--steps K` of them do not fit a bench run: real substeps are run from frame 0 -- the first
+    from rest, then moving ones -- until K are done or the wall budget (FS2D_REF_BUDGET_S, default 100 s: a new substep
+    is only started while less than that has been spent) is used up, and the line reports the steps actually timed.
+    Nothing is extrapolated; the 1024^2 sample the previous round scaled by 1/16 is kept as a secondary field."""
     if rank != 0:
         return
     tmp = tempfile.mkdtemp(prefix="fs2d_bench_")
-    res = REFERENCE_SAMPLE_RES
-    s = make_reference(res, tmp)
+    budget = float(os.environ.get("FS2D_REF_BUDGET_S", "100"))
+    t_init = time.perf_counter()
+    s = make_reference(args.res, tmp)
+    init_s = time.perf_counter() - t_init
     cores = s.threads
-    for _ in range(args.warmup):
-        reference_substep(s)
+    particles = s.particle_count()
+    durations = []
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    while len(durations) < max(args.steps, 1) and (not durations or time.perf_counter() - t0 < budget):
+        t1 = time.perf_counter()
         reference_substep(s)
+        durations.append(time.perf_counter() - t1)
     dt = time.perf_counter() - t0
-    scale = (res * res) / float(args.res * args.res)
-    value = args.steps / dt * scale
-    sample = ("%d substeps of the same scene at %dx%d on %d host threads (reference ThreadPool = all cores); rate x %.4f "
-              "(cell-count ratio) to express it at %dx%d -- favourable to the reference, whose rebin stage is superlinear"
-              % (args.steps, res, res, cores, scale, args.res, args.res))
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3 / scale, "higher_is_better": True, "scaling": "weak",
+    steps = len(durations)
+    stats = s.stats()
+    s.close()
+    value = steps / dt
+    secondary = None
+    if args.res != REFERENCE_SAMPLE_RES and os.environ.get("FS2D_REF_SECONDARY", "1") != "0":
+        s2 = make_reference(REFERENCE_SAMPLE_RES, tmp)
+        reference_substep(s2)
+        t1 = time.perf_counter()
+        n2 = 0
+        while n2 < 2 or (time.perf_counter() - t1 < 10.0 and n2 < 8):
+            reference_substep(s2)
+            n2 += 1
+        d2 = time.perf_counter() - t1
+        s2.close()
+        secondary = {"resolution": REFERENCE_SAMPLE_RES, "substeps": n2, "substeps_per_s": n2 / d2,
+                     "note": "same scene at %dx%d, not scaled, not used for `value`" % (REFERENCE_SAMPLE_RES, REFERENCE_SAMPLE_RES)}
+    sample = ("%d real substeps of the workload itself (%dx%d, %d particles) from frame 0 on %d host threads: %s s each "
+              "(first from rest; later ones pay the reference's rebinParticles, which is superlinear in moved particles); "
+              "scene set-up %.0f s not timed; requested --steps %d --warmup %d, stopped by the %.0f s wall budget"
+              % (steps, args.res, args.res, particles, cores, "/".join("%.1f" % d for d in durations), init_s, args.steps,
+                 args.warmup, budget))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": 0, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.res), "sample_resolution": res, "scale_to_workload": scale},
+            "config": {"workload": workload_name(args.res), "cells": args.res * args.res, "particles": particles,
+                       "pcg_iterations_last_frame": {"pressure": stats["pressure_iters"], "density": stats["density_iters"]}},
+            "requested": {"steps": args.steps, "warmup": args.warmup},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+            "secondary_sample": secondary,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 def cpu_baseline(args, tmp, budget_s=25.0):
-    """The reference's CPU path on this host, bounded: substeps of the 1024^2 scene for ~budget_s."""
+    """The reference's CPU path on this host, bounded (~25 s): substeps of the same scene at 1024^2, rate scaled by the
+    cell ratio. (`--impl reference` runs the workload itself at full size; that takes minutes.)"""
     res = REFERENCE_SAMPLE_RES
     s = make_reference(res, tmp)
     reference_substep(s)  # warm-up (first substep also pays first-touch allocation)
@@ -179,10 +210,94 @@ def cpu_baseline(args, tmp, budget_s=25.0):
     scale = (res * res) / float(args.res * args.res)
     out = {"value": n / dt * scale, "unit": UNIT, "cores": s.threads, "kind": "reference",
            "sample": "%d substeps of the same scene at %dx%d (%.1f s, %.0f ms/substep), rate x %.4f (cell ratio) to express it "
-                     "at %dx%d; unmodified reference sources, flags -O3 -mavx2 -ffast-math, ThreadPool = all host threads"
+                     "at %dx%d -- favourable to the reference, whose rebin stage is superlinear; unmodified reference sources, "
+                     "flags -O3 -mavx2 -ffast-math, ThreadPool = all host threads. The full-size measurement is "
+                     "`bench.py --impl reference`."
                      % (n, res, res, dt, dt / n * 1e3, scale, args.res, args.res)}
     s.close()
     return out
+
+
+# --------------------------------------------------------------------------------------- multi-GPU self checks
+MG_PARITY_RES = 1024
+MG_PARITY_STEPS = 6
+
+
+def mg_parity_check(make_solver, total, world, rank, torch, dist):
+    """The multi-process slab path against a single handle, inside the bench run: every rank steps (a) its slab of a
+    1024^2 dam break together with the other ranks and (b) a private single-handle solver of the same scene on its own
+    GPU, both for MG_PARITY_STEPS substeps from rest with BASELINE's settings (density 0.5: both PCG solves of every
+    substep run into the 200-iteration cap, i.e. a fixed iteration count), then compares the rows it owns: particle
+    count, material grid (bit-exact), U and pressure (relative L2: the dot-product partials are grouped by rank, which
+    is the only arithmetic the decomposition changes)."""
+    import numpy as np
+    scene = scene_for(MG_PARITY_RES)
+    slab = make_solver(scene, "mgp_slab")
+    single = make_solver(scene, "mgp_single", slab=False)
+    slab.prepare()
+    single.prepare()
+    for _ in range(MG_PARITY_STEPS):
+        slab.step_substep()
+        single.step_substep()
+    ds, d1 = slab.device(num_properties=2), single.device(num_properties=2)
+    lo, hi, _ = ds.slab_rows()
+    I, J = slab.I, slab.J
+    p1, _, _ = d1.download_particles()
+    own1 = int(((np.floor(p1[:, 0]) >= lo) & (np.floor(p1[:, 0]) < hi)).sum())
+
+    def rows(a, per_row):
+        return a.reshape(-1, per_row)[lo:hi]
+
+    mat_equal = bool(np.array_equal(rows(ds.download("MATERIAL"), J), rows(d1.download("MATERIAL"), J)))
+    cnt_equal = bool(np.array_equal(rows(ds.download("COUNTS"), J), rows(d1.download("COUNTS"), J)))
+
+    def sq(name, per_row):
+        a, b = rows(ds.download(name), per_row).astype(np.float64), rows(d1.download(name), per_row).astype(np.float64)
+        return float(((a - b) ** 2).sum()), float((b ** 2).sum()), float(a.sum()), float(b.sum())
+
+    u, p = sq("U", J), sq("PRESSURE", J)
+    own_slab = slab.particle_count()
+    out = {"resolution": MG_PARITY_RES, "substeps": MG_PARITY_STEPS, "ranks": world,
+           "particles_slab_total": total(own_slab), "particles_single": single.particle_count(),
+           "particles_owned_rows_equal": bool(total(int(own_slab == own1)) == world),
+           "material_rows_equal": bool(total(int(mat_equal)) == world), "counts_rows_equal": bool(total(int(cnt_equal)) == world),
+           "u_rel_l2": (total(u[0]) / max(total(u[1]), 1e-300)) ** 0.5, "pressure_rel_l2": (total(p[0]) / max(total(p[1]), 1e-300)) ** 0.5,
+           "sum_u": {"slab": total(u[2]), "single": total(u[3])}, "sum_pressure": {"slab": total(p[2]), "single": total(p[3])},
+           "pcg_iterations": {"slab": slab.stats()["pressure_iters"], "single": single.stats()["pressure_iters"]}}
+    out["ok"] = bool(out["particles_slab_total"] == out["particles_single"] and out["particles_owned_rows_equal"]
+                     and out["material_rows_equal"] and out["counts_rows_equal"] and out["u_rel_l2"] < 1e-5
+                     and out["pressure_rel_l2"] < 1e-5)
+    slab.close()
+    single.close()
+    return out
+
+
+def config5_region(make_solver, timed, total, world, local_rank, torch, capi, args):
+    """BASELINE config 5 inside the N-GPU run: the flip dam break at 8192^2 with the near-full tank (fluid block
+    (5,3)-(47,47): ~397 M particles), slab-decomposed over the N GPUs; a few substeps after warm-up, timed like `value`."""
+    global DENSE_FILL
+    keep = DENSE_FILL
+    DENSE_FILL = args.config5_fill == "dense"
+    try:
+        t0 = time.perf_counter()
+        sv = make_solver(scene_for(8192), "config5")
+        sv.prepare()
+        setup_s = time.perf_counter() - t0
+        d = sv.device(num_properties=2)
+        st = torch.cuda.ExternalStream(capi.lib().fs2d_stream(d.h), device=torch.device("cuda", local_rank))
+        for _ in range(2):
+            sv.step_substep()
+        steps = args.config5_steps
+        ms = timed(sv.step_substep, steps, d=d, on=st)
+        stats = sv.stats()
+        out = {"workload": workload_name(8192), "cells": 8192 * 8192, "particles": total(sv.particle_count()), "n_gpus": world,
+               "steps": steps, "warmup": 2, "value": steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+               "pcg_active_cells": total(int(d.pcg_active_cells())), "setup_s": round(setup_s, 1),
+               "pcg_iterations_last_frame": {"pressure": stats["pressure_iters"], "density": stats["density_iters"]}}
+        sv.close()
+        return out
+    finally:
+        DENSE_FILL = keep
 
 
 # --------------------------------------------------------------------------------------- our arm
@@ -201,19 +316,25 @@ def run_ours(args, rank, world, local_rank):
 
     tmp = tempfile.mkdtemp(prefix="fs2d_bench_")
     res = args.res
-    path = scenes.write_scene(scene_for(res), os.path.join(tmp, "scene_%d_r%d.json" % (res, rank)))
-    # N > 1: ONE scene decomposed into row slabs, one rank per GPU (strong scaling). The ranks exchange halo rows,
-    # migrating particles and the PCG reduction partials through peer-mapped device memory (CUDA IPC over NVLink);
-    # torch.distributed only carries the 256-byte IPC blobs at start-up and the timing reduction.
-    solver = host_api.Solver(path, quiet=True, device=local_rank, slab=(rank, world) if world > 1 else None)
-    if world > 1:
-        blob = torch.frombuffer(bytearray(solver.slab_export()), dtype=torch.uint8).cuda()
-        blobs = [torch.empty_like(blob) for _ in range(world)]
-        dist.all_gather(blobs, blob)
-        for r in range(world):
-            if r != rank:
-                solver.slab_connect(r, bytes(blobs[r].cpu().numpy().tobytes()))
-        dist.barrier()
+
+    def make_solver(scene, tag, slab=True):
+        """JsonSceneReader::loadJson on every rank. slab: ONE scene decomposed into row slabs, one rank per GPU (strong
+        scaling): the ranks exchange halo rows, migrating particles and the PCG reduction partials through peer-mapped
+        device memory (CUDA IPC over NVLink); torch.distributed only carries the 256-byte IPC blobs at start-up and the
+        timing reductions."""
+        path = scenes.write_scene(scene, os.path.join(tmp, "%s_r%d.json" % (tag, rank)))
+        sv = host_api.Solver(path, quiet=True, device=local_rank, slab=(rank, world) if (world > 1 and slab) else None)
+        if world > 1 and slab:
+            blob = torch.frombuffer(bytearray(sv.slab_export()), dtype=torch.uint8).cuda()
+            blobs = [torch.empty_like(blob) for _ in range(world)]
+            dist.all_gather(blobs, blob)
+            for r in range(world):
+                if r != rank:
+                    sv.slab_connect(r, bytes(blobs[r].cpu().numpy().tobytes()))
+            dist.barrier()
+        return sv
+
+    solver = make_solver(scene_for(res), "scene_%d" % res)
     solver.prepare()  # frame-0 rasterisation + seeding + upload: set-up, not timed
     dev = solver.device(num_properties=2)
     N = solver.N
@@ -230,20 +351,21 @@ def run_ours(args, rank, world, local_rank):
         return type(v)(t.item())
     stream = torch.cuda.ExternalStream(capi.lib().fs2d_stream(dev.h), device=torch.device("cuda", local_rank))
 
-    def barrier():
+    def barrier(d=None):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        dev.synchronize()
+        (d or dev).synchronize()
 
-    def timed(fn, steps):
-        barrier()
+    def timed(fn, steps, d=None, on=None):
+        """K calls of fn bracketed by barrier + synchronize, CUDA events on the solver's stream, max over ranks."""
+        barrier(d)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
+        e0.record(on or stream)
         for _ in range(steps):
             fn()
-        e1.record(stream)
-        barrier()
+        e1.record(on or stream)
+        barrier(d)
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -254,6 +376,7 @@ def run_ours(args, rank, world, local_rank):
         solver.step_substep()
     dev.pcg_profile(True)
     launches0 = solver.kernel_launches()
+    particles_before = total(solver.particle_count())
     sampler = ClockSampler(local_rank)
     sampler.start()
     ms = timed(solver.step_substep, args.steps)
@@ -328,6 +451,15 @@ def run_ours(args, rank, world, local_rank):
                        "fs2d_download_particles_packed into it (positions, velocities, %d property columns, storage-bin byte)" % K
                        + (" (every rank moves the particles of its slab; bytes summed over ranks)" if world > 1 else "")}
 
+    # ---- N > 1: the run proves itself and carries BASELINE config 5
+    mg_parity = mg_parity_check(make_solver, total, world, rank, torch, dist) if world > 1 and not args.no_mg_parity else None
+    config_5 = None
+    if world > 1 and not args.no_config5:
+        solver.close()
+        del hostbuf
+        torch.cuda.empty_cache()
+        config_5 = config5_region(make_solver, timed, total, world, local_rank, torch, capi, args)
+
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -362,7 +494,10 @@ def run_ours(args, rank, world, local_rank):
         for k in ("k1_phase", "k2_phase"):
             r[k]["frac"] = r[k]["achieved"] / peak
     roofline = {"bound": "hbm", "kernel": "pcgSolveKernel", "achieved": dense["achieved"], "peak": peak, "unit": "GB/s",
-                "frac": dense["achieved"] / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                "frac": dense["achieved"] / peak, "traffic": ncu_traffic() if (world == 1 and res == 4096 and not DENSE_FILL) else None,
+                "traffic_source": "profiles/pcg_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` "
+                                  "capture of this kernel on this workload (1 GPU, dense walk); null on any other configuration",
+                "peak_source": peak_src,
                 "bytes_per_launch": dense["bytes_per_launch"], "avg_launch_ms": dense["avg_launch_ms"],
                 "launches_timed": dense["launches_timed"], "iterations_per_launch": dense["iterations_per_launch"],
                 "k1_phase": dense["k1_phase"], "k2_phase": dense["k2_phase"],
@@ -381,9 +516,10 @@ def run_ours(args, rank, world, local_rank):
     base = cpu_baseline(args, tmp) if world == 1 and not args.no_cpu_baseline else None
     line = {"metric": METRIC, "value": args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak" if world == 1 else "strong",
+            "scaling": "strong",  # one scene of fixed size on 1 .. N GPUs
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(res), "cells": N, "particles": particles_all,
+                       "particles_timed_region": {"start": particles_before, "end": particles_all},
                        "l2": "every PCG vector (%d MB%s) and the particle arrays exceed the 126 MB L2"
                              % (own_cells * 8 // 2 ** 20, " per rank" if world > 1 else ""),
                        "parallelism": "1 GPU" if world == 1 else
@@ -394,6 +530,10 @@ def run_ours(args, rank, world, local_rank):
                        "pcg_walk": "active tiles (%d of %d cells)" % (active_cells_all, N),
                        "stage_ms_per_substep_last_frame": stage_ms},
             "roofline": roofline, "cpu_baseline": base, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+    if mg_parity is not None:
+        line["mg_parity"] = mg_parity
+    if config_5 is not None:
+        line["config_5"] = config_5
     print(json.dumps(line), flush=True)
 
 
@@ -407,6 +547,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fill", default="reference", choices=["reference", "dense"])
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end region (very large particle counts)")
+    ap.add_argument("--no-mg-parity", action="store_true", help="N > 1: skip the slab-vs-single-handle self check")
+    ap.add_argument("--no-config5", action="store_true", help="N > 1: skip the 8192^2 region (BASELINE config 5)")
+    ap.add_argument("--config5-fill", default="dense", choices=["reference", "dense"])
+    ap.add_argument("--config5-steps", type=int, default=3)
     args = ap.parse_args()
     global DENSE_FILL
     DENSE_FILL = args.fill == "dense"
