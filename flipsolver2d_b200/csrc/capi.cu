@@ -169,6 +169,7 @@ int allocAll(Ctx *realCtx)
     FS2D_TRY(devAlloc(*ctxPlan, &ctx->d_counter, 16));
     FS2D_TRY(devAlloc(*ctxPlan, &ctx->d_fscratch, 4096));
     FS2D_TRY(devAlloc(*ctxPlan, &ctx->mail, 1));
+    FS2D_TRY(devAlloc(*ctxPlan, &ctx->haloLL, 8 * static_cast<int64_t>(ctx->J)));
     FS2D_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->heap), plan.total));
     ctx->heapBytes = plan.total;
     {

@@ -117,6 +117,10 @@ struct SlabMail
     unsigned long long data[2];    // "my data of exchange #seq has landed in your memory"
     long long counts[2][4];        // particle exchange: records pushed by neighbour [from] {owned, ghosts}
     SlabGatherSlot gather[2][FS2D_MAX_RANKS];      // double buffered by the parity of the gather sequence
+    unsigned long long mode[2][FS2D_MAX_RANKS];    // whole-solve kernels: {tag, mode} of rank r for the solve of this parity
+                                                   // (1 = resident kernel: talks LL halo rows, 2 = streaming kernel)
+    unsigned long long edgeTiles[2][FS2D_MAX_RANKS][2];  // with mode 1: bit tj set = tile tj of rank r's first / last tile row
+                                                         // is active (a skipped tile pushes nothing: its halo values are 0)
     int error;                     // set when a spin loop timed out
     int pad[3];
 };
@@ -263,6 +267,8 @@ struct fs2d_context
     unsigned char *heap = nullptr;
     size_t heapBytes = 0;
     SlabMail *mail = nullptr;         // inside the heap
+    unsigned long long *haloLL = nullptr;  // inside the heap: halo rows of q / z received as self-validating words,
+                                           // [from lower / upper neighbour][q / z][J][lo, hi] (pcgResidentKernel)
     SlabState slab;
 
     // ---- timing

@@ -91,6 +91,7 @@ struct MgArgs
     SlabMail *peerMail[FS2D_MAX_RANKS];
     double *loOut1, *hiOut1;              // the row neighbours' copies of out1 (nullptr at the domain ends)
     int iterLimit;
+    unsigned long long *haloLL, *loHaloLL, *hiHaloLL;  // LL halo-row buffers: own, lower neighbour's, upper neighbour's
     unsigned long long *timeline;         // debug: 8 globaltimer stamps per phase (nullptr normally)
     int debug;                            // FS2D_MG_DEBUG bit mask (timing experiments only; results are wrong when set):
                                           // 1 = do not wait for the peers' partials, 2 = no halo-row stores into the peers,
@@ -848,6 +849,84 @@ __device__ __forceinline__ unsigned int llTag(const MgArgs &m, int phase)
     return static_cast<unsigned int>((m.solveTag >> 4) + static_cast<unsigned long long>(phase) + 1ull);  // solveSeq * 65536 + phase + 1
 }
 
+// ------------------------------------------------------------------ LL halo rows between resident kernels
+// A slab-boundary row of q (K1) / z (K2) pushed into the neighbour's array has to be ordered before the barrier that
+// publishes it: a system-scope fence behind remote stores waits for their acknowledgement (~3 us per phase, measured on
+// 2 B200: 13.4 -> 10.7 us). When BOTH neighbours run pcgResidentKernel the row travels instead as self-validating
+// 8-byte words {32 payload bits, 32-bit phase tag} (the LL idea again): no fence on the producer, the consumer's ring
+// threads poll the two words of their cell. Which kernel a rank runs is decided on the device (tile count), so the
+// kernels tell their row neighbours at the start of every solve (SlabMail::mode) and fall back to the plain push +
+// fence towards a neighbour that streams.
+enum { SOLVE_MODE_RESIDENT = 1, SOLVE_MODE_STREAMING = 2 };
+
+template <bool MG> __device__ __forceinline__ void solveModePublish(const MgArgs &m, int mode, unsigned long long firstRowTiles = 0,
+                                                                    unsigned long long lastRowTiles = 0)
+{
+    if (!MG) return;
+    const unsigned long long word = (static_cast<unsigned long long>(llTag(m, 0)) << 32) | static_cast<unsigned long long>(mode);
+    const int par = m.ringBase ? 1 : 0;
+    for (int d = -1; d <= 1; d += 2)
+    {
+        const int r = m.rank + d;
+        if (r < 0 || r >= m.world) continue;
+        SlabMail *pm = m.peerMail[r];
+        if (mode == SOLVE_MODE_RESIDENT)
+        {
+            *reinterpret_cast<volatile unsigned long long *>(&pm->edgeTiles[par][m.rank][0]) = firstRowTiles;
+            *reinterpret_cast<volatile unsigned long long *>(&pm->edgeTiles[par][m.rank][1]) = lastRowTiles;
+            __threadfence_system();  // once per solve: the masks are in place before the word that announces them
+        }
+        *reinterpret_cast<volatile unsigned long long *>(&pm->mode[par][m.rank]) = word;
+    }
+}
+
+// mode of the row neighbour `r` for this solve (0 when there is none, -1 when it never answered)
+template <bool MG> __device__ __forceinline__ int solveModeOf(const MgArgs &m, int r)
+{
+    if (!MG || r < 0 || r >= m.world) return 0;
+    const int par = m.ringBase ? 1 : 0;
+    const unsigned int want = llTag(m, 0);
+    const long long t0 = clock64();
+    for (;;)
+    {
+        unsigned long long w;
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(&m.mail->mode[par][r]) : "memory");
+        if (static_cast<unsigned int>(w >> 32) == want) return static_cast<int>(w & 0xffffffffull);
+        if (clock64() - t0 > MG_SPIN_LIMIT)
+        {
+            m.mail->error = 1;
+            return -1;
+        }
+    }
+}
+
+__device__ __forceinline__ void llHaloStore(unsigned long long *buf, int side, int kind, long long J, long long gj, double v, unsigned int tag)
+{
+    const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(v));
+    unsigned long long *dst = buf + ((static_cast<long long>(side) * 2 + kind) * J + gj) * 2;
+    const unsigned long long t = static_cast<unsigned long long>(tag) << 32;
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"((bits & 0xffffffffull) | t), "l"((bits >> 32) | t) : "memory");
+}
+
+__device__ __forceinline__ double llHaloLoad(const unsigned long long *buf, int side, int kind, long long J, long long gj, unsigned int tag,
+                                             int *error)
+{
+    const unsigned long long *src = buf + ((static_cast<long long>(side) * 2 + kind) * J + gj) * 2;
+    const long long t0 = clock64();
+    for (;;)
+    {
+        unsigned long long a, b;
+        asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(src) : "memory");
+        if (static_cast<unsigned int>(a >> 32) == tag && static_cast<unsigned int>(b >> 32) == tag)
+            return __longlong_as_double(static_cast<long long>((a & 0xffffffffull) | (b << 32)));
+        if (clock64() - t0 > MG_SPIN_LIMIT)
+        {
+            *error = 1;
+            return 0.0;
+        }
+    }
+}
+
 // Threads 0 .. 4*world-1 of the calling CTA store one word each into rank (t >> 2)'s mail.
 template <bool MG> __device__ __forceinline__ void llPublish(const MgArgs &m, int phase, double v0, double v1)
 {
@@ -880,9 +959,12 @@ template <bool MG> __device__ __forceinline__ bool llCollect(const MgArgs &m, in
     {
         const unsigned long long *src = &m.mail->ll[m.ringBase + (phase & 7)][lane >> 2].w[lane & 3];
         const long long t0 = clock64();
+        const bool relaxedPoll = MG && (m.debug & 32);  // A/B: poll with relaxed loads, one fence after the last word arrived
         for (;;)
         {
-            if (MG)
+            if (relaxedPoll)
+                asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
+            else if (MG)
                 asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
             else
                 asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
@@ -896,6 +978,7 @@ template <bool MG> __device__ __forceinline__ bool llCollect(const MgArgs &m, in
         }
     }
     ok = __all_sync(0xffffffffu, ok);
+    if (MG && (m.debug & 32)) __threadfence_system();
     double s = 0.0, x = 0.0;
     for (int r = 0; r < m.world; r++)
     {
@@ -1064,6 +1147,7 @@ struct SolveArgs
     PcgArgs a;                            // operator tables, partials, scalars, trace, tol, active-tile list
     double *z, *q, *x, *s[2], *r[2];
     double *loQ, *hiQ, *loZ, *hiZ;        // the row neighbours' copies of q and z (slab mode)
+    const int *tileFlags;                 // activity flag of each of the numTiles tiles this rank walks (nullptr: dense walk)
     int numTiles;                         // tiles of the dense walk (active walk: *a.activeCount)
     int iterLimit;
     unsigned int *ticket;                 // zeroed before the launch
@@ -1365,6 +1449,7 @@ __global__ void __launch_bounds__(NT, 2) pcgSolveKernel(SolveArgs g, MgArgs mg, 
     const bool scribe = blockIdx.x == 0 && tid == 0;  // keeps PcgScalars / the trace for the host
     PcgScalars *sc = g.a.sc;
     if (sc->pad) return;  // pcgResidentKernel (launched just before) took this solve
+    if (MG && scribe) solveModePublish<MG>(mg, SOLVE_MODE_STREAMING);  // row neighbours running the resident kernel push plain rows + fence
     if (tid < 8) sm.preTbl[tid] = g.a.pre[tid];
     if (tid == 0)
     {
@@ -1682,7 +1767,23 @@ template <bool MG> __global__ void __launch_bounds__(RNT, 1) pcgResidentKernel(S
         return;  // too many tiles to hold (or nothing to do): PcgScalars::pad stays 0 and the streaming kernel runs
     if (blockIdx.x >= P) return;
     const bool scribe = blockIdx.x == 0 && tid == 0;
-    if (scribe) sc->pad = 1;  // tells the streaming kernel and pcgFinalizeKernel that this solve is done here
+    if (scribe)
+    {
+        sc->pad = 1;  // tells the streaming kernel and pcgFinalizeKernel that this solve is done here
+        if (MG)
+        {
+            // which tiles of my first / last tile row are walked (one bit per tile column; more than 64 columns: no LL)
+            unsigned long long first = 0, last = 0;
+            const int tj = g.a.tilesJ;
+            if (tj <= 64 && g.tileFlags)
+                for (int k = 0; k < tj; k++)
+                {
+                    if (g.tileFlags[k]) first |= 1ull << k;
+                    if (g.tileFlags[g.numTiles - tj + k]) last |= 1ull << k;
+                }
+            solveModePublish<MG>(mg, (tj <= 64 && g.tileFlags) ? SOLVE_MODE_RESIDENT : SOLVE_MODE_STREAMING, first, last);
+        }
+    }
     if (tid < 8) sm.preTbl[tid] = g.a.pre[tid];
     if (tid == 0)
     {
@@ -1690,11 +1791,33 @@ template <bool MG> __global__ void __launch_bounds__(RNT, 1) pcgResidentKernel(S
         sm.ok = mgCollect(mg, 0, true, &s0, &m0) ? 1 : 0;  // phase 0: rhs.rhs and max|rhs| from pcgInitKernel<true>
         sm.bc[0] = s0;
         sm.bc[1] = m0;
+        sm.isLast = 0;
+        if (MG && sm.ok && s0 == s0 && m0 > 1.0e-15 && !(mg.debug & 16))
+        {
+            // both row neighbours must talk LL for a boundary to use it (bit 0: lower, bit 1: upper)
+            const int lo = solveModeOf<MG>(mg, mg.rank - 1), hi = solveModeOf<MG>(mg, mg.rank + 1);
+            if (lo < 0 || hi < 0) sm.ok = 0;
+            const bool mine = g.a.tilesJ <= 64 && g.tileFlags;
+            sm.isLast = (mine && lo == SOLVE_MODE_RESIDENT ? 1 : 0) | (mine && hi == SOLVE_MODE_RESIDENT ? 2 : 0);
+            __threadfence_system();
+            const int par = mg.ringBase ? 1 : 0;
+            // the lower neighbour's LAST tile row feeds my halo row below rowBegin, the upper neighbour's FIRST my row rowEnd
+            sm.pub[0] = 0.0;
+            sm.pub[1] = 0.0;
+            unsigned long long mlo = 0, mhi = 0;
+            if (sm.isLast & 1) asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(mlo) : "l"(&mg.mail->edgeTiles[par][mg.rank - 1][1]) : "memory");
+            if (sm.isLast & 2) asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(mhi) : "l"(&mg.mail->edgeTiles[par][mg.rank + 1][0]) : "memory");
+            sm.pub[0] = __longlong_as_double(static_cast<long long>(mlo));
+            sm.pub[1] = __longlong_as_double(static_cast<long long>(mhi));
+        }
     }
     __syncthreads();
     double sigma = sm.bc[0];
     const double max0 = sm.bc[1];
     const bool lost0 = sm.ok == 0;
+    const bool loLL = MG && (sm.isLast & 1), hiLL = MG && (sm.isLast & 2);
+    const unsigned long long loTiles = loLL ? static_cast<unsigned long long>(__double_as_longlong(sm.pub[0])) : 0ull;
+    const unsigned long long hiTiles = hiLL ? static_cast<unsigned long long>(__double_as_longlong(sm.pub[1])) : 0ull;
     __syncthreads();
     if (lost0 || !(max0 > 1.0e-15))  // a lost peer, or VOps::isZero (vmath.cpp:47-58): x = 0 (pcgInitKernel), zero iterations
     {
@@ -1715,6 +1838,7 @@ template <bool MG> __global__ void __launch_bounds__(RNT, 1) pcgResidentKernel(S
 
     // ---- per-tile constants in registers: origin, ring cell, operator bytes of the thread's cells
     int ti0[RES_TPC], tj0[RES_TPC], ringPos[RES_TPC];
+    int ringSrc[RES_TPC];                      // 0: the local q / z array, 1 / 2: LL halo row from the lower / upper neighbour
     long long ringN[RES_TPC];
     unsigned int rowBits[RES_TPC];             // 4 x rowInfo byte
     unsigned int validBits[RES_TPC];           // bit k: cell k of this thread lies inside the matrix
@@ -1726,6 +1850,7 @@ template <bool MG> __global__ void __launch_bounds__(RNT, 1) pcgResidentKernel(S
     {
         ti0[t] = tj0[t] = 0;
         ringPos[t] = -1;
+        ringSrc[t] = 0;
         ringN[t] = -1;
         rowBits[t] = 0;
         preBits[t] = 0;
@@ -1739,9 +1864,23 @@ template <bool MG> __global__ void __launch_bounds__(RNT, 1) pcgResidentKernel(S
             ti0[t] = ti * TR;
             tj0[t] = tj * TC;
             resRingCell(tid, ti0[t], tj0[t], I, J, N, &ringPos[t], &ringN[t]);
-            if (MG)
-                remote = remote || (g.loQ && mg.rowBegin >= ti0[t] && mg.rowBegin < ti0[t] + TR) ||
-                         (g.hiQ && mg.rowEnd - 1 >= ti0[t] && mg.rowEnd - 1 < ti0[t] + TR);
+            if (MG && ringN[t] >= 0)
+            {
+                // a ring value that lives on a neighbour's row (wrap columns included: the linear index decides)
+                const long long srcRow = ringN[t] / J;
+                const int srcTile = static_cast<int>((ringN[t] - srcRow * J) / TC);
+                if (loLL && srcRow == mg.rowBegin - 1) ringSrc[t] = 1;
+                if (hiLL && srcRow == mg.rowEnd) ringSrc[t] = 2;
+                // a tile the neighbour skips pushes nothing: every vector is identically zero there
+                if (ringSrc[t] && !(((ringSrc[t] == 1 ? loTiles : hiTiles) >> srcTile) & 1ull))
+                {
+                    ringSrc[t] = 0;
+                    ringN[t] = -1;
+                }
+            }
+            if (MG && !(mg.debug & 2))
+                remote = remote || (g.loQ && !loLL && mg.rowBegin >= ti0[t] && mg.rowBegin < ti0[t] + TR) ||
+                         (g.hiQ && !hiLL && mg.rowEnd - 1 >= ti0[t] && mg.rowEnd - 1 < ti0[t] + TR);
             // s = 0, r = rhs on the halo-extended tile (r0 = z0 = rhs, linearsolver.cpp:32-46), T = z0 interior
             ResTile &rt = sm.t[t];
             for (int e = tid; e < PTILE; e += RNT)
@@ -1787,7 +1926,18 @@ template <bool MG> __global__ void __launch_bounds__(RNT, 1) pcgResidentKernel(S
         double accDot = 0.0, accMax = 0.0, unused = 0.0;
         double ringV[RES_TPC];
 #pragma unroll
-        for (int t = 0; t < RES_TPC; t++) ringV[t] = (t < myTiles && ringN[t] >= 0) ? __ldcg(g.z + ringN[t]) : 0.0;
+        for (int t = 0; t < RES_TPC; t++)
+        {
+            ringV[t] = 0.0;
+            if (t < myTiles && ringN[t] >= 0)
+            {
+                // z of K2(i - 1) = phase 2i; before the first iteration z = rhs, which every rank computed for its halo rows itself
+                if (MG && ringSrc[t] && i > 0)
+                    ringV[t] = llHaloLoad(mg.haloLL, ringSrc[t] - 1, 1, J, ringN[t] % J, llTag(mg, 2 * i), &mg.mail->error);
+                else
+                    ringV[t] = __ldcg(g.z + ringN[t]);
+            }
+        }
 #pragma unroll
         for (int t = 0; t < RES_TPC; t++)
             if (t < myTiles)
@@ -1824,10 +1974,24 @@ template <bool MG> __global__ void __launch_bounds__(RNT, 1) pcgResidentKernel(S
                         const double o = rowA(static_cast<uint8_t>(rowBits[t] >> (8 * k)), g.a.scale, c, rt.S[p - PSW], rt.S[p + PSW], rt.S[p - 1], rt.S[p + 1]);
                         rt.T[row * TC + lc] = o;
                         g.q[n] = o;
-                        if (MG)
+                        if (MG && !(mg.debug & 2))
                         {
-                            if (gi == mg.rowBegin && g.loQ) g.loQ[n] = o;
-                            if (gi == mg.rowEnd - 1 && g.hiQ) g.hiQ[n] = o;
+                            // my first row is the lower neighbour's halo row "from above" (its side 1), my last row the
+                            // upper neighbour's halo row "from below" (its side 0)
+                            if (gi == mg.rowBegin && g.loQ)
+                            {
+                                if (loLL)
+                                    llHaloStore(mg.loHaloLL, 1, 0, J, gj, o, llTag(mg, 2 * i + 1));
+                                else
+                                    g.loQ[n] = o;
+                            }
+                            if (gi == mg.rowEnd - 1 && g.hiQ)
+                            {
+                                if (hiLL)
+                                    llHaloStore(mg.hiHaloLL, 0, 0, J, gj, o, llTag(mg, 2 * i + 1));
+                                else
+                                    g.hiQ[n] = o;
+                            }
                         }
                         accDot += o * c;
                     }
@@ -1844,7 +2008,17 @@ template <bool MG> __global__ void __launch_bounds__(RNT, 1) pcgResidentKernel(S
         // ---- K2(i): r -= alpha q (interior from T, ring from the neighbours' q); z = M r; sigma' = z.r; err = max|r|
         accDot = 0.0;
 #pragma unroll
-        for (int t = 0; t < RES_TPC; t++) ringV[t] = (t < myTiles && ringN[t] >= 0) ? __ldcg(g.q + ringN[t]) : 0.0;
+        for (int t = 0; t < RES_TPC; t++)
+        {
+            ringV[t] = 0.0;
+            if (t < myTiles && ringN[t] >= 0)
+            {
+                if (MG && ringSrc[t])
+                    ringV[t] = llHaloLoad(mg.haloLL, ringSrc[t] - 1, 0, J, ringN[t] % J, llTag(mg, 2 * i + 1), &mg.mail->error);
+                else
+                    ringV[t] = __ldcg(g.q + ringN[t]);
+            }
+        }
 #pragma unroll
         for (int t = 0; t < RES_TPC; t++)
             if (t < myTiles)
@@ -1877,10 +2051,22 @@ template <bool MG> __global__ void __launch_bounds__(RNT, 1) pcgResidentKernel(S
                         const double o = rowM(static_cast<uint16_t>(preBits[t] >> (16 * k)), sm.preTbl, c, rt.R[p - PSW], rt.R[p + PSW], rt.R[p - 1], rt.R[p + 1]);
                         rt.T[row * TC + lc] = o;
                         g.z[n] = o;
-                        if (MG)
+                        if (MG && !(mg.debug & 2))
                         {
-                            if (gi == mg.rowBegin && g.loZ) g.loZ[n] = o;
-                            if (gi == mg.rowEnd - 1 && g.hiZ) g.hiZ[n] = o;
+                            if (gi == mg.rowBegin && g.loZ)
+                            {
+                                if (loLL)
+                                    llHaloStore(mg.loHaloLL, 1, 1, J, gj, o, llTag(mg, 2 * i + 2));
+                                else
+                                    g.loZ[n] = o;
+                            }
+                            if (gi == mg.rowEnd - 1 && g.hiZ)
+                            {
+                                if (hiLL)
+                                    llHaloStore(mg.hiHaloLL, 0, 1, J, gj, o, llTag(mg, 2 * i + 2));
+                                else
+                                    g.hiZ[n] = o;
+                            }
                         }
                         accDot += o * c;
                         accMax = fmax(accMax, fabs(c));
@@ -2432,6 +2618,9 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
         for (int r = 0; r < sl.world; r++)
             mg.peerMail[r] = reinterpret_cast<SlabMail *>(sl.peerHeap[r] + (reinterpret_cast<unsigned char *>(ctx->mail) - ctx->heap));
         mg.iterLimit = iterLimit;
+        mg.haloLL = ctx->haloLL;
+        mg.loHaloLL = sl.rank > 0 ? reinterpret_cast<unsigned long long *>(sl.peerHeap[sl.rank - 1] + (reinterpret_cast<unsigned char *>(ctx->haloLL) - ctx->heap)) : nullptr;
+        mg.hiHaloLL = sl.rank + 1 < sl.world ? reinterpret_cast<unsigned long long *>(sl.peerHeap[sl.rank + 1] + (reinterpret_cast<unsigned char *>(ctx->haloLL) - ctx->heap)) : nullptr;
         static const int mgDebug = std::getenv("FS2D_MG_DEBUG") ? std::atoi(std::getenv("FS2D_MG_DEBUG")) : 0;
         mg.debug = mgDebug;
         if (mgDebug & 8)
@@ -2495,6 +2684,7 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
         g.loZ = mgOn ? peerOf(mg.rank - 1, ctx->z) : nullptr;
         g.hiZ = mgOn ? peerOf(mg.rank + 1, ctx->z) : nullptr;
         g.numTiles = blocks;
+        g.tileFlags = active ? ctx->tileFlags : nullptr;
         g.iterLimit = iterLimit;
         g.ticket = &ctx->scalars->ticketS;
         FS2D_CUDA(cudaMemsetAsync(g.ticket, 0, sizeof(unsigned int), st));

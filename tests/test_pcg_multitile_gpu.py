@@ -225,7 +225,7 @@ def test_smoke_2048_rows_against_reference(sys2048, limit):
 
 
 @pytest.mark.parametrize("world,limit", [(2, 3), (4, 2), (2, 0)])
-@pytest.mark.parametrize("dense", [True, False, None], ids=["dense", "active", "resident"])
+@pytest.mark.parametrize("dense", [True, False, None, "mixed"], ids=["dense", "active", "resident", "mixed"])
 def test_slab_solve_with_many_tiles_per_cta(ref_mod, scene_dir, world, limit, dense):
     """pcgSolveKernel<MG = true> (row slabs; here the ranks share one GPU) with 3 - 8 tiles per CTA: the halo rows
     pushed into the neighbour, the machine-wide barrier and the pipelined walk together, against the reference."""
@@ -246,12 +246,15 @@ def test_slab_solve_with_many_tiles_per_cta(ref_mod, scene_dir, world, limit, de
         d.upload("MATERIAL", mat)
         d.set_step_dt(1.0 / 60.0)
         d.stage("build_matrix")
-        d.pcg_set_dense(bool(dense))
-        d.pcg_set_resident(dense is None)  # None: active walk through pcgResidentKernel<MG> (1 - 4 resident tiles per CTA)
+        # None: active walk through pcgResidentKernel<MG> (1 - 4 resident tiles per CTA; halo rows travel as LL words);
+        # "mixed": even ranks resident, odd ranks streaming -- the kernels interoperate (plain halo rows + fence)
+        resident = dense is None or (dense == "mixed" and d.rank % 2 == 0)
+        d.pcg_set_dense(dense is True)
+        d.pcg_set_resident(resident)
         d.pcg_set_grid_limit(limit)
     J = s.J
     outs = {}
-    for stepwise in ((False,) if dense is None else (False, True)):
+    for stepwise in ((False,) if dense in (None, "mixed") else (False, True)):
         for d in devs:
             d.pcg_set_stepwise(stepwise)
         res = capi.run_ranks([lambda d=d: d.pcg_solve(rhs, iters, 0.0) for d in devs])
@@ -262,7 +265,7 @@ def test_slab_solve_with_many_tiles_per_cta(ref_mod, scene_dir, world, limit, de
             assert nd == iters
         outs[stepwise] = x
         assert H.rel_l2(x, xr) < TOL, (stepwise, H.rel_l2(x, xr))
-    if dense is not None:
+    if dense in (True, False):
         assert np.array_equal(outs[False], outs[True])
     for d in devs:
         d.close()

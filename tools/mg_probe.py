@@ -33,7 +33,11 @@ mat = hs.host_grid("MATERIAL")
 I, J = hs.I, hs.J
 d = capi.Device(I, J, dx=50.0 / res, fluid_density=0.5, device=local)
 if world > 1:
-    d.slab_configure(rank, world)
+    # FS2D_PROBE_BALANCED=1: slab boundaries cut by particles per tile row (what bench.py / the host mirror use), so the
+    # boundaries run through the fluid and halo rows are really pushed; default: equal row counts
+    bounds = hs.slab_bounds(world) if os.environ.get("FS2D_PROBE_BALANCED") else None
+    d.slab_configure(rank, world, row_bounds=bounds)
+    out_bounds = None if bounds is None else [int(b) for b in bounds]
     blob = torch.frombuffer(bytearray(d.slab_export()), dtype=torch.uint8).cuda()
     blobs = [torch.empty_like(blob) for _ in range(world)]
     dist.all_gather(blobs, blob)
@@ -48,7 +52,8 @@ unit = (mat == capi.FLUID)
 rng = np.random.default_rng(3)
 rhs = np.where(unit, rng.standard_normal(I * J), 0.0)
 d.upload("RHS", rhs)
-out = {"rank": rank, "world": world, "res": res, "debug": os.environ.get("FS2D_MG_DEBUG", "0")}
+out = {"rank": rank, "world": world, "res": res, "debug": os.environ.get("FS2D_MG_DEBUG", "0"),
+       "resident": os.environ.get("FS2D_PCG_RESIDENT", "1"), "bounds": out_bounds if world > 1 else None}
 for dense in (True, False):
     d.pcg_set_dense(dense)
     d.pcg_solve_device(200, 0.0)
