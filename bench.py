@@ -375,6 +375,7 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(max(args.warmup, 3)):
         solver.step_substep()
     dev.pcg_profile(True)
+    dev.kernel_profile(True)
     launches0 = solver.kernel_launches()
     particles_before = total(solver.particle_count())
     sampler = ClockSampler(local_rank)
@@ -384,6 +385,8 @@ def run_ours(args, rank, world, local_rank):
     prof_ms, prof_n = dev.pcg_profile_read()
     solve_ms, solve_n = dev.pcg_profile_solves()
     dev.pcg_profile(False)
+    kgroups = dev.kernel_profile_read()
+    dev.kernel_profile(False)
     stats = solver.stats()
     particles = solver.particle_count()          # this rank's
     particles_all = total(particles)
@@ -511,6 +514,31 @@ def run_ours(args, rank, world, local_rank):
                                          note="default mode (timed region of `value`): tiles without matrix rows are skipped; "
                                               "the %d walked cells x 7 vectors fit the 126 MB L2, so these GB/s are not an HBM "
                                               "figure" % active_cells)}
+    # ---- transfer kernels: algorithmic bytes of SURVEY 8(d) (P particles, N cells, k float property columns; one centred
+    # parameter, the viscosity) over the device time of each kernel group in the timed region of `value` (CUDA events on
+    # the solver's stream around every call, fs2d_kernel_profile). These kernels are gathers with the reference's exact
+    # float expressions: ncu (profiles/r2_transfer_ncu_full_summary.csv) shows them bound by instruction issue / latency
+    # at low occupancy, not by DRAM -- the fractions say how far from the HBM roofline that leaves them.
+    Pn, Nn, kprops = float(particles), float(own_cells), 2.0
+    transfer_bytes = {"SORT": 2 * (16 + 4 * kprops) * Pn + 12 * Pn + 12 * Nn,
+                      "P2G": (16 + 4 * kprops) * Pn + (10 + 5 * 1) * Nn + 4 * Nn,
+                      "SDF": 8 * Pn + 4 * Nn + 4 * Nn + 2 * Nn,
+                      "DENSITY": 8 * Pn + 4 * Nn + 4 * Nn,
+                      "ADVECT+G2P": 32 * Pn + 20 * Nn}
+    kg = dict(kgroups)
+    kg["ADVECT+G2P"] = (kg["ADVECT"][0] + kg["G2P"][0], kg["ADVECT"][1])
+    roofline_transfer = {"peak": peak, "unit": "GB/s", "particles": int(Pn), "cells": int(Nn),
+                         "formulas": "SURVEY.md 8(d): sort 2(16+4k)P+12P+12N; P2G (16+4k)P+(10+5)N+4N; sdf 8P+10N; density 8P+8N; "
+                                     "G2P + RK4 advect 32P+20N (k = 2 property columns)", "groups": {}}
+    for name, nbytes in transfer_bytes.items():
+        t_ms, calls = kg[name]
+        if calls > 0 and t_ms > 0:
+            per_call = t_ms / calls
+            roofline_transfer["groups"][name] = {"bytes_per_call": nbytes, "avg_ms": per_call, "calls": calls,
+                                                 "achieved": nbytes / (per_call * 1e-3) / 1e9,
+                                                 "frac": nbytes / (per_call * 1e-3) / 1e9 / peak}
+    roofline_transfer["groups"]["EXTRAPOLATE (velocity BFS, 2 calls per substep)"] = {
+        "avg_ms": kg["EXTRAPOLATE"][0] / max(kg["EXTRAPOLATE"][1], 1), "calls": kg["EXTRAPOLATE"][1]}
     per = max(stats["substeps"], 1)
     stage_ms = {name: round(float(stats["timings"][k]) / per, 3) for k, name in enumerate(host_api.STAGES)}
     base = cpu_baseline(args, tmp) if world == 1 and not args.no_cpu_baseline else None
@@ -529,7 +557,8 @@ def run_ours(args, rank, world, local_rank):
                        "pcg_iterations_last_frame": {"pressure": stats["pressure_iters"], "density": stats["density_iters"]},
                        "pcg_walk": "active tiles (%d of %d cells)" % (active_cells_all, N),
                        "stage_ms_per_substep_last_frame": stage_ms},
-            "roofline": roofline, "cpu_baseline": base, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+            "roofline": roofline, "roofline_transfer": roofline_transfer, "cpu_baseline": base, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clocks}
     if mg_parity is not None:
         line["mg_parity"] = mg_parity
     if config_5 is not None:

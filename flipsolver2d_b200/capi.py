@@ -148,6 +148,8 @@ def lib():
         "fs2d_pcg_set_grid_limit": (i32, [H, i32]),
         "fs2d_pcg_set_tile_kernels": (i32, [H, i32]),
         "fs2d_pcg_set_resident": (i32, [H, i32]),
+        "fs2d_kernel_profile": (i32, [H, i32]),
+        "fs2d_kernel_profile_read": (i32, [H, vp, vp]),
         "fs2d_slab_configure": (i32, [H, i32, i32, i32]),
         "fs2d_slab_configure_rows": (i32, [H, i32, i32, i32, vp]),
         "fs2d_slab_export": (i32, [H, vp]),
@@ -333,6 +335,18 @@ class Device:
 
     def pcg_set_grid_limit(self, max_ctas=0):
         self._ck(self.L.fs2d_pcg_set_grid_limit(self.h, int(max_ctas)), "pcg_set_grid_limit")
+
+    KERNEL_GROUPS = ["SORT", "P2G", "DENSITY", "SDF", "ADVECT", "G2P", "EXTRAPOLATE"]
+
+    def kernel_profile(self, enable=True):
+        self._ck(self.L.fs2d_kernel_profile(self.h, 1 if enable else 0), "kernel_profile")
+
+    def kernel_profile_read(self):
+        """{group: (device ms, calls)} accumulated since kernel_profile(True)."""
+        ms = np.zeros(len(self.KERNEL_GROUPS), np.float64)
+        n = np.zeros(len(self.KERNEL_GROUPS), np.int64)
+        self._ck(self.L.fs2d_kernel_profile_read(self.h, _p(ms), _p(n)), "kernel_profile_read")
+        return {g: (float(ms[k]), int(n[k])) for k, g in enumerate(self.KERNEL_GROUPS)}
 
     def pcg_set_resident(self, resident=True):
         self._ck(self.L.fs2d_pcg_set_resident(self.h, 1 if resident else 0), "pcg_set_resident")

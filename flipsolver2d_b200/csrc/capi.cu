@@ -674,6 +674,49 @@ int fs2d_pcg_set_grid_limit(fs2d_handle ctx, int max_ctas)
     return FS2D_OK;
 }
 
+int fs2d_kernel_profile(fs2d_handle ctx, int enable)
+{
+    if (!ctx) return FS2D_ERR_ARG;
+    FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (auto &it : ctx->kprofPending)
+    {
+        cudaEventDestroy(it.e0);
+        cudaEventDestroy(it.e1);
+    }
+    ctx->kprofPending.clear();
+    for (int g = 0; g < FS2D_KGROUP_COUNT_; g++)
+    {
+        ctx->kprofMs[g] = 0.0;
+        ctx->kprofCalls[g] = 0;
+    }
+    ctx->kprofOn = enable != 0;
+    return FS2D_OK;
+}
+
+int fs2d_kernel_profile_read(fs2d_handle ctx, double *ms, int64_t *calls)
+{
+    if (!ctx || !ms || !calls) return FS2D_ERR_ARG;
+    FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (auto &it : ctx->kprofPending)
+    {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, it.e0, it.e1) == cudaSuccess && it.group >= 0 && it.group < FS2D_KGROUP_COUNT_)
+        {
+            ctx->kprofMs[it.group] += t;
+            ctx->kprofCalls[it.group]++;
+        }
+        cudaEventDestroy(it.e0);
+        cudaEventDestroy(it.e1);
+    }
+    ctx->kprofPending.clear();
+    for (int g = 0; g < FS2D_KGROUP_COUNT_; g++)
+    {
+        ms[g] = ctx->kprofMs[g];
+        calls[g] = ctx->kprofCalls[g];
+    }
+    return FS2D_OK;
+}
+
 int fs2d_pcg_set_resident(fs2d_handle ctx, int resident)
 {
     if (!ctx) return FS2D_ERR_ARG;

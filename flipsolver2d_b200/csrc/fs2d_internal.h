@@ -271,12 +271,40 @@ struct fs2d_context
                                            // [from lower / upper neighbour][q / z][J][lo, hi] (pcgResidentKernel)
     SlabState slab;
 
+    // ---- per-group kernel timing (fs2d_kernel_profile)
+    struct KprofItem { int group; cudaEvent_t e0, e1; };
+    bool kprofOn = false;
+    std::vector<KprofItem> kprofPending;
+    double kprofMs[FS2D_KGROUP_COUNT_] = {};
+    int64_t kprofCalls[FS2D_KGROUP_COUNT_] = {};
+
     // ---- timing
     cudaEvent_t ev[16];
     bool eventsReady = false;
 };
 
 typedef fs2d_context Ctx;
+
+// Measurement aid (fs2d_kernel_profile): CUDA events on the handle's stream around the transfer-kernel groups of
+// SURVEY 8(d), so that bench.py can state a roofline fraction for each from live timings.
+struct KernelGroupTimer
+{
+    Ctx *ctx;
+    int group;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    KernelGroupTimer(Ctx *c, int g) : ctx(c), group(g)
+    {
+        if (!ctx->kprofOn) return;
+        if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { e0 = e1 = nullptr; return; }
+        cudaEventRecord(e0, ctx->stream);
+    }
+    ~KernelGroupTimer()
+    {
+        if (!e0 || !e1) return;
+        cudaEventRecord(e1, ctx->stream);
+        ctx->kprofPending.push_back({group, e0, e1});
+    }
+};
 
 inline int divUp(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
 

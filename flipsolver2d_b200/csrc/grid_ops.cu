@@ -679,6 +679,7 @@ int gridAfterTransfer(Ctx *ctx)
 
 int gridExtrapolateVelocity(Ctx *ctx, int radius)
 {
+    KernelGroupTimer kgt(ctx, FS2D_KGROUP_EXTRAPOLATE);
     // slab mode: both call sites of a substep (after the transfer, after the projection) follow stages that
     // rewrote U / V / validity / material on the owned rows only -> refresh the halo copies first
     FS2D_TRY(slabExchangeVelocity(ctx, true));

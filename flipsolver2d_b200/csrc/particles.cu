@@ -675,6 +675,7 @@ int particlesMaxVelocity(Ctx *ctx, float *out)
 
 int particlesAdvect(Ctx *ctx)
 {
+    KernelGroupTimer kgt(ctx, FS2D_KGROUP_ADVECT);
     if (ctx->count == 0) return FS2D_OK;
     advectKernel<<<gridFor(ctx->count), NT, 0, ctx->stream>>>(ctx->pb[ctx->cur].pos, ctx->dead, ctx->pb[ctx->cur].mis, ctx->count,
                                                              makeVelocityView(ctx->U, ctx->V, ctx->I, ctx->J),
@@ -691,6 +692,7 @@ int particlesAdvect(Ctx *ctx)
 // outside the rows [rows.lo, rows.hi) hold no particle, so the histogram / scan / order passes only cover those.
 int particlesSort(Ctx *ctx)
 {
+    KernelGroupTimer kgt(ctx, FS2D_KGROUP_SORT);
     const bool slab = ctx->slab.enabled && ctx->slab.world > 1;
     const SlabRows rows = slab ? slabExt(ctx, ctx->slab.ghost) : SlabRows{0, ctx->I};
     const int64_t cLo = static_cast<int64_t>(rows.lo) * ctx->J, cHi = static_cast<int64_t>(rows.hi) * ctx->J;
@@ -827,6 +829,7 @@ static int combustionUpdate(Ctx *ctx)
 
 int particlesUpdate(Ctx *ctx)
 {
+    KernelGroupTimer kgt(ctx, FS2D_KGROUP_G2P);
     if (ctx->count == 0) return ctx->p.sim_type == FS2D_SIM_FIRE ? combustionUpdate(ctx) : FS2D_OK;
     const bool smoke = ctx->p.sim_type == FS2D_SIM_SMOKE || ctx->p.sim_type == FS2D_SIM_FIRE;
     ParticleBuffers &b = ctx->pb[ctx->cur];

@@ -218,13 +218,18 @@ template <bool IS_MAX> __device__ double finalReduce(const double *partials, int
 __device__ __forceinline__ double rowA(uint8_t info, double scale, double c, double im, double ip, double jm, double jp)
 {
     if (!(info & FS2D_ROW_UNIT)) return c;  // identity row (pressuredata.h:227-236)
-    const double cnt = static_cast<double>((info >> 4) & 7u);
-    const double ns = -scale;
+    // The reference multiplies by static_cast<double>(count) and by the 0 / 1 neighbour flags. Integer -> double
+    // conversions run on the XU pipe (16 lanes per SM; ncu showed it saturated: five conversions per cell), so the same
+    // values are SELECTED instead: double(k) for k = 0 .. 4 is one of five constants, and -scale * double(bit) is
+    // -scale (bit 1) or -scale * 0.0 (bit 0) -- identical bits, no conversion.
+    const unsigned int k = (info >> 4) & 7u;
+    const double cnt = k < 2u ? (k ? 1.0 : 0.0) : (k == 2u ? 2.0 : (k == 3u ? 3.0 : 4.0));
+    const double ns = -scale, nz = __dmul_rn(ns, 0.0);
     double acc = __dmul_rn(__dmul_rn(scale, cnt), c);
-    acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(ns, static_cast<double>(info & 1u)), im));
-    acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(ns, static_cast<double>((info >> 1) & 1u)), ip));
-    acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(ns, static_cast<double>((info >> 2) & 1u)), jm));
-    acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(ns, static_cast<double>((info >> 3) & 1u)), jp));
+    acc = __dadd_rn(acc, __dmul_rn((info & 1u) ? ns : nz, im));
+    acc = __dadd_rn(acc, __dmul_rn((info & 2u) ? ns : nz, ip));
+    acc = __dadd_rn(acc, __dmul_rn((info & 4u) ? ns : nz, jm));
+    acc = __dadd_rn(acc, __dmul_rn((info & 8u) ? ns : nz, jp));
     return acc;
 }
 
@@ -1639,6 +1644,9 @@ __device__ __forceinline__ void blockReduce2W16(double &s, double &m, double *sc
     }
 }
 
+// (Tried and measured slower: a ticket-less barrier where every CTA publishes its partials as self-validating words and
+// thread k of every CTA polls the words of CTA k -- one L2 round trip in theory, but 148 x 148 pollers instead of 148
+// turn the poll traffic into the bottleneck: 8.2 -> 15 us per iteration at 1024^2.)
 // solveBarrier for `nb` participating CTAs of RNT threads (same protocol; see there).
 template <bool MG>
 __device__ __forceinline__ bool resBarrier(const SolveArgs &g, const MgArgs &m, int phase, unsigned int barrierIndex, unsigned int nb,

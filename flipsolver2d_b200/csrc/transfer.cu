@@ -431,6 +431,7 @@ static int ensureSorted(Ctx *ctx)
 
 int transferVelocity(Ctx *ctx)
 {
+    KernelGroupTimer kgt(ctx, FS2D_KGROUP_P2G);
     FS2D_TRY(ensureSorted(ctx));
     cudaStream_t st = ctx->stream;
     // fill(0)/fill(false) of all four arrays (flipsolver2d.cpp:1315-1318); row I of U and column J of V keep 0
@@ -458,6 +459,7 @@ int transferVelocity(Ctx *ctx)
 
 int transferCentered(Ctx *ctx)
 {
+    KernelGroupTimer kgt(ctx, FS2D_KGROUP_P2G);
     FS2D_TRY(ensureSorted(ctx));
     cudaStream_t st = ctx->stream;
     const SlabRows own = slabOwn(ctx);
@@ -508,6 +510,7 @@ int transferCentered(Ctx *ctx)
 
 int transferDensity(Ctx *ctx)
 {
+    KernelGroupTimer kgt(ctx, FS2D_KGROUP_DENSITY);
     FS2D_TRY(ensureSorted(ctx));
     // slab mode: one extra tile row each side, the density right-hand side needs one halo row (ghost particles
     // reach 12 rows, the tile halo needs 9)
@@ -535,6 +538,7 @@ int transferDensity(Ctx *ctx)
 
 int transferSdf(Ctx *ctx)
 {
+    KernelGroupTimer kgt(ctx, FS2D_KGROUP_SDF);
     FS2D_TRY(ensureSorted(ctx));
     ctx->sdfInsidePending = false;  // the whole level set is rewritten below
     const SlabRows own = slabOwn(ctx);

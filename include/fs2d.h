@@ -237,6 +237,25 @@ int fs2d_pcg_set_grid_limit(fs2d_handle h, int max_ctas);
  * Same iterates up to the grouping of the dot-product partials. */
 int fs2d_pcg_set_resident(fs2d_handle h, int resident);
 int fs2d_pcg_set_tile_kernels(fs2d_handle h, int tile);
+/* Measurement aid for the particle / grid transfer kernels: with profiling enabled every call of a kernel group is
+ * bracketed by CUDA events on the handle's stream; fs2d_kernel_profile_read returns, per group, the accumulated device
+ * ms and the number of calls since profiling was enabled (it synchronises the stream). Groups follow SURVEY 8(d):
+ * SORT = histogram + scan + scatter + in-cell order + gather (pruneParticles / rebinParticles), P2G = velocity + centred
+ * parameters (particleToGrid), DENSITY = updateDensityGrid, SDF = updateSdf, ADVECT = advectThread (RK4 + push-out),
+ * G2P = particleUpdate. */
+enum fs2d_kernel_group
+{
+    FS2D_KGROUP_SORT = 0,
+    FS2D_KGROUP_P2G = 1,
+    FS2D_KGROUP_DENSITY = 2,
+    FS2D_KGROUP_SDF = 3,
+    FS2D_KGROUP_ADVECT = 4,
+    FS2D_KGROUP_G2P = 5,
+    FS2D_KGROUP_EXTRAPOLATE = 6,
+    FS2D_KGROUP_COUNT_
+};
+int fs2d_kernel_profile(fs2d_handle h, int enable);
+int fs2d_kernel_profile_read(fs2d_handle h, double *ms /* FS2D_KGROUP_COUNT_ */, int64_t *calls /* FS2D_KGROUP_COUNT_ */);
 /* IndexedPressureParameters::multiply (pressuredata.h:184-238) and
  * IndexedIPPCoefficients::multiply (PressureIPPCoeficients.h:79-132) alone, host vectors. */
 int fs2d_spmv(fs2d_handle h, const double *host_in, double *host_out);
