@@ -142,6 +142,7 @@ def lib():
         "fs2d_reseed_plan": (i32, [H, C.POINTER(i64)]),
         "fs2d_reseed_apply": (i32, [H, i64, vp]),
         "fs2d_nbflip_advect_grids": (i32, [H]),
+        "fs2d_set_sdf_band": (i32, [H, i32]),
         "fs2d_substep": (i32, [H, f32, vp, vp]),
         "fs2d_pcg_set_stepwise": (i32, [H, i32]),
         "fs2d_pcg_profile_solves": (i32, [H, vp, vp]),
@@ -348,6 +349,9 @@ class Device:
         self._ck(self.L.fs2d_kernel_profile_read(self.h, _p(ms), _p(n)), "kernel_profile_read")
         return {g: (float(ms[k]), int(n[k])) for k, g in enumerate(self.KERNEL_GROUPS)}
 
+    def set_sdf_band(self, layers):
+        self._ck(self.L.fs2d_set_sdf_band(self.h, int(layers)), "set_sdf_band")
+
     def pcg_set_resident(self, resident=True):
         self._ck(self.L.fs2d_pcg_set_resident(self.h, 1 if resident else 0), "pcg_set_resident")
 
@@ -488,7 +492,11 @@ def run_ranks(fns):
         t.start()
     for t in ts:
         t.join()
-    for e in err:
-        if e is not None:
-            raise e
+    failed = [(k, e) for k, e in enumerate(err) if e is not None]
+    if failed:
+        # a rank that gives up makes the others time out: show every rank's error, not only the first in rank order
+        k0, e0 = failed[0]
+        if len(failed) > 1:
+            raise type(e0)("; ".join("rank %d: %s" % (k, e) for k, e in failed)) from e0
+        raise e0
     return out

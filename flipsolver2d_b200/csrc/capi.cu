@@ -334,8 +334,14 @@ int fs2d_download_grid(fs2d_handle ctx, int grid, void *host_data, size_t bytes)
         ctx->lastError = "fs2d_download_grid: unknown grid or size mismatch";
         return FS2D_ERR_ARG;
     }
-    if (grid == FS2D_GRID_FLUID_SDF) FS2D_TRY(gridFlushSdf(ctx));
-    FS2D_CUDA(fs2dCopyToHost(ctx, host_data, *d.ptr, bytes));
+    const void *src = *d.ptr;
+    if (grid == FS2D_GRID_FLUID_SDF)
+    {
+        const float *field = nullptr;
+        FS2D_TRY(gridSdfForRead(ctx, &field));  // deferred (water) / banded (NBFlip) level-set walks completed for the reader
+        src = field;
+    }
+    FS2D_CUDA(fs2dCopyToHost(ctx, host_data, src, bytes));
     FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
     return FS2D_OK;
 }
@@ -862,8 +868,16 @@ int fs2d_reseed_apply(fs2d_handle h, int64_t candidates, const float *host_unifo
 int fs2d_nbflip_advect_grids(fs2d_handle h)
 {
     if (!h) return FS2D_ERR_ARG;
+    FS2D_TRY(gridNbflipHalo(h));  // row slabs: level set and viscosity on the halo rows
     FS2D_TRY(particlesPruneNarrowBand(h));
     return gridNbflipAdvect(h);
+}
+
+int fs2d_set_sdf_band(fs2d_handle ctx, int layers)
+{
+    if (!ctx || layers < 0) return FS2D_ERR_ARG;
+    ctx->sdfBand = layers;
+    return FS2D_OK;
 }
 
 int fs2d_substep(fs2d_handle h, float dt, float *stage_ms, int *iters)

@@ -242,6 +242,7 @@ struct fs2d_context
     bool killedDirty = false;         // d_counter[0] holds kills not yet folded into deadCount
     bool sdfInsidePending = false;    // extrapolateLevelsetInside deferred until the grid is read (grid_ops.cu)
     bool eagerSdf = std::getenv("FS2D_EAGER_SDF") != nullptr;
+    int sdfBand = std::getenv("FS2D_SDF_BAND") ? std::atoi(std::getenv("FS2D_SDF_BAND")) : 24;  // NBFlip level-set walks: layers (0 = unbounded), grid_ops.cu
     bool smokeGridsAdvected = false;  // temperature/concentration/fuel replaced by advected grids (App. A-13)
     int64_t *d_counter = nullptr;     // device scalar scratch (8 int64)
     float *d_fscratch = nullptr;      // device float scratch
@@ -340,6 +341,8 @@ int gridExtrapolateVelocity(Ctx *ctx, int radius);
 int gridExtrapolateSdf(Ctx *ctx, bool inside);
 int gridFlushSdf(Ctx *ctx);
 int gridFlushSdfGathered(Ctx *ctx);   // after every rank pushed its rows of the level set to every other rank
+int gridSdfForRead(Ctx *ctx, const float **field);  // the level set a host reader sees (deferred / banded walks completed)
+int gridNbflipHalo(Ctx *ctx);
 int gridSaveVelocity(Ctx *ctx);
 int gridBodyForces(Ctx *ctx);
 int gridPressureRhs(Ctx *ctx);
@@ -373,6 +376,7 @@ int slabExchangeParticles(Ctx *ctx);
 int slabAllGather(Ctx *ctx, const long long v[4], long long *out /* world x 4 */);
 int slabCheckError(Ctx *ctx);
 int slabGatherRows(Ctx *ctx, void *array, size_t rowBytes, int rowsTotal);  // collective: own rows -> every rank
+int slabGatherMany(Ctx *ctx, void *const *arrays, const size_t *rowBytes, const int *rowsTotal, int count);
 void pcgPreloadSlabKernels();           // pcg.cu
 // step.cu
 int stepSubstep(Ctx *ctx, float dt, float *stageMs, int *iters);

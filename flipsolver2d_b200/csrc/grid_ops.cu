@@ -254,22 +254,23 @@ __global__ void __launch_bounds__(NT) bfsLayerKernel(float *U, float *V, uint8_t
 // version did, cost 0.5 s per nbflip substep. The value of a cell does not depend on the order inside its layer
 // (SURVEY appendix A-9), so the arbitrary list order is harmless: results are bit-identical to the reference.
 // queue: one slot per cell; ctl[0] = tail (cells appended so far).
-__global__ void __launch_bounds__(NT) sdfMarkKernel(const float *__restrict__ sdf, int32_t *__restrict__ marker, long long N, int inside,
-                                                    float maxSdf)
+__global__ void __launch_bounds__(NT) sdfMarkKernel(const float *__restrict__ sdf, int32_t *__restrict__ marker, long long nBegin,
+                                                    long long nEnd, int inside, float maxSdf)
 {
-    const long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
-    if (n >= N) return;
+    const long long n = nBegin + blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    if (n >= nEnd) return;
     const float v = sdf[n];
     const bool known = inside ? (v > 0.f) : (v < maxSdf);
     marker[n] = known ? 0 : 0x7fffffff;
 }
 
-// layer 1: unmarked cells with a known 8-neighbour (flipsolver2d.cpp:1450-1468)
-__global__ void __launch_bounds__(NT) sdfFirstLayerKernel(int32_t *__restrict__ marker, int I, int J, int32_t *__restrict__ queue,
-                                                          unsigned int *__restrict__ ctl)
+// layer 1: unmarked cells with a known 8-neighbour (flipsolver2d.cpp:1450-1468). Rows [rowLo, rowHi) only (the whole grid
+// without slabs); cells outside that range do not exist for the walk.
+__global__ void __launch_bounds__(NT) sdfFirstLayerKernel(int32_t *__restrict__ marker, int J, int rowLo, int rowHi,
+                                                          int32_t *__restrict__ queue, unsigned int *__restrict__ ctl)
 {
-    const long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
-    if (n >= static_cast<long long>(I) * J) return;
+    const long long n = static_cast<long long>(rowLo) * J + blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    if (n >= static_cast<long long>(rowHi) * J) return;
     if (marker[n] == 0) return;
     const int i = static_cast<int>(n / J), j = static_cast<int>(n - static_cast<long long>(i) * J);
     bool hit = false;
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(NT) sdfFirstLayerKernel(int32_t *__restrict__ 
         for (int dj = -1; dj <= 1; dj++)
         {
             const int ni = i + di, nj = j + dj;
-            if ((di == 0 && dj == 0) || ni < 0 || ni >= I || nj < 0 || nj >= J) continue;
+            if ((di == 0 && dj == 0) || ni < rowLo || ni >= rowHi || nj < 0 || nj >= J) continue;
             if (marker[static_cast<long long>(ni) * J + nj] == 0) hit = true;
         }
     if (!hit) return;
@@ -288,20 +289,30 @@ __global__ void __launch_bounds__(NT) sdfFirstLayerKernel(int32_t *__restrict__ 
     queue[atomicAdd(ctl, 1u)] = static_cast<int32_t>(n);
 }
 
+// Band mode, inside walk: cells the walk did not reach within `layers` layers (still unmarked, or claimed for the next
+// layer) get one value below everything the band holds.
+__global__ void __launch_bounds__(NT) sdfClampKernel(float *__restrict__ sdf, const int32_t *__restrict__ marker, long long nBegin,
+                                                     long long nEnd, int layers, float value)
+{
+    const long long n = nBegin + blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    if (n >= nEnd) return;
+    if (marker[n] > layers) sdf[n] = value;
+}
+
 // A cooperative grid of one CTA per SM walks the layers (measured at 4096^2 nbflip, ~3400 layers per substep: one
 // 8-CTA cluster with the hardware cluster barrier 41 ms, this grid 2x faster -- a frontier is several thousand cells
 // and each visit is a chain of dependent L2 / DRAM round trips, so the number of threads in flight matters more than
 // the barrier).
 constexpr int BFS_THREADS = 256;
 
-__global__ void __launch_bounds__(BFS_THREADS) sdfExtrapolateKernel(float *sdf, int32_t *marker, int I, int J, float step, int32_t *queue,
-                                                                    unsigned int *ctl)
+__global__ void __launch_bounds__(BFS_THREADS) sdfExtrapolateKernel(float *sdf, int32_t *marker, int rowLo, int rowHi, int J, float step,
+                                                                    int32_t *queue, unsigned int *ctl, int maxLayers)
 {
     cg::grid_group grid = cg::this_grid();
     const unsigned int stride = gridDim.x * BFS_THREADS;
     const unsigned int me = blockIdx.x * BFS_THREADS + threadIdx.x;
     unsigned int begin = 0, end = *reinterpret_cast<volatile unsigned int *>(ctl);
-    for (int k = 1; begin < end; k++)
+    for (int k = 1; begin < end && (maxLayers <= 0 || k <= maxLayers); k++)
     {
         for (unsigned int t0 = begin + (me & ~31u); t0 < end; t0 += stride)  // warp-uniform trip count (ballots below)
         {
@@ -321,7 +332,7 @@ __global__ void __launch_bounds__(BFS_THREADS) sdfExtrapolateKernel(float *sdf, 
                 const int di = (q < 3) ? -1 : (q < 5 ? 0 : 1);
                 const int dj = (q < 3) ? q - 1 : (q == 3 ? -1 : (q == 4 ? 1 : q - 6));
                 const int ni = i + di, nj = j + dj;
-                const bool in = valid && ni >= 0 && ni < I && nj >= 0 && nj < J;
+                const bool in = valid && ni >= rowLo && ni < rowHi && nj >= 0 && nj < J;
                 nn[q] = in ? static_cast<long long>(ni) * J + nj : -1;
                 m[q] = in ? marker[nn[q]] : -1;
                 v[q] = in ? sdf[nn[q]] : 0.f;
@@ -548,10 +559,11 @@ __global__ void __launch_bounds__(NT) solidFrictionKernel(const int32_t *__restr
 // ------------------------------------------------------------------ semi-Lagrangian advection
 // eulerAdvectionThread (flipsolver2d.cpp:340-351): back-trace RK4(-dt) from the INTEGER sample index
 // (not the staggered sample position) and interpolate the input grid with its own offset / OOB policy.
-__global__ void __launch_bounds__(NT) eulerAdvectKernel(GridView in, VelocityView vel, float dt, float *__restrict__ out)
+__global__ void __launch_bounds__(NT) eulerAdvectKernel(GridView in, VelocityView vel, float dt, float *__restrict__ out,
+                                                        long long nBegin = 0, long long nEnd = -1)
 {
-    const long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
-    if (n >= static_cast<long long>(in.sizeI) * in.sizeJ) return;
+    const long long n = nBegin + blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    if (n >= (nEnd >= 0 ? nEnd : static_cast<long long>(in.sizeI) * in.sizeJ)) return;
     const int i = static_cast<int>(n / in.sizeJ), j = static_cast<int>(n - static_cast<long long>(i) * in.sizeJ);
     const float2 prev = rk4(vel, make_float2(static_cast<float>(i), static_cast<float>(j)), -dt);
     out[n] = gridLerp(in, prev.x, prev.y);
@@ -560,11 +572,11 @@ __global__ void __launch_bounds__(NT) eulerAdvectKernel(GridView in, VelocityVie
 // NBFlipSolver::updateGridFromSources + combineLevelset (nbflipsolver.cpp:329-376)
 __global__ void __launch_bounds__(NT) nbSourcesLevelsetKernel(const float *__restrict__ sourceSdf, const int32_t *__restrict__ sourceId,
                                                               const fs2d_source *__restrict__ sources,
-                                                              const float *__restrict__ advSdf, long long N,
+                                                              const float *__restrict__ advSdf, long long nBegin, long long N,
                                                               float *__restrict__ fluidSdf, float *__restrict__ viscosity,
                                                               float *__restrict__ advViscosity)
 {
-    const long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    const long long n = nBegin + blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
     if (n >= N) return;
     const float d = sourceSdf[n];
     float f = fminf(d, fluidSdf[n]);
@@ -581,26 +593,29 @@ __global__ void __launch_bounds__(NT) nbSourcesLevelsetKernel(const float *__res
 __global__ void __launch_bounds__(NT) nbCombineKernel(GridView fluidSdf, int I, int J, const float *__restrict__ advU,
                                                       const float *__restrict__ advV, const float *__restrict__ advViscosity,
                                                       float *__restrict__ U, float *__restrict__ V, float *__restrict__ viscosity,
-                                                      float *__restrict__ testGrid, float band)
+                                                      float *__restrict__ testGrid, float band, int rowLo, int rowHiU, int rowHi)
 {
-    const long long NU = static_cast<long long>(I + 1) * J, NV = static_cast<long long>(I) * (J + 1), N = static_cast<long long>(I) * J;
+    // rows [rowLo, rowHiU) of U, [rowLo, rowHi) of V and of the centred grids (the whole grids without slabs)
+    const long long NU = static_cast<long long>(rowHiU - rowLo) * J, NV = static_cast<long long>(rowHi - rowLo) * (J + 1),
+                    N = static_cast<long long>(rowHi - rowLo) * J;
     const long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
     if (n < NU)
     {
-        const int i = static_cast<int>(n / J), j = static_cast<int>(n - static_cast<long long>(i) * J);
+        const long long g = n + static_cast<long long>(rowLo) * J;
+        const int i = static_cast<int>(g / J), j = static_cast<int>(g - static_cast<long long>(i) * J);
         const float sdf = gridLerp(fluidSdf, static_cast<float>(i), faddr(0.5f, static_cast<float>(j)));
-        if (!(sdf > band)) U[n] = advU[n];
+        if (!(sdf > band)) U[g] = advU[g];
     }
     else if (n < NU + NV)
     {
-        const long long m = n - NU;
+        const long long m = n - NU + static_cast<long long>(rowLo) * (J + 1);
         const int i = static_cast<int>(m / (J + 1)), j = static_cast<int>(m - static_cast<long long>(i) * (J + 1));
         const float sdf = gridLerp(fluidSdf, faddr(0.5f, static_cast<float>(i)), static_cast<float>(j));
         if (!(sdf > band)) V[m] = advV[m];
     }
     else if (n < NU + NV + N)
     {
-        const long long m = n - NU - NV;
+        const long long m = n - NU - NV + static_cast<long long>(rowLo) * J;
         const int i = static_cast<int>(m / J), j = static_cast<int>(m - static_cast<long long>(i) * J);
         // Vec3(0.5f + i, j + 0.5): the second component is evaluated in double and narrowed
         const float sdf = gridLerp(fluidSdf, faddr(0.5f, static_cast<float>(i)), static_cast<float>(static_cast<double>(j) + 0.5));
@@ -612,6 +627,11 @@ __global__ void __launch_bounds__(NT) nbCombineKernel(GridView fluidSdf, int I, 
 
 int gridBuildMatrix(Ctx *ctx)
 {
+    // NBFlip builds the system AFTER gridUpdate (nbflipsolver.cpp:43-47), which rewrote materials, combined the advected
+    // velocities in and applied the body forces on the owned rows: in slab mode the matrix rows, the right-hand side and
+    // the pressure gradient at a slab boundary need those on the halo rows too. (Water builds it from the previous
+    // substep's materials, whose halo the last velocity extrapolation refreshed.)
+    if (ctx->p.sim_type == FS2D_SIM_NBFLIP) FS2D_TRY(slabExchangeVelocity(ctx, true));
     const int smokeRows = (ctx->p.sim_type == FS2D_SIM_SMOKE || ctx->p.sim_type == FS2D_SIM_FIRE) ? 1 : 0;
     const CellRange cr = cellRange(ctx, slabOwn(ctx));
     buildMatrixKernel<<<divUp(cr.count(), NT), NT, 0, ctx->stream>>>(ctx->material, ctx->I, ctx->J, smokeRows, ctx->rowInfo,
@@ -665,13 +685,24 @@ int gridAfterTransfer(Ctx *ctx)
     if (isSmoke(ctx)) FS2D_CUDA(cudaMemsetAsync(ctx->divergenceControl, 0, sizeof(float) * ctx->N, st));  // flipsmokesolver.cpp:135
     if (ctx->p.sim_type == FS2D_SIM_NBFLIP)
     {
-        // NBFlipSolver::afterTransfer (nbflipsolver.cpp:111-116)
-        nbSourcesLevelsetKernel<<<divUp(ctx->N, NT), NT, 0, st>>>(ctx->sourceSdf, ctx->sourceSdfId, ctx->sources, ctx->advSdf, ctx->N,
-                                                                ctx->fluidSdf, ctx->viscosity, ctx->advViscosity);
-        nbCombineKernel<<<divUp(ctx->NU + ctx->NV + ctx->N, NT), NT, 0, st>>>(fluidSdfView(ctx), ctx->I, ctx->J, ctx->advU, ctx->advV,
-                                                                            ctx->advViscosity, ctx->U, ctx->V, ctx->viscosity,
-                                                                            ctx->testGrid, -2.f);
-        ctx->launches += 2;
+        // NBFlipSolver::afterTransfer (nbflipsolver.cpp:111-116). Slab mode: the owned rows; combineAdvectedGrids samples
+        // the level set combineLevelset has just rewritten at staggered positions, i.e. one row beyond the slab, so the
+        // halo rows of the level set are refreshed in between.
+        const SlabRows own = slabOwn(ctx);
+        const CellRange cr = cellRange(ctx, own);
+        nbSourcesLevelsetKernel<<<divUp(cr.count(), NT), NT, 0, st>>>(ctx->sourceSdf, ctx->sourceSdfId, ctx->sources, ctx->advSdf, cr.begin,
+                                                                    cr.end, ctx->fluidSdf, ctx->viscosity, ctx->advViscosity);
+        ctx->launches++;
+        {
+            const void *arr[1] = {ctx->fluidSdf};
+            const size_t rb[1] = {sizeof(float) * ctx->J};
+            FS2D_TRY(slabExchangeFields(ctx, arr, rb, 1));
+        }
+        const int rowHiU = own.hi == ctx->I ? ctx->I + 1 : own.hi;
+        const long long samples = static_cast<long long>(rowHiU - own.lo) * ctx->J + static_cast<long long>(own.hi - own.lo) * (2ll * ctx->J + 1);
+        nbCombineKernel<<<divUp(samples, NT), NT, 0, st>>>(fluidSdfView(ctx), ctx->I, ctx->J, ctx->advU, ctx->advV, ctx->advViscosity, ctx->U,
+                                                         ctx->V, ctx->viscosity, ctx->testGrid, -2.f, own.lo, rowHiU, own.hi);
+        ctx->launches++;
     }
     FS2D_CUDA(cudaGetLastError());
     return FS2D_OK;
@@ -712,32 +743,63 @@ int gridExtrapolateVelocity(Ctx *ctx, int radius)
     return FS2D_OK;
 }
 
-int gridExtrapolateSdfNow(Ctx *ctx, bool inside, bool wholeGridHeld = false);
+int gridExtrapolateSdfNow(Ctx *ctx, bool inside, float *field, int band, SlabRows rows);
 
-// extrapolateLevelsetInside only rewrites the level set BELOW the surface. Outside NBFlip nothing in the
-// substep reads those values (updateMaterials has already run, the next updateSdf overwrites them,
-// SURVEY section 7 "extrapolate-inside depth"), so the hundreds of dependent BFS layers are deferred until
-// somebody asks for the grid (fs2d_download_grid / fs2d_grid_device_ptr) -- same values, off the hot path.
+// ---- how far the level-set walks go
+// extrapolateLevelsetInside / Outside have unbounded radius: thousands of strictly dependent layers at 4096^2, and
+// nothing to shard (a layer is a thin front).
+//  * Water / smoke / fire: extrapolateLevelsetInside only rewrites the level set BELOW the surface and nothing in the
+//    substep reads it (updateMaterials has already run, the next updateSdf overwrites it), so the walk is deferred
+//    until somebody asks for the grid (fs2d_download_grid / fs2d_grid_device_ptr) -- same values, off the hot path.
+//  * NBFlip reads the level set every substep, but only near the interface: pruneNarrowBand / reseedParticles compare
+//    it with -3 and -1 at particle positions (nbflipsolver.cpp:227-253,118-201), combineAdvectedGrids with -2
+//    (:378-427), updateMaterials with 0, and the semi-Lagrangian step re-samples it at most cflNumber + 1 = 6 cells
+//    away; everything else only has to keep its sign and stay beyond those thresholds. A layer's values depend on lower
+//    layers only, so walking `sdfBand` layers (default 24) leaves every cell within 24 layers of the interface
+//    bit-identical to the unbounded walk. Beyond the band the INSIDE walk writes -(band + 1) (the unbounded walk:
+//    between -layer and -layer + 1.5) and the OUTSIDE walk leaves updateSdf's "no particle" value, sqrt(FLT_MAX) -
+//    radius (the unbounded walk: about +layer). tests/test_nbflip_band_gpu.py steps both variants side by side:
+//    particles, materials, velocities and pressure stay bit-identical, and the level set is identical inside the band.
+//    fs2d_set_sdf_band(h, 0) (env FS2D_SDF_BAND=0) selects the unbounded walks; a download of FLUID_SDF completes the
+//    inside walk on a copy, so host readers see the reference's interior values either way. 4096^2 nbflip substep:
+//    23.7 ms -> under 1 ms for the two walks, and only the band makes the walks local enough for row slabs
+//    (band + 2 <= halo rows).
+static int sdfBandOf(const Ctx *ctx) { return ctx->p.sim_type == FS2D_SIM_NBFLIP ? ctx->sdfBand : 0; }
+
 int gridFlushSdf(Ctx *ctx)
 {
     if (!ctx->sdfInsidePending) return FS2D_OK;
     if (ctx->slab.enabled && ctx->slab.world > 1)
     {
-        // the BFS has unbounded radius: it needs every rank's rows, which only a collective call can bring here
+        // the walk has unbounded radius: it needs every rank's rows, which only a collective call can bring here
         ctx->lastError = "the fluid level set below the surface is computed lazily and needs all slabs: call "
                          "fs2d_slab_gather_grid(FS2D_GRID_FLUID_SDF) on every rank first";
         return FS2D_ERR_STATE;
     }
     ctx->sdfInsidePending = false;
-    return gridExtrapolateSdfNow(ctx, true);
+    return gridExtrapolateSdfNow(ctx, true, ctx->fluidSdf, 0, SlabRows{0, ctx->I});
 }
 
-// After fs2d_slab_gather_grid(FS2D_GRID_FLUID_SDF): every rank holds all rows and runs the deferred BFS on the whole grid.
+// After fs2d_slab_gather_grid(FS2D_GRID_FLUID_SDF): every rank holds all rows and runs the walk on the whole grid
+// (deferred for water; for NBFlip the unbounded completion of the banded interior).
 int gridFlushSdfGathered(Ctx *ctx)
 {
-    if (!ctx->sdfInsidePending) return FS2D_OK;
+    if (!ctx->sdfInsidePending && !(ctx->p.sim_type == FS2D_SIM_NBFLIP && sdfBandOf(ctx) > 0)) return FS2D_OK;
     ctx->sdfInsidePending = false;
-    return gridExtrapolateSdfNow(ctx, true, true);
+    return gridExtrapolateSdfNow(ctx, true, ctx->fluidSdf, 0, SlabRows{0, ctx->I});
+}
+
+// The level set a host reader should see: for NBFlip in band mode a COPY with the interior completed by the unbounded
+// walk (the solver's own field keeps its band values, so stepping does not depend on who looked at the grid).
+int gridSdfForRead(Ctx *ctx, const float **field)
+{
+    *field = ctx->fluidSdf;
+    if (ctx->p.sim_type != FS2D_SIM_NBFLIP || sdfBandOf(ctx) <= 0) return gridFlushSdf(ctx);
+    if (ctx->slab.enabled && ctx->slab.world > 1) return FS2D_OK;  // slabs: band values unless fs2d_slab_gather_grid ran just before
+    FS2D_CUDA(cudaMemcpyAsync(ctx->scratchA, ctx->fluidSdf, sizeof(float) * ctx->N, cudaMemcpyDeviceToDevice, ctx->stream));
+    FS2D_TRY(gridExtrapolateSdfNow(ctx, true, ctx->scratchA, 0, SlabRows{0, ctx->I}));
+    *field = ctx->scratchA;
+    return FS2D_OK;
 }
 
 int gridExtrapolateSdf(Ctx *ctx, bool inside)
@@ -747,13 +809,27 @@ int gridExtrapolateSdf(Ctx *ctx, bool inside)
         ctx->sdfInsidePending = true;
         return FS2D_OK;
     }
+    const int band = sdfBandOf(ctx);
+    if (ctx->slab.enabled && ctx->slab.world > 1)
+    {
+        if (band <= 0 || band + 2 > ctx->slab.halo)
+        {
+            ctx->lastError = "extrapolateLevelset over row slabs needs the banded walk (0 < fs2d_set_sdf_band <= halo rows - 2)";
+            return FS2D_ERR_STATE;
+        }
+        // the walk covers the owned rows plus the halo; what the cut at the outer halo row gets wrong moves one row per
+        // layer, so after `band` layers the owned rows (and halo - band rows around them) are exact
+        const void *arr[1] = {ctx->fluidSdf};
+        const size_t rb[1] = {sizeof(float) * ctx->J};
+        FS2D_TRY(slabExchangeFields(ctx, arr, rb, 1));
+        return gridExtrapolateSdfNow(ctx, inside, ctx->fluidSdf, band, slabExt(ctx, ctx->slab.halo));
+    }
     FS2D_TRY(gridFlushSdf(ctx));
-    return gridExtrapolateSdfNow(ctx, inside);
+    return gridExtrapolateSdfNow(ctx, inside, ctx->fluidSdf, band, SlabRows{0, ctx->I});
 }
 
-int gridExtrapolateSdfNow(Ctx *ctx, bool inside, bool wholeGridHeld)
+int gridExtrapolateSdfNow(Ctx *ctx, bool inside, float *field, int band, SlabRows rows)
 {
-    if (!wholeGridHeld) FS2D_TRY(slabUnsupported(ctx, "extrapolateLevelset"));
     cudaStream_t st = ctx->stream;
     if (!ctx->bfsQueue)
     {
@@ -762,22 +838,30 @@ int gridExtrapolateSdfNow(Ctx *ctx, bool inside, bool wholeGridHeld)
     }
     FS2D_CUDA(cudaMemsetAsync(ctx->bfsCtl, 0, 64, st));
     const float maxSdf = static_cast<float>(static_cast<size_t>(ctx->I) * static_cast<size_t>(ctx->J));
-    sdfMarkKernel<<<divUp(ctx->N, NT), NT, 0, st>>>(ctx->fluidSdf, ctx->markers, ctx->N, inside ? 1 : 0, maxSdf);
-    sdfFirstLayerKernel<<<divUp(ctx->N, NT), NT, 0, st>>>(ctx->markers, ctx->I, ctx->J, ctx->bfsQueue, ctx->bfsCtl);
+    const CellRange cr = cellRange(ctx, rows);
+    sdfMarkKernel<<<divUp(cr.count(), NT), NT, 0, st>>>(field, ctx->markers, cr.begin, cr.end, inside ? 1 : 0, maxSdf);
+    sdfFirstLayerKernel<<<divUp(cr.count(), NT), NT, 0, st>>>(ctx->markers, ctx->J, rows.lo, rows.hi, ctx->bfsQueue, ctx->bfsCtl);
     {
         static const int perSm = std::getenv("FS2D_BFS_CTAS_PER_SM") ? std::atoi(std::getenv("FS2D_BFS_CTAS_PER_SM")) : 1;
-        float *sdf = ctx->fluidSdf;
+        const int share = (ctx->slab.enabled && ctx->slab.world > 1) ? std::max(ctx->slab.share, 1) : 1;
+        float *sdf = field;
         int32_t *markers = ctx->markers;
-        int I = ctx->I, J = ctx->J;
+        int rowLo = rows.lo, rowHi = rows.hi, J = ctx->J;
         float step = inside ? -1.f : 1.f;
         int32_t *queue = ctx->bfsQueue;
         unsigned int *ctl = ctx->bfsCtl;
-        void *args[] = {&sdf, &markers, &I, &J, &step, &queue, &ctl};
-        FS2D_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(sdfExtrapolateKernel), dim3(ctx->smCount * std::max(perSm, 1)),
-                                              dim3(BFS_THREADS), args, 0, st));
+        int maxLayers = band;
+        void *args[] = {&sdf, &markers, &rowLo, &rowHi, &J, &step, &queue, &ctl, &maxLayers};
+        FS2D_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(sdfExtrapolateKernel),
+                                              dim3(std::max(1, ctx->smCount * std::max(perSm, 1) / share)), dim3(BFS_THREADS), args, 0, st));
     }
-    ctx->launches++;
-    ctx->launches += 2;
+    ctx->launches += 3;
+    if (inside && band > 0)
+    {
+        sdfClampKernel<<<divUp(cr.count(), NT), NT, 0, st>>>(field, ctx->markers, cr.begin, cr.end, band, -static_cast<float>(band + 1));
+        ctx->launches++;
+    }
+    FS2D_CUDA(cudaGetLastError());
     return FS2D_OK;
 }
 
@@ -888,17 +972,31 @@ int gridEulerAdvectParameters(Ctx *ctx)
     return FS2D_OK;
 }
 
+// Slab mode: halo rows of the level set and of the viscosity grid before pruneNarrowBand and the semi-Lagrangian step.
+int gridNbflipHalo(Ctx *ctx)
+{
+    if (ctx->p.sim_type != FS2D_SIM_NBFLIP) return FS2D_OK;
+    const void *arr[2] = {ctx->fluidSdf, ctx->viscosity};
+    const size_t rb[2] = {sizeof(float) * ctx->J, sizeof(float) * ctx->J};
+    return slabExchangeFields(ctx, arr, rb, 2);
+}
+
 // NBFlipSolver::advect, the grid part (nbflipsolver.cpp:66-109)
 int gridNbflipAdvect(Ctx *ctx)
 {
     if (ctx->p.sim_type != FS2D_SIM_NBFLIP) return FS2D_OK;
-    FS2D_TRY(slabUnsupported(ctx, "NBFlipSolver::advect"));
+    // Slab mode: the samples of the owned rows; a back-trace reaches cflNumber + 1 rows beyond them, inside the halo
+    // (U and V: refreshed by the extrapolation that ended the previous substep; level set and viscosity: by
+    // gridNbflipHalo, which fs2d_nbflip_advect_grids calls first).
+    const SlabRows own = slabOwn(ctx);
+    const int rowHiU = own.hi == ctx->I ? ctx->I + 1 : own.hi;
+    const long long J = ctx->J;
     const VelocityView vel = makeVelocityView(ctx->U, ctx->V, ctx->I, ctx->J);
     cudaStream_t st = ctx->stream;
-    eulerAdvectKernel<<<divUp(ctx->NU, NT), NT, 0, st>>>(vel.u, vel, ctx->stepDt, ctx->advU);
-    eulerAdvectKernel<<<divUp(ctx->NV, NT), NT, 0, st>>>(vel.v, vel, ctx->stepDt, ctx->advV);
-    eulerAdvectKernel<<<divUp(ctx->N, NT), NT, 0, st>>>(fluidSdfView(ctx), vel, ctx->stepDt, ctx->advSdf);
-    eulerAdvectKernel<<<divUp(ctx->N, NT), NT, 0, st>>>(viscosityView(ctx), vel, ctx->stepDt, ctx->advViscosity);
+    eulerAdvectKernel<<<divUp((rowHiU - own.lo) * J, NT), NT, 0, st>>>(vel.u, vel, ctx->stepDt, ctx->advU, own.lo * J, rowHiU * J);
+    eulerAdvectKernel<<<divUp((own.hi - own.lo) * (J + 1), NT), NT, 0, st>>>(vel.v, vel, ctx->stepDt, ctx->advV, own.lo * (J + 1), own.hi * (J + 1));
+    eulerAdvectKernel<<<divUp((own.hi - own.lo) * J, NT), NT, 0, st>>>(fluidSdfView(ctx), vel, ctx->stepDt, ctx->advSdf, own.lo * J, own.hi * J);
+    eulerAdvectKernel<<<divUp((own.hi - own.lo) * J, NT), NT, 0, st>>>(viscosityView(ctx), vel, ctx->stepDt, ctx->advViscosity, own.lo * J, own.hi * J);
     ctx->launches += 4;
     FS2D_CUDA(cudaGetLastError());
     return FS2D_OK;

@@ -415,11 +415,11 @@ __global__ void __launch_bounds__(NT) countCapKernel(const int32_t *__restrict__
 __global__ void __launch_bounds__(NT) pruneBandKernel(const float2 *__restrict__ pos, uint8_t *__restrict__ dead,
                                                       long long count, GridView fluidSdf, const int8_t *__restrict__ mat,
                                                       const int32_t *__restrict__ counts, int I, int J, int ppc,
-                                                      float narrowBand, float resamplingBand,
+                                                      float narrowBand, float resamplingBand, OwnedRows own,
                                                       unsigned long long *__restrict__ killed)
 {
     const long long p = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
-    if (p >= count || dead[p]) return;
+    if (p >= count || dead[p] || !ownedParticle(own, p)) return;  // ghost copies belong to a neighbour
     const float2 x = pos[p];
     const int i = clampi(static_cast<int>(x.x), 0, I - 1), j = clampi(static_cast<int>(x.y), 0, J - 1);
     const float sdf = gridLerp(fluidSdf, x.x, x.y);
@@ -886,7 +886,7 @@ int particlesPruneNarrowBand(Ctx *ctx)
     if (ctx->count == 0) return FS2D_OK;
     pruneBandKernel<<<gridFor(ctx->count), NT, 0, ctx->stream>>>(ctx->pb[ctx->cur].pos, ctx->dead, ctx->count, fluidSdfView(ctx),
                                                                 ctx->material, ctx->counts, ctx->I, ctx->J,
-                                                                ctx->p.particles_per_cell, -3.f, -1.f,
+                                                                ctx->p.particles_per_cell, -3.f, -1.f, ownedRows(ctx),
                                                                 reinterpret_cast<unsigned long long *>(ctx->d_counter));
     ctx->launches++;
     ctx->killedDirty = true;
@@ -897,6 +897,15 @@ int particlesPruneNarrowBand(Ctx *ctx)
 int particlesReseedPlan(Ctx *ctx, int64_t *candidates)
 {
     const int nb = ctx->p.sim_type == FS2D_SIM_NBFLIP ? 1 : 0;
+    if (nb)
+    {
+        // NBFlip gives a new particle the viscosity GRID value at its position (nbflipsolver.cpp:183-190): a sample one row
+        // beyond the slab for particles in its first / last row. P2G and the combine pass rewrote the owned rows since the
+        // halo was last refreshed.
+        const void *arr[1] = {ctx->viscosity};
+        const size_t rb[1] = {sizeof(float) * ctx->J};
+        FS2D_TRY(slabExchangeFields(ctx, arr, rb, 1));
+    }
     // slab mode: every rank plans its own rows; the host mirror strings the ranks' draws together in rank order,
     // which IS the reference's row-major cell order
     const SlabRows own = slabOwn(ctx);

@@ -32,6 +32,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "fs2d_internal.h"
 
@@ -899,7 +900,7 @@ template <bool MG> __device__ __forceinline__ int solveModeOf(const MgArgs &m, i
         if (static_cast<unsigned int>(w >> 32) == want) return static_cast<int>(w & 0xffffffffull);
         if (clock64() - t0 > MG_SPIN_LIMIT)
         {
-            m.mail->error = 1;
+            m.mail->error = 3;
             return -1;
         }
     }
@@ -926,7 +927,7 @@ __device__ __forceinline__ double llHaloLoad(const unsigned long long *buf, int 
             return __longlong_as_double(static_cast<long long>((a & 0xffffffffull) | (b << 32)));
         if (clock64() - t0 > MG_SPIN_LIMIT)
         {
-            *error = 1;
+            *error = 4;
             return 0.0;
         }
     }
@@ -977,7 +978,7 @@ template <bool MG> __device__ __forceinline__ bool llCollect(const MgArgs &m, in
             if (clock64() - t0 > MG_SPIN_LIMIT)
             {
                 ok = false;
-                m.mail->error = 1;
+                m.mail->error = 2;
                 break;
             }
         }
@@ -2511,6 +2512,30 @@ static bool buildSolveMaps(Ctx *ctx, SolveMaps *out)
     return true;
 }
 
+// Dynamic shared-memory ceilings of the PCG kernels: set ONCE per device to the largest request any launch makes and never
+// lowered. (Setting them per launch raced between the host threads of ranks that share a process in the tests: one
+// thread lowered the ceiling between another thread's set and its cooperative launch -> "too many blocks in
+// cooperative launch".)
+constexpr size_t PCG_EXCLUSIVE_SMEM = 160 * 1024;
+static void pcgKernelAttributes(int device)
+{
+    static std::mutex lock;
+    static unsigned long long done = 0;
+    std::lock_guard<std::mutex> guard(lock);
+    if (device < 0 || device >= 64 || (done >> device) & 1ull) return;
+    const int ceiling = static_cast<int>(std::max({sizeof(SolveSmem), sizeof(PipeSmem<MODE_K1>), sizeof(PipeSmem<MODE_K2>), PCG_EXCLUSIVE_SMEM}));
+    cudaFuncSetAttribute(pcgPipeKernel<MODE_K1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ceiling);
+    cudaFuncSetAttribute(pcgPipeKernel<MODE_K2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ceiling);
+    cudaFuncSetAttribute(pcgPipeKernel<MODE_K1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ceiling);
+    cudaFuncSetAttribute(pcgPipeKernel<MODE_K2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ceiling);
+    cudaFuncSetAttribute(pcgSolveKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ceiling);
+    cudaFuncSetAttribute(pcgSolveKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ceiling);
+    cudaFuncSetAttribute(pcgResidentKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(ResSmem)));
+    cudaFuncSetAttribute(pcgResidentKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(ResSmem)));
+    cudaGetLastError();
+    done |= 1ull << device;
+}
+
 int pcgTileBlocks(const Ctx *ctx) { return divUp(ctx->I, TR) * divUp(ctx->J, TC); }
 
 static bool pipeUsable(const Ctx *ctx) { return (ctx->J % 2) == 0 && !ctx->forceTileKernels; }
@@ -2537,10 +2562,10 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
     // CTAs of the persistent grids: what the device can hold co-resident (a cooperative launch refuses more; queried
     // once, for the kernel with the larger footprint), split between the ranks that share the GPU, capped by the
     // number of tiles and by the test knob.
+    pcgKernelAttributes(ctx->device);
     if (pipe && ctx->pcgOccupancy == 0)
     {
         int perSm = 0;
-        cudaFuncSetAttribute(pcgSolveKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(SolveSmem)));
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, pcgSolveKernel<true>, NT, sizeof(SolveSmem)) != cudaSuccess || perSm < 1)
         {
             cudaGetLastError();
@@ -2548,15 +2573,15 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
         }
         ctx->pcgOccupancy = std::min(perSm, 2);
     }
-    int pipeBlocks = std::max(1, std::min(blocks, std::max(1, ctx->pcgOccupancy) * ctx->smCount / share));
+    // Several ranks on ONE GPU (tests): the kernels of different ranks spin on each other, so all of them have to be
+    // co-resident whatever mix of streaming (109 KB, 256 threads) and resident (218 KB, 512 x 128 registers: a whole SM)
+    // CTAs the ranks launch. Two streaming CTAs of one rank on an SM could keep a resident CTA of another rank out for
+    // good, so with a shared GPU every CTA of these kernels takes an SM of its own (one per SM and rank share, a shared
+    // memory request no two of them fit side by side).
+    const int ctasPerSm = share > 1 ? 1 : std::max(1, ctx->pcgOccupancy);
+    const size_t exclusiveSmem = PCG_EXCLUSIVE_SMEM;
+    int pipeBlocks = std::max(1, std::min(blocks, ctasPerSm * ctx->smCount / share));
     if (ctx->pcgGridLimit > 0) pipeBlocks = std::min(pipeBlocks, ctx->pcgGridLimit);
-    if (pipe)
-    {
-        cudaFuncSetAttribute(pcgPipeKernel<MODE_K1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(PipeSmem<MODE_K1>)));
-        cudaFuncSetAttribute(pcgPipeKernel<MODE_K2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(PipeSmem<MODE_K2>)));
-        cudaFuncSetAttribute(pcgPipeKernel<MODE_K1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(PipeSmem<MODE_K1>)));
-        cudaFuncSetAttribute(pcgPipeKernel<MODE_K2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(PipeSmem<MODE_K2>)));
-    }
     const int flat = std::max(1, ctx->smCount * 8 / share);
     if (pcgTileBlocks(ctx) > ctx->maxBlocks || flat > ctx->maxBlocks)
     {
@@ -2726,12 +2751,10 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
             cudaError_t re;
             if (mgOn)
             {
-                cudaFuncSetAttribute(pcgResidentKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rsmem));
                 re = cudaLaunchCooperativeKernel(reinterpret_cast<void *>(pcgResidentKernel<true>), dim3(resBlocks), dim3(RNT), rargs, rsmem, st);
             }
             else
             {
-                cudaFuncSetAttribute(pcgResidentKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rsmem));
                 re = cudaLaunchCooperativeKernel(reinterpret_cast<void *>(pcgResidentKernel<false>), dim3(resBlocks), dim3(RNT), rargs, rsmem, st);
             }
             if (re == cudaErrorCooperativeLaunchTooLarge)
@@ -2743,15 +2766,13 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
             }
         }
         void *args[] = {&g, &mg, &maps, &useTensor};
-        const size_t smem = sizeof(SolveSmem);
+        const size_t smem = (mgOn && share > 1) ? std::max(sizeof(SolveSmem), exclusiveSmem) : sizeof(SolveSmem);
         if (mgOn)
         {
-            cudaFuncSetAttribute(pcgSolveKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
             FS2D_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(pcgSolveKernel<true>), dim3(pipeBlocks), dim3(NT), args, smem, st));
         }
         else
         {
-            cudaFuncSetAttribute(pcgSolveKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
             const cudaError_t le = cudaLaunchCooperativeKernel(reinterpret_cast<void *>(pcgSolveKernel<false>), dim3(pipeBlocks), dim3(NT), args, smem, st);
             if (le == cudaErrorCooperativeLaunchTooLarge)
             {
@@ -2802,7 +2823,7 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
             mg.phase = 2 * i + 1;
             mg.loOut1 = peerOf(mg.rank - 1, ctx->q);
             mg.hiOut1 = peerOf(mg.rank + 1, ctx->q);
-            pcgPipeKernel<MODE_K1, true><<<pipeBlocks, NT, sizeof(PipeSmem<MODE_K1>), st>>>(k1, blocks, mg);
+            pcgPipeKernel<MODE_K1, true><<<pipeBlocks, NT, share > 1 ? exclusiveSmem : sizeof(PipeSmem<MODE_K1>), st>>>(k1, blocks, mg);
         }
         else if (pipe)
             pcgPipeKernel<MODE_K1, false><<<pipeBlocks, NT, sizeof(PipeSmem<MODE_K1>), st>>>(k1, blocks, mg);
@@ -2819,7 +2840,7 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
             mg.phase = 2 * i + 2;
             mg.loOut1 = peerOf(mg.rank - 1, ctx->z);
             mg.hiOut1 = peerOf(mg.rank + 1, ctx->z);
-            pcgPipeKernel<MODE_K2, true><<<pipeBlocks, NT, sizeof(PipeSmem<MODE_K2>), st>>>(k2, blocks, mg);
+            pcgPipeKernel<MODE_K2, true><<<pipeBlocks, NT, share > 1 ? exclusiveSmem : sizeof(PipeSmem<MODE_K2>), st>>>(k2, blocks, mg);
         }
         else if (pipe)
             pcgPipeKernel<MODE_K2, false><<<pipeBlocks, NT, sizeof(PipeSmem<MODE_K2>), st>>>(k2, blocks, mg);

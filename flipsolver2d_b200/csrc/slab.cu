@@ -40,7 +40,7 @@ struct ExportBlob
 };
 static_assert(sizeof(ExportBlob) <= FS2D_SLAB_HANDLE_BYTES, "export blob does not fit the ABI buffer");
 
-__device__ __forceinline__ bool spinAtLeast(const unsigned long long *flag, unsigned long long want, int *err)
+__device__ __forceinline__ bool spinAtLeast(const unsigned long long *flag, unsigned long long want, int *err, int site = 9)
 {
     const volatile unsigned long long *f = flag;
     const long long t0 = clock64();
@@ -48,7 +48,7 @@ __device__ __forceinline__ bool spinAtLeast(const unsigned long long *flag, unsi
     {
         if (clock64() - t0 > SPIN_LIMIT)
         {
-            *err = 1;
+            *err = site;
             return false;
         }
     }
@@ -93,8 +93,8 @@ __device__ void exchangeOpen(SlabMail *mail, SlabMail *loMail, SlabMail *hiMail,
             if (loMail) storeFlag(&loMail->ready[1], seq);
             if (hiMail) storeFlag(&hiMail->ready[0], seq);
         }
-        if (loMail) spinAtLeast(&mail->ready[0], seq, &mail->error);
-        if (hiMail) spinAtLeast(&mail->ready[1], seq, &mail->error);
+        if (loMail) spinAtLeast(&mail->ready[0], seq, &mail->error, 5);
+        if (hiMail) spinAtLeast(&mail->ready[1], seq, &mail->error, 5);
     }
     __syncthreads();
 }
@@ -111,8 +111,8 @@ __device__ void exchangeClose(SlabMail *mail, SlabMail *loMail, SlabMail *hiMail
             __threadfence_system();
             if (loMail) storeFlag(&loMail->data[1], seq);
             if (hiMail) storeFlag(&hiMail->data[0], seq);
-            if (loMail) spinAtLeast(&mail->data[0], seq, &mail->error);
-            if (hiMail) spinAtLeast(&mail->data[1], seq, &mail->error);
+            if (loMail) spinAtLeast(&mail->data[0], seq, &mail->error, 6);
+            if (hiMail) spinAtLeast(&mail->data[1], seq, &mail->error, 6);
             __threadfence_system();
         }
     }
@@ -303,7 +303,7 @@ __global__ void slabGatherKernel(GatherArgs a)
         for (int k = 0; k < 4; k++) *reinterpret_cast<volatile long long *>(&slot->v[k]) = a.v[k];
         __threadfence_system();
         storeFlag(&slot->tag, a.seq);
-        spinAtLeast(&a.mail->gather[par][r].tag, a.seq, &a.mail->error);
+        spinAtLeast(&a.mail->gather[par][r].tag, a.seq, &a.mail->error, 7);
         __threadfence_system();
     }
 }
@@ -383,7 +383,9 @@ int slabCheckError(Ctx *ctx)
     FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
     if (err)
     {
-        ctx->lastError = "slab: a peer did not answer within the spin limit";
+        // which wait gave up: 1 PCG phase-0 partials, 2 PCG barrier words, 3 solve mode of a row neighbour, 4 LL halo row,
+        // 5 / 6 halo exchange open / close, 7 all-gather, 9 other
+        ctx->lastError = "slab: a peer did not answer within the spin limit (wait site " + std::to_string(err) + ")";
         return FS2D_ERR_COMM;
     }
     return FS2D_OK;
@@ -551,24 +553,36 @@ int slabAllGather(Ctx *ctx, const long long v[4], long long *out)
 // synchronous): nobody is overwritten before it has finished what it was doing, nobody reads before all pushes landed.
 int slabGatherRows(Ctx *ctx, void *array, size_t rowBytes, int rowsTotal)
 {
+    void *arrays[1] = {array};
+    const size_t rb[1] = {rowBytes};
+    const int rt[1] = {rowsTotal};
+    return slabGatherMany(ctx, arrays, rb, rt, 1);
+}
+
+// Several arrays inside one pair of all-gathers.
+int slabGatherMany(Ctx *ctx, void *const *arrays, const size_t *rowBytes, const int *rowsTotal, int count)
+{
     SlabState &s = ctx->slab;
     if (!s.enabled || s.world == 1) return FS2D_OK;
     FS2D_TRY(requireConnected(ctx));
     const long long zero[4] = {0, 0, 0, 0};
     long long all[4 * FS2D_MAX_RANKS];
     FS2D_TRY(slabAllGather(ctx, zero, all));
-    GatherRowsArgs a;
-    a.heap = ctx->heap;
-    for (int r = 0; r < FS2D_MAX_RANKS; r++) a.peerHeap[r] = r < s.world ? s.peerHeap[r] : nullptr;
-    a.rank = s.rank;
-    a.world = s.world;
-    a.offset = static_cast<unsigned long long>(static_cast<unsigned char *>(array) - ctx->heap);
-    const int rowEnd = s.rank == s.world - 1 ? rowsTotal : s.rowEnd;  // the extra U row belongs to the last slab
-    a.bytesBegin = static_cast<unsigned long long>(s.rowBegin) * rowBytes;
-    a.bytes = static_cast<unsigned long long>(rowEnd - s.rowBegin) * rowBytes;
-    const int blocks = std::max(1, ctx->smCount / s.share);
-    slabGatherRowsKernel<<<blocks, 256, 0, ctx->stream>>>(a);
-    ctx->launches++;
+    for (int k = 0; k < count; k++)
+    {
+        GatherRowsArgs a;
+        a.heap = ctx->heap;
+        for (int r = 0; r < FS2D_MAX_RANKS; r++) a.peerHeap[r] = r < s.world ? s.peerHeap[r] : nullptr;
+        a.rank = s.rank;
+        a.world = s.world;
+        a.offset = static_cast<unsigned long long>(static_cast<unsigned char *>(arrays[k]) - ctx->heap);
+        const int rowEnd = s.rank == s.world - 1 ? rowsTotal[k] : s.rowEnd;  // the extra U row belongs to the last slab
+        a.bytesBegin = static_cast<unsigned long long>(s.rowBegin) * rowBytes[k];
+        a.bytes = static_cast<unsigned long long>(rowEnd - s.rowBegin) * rowBytes[k];
+        const int blocks = std::max(1, ctx->smCount / s.share);
+        slabGatherRowsKernel<<<blocks, 256, 0, ctx->stream>>>(a);
+        ctx->launches++;
+    }
     FS2D_CUDA(cudaGetLastError());
     FS2D_TRY(slabAllGather(ctx, zero, all));
     return FS2D_OK;

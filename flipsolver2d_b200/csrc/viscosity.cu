@@ -577,8 +577,20 @@ int gridViscosity(Ctx *ctx, int *iters)
 {
     if (ctx->slab.enabled && ctx->slab.world > 1)
     {
-        ctx->lastError = "applyViscosity is not slab-aware yet (only FS2D_SIM_LIQUID without viscosity runs on several GPUs)";
-        return FS2D_ERR_STATE;
+        // Row slabs: the solve is REPLICATED. Every rank pushes its rows of U, V, the viscosity grid and the material grid
+        // to all the others (one collective) and then solves the whole system itself -- same kernels, same reduction
+        // order, hence bit-identical to a single handle on every rank, and U / V come out valid on all rows. The stage
+        // is a handful of iterations of grid-only passes; distributing it would add two all-reduces
+        // and a halo exchange per iteration for a stage that is ~2 ms at 4096^2.
+        if (ctx->p.heavy_viscosity)
+        {
+            ctx->lastError = "HeavyViscosityModel is not slab-aware";
+            return FS2D_ERR_STATE;
+        }
+        void *arr[4] = {ctx->U, ctx->V, ctx->viscosity, ctx->material};
+        const size_t rb[4] = {sizeof(float) * ctx->J, sizeof(float) * (ctx->J + 1), sizeof(float) * ctx->J, static_cast<size_t>(ctx->J)};
+        const int rt[4] = {ctx->I + 1, ctx->I, ctx->I, ctx->I};
+        FS2D_TRY(slabGatherMany(ctx, arr, rb, rt, 4));
     }
     if (ctx->p.heavy_viscosity) return gridViscosityHeavy(ctx, iters);
     if (!ctx->viscScalars) FS2D_CUDA(cudaMalloc(&ctx->viscScalars, 256));

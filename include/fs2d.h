@@ -308,6 +308,14 @@ int fs2d_reseed_apply(fs2d_handle h, int64_t candidates, const float *host_unifo
 /* NBFlipSolver::pruneNarrowBand + semi-Lagrangian advection of U, V, sdf, viscosity
  * (nbflipsolver.cpp:66-109,227-253) */
 int fs2d_nbflip_advect_grids(fs2d_handle h);
+/* NBFlipSolver runs extrapolateLevelsetOutside / Inside (flipsolver2d.cpp:1433-1558) every substep; their radius is
+ * unbounded (thousands of dependent layers at 4096^2) although the solver only reads the level set near the interface.
+ * By default the device walks `layers` = 24 layers: every cell within 24 layers of the interface is bit-identical to the
+ * unbounded walk, beyond it the inside walk writes -(layers + 1) and the outside walk leaves updateSdf's "no particle"
+ * value; particles, materials, velocities and pressures are unaffected (tests/test_nbflip_band_gpu.py), and a download
+ * of FS2D_GRID_FLUID_SDF completes the inside walk on a copy. layers = 0 selects the reference's unbounded walks
+ * (required for a bit-exact level-set field far from the interface; not available over row slabs). */
+int fs2d_set_sdf_band(fs2d_handle h, int layers);
 
 /* One whole FlipSolver::step() (flipsolver2d.cpp:412-462) or NBFlipSolver::step()
  * (nbflipsolver.cpp:26-64) for scenes without sources (no host RNG needed):
@@ -325,7 +333,9 @@ int fs2d_substep(fs2d_handle h, float dt, float *stage_ms, int *iters);
  *   grids on every rank, only the rank's OWN particles) -> stage calls, the same sequence on every rank.
  * device_share = how many ranks run on the same GPU (1 in production; > 1 lets a single GPU host several
  * ranks for testing, with the persistent kernels sized so that all ranks stay co-resident).
- * Only FS2D_SIM_LIQUID without viscosity is slab-aware so far; other solvers report FS2D_ERR_STATE. */
+ * Slab-aware: FS2D_SIM_LIQUID and FS2D_SIM_NBFLIP, with or without the light viscosity model (the viscosity solve is
+ * replicated: every rank gathers the velocity rows of the others and solves the whole system, bit-identical to one
+ * handle); smoke / fire and the heavy viscosity model report FS2D_ERR_STATE. */
 #define FS2D_SLAB_HANDLE_BYTES 256
 int fs2d_slab_configure(fs2d_handle h, int rank, int world, int device_share);
 /* The same with explicit slab boundaries: row_bounds[world + 1], row_bounds[0] = 0, row_bounds[world] = gridSizeI,

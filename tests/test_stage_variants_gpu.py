@@ -124,6 +124,7 @@ def test_nbflip_stage_sequence(ref_mod, scene_dir, viscous):
     materials, body forces, matrix, rhs."""
     scene = scenes.dam_break(64, "nbflip", viscosity_enabled=viscous)
     s, h, d = _pair(ref_mod, scene_dir, scene, "var_nbflip_%d" % viscous, 2, 2)
+    d.set_sdf_band(0)   # the reference's unbounded level-set walks: the whole field is compared bit for bit below
     dt = 1.0 / 120.0
     s.set_step_dt(dt)
     d.set_step_dt(dt)
