@@ -409,7 +409,18 @@ def run_ours(args, rank, world, local_rank):
     # ---- end to end: the particle state crosses PCIe both ways every step, through the packed C-ABI calls (one copy per
     # direction; lossless: the storage-bin byte travels with the records, tests/test_substep_gpu.py proves the round trip
     # is the identity on the solver state)
-    P = particles
+    # The region runs on a SECOND solver of the same scene, warmed up by the same number of substeps, so that it covers
+    # the same simulation window as `value` (the dam break spreads: later substeps have more active PCG tiles and a
+    # larger extrapolation box; timing the regions back to back on one solver compared different work).
+    if not args.no_e2e:
+        resident_solver, resident_dev = solver, dev
+        solver = make_solver(scene_for(res), "scene_e2e_%d" % res)
+        solver.prepare()
+        dev = solver.device(num_properties=2)
+        stream = torch.cuda.ExternalStream(capi.lib().fs2d_stream(dev.h), device=torch.device("cuda", local_rank))
+        for _ in range(max(args.warmup, 3) - 1):   # + the warm-up step of the transfer path below
+            solver.step_substep()
+    P = solver.particle_count()
     K = 2
     rec = 16 + 4 * K + 1
     cap = int(P * 1.25) + 1024
@@ -431,25 +442,49 @@ def run_ours(args, rank, world, local_rank):
         state["n_max"] = max(state["n_max"], n.value)
         state["d2h"] += n.value * rec
 
+    phase_s = {"upload": 0.0, "substep": 0.0, "download": 0.0}
+
     def e2e_step():
         n = state["n"]
+        t0 = time.perf_counter()
         rc = L.fs2d_upload_particles_packed(dev.h, hostbuf.data_ptr(), n)
         assert rc == 0, dev.L.fs2d_last_error(dev.h)
         state["h2d"] += n * rec
+        t1 = time.perf_counter()
         solver.step_substep()
+        dev.synchronize()
+        t2 = time.perf_counter()
         download()
+        t3 = time.perf_counter()
+        phase_s["upload"] += t1 - t0
+        phase_s["substep"] += t2 - t1
+        phase_s["download"] += t3 - t2
 
     e2e = None
     if not args.no_e2e:
         download()
         e2e_step()  # warm-up of the path
         state["h2d"] = state["d2h"] = 0
+        for k in phase_s:
+            phase_s[k] = 0.0
         state["n_min"] = state["n_max"] = n_start = state["n"]
         e2e_steps = args.steps
+        dev.pcg_profile(True)
+        dev.kernel_profile(True)
         e2e_ms = timed(e2e_step, e2e_steps)
+        e2e_solve_ms, e2e_solve_n = dev.pcg_profile_solves()
+        e2e_groups = dev.kernel_profile_read()
+        dev.pcg_profile(False)
+        dev.kernel_profile(False)
         e2e = {"value": e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": total(state["h2d"]) // e2e_steps,
                "d2h_bytes_per_step": total(state["d2h"]) // e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                "particles_start": total(n_start), "particles_end": total(state["n"]), "bytes_per_particle": rec,
+               "host_ms_per_step_rank0": {k: round(v / e2e_steps * 1e3, 3) for k, v in phase_s.items()},
+               "pcg_solve_kernel_ms": e2e_solve_ms / max(e2e_solve_n, 1),
+               "kernel_group_ms": {g: round(v[0] / max(v[1], 1), 3) for g, v in e2e_groups.items()},
+               "stage_ms_per_substep_last_frame": (lambda st: {n: round(float(st["timings"][k]) / max(st["substeps"], 1), 3)
+                                                               for k, n in enumerate(host_api.STAGES)})(solver.stats()),
+               "window": "substeps %d .. %d of the scene, the window `value` was timed on (second solver, same warm-up)" % (max(args.warmup, 3) + 1, max(args.warmup, 3) + 1 + e2e_steps),
                "what": "per step: fs2d_upload_particles_packed from a pinned host buffer, FlipSolver::stepSubstep, "
                        "fs2d_download_particles_packed into it (positions, velocities, %d property columns, storage-bin byte)" % K
                        + (" (every rank moves the particles of its slab; bytes summed over ranks)" if world > 1 else "")}
@@ -459,6 +494,8 @@ def run_ours(args, rank, world, local_rank):
     config_5 = None
     if world > 1 and not args.no_config5:
         solver.close()
+        if not args.no_e2e:
+            resident_solver.close()
         del hostbuf
         torch.cuda.empty_cache()
         config_5 = config5_region(make_solver, timed, total, world, local_rank, torch, capi, args)

@@ -290,7 +290,8 @@ class Device:
         """Packed particle state (pos | vel | props | storage byte) into `buf` (uint8 numpy array; allocated when
         None). Returns (buf, count)."""
         if buf is None:
-            buf = np.zeros(int(self.L.fs2d_packed_particle_bytes(self.h, self.particle_count())) + 64, np.uint8)
+            # records flagged dead since the last sort travel too: leave room for them
+            buf = np.zeros(int(self.L.fs2d_packed_particle_bytes(self.h, self.particle_count())) * 5 // 4 + 4096, np.uint8)
         n = C.c_int64(0)
         self._ck(self.L.fs2d_download_particles_packed(self.h, _p(buf), buf.nbytes, C.byref(n)), "download_packed")
         return buf, n.value

@@ -89,6 +89,28 @@ __global__ void fillFloatKernel(float *p, long long n, float v)
         p[k] = v;
 }
 
+// Packed particle transfers: the storage-bin byte of a record doubles as its dead flag (254).
+#define FS2D_PACKED_DEAD 254
+__global__ void packStorageKernel(const uint8_t *__restrict__ mis, const uint8_t *__restrict__ dead, long long n, unsigned char *__restrict__ out)
+{
+    const long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (p < n) out[p] = dead[p] ? FS2D_PACKED_DEAD : mis[p];
+}
+
+__global__ void unpackStorageKernel(const unsigned char *__restrict__ in, long long n, uint8_t *__restrict__ mis, uint8_t *__restrict__ dead,
+                                    unsigned long long *__restrict__ killed)
+{
+    const long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const bool isDead = p < n && in[p] == FS2D_PACKED_DEAD;
+    if (p < n)
+    {
+        mis[p] = isDead ? FS2D_MIS_HOME : in[p];
+        dead[p] = isDead ? 1 : 0;
+    }
+    const unsigned int votes = __popc(__ballot_sync(0xffffffffu, isDead));
+    if ((threadIdx.x & 31) == 0 && votes) atomicAdd(killed, static_cast<unsigned long long>(votes));
+}
+
 __global__ void fillIntKernel(int32_t *p, long long n, int32_t v)
 {
     for (long long k = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; k < n;
@@ -513,12 +535,20 @@ size_t fs2d_packed_particle_bytes(fs2d_handle ctx, int64_t count)
 int fs2d_download_particles_packed(fs2d_handle ctx, void *host_buf, size_t capacity_bytes, int64_t *count)
 {
     if (!ctx || !host_buf || !count) return FS2D_ERR_ARG;
-    int64_t alive = 0;
-    FS2D_TRY(particlesAliveCount(ctx, &alive));
     const bool slab = ctx->slab.enabled && ctx->slab.world > 1;
-    if (alive != ctx->count - ctx->slab.ghostCount || !ctx->sorted) FS2D_TRY(particlesSort(ctx));
-    const int64_t first = slab ? ctx->slab.ownedBegin : 0;
-    const int64_t n = slab ? ctx->slab.ownedEnd - ctx->slab.ownedBegin : ctx->count;
+    int64_t first = 0, n = ctx->count;
+    if (slab)
+    {
+        // row slabs: the arrays also hold ghost copies of the neighbours' particles; after a sort the owned records
+        // are one contiguous range
+        int64_t alive = 0;
+        FS2D_TRY(particlesAliveCount(ctx, &alive));
+        if (alive != ctx->count - ctx->slab.ghostCount || !ctx->sorted) FS2D_TRY(particlesSort(ctx));
+        first = ctx->slab.ownedBegin;
+        n = ctx->slab.ownedEnd - ctx->slab.ownedBegin;
+    }
+    // one handle: every record in the CURRENT device order, flagged-dead ones included (storage byte 254) -- no sort,
+    // no host synchronisation before the copy, and the round trip restores the arrays exactly as they are
     *count = n;
     const size_t bytes = fs2d_packed_particle_bytes(ctx, n);
     if (bytes > capacity_bytes)
@@ -537,7 +567,8 @@ int fs2d_download_particles_packed(fs2d_handle ctx, void *host_buf, size_t capac
     for (int k = 0; k < K; k++)
         FS2D_CUDA(cudaMemcpyAsync(d + (16u + 4u * k) * n, b.props + static_cast<int64_t>(k) * b.capacity + first, 4u * n,
                                   cudaMemcpyDeviceToDevice, st));
-    FS2D_CUDA(cudaMemcpyAsync(d + (16u + 4u * K) * n, b.mis + first, static_cast<size_t>(n), cudaMemcpyDeviceToDevice, st));
+    packStorageKernel<<<divUp(n, 256), 256, 0, st>>>(b.mis + first, ctx->dead + first, n, d + (16u + 4u * K) * n);
+    ctx->launches++;
     FS2D_CUDA(cudaMemcpyAsync(host_buf, d, bytes, cudaMemcpyDeviceToHost, st));
     FS2D_CUDA(cudaStreamSynchronize(st));
     return FS2D_OK;
@@ -546,26 +577,40 @@ int fs2d_download_particles_packed(fs2d_handle ctx, void *host_buf, size_t capac
 int fs2d_upload_particles_packed(fs2d_handle ctx, const void *host_buf, int64_t count)
 {
     if (!ctx || count < 0 || (count > 0 && !host_buf)) return FS2D_ERR_ARG;
-    FS2D_TRY(fs2d_upload_particles(ctx, 0, nullptr, nullptr, nullptr));  // resets the particle state
-    if (count == 0) return FS2D_OK;
     const bool slab = ctx->slab.enabled && ctx->slab.world > 1;
+    cudaStream_t st = ctx->stream;
+    FS2D_CUDA(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), st));
+    ctx->count = 0;
+    ctx->deadCount = 0;
+    ctx->killedDirty = false;
+    ctx->sorted = false;
+    ctx->slab.ghostCount = 0;
+    ctx->slab.ownedBegin = ctx->slab.ownedEnd = 0;
+    if (count == 0)
+    {
+        FS2D_CUDA(cudaMemsetAsync(ctx->cellStart, 0, sizeof(int32_t) * (ctx->N + 1), st));
+        ctx->sorted = true;
+        return FS2D_OK;
+    }
     FS2D_TRY(particlesReserve(ctx, count + (slab ? 2 * ctx->slab.xchgCapacity : 0)));
     const size_t bytes = fs2d_packed_particle_bytes(ctx, count);
     FS2D_TRY(stageReserve(ctx, bytes));
     ParticleBuffers &b = ctx->pb[ctx->cur];
     const int K = ctx->p.num_properties;
     const size_t n = static_cast<size_t>(count);
-    cudaStream_t st = ctx->stream;
     unsigned char *d = ctx->stage;
     FS2D_CUDA(cudaMemcpyAsync(d, host_buf, bytes, cudaMemcpyHostToDevice, st));
     FS2D_CUDA(cudaMemcpyAsync(b.pos, d, 8u * n, cudaMemcpyDeviceToDevice, st));
     FS2D_CUDA(cudaMemcpyAsync(b.vel, d + 8u * n, 8u * n, cudaMemcpyDeviceToDevice, st));
     for (int k = 0; k < K; k++)
         FS2D_CUDA(cudaMemcpyAsync(b.props + static_cast<int64_t>(k) * b.capacity, d + (16u + 4u * k) * n, 4u * n, cudaMemcpyDeviceToDevice, st));
-    FS2D_CUDA(cudaMemcpyAsync(b.mis, d + (16u + 4u * K) * n, n, cudaMemcpyDeviceToDevice, st));
-    FS2D_CUDA(cudaMemsetAsync(ctx->dead, 0, n, st));
+    // storage byte -> storage-bin code + dead flag; the dead ones are counted on the device (folded into the host's view
+    // at the next particle count, like the kills of a stage)
+    unpackStorageKernel<<<divUp(count, 256), 256, 0, st>>>(d + (16u + 4u * K) * n, count, b.mis, ctx->dead,
+                                                           reinterpret_cast<unsigned long long *>(ctx->d_counter));
+    ctx->launches++;
     ctx->count = count;
-    ctx->sorted = false;
+    ctx->killedDirty = true;
     FS2D_TRY(particlesKeyRange(ctx, 0, count));
     // the host buffer may be reused as soon as this returns
     FS2D_CUDA(cudaStreamSynchronize(st));

@@ -185,8 +185,11 @@ int fs2d_get_particle_storage_bins(fs2d_handle h, int32_t *host_bins);
  * dump / restore (the grids go through fs2d_download_grid / fs2d_upload_grid). Layout for n particles, K property
  * columns: float2 pos[n] | float2 vel[n] | float props[K][n] | uint8 storage[n]; storage = (di+2)*5 + (dj+2) with
  * (di, dj) = bin the particle is filed in minus bin of its position (markerparticlesystem.cpp:146-159), 12 = at home,
- * 255 = further than two bins away. fs2d_packed_particle_bytes(h, n) = n * (16 + 4K + 1). Pinned host buffers make
- * the copies run at PCIe speed; the calls return when the host buffer may be reused / read. */
+ * 255 = further than two bins away, 254 = the record is flagged dead (killed by a stage, not yet compacted by the
+ * next sort: the download copies the arrays as they are, in the current device order, without sorting -- *count is the
+ * number of RECORDS, fs2d_particle_count() the number of live particles). fs2d_packed_particle_bytes(h, n) =
+ * n * (16 + 4K + 1). Pinned host buffers make the copies run at PCIe speed; the calls return when the host buffer may
+ * be reused / read. Over row slabs the download sorts first and returns the records the rank owns. */
 size_t fs2d_packed_particle_bytes(fs2d_handle h, int64_t count);
 int fs2d_download_particles_packed(fs2d_handle h, void *host_buf, size_t capacity_bytes, int64_t *count);
 int fs2d_upload_particles_packed(fs2d_handle h, const void *host_buf, int64_t count);

@@ -93,7 +93,7 @@ def test_packed_round_trip_equals_resident_stepping(ref_mod, scene_dir, res, den
     for k in range(steps):
         resident.substep(dt)
         buf, n = packed.download_packed()
-        assert n == packed.particle_count()
+        assert n >= packed.particle_count()   # records, flagged-dead ones included; no sort on the way out
         packed.upload_packed(buf, n)
         packed.substep(dt)
         pos, vel, props = plain.download_particles()
