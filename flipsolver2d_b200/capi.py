@@ -149,6 +149,7 @@ def lib():
         "fs2d_pcg_set_grid_limit": (i32, [H, i32]),
         "fs2d_pcg_set_tile_kernels": (i32, [H, i32]),
         "fs2d_pcg_set_resident": (i32, [H, i32]),
+        "fs2d_pcg_last_kernel": (i32, [H, C.POINTER(C.c_int)]),
         "fs2d_kernel_profile": (i32, [H, i32]),
         "fs2d_kernel_profile_read": (i32, [H, vp, vp]),
         "fs2d_slab_configure": (i32, [H, i32, i32, i32]),
@@ -354,7 +355,14 @@ class Device:
         self._ck(self.L.fs2d_set_sdf_band(self.h, int(layers)), "set_sdf_band")
 
     def pcg_set_resident(self, resident=True):
-        self._ck(self.L.fs2d_pcg_set_resident(self.h, 1 if resident else 0), "pcg_set_resident")
+        """True / 1: resident kernel, paged tiles allowed; 2: resident kernel without paging; False / 0: streaming kernel."""
+        self._ck(self.L.fs2d_pcg_set_resident(self.h, int(resident)), "pcg_set_resident")
+
+    def pcg_last_kernel(self):
+        """0 = streaming whole-solve kernel (or stepwise), 1 = resident, 2 = resident + paged tiles."""
+        k = C.c_int(0)
+        self._ck(self.L.fs2d_pcg_last_kernel(self.h, C.byref(k)), "pcg_last_kernel")
+        return k.value
 
     def pcg_set_tile_kernels(self, tile=True):
         self._ck(self.L.fs2d_pcg_set_tile_kernels(self.h, 1 if tile else 0), "pcg_set_tile_kernels")

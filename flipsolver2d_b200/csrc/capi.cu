@@ -772,6 +772,17 @@ int fs2d_pcg_set_resident(fs2d_handle ctx, int resident)
 {
     if (!ctx) return FS2D_ERR_ARG;
     ctx->residentPcg = resident != 0;
+    ctx->pagedPcg = resident == 1 && !(std::getenv("FS2D_PCG_PAGED") && std::atoi(std::getenv("FS2D_PCG_PAGED")) == 0);
+    return FS2D_OK;
+}
+
+int fs2d_pcg_last_kernel(fs2d_handle ctx, int *kind)
+{
+    if (!ctx || !kind) return FS2D_ERR_ARG;
+    int pad = 0;
+    FS2D_CUDA(fs2dCopyToHost(ctx, &pad, &ctx->scalars->pad, sizeof(pad)));
+    FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
+    *kind = pad;
     return FS2D_OK;
 }
 

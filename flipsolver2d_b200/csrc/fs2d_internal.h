@@ -218,6 +218,7 @@ struct fs2d_context
     // grid already gives every CTA several tiles to walk (the pipelined k >= 1 path the 4096^2 runs live on); 0 = no cap
     int pcgGridLimit = std::getenv("FS2D_PCG_GRID") ? std::atoi(std::getenv("FS2D_PCG_GRID")) : 0;
     bool residentPcg = !(std::getenv("FS2D_PCG_RESIDENT") && std::atoi(std::getenv("FS2D_PCG_RESIDENT")) == 0);  // A/B switch (fs2d_pcg_set_resident)
+    bool pagedPcg = !(std::getenv("FS2D_PCG_PAGED") && std::atoi(std::getenv("FS2D_PCG_PAGED")) == 0);          // resident + paged tiles (pcgResidentKernel<false, true>)
     int pcgOccupancy = 0;                 // CTAs of pcgSolveKernel one SM holds (occupancy query, cached)
     void *solveMaps = nullptr;            // host copy of the tensor maps of the Krylov vectors (pcg.cu)
     bool solveMapsTried = false, solveMapsOk = false;

@@ -534,6 +534,16 @@ __device__ __forceinline__ void bulkLoad(void *dstSmem, const void *srcGlobal, u
 
 __device__ __forceinline__ void fenceProxyAsync() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// shared -> global bulk copy (bulk-group completion), used by the paged tiles of pcgResidentKernel
+__device__ __forceinline__ void bulkStore(void *dstGlobal, const void *srcSmem, unsigned int bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dstGlobal), "r"(smemAddr(srcSmem)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulkWaitRead0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }  // sources may be overwritten
+__device__ __forceinline__ void bulkWaitAllButLast() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); }  // all but the newest group complete
+__device__ __forceinline__ void bulkWaitAll() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // Warp 0 fetches one tile: every lane owns whole rows. A row segment clipped by the ends of the vector is
 // zero-filled with ordinary stores (visible to the consumers through the __syncthreads that separates
 // the issue from the use of a stage).
@@ -1602,9 +1612,21 @@ __global__ void __launch_bounds__(NT, 2) pcgSolveKernel(SolveArgs g, MgArgs mg, 
 // barrier plus ~1 us of shared-memory arithmetic. Arithmetic, barrier protocol (phases, tags, mail ring), halo-row pushes
 // into the row neighbours' q / z and convergence logic are those of pcgSolveKernel, so a rank running this kernel
 // interoperates with a rank streaming its tiles. x is written once, at the end (pending alpha * s included).
+//
+// PAGED = true (one GPU, RES_TPC * CTAs < tiles <= RES_PAGED_TPC * CTAs: the 4096^2 dam break has 904 tiles for 148 SMs): a
+// CTA keeps RES_TPC - 1 tiles resident as above and treats its other tiles as *paged* resident tiles: the same
+// halo-extended private boxes of s and r, but stored in global memory (L2) -- in the s[0] / r[0] arrays, which nothing else
+// uses while this kernel runs, box k of the active list at k * PTILE_PAD -- and brought through two shared-memory scratch
+// boxes (the storage of the fourth resident tile) by 19 KB bulk copies: cp.async.bulk in (the box of the NEXT paged tile,
+// or of the next phase's first one, flies while the CTA computes; mbarrier completion), in-place update and stencil in
+// shared memory, cp.async.bulk out (bulk group). The inter-phase values (z into K1, q into K2) are the ones the thread
+// itself wrote to the global arrays one phase earlier, x is updated in place in global memory. Same arithmetic, same ring
+// protocol, so resident and paged tiles are neighbours without knowing it.
 constexpr int RNT = 512;          // threads per CTA
 constexpr int RES_TPC = 4;        // tiles a CTA can hold
+constexpr int RES_PAGED_TPC = 12; // tiles per CTA (resident + paged) beyond which the streaming kernel takes the solve
 constexpr int RES_CELLS = TR * TC / RNT;  // interior cells per thread and tile (4)
+constexpr unsigned int RES_BOX_BYTES = PTILE_PAD * 8u;
 
 struct ResTile
 {
@@ -1620,6 +1642,7 @@ struct ResSmem
     double preTbl[8];
     double pub[2];
     double bc[2];
+    unsigned long long full[2];  // paged tiles: arrival of a box in scratch 0 / 1
     int isLast;
     int ok;
 };
@@ -1764,21 +1787,27 @@ __device__ __forceinline__ void resRingCell(int tid, int i0, int j0, int I, long
     }
 }
 
-template <bool MG> __global__ void __launch_bounds__(RNT, 1) pcgResidentKernel(SolveArgs g, MgArgs mg)
+template <bool MG, bool PAGED> __global__ void __launch_bounds__(RNT, 1) pcgResidentKernel(SolveArgs g, MgArgs mg)
 {
+    static_assert(!(MG && PAGED), "paged tiles: one GPU only");
+    constexpr int RES = PAGED ? RES_TPC - 1 : RES_TPC;  // resident tiles of a CTA (paged mode: the last tile's storage is scratch)
     extern __shared__ __align__(128) unsigned char resRaw[];
     ResSmem &sm = *reinterpret_cast<ResSmem *>(resRaw);
     const int tid = threadIdx.x;
     PcgScalars *sc = g.a.sc;
     const int count = *g.a.activeCount;
     const unsigned int P = static_cast<unsigned int>(min(static_cast<int>(gridDim.x), count));  // participating CTAs
-    if (count > RES_TPC * static_cast<int>(gridDim.x) || count <= 0)
-        return;  // too many tiles to hold (or nothing to do): PcgScalars::pad stays 0 and the streaming kernel runs
+    // too many tiles to hold (or nothing to do): PcgScalars::pad stays 0 and the next kernel in line runs
+    if (count <= 0) return;
+    if (!PAGED && count > RES_TPC * static_cast<int>(gridDim.x)) return;
+    if (PAGED && (count <= RES_TPC * static_cast<int>(gridDim.x) || count > RES_PAGED_TPC * static_cast<int>(gridDim.x) ||
+                  static_cast<long long>(count) * PTILE_PAD > g.a.N))
+        return;
     if (blockIdx.x >= P) return;
     const bool scribe = blockIdx.x == 0 && tid == 0;
     if (scribe)
     {
-        sc->pad = 1;  // tells the streaming kernel and pcgFinalizeKernel that this solve is done here
+        sc->pad = PAGED ? 2 : 1;  // tells the streaming kernel and pcgFinalizeKernel that this solve is done here
         if (MG)
         {
             // which tiles of my first / last tile row are walked (one bit per tile column; more than 64 columns: no LL)
@@ -1796,6 +1825,12 @@ template <bool MG> __global__ void __launch_bounds__(RNT, 1) pcgResidentKernel(S
     if (tid < 8) sm.preTbl[tid] = g.a.pre[tid];
     if (tid == 0)
     {
+        if (PAGED)
+        {
+            mbarInit(&sm.full[0], 1);
+            mbarInit(&sm.full[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
         double s0 = 0.0, m0 = 0.0;
         sm.ok = mgCollect(mg, 0, true, &s0, &m0) ? 1 : 0;  // phase 0: rhs.rhs and max|rhs| from pcgInitKernel<true>
         sm.bc[0] = s0;
@@ -1842,20 +1877,26 @@ template <bool MG> __global__ void __launch_bounds__(RNT, 1) pcgResidentKernel(S
     }
     const int I = g.a.I;
     const long long J = g.a.J, N = g.a.N;
-    const int myTiles = (count - static_cast<int>(blockIdx.x) + static_cast<int>(P) - 1) / static_cast<int>(P);
+    const int allTiles = (count - static_cast<int>(blockIdx.x) + static_cast<int>(P) - 1) / static_cast<int>(P);
+    const int myTiles = min(allTiles, RES);              // resident tiles: list entries blockIdx.x + t * P, t < myTiles
+    const int nPaged = PAGED ? allTiles - myTiles : 0;   // paged tiles: list entries blockIdx.x + (RES + k) * P
     const int lr = tid >> 7, lc = tid & (TC - 1);  // this thread's interior cells of a tile: rows lr + 4k, column lc
+    double *const scratch0 = sm.t[RES_TPC - 1].S, *const scratch1 = sm.t[RES_TPC - 1].R;  // PAGED only
+    double *const boxS = g.s[0], *const boxR = g.r[0];                                    // PAGED only: private boxes of the paged tiles
+    unsigned int use0 = 0, use1 = 0;  // completed uses of the two scratch boxes (mbarrier parity)
+    int pb = 0;                       // scratch box the next paged tile arrives in
 
     // ---- per-tile constants in registers: origin, ring cell, operator bytes of the thread's cells
-    int ti0[RES_TPC], tj0[RES_TPC], ringPos[RES_TPC];
-    int ringSrc[RES_TPC];                      // 0: the local q / z array, 1 / 2: LL halo row from the lower / upper neighbour
-    long long ringN[RES_TPC];
-    unsigned int rowBits[RES_TPC];             // 4 x rowInfo byte
-    unsigned int validBits[RES_TPC];           // bit k: cell k of this thread lies inside the matrix
-    unsigned long long preBits[RES_TPC];       // 4 x preInfo half-word
-    double xacc[RES_TPC][RES_CELLS];
+    int ti0[RES], tj0[RES], ringPos[RES];
+    int ringSrc[RES];                      // 0: the local q / z array, 1 / 2: LL halo row from the lower / upper neighbour
+    long long ringN[RES];
+    unsigned int rowBits[RES];             // 4 x rowInfo byte
+    unsigned int validBits[RES];           // bit k: cell k of this thread lies inside the matrix
+    unsigned long long preBits[RES];       // 4 x preInfo half-word
+    double xacc[RES][RES_CELLS];
     bool remote = false;                       // (uniform over the CTA) a tile holds a slab-boundary row pushed to a neighbour
 #pragma unroll
-    for (int t = 0; t < RES_TPC; t++)
+    for (int t = 0; t < RES; t++)
     {
         ti0[t] = tj0[t] = 0;
         ringPos[t] = -1;
@@ -1923,7 +1964,43 @@ template <bool MG> __global__ void __launch_bounds__(RNT, 1) pcgResidentKernel(S
             }
         }
     }
+    if (PAGED)
+    {
+        // private boxes of the paged tiles: s = 0, r = rhs on the halo-extended tile (as above), written with ordinary
+        // stores and read by bulk copies from here on
+        for (int k = 0; k < nPaged; k++)
+        {
+            const long long a = static_cast<long long>(blockIdx.x) + static_cast<long long>(RES + k) * P;
+            const int tile = g.a.activeTiles[a];
+            const int ti = tile / g.a.tilesJ, tj = tile - ti * g.a.tilesJ;
+            for (int e = tid; e < PTILE_PAD; e += RNT)
+            {
+                const int ar = e / PSW, c = e - ar * PSW;
+                const long long gi = static_cast<long long>(ti) * TR - 1 + ar, gj = static_cast<long long>(tj) * TC - 2 + c;
+                double v = 0.0;
+                if (e < PTILE && gi >= 0 && gi < I && gj >= -1 && gj <= J)
+                {
+                    const long long n = gi * J + gj;
+                    if (n >= 0 && n < N) v = g.z[n];
+                }
+                __stcg(boxS + a * PTILE_PAD + e, 0.0);
+                __stcg(boxR + a * PTILE_PAD + e, v);
+            }
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");
+    }
     __syncthreads();
+    bool inFlight = false;  // a box is on its way into scratch `pb` (uniform over the CTA)
+    if (PAGED && nPaged > 0)
+    {
+        if (tid == 0)
+        {
+            asm volatile("fence.proxy.async;" ::: "memory");
+            mbarArriveExpectTx(&sm.full[0], RES_BOX_BYTES);
+            bulkLoad(scratch0, boxS + (static_cast<long long>(blockIdx.x) + static_cast<long long>(RES) * P) * PTILE_PAD, RES_BOX_BYTES, &sm.full[0]);
+        }
+        inFlight = true;
+    }
 
     unsigned int bar = 0;
     double alpha = 0.0, beta = 0.0, alphaPrev = 0.0, gamma = 0.0, err = 0.0;
@@ -1933,9 +2010,10 @@ template <bool MG> __global__ void __launch_bounds__(RNT, 1) pcgResidentKernel(S
     {
         // ---- K1(i): s = z + beta s (interior from T, ring from the neighbours' z); x += alpha_{i-1} s_{i-1}; q = A s; gamma = q.s
         double accDot = 0.0, accMax = 0.0, unused = 0.0;
-        double ringV[RES_TPC];
+        if (scribe) mgStampAt(mg, 2 * i + 1, 0);
+        double ringV[RES];
 #pragma unroll
-        for (int t = 0; t < RES_TPC; t++)
+        for (int t = 0; t < RES; t++)
         {
             ringV[t] = 0.0;
             if (t < myTiles && ringN[t] >= 0)
@@ -1948,7 +2026,7 @@ template <bool MG> __global__ void __launch_bounds__(RNT, 1) pcgResidentKernel(S
             }
         }
 #pragma unroll
-        for (int t = 0; t < RES_TPC; t++)
+        for (int t = 0; t < RES; t++)
             if (t < myTiles)
             {
                 ResTile &rt = sm.t[t];
@@ -1967,7 +2045,7 @@ template <bool MG> __global__ void __launch_bounds__(RNT, 1) pcgResidentKernel(S
             }
         __syncthreads();
 #pragma unroll
-        for (int t = 0; t < RES_TPC; t++)
+        for (int t = 0; t < RES; t++)
             if (t < myTiles)
             {
                 ResTile &rt = sm.t[t];
@@ -2006,7 +2084,94 @@ template <bool MG> __global__ void __launch_bounds__(RNT, 1) pcgResidentKernel(S
                     }
                 }
             }
+        if (scribe) mgStampAt(mg, 2 * i + 1, 1);
+        if (PAGED)
+        {
+            for (int k = 0; k < nPaged; k++)
+            {
+                const long long a = static_cast<long long>(blockIdx.x) + static_cast<long long>(RES + k) * P;
+                const int tile = g.a.activeTiles[a];
+                const int ti = tile / g.a.tilesJ, tj = tile - ti * g.a.tilesJ;
+                const int i0 = ti * TR, j0 = tj * TC;
+                double *box = pb ? scratch1 : scratch0;
+                // operands from global memory: z and x of the thread's cells, the ring value of the neighbours' z
+                double zv[RES_CELLS], xv[RES_CELLS];
+                unsigned int rb = 0;
+#pragma unroll
+                for (int c = 0; c < RES_CELLS; c++)
+                {
+                    const long long gi = i0 + lr + 4 * c, gj = j0 + lc;
+                    zv[c] = xv[c] = 0.0;
+                    if (gi < I && gj < J)
+                    {
+                        const long long n = gi * J + gj;
+                        zv[c] = __ldcg(g.z + n);
+                        xv[c] = __ldcg(g.x + n);
+                        rb |= static_cast<unsigned int>(g.a.rowInfo[n]) << (8 * c);
+                    }
+                }
+                int rpos;
+                long long rn;
+                resRingCell(tid, i0, j0, I, J, N, &rpos, &rn);
+                const double rv = rn >= 0 ? __ldcg(g.z + rn) : 0.0;
+                if (tid == 0 && k + 1 < nPaged)
+                {
+                    // the next paged tile's box flies into the other scratch while this one is worked on; that scratch
+                    // was the source of the previous tile's write-back
+                    bulkWaitRead0();
+                    mbarArriveExpectTx(&sm.full[pb ^ 1], RES_BOX_BYTES);
+                    bulkLoad(pb ? scratch0 : scratch1, boxS + (a + P) * PTILE_PAD, RES_BOX_BYTES, &sm.full[pb ^ 1]);
+                }
+                mbarWait(&sm.full[pb], (pb ? use1 : use0) & 1u);
+                if (pb) use1++; else use0++;
+#pragma unroll
+                for (int c = 0; c < RES_CELLS; c++)
+                {
+                    const long long gi = i0 + lr + 4 * c, gj = j0 + lc;
+                    if (gi < I && gj < J)
+                    {
+                        const int q = (lr + 4 * c + 1) * PSW + lc + 2;
+                        const double so = box[q];
+                        box[q] = __dadd_rn(zv[c], __dmul_rn(so, beta));
+                        g.x[gi * J + gj] = __dadd_rn(xv[c], __dmul_rn(so, alphaPrev));
+                    }
+                }
+                if (rpos >= 0) box[rpos] = __dadd_rn(rv, __dmul_rn(box[rpos], beta));
+                __syncthreads();
+#pragma unroll
+                for (int c = 0; c < RES_CELLS; c++)
+                {
+                    const long long gi = i0 + lr + 4 * c, gj = j0 + lc;
+                    if (gi < I && gj < J)
+                    {
+                        const int q = (lr + 4 * c + 1) * PSW + lc + 2;
+                        const double cv = box[q];
+                        const double o = rowA(static_cast<uint8_t>(rb >> (8 * c)), g.a.scale, cv, box[q - PSW], box[q + PSW], box[q - 1], box[q + 1]);
+                        g.q[gi * J + gj] = o;
+                        accDot += o * cv;
+                    }
+                }
+                fenceProxyAsync();
+                __syncthreads();
+                if (tid == 0) bulkStore(boxS + a * PTILE_PAD, box, RES_BOX_BYTES);
+                pb ^= 1;
+            }
+            if (nPaged > 0)
+            {
+                // the r box of the first paged tile, for K2(i), travels during the barrier
+                if (tid == 0)
+                {
+                    bulkWaitAllButLast();
+                    mbarArriveExpectTx(&sm.full[pb], RES_BOX_BYTES);
+                    bulkLoad(pb ? scratch1 : scratch0, boxR + (static_cast<long long>(blockIdx.x) + static_cast<long long>(RES) * P) * PTILE_PAD,
+                             RES_BOX_BYTES, &sm.full[pb]);
+                }
+                inFlight = true;
+            }
+        }
+        if (scribe) mgStampAt(mg, 2 * i + 1, 2);
         if (!resBarrier<MG>(g, mg, 2 * i + 1, bar++, P, accDot, 0.0, sm, &gamma, &unused, remote)) break;
+        if (scribe) mgStampAt(mg, 2 * i + 1, 3);
         alpha = sigma / (gamma + 1e-8);  // linearsolver.cpp:50
         if (scribe)
         {
@@ -2016,8 +2181,9 @@ template <bool MG> __global__ void __launch_bounds__(RNT, 1) pcgResidentKernel(S
         }
         // ---- K2(i): r -= alpha q (interior from T, ring from the neighbours' q); z = M r; sigma' = z.r; err = max|r|
         accDot = 0.0;
+        if (scribe) mgStampAt(mg, 2 * i + 2, 0);
 #pragma unroll
-        for (int t = 0; t < RES_TPC; t++)
+        for (int t = 0; t < RES; t++)
         {
             ringV[t] = 0.0;
             if (t < myTiles && ringN[t] >= 0)
@@ -2029,7 +2195,7 @@ template <bool MG> __global__ void __launch_bounds__(RNT, 1) pcgResidentKernel(S
             }
         }
 #pragma unroll
-        for (int t = 0; t < RES_TPC; t++)
+        for (int t = 0; t < RES; t++)
             if (t < myTiles)
             {
                 ResTile &rt = sm.t[t];
@@ -2044,7 +2210,7 @@ template <bool MG> __global__ void __launch_bounds__(RNT, 1) pcgResidentKernel(S
             }
         __syncthreads();
 #pragma unroll
-        for (int t = 0; t < RES_TPC; t++)
+        for (int t = 0; t < RES; t++)
             if (t < myTiles)
             {
                 ResTile &rt = sm.t[t];
@@ -2082,8 +2248,90 @@ template <bool MG> __global__ void __launch_bounds__(RNT, 1) pcgResidentKernel(S
                     }
                 }
             }
+        if (scribe) mgStampAt(mg, 2 * i + 2, 1);
+        if (PAGED)
+        {
+            for (int k = 0; k < nPaged; k++)
+            {
+                const long long a = static_cast<long long>(blockIdx.x) + static_cast<long long>(RES + k) * P;
+                const int tile = g.a.activeTiles[a];
+                const int ti = tile / g.a.tilesJ, tj = tile - ti * g.a.tilesJ;
+                const int i0 = ti * TR, j0 = tj * TC;
+                double *box = pb ? scratch1 : scratch0;
+                double qv[RES_CELLS];
+                unsigned long long pbits = 0;
+#pragma unroll
+                for (int c = 0; c < RES_CELLS; c++)
+                {
+                    const long long gi = i0 + lr + 4 * c, gj = j0 + lc;
+                    qv[c] = 0.0;
+                    if (gi < I && gj < J)
+                    {
+                        const long long n = gi * J + gj;
+                        qv[c] = __ldcg(g.q + n);
+                        pbits |= static_cast<unsigned long long>(g.a.preInfo[n]) << (16 * c);
+                    }
+                }
+                int rpos;
+                long long rn;
+                resRingCell(tid, i0, j0, I, J, N, &rpos, &rn);
+                const double rv = rn >= 0 ? __ldcg(g.q + rn) : 0.0;
+                if (tid == 0 && k + 1 < nPaged)
+                {
+                    bulkWaitRead0();
+                    mbarArriveExpectTx(&sm.full[pb ^ 1], RES_BOX_BYTES);
+                    bulkLoad(pb ? scratch0 : scratch1, boxR + (a + P) * PTILE_PAD, RES_BOX_BYTES, &sm.full[pb ^ 1]);
+                }
+                mbarWait(&sm.full[pb], (pb ? use1 : use0) & 1u);
+                if (pb) use1++; else use0++;
+#pragma unroll
+                for (int c = 0; c < RES_CELLS; c++)
+                {
+                    const long long gi = i0 + lr + 4 * c, gj = j0 + lc;
+                    if (gi < I && gj < J)
+                    {
+                        const int q = (lr + 4 * c + 1) * PSW + lc + 2;
+                        box[q] = __dsub_rn(box[q], __dmul_rn(qv[c], alpha));
+                    }
+                }
+                if (rpos >= 0) box[rpos] = __dsub_rn(box[rpos], __dmul_rn(rv, alpha));
+                __syncthreads();
+#pragma unroll
+                for (int c = 0; c < RES_CELLS; c++)
+                {
+                    const long long gi = i0 + lr + 4 * c, gj = j0 + lc;
+                    if (gi < I && gj < J)
+                    {
+                        const int q = (lr + 4 * c + 1) * PSW + lc + 2;
+                        const double cv = box[q];
+                        const double o = rowM(static_cast<uint16_t>(pbits >> (16 * c)), sm.preTbl, cv, box[q - PSW], box[q + PSW], box[q - 1], box[q + 1]);
+                        g.z[gi * J + gj] = o;
+                        accDot += o * cv;
+                        accMax = fmax(accMax, fabs(cv));
+                    }
+                }
+                fenceProxyAsync();
+                __syncthreads();
+                if (tid == 0) bulkStore(boxR + a * PTILE_PAD, box, RES_BOX_BYTES);
+                pb ^= 1;
+            }
+            if (nPaged > 0)
+            {
+                // the s box of the first paged tile, for K1(i + 1) (drained after the loop if there is none)
+                if (tid == 0)
+                {
+                    bulkWaitAllButLast();
+                    mbarArriveExpectTx(&sm.full[pb], RES_BOX_BYTES);
+                    bulkLoad(pb ? scratch1 : scratch0, boxS + (static_cast<long long>(blockIdx.x) + static_cast<long long>(RES) * P) * PTILE_PAD,
+                             RES_BOX_BYTES, &sm.full[pb]);
+                }
+                inFlight = true;
+            }
+        }
         double sigmaNew = 0.0;
+        if (scribe) mgStampAt(mg, 2 * i + 2, 2);
         if (!resBarrier<MG>(g, mg, 2 * i + 2, bar++, P, accDot, accMax, sm, &sigmaNew, &err, remote)) break;
+        if (scribe) mgStampAt(mg, 2 * i + 2, 3);
         executed = i + 1;
         const bool converged = err <= g.a.tol;                      // linearsolver.cpp:59-61
         const double betaNew = converged ? 0.0 : sigmaNew / sigma;  // :66-67
@@ -2109,9 +2357,35 @@ template <bool MG> __global__ void __launch_bounds__(RNT, 1) pcgResidentKernel(S
         sigma = sigmaNew;
         alphaPrev = alpha;
     }
+    if (PAGED && nPaged > 0)
+    {
+        // the box requested for a phase that never came lands before the CTA gives its shared memory back; all write-backs
+        // complete; then the pending alpha * s of the paged tiles, from their private s boxes
+        if (inFlight) mbarWait(&sm.full[pb], (pb ? use1 : use0) & 1u);
+        if (tid == 0) bulkWaitAll();
+        __syncthreads();
+        asm volatile("fence.proxy.async;" ::: "memory");
+        if (executed > 0)
+            for (int k = 0; k < nPaged; k++)
+            {
+                const long long a = static_cast<long long>(blockIdx.x) + static_cast<long long>(RES + k) * P;
+                const int tile = g.a.activeTiles[a];
+                const int ti = tile / g.a.tilesJ, tj = tile - ti * g.a.tilesJ;
+#pragma unroll
+                for (int c = 0; c < RES_CELLS; c++)
+                {
+                    const long long gi = static_cast<long long>(ti) * TR + lr + 4 * c, gj = static_cast<long long>(tj) * TC + lc;
+                    if (gi < I && gj < J)
+                    {
+                        const double sv = __ldcg(boxS + a * PTILE_PAD + (lr + 4 * c + 1) * PSW + lc + 2);
+                        g.x[gi * J + gj] = __dadd_rn(__ldcg(g.x + gi * J + gj), __dmul_rn(sv, alpha));
+                    }
+                }
+            }
+    }
     // ---- x = accumulated steps + the pending alpha * s of the last executed iteration (linearsolver.cpp:51)
 #pragma unroll
-    for (int t = 0; t < RES_TPC; t++)
+    for (int t = 0; t < RES; t++)
         if (t < myTiles)
         {
             ResTile &rt = sm.t[t];
@@ -2469,8 +2743,9 @@ void pcgPreloadSlabKernels()
     cudaFuncGetAttributes(&at, pcgMgCloseKernel);
     cudaFuncGetAttributes(&at, pcgSolveKernel<true>);
     cudaFuncGetAttributes(&at, pcgSolveKernel<false>);
-    cudaFuncGetAttributes(&at, pcgResidentKernel<true>);
-    cudaFuncGetAttributes(&at, pcgResidentKernel<false>);
+    cudaFuncGetAttributes(&at, pcgResidentKernel<true, false>);
+    cudaFuncGetAttributes(&at, pcgResidentKernel<false, false>);
+    cudaFuncGetAttributes(&at, pcgResidentKernel<false, true>);
     cudaFuncGetAttributes(&at, pcgFinalizeKernel);
     cudaFuncGetAttributes(&at, pcgTileFlagKernel);
     cudaFuncGetAttributes(&at, pcgTileCompactKernel);
@@ -2530,8 +2805,9 @@ static void pcgKernelAttributes(int device)
     cudaFuncSetAttribute(pcgPipeKernel<MODE_K2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ceiling);
     cudaFuncSetAttribute(pcgSolveKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ceiling);
     cudaFuncSetAttribute(pcgSolveKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ceiling);
-    cudaFuncSetAttribute(pcgResidentKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(ResSmem)));
-    cudaFuncSetAttribute(pcgResidentKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(ResSmem)));
+    cudaFuncSetAttribute(pcgResidentKernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(ResSmem)));
+    cudaFuncSetAttribute(pcgResidentKernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(ResSmem)));
+    cudaFuncSetAttribute(pcgResidentKernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(ResSmem)));
     cudaGetLastError();
     done |= 1ull << device;
 }
@@ -2751,11 +3027,11 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
             cudaError_t re;
             if (mgOn)
             {
-                re = cudaLaunchCooperativeKernel(reinterpret_cast<void *>(pcgResidentKernel<true>), dim3(resBlocks), dim3(RNT), rargs, rsmem, st);
+                re = cudaLaunchCooperativeKernel(reinterpret_cast<void *>(pcgResidentKernel<true, false>), dim3(resBlocks), dim3(RNT), rargs, rsmem, st);
             }
             else
             {
-                re = cudaLaunchCooperativeKernel(reinterpret_cast<void *>(pcgResidentKernel<false>), dim3(resBlocks), dim3(RNT), rargs, rsmem, st);
+                re = cudaLaunchCooperativeKernel(reinterpret_cast<void *>(pcgResidentKernel<false, false>), dim3(resBlocks), dim3(RNT), rargs, rsmem, st);
             }
             if (re == cudaErrorCooperativeLaunchTooLarge)
                 cudaGetLastError();  // the device is shared: the streaming kernel (or its stepwise fallback) takes the solve
@@ -2763,6 +3039,19 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
             {
                 FS2D_CUDA(re);
                 ctx->launches++;
+                if (!mgOn && ctx->pagedPcg)
+                {
+                    // more tiles than the SMs hold, but not many more (4096^2 dam break): resident + paged tiles; returns
+                    // at once when the resident kernel took the solve or when the list is too long
+                    re = cudaLaunchCooperativeKernel(reinterpret_cast<void *>(pcgResidentKernel<false, true>), dim3(resBlocks), dim3(RNT), rargs, rsmem, st);
+                    if (re == cudaErrorCooperativeLaunchTooLarge)
+                        cudaGetLastError();
+                    else
+                    {
+                        FS2D_CUDA(re);
+                        ctx->launches++;
+                    }
+                }
             }
         }
         void *args[] = {&g, &mg, &maps, &useTensor};

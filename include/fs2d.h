@@ -236,9 +236,13 @@ int fs2d_pcg_profile_solves(fs2d_handle h, double *ms, int64_t *solves);
 int fs2d_pcg_set_grid_limit(fs2d_handle h, int max_ctas);
 /* Active-tile solves whose tiles fit the shared memory of the SMs (<= 4 tiles of 16x128 per SM) run in
  * pcgResidentKernel: s, r and the inter-phase vector stay in shared memory for the whole solve, x in registers, only
- * halo values cross L2. fs2d_pcg_set_resident(h, 0) forces the streaming kernel (A/B switch; env FS2D_PCG_RESIDENT=0).
- * Same iterates up to the grouping of the dot-product partials. */
+ * halo values cross L2. With up to 12 tiles per SM (one GPU) the same kernel keeps 3 tiles per SM resident and pages the
+ * private boxes of the others through two shared-memory scratch boxes with bulk copies. fs2d_pcg_set_resident(h, 0)
+ * forces the streaming kernel, 2 = resident kernel without paging (A/B switches; env FS2D_PCG_RESIDENT=0,
+ * FS2D_PCG_PAGED=0). Same iterates up to the grouping of the dot-product partials. fs2d_pcg_last_kernel: which kernel
+ * ran the last whole solve (0 streaming, 1 resident, 2 resident + paged; synchronises the stream). */
 int fs2d_pcg_set_resident(fs2d_handle h, int resident);
+int fs2d_pcg_last_kernel(fs2d_handle h, int *kind);
 int fs2d_pcg_set_tile_kernels(fs2d_handle h, int tile);
 /* Measurement aid for the particle / grid transfer kernels: with profiling enabled every call of a kernel group is
  * bracketed by CUDA events on the handle's stream; fs2d_kernel_profile_read returns, per group, the accumulated device

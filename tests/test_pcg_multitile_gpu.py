@@ -142,6 +142,59 @@ def test_shrunk_grid_converging_solve_and_zero_rhs(sys256):
     del scene, s2
 
 
+@pytest.mark.parametrize("per_cta", [5, 7, 11])
+def test_paged_resident_tiles(sys256, per_cta):
+    """More active tiles than the CTAs hold resident (4 each), up to 12 per CTA: pcgResidentKernel<PAGED> keeps 3 tiles in
+    shared memory and pages the private boxes of the others through two scratch boxes with bulk copies (the 4096^2 dam
+    break on one GPU: 904 tiles for 148 SMs). per_cta 5 -> 3 resident + 2 paged (one box prefetched across every phase
+    boundary), 7 -> + 4 paged (double-buffered inside a phase, even count), 11 -> + 8."""
+    s, d = sys256
+    rhs, unit = _rhs(s, 300 + per_cta)
+    iters = 30
+    xr, _ = s.pcg(rhs, iters, 0.0)
+    d.pcg_set_dense(False)
+    d.pcg_set_resident(False)
+    xw, nw = d.pcg_solve(rhs, iters, 0.0)
+    trw = d.pcg_trace().copy()
+    assert d.pcg_last_kernel() == 0
+    tiles = d.pcg_active_cells() // (16 * 128)
+    limit = -(-tiles // per_cta)
+    assert 4 * limit < tiles <= 12 * limit, (tiles, limit)
+    d.pcg_set_grid_limit(limit)
+    try:
+        d.pcg_set_resident(True)
+        xp, n = d.pcg_solve(rhs, iters, 0.0)
+        trp = d.pcg_trace().copy()
+        assert d.pcg_last_kernel() == 2
+        d.pcg_set_resident(2)  # no paging: the list does not fit, the streaming kernel takes it
+        x2, n2 = d.pcg_solve(rhs, iters, 0.0)
+        assert d.pcg_last_kernel() == 0
+        d.pcg_set_resident(True)
+        assert n == n2 == nw == iters
+        assert H.rel_l2(xp, xr) < TOL, H.rel_l2(xp, xr)
+        assert H.rel_l2(xp, xw) < 1e-11
+        assert np.allclose(trp[:iters], trw[:iters], rtol=1e-9, atol=0)
+        assert not xp[~unit & (rhs == 0)].any()
+        # run to run: bit-identical
+        xq, _ = d.pcg_solve(rhs, iters, 0.0)
+        assert np.array_equal(xq, xp)
+        # convergence exit with a prefetched box in flight, zero rhs, reuse
+        tol = float(trp[12, 3]) * 1.0000001
+        first = int(np.argmax(trp[:, 3] <= tol))
+        xc, nc = d.pcg_solve(rhs, iters, tol)
+        assert nc == first and d.pcg_last_kernel() == 2
+        xrc, nrc = s.pcg(rhs, first + 1, 0.0)
+        assert H.rel_l2(xc, xrc) < TOL
+        x0, n0 = d.pcg_solve(np.zeros(s.N), iters, 0.0)
+        assert n0 == 0 and not x0.any()
+        x1, n1 = d.pcg_solve(rhs, 1, 0.0)
+        xr1, _ = s.pcg(rhs, 1, 0.0)
+        assert n1 == 1 and H.rel_l2(x1, xr1) < TOL
+    finally:
+        d.pcg_set_grid_limit(0)
+        d.pcg_set_resident(True)
+
+
 @pytest.fixture(scope="module")
 def sys1024(ref_mod, scene_dir):
     scene = scenes.dam_break(1024, "flip")
@@ -190,6 +243,14 @@ def test_flip_1024_against_reference(sys1024, limit):
             xres, nres = d.pcg_solve(rhs, iters, 0.0)
             assert nres == iters and H.rel_l2(xres, xr) < TOL, H.rel_l2(xres, xr)
             assert H.rel_l2(xres, xw) < 1e-11
+    if limit:
+        # ~60 active tiles over 10 CTAs: 3 resident + 3 paged tiles each
+        d.pcg_set_dense(False)
+        d.pcg_set_grid_limit(10)
+        xpg, npg = d.pcg_solve(rhs, iters, 0.0)
+        assert d.pcg_last_kernel() == 2, (d.pcg_last_kernel(), d.pcg_active_cells() // 2048)
+        assert npg == iters and H.rel_l2(xpg, xr) < TOL and H.rel_l2(xpg, xw) < 1e-11
+        d.pcg_set_grid_limit(limit)
     # the real right-hand side of the scene (hydrostatic column at rest): body forces, then calcPressureRhs
     s.stage("BODY_FORCES")
     rhs2 = s.pressure_rhs()
