@@ -150,6 +150,9 @@ def lib():
         "fs2d_pcg_set_tile_kernels": (i32, [H, i32]),
         "fs2d_pcg_set_resident": (i32, [H, i32]),
         "fs2d_pcg_last_kernel": (i32, [H, C.POINTER(C.c_int)]),
+        "fs2d_state_bytes": (i32, [H, C.POINTER(C.c_size_t)]),
+        "fs2d_state_save": (i32, [H, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+        "fs2d_state_load": (i32, [H, vp, C.c_size_t]),
         "fs2d_kernel_profile": (i32, [H, i32]),
         "fs2d_kernel_profile_read": (i32, [H, vp, vp]),
         "fs2d_slab_configure": (i32, [H, i32, i32, i32]),
@@ -357,6 +360,19 @@ class Device:
     def pcg_set_resident(self, resident=True):
         """True / 1: resident kernel, paged tiles allowed; 2: resident kernel without paging; False / 0: streaming kernel."""
         self._ck(self.L.fs2d_pcg_set_resident(self.h, int(resident)), "pcg_set_resident")
+
+    def state_save(self):
+        """The whole device state (grids + particle records) as one uint8 array (fs2d_state_save)."""
+        n = C.c_size_t(0)
+        self._ck(self.L.fs2d_state_bytes(self.h, C.byref(n)), "state_bytes")
+        buf = np.zeros(n.value + 64, np.uint8)
+        w = C.c_size_t(0)
+        self._ck(self.L.fs2d_state_save(self.h, _p(buf), buf.nbytes, C.byref(w)), "state_save")
+        return buf[: w.value]
+
+    def state_load(self, blob):
+        blob = np.ascontiguousarray(blob, np.uint8)
+        self._ck(self.L.fs2d_state_load(self.h, _p(blob), blob.nbytes), "state_load")
 
     def pcg_last_kernel(self):
         """0 = streaming whole-solve kernel (or stepwise), 1 = resident, 2 = resident + paged tiles."""

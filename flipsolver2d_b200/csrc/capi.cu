@@ -838,6 +838,130 @@ int fs2d_download_matrix(fs2d_handle ctx, uint8_t *host_is_unit, uint8_t *host_m
 }
 
 // ---------------------------------------------------------------- stages
+// ---- state dump / restore ("a state dump/restore that doubles as checkpoint"; the reference has none,
+// its viewer reads the live solver object: Liquid2dRender/fluidrenderer.cpp:497-986)
+namespace
+{
+struct StateHeader
+{
+    uint32_t magic, version;
+    int32_t I, J, simType, numProperties;
+    int64_t records;          // particle records (flagged-dead ones included, see fs2d_download_particles_packed)
+    uint64_t gridMask;        // bit g: grid g of the FS2D_GRID_* table follows
+    float stepDt;
+    int32_t flags;            // bit 0 sdfInsidePending, bit 1 smokeGridsAdvected
+    double matrixScale;
+    uint64_t reserved[4];
+};
+constexpr uint32_t STATE_MAGIC = 0x44325346u;  // "FS2D"
+size_t stateGridBytes(Ctx *ctx, uint64_t *mask)
+{
+    size_t total = 0;
+    uint64_t m = 0;
+    for (int g = 0; g < FS2D_GRID_COUNT_; g++)
+    {
+        GridDesc d = gridDesc(ctx, g);
+        if (!d.ptr || !*d.ptr) continue;
+        m |= 1ull << g;
+        total += (static_cast<size_t>(d.count) * d.elemSize + 15) & ~static_cast<size_t>(15);
+    }
+    if (mask) *mask = m;
+    return total;
+}
+}  // namespace
+
+int fs2d_state_bytes(fs2d_handle ctx, size_t *bytes)
+{
+    if (!ctx || !bytes) return FS2D_ERR_ARG;
+    *bytes = sizeof(StateHeader) + stateGridBytes(ctx, nullptr) + fs2d_packed_particle_bytes(ctx, ctx->count);
+    return FS2D_OK;
+}
+
+int fs2d_state_save(fs2d_handle ctx, void *host_buf, size_t capacity_bytes, size_t *written)
+{
+    if (!ctx || !host_buf || !written) return FS2D_ERR_ARG;
+    if (ctx->slab.enabled && ctx->slab.world > 1)
+    {
+        ctx->lastError = "fs2d_state_save: not available over row slabs";
+        return FS2D_ERR_STATE;
+    }
+    size_t need = 0;
+    FS2D_TRY(fs2d_state_bytes(ctx, &need));
+    if (need > capacity_bytes)
+    {
+        ctx->lastError = "fs2d_state_save: buffer too small";
+        return FS2D_ERR_ARG;
+    }
+    StateHeader h;
+    memset(&h, 0, sizeof(h));
+    h.magic = STATE_MAGIC;
+    h.version = 1;
+    h.I = ctx->I;
+    h.J = ctx->J;
+    h.simType = ctx->p.sim_type;
+    h.numProperties = ctx->p.num_properties;
+    h.stepDt = ctx->stepDt;
+    h.flags = (ctx->sdfInsidePending ? 1 : 0) | (ctx->smokeGridsAdvected ? 2 : 0);
+    h.matrixScale = ctx->matrixScale;
+    stateGridBytes(ctx, &h.gridMask);
+    unsigned char *out = static_cast<unsigned char *>(host_buf) + sizeof(StateHeader);
+    FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int g = 0; g < FS2D_GRID_COUNT_; g++)
+    {
+        if (!((h.gridMask >> g) & 1ull)) continue;
+        GridDesc d = gridDesc(ctx, g);
+        const size_t bytes = static_cast<size_t>(d.count) * d.elemSize;
+        // the arrays as they are: a deferred level-set walk stays deferred (flag above)
+        FS2D_CUDA(cudaMemcpyAsync(out, *d.ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        out += (bytes + 15) & ~static_cast<size_t>(15);
+    }
+    FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
+    int64_t records = 0;
+    FS2D_TRY(fs2d_download_particles_packed(ctx, out, capacity_bytes - static_cast<size_t>(out - static_cast<unsigned char *>(host_buf)), &records));
+    h.records = records;
+    out += fs2d_packed_particle_bytes(ctx, records);
+    memcpy(host_buf, &h, sizeof(h));
+    *written = static_cast<size_t>(out - static_cast<unsigned char *>(host_buf));
+    return FS2D_OK;
+}
+
+int fs2d_state_load(fs2d_handle ctx, const void *host_buf, size_t bytes)
+{
+    if (!ctx || !host_buf || bytes < sizeof(StateHeader)) return FS2D_ERR_ARG;
+    if (ctx->slab.enabled && ctx->slab.world > 1)
+    {
+        ctx->lastError = "fs2d_state_load: not available over row slabs";
+        return FS2D_ERR_STATE;
+    }
+    StateHeader h;
+    memcpy(&h, host_buf, sizeof(h));
+    uint64_t mask = 0;
+    const size_t gridBytes = stateGridBytes(ctx, &mask);
+    if (h.magic != STATE_MAGIC || h.version != 1 || h.I != ctx->I || h.J != ctx->J || h.simType != ctx->p.sim_type ||
+        h.numProperties != ctx->p.num_properties || h.gridMask != mask || h.records < 0 ||
+        bytes < sizeof(StateHeader) + gridBytes + fs2d_packed_particle_bytes(ctx, h.records))
+    {
+        ctx->lastError = "fs2d_state_load: the blob was not written by a handle with these parameters";
+        return FS2D_ERR_ARG;
+    }
+    const unsigned char *in = static_cast<const unsigned char *>(host_buf) + sizeof(StateHeader);
+    for (int g = 0; g < FS2D_GRID_COUNT_; g++)
+    {
+        if (!((mask >> g) & 1ull)) continue;
+        GridDesc d = gridDesc(ctx, g);
+        const size_t gb = static_cast<size_t>(d.count) * d.elemSize;
+        FS2D_CUDA(cudaMemcpyAsync(*d.ptr, in, gb, cudaMemcpyHostToDevice, ctx->stream));
+        in += (gb + 15) & ~static_cast<size_t>(15);
+    }
+    FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
+    FS2D_TRY(fs2d_upload_particles_packed(ctx, in, h.records));
+    ctx->stepDt = h.stepDt;
+    ctx->matrixScale = h.matrixScale;
+    ctx->sdfInsidePending = (h.flags & 1) != 0;
+    ctx->smokeGridsAdvected = (h.flags & 2) != 0;
+    return FS2D_OK;
+}
+
 int fs2d_set_step_dt(fs2d_handle h, float dt)
 {
     if (!h) return FS2D_ERR_ARG;

@@ -3,8 +3,10 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
 #include <iostream>
 #include <limits>
+#include <sstream>
 #include <stdexcept>
 #include <thread>
 
@@ -270,6 +272,83 @@ bool FlipSolver::stepSubstep()
 void FlipSolver::stepFrame()
 {
     while (!stepSubstep()) {}
+}
+
+// ------------------------------------------------------------------ state dump / restore
+namespace
+{
+struct HostStateHeader
+{
+    char magic[8];  // "FS2DHOST"
+    uint32_t version;
+    int32_t frameNumber, inFrame, substepCount;
+    float substepTime, stepDt;
+    int32_t statSubsteps, pressureIters, densityIters, viscosityIters;
+    float stageMs[SOLVER_STAGE_COUNT];
+    uint64_t rngBytes, deviceBytes;
+};
+}  // namespace
+
+void FlipSolver::saveState(const std::string &path)
+{
+    prepare();
+    size_t need = 0;
+    check(fs2d_state_bytes(device(), &need), "fs2d_state_bytes");
+    std::vector<unsigned char> blob(need + 64);
+    size_t written = 0;
+    check(fs2d_state_save(device(), blob.data(), blob.size(), &written), "fs2d_state_save");
+    std::ostringstream rng;
+    rng << m_randEngine;
+    const std::string rngText = rng.str();
+    HostStateHeader h;
+    std::memset(&h, 0, sizeof(h));
+    std::memcpy(h.magic, "FS2DHOST", 8);
+    h.version = 1;
+    h.frameNumber = m_frameNumber;
+    h.inFrame = m_inFrame ? 1 : 0;
+    h.substepCount = m_substepCount;
+    h.substepTime = m_substepTime;
+    h.stepDt = m_stepDt;
+    h.statSubsteps = m_stats.substepCount();
+    h.pressureIters = m_stats.pressureIterations();
+    h.densityIters = m_stats.densityIterations();
+    h.viscosityIters = m_stats.viscosityIterations();
+    const SolverStats::StageTimings t = m_stats.timings();
+    for (int k = 0; k < SOLVER_STAGE_COUNT; k++) h.stageMs[k] = t[static_cast<size_t>(k)];
+    h.rngBytes = rngText.size();
+    h.deviceBytes = written;
+    std::ofstream f(path, std::ios::binary | std::ios::trunc);
+    f.write(reinterpret_cast<const char *>(&h), sizeof(h));
+    f.write(rngText.data(), static_cast<std::streamsize>(rngText.size()));
+    f.write(reinterpret_cast<const char *>(blob.data()), static_cast<std::streamsize>(written));
+    if (!f) throw std::runtime_error("saveState: cannot write " + path);
+}
+
+void FlipSolver::loadState(const std::string &path)
+{
+    std::ifstream f(path, std::ios::binary);
+    HostStateHeader h;
+    f.read(reinterpret_cast<char *>(&h), sizeof(h));
+    if (!f || std::memcmp(h.magic, "FS2DHOST", 8) != 0 || h.version != 1) throw std::runtime_error("loadState: not a state file: " + path);
+    std::string rngText(h.rngBytes, '\0');
+    f.read(rngText.data(), static_cast<std::streamsize>(h.rngBytes));
+    std::vector<unsigned char> blob(h.deviceBytes);
+    f.read(reinterpret_cast<char *>(blob.data()), static_cast<std::streamsize>(h.deviceBytes));
+    if (!f) throw std::runtime_error("loadState: truncated state file: " + path);
+    prepare();  // device, scene tables (sources, obstacles) and the static grids; everything dynamic is overwritten below
+    check(fs2d_state_load(device(), blob.data(), blob.size()), "fs2d_state_load");
+    std::istringstream rng(rngText);
+    rng >> m_randEngine;
+    m_frameNumber = h.frameNumber;
+    m_prepared = true;
+    m_inFrame = h.inFrame != 0;
+    m_substepCount = h.substepCount;
+    m_substepTime = h.substepTime;
+    m_stepDt = h.stepDt;
+    SolverStats::StageTimings t;
+    for (int k = 0; k < SOLVER_STAGE_COUNT; k++) t[static_cast<size_t>(k)] = h.stageMs[k];
+    m_stats.restore(t, h.statSubsteps, h.pressureIters, h.densityIters, h.viscosityIters);
+    invalidateMirrors();
 }
 
 // ------------------------------------------------------------------ one substep (flipsolver2d.cpp:412-462)

@@ -96,6 +96,16 @@ public:
     }
     void endFrame() { m_total = std::chrono::duration<float, std::milli>(Clock::now() - m_frameStart).count(); }
     void addSubstep() { m_substeps++; }
+    // checkpoint support (FlipSolver::loadState): the counters of the frame in progress
+    void restore(const StageTimings &times, int substeps, int pressureIters, int densityIters, int viscosityIters)
+    {
+        m_times = times;
+        m_substeps = substeps;
+        m_pressureIters = pressureIters;
+        m_densityIters = densityIters;
+        m_viscosityIters = viscosityIters;
+        m_last = Clock::now();
+    }
     int substepCount() const { return m_substeps; }
     StageTimings timings() const { return m_times; }
     float frameTime() const { return m_total; }
@@ -190,6 +200,12 @@ public:
     // pool of T threads (vmath.cpp:100-136), 0 = true max-norm (env FS2D_CONVERGENCE_THREADS).
     static void setConvergenceThreads(int t);
     int64_t kernelLaunches();
+    // State dump / restore, doubling as checkpoint (the reference has no serialisation). saveState writes
+    // the device state (fs2d_state_save: all grids, particle records) plus the host side of the stepping loop: frame
+    // and substep counters, substep time, the mt19937 stream, the stage counters of the frame in progress. loadState on
+    // a solver loaded from the SAME scene continues bit-identically to the uninterrupted run. Single GPU only.
+    void saveState(const std::string &path);
+    void loadState(const std::string &path);
     // Row slabs over several GPUs (include/fs2d.h "row slabs"; the reference's ThreadPool splits the same loops over
     // row ranges, threadpool.cpp:41-76): one process -- one solver -- per GPU, every rank loads the SAME scene.
     // setSlab before the solver touches the device; then exchange the 256-byte blobs (slabExport -> every other

@@ -168,6 +168,18 @@ int fs2dh_step_substep(fs2dh_solver s, int *frame_finished)
     });
 }
 
+int fs2dh_save_state(fs2dh_solver s, const char *path)
+{
+    Holder *h = static_cast<Holder *>(s);
+    return guarded(h, [&]() { h->solver->saveState(path); });
+}
+
+int fs2dh_load_state(fs2dh_solver s, const char *path)
+{
+    Holder *h = static_cast<Holder *>(s);
+    return guarded(h, [&]() { h->solver->loadState(path); });
+}
+
 int fs2dh_get_stats(fs2dh_solver s, float *timings12, float *misc5)
 {
     Holder *h = static_cast<Holder *>(s);

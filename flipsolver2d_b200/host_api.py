@@ -50,6 +50,8 @@ def lib():
         "fs2dh_prepare": (i32, [vp]),
         "fs2dh_step_frame": (i32, [vp]),
         "fs2dh_step_substep": (i32, [vp, C.POINTER(i32)]),
+        "fs2dh_save_state": (i32, [vp, C.c_char_p]),
+        "fs2dh_load_state": (i32, [vp, C.c_char_p]),
         "fs2dh_get_stats": (i32, [vp, vp, vp]),
         "fs2dh_size_i": (i32, [vp]),
         "fs2dh_size_j": (i32, [vp]),
@@ -175,6 +177,13 @@ class Solver:
         done = C.c_int(0)
         self._ck(self.L.fs2dh_step_substep(self.h, C.byref(done)), "step_substep")
         return bool(done.value)
+
+    def save_state(self, path):
+        """FlipSolver::saveState: device grids + particle records + frame / substep counters + mt19937 stream."""
+        self._ck(self.L.fs2dh_save_state(self.h, str(path).encode()), "save_state")
+
+    def load_state(self, path):
+        self._ck(self.L.fs2dh_load_state(self.h, str(path).encode()), "load_state")
 
     def stats(self):
         t = np.zeros(12, np.float32)

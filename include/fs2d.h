@@ -193,6 +193,16 @@ int fs2d_get_particle_storage_bins(fs2d_handle h, int32_t *host_bins);
 size_t fs2d_packed_particle_bytes(fs2d_handle h, int64_t count);
 int fs2d_download_particles_packed(fs2d_handle h, void *host_buf, size_t capacity_bytes, int64_t *count);
 int fs2d_upload_particles_packed(fs2d_handle h, const void *host_buf, int64_t count);
+/* State dump / restore (checkpoint). The reference keeps its state in the solver object and has no serialisation
+ * (its viewer reads the live object, Liquid2dRender/fluidrenderer.cpp:497-986); SURVEY 8(f)4 asks for one here. The blob
+ * holds every device grid of the FS2D_GRID_* table as it is (a deferred level-set walk stays deferred), the particle
+ * records in device order with their storage-bin / dead bytes (the packed layout above), the step dt and the matrix
+ * scale. Loading it into a handle created with the same parameters and stepping on gives bit-identical results to the
+ * uninterrupted run (tests/test_state_gpu.py). One handle only (FS2D_ERR_STATE over row slabs). The host-side state of
+ * a solver (frame and substep counters, mt19937 stream) is added by FlipSolver::saveState / fs2dh_save_state. */
+int fs2d_state_bytes(fs2d_handle h, size_t *bytes);
+int fs2d_state_save(fs2d_handle h, void *host_buf, size_t capacity_bytes, size_t *written);
+int fs2d_state_load(fs2d_handle h, const void *host_buf, size_t bytes);
 /* Append particles (seedInitialFluid / reseedParticles callers, flipsolver2d.cpp:627-707). */
 int fs2d_append_particles(fs2d_handle h, int64_t count, const float *host_pos, const float *host_vel,
                           const float *host_props);

@@ -52,6 +52,11 @@ int fs2dh_step_substep(fs2dh_solver s, int *frame_finished);
 /* timings12: ms per SolverStage; misc5: frameTime ms, substeps, pressure/density/viscosity iterations */
 int fs2dh_get_stats(fs2dh_solver s, float *timings12, float *misc5);
 
+/* FlipSolver::saveState / loadState: checkpoint of the device state (fs2d_state_save) plus the host side of the
+ * stepping loop (frame / substep counters, mt19937 stream). Load into a solver created from the same scene. */
+int fs2dh_save_state(fs2dh_solver s, const char *path);
+int fs2dh_load_state(fs2dh_solver s, const char *path);
+
 int fs2dh_size_i(fs2dh_solver s);
 int fs2dh_size_j(fs2dh_solver s);
 int fs2dh_sim_type(fs2dh_solver s);
