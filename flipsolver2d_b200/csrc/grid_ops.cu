@@ -193,11 +193,11 @@ __global__ void __launch_bounds__(NT) bfsInitKernel(const uint8_t *__restrict__ 
     }
 }
 
-__device__ __forceinline__ void bfsLayerSample(float *__restrict__ g, uint8_t *__restrict__ valid, uint8_t *__restrict__ marker,
-                                               int sI, int sJ, long long n, int k)
+__device__ __forceinline__ void bfsLayerSampleAt(float *__restrict__ g, uint8_t *__restrict__ valid, uint8_t *__restrict__ marker,
+                                                 int sI, int sJ, int i, int j, int k)
 {
+    const long long n = static_cast<long long>(i) * sJ + j;
     if (marker[n] != 255) return;
-    const int i = static_cast<int>(n / sJ), j = static_cast<int>(n - static_cast<long long>(i) * sJ);
     bool hit = false;
     double avg = 0.0;
     int cnt = 0;
@@ -224,6 +224,13 @@ __device__ __forceinline__ void bfsLayerSample(float *__restrict__ g, uint8_t *_
     marker[n] = static_cast<uint8_t>(k);
 }
 
+__device__ __forceinline__ void bfsLayerSample(float *__restrict__ g, uint8_t *__restrict__ valid, uint8_t *__restrict__ marker,
+                                               int sI, int sJ, long long n, int k)
+{
+    const int i = static_cast<int>(n / sJ);
+    bfsLayerSampleAt(g, valid, marker, sI, sJ, i, static_cast<int>(n - static_cast<long long>(i) * sJ), k);
+}
+
 // One layer over the box [i0, i0+h) x [j0, j0+w) of both sample grids (clipped to each grid's extent).
 __global__ void __launch_bounds__(NT) bfsLayerKernel(float *U, float *V, uint8_t *uValid, uint8_t *vValid, uint8_t *marker, int I,
                                                      int J, int k, int i0, int j0, int h, int w)
@@ -242,6 +249,167 @@ __global__ void __launch_bounds__(NT) bfsLayerKernel(float *U, float *V, uint8_t
     else if (i < I && j <= J)
     {
         bfsLayerSample(V, vValid, marker + NU, I, J + 1, static_cast<long long>(i) * (J + 1) + j, k);
+    }
+}
+
+// All layers in ONE cooperative launch: the bounding box is read on the device (no host round trip between
+// bfsInitKernel and the sweeps) and a grid-wide barrier separates the layers. The box is swept ONCE, to list its unknown
+// samples (at 4096^2: 3.1 M samples in the box, ~0.1 M of them unknown -- the fluid interior is all valid); the layers
+// then only visit the list. (History at 4096^2, per call: 11 launches sweeping the box + a D2H synchronisation 0.35 ms;
+// the same sweeps inside one cooperative kernel 0.31-0.34 ms whatever the index arithmetic, load batching or grid size
+// -- a layer costs its grid barrier plus a chain of dependent L2 round trips over mostly known samples.)
+constexpr int BFSV_THREADS = 1024;
+__global__ void __launch_bounds__(BFSV_THREADS) bfsLayersKernel(float *U, float *V, uint8_t *uValid, uint8_t *vValid, uint8_t *marker, int I,
+                                                                int J, int layers, const int *__restrict__ bbox, int grow, int rowLo,
+                                                                int rowHiU, int32_t *__restrict__ queue, unsigned int *__restrict__ ctl,
+                                                                unsigned int capacity)
+{
+    cg::grid_group grid = cg::this_grid();
+    const int b0 = bbox[0], b1 = bbox[1], b2 = bbox[2], b3 = bbox[3];
+    if (b1 < b0) return;  // no valid sample anywhere: the BFS has no seed (mathfuncs.cpp:171-189); uniform over the grid
+    const int i0 = max(max(b0 - grow, 0), rowLo), i1 = min(min(b1 + grow, I), rowHiU - 1);
+    const int j0 = max(b2 - grow, 0), j1 = min(b3 + grow, J);
+    const int h = i1 - i0 + 1, w = j1 - j0 + 1;
+    const unsigned int NU = static_cast<unsigned int>(I + 1) * static_cast<unsigned int>(J);
+    // ---- the unknown samples of the box, as indices into the marker array (U samples first, V samples from NU on)
+    for (int r = blockIdx.x; r < 2 * h; r += gridDim.x)
+    {
+        const bool second = r >= h;
+        const int i = i0 + (second ? r - h : r);
+        const int sI = second ? I : I + 1, sJ = second ? J + 1 : J;
+        if (i >= sI) continue;
+        const unsigned int rowBase = (second ? NU : 0u) + static_cast<unsigned int>(i) * sJ;
+        const int jEnd = min(j0 + w, sJ);
+        for (int jb = j0; jb < jEnd; jb += BFSV_THREADS)  // warp-uniform trip count (ballot below)
+        {
+            const int j = jb + static_cast<int>(threadIdx.x);
+            const bool unknown = j < jEnd && marker[rowBase + j] == 255;
+            const unsigned int votes = __ballot_sync(0xffffffffu, unknown);
+            if (!votes) continue;
+            const int lane = threadIdx.x & 31;
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(ctl, static_cast<unsigned int>(__popc(votes)));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const unsigned int slot = base + __popc(votes & ((1u << lane) - 1u));
+            if (unknown && slot < capacity) queue[slot] = static_cast<int32_t>(rowBase + j);
+        }
+    }
+    grid.sync();
+    const unsigned int count = *reinterpret_cast<volatile unsigned int *>(ctl);
+    const bool listed = count <= capacity;
+    const unsigned int stride = gridDim.x * static_cast<unsigned int>(BFSV_THREADS);
+    for (int k = 1; k <= layers; k++)
+    {
+        if (listed)
+        {
+            for (unsigned int t = blockIdx.x * static_cast<unsigned int>(BFSV_THREADS) + threadIdx.x; t < count; t += stride)
+            {
+                const unsigned int id = static_cast<unsigned int>(queue[t]);
+                if (id < NU)
+                {
+                    const unsigned int i = id / static_cast<unsigned int>(J);
+                    bfsLayerSampleAt(U, uValid, marker, I + 1, J, static_cast<int>(i), static_cast<int>(id - i * J), k);
+                }
+                else
+                {
+                    const unsigned int m = id - NU, i = m / static_cast<unsigned int>(J + 1);
+                    bfsLayerSampleAt(V, vValid, marker + NU, I, J + 1, static_cast<int>(i), static_cast<int>(m - i * (J + 1)), k);
+                }
+            }
+        }
+        else
+        {
+            // more unknown samples than the list holds: sweep the box rows
+            for (int r = blockIdx.x; r < 2 * h; r += gridDim.x)
+            {
+                const bool second = r >= h;
+                const int i = i0 + (second ? r - h : r);
+                const int sI = second ? I : I + 1, sJ = second ? J + 1 : J;
+                if (i >= sI) continue;
+                const int jEnd = min(j0 + w, sJ);
+                for (int j = j0 + static_cast<int>(threadIdx.x); j < jEnd; j += BFSV_THREADS)
+                {
+                    if (!second)
+                        bfsLayerSampleAt(U, uValid, marker, I + 1, J, i, j, k);
+                    else
+                        bfsLayerSampleAt(V, vValid, marker + NU, I, J + 1, i, j, k);
+                }
+            }
+        }
+        if (k < layers) grid.sync();
+    }
+}
+
+// bfsInitKernel, sixteen samples per thread (gridSizeJ a multiple of 16, fewer than 2^31 samples, rowLo a multiple of 16):
+// markers by byte-wise compare, the bounding-box reduction only in warps that saw a valid sample.
+__global__ void __launch_bounds__(NT) bfsInitVecKernel(const uint8_t *__restrict__ uValid, const uint8_t *__restrict__ vValid, int I, int J,
+                                                       uint8_t *__restrict__ marker, int *__restrict__ bbox, int rowLo, int rowHiU, int rowHiV)
+{
+    const unsigned int NU = static_cast<unsigned int>(I + 1) * static_cast<unsigned int>(J);
+    const unsigned int uBegin = static_cast<unsigned int>(rowLo) * J, gU = static_cast<unsigned int>(rowHiU - rowLo) * J / 16u;
+    const unsigned int vBegin = static_cast<unsigned int>(rowLo) * (J + 1), cntV = static_cast<unsigned int>(rowHiV - rowLo) * (J + 1);
+    const unsigned int gV = (cntV + 15u) / 16u;
+    const unsigned int t = blockIdx.x * static_cast<unsigned int>(NT) + threadIdx.x;
+    int iMin = 0x7fffffff, iMax = -1, jMin = 0x7fffffff, jMax = -1;
+    if (t < gU + gV)
+    {
+        const bool second = t >= gU;
+        const unsigned int n = second ? vBegin + 16u * (t - gU) : uBegin + 16u * t;   // first sample of the group
+        const unsigned int end = second ? vBegin + cntV : uBegin + gU * 16u;
+        const uint8_t *src = second ? vValid : uValid;
+        uint8_t *dst = second ? marker + NU : marker;
+        const unsigned int sJ = second ? J + 1 : J;
+        if (n + 16u <= end)
+        {
+            const uint4 v = *reinterpret_cast<const uint4 *>(src + n);
+            uint4 m;  // 0xff where the flag byte is zero (unknown), 0 where the sample is valid
+            m.x = __vcmpeq4(v.x, 0u);
+            m.y = __vcmpeq4(v.y, 0u);
+            m.z = __vcmpeq4(v.z, 0u);
+            m.w = __vcmpeq4(v.w, 0u);
+            *reinterpret_cast<uint4 *>(dst + n) = m;
+            if ((m.x & m.y & m.z & m.w) != 0xffffffffu)
+            {
+                const unsigned int words[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                for (int b = 0; b < 16; b++)
+                    if (!((words[b >> 2] >> (8 * (b & 3))) & 0xffu))
+                    {
+                        const unsigned int q = n + b;
+                        const int i = static_cast<int>(q / sJ), j = static_cast<int>(q - static_cast<unsigned int>(i) * sJ);
+                        iMin = min(iMin, i);
+                        iMax = max(iMax, i);
+                        jMin = min(jMin, j);
+                        jMax = max(jMax, j);
+                    }
+            }
+        }
+        else
+            for (unsigned int q = n; q < end; q++)
+            {
+                const bool valid = src[q] != 0;
+                dst[q] = valid ? 0 : 255;
+                if (valid)
+                {
+                    const int i = static_cast<int>(q / sJ), j = static_cast<int>(q - static_cast<unsigned int>(i) * sJ);
+                    iMin = min(iMin, i);
+                    iMax = max(iMax, i);
+                    jMin = min(jMin, j);
+                    jMax = max(jMax, j);
+                }
+            }
+    }
+    if (!__any_sync(0xffffffffu, iMax >= 0)) return;
+    iMin = __reduce_min_sync(0xffffffffu, iMin);
+    iMax = __reduce_max_sync(0xffffffffu, iMax);
+    jMin = __reduce_min_sync(0xffffffffu, jMin);
+    jMax = __reduce_max_sync(0xffffffffu, jMax);
+    if ((threadIdx.x & 31) == 0)
+    {
+        atomicMin(bbox + 0, iMin);
+        atomicMax(bbox + 1, iMax);
+        atomicMin(bbox + 2, jMin);
+        atomicMax(bbox + 3, jMax);
     }
 }
 
@@ -724,14 +892,44 @@ int gridExtrapolateVelocity(Ctx *ctx, int radius)
     // the inner halo - (radius+2) rows are exact.
     const SlabRows reg = slabExt(ctx, ctx->slab.halo);
     const int rowHiU = reg.hi == ctx->I ? ctx->I + 1 : reg.hi;
-    bfsInitKernel<<<divUp(static_cast<long long>(rowHiU - reg.lo) * ctx->J + static_cast<long long>(reg.hi - reg.lo) * (ctx->J + 1), NT), NT, 0,
-                    st>>>(ctx->uValid, ctx->vValid, ctx->I, ctx->J, marker, bbox, reg.lo, rowHiU, reg.hi);
+    const long long samples = static_cast<long long>(rowHiU - reg.lo) * ctx->J + static_cast<long long>(reg.hi - reg.lo) * (ctx->J + 1);
+    if (ctx->J % 16 == 0 && reg.lo % 16 == 0 && ctx->NU + ctx->NV < (1ll << 31))
+        bfsInitVecKernel<<<divUp(samples / 16 + 2, NT), NT, 0, st>>>(ctx->uValid, ctx->vValid, ctx->I, ctx->J, marker, bbox, reg.lo, rowHiU, reg.hi);
+    else
+        bfsInitKernel<<<divUp(samples, NT), NT, 0, st>>>(ctx->uValid, ctx->vValid, ctx->I, ctx->J, marker, bbox, reg.lo, rowHiU, reg.hi);
     ctx->launches++;
+    const int grow = radius + 2;
+    static const bool stepwiseBfs = std::getenv("FS2D_BFS_STEPWISE") != nullptr;  // A/B: one launch per layer, bounding box via the host
+    if (!stepwiseBfs && ctx->NU + ctx->NV < (1ll << 31))
+    {
+        if (!ctx->bfsQueue)
+        {
+            FS2D_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->bfsQueue), sizeof(int32_t) * static_cast<size_t>(ctx->N)));
+            FS2D_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->bfsCtl), 64));
+        }
+        FS2D_CUDA(cudaMemsetAsync(ctx->bfsCtl, 0, 64, st));
+        const int share = (ctx->slab.enabled && ctx->slab.world > 1) ? std::max(ctx->slab.share, 1) : 1;
+        float *U = ctx->U, *V = ctx->V;
+        uint8_t *uv = ctx->uValid, *vv = ctx->vValid;
+        int I = ctx->I, J = ctx->J, layers = radius + 1, g = grow, rowLo = reg.lo, rowHi = rowHiU;
+        const int *bb = bbox;
+        int32_t *queue = ctx->bfsQueue;
+        unsigned int *ctl = ctx->bfsCtl;
+        unsigned int capacity = static_cast<unsigned int>(ctx->N);
+        void *args[] = {&U, &V, &uv, &vv, &marker, &I, &J, &layers, &bb, &g, &rowLo, &rowHi, &queue, &ctl, &capacity};
+        const cudaError_t le = cudaLaunchCooperativeKernel(reinterpret_cast<void *>(bfsLayersKernel), dim3(std::max(1, ctx->smCount / share)),
+                                                           dim3(BFSV_THREADS), args, 0, st);
+        if (le == cudaSuccess)
+        {
+            ctx->launches++;
+            return FS2D_OK;
+        }
+        cudaGetLastError();  // the grid cannot be co-resident here: one launch per layer below
+    }
     int box[4];
     FS2D_CUDA(fs2dCopyToHost(ctx, box, bbox, sizeof(box)));
     FS2D_CUDA(cudaStreamSynchronize(st));
     if (box[1] < box[0]) return FS2D_OK;  // no valid sample anywhere: the BFS has no seed (mathfuncs.cpp:171-189)
-    const int grow = radius + 2;
     const int i0 = std::max({box[0] - grow, 0, reg.lo}), i1 = std::min({box[1] + grow, ctx->I, rowHiU - 1});
     const int j0 = std::max(box[2] - grow, 0), j1 = std::min(box[3] + grow, ctx->J);
     const int h = i1 - i0 + 1, w = j1 - j0 + 1;

@@ -2575,25 +2575,36 @@ __global__ void __launch_bounds__(1024) pcgTileCompactKernel(const int *__restri
 // Slab mode: the walk covers the owned rows plus one halo row each side [nLo, nHi) (the halo rows of r0 = z = rhs
 // come from the locally computed halo of the right-hand side); only owned cells [oLo, oHi) enter the sums, and
 // the last CTA publishes them as phase 0 instead of writing the scalars.
+// residentLimit > 0: the tile list was built BEFORE this kernel and a list of at most that many tiles will be taken by
+// pcgResidentKernel, which never reads r0 / s0 / r1 / s1 (its vectors live in shared memory, the paged boxes are
+// initialised by the kernel itself): those four passes (537 MB at 4096^2, 0.11 ms) are skipped.
 template <bool MG>
 __global__ void __launch_bounds__(NT) pcgInitKernel(const double *rhs, double *x, double *r0, double *z, double *s0, double *r1,
                                                     double *s1, double *q, long long N, double *partials, PcgScalars *sc,
-                                                    long long nLo, long long oLo, long long oHi, MgArgs mg)
+                                                    long long nLo, long long oLo, long long oHi, MgArgs mg,
+                                                    const int *activeCount, int residentLimit)
 {
     __shared__ double red[8];
     __shared__ int isLast;
     double acc = 0.0, amax = 0.0;
+    const bool light = residentLimit > 0 && activeCount && *activeCount > 0 && *activeCount <= residentLimit;
     for (long long n = nLo + blockIdx.x * static_cast<long long>(NT) + threadIdx.x; n < N; n += static_cast<long long>(gridDim.x) * NT)
     {
         const double v = rhs[n];
         x[n] = 0.0;
-        r0[n] = v;
         z[n] = v;
-        s0[n] = 0.0;
+        if (!light)
+        {
+            r0[n] = v;
+            s0[n] = 0.0;
+        }
         if (r1)  // active-tile mode: skipped tiles are never written again and must read as zero
         {
-            r1[n] = 0.0;
-            s1[n] = 0.0;
+            if (!light)
+            {
+                r1[n] = 0.0;
+                s1[n] = 0.0;
+            }
             q[n] = 0.0;
         }
         if (MG && (n < oLo || n >= oHi)) continue;
@@ -2646,6 +2657,18 @@ __global__ void __launch_bounds__(NT) pcgInitKernel(const double *rhs, double *x
         sc->ticketA = 0;
         sc->ticketB = 0;
         sc->ticketC = 0;
+    }
+}
+
+// What a light pcgInitKernel left out, for the (rare) case that the resident kernel could not be launched after all.
+__global__ void __launch_bounds__(NT) pcgInitRestKernel(const double *rhs, double *r0, double *s0, double *r1, double *s1, long long nLo, long long N)
+{
+    for (long long n = nLo + blockIdx.x * static_cast<long long>(NT) + threadIdx.x; n < N; n += static_cast<long long>(gridDim.x) * NT)
+    {
+        r0[n] = rhs[n];
+        s0[n] = 0.0;
+        r1[n] = 0.0;
+        s1[n] = 0.0;
     }
 }
 
@@ -2957,18 +2980,6 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
         }
     const bool active = pipe && !ctx->densePcg;
     FS2D_CUDA(cudaMemsetAsync(&ctx->scalars->pad, 0, sizeof(int), st));  // set by pcgResidentKernel when it takes the solve
-    if (mgOn || whole)
-    {
-        mg.phase = 0;
-        pcgInitKernel<true><<<flat, NT, 0, st>>>(ctx->rhs, ctx->x, ctx->r[0], ctx->z, ctx->s[0], active ? ctx->r[1] : nullptr, ctx->s[1], ctx->q,
-                                                 nHi, ctx->partials, ctx->scalars, nLo, oLo, oHi, mg);
-    }
-    else
-    {
-        pcgInitKernel<false><<<flat, NT, 0, st>>>(ctx->rhs, ctx->x, ctx->r[0], ctx->z, ctx->s[0], active ? ctx->r[1] : nullptr, ctx->s[1],
-                                                  ctx->q, ctx->N, ctx->partials, ctx->scalars, 0, 0, ctx->N, mg);
-    }
-    ctx->launches++;
     if (active)
     {
         pcgTileFlagKernel<<<blocks, NT, 0, st>>>(ctx->rowInfo, ctx->rhs, ctx->I, ctx->J, a.tilesJ, tileBase, ctx->tileFlags);
@@ -2977,6 +2988,29 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
         a.activeTiles = ctx->activeTiles;
         a.activeCount = ctx->activeCount;
     }
+    // the longest tile list pcgResidentKernel takes (the same tests as in the kernel): such a solve needs no r / s arrays
+    int resBlocks = std::max(1, ctx->smCount / share);
+    if (ctx->pcgGridLimit > 0) resBlocks = std::min(resBlocks, ctx->pcgGridLimit);
+    int residentLimit = 0;
+    if (whole && active && ctx->residentPcg)
+    {
+        residentLimit = RES_TPC * resBlocks;
+        if (!mgOn && ctx->pagedPcg)
+            residentLimit = static_cast<int>(std::max<long long>(residentLimit, std::min<long long>(static_cast<long long>(RES_PAGED_TPC) * resBlocks, ctx->N / PTILE_PAD)));
+    }
+    bool initLight = residentLimit > 0;
+    if (mgOn || whole)
+    {
+        mg.phase = 0;
+        pcgInitKernel<true><<<flat, NT, 0, st>>>(ctx->rhs, ctx->x, ctx->r[0], ctx->z, ctx->s[0], active ? ctx->r[1] : nullptr, ctx->s[1], ctx->q,
+                                                 nHi, ctx->partials, ctx->scalars, nLo, oLo, oHi, mg, ctx->activeCount, residentLimit);
+    }
+    else
+    {
+        pcgInitKernel<false><<<flat, NT, 0, st>>>(ctx->rhs, ctx->x, ctx->r[0], ctx->z, ctx->s[0], active ? ctx->r[1] : nullptr, ctx->s[1],
+                                                  ctx->q, ctx->N, ctx->partials, ctx->scalars, 0, 0, ctx->N, mg, nullptr, 0);
+    }
+    ctx->launches++;
     if (whole)
     {
         SolveArgs g;
@@ -3020,8 +3054,6 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
         {
             // small active sets stay in shared memory for the whole solve (pcgResidentKernel decides on the device,
             // from the tile count, whether it can hold them; if not it returns at once and the streaming kernel runs)
-            int resBlocks = std::max(1, ctx->smCount / share);
-            if (ctx->pcgGridLimit > 0) resBlocks = std::min(resBlocks, ctx->pcgGridLimit);
             void *rargs[] = {&g, &mg};
             const size_t rsmem = sizeof(ResSmem);
             cudaError_t re;
@@ -3033,8 +3065,12 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
             {
                 re = cudaLaunchCooperativeKernel(reinterpret_cast<void *>(pcgResidentKernel<false, false>), dim3(resBlocks), dim3(RNT), rargs, rsmem, st);
             }
+            bool launched = true;
             if (re == cudaErrorCooperativeLaunchTooLarge)
+            {
                 cudaGetLastError();  // the device is shared: the streaming kernel (or its stepwise fallback) takes the solve
+                launched = false;
+            }
             else
             {
                 FS2D_CUDA(re);
@@ -3045,13 +3081,23 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
                     // at once when the resident kernel took the solve or when the list is too long
                     re = cudaLaunchCooperativeKernel(reinterpret_cast<void *>(pcgResidentKernel<false, true>), dim3(resBlocks), dim3(RNT), rargs, rsmem, st);
                     if (re == cudaErrorCooperativeLaunchTooLarge)
+                    {
                         cudaGetLastError();
+                        launched = false;
+                    }
                     else
                     {
                         FS2D_CUDA(re);
                         ctx->launches++;
                     }
                 }
+            }
+            if (!launched && initLight)
+            {
+                // a kernel the light initialisation counted on did not start: the streaming kernel needs the r / s arrays
+                pcgInitRestKernel<<<flat, NT, 0, st>>>(ctx->rhs, ctx->r[0], ctx->s[0], ctx->r[1], ctx->s[1], nLo, nHi);
+                ctx->launches++;
+                initLight = false;
             }
         }
         void *args[] = {&g, &mg, &maps, &useTensor};
