@@ -105,9 +105,12 @@ __device__ __forceinline__ float gridLerp(const GridView &g, float i, float j)
     j = faddr(j, g.offY);
     i = fminf(fmaxf(i, 0.f), static_cast<float>(g.sizeI - 1));
     j = fminf(fmaxf(j, 0.f), static_cast<float>(g.sizeJ - 1));
-    const int ci = static_cast<int>(floorf(i)), cj = static_cast<int>(floorf(j));
-    const float fi = fsubr(i, static_cast<float>(static_cast<long long>(i)));
-    const float fj = fsubr(j, static_cast<float>(static_cast<long long>(j)));
+    // i, j are clamped to [0, size - 1] above, so floor = truncation and one 32-bit conversion each way gives the
+    // reference's std::floor / static_cast<ssize_t> values (the 64-bit conversions and the two roundings ran on the
+    // 16-lane XU pipe: 8 of them per sample, 9 samples per advected particle)
+    const int ci = __float2int_rz(i), cj = __float2int_rz(j);
+    const float fi = fsubr(i, __int2float_rn(ci));
+    const float fj = fsubr(j, __int2float_rn(cj));
     const int ni = fi >= 0.5f ? ci + 1 : ci - 1;
     const int nj = fj >= 0.5f ? cj + 1 : cj - 1;
     const float iF = fi < 0.5f ? fsubr(0.5f, fi) : fsubr(fi, 0.5f);
@@ -117,14 +120,17 @@ __device__ __forceinline__ float gridLerp(const GridView &g, float i, float j)
     return lerpf(v1, v2, jF);
 }
 
-// simmath::bSpline (mathfuncs.cpp:32-37)
+// simmath::bSpline (mathfuncs.cpp:32-37). The reference evaluates both pieces, multiplies each by its 0 / 1 range flag
+// and adds them: (0.75 - v^2)*[v < 0.5] + 0.5*(1.5 - v)^2*[0.5 <= v < 1.5]. For finite v the piece with flag 0
+// contributes +-0 and the sum IS the other piece (x + +-0 = x; both flags 0: -0 + +0 = +0), so selecting the piece gives
+// the same bits with half the arithmetic -- this function runs four times per particle-cell pair of the P2G gather.
 __device__ __forceinline__ float bSpline(float v)
 {
     v = fabsf(v);
-    const float a = fmulr(fsubr(0.75f, fmulr(v, v)), (v < 0.5f) ? 1.f : 0.f);
+    const float a = fsubr(0.75f, fmulr(v, v));
     const float h = fsubr(1.5f, v);
-    const float b = fmulr(fmulr(fmulr(0.5f, h), h), (v >= 0.5f && v < 1.5f) ? 1.f : 0.f);
-    return faddr(a, b);
+    const float b = fmulr(fmulr(0.5f, h), h);
+    return v < 0.5f ? a : (v < 1.5f ? b : 0.f);  // selects, no branch: the gather loop stays convergent
 }
 
 // simmath::quadraticBSpline (mathfuncs.cpp:39-43); bSpline(0) = 0.75

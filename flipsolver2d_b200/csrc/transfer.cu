@@ -25,23 +25,33 @@ namespace
 constexpr int TI = 8;          // tile rows (cells)
 constexpr int TJ = 32;         // tile columns (cells)
 constexpr int NT = TI * TJ;    // one thread per cell
-constexpr int STAGE = 6144;    // staged particle records per CTA (pos + 2 payload floats = 16 B each)
+constexpr int STAGE = 4352;    // staged particle records per CTA (pos + 2 payload floats + storage byte = 17 B each): 72 KB, 3 CTAs per SM
 
-struct TileStage
+// PAY = payload floats per record: 2 (velocity), 1 (one property column), 0 (positions only: density). The shared
+// memory request follows the payload -- 72 / 55 / 38 KB, i.e. 3 / 4 / 5 CTAs per SM: the gathers are bound by instruction
+// issue at low occupancy (ncu: 25 % warps active with the former 96 KB for every kernel), not by staging traffic.
+template <int PAY> struct TileStage
 {
     float2 pos[STAGE];
-    float2 pay[STAGE];          // velocity, or (property, unused)
+    float pay[PAY > 0 ? STAGE * PAY : 1];
     unsigned char mis[STAGE];   // storage-bin code (FS2D_MIS_*)
     int rowBegin[TI + 4];       // global particle index where each staged row starts
     int rowOffset[TI + 5];      // offset of each staged row inside pos/pay
+    __device__ __forceinline__ float2 payload(int k) const
+    {
+        if (PAY == 2) return make_float2(pay[2 * k], pay[2 * k + 1]);
+        if (PAY == 1) return make_float2(pay[k], 0.f);
+        return make_float2(0.f, 0.f);
+    }
 };
-constexpr size_t STAGE_BYTES = sizeof(TileStage);  // 96 KB + row tables: dynamic shared memory, 2 CTAs per SM
+template <int PAY> constexpr size_t stageBytes() { return sizeof(TileStage<PAY>); }
+template <int PAY> constexpr int stageCtasPerSm() { return PAY == 2 ? 3 : (PAY == 1 ? 4 : 5); }
 
 // Stage rows [i0-haloLo, i0+TI-1+haloHi] x columns [j0-haloLo, j0+TJ-1+haloHi] of the sorted
 // particle arrays. Returns (for the whole CTA) 1 = staged, 0 = the records do not fit (read them from global memory),
 // 2 = there is no particle at all in the tile and its halo.
-template <bool WITH_PAYLOAD2>
-__device__ int stageTile(TileStage &s, const int32_t *__restrict__ cellStart, const float2 *__restrict__ pos,
+template <int PAY>
+__device__ int stageTile(TileStage<PAY> &s, const int32_t *__restrict__ cellStart, const float2 *__restrict__ pos,
                           const float2 *__restrict__ pay2, const float *__restrict__ pay1, const uint8_t *__restrict__ mis, int I,
                           int J, int i0, int j0, int haloLo, int haloHi)
 {
@@ -87,10 +97,14 @@ __device__ int stageTile(TileStage &s, const int32_t *__restrict__ cellStart, co
         {
             s.pos[so + k] = pos[gb + k];
             s.mis[so + k] = mis[gb + k];
-            if (WITH_PAYLOAD2)
-                s.pay[so + k] = pay2[gb + k];
-            else
-                s.pay[so + k] = make_float2(pay1 ? pay1[gb + k] : 0.f, 0.f);
+            if (PAY == 2)
+            {
+                const float2 v = pay2[gb + k];
+                s.pay[2 * (so + k)] = v.x;
+                s.pay[2 * (so + k) + 1] = v.y;
+            }
+            else if (PAY == 1)
+                s.pay[so + k] = pay1 ? pay1[gb + k] : 0.f;
         }
     }
     __syncthreads();
@@ -98,8 +112,8 @@ __device__ int stageTile(TileStage &s, const int32_t *__restrict__ cellStart, co
 }
 
 // Iterate the particles of cells [ja..jb] of row gi, staged or global. F(pos, payload).
-template <bool WITH_PAYLOAD2, class F>
-__device__ __forceinline__ void forRowRange(const TileStage &s, bool staged, const int32_t *__restrict__ cellStart,
+template <int PAY, class F>
+__device__ __forceinline__ void forRowRange(const TileStage<PAY> &s, bool staged, const int32_t *__restrict__ cellStart,
                                             const float2 *__restrict__ pos, const float2 *__restrict__ pay2,
                                             const float *__restrict__ pay1, const uint8_t *__restrict__ mis, int J, int gi,
                                             int ja, int jb, int stagedRow, int ci, int cj, F f)
@@ -116,7 +130,7 @@ __device__ __forceinline__ void forRowRange(const TileStage &s, bool staged, con
             const unsigned int m = s.mis[k + shift];
             const float2 p = s.pos[k + shift];
             if (m != FS2D_MIS_HOME && !storageVisible(m, p, ci, cj)) continue;
-            f(p, s.pay[k + shift]);
+            f(p, s.payload(k + shift));
         }
     }
     else
@@ -126,7 +140,7 @@ __device__ __forceinline__ void forRowRange(const TileStage &s, bool staged, con
             const unsigned int m = mis[k];
             const float2 p = pos[k];
             if (m != FS2D_MIS_HOME && !storageVisible(m, p, ci, cj)) continue;
-            f(p, WITH_PAYLOAD2 ? pay2[k] : make_float2(pay1 ? pay1[k] : 0.f, 0.f));
+            f(p, PAY == 2 ? pay2[k] : make_float2((PAY == 1 && pay1) ? pay1[k] : 0.f, 0.f));
         }
     }
 }
@@ -141,14 +155,14 @@ __global__ void __launch_bounds__(NT) p2gVelocityKernel(const int32_t *__restric
                                                         uint8_t *__restrict__ uValid, uint8_t *__restrict__ vValid)
 {
     extern __shared__ __align__(16) unsigned char stageRaw[];
-    TileStage &s = *reinterpret_cast<TileStage *>(stageRaw);
+    TileStage<2> &s = *reinterpret_cast<TileStage<2> *>(stageRaw);
     const int count = *tileCount;
     for (int t = blockIdx.x; t < count; t += gridDim.x)  // persistent CTAs walk the tiles that have particles in reach
     {
         const int tile = tileList[t];
         const int ti = tile / tilesJ, tj = tile - ti * tilesJ;
         const int i0 = ti * TI, j0 = tj * TJ;
-        const int stageMode = stageTile<true>(s, cellStart, pos, vel, nullptr, mis, I, J, i0, j0, 1, 1);
+        const int stageMode = stageTile<2>(s, cellStart, pos, vel, nullptr, mis, I, J, i0, j0, 1, 1);
         const bool staged = stageMode != 0, empty = stageMode == 2;
         const int li = threadIdx.x / TJ, lj = threadIdx.x - li * TJ;
         const int i = i0 + li, j = j0 + lj;
@@ -161,7 +175,7 @@ __global__ void __launch_bounds__(NT) p2gVelocityKernel(const int32_t *__restric
             const int ja = max(j - 1, 0), jb = min(j + 1, J - 1);
             for (int gi = max(i - 1, 0); !empty && gi <= min(i + 1, I - 1); gi++)
             {
-                forRowRange<true>(s, staged, cellStart, pos, vel, nullptr, mis, J, gi, ja, jb, gi - (i0 - 1), i, j,
+                forRowRange<2>(s, staged, cellStart, pos, vel, nullptr, mis, J, gi, ja, jb, gi - (i0 - 1), i, j,
                                   [&](float2 p, float2 v)
                                   {
                                       const float wU = quadraticBSpline(fsubr(p.x, ci), fsubr(p.y, cjh));
@@ -197,14 +211,14 @@ __global__ void __launch_bounds__(NT) p2gCenteredKernel(const int32_t *__restric
                                                         float *__restrict__ out, uint8_t *__restrict__ known)
 {
     extern __shared__ __align__(16) unsigned char stageRaw[];
-    TileStage &s = *reinterpret_cast<TileStage *>(stageRaw);
+    TileStage<1> &s = *reinterpret_cast<TileStage<1> *>(stageRaw);
     const int count = *tileCount;
     for (int t = blockIdx.x; t < count; t += gridDim.x)
     {
         const int tile = tileList[t];
         const int ti = tile / tilesJ, tj = tile - ti * tilesJ;
         const int i0 = ti * TI, j0 = tj * TJ;
-        const int stageMode = stageTile<false>(s, cellStart, pos, nullptr, prop, mis, I, J, i0, j0, 2, 1);
+        const int stageMode = stageTile<1>(s, cellStart, pos, nullptr, prop, mis, I, J, i0, j0, 2, 1);
         const bool staged = stageMode != 0, empty = stageMode == 2;
         const int li = threadIdx.x / TJ, lj = threadIdx.x - li * TJ;
         const int i = i0 + li, j = j0 + lj;
@@ -216,7 +230,7 @@ __global__ void __launch_bounds__(NT) p2gCenteredKernel(const int32_t *__restric
             const int ja = max(j - 2, 0), jb = min(j + 1, J - 1);
             for (int gi = max(i - 2, 0); !empty && gi <= min(i + 1, I - 1); gi++)
             {
-                forRowRange<false>(s, staged, cellStart, pos, nullptr, prop, mis, J, gi, ja, jb, gi - (i0 - 2), i, j,
+                forRowRange<1>(s, staged, cellStart, pos, nullptr, prop, mis, J, gi, ja, jb, gi - (i0 - 2), i, j,
                                    [&](float2 p, float2 v)
                                    {
                                        const float w = quadraticBSpline(fsubr(p.x, ci), fsubr(p.y, cj));
@@ -289,14 +303,14 @@ __global__ void __launch_bounds__(NT) densityKernel(const int32_t *__restrict__ 
                                                     float particleMass, float cellVolume, float restDensity, float *__restrict__ density)
 {
     extern __shared__ __align__(16) unsigned char stageRaw[];
-    TileStage &s = *reinterpret_cast<TileStage *>(stageRaw);
+    TileStage<0> &s = *reinterpret_cast<TileStage<0> *>(stageRaw);
     const int count = *tileCount;
     for (int t = blockIdx.x; t < count; t += gridDim.x)
     {
         const int tile = tileList[t];
         const int ti = tile / tilesJ, tj = tile - ti * tilesJ;
         const int i0 = ti * TI, j0 = tj * TJ;
-        const int stageMode = stageTile<false>(s, cellStart, pos, nullptr, nullptr, mis, I, J, i0, j0, 1, 1);
+        const int stageMode = stageTile<0>(s, cellStart, pos, nullptr, nullptr, mis, I, J, i0, j0, 1, 1);
         const bool staged = stageMode != 0, empty = stageMode == 2;
         const int li = threadIdx.x / TJ, lj = threadIdx.x - li * TJ;
         const int i = i0 + li, j = j0 + lj;
@@ -307,7 +321,7 @@ __global__ void __launch_bounds__(NT) densityKernel(const int32_t *__restrict__ 
             const int ja = max(j - 1, 0), jb = min(j + 1, J - 1);
             for (int gi = max(i - 1, 0); !empty && gi <= min(i + 1, I - 1); gi++)
             {
-                forRowRange<false>(s, staged, cellStart, pos, nullptr, nullptr, mis, J, gi, ja, jb, gi - (i0 - 1), i, j,
+                forRowRange<0>(s, staged, cellStart, pos, nullptr, nullptr, mis, J, gi, ja, jb, gi - (i0 - 1), i, j,
                                    [&](float2 p, float2)
                                    {
                                        const float w = bilinearHat(fsubr(fsubr(p.x, ci), 0.5f), fsubr(fsubr(p.y, cj), 0.5f));
@@ -388,9 +402,9 @@ __global__ void __launch_bounds__(256) sdfKernel(const int32_t *__restrict__ cel
     sdf[n] = fsubr(__fsqrt_rn(best), radius);
 }
 
-template <class K> void allowStage(K kernel)
+template <int PAY, class K> void allowStage(K kernel)
 {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(STAGE_BYTES));
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(stageBytes<PAY>()));
 }
 
 // Tiles covering the rows `r` (slab boundaries are multiples of 16, hence of TI); *tileBase = first tile.
@@ -406,7 +420,7 @@ int tileCount(const Ctx *ctx, SlabRows r, int *tilesJ, int *tileBase)
 int particlesSort(Ctx *ctx);
 
 // Builds the list of tiles with particles in reach for the rows `r`; returns the persistent grid size to launch.
-static int buildTileList(Ctx *ctx, SlabRows r, int *tilesJ)
+static int buildTileList(Ctx *ctx, SlabRows r, int *tilesJ, int ctasPerSm)
 {
     int tileBase = 0;
     const int tiles = tileCount(ctx, r, tilesJ, &tileBase);
@@ -420,7 +434,7 @@ static int buildTileList(Ctx *ctx, SlabRows r, int *tilesJ)
     p2gTileListKernel<<<divUp(tiles, 8), 256, 0, ctx->stream>>>(ctx->cellStart, ctx->I, ctx->J, *tilesJ, tileBase, tiles, list, count);
     ctx->launches++;
     (void)list;
-    return std::max(1, std::min(tiles, 2 * ctx->smCount));
+    return std::max(1, std::min(tiles, ctasPerSm * ctx->smCount));
 }
 
 static int ensureSorted(Ctx *ctx)
@@ -446,11 +460,11 @@ int transferVelocity(Ctx *ctx)
     FS2D_CUDA(cudaMemsetAsync(ctx->U + uOff, 0, sizeof(float) * uCnt, st));
     FS2D_CUDA(cudaMemsetAsync(ctx->uValid + uOff, 0, uCnt, st));
     int tilesJ;
-    const int grid = buildTileList(ctx, own, &tilesJ);
+    const int grid = buildTileList(ctx, own, &tilesJ, stageCtasPerSm<2>());
     if (grid < 0) return FS2D_ERR_CUDA;
     ParticleBuffers &b = ctx->pb[ctx->cur];
-    allowStage(p2gVelocityKernel);
-    p2gVelocityKernel<<<grid, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, b.vel, b.mis, ctx->I, ctx->J, tilesJ, ctx->p2gTileList + 1,
+    allowStage<2>(p2gVelocityKernel);
+    p2gVelocityKernel<<<grid, NT, stageBytes<2>(), st>>>(ctx->cellStart, b.pos, b.vel, b.mis, ctx->I, ctx->J, tilesJ, ctx->p2gTileList + 1,
                                                      ctx->p2gTileList, ctx->U, ctx->V, ctx->uValid, ctx->vValid);
     ctx->launches++;
     FS2D_CUDA(cudaGetLastError());
@@ -464,7 +478,7 @@ int transferCentered(Ctx *ctx)
     cudaStream_t st = ctx->stream;
     const SlabRows own = slabOwn(ctx);
     int tilesJ;
-    const int grid = buildTileList(ctx, own, &tilesJ);
+    const int grid = buildTileList(ctx, own, &tilesJ, stageCtasPerSm<1>());
     if (grid < 0) return FS2D_ERR_CUDA;
     const int *tl = ctx->p2gTileList + 1, *tc = ctx->p2gTileList;
     ParticleBuffers &b = ctx->pb[ctx->cur];
@@ -477,29 +491,29 @@ int transferCentered(Ctx *ctx)
     const size_t cOff = static_cast<size_t>(own.lo) * ctx->J, cCnt = static_cast<size_t>(own.hi - own.lo) * ctx->J;
     auto clear = [&](float *grid) { return cudaMemsetAsync(grid + cOff, 0, sizeof(float) * cCnt, st); };
     FS2D_CUDA(cudaMemsetAsync(ctx->knownCentered + cOff, 0, cCnt, st));
-    allowStage(p2gCenteredKernel<0>);
-    allowStage(p2gCenteredKernel<1>);
+    allowStage<1>(p2gCenteredKernel<0>);
+    allowStage<1>(p2gCenteredKernel<1>);
     auto column = [&](int prop) -> const float * { return prop >= 0 ? b.props + static_cast<int64_t>(prop) * b.capacity : nullptr; };
     switch (ctx->p.sim_type)
     {
     case FS2D_SIM_LIQUID:
         FS2D_CUDA(clear(ctx->viscosity));
-        p2gCenteredKernel<0><<<grid, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, column(ctx->p.viscosity_property), b.mis, ctx->I, ctx->J,
+        p2gCenteredKernel<0><<<grid, NT, stageBytes<1>(), st>>>(ctx->cellStart, b.pos, column(ctx->p.viscosity_property), b.mis, ctx->I, ctx->J,
                                                   tilesJ, tl, tc, ctx->viscosity, ctx->knownCentered);
         ctx->launches++;
         break;
     case FS2D_SIM_NBFLIP:
         FS2D_CUDA(clear(ctx->viscosity));
-        p2gCenteredKernel<1><<<grid, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, column(ctx->p.viscosity_property), b.mis, ctx->I, ctx->J,
+        p2gCenteredKernel<1><<<grid, NT, stageBytes<1>(), st>>>(ctx->cellStart, b.pos, column(ctx->p.viscosity_property), b.mis, ctx->I, ctx->J,
                                                   tilesJ, tl, tc, ctx->viscosity, ctx->knownCentered);
         ctx->launches++;
         break;
     default:  // smoke / fire: temperature and concentration (fire's fuel column has no P2G in the reference)
         FS2D_CUDA(clear(ctx->temperature));
         FS2D_CUDA(clear(ctx->concentration));
-        p2gCenteredKernel<1><<<grid, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, column(ctx->p.temperature_property), b.mis, ctx->I, ctx->J,
+        p2gCenteredKernel<1><<<grid, NT, stageBytes<1>(), st>>>(ctx->cellStart, b.pos, column(ctx->p.temperature_property), b.mis, ctx->I, ctx->J,
                                                   tilesJ, tl, tc, ctx->temperature, ctx->knownCentered);
-        p2gCenteredKernel<1><<<grid, NT, STAGE_BYTES, st>>>(ctx->cellStart, b.pos, column(ctx->p.concentration_property), b.mis, ctx->I, ctx->J,
+        p2gCenteredKernel<1><<<grid, NT, stageBytes<1>(), st>>>(ctx->cellStart, b.pos, column(ctx->p.concentration_property), b.mis, ctx->I, ctx->J,
                                                   tilesJ, tl, tc, ctx->concentration, nullptr);
         ctx->launches += 2;
         break;
@@ -516,7 +530,7 @@ int transferDensity(Ctx *ctx)
     // reach 12 rows, the tile halo needs 9)
     const SlabRows rows = slabExt(ctx, ctx->slab.enabled ? TI : 0);
     int tilesJ;
-    const int grid = buildTileList(ctx, rows, &tilesJ);
+    const int grid = buildTileList(ctx, rows, &tilesJ, stageCtasPerSm<0>());
     if (grid < 0) return FS2D_ERR_CUDA;
     // float cellVolume = dx*dx*dx; float particleMass = (rho * cellVolume) / float(ppc) (flipsolver2d.cpp:203-204)
     const float cellVolume = static_cast<float>(ctx->p.dx * ctx->p.dx * ctx->p.dx);
@@ -526,8 +540,8 @@ int transferDensity(Ctx *ctx)
     const long long nBegin = static_cast<long long>(rLo) * ctx->J, nEnd = static_cast<long long>(rHi) * ctx->J;
     densityBackgroundKernel<<<divUp(nEnd - nBegin, 256), 256, 0, ctx->stream>>>(ctx->material, ctx->I, ctx->J, cellVolume,
                                                                                static_cast<float>(ctx->p.fluid_density), ctx->density, nBegin, nEnd);
-    allowStage(densityKernel);
-    densityKernel<<<grid, NT, STAGE_BYTES, ctx->stream>>>(ctx->cellStart, ctx->pb[ctx->cur].pos, ctx->pb[ctx->cur].mis, ctx->material, ctx->I, ctx->J,
+    allowStage<0>(densityKernel);
+    densityKernel<<<grid, NT, stageBytes<0>(), ctx->stream>>>(ctx->cellStart, ctx->pb[ctx->cur].pos, ctx->pb[ctx->cur].mis, ctx->material, ctx->I, ctx->J,
                                                          tilesJ, ctx->p2gTileList + 1, ctx->p2gTileList, particleMass, cellVolume,
                                                          static_cast<float>(ctx->p.fluid_density), ctx->density);
     ctx->launches++;
