@@ -1643,6 +1643,7 @@ struct ResSmem
     double pub[2];
     double bc[2];
     unsigned long long full[2];  // paged tiles: arrival of a box in scratch 0 / 1
+    int pagedI0[RES_PAGED_TPC], pagedJ0[RES_PAGED_TPC];  // origins of the CTA's paged tiles
     int isLast;
     int ok;
 };
@@ -1787,6 +1788,34 @@ __device__ __forceinline__ void resRingCell(int tid, int i0, int j0, int I, long
     }
 }
 
+// The same with 32-bit indices (paged tiles: N < 2^31 there), a third of the instructions.
+__device__ __forceinline__ void resRingCell32(int tid, int i0, int j0, int I, int J, int N, int *pos, int *n)
+{
+    *pos = -1;
+    *n = -1;
+    if (tid < 2 * TC)
+    {
+        const int bottom = tid >= TC ? 1 : 0, col = tid - bottom * TC;
+        const int gi = bottom ? i0 + TR : i0 - 1, gj = j0 + col;
+        if (gj < J)
+        {
+            *pos = (bottom ? TR + 1 : 0) * PSW + col + 2;
+            if (gi >= 0 && gi < I) *n = gi * J + gj;
+        }
+    }
+    else if (tid < 2 * TC + 2 * TR)
+    {
+        const int e = tid - 2 * TC, right = e >= TR ? 1 : 0, ar = 1 + (e - right * TR);
+        const int gi = i0 - 1 + ar;
+        const int span = J - j0;
+        const int c = right ? (span < TC ? span : TC) + 2 : 1;
+        const int gj = j0 - 2 + c;
+        *pos = ar * PSW + c;
+        const long long lin = static_cast<long long>(gi) * J + gj;
+        if (gi < I && lin >= 0 && lin < N) *n = static_cast<int>(lin);
+    }
+}
+
 template <bool MG, bool PAGED> __global__ void __launch_bounds__(RNT, 1) pcgResidentKernel(SolveArgs g, MgArgs mg)
 {
     static_assert(!(MG && PAGED), "paged tiles: one GPU only");
@@ -1801,7 +1830,7 @@ template <bool MG, bool PAGED> __global__ void __launch_bounds__(RNT, 1) pcgResi
     if (count <= 0) return;
     if (!PAGED && count > RES_TPC * static_cast<int>(gridDim.x)) return;
     if (PAGED && (count <= RES_TPC * static_cast<int>(gridDim.x) || count > RES_PAGED_TPC * static_cast<int>(gridDim.x) ||
-                  static_cast<long long>(count) * PTILE_PAD > g.a.N))
+                  static_cast<long long>(count) * PTILE_PAD > g.a.N || g.a.N >= (1ll << 31)))
         return;
     if (blockIdx.x >= P) return;
     const bool scribe = blockIdx.x == 0 && tid == 0;
@@ -1894,6 +1923,9 @@ template <bool MG, bool PAGED> __global__ void __launch_bounds__(RNT, 1) pcgResi
     unsigned int validBits[RES];           // bit k: cell k of this thread lies inside the matrix
     unsigned long long preBits[RES];       // 4 x preInfo half-word
     double xacc[RES][RES_CELLS];
+    long long cell0[RES];                      // linear index of the thread's first cell of the tile (rows advance by rowStep)
+    const long long rowStep = 4 * J;
+    const int q0 = (lr + 1) * PSW + lc + 2, t0i = lr * TC + lc;  // the same cell inside the halo-extended box / the interior array
     bool remote = false;                       // (uniform over the CTA) a tile holds a slab-boundary row pushed to a neighbour
 #pragma unroll
     for (int t = 0; t < RES; t++)
@@ -1902,6 +1934,7 @@ template <bool MG, bool PAGED> __global__ void __launch_bounds__(RNT, 1) pcgResi
         ringPos[t] = -1;
         ringSrc[t] = 0;
         ringN[t] = -1;
+        cell0[t] = 0;
         rowBits[t] = 0;
         preBits[t] = 0;
         validBits[t] = 0;
@@ -1913,6 +1946,7 @@ template <bool MG, bool PAGED> __global__ void __launch_bounds__(RNT, 1) pcgResi
             const int ti = tile / g.a.tilesJ, tj = tile - ti * g.a.tilesJ;
             ti0[t] = ti * TR;
             tj0[t] = tj * TC;
+            cell0[t] = static_cast<long long>(ti0[t] + lr) * J + tj0[t] + lc;
             resRingCell(tid, ti0[t], tj0[t], I, J, N, &ringPos[t], &ringN[t]);
             if (MG && ringN[t] >= 0)
             {
@@ -1973,6 +2007,11 @@ template <bool MG, bool PAGED> __global__ void __launch_bounds__(RNT, 1) pcgResi
             const long long a = static_cast<long long>(blockIdx.x) + static_cast<long long>(RES + k) * P;
             const int tile = g.a.activeTiles[a];
             const int ti = tile / g.a.tilesJ, tj = tile - ti * g.a.tilesJ;
+            if (tid == 0)
+            {
+                sm.pagedI0[k] = ti * TR;
+                sm.pagedJ0[k] = tj * TC;
+            }
             for (int e = tid; e < PTILE_PAD; e += RNT)
             {
                 const int ar = e / PSW, c = e - ar * PSW;
@@ -2036,9 +2075,9 @@ template <bool MG, bool PAGED> __global__ void __launch_bounds__(RNT, 1) pcgResi
                     // cells outside the matrix stay zero; in an edge tile the slot right of the last valid column is the
                     // ring cell (wrap neighbour) and belongs to the ring thread
                     if (!((validBits[t] >> k) & 1u)) continue;
-                    const int row = lr + 4 * k, p = (row + 1) * PSW + lc + 2;
+                    const int p = q0 + k * 4 * PSW;
                     const double so = rt.S[p];
-                    rt.S[p] = __dadd_rn(rt.T[row * TC + lc], __dmul_rn(so, beta));
+                    rt.S[p] = __dadd_rn(rt.T[t0i + k * 4 * TC], __dmul_rn(so, beta));
                     xacc[t][k] = __dadd_rn(xacc[t][k], __dmul_rn(so, alphaPrev));
                 }
                 if (ringPos[t] >= 0) rt.S[ringPos[t]] = __dadd_rn(ringV[t], __dmul_rn(rt.S[ringPos[t]], beta));
@@ -2052,14 +2091,16 @@ template <bool MG, bool PAGED> __global__ void __launch_bounds__(RNT, 1) pcgResi
 #pragma unroll
                 for (int k = 0; k < RES_CELLS; k++)
                 {
-                    const int row = lr + 4 * k, p = (row + 1) * PSW + lc + 2;
-                    const long long gi = ti0[t] + row, gj = tj0[t] + lc;
-                    if (gi < I && gj < J)
+                    const int p = q0 + k * 4 * PSW;
+                    if ((validBits[t] >> k) & 1u)
                     {
-                        const long long n = gi * J + gj;
+                        const long long n = cell0[t] + k * rowStep;
+                        const long long gi = ti0[t] + lr + 4 * k, gj = tj0[t] + lc;  // slab-boundary tests only (MG)
+                        (void)gi;
+                        (void)gj;
                         const double c = rt.S[p];
                         const double o = rowA(static_cast<uint8_t>(rowBits[t] >> (8 * k)), g.a.scale, c, rt.S[p - PSW], rt.S[p + PSW], rt.S[p - 1], rt.S[p + 1]);
-                        rt.T[row * TC + lc] = o;
+                        rt.T[t0i + k * 4 * TC] = o;
                         g.q[n] = o;
                         if (MG && !(mg.debug & 2))
                         {
@@ -2087,32 +2128,31 @@ template <bool MG, bool PAGED> __global__ void __launch_bounds__(RNT, 1) pcgResi
         if (scribe) mgStampAt(mg, 2 * i + 1, 1);
         if (PAGED)
         {
+            // 32-bit indices and kernel-invariant offsets throughout: the paged tiles are bound by instruction issue
+            const int J32 = static_cast<int>(J), N32 = static_cast<int>(N), rowStep = 4 * J32;
+            const int q0 = (lr + 1) * PSW + lc + 2;
             for (int k = 0; k < nPaged; k++)
             {
                 const long long a = static_cast<long long>(blockIdx.x) + static_cast<long long>(RES + k) * P;
-                const int tile = g.a.activeTiles[a];
-                const int ti = tile / g.a.tilesJ, tj = tile - ti * g.a.tilesJ;
-                const int i0 = ti * TR, j0 = tj * TC;
+                const int i0 = sm.pagedI0[k], j0 = sm.pagedJ0[k];
                 double *box = pb ? scratch1 : scratch0;
                 // operands from global memory: z and x of the thread's cells, the ring value of the neighbours' z
+                const int row0 = i0 + lr, col = j0 + lc;
+                const int n0 = row0 * J32 + col;
+                const bool colOk = col < J32;
                 double zv[RES_CELLS], xv[RES_CELLS];
-                unsigned int rb = 0;
+                unsigned int info[RES_CELLS];
 #pragma unroll
                 for (int c = 0; c < RES_CELLS; c++)
                 {
-                    const long long gi = i0 + lr + 4 * c, gj = j0 + lc;
-                    zv[c] = xv[c] = 0.0;
-                    if (gi < I && gj < J)
-                    {
-                        const long long n = gi * J + gj;
-                        zv[c] = __ldcg(g.z + n);
-                        xv[c] = __ldcg(g.x + n);
-                        rb |= static_cast<unsigned int>(g.a.rowInfo[n]) << (8 * c);
-                    }
+                    const bool ok = colOk && row0 + 4 * c < I;
+                    const int n = n0 + c * rowStep;
+                    zv[c] = ok ? __ldcg(g.z + n) : 0.0;
+                    xv[c] = ok ? __ldcg(g.x + n) : 0.0;
+                    info[c] = ok ? static_cast<unsigned int>(g.a.rowInfo[n]) : 0u;
                 }
-                int rpos;
-                long long rn;
-                resRingCell(tid, i0, j0, I, J, N, &rpos, &rn);
+                int rpos, rn;
+                resRingCell32(tid, i0, j0, I, J32, N32, &rpos, &rn);
                 const double rv = rn >= 0 ? __ldcg(g.z + rn) : 0.0;
                 if (tid == 0 && k + 1 < nPaged)
                 {
@@ -2126,31 +2166,25 @@ template <bool MG, bool PAGED> __global__ void __launch_bounds__(RNT, 1) pcgResi
                 if (pb) use1++; else use0++;
 #pragma unroll
                 for (int c = 0; c < RES_CELLS; c++)
-                {
-                    const long long gi = i0 + lr + 4 * c, gj = j0 + lc;
-                    if (gi < I && gj < J)
+                    if (colOk && row0 + 4 * c < I)
                     {
-                        const int q = (lr + 4 * c + 1) * PSW + lc + 2;
+                        const int q = q0 + c * 4 * PSW;
                         const double so = box[q];
                         box[q] = __dadd_rn(zv[c], __dmul_rn(so, beta));
-                        g.x[gi * J + gj] = __dadd_rn(xv[c], __dmul_rn(so, alphaPrev));
+                        g.x[n0 + c * rowStep] = __dadd_rn(xv[c], __dmul_rn(so, alphaPrev));
                     }
-                }
                 if (rpos >= 0) box[rpos] = __dadd_rn(rv, __dmul_rn(box[rpos], beta));
                 __syncthreads();
 #pragma unroll
                 for (int c = 0; c < RES_CELLS; c++)
-                {
-                    const long long gi = i0 + lr + 4 * c, gj = j0 + lc;
-                    if (gi < I && gj < J)
+                    if (colOk && row0 + 4 * c < I)
                     {
-                        const int q = (lr + 4 * c + 1) * PSW + lc + 2;
+                        const int q = q0 + c * 4 * PSW;
                         const double cv = box[q];
-                        const double o = rowA(static_cast<uint8_t>(rb >> (8 * c)), g.a.scale, cv, box[q - PSW], box[q + PSW], box[q - 1], box[q + 1]);
-                        g.q[gi * J + gj] = o;
+                        const double o = rowA(static_cast<uint8_t>(info[c]), g.a.scale, cv, box[q - PSW], box[q + PSW], box[q - 1], box[q + 1]);
+                        g.q[n0 + c * rowStep] = o;
                         accDot += o * cv;
                     }
-                }
                 fenceProxyAsync();
                 __syncthreads();
                 if (tid == 0) bulkStore(boxS + a * PTILE_PAD, box, RES_BOX_BYTES);
@@ -2203,8 +2237,8 @@ template <bool MG, bool PAGED> __global__ void __launch_bounds__(RNT, 1) pcgResi
                 for (int k = 0; k < RES_CELLS; k++)
                 {
                     if (!((validBits[t] >> k) & 1u)) continue;
-                    const int row = lr + 4 * k, p = (row + 1) * PSW + lc + 2;
-                    rt.R[p] = __dsub_rn(rt.R[p], __dmul_rn(rt.T[row * TC + lc], alpha));
+                    const int p = q0 + k * 4 * PSW;
+                    rt.R[p] = __dsub_rn(rt.R[p], __dmul_rn(rt.T[t0i + k * 4 * TC], alpha));
                 }
                 if (ringPos[t] >= 0) rt.R[ringPos[t]] = __dsub_rn(rt.R[ringPos[t]], __dmul_rn(ringV[t], alpha));
             }
@@ -2217,14 +2251,16 @@ template <bool MG, bool PAGED> __global__ void __launch_bounds__(RNT, 1) pcgResi
 #pragma unroll
                 for (int k = 0; k < RES_CELLS; k++)
                 {
-                    const int row = lr + 4 * k, p = (row + 1) * PSW + lc + 2;
-                    const long long gi = ti0[t] + row, gj = tj0[t] + lc;
-                    if (gi < I && gj < J)
+                    const int p = q0 + k * 4 * PSW;
+                    if ((validBits[t] >> k) & 1u)
                     {
-                        const long long n = gi * J + gj;
+                        const long long n = cell0[t] + k * rowStep;
+                        const long long gi = ti0[t] + lr + 4 * k, gj = tj0[t] + lc;  // slab-boundary tests only (MG)
+                        (void)gi;
+                        (void)gj;
                         const double c = rt.R[p];
                         const double o = rowM(static_cast<uint16_t>(preBits[t] >> (16 * k)), sm.preTbl, c, rt.R[p - PSW], rt.R[p + PSW], rt.R[p - 1], rt.R[p + 1]);
-                        rt.T[row * TC + lc] = o;
+                        rt.T[t0i + k * 4 * TC] = o;
                         g.z[n] = o;
                         if (MG && !(mg.debug & 2))
                         {
@@ -2251,30 +2287,28 @@ template <bool MG, bool PAGED> __global__ void __launch_bounds__(RNT, 1) pcgResi
         if (scribe) mgStampAt(mg, 2 * i + 2, 1);
         if (PAGED)
         {
+            const int J32 = static_cast<int>(J), N32 = static_cast<int>(N), rowStep = 4 * J32;
+            const int q0 = (lr + 1) * PSW + lc + 2;
             for (int k = 0; k < nPaged; k++)
             {
                 const long long a = static_cast<long long>(blockIdx.x) + static_cast<long long>(RES + k) * P;
-                const int tile = g.a.activeTiles[a];
-                const int ti = tile / g.a.tilesJ, tj = tile - ti * g.a.tilesJ;
-                const int i0 = ti * TR, j0 = tj * TC;
+                const int i0 = sm.pagedI0[k], j0 = sm.pagedJ0[k];
                 double *box = pb ? scratch1 : scratch0;
+                const int row0 = i0 + lr, col = j0 + lc;
+                const int n0 = row0 * J32 + col;
+                const bool colOk = col < J32;
                 double qv[RES_CELLS];
-                unsigned long long pbits = 0;
+                unsigned int info[RES_CELLS];
 #pragma unroll
                 for (int c = 0; c < RES_CELLS; c++)
                 {
-                    const long long gi = i0 + lr + 4 * c, gj = j0 + lc;
-                    qv[c] = 0.0;
-                    if (gi < I && gj < J)
-                    {
-                        const long long n = gi * J + gj;
-                        qv[c] = __ldcg(g.q + n);
-                        pbits |= static_cast<unsigned long long>(g.a.preInfo[n]) << (16 * c);
-                    }
+                    const bool ok = colOk && row0 + 4 * c < I;
+                    const int n = n0 + c * rowStep;
+                    qv[c] = ok ? __ldcg(g.q + n) : 0.0;
+                    info[c] = ok ? static_cast<unsigned int>(g.a.preInfo[n]) : 0u;
                 }
-                int rpos;
-                long long rn;
-                resRingCell(tid, i0, j0, I, J, N, &rpos, &rn);
+                int rpos, rn;
+                resRingCell32(tid, i0, j0, I, J32, N32, &rpos, &rn);
                 const double rv = rn >= 0 ? __ldcg(g.q + rn) : 0.0;
                 if (tid == 0 && k + 1 < nPaged)
                 {
@@ -2286,30 +2320,24 @@ template <bool MG, bool PAGED> __global__ void __launch_bounds__(RNT, 1) pcgResi
                 if (pb) use1++; else use0++;
 #pragma unroll
                 for (int c = 0; c < RES_CELLS; c++)
-                {
-                    const long long gi = i0 + lr + 4 * c, gj = j0 + lc;
-                    if (gi < I && gj < J)
+                    if (colOk && row0 + 4 * c < I)
                     {
-                        const int q = (lr + 4 * c + 1) * PSW + lc + 2;
+                        const int q = q0 + c * 4 * PSW;
                         box[q] = __dsub_rn(box[q], __dmul_rn(qv[c], alpha));
                     }
-                }
                 if (rpos >= 0) box[rpos] = __dsub_rn(box[rpos], __dmul_rn(rv, alpha));
                 __syncthreads();
 #pragma unroll
                 for (int c = 0; c < RES_CELLS; c++)
-                {
-                    const long long gi = i0 + lr + 4 * c, gj = j0 + lc;
-                    if (gi < I && gj < J)
+                    if (colOk && row0 + 4 * c < I)
                     {
-                        const int q = (lr + 4 * c + 1) * PSW + lc + 2;
+                        const int q = q0 + c * 4 * PSW;
                         const double cv = box[q];
-                        const double o = rowM(static_cast<uint16_t>(pbits >> (16 * c)), sm.preTbl, cv, box[q - PSW], box[q + PSW], box[q - 1], box[q + 1]);
-                        g.z[gi * J + gj] = o;
+                        const double o = rowM(static_cast<uint16_t>(info[c]), sm.preTbl, cv, box[q - PSW], box[q + PSW], box[q - 1], box[q + 1]);
+                        g.z[n0 + c * rowStep] = o;
                         accDot += o * cv;
                         accMax = fmax(accMax, fabs(cv));
                     }
-                }
                 fenceProxyAsync();
                 __syncthreads();
                 if (tid == 0) bulkStore(boxR + a * PTILE_PAD, box, RES_BOX_BYTES);
@@ -2392,13 +2420,12 @@ template <bool MG, bool PAGED> __global__ void __launch_bounds__(RNT, 1) pcgResi
 #pragma unroll
             for (int k = 0; k < RES_CELLS; k++)
             {
-                const int row = lr + 4 * k, p = (row + 1) * PSW + lc + 2;
-                const long long gi = ti0[t] + row, gj = tj0[t] + lc;
-                if (gi < I && gj < J)
+                const int p = q0 + k * 4 * PSW;
+                if ((validBits[t] >> k) & 1u)
                 {
                     double xv = xacc[t][k];
                     if (executed > 0) xv = __dadd_rn(xv, __dmul_rn(rt.S[p], alpha));
-                    g.x[gi * J + gj] = xv;
+                    g.x[cell0[t] + k * rowStep] = xv;
                 }
             }
         }
@@ -2995,7 +3022,7 @@ int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
     if (whole && active && ctx->residentPcg)
     {
         residentLimit = RES_TPC * resBlocks;
-        if (!mgOn && ctx->pagedPcg)
+        if (!mgOn && ctx->pagedPcg && ctx->N < (1ll << 31))
             residentLimit = static_cast<int>(std::max<long long>(residentLimit, std::min<long long>(static_cast<long long>(RES_PAGED_TPC) * resBlocks, ctx->N / PTILE_PAD)));
     }
     bool initLight = residentLimit > 0;
