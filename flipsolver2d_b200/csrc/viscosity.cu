@@ -52,7 +52,43 @@ struct ViscArgs
     double *partials;
     ViscScalars *sc;
     long long maxIters;
+    const int *box;  // {iMin, iMax, jMin, jMax} of the cells with a non-zero right-hand side or viscosity (viscBoxKernel)
 };
+
+// The rows of the system outside the box B of cells with a non-zero right-hand side or a non-zero viscosity are identity
+// rows with b = 0, and so are their couplings: their r, p, z and x stay exactly zero in Eigen's CG (a solid cell next to
+// a viscous one has a non-zero coupling -- it lies within one cell of B). The solve therefore runs on B grown by one
+// cell and keeps zeros on a second ring for the operator to read; everything outside contributes exact zeros to the dot
+// products and keeps its (zero) velocity. At 4096^2 the box of the narrow-band dam break is 9 % of the grid.
+struct ViscBox
+{
+    int i0, j0, h, w;  // first row / column, rows, columns
+    __device__ __forceinline__ long long cells() const { return static_cast<long long>(h) * w; }
+};
+
+__device__ __forceinline__ ViscBox viscBox(const ViscArgs &a, int grow)
+{
+    ViscBox b;
+    const int iMin = a.box[0], iMax = a.box[1], jMin = a.box[2], jMax = a.box[3];
+    if (iMax < iMin)
+    {
+        b.i0 = b.j0 = b.h = b.w = 0;
+        return b;
+    }
+    b.i0 = max(iMin - grow, 0);
+    b.j0 = max(jMin - grow, 0);
+    b.h = min(iMax + grow, a.I - 1) - b.i0 + 1;
+    b.w = min(jMax + grow, a.J - 1) - b.j0 + 1;
+    return b;
+}
+
+// cell t of the box -> (i, j); the boxes of the grids this runs on have fewer than 2^32 cells
+__device__ __forceinline__ void viscCell(const ViscBox &b, long long t, int *i, int *j)
+{
+    const unsigned int q = static_cast<unsigned int>(t) / static_cast<unsigned int>(b.w);
+    *i = b.i0 + static_cast<int>(q);
+    *j = b.j0 + static_cast<int>(static_cast<unsigned int>(t) - q * static_cast<unsigned int>(b.w));
+}
 
 __device__ __forceinline__ double warpSum(double v)
 {
@@ -112,6 +148,13 @@ __device__ bool gridSum2(double &a, double &b, double *partials, unsigned int *t
     return true;
 }
 
+// n / J: a 32-bit division whenever the grid allows it (the 64-bit one is ~100 instructions and was most of the
+// per-cell work of these streaming kernels)
+__device__ __forceinline__ long long rowOf(long long n, long long J, long long N)
+{
+    return N <= 0x7fffffffll ? static_cast<long long>(static_cast<unsigned int>(n) / static_cast<unsigned int>(J)) : n / J;
+}
+
 __device__ __forceinline__ double diagAt(const ViscArgs &a, long long n)
 {
     if (matSolid(a.material[n])) return 1.0;
@@ -142,6 +185,43 @@ __device__ __forceinline__ double applyRow(const ViscArgs &a, const double *__re
     return y;
 }
 
+__global__ void viscBoxResetKernel(int *box)
+{
+    box[0] = 0x7fffffff;
+    box[1] = -1;
+    box[2] = 0x7fffffff;
+    box[3] = -1;
+}
+
+// Bounding box of the cells whose right-hand side (density * field, zero exactly when the field is) or viscosity is not zero.
+__global__ void __launch_bounds__(NT) viscBoxKernel(const float *__restrict__ field, int fieldStride, const float *__restrict__ mu, int I, int J,
+                                                    int *__restrict__ box)
+{
+    // a CTA takes whole rows, its threads stride over the columns (no index division)
+    int iMin = 0x7fffffff, iMax = -1, jMin = 0x7fffffff, jMax = -1;
+    for (int i = blockIdx.x; i < I; i += gridDim.x)
+        for (int j = threadIdx.x; j < J; j += NT)
+            if (field[static_cast<long long>(i) * fieldStride + j] != 0.f || mu[static_cast<long long>(i) * J + j] != 0.f)
+            {
+                iMin = min(iMin, i);
+                iMax = max(iMax, i);
+                jMin = min(jMin, j);
+                jMax = max(jMax, j);
+            }
+    if (!__any_sync(0xffffffffu, iMax >= 0)) return;
+    iMin = __reduce_min_sync(0xffffffffu, iMin);
+    iMax = __reduce_max_sync(0xffffffffu, iMax);
+    jMin = __reduce_min_sync(0xffffffffu, jMin);
+    jMax = __reduce_max_sync(0xffffffffu, jMax);
+    if ((threadIdx.x & 31) == 0)
+    {
+        atomicMin(box + 0, iMin);
+        atomicMax(box + 1, iMax);
+        atomicMin(box + 2, jMin);
+        atomicMax(box + 3, jMax);
+    }
+}
+
 // rhs = density * field (float product, viscositymodel.cpp:140-150); x = 0; r = rhs; p = r / diag;
 // rhsNorm2 = |rhs|^2, absNew = r.p; zero / already-converged exits of Eigen's conjugate_gradient.
 __global__ void __launch_bounds__(NT) viscInitKernel(ViscArgs a, const float *__restrict__ field, int fieldStride, float density)
@@ -149,10 +229,13 @@ __global__ void __launch_bounds__(NT) viscInitKernel(ViscArgs a, const float *__
     __shared__ double scratch[16];
     __shared__ int isLast;
     double s0 = 0.0, s1 = 0.0;
-    for (long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x; n < a.N; n += static_cast<long long>(gridDim.x) * NT)
+    const ViscBox bx = viscBox(a, 2);
+    for (long long t = blockIdx.x * static_cast<long long>(NT) + threadIdx.x; t < bx.cells(); t += static_cast<long long>(gridDim.x) * NT)
     {
-        const long long i = n / a.J, j = n - i * a.J;
-        const double b = static_cast<double>(__fmul_rn(density, field[i * fieldStride + j]));
+        int i, j;
+        viscCell(bx, t, &i, &j);
+        const long long n = static_cast<long long>(i) * a.J + j;
+        const double b = static_cast<double>(__fmul_rn(density, field[static_cast<long long>(i) * fieldStride + j]));
         a.x[n] = 0.0;
         a.r[n] = b;
         const double p = b * (1.0 / diagAt(a, n));  // DiagonalPreconditioner: m_invdiag(j) * b(j)
@@ -182,9 +265,12 @@ __global__ void __launch_bounds__(NT) viscApplyKernel(ViscArgs a)
     __shared__ int isLast;
     if (a.sc->done) return;
     double s0 = 0.0, s1 = 0.0;
-    for (long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x; n < a.N; n += static_cast<long long>(gridDim.x) * NT)
+    const ViscBox bx = viscBox(a, 1);
+    for (long long t = blockIdx.x * static_cast<long long>(NT) + threadIdx.x; t < bx.cells(); t += static_cast<long long>(gridDim.x) * NT)
     {
-        const int i = static_cast<int>(n / a.J), j = static_cast<int>(n - static_cast<long long>(i) * a.J);
+        int i, j;
+        viscCell(bx, t, &i, &j);
+        const long long n = static_cast<long long>(i) * a.J + j;
         const double y = applyRow(a, a.p, i, j);
         a.tmp[n] = y;
         s0 += a.p[n] * y;
@@ -205,8 +291,12 @@ __global__ void __launch_bounds__(NT) viscUpdateKernel(ViscArgs a)
     if (a.sc->done) return;
     const double alpha = a.sc->alpha;
     double s0 = 0.0, s1 = 0.0;
-    for (long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x; n < a.N; n += static_cast<long long>(gridDim.x) * NT)
+    const ViscBox bx = viscBox(a, 1);
+    for (long long t = blockIdx.x * static_cast<long long>(NT) + threadIdx.x; t < bx.cells(); t += static_cast<long long>(gridDim.x) * NT)
     {
+        int i, j;
+        viscCell(bx, t, &i, &j);
+        const long long n = static_cast<long long>(i) * a.J + j;
         a.x[n] += alpha * a.p[n];
         const double r = a.r[n] - alpha * a.tmp[n];
         a.r[n] = r;
@@ -238,17 +328,25 @@ __global__ void __launch_bounds__(NT) viscDirectionKernel(ViscArgs a)
 {
     if (a.sc->done) return;
     const double beta = a.sc->beta;
-    for (long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x; n < a.N; n += static_cast<long long>(gridDim.x) * NT)
+    const ViscBox bx = viscBox(a, 1);
+    for (long long t = blockIdx.x * static_cast<long long>(NT) + threadIdx.x; t < bx.cells(); t += static_cast<long long>(gridDim.x) * NT)
+    {
+        int i, j;
+        viscCell(bx, t, &i, &j);
+        const long long n = static_cast<long long>(i) * a.J + j;
         a.p[n] = a.z[n] + beta * a.p[n];
+    }
 }
 
 // field(i, j) = x / density (viscositymodel.cpp:152-162)
 __global__ void __launch_bounds__(NT) viscWriteBackKernel(ViscArgs a, float *__restrict__ field, int fieldStride, float density)
 {
-    for (long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x; n < a.N; n += static_cast<long long>(gridDim.x) * NT)
+    const ViscBox bx = viscBox(a, 1);
+    for (long long t = blockIdx.x * static_cast<long long>(NT) + threadIdx.x; t < bx.cells(); t += static_cast<long long>(gridDim.x) * NT)
     {
-        const long long i = n / a.J, j = n - i * a.J;
-        field[i * fieldStride + j] = static_cast<float>(a.x[n] / static_cast<double>(density));
+        int i, j;
+        viscCell(bx, t, &i, &j);
+        field[static_cast<long long>(i) * fieldStride + j] = static_cast<float>(a.x[static_cast<long long>(i) * a.J + j] / static_cast<double>(density));
     }
 }
 
@@ -481,8 +579,12 @@ static int viscSolve(Ctx *ctx, ViscArgs &a, float *field, int stride, float dens
 {
     cudaStream_t st = ctx->stream;
     const int blocks = std::min<long long>(divUp(ctx->N, NT), static_cast<long long>(ctx->smCount) * 8);
+    int *box = reinterpret_cast<int *>(static_cast<unsigned char *>(ctx->viscScalars) + 128);
+    viscBoxResetKernel<<<1, 1, 0, st>>>(box);
+    viscBoxKernel<<<std::min(ctx->I, ctx->smCount * 8), NT, 0, st>>>(field, stride, a.mu, ctx->I, ctx->J, box);
+    a.box = box;
     viscInitKernel<<<blocks, NT, 0, st>>>(a, field, stride, density);
-    ctx->launches++;
+    ctx->launches += 3;
     ViscScalars sc;
     const int batch = 8;
     for (;;)
