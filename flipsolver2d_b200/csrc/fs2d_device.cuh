@@ -17,6 +17,15 @@ __device__ __forceinline__ float fmulr(float a, float b) { return __fmul_rn(a, b
 __device__ __forceinline__ float faddr(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float fsubr(float a, float b) { return __fsub_rn(a, b); }
 
+// n / J for a linear cell index: one 32-bit division whenever the index allows it (every grid up to 65536^2 cells... in
+// practice always); the 64-bit division the plain expression compiles to is a ~100-instruction routine and made the
+// streaming grid kernels instruction-bound.
+__device__ __forceinline__ int rowOfCell(long long n, int J)
+{
+    return static_cast<unsigned long long>(n) <= 0xffffffffull ? static_cast<int>(static_cast<unsigned int>(n) / static_cast<unsigned int>(J))
+                                                                 : static_cast<int>(n / J);
+}
+
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // MaterialGrid is OOB_EXTEND (materialgrid.cpp:5-8): out-of-domain look-ups replicate the border.

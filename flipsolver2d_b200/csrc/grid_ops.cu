@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(NT) buildMatrixKernel(const int8_t *__restrict
     const long long N = static_cast<long long>(I) * J;
     const long long n = nBegin + blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
     if (n >= nEnd) return;
-    const int i = static_cast<int>(n / J), j = static_cast<int>(n - static_cast<long long>(i) * J);
+    const int i = rowOfCell(n, J), j = static_cast<int>(n - static_cast<long long>(i) * J);
     const int8_t m = mat[n];
     const bool hasRow = smokeRows ? !matSolid(m) : matFluid(m);
     if (!hasRow)
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(NT) afterTransferKernel(const int8_t *__restri
 {
     const long long n = nBegin + blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
     if (n >= nEnd || !matSource(mat[n])) return;
-    const int i = static_cast<int>(n / J), j = static_cast<int>(n - static_cast<long long>(i) * J);
+    const int i = rowOfCell(n, J), j = static_cast<int>(n - static_cast<long long>(i) * J);
     const fs2d_source s = sources[emitterId[n]];
     viscosity[n] = s.viscosity;
     if (s.transfer_velocity)
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(NT) bfsInitKernel(const uint8_t *__restrict__ 
         marker[n] = v ? 0 : 255;
         if (v)
         {
-            i = static_cast<int>(n / J);
+            i = rowOfCell(n, J);
             j = static_cast<int>(n - static_cast<long long>(i) * J);
         }
     }
@@ -227,7 +227,7 @@ __device__ __forceinline__ void bfsLayerSampleAt(float *__restrict__ g, uint8_t 
 __device__ __forceinline__ void bfsLayerSample(float *__restrict__ g, uint8_t *__restrict__ valid, uint8_t *__restrict__ marker,
                                                int sI, int sJ, long long n, int k)
 {
-    const int i = static_cast<int>(n / sJ);
+    const int i = rowOfCell(n, sJ);
     bfsLayerSampleAt(g, valid, marker, sI, sJ, i, static_cast<int>(n - static_cast<long long>(i) * sJ), k);
 }
 
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(NT) bfsLayerKernel(float *U, float *V, uint8_t
     if (t >= 2 * box) return;
     const bool second = t >= box;
     const long long q = second ? t - box : t;
-    const int i = i0 + static_cast<int>(q / w), j = j0 + static_cast<int>(q % w);
+    const int i = i0 + rowOfCell(q, w), j = j0 + static_cast<int>(q % w);
     if (!second)
     {
         if (i <= I && j < J) bfsLayerSample(U, uValid, marker, I + 1, J, static_cast<long long>(i) * J + j, k);
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(NT) bfsInitVecKernel(const uint8_t *__restrict
                     if (!((words[b >> 2] >> (8 * (b & 3))) & 0xffu))
                     {
                         const unsigned int q = n + b;
-                        const int i = static_cast<int>(q / sJ), j = static_cast<int>(q - static_cast<unsigned int>(i) * sJ);
+                        const int i = rowOfCell(q, sJ), j = static_cast<int>(q - static_cast<unsigned int>(i) * sJ);
                         iMin = min(iMin, i);
                         iMax = max(iMax, i);
                         jMin = min(jMin, j);
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(NT) bfsInitVecKernel(const uint8_t *__restrict
                 dst[q] = valid ? 0 : 255;
                 if (valid)
                 {
-                    const int i = static_cast<int>(q / sJ), j = static_cast<int>(q - static_cast<unsigned int>(i) * sJ);
+                    const int i = rowOfCell(q, sJ), j = static_cast<int>(q - static_cast<unsigned int>(i) * sJ);
                     iMin = min(iMin, i);
                     iMax = max(iMax, i);
                     jMin = min(jMin, j);
@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(NT) sdfFirstLayerKernel(int32_t *__restrict__ 
     const long long n = static_cast<long long>(rowLo) * J + blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
     if (n >= static_cast<long long>(rowHi) * J) return;
     if (marker[n] == 0) return;
-    const int i = static_cast<int>(n / J), j = static_cast<int>(n - static_cast<long long>(i) * J);
+    const int i = rowOfCell(n, J), j = static_cast<int>(n - static_cast<long long>(i) * J);
     bool hit = false;
 #pragma unroll
     for (int di = -1; di <= 1; di++)
@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(BFS_THREADS) sdfExtrapolateKernel(float *sdf, 
             const unsigned int t = t0 + (threadIdx.x & 31u);
             const bool valid = t < end;
             const long long n = valid ? queue[t] : 0;
-            const int i = static_cast<int>(n / J), j = static_cast<int>(n - static_cast<long long>(i) * J);
+            const int i = rowOfCell(n, J), j = static_cast<int>(n - static_cast<long long>(i) * J);
             // markers and values of all eight neighbours in flight together; the values of cells that turn out not to
             // be in a lower layer are simply not used
             int m[8];
@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(NT) smokeBodyForceKernel(float *__restrict__ U
     const long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
     if (n < NU)
     {
-        const int i = static_cast<int>(n / J), j = static_cast<int>(n - static_cast<long long>(i) * J);
+        const int i = rowOfCell(n, J), j = static_cast<int>(n - static_cast<long long>(i) * J);
         const float x = static_cast<float>(i), y = faddr(static_cast<float>(j), 0.5f);
         const float td = fsubr(gridLerp(temperature, x, y), ambient);
         const float c = gridLerp(concentration, x, y);
@@ -600,7 +600,7 @@ __global__ void __launch_bounds__(NT) pressureRhsKernel(const float *__restrict_
 {
     const long long n = nBegin + blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
     if (n >= nEnd) return;
-    const int i = static_cast<int>(n / J), j = static_cast<int>(n - static_cast<long long>(i) * J);
+    const int i = rowOfCell(n, J), j = static_cast<int>(n - static_cast<long long>(i) * J);
     const int8_t m = mat[n];
     const bool row = smokeRows ? !matSolid(m) : matFluid(m);
     if (!row)
@@ -650,7 +650,7 @@ __global__ void __launch_bounds__(NT) applyPressureKernel(const double *__restri
 {
     const long long n = nBegin + blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
     if (n >= nEnd) return;
-    const int i = static_cast<int>(n / J), j = static_cast<int>(n - static_cast<long long>(i) * J);
+    const int i = rowOfCell(n, J), j = static_cast<int>(n - static_cast<long long>(i) * J);
     const double pc = p[n];
     const int8_t mc = mat[n];
     {
@@ -697,7 +697,7 @@ __global__ void __launch_bounds__(NT) solidFrictionKernel(const int32_t *__restr
 {
     const long long n = nBegin + blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
     if (n >= nEnd) return;
-    const int i = static_cast<int>(n / J), j = static_cast<int>(n - static_cast<long long>(i) * J);
+    const int i = rowOfCell(n, J), j = static_cast<int>(n - static_cast<long long>(i) * J);
     float avg = 0.f;
     int cnt = 0;
     for (int di = -1; di <= 1; di++)
@@ -732,7 +732,7 @@ __global__ void __launch_bounds__(NT) eulerAdvectKernel(GridView in, VelocityVie
 {
     const long long n = nBegin + blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
     if (n >= (nEnd >= 0 ? nEnd : static_cast<long long>(in.sizeI) * in.sizeJ)) return;
-    const int i = static_cast<int>(n / in.sizeJ), j = static_cast<int>(n - static_cast<long long>(i) * in.sizeJ);
+    const int i = rowOfCell(n, in.sizeJ), j = static_cast<int>(n - static_cast<long long>(i) * in.sizeJ);
     const float2 prev = rk4(vel, make_float2(static_cast<float>(i), static_cast<float>(j)), -dt);
     out[n] = gridLerp(in, prev.x, prev.y);
 }
@@ -770,7 +770,7 @@ __global__ void __launch_bounds__(NT) nbCombineKernel(GridView fluidSdf, int I, 
     if (n < NU)
     {
         const long long g = n + static_cast<long long>(rowLo) * J;
-        const int i = static_cast<int>(g / J), j = static_cast<int>(g - static_cast<long long>(i) * J);
+        const int i = rowOfCell(g, J), j = static_cast<int>(g - static_cast<long long>(i) * J);
         const float sdf = gridLerp(fluidSdf, static_cast<float>(i), faddr(0.5f, static_cast<float>(j)));
         if (!(sdf > band)) U[g] = advU[g];
     }
@@ -784,7 +784,7 @@ __global__ void __launch_bounds__(NT) nbCombineKernel(GridView fluidSdf, int I, 
     else if (n < NU + NV + N)
     {
         const long long m = n - NU - NV + static_cast<long long>(rowLo) * J;
-        const int i = static_cast<int>(m / J), j = static_cast<int>(m - static_cast<long long>(i) * J);
+        const int i = rowOfCell(m, J), j = static_cast<int>(m - static_cast<long long>(i) * J);
         // Vec3(0.5f + i, j + 0.5): the second component is evaluated in double and narrowed
         const float sdf = gridLerp(fluidSdf, faddr(0.5f, static_cast<float>(i)), static_cast<float>(static_cast<double>(j) + 0.5));
         if (!(sdf > band)) viscosity[m] = advViscosity[m];

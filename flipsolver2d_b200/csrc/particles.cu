@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(NT) densityAdjustKernel(float2 *__restrict__ p
     const int2 nb = positionBin(x);
     const unsigned int m = mis[p];
     if ((ob.x != nb.x || ob.y != nb.y) && m != FS2D_MIS_LOST)
-        mis[p] = static_cast<uint8_t>(storageCode(static_cast<int>(m / 5u) - 2 + ob.x - nb.x, static_cast<int>(m % 5u) - 2 + ob.y - nb.y));
+        mis[p] = static_cast<uint8_t>(storageCode(rowOfCell(m, 5u) - 2 + ob.x - nb.x, static_cast<int>(m % 5u) - 2 + ob.y - nb.y));
 }
 
 // countParticles (flipsolver2d.cpp:1021-1051): per-cell count, particles beyond 2*ppc die.
@@ -486,7 +486,7 @@ __global__ void __launch_bounds__(NT) reseedApplyKernel(const int32_t *__restric
     if (c >= N) return;
     const int32_t b = offset[c], e = offset[c + 1];
     if (e == b) return;
-    const int i = static_cast<int>(c / a.J), j = static_cast<int>(c - static_cast<long long>(i) * a.J);
+    const int i = rowOfCell(c, a.J), j = static_cast<int>(c - static_cast<long long>(i) * a.J);
     const bool src = matSource(mat[c]);
     // a SOURCE cell without a (valid) emitter -- a material grid uploaded through the C ABI without its emitter grid --
     // behaves like an emitter with zero velocity / viscosity instead of indexing the table out of bounds
@@ -999,7 +999,7 @@ __global__ void __launch_bounds__(NT) getStorageBinsKernel(const float2 *__restr
     if (p >= count) return;
     const int2 pb = positionBin(pos[p]);
     const unsigned int m = mis[p];
-    bins[p] = m == FS2D_MIS_LOST ? -1 : (pb.x + static_cast<int>(m / 5u) - 2) * binsJ + pb.y + static_cast<int>(m % 5u) - 2;
+    bins[p] = m == FS2D_MIS_LOST ? -1 : (pb.x + rowOfCell(m, 5u) - 2) * binsJ + pb.y + static_cast<int>(m % 5u) - 2;
 }
 }  // namespace
 

@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(256) densityBackgroundKernel(const int8_t *__r
 {
     const long long n = nBegin + blockIdx.x * 256ll + threadIdx.x;
     if (n >= nEnd) return;
-    const int i = static_cast<int>(n / J), j = static_cast<int>(n - static_cast<long long>(i) * J);
+    const int i = rowOfCell(n, J), j = static_cast<int>(n - static_cast<long long>(i) * J);
     density[n] = densityClamp(mat, I, J, i, j, __fdiv_rn(0.f, cellVolume), restDensity);
 }
 
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(256) sdfKernel(const int32_t *__restrict__ cel
     const long long n = nBegin + blockIdx.x * 256ll + threadIdx.x;
     const bool valid = n < nEnd;
     const long long nc = valid ? n : nEnd - 1;
-    const int i = static_cast<int>(nc / J), j = static_cast<int>(nc - static_cast<long long>(i) * J);
+    const int i = rowOfCell(nc, J), j = static_cast<int>(nc - static_cast<long long>(i) * J);
     const int bi = i / 3, bj = j / 3;
     const int iLo = max(3 * (bi - 2), 0), iHi = min(3 * (bi + 2) + 2, I - 1);
     const int jLo = max(3 * (bj - 2), 0), jHi = min(3 * (bj + 2) + 2, J - 1);

@@ -400,7 +400,7 @@ __device__ __forceinline__ double heavyDiag(const HeavyArgs &a, long long row)
     double d = static_cast<double>(a.rho);
     if (row < a.NU)
     {
-        const int i = static_cast<int>(row / a.J), j = static_cast<int>(row - static_cast<long long>(i) * a.J);
+        const int i = rowOfCell(row, a.J), j = static_cast<int>(row - static_cast<long long>(i) * a.J);
         if (uval(a, i - 1, j)) d += heavyT(a, i - 1, j);
         if (uval(a, i + 1, j)) d += heavyT(a, i, j);
         if (uval(a, i, j - 1) && vval(a, i, j) && vval(a, i - 1, j)) d += heavyC(a, i, j);
@@ -426,7 +426,7 @@ __device__ __forceinline__ double heavyApplyRow(const HeavyArgs &a, const double
     double y = a.diag[row] * v[row];
     if (row < a.NU)
     {
-        const int i = static_cast<int>(row / J), j = static_cast<int>(row - static_cast<long long>(i) * J);
+        const int i = rowOfCell(row, J), j = static_cast<int>(row - static_cast<long long>(i) * J);
         const bool jm = uval(a, i, j - 1) && vval(a, i, j) && vval(a, i - 1, j);
         const bool jp = uval(a, i, j + 1) && vval(a, i, j + 1) && vval(a, i - 1, j + 1);
         if (uval(a, i + 1, j)) y += -heavyT(a, i, j) * vU[(i + 1) * J + j];
@@ -449,7 +449,7 @@ __device__ __forceinline__ double heavyApplyRow(const HeavyArgs &a, const double
     else
     {
         const long long m = row - a.NU;
-        const int i = static_cast<int>(m / J1), j = static_cast<int>(m - static_cast<long long>(i) * J1);
+        const int i = rowOfCell(m, J1), j = static_cast<int>(m - static_cast<long long>(i) * J1);
         if (vval(a, i, j + 1)) y += -heavyT(a, i, j) * vV[i * J1 + j + 1];
         if (uval(a, i + 1, j) && vval(a, i + 1, j - 1) && vval(a, i + 1, j)) y += -heavyC(a, i + 1, j) * vV[(i + 1) * J1 + j];
         if (vval(a, i, j - 1)) y += -heavyT(a, i, j - 1) * vV[i * J1 + j - 1];                                   // V(i,j-1)
