@@ -444,7 +444,31 @@ def run_ours(args, rank, world, local_rank):
 
     phase_s = {"upload": 0.0, "substep": 0.0, "download": 0.0}
 
+    # one handle: the streamed calls (sections of the pinned buffer travel on a copy stream while the substep runs:
+    # FlipSolver::stepSubstepStreamed); row slabs: packed upload -> substep -> packed download
+    streamed = world == 1
+
+    def download_sectioned():
+        n = dev.stream_end(hostbuf.numpy(), cap)
+        state["n"] = n
+        state["n_min"] = min(state["n_min"], n)
+        state["n_max"] = max(state["n_max"], n)
+
+    def e2e_step_streamed():
+        n = state["n"]
+        t0 = time.perf_counter()
+        _, m = solver.step_substep_streamed(hostbuf.data_ptr(), cap, n)
+        t1 = time.perf_counter()
+        state["h2d"] += n * rec
+        state["d2h"] += m * rec
+        state["n"] = m
+        state["n_min"] = min(state["n_min"], m)
+        state["n_max"] = max(state["n_max"], m)
+        phase_s["substep"] += t1 - t0
+
     def e2e_step():
+        if streamed:
+            return e2e_step_streamed()
         n = state["n"]
         t0 = time.perf_counter()
         rc = L.fs2d_upload_particles_packed(dev.h, hostbuf.data_ptr(), n)
@@ -462,7 +486,10 @@ def run_ours(args, rank, world, local_rank):
 
     e2e = None
     if not args.no_e2e:
-        download()
+        if streamed:
+            download_sectioned()
+        else:
+            download()
         e2e_step()  # warm-up of the path
         state["h2d"] = state["d2h"] = 0
         for k in phase_s:
@@ -485,7 +512,12 @@ def run_ours(args, rank, world, local_rank):
                "stage_ms_per_substep_last_frame": (lambda st: {n: round(float(st["timings"][k]) / max(st["substeps"], 1), 3)
                                                                for k, n in enumerate(host_api.STAGES)})(solver.stats()),
                "window": "substeps %d .. %d of the scene, the window `value` was timed on (second solver, same warm-up)" % (max(args.warmup, 3) + 1, max(args.warmup, 3) + 1 + e2e_steps),
-               "what": "per step: fs2d_upload_particles_packed from a pinned host buffer, FlipSolver::stepSubstep, "
+               "what": ("per step: FlipSolver::stepSubstepStreamed on a pinned host buffer = fs2d_particle_stream_begin (all %d "
+                        "bytes per record host -> device on a copy stream, each section awaited where a stage first reads it), the "
+                        "stages of stepSubstep, fs2d_particle_stream_positions_final after the density correction (positions and "
+                        "property columns device -> host under the P2G / pressure stages), fs2d_particle_stream_end (velocities, "
+                        "storage bytes, reseeded records; returns when the buffer is complete)" % rec) if streamed else
+                       "per step: fs2d_upload_particles_packed from a pinned host buffer, FlipSolver::stepSubstep, "
                        "fs2d_download_particles_packed into it (positions, velocities, %d property columns, storage-bin byte)" % K
                        + (" (every rank moves the particles of its slab; bytes summed over ranks)" if world > 1 else "")}
 

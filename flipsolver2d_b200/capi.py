@@ -102,6 +102,11 @@ def lib():
         "fs2d_packed_particle_bytes": (C.c_size_t, [H, i64]),
         "fs2d_download_particles_packed": (i32, [H, vp, C.c_size_t, C.POINTER(i64)]),
         "fs2d_upload_particles_packed": (i32, [H, vp, i64]),
+        "fs2d_particle_stream_bytes": (C.c_size_t, [H, i64]),
+        "fs2d_particle_stream_begin": (i32, [H, vp, i64, i64]),
+        "fs2d_particle_stream_positions_final": (i32, [H, vp, i64, i32]),
+        "fs2d_particle_stream_end": (i32, [H, vp, i64, C.POINTER(i64)]),
+        "fs2d_particle_stream_set_output": (i32, [H, vp, i64]),
         "fs2d_set_particle_storage_bins": (i32, [H, vp]),
         "fs2d_get_particle_storage_bins": (i32, [H, vp]),
         "fs2d_pcg_solve": (i32, [H, vp, vp, i32, f64, C.POINTER(i32)]),
@@ -299,6 +304,20 @@ class Device:
         n = C.c_int64(0)
         self._ck(self.L.fs2d_download_particles_packed(self.h, _p(buf), buf.nbytes, C.byref(n)), "download_packed")
         return buf, n.value
+
+    def stream_begin(self, buf, count, capacity):
+        self._ck(self.L.fs2d_particle_stream_begin(self.h, _p(buf), int(count), int(capacity)), "stream_begin")
+
+    def stream_positions_final(self, buf, capacity, props_final=True):
+        self._ck(self.L.fs2d_particle_stream_positions_final(self.h, _p(buf), int(capacity), 1 if props_final else 0), "stream_positions_final")
+
+    def stream_set_output(self, buf, capacity):
+        self._ck(self.L.fs2d_particle_stream_set_output(self.h, _p(buf), int(capacity)), "stream_set_output")
+
+    def stream_end(self, buf, capacity):
+        n = C.c_int64(0)
+        self._ck(self.L.fs2d_particle_stream_end(self.h, _p(buf), int(capacity), C.byref(n)), "stream_end")
+        return n.value
 
     def upload_packed(self, buf, count):
         self._ck(self.L.fs2d_upload_particles_packed(self.h, _p(buf), int(count)), "upload_packed")

@@ -234,6 +234,13 @@ void freeAll(Ctx *c)
     if (c->eventsReady)
         for (int k = 0; k < 16; k++) cudaEventDestroy(c->ev[k]);
     for (cudaEvent_t e : c->profEvents) cudaEventDestroy(e);
+    if (c->pstream.copy)
+    {
+        cudaStreamDestroy(c->pstream.copy);
+        cudaEvent_t ev[5] = {c->pstream.evByte, c->pstream.evVel, c->pstream.evPos, c->pstream.evProps, c->pstream.evMain};
+        for (cudaEvent_t e : ev)
+            if (e) cudaEventDestroy(e);
+    }
     if (c->stream) cudaStreamDestroy(c->stream);
 }
 }  // namespace
@@ -244,6 +251,31 @@ void freeAll(Ctx *c)
 // has not made yet. Ask for eager loading before the driver is initialised; fs2d_slab_configure additionally
 // touches the kernels that only exist in slab mode.
 __attribute__((constructor)) static void fs2dEagerModuleLoading() { setenv("CUDA_MODULE_LOADING", "EAGER", 0); }
+
+// Streamed uploads (fs2d_particle_stream_begin): the solver's stream waits for a section of the host buffer where the
+// substep first needs it.
+int particleStreamSettleSlow(Ctx *ctx, bool all)
+{
+    Ctx::ParticleStream &ps = ctx->pstream;
+    if (ps.posPending)
+    {
+        FS2D_CUDA(cudaStreamWaitEvent(ctx->stream, ps.evPos, 0));
+        ps.posPending = false;
+        FS2D_TRY(particlesKeyRange(ctx, 0, ctx->count));
+    }
+    if (!all) return FS2D_OK;
+    if (ps.propsPending)
+    {
+        FS2D_CUDA(cudaStreamWaitEvent(ctx->stream, ps.evProps, 0));
+        ps.propsPending = false;
+    }
+    if (ps.propsGatherPending)
+    {
+        ps.propsGatherPending = false;
+        FS2D_TRY(particlesGatherProps(ctx, ps.propsFrom, ps.gatherCount));
+    }
+    return FS2D_OK;
+}
 
 extern "C" {
 
@@ -437,8 +469,10 @@ int fs2d_upload_particles(fs2d_handle ctx, int64_t count, const float *host_pos,
                           const float *host_props)
 {
     if (!ctx || count < 0) return FS2D_ERR_ARG;
+    FS2D_TRY(particleStreamSettleAll(ctx));
     FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
     FS2D_CUDA(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), ctx->stream));
+    ctx->pstream.earlyCount = -1;
     ctx->count = 0;
     ctx->deadCount = 0;
     ctx->killedDirty = false;
@@ -459,6 +493,7 @@ int fs2d_append_particles(fs2d_handle ctx, int64_t count, const float *host_pos,
 {
     if (!ctx || count < 0 || (count > 0 && !host_pos)) return FS2D_ERR_ARG;
     if (count == 0) return FS2D_OK;
+    FS2D_TRY(particleStreamSettleAll(ctx));
     const int64_t base = ctx->count;
     // slab mode: room for the ghosts and migrants of the neighbours up front, so that no exchange has to grow the
     // buffers (cudaFree synchronises the device, which must not happen while a peer spins on this rank)
@@ -491,6 +526,7 @@ int fs2d_append_particles(fs2d_handle ctx, int64_t count, const float *host_pos,
 int fs2d_download_particles(fs2d_handle ctx, float *host_pos, float *host_vel, float *host_props)
 {
     if (!ctx) return FS2D_ERR_ARG;
+    FS2D_TRY(particleStreamSettleAll(ctx));
     // dead-flagged particles (cap, sinks, narrow band) are dropped by the sort; do it now so the
     // caller sees exactly fs2d_particle_count() records in device order
     int64_t alive = 0;
@@ -535,6 +571,7 @@ size_t fs2d_packed_particle_bytes(fs2d_handle ctx, int64_t count)
 int fs2d_download_particles_packed(fs2d_handle ctx, void *host_buf, size_t capacity_bytes, int64_t *count)
 {
     if (!ctx || !host_buf || !count) return FS2D_ERR_ARG;
+    FS2D_TRY(particleStreamSettleAll(ctx));
     const bool slab = ctx->slab.enabled && ctx->slab.world > 1;
     int64_t first = 0, n = ctx->count;
     if (slab)
@@ -577,9 +614,11 @@ int fs2d_download_particles_packed(fs2d_handle ctx, void *host_buf, size_t capac
 int fs2d_upload_particles_packed(fs2d_handle ctx, const void *host_buf, int64_t count)
 {
     if (!ctx || count < 0 || (count > 0 && !host_buf)) return FS2D_ERR_ARG;
+    FS2D_TRY(particleStreamSettleAll(ctx));
     const bool slab = ctx->slab.enabled && ctx->slab.world > 1;
     cudaStream_t st = ctx->stream;
     FS2D_CUDA(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), st));
+    ctx->pstream.earlyCount = -1;
     ctx->count = 0;
     ctx->deadCount = 0;
     ctx->killedDirty = false;
@@ -613,6 +652,163 @@ int fs2d_upload_particles_packed(fs2d_handle ctx, const void *host_buf, int64_t 
     ctx->killedDirty = true;
     FS2D_TRY(particlesKeyRange(ctx, 0, count));
     // the host buffer may be reused as soon as this returns
+    FS2D_CUDA(cudaStreamSynchronize(st));
+    return FS2D_OK;
+}
+
+// ---- streamed particle state: the copies of a substep's particle state overlap the substep itself
+static int streamReady(Ctx *ctx)
+{
+    Ctx::ParticleStream &ps = ctx->pstream;
+    if (ps.copy) return FS2D_OK;
+    FS2D_CUDA(cudaStreamCreateWithFlags(&ps.copy, cudaStreamNonBlocking));
+    cudaEvent_t *ev[5] = {&ps.evByte, &ps.evVel, &ps.evPos, &ps.evProps, &ps.evMain};
+    for (cudaEvent_t *e : ev) FS2D_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    return FS2D_OK;
+}
+
+size_t fs2d_particle_stream_bytes(fs2d_handle ctx, int64_t capacity_records) { return fs2d_packed_particle_bytes(ctx, capacity_records); }
+
+int fs2d_particle_stream_begin(fs2d_handle ctx, const void *host_in, int64_t count, int64_t capacity_records)
+{
+    if (!ctx || count < 0 || capacity_records < count || (count > 0 && !host_in)) return FS2D_ERR_ARG;
+    if (ctx->slab.enabled && ctx->slab.world > 1)
+    {
+        ctx->lastError = "fs2d_particle_stream_begin: one handle only (row slabs use the packed transfers)";
+        return FS2D_ERR_STATE;
+    }
+    FS2D_TRY(particleStreamSettleAll(ctx));
+    FS2D_TRY(streamReady(ctx));
+    Ctx::ParticleStream &ps = ctx->pstream;
+    cudaStream_t st = ctx->stream;
+    FS2D_CUDA(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), st));
+    ctx->count = 0;
+    ctx->deadCount = 0;
+    ctx->killedDirty = false;
+    ctx->sorted = false;
+    ps.earlyCount = -1;
+    if (count == 0)
+    {
+        FS2D_CUDA(cudaMemsetAsync(ctx->cellStart, 0, sizeof(int32_t) * (ctx->N + 1), st));
+        ctx->sorted = true;
+        return FS2D_OK;
+    }
+    FS2D_TRY(particlesReserve(ctx, count));
+    FS2D_TRY(stageReserve(ctx, static_cast<size_t>(count)));
+    ParticleBuffers &b = ctx->pb[ctx->cur];
+    const int K = ctx->p.num_properties;
+    const size_t n = static_cast<size_t>(count), cap = static_cast<size_t>(capacity_records);
+    const unsigned char *h = static_cast<const unsigned char *>(host_in);
+    // the copy stream starts when everything queued on the solver's stream (readers of the arrays about to be
+    // overwritten) is done; sections in the order the substep needs them: dead flags and velocities (CFL maximum),
+    // positions (advection, sort, density correction), property columns (centred P2G)
+    FS2D_CUDA(cudaEventRecord(ps.evMain, st));
+    FS2D_CUDA(cudaStreamWaitEvent(ps.copy, ps.evMain, 0));
+    FS2D_CUDA(cudaMemcpyAsync(ctx->stage, h + (16u + 4u * K) * cap, n, cudaMemcpyHostToDevice, ps.copy));
+    FS2D_CUDA(cudaEventRecord(ps.evByte, ps.copy));
+    FS2D_CUDA(cudaMemcpyAsync(b.vel, h + 8u * cap, 8u * n, cudaMemcpyHostToDevice, ps.copy));
+    FS2D_CUDA(cudaEventRecord(ps.evVel, ps.copy));
+    FS2D_CUDA(cudaMemcpyAsync(b.pos, h, 8u * n, cudaMemcpyHostToDevice, ps.copy));
+    FS2D_CUDA(cudaEventRecord(ps.evPos, ps.copy));
+    for (int k = 0; k < K; k++)
+        FS2D_CUDA(cudaMemcpyAsync(b.props + static_cast<int64_t>(k) * b.capacity, h + (16u + 4u * k) * cap, 4u * n, cudaMemcpyHostToDevice, ps.copy));
+    FS2D_CUDA(cudaEventRecord(ps.evProps, ps.copy));
+    FS2D_CUDA(cudaStreamWaitEvent(st, ps.evByte, 0));
+    unpackStorageKernel<<<divUp(count, 256), 256, 0, st>>>(ctx->stage, count, b.mis, ctx->dead, reinterpret_cast<unsigned long long *>(ctx->d_counter));
+    ctx->launches++;
+    FS2D_CUDA(cudaStreamWaitEvent(st, ps.evVel, 0));
+    ctx->count = count;
+    ctx->killedDirty = true;
+    ps.posPending = true;
+    ps.propsPending = K > 0;
+    ps.propsGatherPending = false;
+    FS2D_CUDA(cudaGetLastError());
+    return FS2D_OK;
+}
+
+int fs2d_particle_stream_positions_final(fs2d_handle ctx, void *host_out, int64_t capacity_records, int props_final)
+{
+    if (!ctx || !host_out) return FS2D_ERR_ARG;
+    if (ctx->slab.enabled && ctx->slab.world > 1) return FS2D_OK;  // nothing leaves early over row slabs
+    FS2D_TRY(particleStreamSettleAll(ctx));
+    FS2D_TRY(streamReady(ctx));
+    Ctx::ParticleStream &ps = ctx->pstream;
+    const int64_t n = ctx->count;
+    if (n > capacity_records)
+    {
+        ctx->lastError = "fs2d_particle_stream_positions_final: host buffer too small";
+        return FS2D_ERR_ARG;
+    }
+    ps.earlyCount = -1;
+    if (n == 0) return FS2D_OK;
+    const ParticleBuffers &b = ctx->pb[ctx->cur];
+    const int K = ctx->p.num_properties;
+    const size_t cap = static_cast<size_t>(capacity_records);
+    unsigned char *h = static_cast<unsigned char *>(host_out);
+    FS2D_CUDA(cudaEventRecord(ps.evMain, ctx->stream));
+    FS2D_CUDA(cudaStreamWaitEvent(ps.copy, ps.evMain, 0));
+    FS2D_CUDA(cudaMemcpyAsync(h, b.pos, 8u * static_cast<size_t>(n), cudaMemcpyDeviceToHost, ps.copy));
+    if (props_final)
+        for (int k = 0; k < K; k++)
+            FS2D_CUDA(cudaMemcpyAsync(h + (16u + 4u * k) * cap, b.props + static_cast<int64_t>(k) * b.capacity, 4u * static_cast<size_t>(n),
+                                      cudaMemcpyDeviceToHost, ps.copy));
+    ps.earlyCount = n;
+    ps.earlyProps = props_final != 0;
+    ps.earlyHost = host_out;
+    ps.earlyCapacity = capacity_records;
+    return FS2D_OK;
+}
+
+int fs2d_particle_stream_set_output(fs2d_handle ctx, void *host_out, int64_t capacity_records)
+{
+    if (!ctx || capacity_records < 0) return FS2D_ERR_ARG;
+    ctx->pstream.outHost = host_out;
+    ctx->pstream.outCapacity = capacity_records;
+    return FS2D_OK;
+}
+
+int fs2d_particle_stream_end(fs2d_handle ctx, void *host_out, int64_t capacity_records, int64_t *count)
+{
+    if (!ctx || !host_out || !count) return FS2D_ERR_ARG;
+    ctx->pstream.outHost = nullptr;
+    if (ctx->slab.enabled && ctx->slab.world > 1)
+    {
+        ctx->lastError = "fs2d_particle_stream_end: one handle only (row slabs use the packed transfers)";
+        return FS2D_ERR_STATE;
+    }
+    FS2D_TRY(particleStreamSettleAll(ctx));
+    Ctx::ParticleStream &ps = ctx->pstream;
+    const int64_t n = ctx->count;
+    *count = n;
+    if (n > capacity_records)
+    {
+        ctx->lastError = "fs2d_particle_stream_end: host buffer too small";
+        return FS2D_ERR_ARG;
+    }
+    // what left early (fs2d_particle_stream_positions_final into the same buffer, nothing moved since)
+    int64_t early = (ps.earlyCount >= 0 && ps.earlyHost == host_out && ps.earlyCapacity == capacity_records) ? std::min(ps.earlyCount, n) : 0;
+    const bool earlyProps = early > 0 && ps.earlyProps;
+    cudaStream_t st = ctx->stream;
+    if (n > 0)
+    {
+        FS2D_TRY(stageReserve(ctx, static_cast<size_t>(n)));
+        const ParticleBuffers &b = ctx->pb[ctx->cur];
+        const int K = ctx->p.num_properties;
+        const size_t cap = static_cast<size_t>(capacity_records), un = static_cast<size_t>(n), ue = static_cast<size_t>(early);
+        unsigned char *h = static_cast<unsigned char *>(host_out);
+        packStorageKernel<<<divUp(n, 256), 256, 0, st>>>(b.mis, ctx->dead, n, ctx->stage);
+        ctx->launches++;
+        FS2D_CUDA(cudaMemcpyAsync(h + 8u * cap, b.vel, 8u * un, cudaMemcpyDeviceToHost, st));
+        FS2D_CUDA(cudaMemcpyAsync(h + (16u + 4u * K) * cap, ctx->stage, un, cudaMemcpyDeviceToHost, st));
+        if (un > ue) FS2D_CUDA(cudaMemcpyAsync(h + 8u * ue, b.pos + early, 8u * (un - ue), cudaMemcpyDeviceToHost, st));
+        const size_t pe = earlyProps ? ue : 0u;
+        if (un > pe)
+            for (int k = 0; k < K; k++)
+                FS2D_CUDA(cudaMemcpyAsync(h + (16u + 4u * k) * cap + 4u * pe, b.props + static_cast<int64_t>(k) * b.capacity + pe, 4u * (un - pe),
+                                          cudaMemcpyDeviceToHost, st));
+    }
+    ps.earlyCount = -1;
+    if (ps.copy) FS2D_CUDA(cudaStreamSynchronize(ps.copy));
     FS2D_CUDA(cudaStreamSynchronize(st));
     return FS2D_OK;
 }

@@ -251,6 +251,25 @@ struct fs2d_context
     unsigned char *stage = nullptr;   // device staging buffer of the packed particle transfers (capi.cu)
     size_t stageBytes = 0;
 
+    // ---- streamed particle state (fs2d_particle_stream_*, capi.cu): the sections of the host buffer travel on a copy
+    // stream of their own and the solver's stream waits for each section where it is first needed
+    struct ParticleStream
+    {
+        cudaStream_t copy = nullptr;
+        cudaEvent_t evByte = nullptr, evVel = nullptr, evPos = nullptr, evProps = nullptr, evMain = nullptr;
+        bool posPending = false;          // positions (and cell keys) not yet waited for / derived
+        bool propsPending = false;        // property columns not yet waited for
+        bool propsGatherPending = false;  // a sort ran meanwhile: the columns still lie in buffer `propsFrom`, unsorted
+        int propsFrom = 0;
+        int64_t gatherCount = 0;
+        int64_t earlyCount = -1;          // records whose positions already left for the host (-1: none)
+        bool earlyProps = false;          // ... and whose property columns did
+        void *earlyHost = nullptr;
+        int64_t earlyCapacity = 0;
+        void *outHost = nullptr;          // fs2d_particle_stream_set_output: where the composite fs2d_substep sends early sections
+        int64_t outCapacity = 0;
+    } pstream;
+
     // ---- scene tables
     float *obstacleFriction = nullptr;
     int numObstacles = 0;
@@ -329,6 +348,19 @@ int particlesPruneNarrowBand(Ctx *ctx);
 int particlesAliveCount(Ctx *ctx, int64_t *out);
 int particlesSetStorageBins(Ctx *ctx, const int32_t *hostBins);
 int particlesGetStorageBins(Ctx *ctx, int32_t *hostBins);
+// Streamed uploads (capi.cu): make the solver's stream wait for the position section (SettlePos) or for every section
+// (SettleAll, which also runs the property gather a sort had to postpone). No-ops unless an upload is in flight.
+int particleStreamSettleSlow(Ctx *ctx, bool all);
+inline int particleStreamSettlePos(Ctx *ctx)
+{
+    return (ctx->pstream.posPending) ? particleStreamSettleSlow(ctx, false) : FS2D_OK;
+}
+inline int particleStreamSettleAll(Ctx *ctx)
+{
+    return (ctx->pstream.posPending || ctx->pstream.propsPending || ctx->pstream.propsGatherPending) ? particleStreamSettleSlow(ctx, true) : FS2D_OK;
+}
+inline void particleStreamPositionsChanged(Ctx *ctx) { ctx->pstream.earlyCount = -1; }
+int particlesGatherProps(Ctx *ctx, int from, int64_t count);  // particles.cu
 // transfer.cu
 int transferVelocity(Ctx *ctx);
 int transferCentered(Ctx *ctx);

@@ -241,6 +241,16 @@ __global__ void __launch_bounds__(NT) gatherKernel(const uint32_t *__restrict__ 
     dead[s] = 0;
 }
 
+// The property columns of a sort whose input columns were still on their way from the host (streamed upload).
+__global__ void __launch_bounds__(NT) gatherPropsKernel(const uint32_t *__restrict__ perm, long long alive, const float *__restrict__ propsIn,
+                                                        long long capIn, float *__restrict__ propsOut, long long capOut, int numProps)
+{
+    const long long s = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    if (s >= alive) return;
+    const uint32_t p = perm[s];
+    for (int k = 0; k < numProps; k++) propsOut[k * capOut + s] = propsIn[k * capIn + p];
+}
+
 __global__ void __launch_bounds__(NT) cellKeyKernel(const float2 *__restrict__ pos, long long begin, long long end, int I, int J,
                                                     uint32_t *__restrict__ key)
 {
@@ -589,9 +599,22 @@ int particlesKeyRange(Ctx *ctx, int64_t begin, int64_t end)
     return FS2D_OK;
 }
 
+int particlesGatherProps(Ctx *ctx, int from, int64_t count)
+{
+    if (count == 0 || ctx->p.num_properties == 0) return FS2D_OK;
+    const ParticleBuffers &in = ctx->pb[from];
+    ParticleBuffers &out = ctx->pb[ctx->cur];
+    gatherPropsKernel<<<gridFor(count), NT, 0, ctx->stream>>>(ctx->perm, count, in.props, in.capacity, out.props, out.capacity,
+                                                             ctx->p.num_properties);
+    ctx->launches++;
+    FS2D_CUDA(cudaGetLastError());
+    return FS2D_OK;
+}
+
 int particlesReserve(Ctx *ctx, int64_t capacity)
 {
     if (capacity <= ctx->pb[0].capacity) return FS2D_OK;
+    FS2D_TRY(particleStreamSettleAll(ctx));  // the copies below move whole records
     const int64_t newCap = std::max<int64_t>(capacity + capacity / 4, 1024);
     const int K = ctx->p.num_properties;
     // Stream-ordered allocation and copies: growing the buffers never synchronises the device (another rank sharing
@@ -675,6 +698,8 @@ int particlesMaxVelocity(Ctx *ctx, float *out)
 
 int particlesAdvect(Ctx *ctx)
 {
+    FS2D_TRY(particleStreamSettlePos(ctx));
+    particleStreamPositionsChanged(ctx);
     KernelGroupTimer kgt(ctx, FS2D_KGROUP_ADVECT);
     if (ctx->count == 0) return FS2D_OK;
     advectKernel<<<gridFor(ctx->count), NT, 0, ctx->stream>>>(ctx->pb[ctx->cur].pos, ctx->dead, ctx->pb[ctx->cur].mis, ctx->count,
@@ -692,6 +717,14 @@ int particlesAdvect(Ctx *ctx)
 // outside the rows [rows.lo, rows.hi) hold no particle, so the histogram / scan / order passes only cover those.
 int particlesSort(Ctx *ctx)
 {
+    // streamed upload: the sort itself needs positions only; property columns still in flight are gathered later
+    // (particleStreamSettleAll), from the input buffer and the permutation this sort leaves behind
+    if (ctx->pstream.propsGatherPending)
+        FS2D_TRY(particleStreamSettleAll(ctx));
+    else
+        FS2D_TRY(particleStreamSettlePos(ctx));
+    particleStreamPositionsChanged(ctx);
+    const bool propsLater = ctx->pstream.propsPending;
     KernelGroupTimer kgt(ctx, FS2D_KGROUP_SORT);
     const bool slab = ctx->slab.enabled && ctx->slab.world > 1;
     const SlabRows rows = slab ? slabExt(ctx, ctx->slab.ghost) : SlabRows{0, ctx->I};
@@ -726,9 +759,15 @@ int particlesSort(Ctx *ctx)
     if (alive > 0)
     {
         gatherKernel<<<gridFor(alive), NT, 0, st>>>(ctx->perm, alive, in.pos, in.vel, in.props, in.capacity, in.key, in.mis, out.pos,
-                                                    out.vel, out.props, out.capacity, out.key, out.mis, ctx->p.num_properties,
+                                                    out.vel, out.props, out.capacity, out.key, out.mis, propsLater ? 0 : ctx->p.num_properties,
                                                     ctx->dead);
         ctx->launches++;
+    }
+    if (propsLater)
+    {
+        ctx->pstream.propsGatherPending = true;
+        ctx->pstream.propsFrom = ctx->cur;
+        ctx->pstream.gatherCount = alive;
     }
     FS2D_CUDA(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), st));
     ctx->cur ^= 1;
@@ -829,6 +868,8 @@ static int combustionUpdate(Ctx *ctx)
 
 int particlesUpdate(Ctx *ctx)
 {
+    FS2D_TRY(particleStreamSettleAll(ctx));
+    if (ctx->p.sim_type == FS2D_SIM_SMOKE || ctx->p.sim_type == FS2D_SIM_FIRE) ctx->pstream.earlyProps = false;  // decay / combustion rewrite the columns
     KernelGroupTimer kgt(ctx, FS2D_KGROUP_G2P);
     if (ctx->count == 0) return ctx->p.sim_type == FS2D_SIM_FIRE ? combustionUpdate(ctx) : FS2D_OK;
     const bool smoke = ctx->p.sim_type == FS2D_SIM_SMOKE || ctx->p.sim_type == FS2D_SIM_FIRE;
@@ -855,6 +896,8 @@ int particlesUpdate(Ctx *ctx)
 
 int particlesAdjustByDensity(Ctx *ctx)
 {
+    FS2D_TRY(particleStreamSettlePos(ctx));
+    particleStreamPositionsChanged(ctx);
     if (ctx->count == 0) return FS2D_OK;
     // (dt*dt) in float, denominator in double, result narrowed to float (flipsolver2d.cpp:263)
     const float scale = static_cast<float>(static_cast<double>(ctx->stepDt * ctx->stepDt) /
@@ -869,6 +912,7 @@ int particlesAdjustByDensity(Ctx *ctx)
 
 int particlesCount(Ctx *ctx)
 {
+    FS2D_TRY(particleStreamSettlePos(ctx));
     if (!ctx->sorted) FS2D_TRY(particlesSort(ctx));
     const SlabRows own = slabOwn(ctx);
     const int64_t cLo = static_cast<int64_t>(own.lo) * ctx->J, cHi = static_cast<int64_t>(own.hi) * ctx->J;
@@ -883,6 +927,7 @@ int particlesCount(Ctx *ctx)
 
 int particlesPruneNarrowBand(Ctx *ctx)
 {
+    FS2D_TRY(particleStreamSettlePos(ctx));
     if (ctx->count == 0) return FS2D_OK;
     pruneBandKernel<<<gridFor(ctx->count), NT, 0, ctx->stream>>>(ctx->pb[ctx->cur].pos, ctx->dead, ctx->count, fluidSdfView(ctx),
                                                                 ctx->material, ctx->counts, ctx->I, ctx->J,
@@ -931,6 +976,7 @@ int particlesReseedApply(Ctx *ctx, int64_t candidates, const float *hostUniform)
     }
     if (candidates == 0) return FS2D_OK;
     if (!hostUniform) return FS2D_ERR_ARG;
+    FS2D_TRY(particleStreamSettleAll(ctx));
     if (ctx->numSources == 0 && ctx->p.sim_type != FS2D_SIM_NBFLIP)
     {
         ctx->lastError = "fs2d_reseed_apply: SOURCE cells exist but no source table was set";
@@ -1006,6 +1052,7 @@ __global__ void __launch_bounds__(NT) getStorageBinsKernel(const float2 *__restr
 // Storage bin (linear index in the ceil(I/3) x ceil(J/3) bin grid) of every particle, in device order.
 int particlesSetStorageBins(Ctx *ctx, const int32_t *hostBins)
 {
+    FS2D_TRY(particleStreamSettleAll(ctx));  // ctx->perm is the scratch array here
     if (ctx->count == 0) return FS2D_OK;
     FS2D_CUDA(cudaMemcpyAsync(ctx->perm, hostBins, sizeof(int32_t) * ctx->count, cudaMemcpyHostToDevice, ctx->stream));
     setStorageBinsKernel<<<gridFor(ctx->count), NT, 0, ctx->stream>>>(ctx->pb[ctx->cur].pos, reinterpret_cast<const int32_t *>(ctx->perm),
@@ -1017,6 +1064,7 @@ int particlesSetStorageBins(Ctx *ctx, const int32_t *hostBins)
 
 int particlesGetStorageBins(Ctx *ctx, int32_t *hostBins)
 {
+    FS2D_TRY(particleStreamSettleAll(ctx));
     if (ctx->count == 0) return FS2D_OK;
     getStorageBinsKernel<<<gridFor(ctx->count), NT, 0, ctx->stream>>>(ctx->pb[ctx->cur].pos, ctx->pb[ctx->cur].mis, ctx->count,
                                                                      (ctx->J + 2) / 3, reinterpret_cast<int32_t *>(ctx->perm));

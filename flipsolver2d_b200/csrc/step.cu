@@ -76,6 +76,9 @@ int stepFlip(Ctx *ctx, StageClock &clk, int *iters)
         FS2D_TRY(fs2d_density_correction(ctx, iters ? iters + 1 : nullptr));
         clk.end(DENSITY);
     }
+    // streamed particle state with an announced output buffer: nothing below moves or reorders the existing records
+    if (ctx->pstream.outHost)
+        FS2D_TRY(fs2d_particle_stream_positions_final(ctx, ctx->pstream.outHost, ctx->pstream.outCapacity, ctx->p.sim_type == FS2D_SIM_LIQUID ? 1 : 0));
     FS2D_TRY(fs2d_particle_to_grid(ctx));
     clk.end(PARTICLE_TO_GRID);
     FS2D_TRY(transferSdf(ctx));

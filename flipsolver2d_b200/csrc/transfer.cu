@@ -440,7 +440,7 @@ static int buildTileList(Ctx *ctx, SlabRows r, int *tilesJ, int ctasPerSm)
 static int ensureSorted(Ctx *ctx)
 {
     if (!ctx->sorted) return particlesSort(ctx);
-    return FS2D_OK;
+    return particleStreamSettlePos(ctx);
 }
 
 int transferVelocity(Ctx *ctx)
@@ -475,6 +475,7 @@ int transferCentered(Ctx *ctx)
 {
     KernelGroupTimer kgt(ctx, FS2D_KGROUP_P2G);
     FS2D_TRY(ensureSorted(ctx));
+    FS2D_TRY(particleStreamSettleAll(ctx));  // streamed upload: the property columns are needed from here on
     cudaStream_t st = ctx->stream;
     const SlabRows own = slabOwn(ctx);
     int tilesJ;

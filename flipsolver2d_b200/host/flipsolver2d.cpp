@@ -274,6 +274,29 @@ void FlipSolver::stepFrame()
     while (!stepSubstep()) {}
 }
 
+bool FlipSolver::stepSubstepStreamed(void *hostBuf, int64_t capacityRecords, int64_t countIn, int64_t *countOut)
+{
+    prepare();
+    check(fs2d_particle_stream_begin(device(), hostBuf, countIn, capacityRecords), "fs2d_particle_stream_begin");
+    m_streamBuf = hostBuf;
+    m_streamCapacity = capacityRecords;
+    bool finished = false;
+    try
+    {
+        finished = stepSubstep();
+    }
+    catch (...)
+    {
+        m_streamBuf = nullptr;
+        throw;
+    }
+    m_streamBuf = nullptr;
+    int64_t n = 0;
+    check(fs2d_particle_stream_end(device(), hostBuf, capacityRecords, &n), "fs2d_particle_stream_end");
+    if (countOut) *countOut = n;
+    return finished;
+}
+
 // ------------------------------------------------------------------ state dump / restore
 namespace
 {
@@ -366,6 +389,9 @@ void FlipSolver::step()
         densityCorrection();
         endStage(DENSITY);
     }
+    // streamed particle state: no stage below moves or reorders the existing records (reseeding appends, the count cap
+    // flags), and the liquid solver never rewrites property columns: positions and columns leave for the host now
+    if (m_streamBuf) check(fs2d_particle_stream_positions_final(device(), m_streamBuf, m_streamCapacity, 1), "fs2d_particle_stream_positions_final");
     gridUpdate();
     endStage(GRID_UPDATE);
     afterTransfer();

@@ -131,6 +131,9 @@ public:
     // One CFL substep of the current frame (starts a new frame when the last one is complete);
     // returns true when this substep finished its frame. stepFrame() == loop until true.
     bool stepSubstep();
+    // One substep whose particle state comes from and returns to a (pinned) host buffer in the sectioned layout of
+    // fs2d_particle_stream_begin; the copies overlap the stages (include/fs2d.h). Returns what stepSubstep() returns.
+    bool stepSubstepStreamed(void *hostBuf, int64_t capacityRecords, int64_t countIn, int64_t *countOut);
     // Frame-0 initialisation (scene rasterisation, seeding, upload) without stepping; stepFrame()
     // calls it when needed. Lets callers keep set-up out of a timed region.
     void prepare();
@@ -264,6 +267,8 @@ protected:
     bool m_prepared = false;
     bool m_sceneBuilt = false;
     bool m_inFrame = false;
+    void *m_streamBuf = nullptr;       // set during stepSubstepStreamed: where the particle state of this substep goes
+    int64_t m_streamCapacity = 0;
     float m_substepTime = 0.f;
     int m_substepCount = 0;
     std::mt19937 m_randEngine;

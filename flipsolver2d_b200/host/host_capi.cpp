@@ -168,6 +168,16 @@ int fs2dh_step_substep(fs2dh_solver s, int *frame_finished)
     });
 }
 
+int fs2dh_step_substep_streamed(fs2dh_solver s, void *host_buf, int64_t capacity_records, int64_t count_in, int64_t *count_out,
+                                int *frame_finished)
+{
+    Holder *h = static_cast<Holder *>(s);
+    return guarded(h, [&]() {
+        const bool done = h->solver->stepSubstepStreamed(host_buf, capacity_records, count_in, count_out);
+        if (frame_finished) *frame_finished = done ? 1 : 0;
+    });
+}
+
 int fs2dh_save_state(fs2dh_solver s, const char *path)
 {
     Holder *h = static_cast<Holder *>(s);

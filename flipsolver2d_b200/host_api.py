@@ -50,6 +50,7 @@ def lib():
         "fs2dh_prepare": (i32, [vp]),
         "fs2dh_step_frame": (i32, [vp]),
         "fs2dh_step_substep": (i32, [vp, C.POINTER(i32)]),
+        "fs2dh_step_substep_streamed": (i32, [vp, vp, C.c_int64, C.c_int64, C.POINTER(C.c_int64), C.POINTER(i32)]),
         "fs2dh_save_state": (i32, [vp, C.c_char_p]),
         "fs2dh_load_state": (i32, [vp, C.c_char_p]),
         "fs2dh_get_stats": (i32, [vp, vp, vp]),
@@ -177,6 +178,15 @@ class Solver:
         done = C.c_int(0)
         self._ck(self.L.fs2dh_step_substep(self.h, C.byref(done)), "step_substep")
         return bool(done.value)
+
+    def step_substep_streamed(self, host_ptr, capacity_records, count_in):
+        """One substep with the particle state in a (pinned) host buffer, sectioned layout (include/fs2d.h).
+        Returns (frame_finished, records now in the buffer)."""
+        done = C.c_int(0)
+        n = C.c_int64(0)
+        self._ck(self.L.fs2dh_step_substep_streamed(self.h, C.c_void_p(host_ptr), int(capacity_records), int(count_in), C.byref(n),
+                                                    C.byref(done)), "step_substep_streamed")
+        return bool(done.value), n.value
 
     def save_state(self, path):
         """FlipSolver::saveState: device grids + particle records + frame / substep counters + mt19937 stream."""

@@ -193,6 +193,33 @@ int fs2d_get_particle_storage_bins(fs2d_handle h, int32_t *host_bins);
 size_t fs2d_packed_particle_bytes(fs2d_handle h, int64_t count);
 int fs2d_download_particles_packed(fs2d_handle h, void *host_buf, size_t capacity_bytes, int64_t *count);
 int fs2d_upload_particles_packed(fs2d_handle h, const void *host_buf, int64_t count);
+/* Streamed particle state: the same records as the packed transfers, moved WHILE the substep runs. Replaces, for a
+ * caller that keeps the particles in host memory, the reference's in-object particle arrays
+ * (markerparticlesystem.h:59-249) read at the start of FlipSolver::step (flipsolver2d.cpp:412-462) and written by its
+ * stages. The host buffer is SECTIONED with a fixed stride, so that a section can travel before the final record count
+ * is known: float2 pos[cap] | float2 vel[cap] | float props[K][cap] | uint8 storage[cap] (cap = capacity_records,
+ * fs2d_particle_stream_bytes(h, cap) bytes; the first `count` entries of each section are used; storage byte as in the
+ * packed layout, 254 = flagged dead). Pinned memory is needed for the copies to be asynchronous.
+ *   fs2d_particle_stream_begin   replaces the particle state by `count` records of host_in; returns at once. A copy
+ *       stream of the handle brings the sections in the order a substep needs them (dead flags and velocities for the
+ *       CFL maximum, positions for advection / sort / density correction, property columns for the centred P2G) and the
+ *       solver's stream waits for each where a stage first reads it; a sort that runs before the property columns have
+ *       arrived gathers them afterwards. host_in must stay untouched until the matching fs2d_particle_stream_end.
+ *   fs2d_particle_stream_positions_final   the caller (the host mirror's step(), after the density correction) states
+ *       that no stage of this substep moves or reorders the existing records any more: their positions (and property
+ *       columns, with props_final != 0) start for host_out now, under the P2G / pressure stages. Any later advection,
+ *       position adjustment or sort silently cancels the promise (fs2d_particle_stream_end then sends everything).
+ *   fs2d_particle_stream_end   sends what has not left yet -- velocities, storage bytes, records appended by the
+ *       reseed -- waits for all copies and returns the number of records. Works without a preceding begin (a plain
+ *       download in the sectioned layout). host_in and host_out may be the same buffer.
+ * One handle only: FS2D_ERR_STATE over row slabs (use the packed transfers there). */
+size_t fs2d_particle_stream_bytes(fs2d_handle h, int64_t capacity_records);
+int fs2d_particle_stream_begin(fs2d_handle h, const void *host_in, int64_t count, int64_t capacity_records);
+int fs2d_particle_stream_positions_final(fs2d_handle h, void *host_out, int64_t capacity_records, int props_final);
+int fs2d_particle_stream_end(fs2d_handle h, void *host_out, int64_t capacity_records, int64_t *count);
+/* For the composite fs2d_substep (which has no caller between its stages): announce the buffer the next
+ * fs2d_particle_stream_end will be given, so that the substep sends the early sections itself. Cleared by _end. */
+int fs2d_particle_stream_set_output(fs2d_handle h, void *host_out, int64_t capacity_records);
 /* State dump / restore (checkpoint). The reference keeps its state in the solver object and has no serialisation
  * (its viewer reads the live object, Liquid2dRender/fluidrenderer.cpp:497-986); SURVEY 8(f)4 asks for one here. The blob
  * holds every device grid of the FS2D_GRID_* table as it is (a deferred level-set walk stays deferred), the particle

@@ -49,6 +49,11 @@ int fs2dh_step_frame(fs2dh_solver s);                 /* FlipSolver::stepFrame *
 /* One CFL substep of the current frame (the body of stepFrame's loop, flipsolver2d.cpp:476-497);
  * *frame_finished = 1 when it completed the frame. */
 int fs2dh_step_substep(fs2dh_solver s, int *frame_finished);
+/* The same substep with the particle state in a caller-owned (pinned) host buffer: count_in records of host_buf in the
+ * sectioned layout of fs2d_particle_stream_begin (include/fs2d.h) are the particles the substep starts from, the
+ * buffer holds *count_out records when the call returns; uploads and downloads overlap the stages. */
+int fs2dh_step_substep_streamed(fs2dh_solver s, void *host_buf, int64_t capacity_records, int64_t count_in, int64_t *count_out,
+                                int *frame_finished);
 /* timings12: ms per SolverStage; misc5: frameTime ms, substeps, pressure/density/viscosity iterations */
 int fs2dh_get_stats(fs2dh_solver s, float *timings12, float *misc5);
 

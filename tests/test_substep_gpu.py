@@ -110,3 +110,57 @@ def test_packed_round_trip_equals_resident_stepping(ref_mod, scene_dir, res, den
     for d in devs:
         d.close()
     s.close()
+
+
+def _pinned(nbytes):
+    """Pinned host bytes (the streamed copies are only asynchronous from pinned memory); the tensor keeps them alive."""
+    import torch
+    t = torch.zeros((nbytes,), dtype=torch.uint8).pin_memory()
+    return t, t.numpy()
+
+
+@pytest.mark.parametrize("res,density,early", [(96, 0.5, True), (128, 0.02, True), (96, 0.5, False)])
+def test_streamed_round_trip_equals_resident_stepping(ref_mod, scene_dir, res, density, early):
+    """The e2e path of bench.py: fs2d_particle_stream_begin (sections of the host buffer arrive while the substep runs;
+    a sort that runs before the property columns are there gathers them later) -> substep -> positions and columns
+    leave after the density correction (fs2d_particle_stream_positions_final, here through the composite fs2d_substep
+    and fs2d_particle_stream_set_output) -> fs2d_particle_stream_end. Stepping that way is bit-identical to stepping
+    resident, and the host buffer holds exactly the state a plain sectioned download gives. At density 0.02 the
+    density solve converges, particles are adjusted and re-sorted (second sort with the columns still pending)."""
+    scene = scenes.dam_break(res, "flip")
+    scene["settings"]["density"] = density
+    s = H.make_ref(ref_mod, scene, scene_dir / ("st%d.json" % res))
+    s.stage("FIRST_FRAME_INIT")
+    s.bump_frame()
+    resident, streamed = H.make_device(s, scene), H.make_device(s, scene)
+    H.sync_state(s, resident)
+    H.sync_state(s, streamed)
+    cap = int(streamed.particle_count() * 1.3) + 4096
+    nbytes = int(streamed.L.fs2d_particle_stream_bytes(streamed.h, cap))
+    keep, buf = _pinned(nbytes)
+    keep2, buf2 = _pinned(nbytes)
+    n = streamed.stream_end(buf, cap)          # no begin before: a plain download in the sectioned layout
+    assert n == streamed.particle_count()
+    dt = 1.0 / 60.0
+    for k in range(8):
+        resident.substep(dt)
+        streamed.stream_begin(buf, n, cap)
+        if early:
+            streamed.stream_set_output(buf, cap)
+        streamed.substep(dt)
+        n = streamed.stream_end(buf, cap)
+        assert n >= streamed.particle_count()
+    n2 = streamed.stream_end(buf2, cap)         # nothing left early: every section from the device arrays
+    assert n2 == n
+    K = streamed.K
+    for off, width in [(0, 8), (8 * cap, 8)] + [((16 + 4 * k) * cap, 4) for k in range(K)] + [((16 + 4 * K) * cap, 1)]:
+        assert np.array_equal(buf[off:off + width * n], buf2[off:off + width * n]), off
+    assert resident.particle_count() == streamed.particle_count()
+    for a, b in zip(resident.download_particles(), streamed.download_particles()):
+        assert np.array_equal(a, b)
+    for g in ("U", "V", "MATERIAL", "COUNTS", "PRESSURE", "VISCOSITY"):
+        assert np.array_equal(resident.download(g), streamed.download(g)), g
+    assert np.array_equal(resident.storage_bins(), streamed.storage_bins())
+    resident.close()
+    streamed.close()
+    s.close()
