@@ -564,14 +564,16 @@ __global__ void __launch_bounds__(NT) bodyForceKernel(float *__restrict__ U, flo
 }
 
 // FlipSmokeSolver::applyBodyForces (flipsmokesolver.cpp:23-52)
-__global__ void __launch_bounds__(NT) smokeBodyForceKernel(float *__restrict__ U, float *__restrict__ V, int I, int J,
+__global__ void __launch_bounds__(NT) smokeBodyForceKernel(float *__restrict__ U, float *__restrict__ V, int J, long long uBegin, long long NU,
+                                                           long long vBegin, long long NV,
                                                            GridView temperature, GridView concentration, float sootWeight,
                                                            float buoyancyInfluence, float ambient, float gx, float gy, float factor)
 {
-    const long long NU = static_cast<long long>(I + 1) * J, NV = static_cast<long long>(I) * (J + 1);
-    const long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    // samples [uBegin, uBegin + NU) of U and [vBegin, vBegin + NV) of V (row slabs: the rows with valid inputs)
+    long long n = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
     if (n < NU)
     {
+        n += uBegin;
         const int i = rowOfCell(n, J), j = static_cast<int>(n - static_cast<long long>(i) * J);
         const float x = static_cast<float>(i), y = faddr(static_cast<float>(j), 0.5f);
         const float td = fsubr(gridLerp(temperature, x, y), ambient);
@@ -581,7 +583,7 @@ __global__ void __launch_bounds__(NT) smokeBodyForceKernel(float *__restrict__ U
     }
     else if (n < NU + NV)
     {
-        const long long m = n - NU;
+        const long long m = vBegin + n - NU;
         const int i = static_cast<int>(m / (J + 1)), j = static_cast<int>(m - static_cast<long long>(i) * (J + 1));
         const float x = faddr(static_cast<float>(i), 0.5f), y = static_cast<float>(j);
         const float td = fsubr(gridLerp(temperature, x, y), ambient);
@@ -820,11 +822,13 @@ GridView fuelView(const Ctx *c);
 
 static bool isSmoke(const Ctx *ctx) { return ctx->p.sim_type == FS2D_SIM_SMOKE || ctx->p.sim_type == FS2D_SIM_FIRE; }
 
-static int slabUnsupported(Ctx *ctx, const char *what)
+// Row slabs, smoke / fire: halo rows of the temperature, soot (and fuel) grids from the row neighbours.
+static int smokeHalo(Ctx *ctx)
 {
     if (!ctx->slab.enabled || ctx->slab.world == 1) return FS2D_OK;
-    ctx->lastError = std::string(what) + " is not slab-aware yet (only FS2D_SIM_LIQUID without viscosity runs on several GPUs)";
-    return FS2D_ERR_STATE;
+    const void *arr[3] = {ctx->temperature, ctx->concentration, ctx->fuel};
+    const size_t rb[3] = {sizeof(float) * ctx->J, sizeof(float) * ctx->J, sizeof(float) * ctx->J};
+    return slabExchangeFields(ctx, arr, rb, ctx->p.sim_type == FS2D_SIM_FIRE ? 3 : 2);
 }
 
 
@@ -1079,13 +1083,22 @@ int gridBodyForces(Ctx *ctx)
 {
     // const float factor = m_stepDt / m_dx (float / double, narrowed)
     const float factor = static_cast<float>(static_cast<double>(ctx->stepDt) / ctx->p.dx);
-    const int blocks = divUp(ctx->NU + ctx->NV, NT);
     if (isSmoke(ctx))
     {
-        FS2D_TRY(slabUnsupported(ctx, "FlipSmokeSolver::applyBodyForces"));
-        smokeBodyForceKernel<<<blocks, NT, 0, ctx->stream>>>(ctx->U, ctx->V, ctx->I, ctx->J, temperatureView(ctx), concentrationView(ctx),
-                                                            ctx->p.soot_factor, ctx->p.buoyancy_factor / ctx->p.ambient_temperature,
-                                                            ctx->p.ambient_temperature, ctx->p.gravity_x, ctx->p.gravity_y, factor);
+        // Row slabs: the buoyancy samples temperature and soot one row around a velocity sample. The owned rows of both
+        // grids were rewritten since their halo copies were last refreshed (P2G, or the semi-Lagrangian step in grid
+        // mode), so the halo rows travel first; the force then goes to every velocity sample this rank holds a valid copy
+        // of and has valid inputs for (owned rows + halo - 1).
+        FS2D_TRY(smokeHalo(ctx));
+        const bool slab = ctx->slab.enabled && ctx->slab.world > 1;
+        const SlabRows reg = slabExt(ctx, slab ? ctx->slab.halo - 1 : 0);
+        const int rowHiU = reg.hi == ctx->I ? ctx->I + 1 : reg.hi;
+        const long long uBegin = static_cast<long long>(reg.lo) * ctx->J, nu = static_cast<long long>(rowHiU - reg.lo) * ctx->J;
+        const long long vBegin = static_cast<long long>(reg.lo) * (ctx->J + 1), nv = static_cast<long long>(reg.hi - reg.lo) * (ctx->J + 1);
+        smokeBodyForceKernel<<<divUp(nu + nv, NT), NT, 0, ctx->stream>>>(ctx->U, ctx->V, ctx->J, uBegin, nu, vBegin, nv, temperatureView(ctx),
+                                                                        concentrationView(ctx), ctx->p.soot_factor,
+                                                                        ctx->p.buoyancy_factor / ctx->p.ambient_temperature,
+                                                                        ctx->p.ambient_temperature, ctx->p.gravity_x, ctx->p.gravity_y, factor);
     }
     else
     {
@@ -1151,15 +1164,19 @@ int gridVelocityFromSolids(Ctx *ctx)
 int gridEulerAdvectParameters(Ctx *ctx)
 {
     if (!isSmoke(ctx)) return FS2D_OK;  // FlipSolver::eulerAdvectParameters is empty for water
-    FS2D_TRY(slabUnsupported(ctx, "eulerAdvectParameters"));
+    // Row slabs: the samples of the owned rows; a back-trace reaches cflNumber + 1 rows beyond them, inside the halo (U and V
+    // were refreshed by the extrapolation that ended the previous substep, the advected grids travel here). Every rank
+    // swaps the same arrays, so a grid keeps one offset in the symmetric heap on all ranks.
+    FS2D_TRY(smokeHalo(ctx));
     const VelocityView vel = makeVelocityView(ctx->U, ctx->V, ctx->I, ctx->J);
-    const int blocks = divUp(ctx->N, NT);
-    eulerAdvectKernel<<<blocks, NT, 0, ctx->stream>>>(concentrationView(ctx), vel, ctx->stepDt, ctx->scratchA);
-    eulerAdvectKernel<<<blocks, NT, 0, ctx->stream>>>(temperatureView(ctx), vel, ctx->stepDt, ctx->scratchB);
+    const CellRange cr = cellRange(ctx, slabOwn(ctx));
+    const int blocks = divUp(cr.count(), NT);
+    eulerAdvectKernel<<<blocks, NT, 0, ctx->stream>>>(concentrationView(ctx), vel, ctx->stepDt, ctx->scratchA, cr.begin, cr.end);
+    eulerAdvectKernel<<<blocks, NT, 0, ctx->stream>>>(temperatureView(ctx), vel, ctx->stepDt, ctx->scratchB, cr.begin, cr.end);
     ctx->launches += 2;
     if (ctx->p.sim_type == FS2D_SIM_FIRE)
     {
-        eulerAdvectKernel<<<blocks, NT, 0, ctx->stream>>>(fuelView(ctx), vel, ctx->stepDt, ctx->scratchC);
+        eulerAdvectKernel<<<blocks, NT, 0, ctx->stream>>>(fuelView(ctx), vel, ctx->stepDt, ctx->scratchC, cr.begin, cr.end);
         ctx->launches++;
         std::swap(ctx->fuel, ctx->scratchC);
     }

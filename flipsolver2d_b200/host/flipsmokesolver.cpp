@@ -1,5 +1,7 @@
 #include "flipsmokesolver.h"
 
+#include <cmath>
+
 FlipSmokeSolver::FlipSmokeSolver(const SmokeSolverParameters *p)
     : FlipSolver(p), m_temperature(p->gridSizeI, p->gridSizeJ, p->ambientTemperature, OOB_CONST, p->ambientTemperature),
       m_smokeConcentration(p->gridSizeI, p->gridSizeJ, 0.f, OOB_CONST, 0.f), m_ambientTemperature(p->ambientTemperature),
@@ -34,6 +36,8 @@ fs2d_params FlipSmokeSolver::deviceParameters() const
 void FlipSmokeSolver::seedInitialFluid()
 {
     m_seedProps.assign(m_markerParticles.propertyCount(), std::vector<float>());
+    int rowLo = 0, rowHi = 0;
+    seedRows(rowLo, rowHi);  // row slabs: the whole jitter stream is drawn, the particles of the own rows are kept
     for (ssize_t i = 0; i < m_sizeI; i++)
         for (ssize_t j = 0; j < m_sizeJ; j++)
         {
@@ -41,6 +45,8 @@ void FlipSmokeSolver::seedInitialFluid()
             for (int p = 0; p < m_particlesPerCell; p++)
             {
                 const Vec3 pos = jitteredPosInCell(i, j);
+                const int row = static_cast<int>(std::floor(pos.x()));
+                if (row < rowLo || row >= rowHi) continue;
                 const Vec3 velocity = m_fluidVelocityGrid.velocityAt(pos);
                 const float conc = m_smokeConcentration.interpolateAt(pos);
                 const float temp = m_temperature.interpolateAt(pos);

@@ -598,6 +598,19 @@ void FlipSolver::updateInitialFluid()
     });
 }
 
+// The cell rows whose seed particles this solver keeps (all rows unless it owns a row slab).
+void FlipSolver::seedRows(int &rowLo, int &rowHi) const
+{
+    rowLo = 0;
+    rowHi = static_cast<int>(m_sizeI);
+    if (g_slabWorld > 1)
+    {
+        const std::vector<int32_t> b = slabBoundsFromMaterial(g_slabWorld);
+        rowLo = b[static_cast<size_t>(g_slabRank)];
+        rowHi = b[static_cast<size_t>(g_slabRank) + 1];
+    }
+}
+
 // seedInitialFluid (flipsolver2d.cpp:682-707): ppc jittered particles per strict-FLUID cell, row major;
 // velocity and viscosity sampled from the (frame-0) grids.
 void FlipSolver::seedInitialFluid()
@@ -606,13 +619,8 @@ void FlipSolver::seedInitialFluid()
     // Row slabs: every rank draws the WHOLE mt19937 stream (the jitter of a particle depends on all particles before
     // it) but keeps only the particles of its own rows -- at 8192^2 with a full tank that is 50 M instead of 400 M
     // records of host memory per rank.
-    int rowLo = 0, rowHi = static_cast<int>(m_sizeI);
-    if (g_slabWorld > 1)
-    {
-        const std::vector<int32_t> b = slabBoundsFromMaterial(g_slabWorld);
-        rowLo = b[static_cast<size_t>(g_slabRank)];
-        rowHi = b[static_cast<size_t>(g_slabRank) + 1];
-    }
+    int rowLo = 0, rowHi = 0;
+    seedRows(rowLo, rowHi);
     for (ssize_t i = 0; i < m_sizeI; i++)
         for (ssize_t j = 0; j < m_sizeJ; j++)
         {

@@ -223,6 +223,7 @@ public:
     size_t globalParticleCount();
     std::vector<int32_t> slabBounds(int world);  // row boundaries balanced by seed particles per tile row
     std::vector<int32_t> slabBoundsFromMaterial(int world) const;
+    void seedRows(int &rowLo, int &rowHi) const;
 
 protected:
     virtual fs2d_params deviceParameters() const;

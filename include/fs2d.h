@@ -377,9 +377,11 @@ int fs2d_substep(fs2d_handle h, float dt, float *stage_ms, int *iters);
  *   grids on every rank, only the rank's OWN particles) -> stage calls, the same sequence on every rank.
  * device_share = how many ranks run on the same GPU (1 in production; > 1 lets a single GPU host several
  * ranks for testing, with the persistent kernels sized so that all ranks stay co-resident).
- * Slab-aware: FS2D_SIM_LIQUID and FS2D_SIM_NBFLIP, with or without the light viscosity model (the viscosity solve is
- * replicated: every rank gathers the velocity rows of the others and solves the whole system, bit-identical to one
- * handle); smoke / fire and the heavy viscosity model report FS2D_ERR_STATE. */
+ * Slab-aware: all four simulation types. FS2D_SIM_LIQUID and FS2D_SIM_NBFLIP with or without the light viscosity
+ * model (the viscosity solve is replicated: every rank gathers the velocity rows of the others and solves the whole
+ * system, bit-identical to one handle); FS2D_SIM_SMOKE and FS2D_SIM_FIRE in particle and grid parameter mode (the
+ * temperature / soot / fuel grids travel as halo rows before the buoyancy force and the semi-Lagrangian step). The
+ * heavy viscosity model reports FS2D_ERR_STATE. */
 #define FS2D_SLAB_HANDLE_BYTES 256
 int fs2d_slab_configure(fs2d_handle h, int rank, int world, int device_share);
 /* The same with explicit slab boundaries: row_bounds[world + 1], row_bounds[0] = 0, row_bounds[world] = gridSizeI,
