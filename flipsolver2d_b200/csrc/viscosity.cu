@@ -684,11 +684,6 @@ int gridViscosity(Ctx *ctx, int *iters)
         // order, hence bit-identical to a single handle on every rank, and U / V come out valid on all rows. The stage
         // is a handful of iterations of grid-only passes; distributing it would add two all-reduces
         // and a halo exchange per iteration for a stage that is ~2 ms at 4096^2.
-        if (ctx->p.heavy_viscosity)
-        {
-            ctx->lastError = "HeavyViscosityModel is not slab-aware";
-            return FS2D_ERR_STATE;
-        }
         void *arr[4] = {ctx->U, ctx->V, ctx->viscosity, ctx->material};
         const size_t rb[4] = {sizeof(float) * ctx->J, sizeof(float) * (ctx->J + 1), sizeof(float) * ctx->J, static_cast<size_t>(ctx->J)};
         const int rt[4] = {ctx->I + 1, ctx->I, ctx->I, ctx->I};

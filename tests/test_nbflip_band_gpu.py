@@ -57,15 +57,17 @@ def test_banded_walks_leave_the_simulation_unchanged(scene_dir, viscous):
     exact.close()
 
 
-@pytest.mark.parametrize("viscous,world,density", [(False, 2, 0.5), (True, 2, 0.02), (True, 3, 0.02), (False, 3, 0.5)])
+@pytest.mark.parametrize("viscous,world,density", [(False, 2, 0.5), (True, 2, 0.02), (True, 3, 0.02), (False, 3, 0.5), ("heavy", 2, 0.02)])
 def test_nbflip_slabs_match_single_solver(scene_dir, viscous, world, density):
     """BASELINE config 4 at test size: NBFlipSolver::step over row slabs (semi-Lagrangian grids and pruneNarrowBand
     with halo rows, banded level-set walks on slab + halo, combine passes, replicated viscosity solve, reseeding with
     the host mt19937 stream stitched over the ranks) against one solver on one handle."""
-    scene = _scene(128, viscous, density)
+    scene = _scene(128, bool(viscous), density)
+    if viscous == "heavy":
+        scene["settings"]["heavyViscosity"] = True   # the coupled U + V model, solved replicated like the light one
     # a block that straddles the slab boundaries and falls across them
     scene["solver"]["objects"][-1]["verts"] = [[15, 3], [15, 13], [40, 13], [40, 3]]
-    path = scenes.write_scene(scene, str(scene_dir / ("nbslab_%d_%d.json" % (viscous, world))))
+    path = scenes.write_scene(scene, str(scene_dir / ("nbslab_%s_%d.json" % (viscous, world))))
     frames = 3
     single = host_api.Solver(path, quiet=True)
     for _ in range(frames):
