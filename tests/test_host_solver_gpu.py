@@ -59,26 +59,42 @@ def test_substep_granular_stepping_equals_step_frame(scene_dir):
     b.close()
 
 
-def test_streamed_substeps_equal_resident_substeps(scene_dir):
+@pytest.mark.parametrize("kind", ["flip", "nbflip_viscous", "smoke", "fire_grid"])
+def test_streamed_substeps_equal_resident_substeps(scene_dir, kind):
     """FlipSolver::stepSubstepStreamed (particle state in a pinned host buffer, copies overlapping the stages; the
-    scene has a source, so reseeded records are appended after the positions have left) against stepSubstep."""
+    scenes have a source, so reseeded records are appended after the positions have left) against stepSubstep. The
+    liquid solver sends positions and property columns early; nbflip / smoke / fire keep their own step() and only use
+    the streamed upload (sort before the columns arrive, smoke decay rewriting columns) and the download at the end."""
     import torch
-    scene = scenes.source_sink(96, "flip")
-    path = scenes.write_scene(scene, str(scene_dir / "hostgpu_streamed.json"))
+    K = 2
+    if kind == "flip":
+        scene = scenes.source_sink(96, "flip")
+    elif kind == "nbflip_viscous":
+        scene = scenes.source_sink(96, "nbflip")
+        scene["settings"]["viscosityEnabled"] = True
+        scene["settings"]["density"] = 0.02
+    elif kind == "smoke":
+        scene = scenes.smoke_test(96, parameter_handling="particle", sim_type="smoke")
+        K = 3   # viscosity, concentration, temperature
+    else:
+        scene = scenes.smoke_test(96, parameter_handling="grid", sim_type="fire")
+        K = 4   # + fuel
+    path = scenes.write_scene(scene, str(scene_dir / ("hostgpu_streamed_%s.json" % kind)))
     a, b = host_api.Solver(path), host_api.Solver(path)
     a.prepare()
     b.prepare()
-    db = b.device(2)
-    cap = int(b.particle_count() * 1.5) + 4096
+    db = b.device(K)
+    cap = int(b.particle_count() * 1.5) + 20000
     pinned = torch.zeros((int(db.L.fs2d_particle_stream_bytes(db.h, cap)),), dtype=torch.uint8).pin_memory()
     n = db.stream_end(pinned.numpy(), cap)
     for _ in range(12):
         fa = a.step_substep()
         fb, n = b.step_substep_streamed(pinned.data_ptr(), cap, n)
         assert fa == fb
-    da = a.device(2)
-    assert a.particle_count() == b.particle_count()
-    for g in ("U", "V", "MATERIAL", "PRESSURE", "VISCOSITY"):
+    da = a.device(K)
+    assert a.particle_count() == b.particle_count() > 0
+    grids = ("U", "V", "MATERIAL", "PRESSURE") + (("TEMPERATURE", "CONCENTRATION") if kind in ("smoke", "fire_grid") else ("VISCOSITY",))
+    for g in grids:
         assert np.array_equal(da.download(g), db.download(g)), g
     for x, y in zip(da.download_particles(), db.download_particles()):
         assert np.array_equal(x, y)

@@ -238,7 +238,7 @@ def test_smoke_fire_slabs_match_single_solver(scene_dir, sim, handling):
     counts = capi.run_ranks([lambda s=s: s.global_particle_count() for s in solvers])
     assert counts == [single.particle_count()] * world
     assert min(s.particle_count() for s in solvers) > 0
-    K = 3 if sim == "fire" else 2
+    K = 4 if sim == "fire" else 3   # property columns: viscosity, concentration, temperature (+ fuel)
     ds, dd = single.device(K), [s.device(K) for s in solvers]
     for g in ("TEMPERATURE", "CONCENTRATION", "U", "V"):
         capi.run_ranks([lambda d=d: d.slab_gather(g) for d in dd])
