@@ -443,6 +443,7 @@ def run_ours(args, rank, world, local_rank):
         state["d2h"] += n.value * rec
 
     phase_s = {"upload": 0.0, "substep": 0.0, "download": 0.0}
+    copy_ms = {}
 
     # one handle: the streamed calls (sections of the pinned buffer travel on a copy stream while the substep runs:
     # FlipSolver::stepSubstepStreamed); row slabs: packed upload -> substep -> packed download
@@ -459,6 +460,8 @@ def run_ours(args, rank, world, local_rank):
         t0 = time.perf_counter()
         _, m = solver.step_substep_streamed(hostbuf.data_ptr(), cap, n)
         t1 = time.perf_counter()
+        for k, v in dev.stream_timing().items():   # CUDA-event durations of this step's copies (read after the step)
+            copy_ms[k] = copy_ms.get(k, 0.0) + v
         state["h2d"] += n * rec
         state["d2h"] += m * rec
         state["n"] = m
@@ -494,6 +497,7 @@ def run_ours(args, rank, world, local_rank):
         state["h2d"] = state["d2h"] = 0
         for k in phase_s:
             phase_s[k] = 0.0
+        copy_ms.clear()
         state["n_min"] = state["n_max"] = n_start = state["n"]
         e2e_steps = args.steps
         dev.pcg_profile(True)
@@ -507,6 +511,7 @@ def run_ours(args, rank, world, local_rank):
                "d2h_bytes_per_step": total(state["d2h"]) // e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                "particles_start": total(n_start), "particles_end": total(state["n"]), "bytes_per_particle": rec,
                "host_ms_per_step_rank0": {k: round(v / e2e_steps * 1e3, 3) for k, v in phase_s.items()},
+               "copy_ms_per_step_rank0": {k: round(v / e2e_steps, 3) for k, v in copy_ms.items()},
                "pcg_solve_kernel_ms": e2e_solve_ms / max(e2e_solve_n, 1),
                "kernel_group_ms": {g: round(v[0] / max(v[1], 1), 3) for g, v in e2e_groups.items()},
                "stage_ms_per_substep_last_frame": (lambda st: {n: round(float(st["timings"][k]) / max(st["substeps"], 1), 3)

@@ -105,8 +105,10 @@ def lib():
         "fs2d_particle_stream_bytes": (C.c_size_t, [H, i64]),
         "fs2d_particle_stream_begin": (i32, [H, vp, i64, i64]),
         "fs2d_particle_stream_positions_final": (i32, [H, vp, i64, i32]),
+        "fs2d_particle_stream_velocities_final": (i32, [H, vp, i64]),
         "fs2d_particle_stream_end": (i32, [H, vp, i64, C.POINTER(i64)]),
         "fs2d_particle_stream_set_output": (i32, [H, vp, i64]),
+        "fs2d_particle_stream_timing": (i32, [H, vp]),
         "fs2d_set_particle_storage_bins": (i32, [H, vp]),
         "fs2d_get_particle_storage_bins": (i32, [H, vp]),
         "fs2d_pcg_solve": (i32, [H, vp, vp, i32, f64, C.POINTER(i32)]),
@@ -313,6 +315,12 @@ class Device:
 
     def stream_set_output(self, buf, capacity):
         self._ck(self.L.fs2d_particle_stream_set_output(self.h, _p(buf), int(capacity)), "stream_set_output")
+
+    def stream_timing(self):
+        """ms of the copies of the last streamed substep: H2D storage bytes / velocities / positions / columns, early D2H, final D2H."""
+        out = np.zeros(6, np.float32)
+        self._ck(self.L.fs2d_particle_stream_timing(self.h, _p(out)), "stream_timing")
+        return dict(zip(("h2d_storage", "h2d_vel", "h2d_pos", "h2d_props", "d2h_early", "d2h_end"), [float(x) for x in out]))
 
     def stream_end(self, buf, capacity):
         n = C.c_int64(0)

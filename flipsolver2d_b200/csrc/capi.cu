@@ -237,8 +237,11 @@ void freeAll(Ctx *c)
     if (c->pstream.copy)
     {
         cudaStreamDestroy(c->pstream.copy);
-        cudaEvent_t ev[5] = {c->pstream.evByte, c->pstream.evVel, c->pstream.evPos, c->pstream.evProps, c->pstream.evMain};
+        cudaEvent_t ev[10] = {c->pstream.evByte, c->pstream.evVel, c->pstream.evPos, c->pstream.evProps, c->pstream.evMain,
+                              c->pstream.evStart, c->pstream.evEarly0, c->pstream.evEarly1, c->pstream.evEnd0, c->pstream.evEnd1};
         for (cudaEvent_t e : ev)
+            if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : c->pstream.evPosChunk)
             if (e) cudaEventDestroy(e);
     }
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -254,6 +257,16 @@ __attribute__((constructor)) static void fs2dEagerModuleLoading() { setenv("CUDA
 
 // Streamed uploads (fs2d_particle_stream_begin): the solver's stream waits for a section of the host buffer where the
 // substep first needs it.
+bool particleStreamNextPosChunk(Ctx *ctx, int idx, int64_t *begin, int64_t *end)
+{
+    Ctx::ParticleStream &ps = ctx->pstream;
+    if (!ps.posPending || idx < 0 || idx >= Ctx::ParticleStream::POS_CHUNKS) return false;
+    if (cudaStreamWaitEvent(ctx->stream, ps.evPosChunk[idx], 0) != cudaSuccess) return false;
+    *begin = idx == 0 ? 0 : ps.posChunkEnd[idx - 1];
+    *end = ps.posChunkEnd[idx];
+    return true;
+}
+
 int particleStreamSettleSlow(Ctx *ctx, bool all)
 {
     Ctx::ParticleStream &ps = ctx->pstream;
@@ -472,7 +485,7 @@ int fs2d_upload_particles(fs2d_handle ctx, int64_t count, const float *host_pos,
     FS2D_TRY(particleStreamSettleAll(ctx));
     FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
     FS2D_CUDA(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), ctx->stream));
-    ctx->pstream.earlyCount = -1;
+    ctx->pstream.earlyCount = ctx->pstream.earlyVelCount = -1;
     ctx->count = 0;
     ctx->deadCount = 0;
     ctx->killedDirty = false;
@@ -618,7 +631,7 @@ int fs2d_upload_particles_packed(fs2d_handle ctx, const void *host_buf, int64_t 
     const bool slab = ctx->slab.enabled && ctx->slab.world > 1;
     cudaStream_t st = ctx->stream;
     FS2D_CUDA(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), st));
-    ctx->pstream.earlyCount = -1;
+    ctx->pstream.earlyCount = ctx->pstream.earlyVelCount = -1;
     ctx->count = 0;
     ctx->deadCount = 0;
     ctx->killedDirty = false;
@@ -662,8 +675,9 @@ static int streamReady(Ctx *ctx)
     Ctx::ParticleStream &ps = ctx->pstream;
     if (ps.copy) return FS2D_OK;
     FS2D_CUDA(cudaStreamCreateWithFlags(&ps.copy, cudaStreamNonBlocking));
-    cudaEvent_t *ev[5] = {&ps.evByte, &ps.evVel, &ps.evPos, &ps.evProps, &ps.evMain};
-    for (cudaEvent_t *e : ev) FS2D_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    cudaEvent_t *ev[10] = {&ps.evByte, &ps.evVel, &ps.evPos, &ps.evProps, &ps.evMain, &ps.evStart, &ps.evEarly0, &ps.evEarly1, &ps.evEnd0, &ps.evEnd1};
+    for (cudaEvent_t *e : ev) FS2D_CUDA(cudaEventCreate(e));
+    for (cudaEvent_t &e : ps.evPosChunk) FS2D_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     return FS2D_OK;
 }
 
@@ -686,7 +700,7 @@ int fs2d_particle_stream_begin(fs2d_handle ctx, const void *host_in, int64_t cou
     ctx->deadCount = 0;
     ctx->killedDirty = false;
     ctx->sorted = false;
-    ps.earlyCount = -1;
+    ps.earlyCount = ps.earlyVelCount = -1;
     if (count == 0)
     {
         FS2D_CUDA(cudaMemsetAsync(ctx->cellStart, 0, sizeof(int32_t) * (ctx->N + 1), st));
@@ -704,11 +718,27 @@ int fs2d_particle_stream_begin(fs2d_handle ctx, const void *host_in, int64_t cou
     // positions (advection, sort, density correction), property columns (centred P2G)
     FS2D_CUDA(cudaEventRecord(ps.evMain, st));
     FS2D_CUDA(cudaStreamWaitEvent(ps.copy, ps.evMain, 0));
+    FS2D_CUDA(cudaEventRecord(ps.evStart, ps.copy));
+    ps.timedUpload = true;
+    ps.timedEarly = ps.timedEnd = false;
     FS2D_CUDA(cudaMemcpyAsync(ctx->stage, h + (16u + 4u * K) * cap, n, cudaMemcpyHostToDevice, ps.copy));
     FS2D_CUDA(cudaEventRecord(ps.evByte, ps.copy));
     FS2D_CUDA(cudaMemcpyAsync(b.vel, h + 8u * cap, 8u * n, cudaMemcpyHostToDevice, ps.copy));
     FS2D_CUDA(cudaEventRecord(ps.evVel, ps.copy));
-    FS2D_CUDA(cudaMemcpyAsync(b.pos, h, 8u * n, cudaMemcpyHostToDevice, ps.copy));
+    {
+        // in chunks of whole 4096-record blocks: the advection of a chunk starts while the next one travels
+        const int64_t per = ((count + Ctx::ParticleStream::POS_CHUNKS - 1) / Ctx::ParticleStream::POS_CHUNKS + 4095) / 4096 * 4096;
+        int64_t done = 0;
+        for (int c = 0; c < Ctx::ParticleStream::POS_CHUNKS; c++)
+        {
+            const int64_t end = std::min<int64_t>(count, done + per);
+            if (end > done)
+                FS2D_CUDA(cudaMemcpyAsync(b.pos + done, h + 8u * static_cast<size_t>(done), 8u * static_cast<size_t>(end - done), cudaMemcpyHostToDevice, ps.copy));
+            FS2D_CUDA(cudaEventRecord(ps.evPosChunk[c], ps.copy));
+            ps.posChunkEnd[c] = end;
+            done = end;
+        }
+    }
     FS2D_CUDA(cudaEventRecord(ps.evPos, ps.copy));
     for (int k = 0; k < K; k++)
         FS2D_CUDA(cudaMemcpyAsync(b.props + static_cast<int64_t>(k) * b.capacity, h + (16u + 4u * k) * cap, 4u * n, cudaMemcpyHostToDevice, ps.copy));
@@ -747,15 +777,43 @@ int fs2d_particle_stream_positions_final(fs2d_handle ctx, void *host_out, int64_
     unsigned char *h = static_cast<unsigned char *>(host_out);
     FS2D_CUDA(cudaEventRecord(ps.evMain, ctx->stream));
     FS2D_CUDA(cudaStreamWaitEvent(ps.copy, ps.evMain, 0));
+    FS2D_CUDA(cudaEventRecord(ps.evEarly0, ps.copy));
     FS2D_CUDA(cudaMemcpyAsync(h, b.pos, 8u * static_cast<size_t>(n), cudaMemcpyDeviceToHost, ps.copy));
     if (props_final)
         for (int k = 0; k < K; k++)
             FS2D_CUDA(cudaMemcpyAsync(h + (16u + 4u * k) * cap, b.props + static_cast<int64_t>(k) * b.capacity, 4u * static_cast<size_t>(n),
                                       cudaMemcpyDeviceToHost, ps.copy));
+    FS2D_CUDA(cudaEventRecord(ps.evEarly1, ps.copy));
+    ps.timedEarly = true;
     ps.earlyCount = n;
     ps.earlyProps = props_final != 0;
     ps.earlyHost = host_out;
     ps.earlyCapacity = capacity_records;
+    return FS2D_OK;
+}
+
+int fs2d_particle_stream_velocities_final(fs2d_handle ctx, void *host_out, int64_t capacity_records)
+{
+    if (!ctx || !host_out) return FS2D_ERR_ARG;
+    if (ctx->slab.enabled && ctx->slab.world > 1) return FS2D_OK;
+    FS2D_TRY(particleStreamSettleAll(ctx));
+    FS2D_TRY(streamReady(ctx));
+    Ctx::ParticleStream &ps = ctx->pstream;
+    const int64_t n = ctx->count;
+    if (n > capacity_records)
+    {
+        ctx->lastError = "fs2d_particle_stream_velocities_final: host buffer too small";
+        return FS2D_ERR_ARG;
+    }
+    ps.earlyVelCount = -1;
+    if (n == 0) return FS2D_OK;
+    FS2D_CUDA(cudaEventRecord(ps.evMain, ctx->stream));
+    FS2D_CUDA(cudaStreamWaitEvent(ps.copy, ps.evMain, 0));
+    FS2D_CUDA(cudaMemcpyAsync(static_cast<unsigned char *>(host_out) + 8u * static_cast<size_t>(capacity_records), ctx->pb[ctx->cur].vel,
+                              8u * static_cast<size_t>(n), cudaMemcpyDeviceToHost, ps.copy));
+    ps.earlyVelCount = n;
+    ps.earlyVelHost = host_out;
+    ps.earlyVelCapacity = capacity_records;
     return FS2D_OK;
 }
 
@@ -788,6 +846,7 @@ int fs2d_particle_stream_end(fs2d_handle ctx, void *host_out, int64_t capacity_r
     // what left early (fs2d_particle_stream_positions_final into the same buffer, nothing moved since)
     int64_t early = (ps.earlyCount >= 0 && ps.earlyHost == host_out && ps.earlyCapacity == capacity_records) ? std::min(ps.earlyCount, n) : 0;
     const bool earlyProps = early > 0 && ps.earlyProps;
+    const int64_t earlyVel = (ps.earlyVelCount >= 0 && ps.earlyVelHost == host_out && ps.earlyVelCapacity == capacity_records) ? std::min(ps.earlyVelCount, n) : 0;
     cudaStream_t st = ctx->stream;
     if (n > 0)
     {
@@ -796,9 +855,15 @@ int fs2d_particle_stream_end(fs2d_handle ctx, void *host_out, int64_t capacity_r
         const int K = ctx->p.num_properties;
         const size_t cap = static_cast<size_t>(capacity_records), un = static_cast<size_t>(n), ue = static_cast<size_t>(early);
         unsigned char *h = static_cast<unsigned char *>(host_out);
+        if (ps.evEnd0)
+        {
+            FS2D_CUDA(cudaEventRecord(ps.evEnd0, st));
+            ps.timedEnd = true;
+        }
         packStorageKernel<<<divUp(n, 256), 256, 0, st>>>(b.mis, ctx->dead, n, ctx->stage);
         ctx->launches++;
-        FS2D_CUDA(cudaMemcpyAsync(h + 8u * cap, b.vel, 8u * un, cudaMemcpyDeviceToHost, st));
+        const size_t uv = static_cast<size_t>(earlyVel);
+        if (un > uv) FS2D_CUDA(cudaMemcpyAsync(h + 8u * cap + 8u * uv, b.vel + earlyVel, 8u * (un - uv), cudaMemcpyDeviceToHost, st));
         FS2D_CUDA(cudaMemcpyAsync(h + (16u + 4u * K) * cap, ctx->stage, un, cudaMemcpyDeviceToHost, st));
         if (un > ue) FS2D_CUDA(cudaMemcpyAsync(h + 8u * ue, b.pos + early, 8u * (un - ue), cudaMemcpyDeviceToHost, st));
         const size_t pe = earlyProps ? ue : 0u;
@@ -807,9 +872,30 @@ int fs2d_particle_stream_end(fs2d_handle ctx, void *host_out, int64_t capacity_r
                 FS2D_CUDA(cudaMemcpyAsync(h + (16u + 4u * k) * cap + 4u * pe, b.props + static_cast<int64_t>(k) * b.capacity + pe, 4u * (un - pe),
                                           cudaMemcpyDeviceToHost, st));
     }
-    ps.earlyCount = -1;
+    ps.earlyCount = ps.earlyVelCount = -1;
+    if (ps.timedEnd) FS2D_CUDA(cudaEventRecord(ps.evEnd1, st));
     if (ps.copy) FS2D_CUDA(cudaStreamSynchronize(ps.copy));
     FS2D_CUDA(cudaStreamSynchronize(st));
+    return FS2D_OK;
+}
+
+int fs2d_particle_stream_timing(fs2d_handle ctx, float *ms6)
+{
+    if (!ctx || !ms6) return FS2D_ERR_ARG;
+    Ctx::ParticleStream &ps = ctx->pstream;
+    for (int k = 0; k < 6; k++) ms6[k] = 0.f;
+    if (!ps.copy) return FS2D_OK;
+    FS2D_CUDA(cudaStreamSynchronize(ps.copy));
+    FS2D_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ps.timedUpload)
+    {
+        cudaEventElapsedTime(&ms6[0], ps.evStart, ps.evByte);
+        cudaEventElapsedTime(&ms6[1], ps.evByte, ps.evVel);
+        cudaEventElapsedTime(&ms6[2], ps.evVel, ps.evPos);
+        cudaEventElapsedTime(&ms6[3], ps.evPos, ps.evProps);
+    }
+    if (ps.timedEarly) cudaEventElapsedTime(&ms6[4], ps.evEarly0, ps.evEarly1);
+    if (ps.timedEnd) cudaEventElapsedTime(&ms6[5], ps.evEnd0, ps.evEnd1);
     return FS2D_OK;
 }
 

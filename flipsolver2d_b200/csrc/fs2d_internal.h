@@ -257,12 +257,20 @@ struct fs2d_context
     {
         cudaStream_t copy = nullptr;
         cudaEvent_t evByte = nullptr, evVel = nullptr, evPos = nullptr, evProps = nullptr, evMain = nullptr;
+        cudaEvent_t evStart = nullptr, evEarly0 = nullptr, evEarly1 = nullptr, evEnd0 = nullptr, evEnd1 = nullptr;  // timing only
+        bool timedUpload = false, timedEarly = false, timedEnd = false;
         bool posPending = false;          // positions (and cell keys) not yet waited for / derived
+        static constexpr int POS_CHUNKS = 4;   // the position section travels in chunks so that advection can follow it
+        cudaEvent_t evPosChunk[POS_CHUNKS] = {};
+        int64_t posChunkEnd[POS_CHUNKS] = {};
         bool propsPending = false;        // property columns not yet waited for
         bool propsGatherPending = false;  // a sort ran meanwhile: the columns still lie in buffer `propsFrom`, unsorted
         int propsFrom = 0;
         int64_t gatherCount = 0;
         int64_t earlyCount = -1;          // records whose positions already left for the host (-1: none)
+        int64_t earlyVelCount = -1;       // records whose velocities already left for the host (-1: none)
+        void *earlyVelHost = nullptr;
+        int64_t earlyVelCapacity = 0;
         bool earlyProps = false;          // ... and whose property columns did
         void *earlyHost = nullptr;
         int64_t earlyCapacity = 0;
@@ -359,8 +367,11 @@ inline int particleStreamSettleAll(Ctx *ctx)
 {
     return (ctx->pstream.posPending || ctx->pstream.propsPending || ctx->pstream.propsGatherPending) ? particleStreamSettleSlow(ctx, true) : FS2D_OK;
 }
-inline void particleStreamPositionsChanged(Ctx *ctx) { ctx->pstream.earlyCount = -1; }
+inline void particleStreamPositionsChanged(Ctx *ctx) { ctx->pstream.earlyCount = ctx->pstream.earlyVelCount = -1; }
 int particlesGatherProps(Ctx *ctx, int from, int64_t count);  // particles.cu
+// Streamed upload, advection only: makes the solver's stream wait for chunk `idx` of the position section and returns its
+// record range; false when there is no such chunk. After the last chunk the caller calls particleStreamSettlePos.
+bool particleStreamNextPosChunk(Ctx *ctx, int idx, int64_t *begin, int64_t *end);
 // transfer.cu
 int transferVelocity(Ctx *ctx);
 int transferCentered(Ctx *ctx);

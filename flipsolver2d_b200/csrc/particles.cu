@@ -698,9 +698,29 @@ int particlesMaxVelocity(Ctx *ctx, float *out)
 
 int particlesAdvect(Ctx *ctx)
 {
-    FS2D_TRY(particleStreamSettlePos(ctx));
     particleStreamPositionsChanged(ctx);
     KernelGroupTimer kgt(ctx, FS2D_KGROUP_ADVECT);
+    if (ctx->pstream.posPending && ctx->count > 0)
+    {
+        // streamed upload (one handle): the position section arrives in chunks and the advection follows it chunk by chunk
+        ParticleBuffers &b = ctx->pb[ctx->cur];
+        int64_t lo = 0, hi = 0;
+        for (int c = 0; particleStreamNextPosChunk(ctx, c, &lo, &hi); c++)
+        {
+            if (hi <= lo) continue;
+            advectKernel<<<gridFor(hi - lo), NT, 0, ctx->stream>>>(b.pos + lo, ctx->dead + lo, b.mis + lo, hi - lo,
+                                                                 makeVelocityView(ctx->U, ctx->V, ctx->I, ctx->J), solidSdfView(ctx),
+                                                                 ctx->material, ctx->I, ctx->J, ctx->stepDt, ownedRows(ctx),
+                                                                 reinterpret_cast<unsigned long long *>(ctx->d_counter));
+            ctx->launches++;
+        }
+        FS2D_TRY(particleStreamSettlePos(ctx));  // the whole section has arrived: cell keys
+        ctx->killedDirty = true;
+        ctx->sorted = false;
+        FS2D_CUDA(cudaGetLastError());
+        return FS2D_OK;
+    }
+    FS2D_TRY(particleStreamSettlePos(ctx));
     if (ctx->count == 0) return FS2D_OK;
     advectKernel<<<gridFor(ctx->count), NT, 0, ctx->stream>>>(ctx->pb[ctx->cur].pos, ctx->dead, ctx->pb[ctx->cur].mis, ctx->count,
                                                              makeVelocityView(ctx->U, ctx->V, ctx->I, ctx->J),
@@ -869,6 +889,7 @@ static int combustionUpdate(Ctx *ctx)
 int particlesUpdate(Ctx *ctx)
 {
     FS2D_TRY(particleStreamSettleAll(ctx));
+    ctx->pstream.earlyVelCount = -1;
     if (ctx->p.sim_type == FS2D_SIM_SMOKE || ctx->p.sim_type == FS2D_SIM_FIRE) ctx->pstream.earlyProps = false;  // decay / combustion rewrite the columns
     KernelGroupTimer kgt(ctx, FS2D_KGROUP_G2P);
     if (ctx->count == 0) return ctx->p.sim_type == FS2D_SIM_FIRE ? combustionUpdate(ctx) : FS2D_OK;

@@ -76,9 +76,6 @@ int stepFlip(Ctx *ctx, StageClock &clk, int *iters)
         FS2D_TRY(fs2d_density_correction(ctx, iters ? iters + 1 : nullptr));
         clk.end(DENSITY);
     }
-    // streamed particle state with an announced output buffer: nothing below moves or reorders the existing records
-    if (ctx->pstream.outHost)
-        FS2D_TRY(fs2d_particle_stream_positions_final(ctx, ctx->pstream.outHost, ctx->pstream.outCapacity, ctx->p.sim_type == FS2D_SIM_LIQUID ? 1 : 0));
     FS2D_TRY(fs2d_particle_to_grid(ctx));
     clk.end(PARTICLE_TO_GRID);
     FS2D_TRY(transferSdf(ctx));
@@ -90,6 +87,10 @@ int stepFlip(Ctx *ctx, StageClock &clk, int *iters)
     FS2D_TRY(gridSaveVelocity(ctx));
     FS2D_TRY(gridBodyForces(ctx));
     clk.end(AFTER_TRANSFER);
+    // streamed particle state with an announced output buffer: no stage since the density correction, and none below, moves
+    // or reorders the existing records; the copy runs under the pressure solve
+    if (ctx->pstream.outHost)
+        FS2D_TRY(fs2d_particle_stream_positions_final(ctx, ctx->pstream.outHost, ctx->pstream.outCapacity, ctx->p.sim_type == FS2D_SIM_LIQUID ? 1 : 0));
     FS2D_TRY(projectStage(ctx, iters));
     clk.end(PRESSURE);
     FS2D_TRY(gridVelocityFromSolids(ctx));
@@ -102,6 +103,7 @@ int stepFlip(Ctx *ctx, StageClock &clk, int *iters)
     }
     FS2D_TRY(gridExtrapolateVelocity(ctx, 10));
     FS2D_TRY(particlesUpdate(ctx));
+    if (ctx->pstream.outHost) FS2D_TRY(fs2d_particle_stream_velocities_final(ctx, ctx->pstream.outHost, ctx->pstream.outCapacity));
     clk.end(PARTICLE_UPDATE);
     FS2D_TRY(particlesCount(ctx));
     return FS2D_OK;

@@ -389,9 +389,6 @@ void FlipSolver::step()
         densityCorrection();
         endStage(DENSITY);
     }
-    // streamed particle state: no stage below moves or reorders the existing records (reseeding appends, the count cap
-    // flags), and the liquid solver never rewrites property columns: positions and columns leave for the host now
-    if (m_streamBuf) check(fs2d_particle_stream_positions_final(device(), m_streamBuf, m_streamCapacity, 1), "fs2d_particle_stream_positions_final");
     gridUpdate();
     endStage(GRID_UPDATE);
     afterTransfer();
@@ -400,6 +397,12 @@ void FlipSolver::step()
     saveVelocity();
     applyBodyForces();
     endStage(AFTER_TRANSFER);
+    // Streamed particle state: since the density correction no stage moves or reorders the existing records (reseeding
+    // appends, the count cap flags) and the liquid solver never rewrites property columns, so positions and columns can
+    // leave for the host. They do so HERE, under the pressure solve -- a latency-bound kernel working out of L2 that the
+    // copy does not disturb -- rather than under the gathers right after the density correction, which it slowed down by
+    // ~20 % (P2G 0.94 -> 1.27 ms at 4096^2).
+    if (m_streamBuf) check(fs2d_particle_stream_positions_final(device(), m_streamBuf, m_streamCapacity, 1), "fs2d_particle_stream_positions_final");
     project();
     endStage(PRESSURE);
     updateVelocityFromSolids();
@@ -412,6 +415,8 @@ void FlipSolver::step()
     }
     extrapolateVelocity(10);
     particleUpdate();
+    // streamed particle state: the velocities of the existing records are final (the count cap flags, reseeding appends)
+    if (m_streamBuf) check(fs2d_particle_stream_velocities_final(device(), m_streamBuf, m_streamCapacity), "fs2d_particle_stream_velocities_final");
     endStage(PARTICLE_UPDATE);
     countParticles();
     reseedParticles();

@@ -209,6 +209,8 @@ int fs2d_upload_particles_packed(fs2d_handle h, const void *host_buf, int64_t co
  *       that no stage of this substep moves or reorders the existing records any more: their positions (and property
  *       columns, with props_final != 0) start for host_out now, under the P2G / pressure stages. Any later advection,
  *       position adjustment or sort silently cancels the promise (fs2d_particle_stream_end then sends everything).
+ *   fs2d_particle_stream_velocities_final   the same promise for the velocities, after the G2P update: they travel while
+ *       the count cap and the reseeding run.
  *   fs2d_particle_stream_end   sends what has not left yet -- velocities, storage bytes, records appended by the
  *       reseed -- waits for all copies and returns the number of records. Works without a preceding begin (a plain
  *       download in the sectioned layout). host_in and host_out may be the same buffer.
@@ -216,10 +218,15 @@ int fs2d_upload_particles_packed(fs2d_handle h, const void *host_buf, int64_t co
 size_t fs2d_particle_stream_bytes(fs2d_handle h, int64_t capacity_records);
 int fs2d_particle_stream_begin(fs2d_handle h, const void *host_in, int64_t count, int64_t capacity_records);
 int fs2d_particle_stream_positions_final(fs2d_handle h, void *host_out, int64_t capacity_records, int props_final);
+int fs2d_particle_stream_velocities_final(fs2d_handle h, void *host_out, int64_t capacity_records);
 int fs2d_particle_stream_end(fs2d_handle h, void *host_out, int64_t capacity_records, int64_t *count);
 /* For the composite fs2d_substep (which has no caller between its stages): announce the buffer the next
  * fs2d_particle_stream_end will be given, so that the substep sends the early sections itself. Cleared by _end. */
 int fs2d_particle_stream_set_output(fs2d_handle h, void *host_out, int64_t capacity_records);
+/* Measurement aid: device time (ms, CUDA events) of the copies of the last streamed substep -- host -> device sections
+ * storage bytes, velocities, positions, property columns; the early device -> host sections; the device -> host copies
+ * of fs2d_particle_stream_end (with its pack kernel). Call after fs2d_particle_stream_end. */
+int fs2d_particle_stream_timing(fs2d_handle h, float *ms6);
 /* State dump / restore (checkpoint). The reference keeps its state in the solver object and has no serialisation
  * (its viewer reads the live object, Liquid2dRender/fluidrenderer.cpp:497-986); SURVEY 8(f)4 asks for one here. The blob
  * holds every device grid of the FS2D_GRID_* table as it is (a deferred level-set walk stays deferred), the particle
