@@ -953,9 +953,12 @@ template <bool MG> __device__ __forceinline__ void llPublish(const MgArgs &m, in
         const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(word < 2 ? v0 : v1));
         const unsigned long long half = (word & 1) ? (bits >> 32) : (bits & 0xffffffffull);
         unsigned long long *dst = &m.peerMail[r]->ll[m.ringBase + (phase & 7)][m.rank].w[word];
-        // everything this rank wrote before the barrier (tile outputs; halo rows pushed into the neighbours) is ordered
-        // before the word the consumers wait for
-        if (MG)
+        // Everything this rank wrote before the barrier is ordered before the word the consumers wait for -- at GPU scope:
+        // the tile outputs are only ever read by CTAs of this rank; halo rows stored into a neighbour's arrays were fenced
+        // at system scope by the CTA that stored them, before its ticket (resBarrier / solveBarrier, `remoteStores`), and
+        // this CTA has seen every ticket; halo rows sent as self-validating words need no ordering at all. A system-scope
+        // fence here costs 1.3 us per barrier (one rank in slab mode: 4.5-4.9 -> 3.2-3.6 us; FS2D_MG_DEBUG & 64 restores it).
+        if (MG && (m.debug & 64))
             __threadfence_system();
         else
             __threadfence();
@@ -975,7 +978,7 @@ template <bool MG> __device__ __forceinline__ bool llCollect(const MgArgs &m, in
     {
         const unsigned long long *src = &m.mail->ll[m.ringBase + (phase & 7)][lane >> 2].w[lane & 3];
         const long long t0 = clock64();
-        const bool relaxedPoll = MG && (m.debug & 32);  // A/B: poll with relaxed loads, one fence after the last word arrived
+        const bool relaxedPoll = MG && (m.debug & (32 | 128));  // A/B: poll with relaxed loads; 32: one fence after the last word arrived, 128: none
         for (;;)
         {
             if (relaxedPoll)
@@ -1828,7 +1831,7 @@ template <bool MG, bool PAGED> __global__ void __launch_bounds__(RNT, 1) pcgResi
     const unsigned int P = static_cast<unsigned int>(min(static_cast<int>(gridDim.x), count));  // participating CTAs
     // too many tiles to hold (or nothing to do): PcgScalars::pad stays 0 and the next kernel in line runs
     if (count <= 0) return;
-    if (!PAGED && count > RES_TPC * static_cast<int>(gridDim.x)) return;
+    if (!PAGED && (count > RES_TPC * static_cast<int>(gridDim.x) || g.a.N >= (1ll << 31))) return;  // 32-bit cell indices below
     if (PAGED && (count <= RES_TPC * static_cast<int>(gridDim.x) || count > RES_PAGED_TPC * static_cast<int>(gridDim.x) ||
                   static_cast<long long>(count) * PTILE_PAD > g.a.N || g.a.N >= (1ll << 31)))
         return;
@@ -1918,13 +1921,15 @@ template <bool MG, bool PAGED> __global__ void __launch_bounds__(RNT, 1) pcgResi
     // ---- per-tile constants in registers: origin, ring cell, operator bytes of the thread's cells
     int ti0[RES], tj0[RES], ringPos[RES];
     int ringSrc[RES];                      // 0: the local q / z array, 1 / 2: LL halo row from the lower / upper neighbour
-    long long ringN[RES];
+    int ringN[RES];                        // linear index of the ring value (N < 2^31 here), -1: outside the vector
+    unsigned int edge[RES];                // MG: bit k: cell k lies on my first row and is pushed to the lower neighbour; bit 4 + k: last row, upper
     unsigned int rowBits[RES];             // 4 x rowInfo byte
     unsigned int validBits[RES];           // bit k: cell k of this thread lies inside the matrix
     unsigned long long preBits[RES];       // 4 x preInfo half-word
     double xacc[RES][RES_CELLS];
-    long long cell0[RES];                      // linear index of the thread's first cell of the tile (rows advance by rowStep)
-    const long long rowStep = 4 * J;
+    int cell0[RES];                            // linear index of the thread's first cell of the tile (rows advance by rowStep)
+    const int J32 = static_cast<int>(J), N32 = static_cast<int>(N);
+    const int rowStep = 4 * J32;
     const int q0 = (lr + 1) * PSW + lc + 2, t0i = lr * TC + lc;  // the same cell inside the halo-extended box / the interior array
     bool remote = false;                       // (uniform over the CTA) a tile holds a slab-boundary row pushed to a neighbour
 #pragma unroll
@@ -1934,6 +1939,7 @@ template <bool MG, bool PAGED> __global__ void __launch_bounds__(RNT, 1) pcgResi
         ringPos[t] = -1;
         ringSrc[t] = 0;
         ringN[t] = -1;
+        edge[t] = 0;
         cell0[t] = 0;
         rowBits[t] = 0;
         preBits[t] = 0;
@@ -1946,13 +1952,24 @@ template <bool MG, bool PAGED> __global__ void __launch_bounds__(RNT, 1) pcgResi
             const int ti = tile / g.a.tilesJ, tj = tile - ti * g.a.tilesJ;
             ti0[t] = ti * TR;
             tj0[t] = tj * TC;
-            cell0[t] = static_cast<long long>(ti0[t] + lr) * J + tj0[t] + lc;
-            resRingCell(tid, ti0[t], tj0[t], I, J, N, &ringPos[t], &ringN[t]);
+            cell0[t] = (ti0[t] + lr) * J32 + tj0[t] + lc;
+            resRingCell32(tid, ti0[t], tj0[t], I, J32, N32, &ringPos[t], &ringN[t]);
+            if (MG && !(mg.debug & 2))
+            {
+                // which of the thread's cells sit on a slab-boundary row that is pushed to a row neighbour
+#pragma unroll
+                for (int k = 0; k < RES_CELLS; k++)
+                {
+                    const int gi = ti0[t] + lr + 4 * k;
+                    if (gi == mg.rowBegin && g.loQ) edge[t] |= 1u << k;
+                    if (gi == mg.rowEnd - 1 && g.hiQ) edge[t] |= 16u << k;
+                }
+            }
             if (MG && ringN[t] >= 0)
             {
                 // a ring value that lives on a neighbour's row (wrap columns included: the linear index decides)
-                const long long srcRow = ringN[t] / J;
-                const int srcTile = static_cast<int>((ringN[t] - srcRow * J) / TC);
+                const int srcRow = ringN[t] / J32;
+                const int srcTile = (ringN[t] - srcRow * J32) / TC;
                 if (loLL && srcRow == mg.rowBegin - 1) ringSrc[t] = 1;
                 if (hiLL && srcRow == mg.rowEnd) ringSrc[t] = 2;
                 // a tile the neighbour skips pushes nothing: every vector is identically zero there
@@ -2059,7 +2076,7 @@ template <bool MG, bool PAGED> __global__ void __launch_bounds__(RNT, 1) pcgResi
             {
                 // z of K2(i - 1) = phase 2i; before the first iteration z = rhs, which every rank computed for its halo rows itself
                 if (MG && ringSrc[t] && i > 0)
-                    ringV[t] = llHaloLoad(mg.haloLL, ringSrc[t] - 1, 1, J, ringN[t] % J, llTag(mg, 2 * i), &mg.mail->error);
+                    ringV[t] = llHaloLoad(mg.haloLL, ringSrc[t] - 1, 1, J, ringN[t] % J32, llTag(mg, 2 * i), &mg.mail->error);
                 else
                     ringV[t] = __ldcg(g.z + ringN[t]);
             }
@@ -2094,29 +2111,26 @@ template <bool MG, bool PAGED> __global__ void __launch_bounds__(RNT, 1) pcgResi
                     const int p = q0 + k * 4 * PSW;
                     if ((validBits[t] >> k) & 1u)
                     {
-                        const long long n = cell0[t] + k * rowStep;
-                        const long long gi = ti0[t] + lr + 4 * k, gj = tj0[t] + lc;  // slab-boundary tests only (MG)
-                        (void)gi;
-                        (void)gj;
+                        const int n = cell0[t] + k * rowStep;
                         const double c = rt.S[p];
                         const double o = rowA(static_cast<uint8_t>(rowBits[t] >> (8 * k)), g.a.scale, c, rt.S[p - PSW], rt.S[p + PSW], rt.S[p - 1], rt.S[p + 1]);
                         rt.T[t0i + k * 4 * TC] = o;
                         g.q[n] = o;
-                        if (MG && !(mg.debug & 2))
+                        if (MG && edge[t])
                         {
                             // my first row is the lower neighbour's halo row "from above" (its side 1), my last row the
                             // upper neighbour's halo row "from below" (its side 0)
-                            if (gi == mg.rowBegin && g.loQ)
+                            if ((edge[t] >> k) & 1u)
                             {
                                 if (loLL)
-                                    llHaloStore(mg.loHaloLL, 1, 0, J, gj, o, llTag(mg, 2 * i + 1));
+                                    llHaloStore(mg.loHaloLL, 1, 0, J, tj0[t] + lc, o, llTag(mg, 2 * i + 1));
                                 else
                                     g.loQ[n] = o;
                             }
-                            if (gi == mg.rowEnd - 1 && g.hiQ)
+                            if ((edge[t] >> (4 + k)) & 1u)
                             {
                                 if (hiLL)
-                                    llHaloStore(mg.hiHaloLL, 0, 0, J, gj, o, llTag(mg, 2 * i + 1));
+                                    llHaloStore(mg.hiHaloLL, 0, 0, J, tj0[t] + lc, o, llTag(mg, 2 * i + 1));
                                 else
                                     g.hiQ[n] = o;
                             }
@@ -2223,7 +2237,7 @@ template <bool MG, bool PAGED> __global__ void __launch_bounds__(RNT, 1) pcgResi
             if (t < myTiles && ringN[t] >= 0)
             {
                 if (MG && ringSrc[t])
-                    ringV[t] = llHaloLoad(mg.haloLL, ringSrc[t] - 1, 0, J, ringN[t] % J, llTag(mg, 2 * i + 1), &mg.mail->error);
+                    ringV[t] = llHaloLoad(mg.haloLL, ringSrc[t] - 1, 0, J, ringN[t] % J32, llTag(mg, 2 * i + 1), &mg.mail->error);
                 else
                     ringV[t] = __ldcg(g.q + ringN[t]);
             }
@@ -2254,27 +2268,24 @@ template <bool MG, bool PAGED> __global__ void __launch_bounds__(RNT, 1) pcgResi
                     const int p = q0 + k * 4 * PSW;
                     if ((validBits[t] >> k) & 1u)
                     {
-                        const long long n = cell0[t] + k * rowStep;
-                        const long long gi = ti0[t] + lr + 4 * k, gj = tj0[t] + lc;  // slab-boundary tests only (MG)
-                        (void)gi;
-                        (void)gj;
+                        const int n = cell0[t] + k * rowStep;
                         const double c = rt.R[p];
                         const double o = rowM(static_cast<uint16_t>(preBits[t] >> (16 * k)), sm.preTbl, c, rt.R[p - PSW], rt.R[p + PSW], rt.R[p - 1], rt.R[p + 1]);
                         rt.T[t0i + k * 4 * TC] = o;
                         g.z[n] = o;
-                        if (MG && !(mg.debug & 2))
+                        if (MG && edge[t])
                         {
-                            if (gi == mg.rowBegin && g.loZ)
+                            if ((edge[t] >> k) & 1u)
                             {
                                 if (loLL)
-                                    llHaloStore(mg.loHaloLL, 1, 1, J, gj, o, llTag(mg, 2 * i + 2));
+                                    llHaloStore(mg.loHaloLL, 1, 1, J, tj0[t] + lc, o, llTag(mg, 2 * i + 2));
                                 else
                                     g.loZ[n] = o;
                             }
-                            if (gi == mg.rowEnd - 1 && g.hiZ)
+                            if ((edge[t] >> (4 + k)) & 1u)
                             {
                                 if (hiLL)
-                                    llHaloStore(mg.hiHaloLL, 0, 1, J, gj, o, llTag(mg, 2 * i + 2));
+                                    llHaloStore(mg.hiHaloLL, 0, 1, J, tj0[t] + lc, o, llTag(mg, 2 * i + 2));
                                 else
                                     g.hiZ[n] = o;
                             }
@@ -2868,7 +2879,9 @@ static bool pipeUsable(const Ctx *ctx) { return (ctx->J % 2) == 0 && !ctx->force
 
 int pcgSolveDevice(Ctx *ctx, int iterLimit, double tol)
 {
-    const bool mgOn = ctx->slab.enabled && ctx->slab.world > 1;
+    // FS2D_MG_FORCE (measurement aid): a single rank in slab mode runs the <MG = true> kernels, without a neighbour
+    static const bool mgForce = std::getenv("FS2D_MG_FORCE") != nullptr;
+    const bool mgOn = ctx->slab.enabled && (ctx->slab.world > 1 || mgForce);
     const int tilesJ = divUp(ctx->J, TC);
     int blocks = pcgTileBlocks(ctx);  // tiles this rank walks
     int tileBase = 0;

@@ -99,6 +99,16 @@ if int(os.environ.get("FS2D_MG_DEBUG", "0")) & 8:
         L.fs2d_debug_mg_timeline(d.h, tl.ctypes.data_as(C.c_void_p))
         t = tl[101:301].astype(np.int64)  # phases 101..300: K1 odd, K2 even
         rows = {}
+        if d.pcg_last_kernel() > 0:
+            # pcgResidentKernel stamps: 0 phase start, 1 resident tiles done, 2 paged tiles done, 3 barrier passed (CTA 0)
+            for name, sel in (("k1", t[0::2]), ("k2", t[1::2])):
+                rows[name] = {"resident_us": float(np.mean(sel[:, 1] - sel[:, 0])) / 1e3, "paged_us": float(np.mean(sel[:, 2] - sel[:, 1])) / 1e3,
+                              "barrier_us": float(np.mean(sel[:, 3] - sel[:, 2])) / 1e3,
+                              "barrier_p10_p50_p90_us": [float(x) / 1e3 for x in np.percentile(sel[:, 3] - sel[:, 2], [10, 50, 90])]}
+            rows["phase_period_us"] = float(np.mean(np.diff(t[:, 0]))) / 1e3
+            rows["kernel"] = int(d.pcg_last_kernel())
+            out["timeline_" + ("dense" if dense else "active")] = rows
+            continue
         for name, sel in (("k1", t[0::2]), ("k2", t[1::2])):
             rows[name] = {"first_tile_us": float(np.mean(sel[:, 1] - sel[:, 0])) / 1e3,
                           "walk_rest_us": float(np.mean(sel[:, 2] - sel[:, 1])) / 1e3,

@@ -14,6 +14,8 @@ def material(res):
 for res in [int(a) for a in sys.argv[1:]] or [1024, 4096]:
     d = capi.Device(res, res, dx=50.0 / res, fluid_density=0.5, pcg_iter_limit=200)
     m = material(res)
+    if os.environ.get("FS2D_PROBE_SLAB1"):
+        d.slab_configure(0, 1)   # one rank in slab mode: the <MG = true> kernels without a neighbour
     d.upload("MATERIAL", m)
     d.set_step_dt(1 / 30.0)
     d.stage("build_matrix")
