@@ -1011,6 +1011,46 @@ template <bool MG> __device__ __forceinline__ bool llCollect(const MgArgs &m, in
     return ok;
 }
 
+// The same for a rank that already knows its own sums (lane 0 holds them): only the words of the OTHER ranks are waited for.
+template <bool MG> __device__ __forceinline__ bool llCollectPeers(const MgArgs &m, int phase, double ownSum, double ownMax, double *sum, double *mx)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned int want = llTag(m, phase);
+    unsigned long long w = 0;
+    bool ok = true;
+    if (lane < 4 * m.world && (lane >> 2) != m.rank)
+    {
+        const unsigned long long *src = &m.mail->ll[m.ringBase + (phase & 7)][lane >> 2].w[lane & 3];
+        const long long t0 = clock64();
+        for (;;)
+        {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
+            if (static_cast<unsigned int>(w >> 32) == want) break;
+            if (clock64() - t0 > MG_SPIN_LIMIT)
+            {
+                ok = false;
+                m.mail->error = 2;
+                break;
+            }
+        }
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    ownSum = __shfl_sync(0xffffffffu, ownSum, 0);
+    ownMax = __shfl_sync(0xffffffffu, ownMax, 0);
+    double s = 0.0, x = 0.0;
+    for (int r = 0; r < m.world; r++)
+    {
+        const unsigned long long a0 = __shfl_sync(0xffffffffu, w, 4 * r), a1 = __shfl_sync(0xffffffffu, w, 4 * r + 1);
+        const unsigned long long b0 = __shfl_sync(0xffffffffu, w, 4 * r + 2), b1 = __shfl_sync(0xffffffffu, w, 4 * r + 3);
+        const bool mine = r == m.rank;
+        s += mine ? ownSum : __longlong_as_double(static_cast<long long>((a0 & 0xffffffffull) | (a1 << 32)));
+        x = fmax(x, mine ? ownMax : __longlong_as_double(static_cast<long long>((b0 & 0xffffffffull) | (b1 << 32))));
+    }
+    *sum = s;
+    *mx = x;
+    return ok;
+}
+
 // Sum and max over the CTA in one pass (same operation order as blockReduce); result valid in thread 0.
 __device__ __forceinline__ void blockReduce2(double &s, double &m, double *scratch /* >= 16 doubles */)
 {
@@ -1716,43 +1756,57 @@ __device__ __forceinline__ bool resBarrier(const SolveArgs &g, const MgArgs &m, 
         *mx = sm.bc[1];
         return true;
     }
-    if (tid == 0)
+    // Row slabs: the local half is the one-GPU barrier above -- ticket, and EVERY CTA sums the partials of the rank's CTAs
+    // itself (same order everywhere, hence the same bits) -- so no CTA waits for its own rank's result to come back
+    // through the mail (the last-CTA reduction + publish + collect chain cost 0.9 us per barrier more, measured with one
+    // rank). CTA 0 publishes the rank's sums to the other ranks; warp 0 of every CTA polls the words of the OTHER ranks in
+    // its own mail and combines all of them in rank order.
     {
-        g.a.partials[blockIdx.x] = v0;
-        g.a.partials[nb + blockIdx.x] = v1;
-        if (remoteStores)
-            __threadfence_system();
-        else
-            __threadfence();
-        sm.isLast = (atomicAdd(g.ticket, 1u) == (barrierIndex + 1u) * nb - 1u);
-    }
-    __syncthreads();
-    if (sm.isLast)
-    {
+        double *part = g.a.partials + (barrierIndex & 1u) * 2u * nb;
+        if (tid == 0)
+        {
+            part[blockIdx.x] = v0;
+            part[nb + blockIdx.x] = v1;
+            if (remoteStores)
+                __threadfence_system();  // halo rows stored into a neighbour's arrays: acknowledged before the ticket
+            else
+                __threadfence();
+            atomicAdd(g.ticket, 1u);
+            const unsigned int target = (barrierIndex + 1u) * nb;
+            unsigned int seen;
+            do
+            {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(g.ticket) : "memory");
+            } while (seen < target);
+        }
+        __syncthreads();
         double ts = 0.0, tm = 0.0;
         for (unsigned int k = tid; k < nb; k += RNT)
         {
-            ts += __ldcg(g.a.partials + k);
-            tm = fmax(tm, __ldcg(g.a.partials + nb + k));
+            ts += __ldcg(part + k);
+            tm = fmax(tm, __ldcg(part + nb + k));
         }
-        blockReduce2W16(ts, tm, sm.red);
-        if (tid == 0)
+        blockReduce2W16(ts, tm, sm.red);  // thread 0: the rank's sums
+        if (blockIdx.x == 0)
         {
-            sm.pub[0] = ts;
-            sm.pub[1] = tm;
+            if (tid == 0)
+            {
+                sm.pub[0] = ts;
+                sm.pub[1] = tm;
+            }
+            __syncthreads();
+            llPublish<MG>(m, phase, sm.pub[0], sm.pub[1]);
         }
-        __syncthreads();
-        llPublish<MG>(m, phase, sm.pub[0], sm.pub[1]);
-    }
-    if (tid < 32)
-    {
-        double s = 0.0, x = 0.0;
-        const bool ok = llCollect<MG>(m, phase, &s, &x);
-        if (tid == 0)
+        if (tid < 32)
         {
-            sm.ok = ok ? 1 : 0;
-            sm.bc[0] = s;
-            sm.bc[1] = x;
+            double s = 0.0, x = 0.0;
+            const bool ok = llCollectPeers<MG>(m, phase, ts, tm, &s, &x);
+            if (tid == 0)
+            {
+                sm.ok = ok ? 1 : 0;
+                sm.bc[0] = s;
+                sm.bc[1] = x;
+            }
         }
     }
     __syncthreads();
