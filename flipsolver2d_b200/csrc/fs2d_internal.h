@@ -421,6 +421,11 @@ int slabAllGather(Ctx *ctx, const long long v[4], long long *out /* world x 4 */
 int slabCheckError(Ctx *ctx);
 int slabGatherRows(Ctx *ctx, void *array, size_t rowBytes, int rowsTotal);  // collective: own rows -> every rank
 int slabGatherMany(Ctx *ctx, void *const *arrays, const size_t *rowBytes, const int *rowsTotal, int count);
+// The same for a band of rows only: every rank contributes the first / last row it finds interesting among its own
+// (localMax < localMin: none), the union over the ranks grown by `margin` rows is what travels; *rowLo / *rowHi return it
+// (half open; rowHi <= rowLo: no rank found anything, nothing was sent).
+int slabGatherBand(Ctx *ctx, void *const *arrays, const size_t *rowBytes, const int *rowsTotal, int count, int localMin, int localMax,
+                   int margin, int *rowLo, int *rowHi);
 void pcgPreloadSlabKernels();           // pcg.cu
 // step.cu
 int stepSubstep(Ctx *ctx, float dt, float *stageMs, int *iters);

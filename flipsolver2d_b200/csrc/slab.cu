@@ -588,6 +588,56 @@ int slabGatherMany(Ctx *ctx, void *const *arrays, const size_t *rowBytes, const 
     return FS2D_OK;
 }
 
+int slabGatherBand(Ctx *ctx, void *const *arrays, const size_t *rowBytes, const int *rowsTotal, int count, int localMin, int localMax,
+                   int margin, int *rowLo, int *rowHi)
+{
+    SlabState &s = ctx->slab;
+    *rowLo = 0;
+    *rowHi = ctx->I;
+    if (!s.enabled || s.world == 1) return FS2D_OK;
+    FS2D_TRY(requireConnected(ctx));
+    // the opening all-gather (nobody is overwritten before it has finished what it was doing) carries the rows
+    const long long mine[4] = {localMax >= localMin ? localMin : 0x7fffffff, localMax >= localMin ? localMax : -1, 0, 0};
+    long long all[4 * FS2D_MAX_RANKS];
+    FS2D_TRY(slabAllGather(ctx, mine, all));
+    long long gmin = 0x7fffffff, gmax = -1;
+    for (int r = 0; r < s.world; r++)
+    {
+        gmin = std::min(gmin, all[4 * r]);
+        gmax = std::max(gmax, all[4 * r + 1]);
+    }
+    const long long zero[4] = {0, 0, 0, 0};
+    if (gmax < gmin)
+    {
+        *rowLo = *rowHi = 0;
+        return slabAllGather(ctx, zero, all);  // every rank takes this branch: keep the pair of handshakes
+    }
+    const int lo = static_cast<int>(std::max<long long>(0, gmin - margin)), hi = static_cast<int>(std::min<long long>(ctx->I, gmax + 1 + margin));
+    *rowLo = lo;
+    *rowHi = hi;
+    for (int k = 0; k < count; k++)
+    {
+        // the extra U row belongs to the last slab and travels when the band reaches the last cell row
+        const int ownEnd = s.rank == s.world - 1 ? rowsTotal[k] : s.rowEnd;
+        const int bandEnd = hi == ctx->I ? rowsTotal[k] : hi;
+        const int b = std::max(s.rowBegin, lo), e = std::min(ownEnd, bandEnd);
+        if (e <= b) continue;
+        GatherRowsArgs a;
+        a.heap = ctx->heap;
+        for (int r = 0; r < FS2D_MAX_RANKS; r++) a.peerHeap[r] = r < s.world ? s.peerHeap[r] : nullptr;
+        a.rank = s.rank;
+        a.world = s.world;
+        a.offset = static_cast<unsigned long long>(static_cast<unsigned char *>(arrays[k]) - ctx->heap);
+        a.bytesBegin = static_cast<unsigned long long>(b) * rowBytes[k];
+        a.bytes = static_cast<unsigned long long>(e - b) * rowBytes[k];
+        const int blocks = std::max(1, ctx->smCount / s.share);
+        slabGatherRowsKernel<<<blocks, 256, 0, ctx->stream>>>(a);
+        ctx->launches++;
+    }
+    FS2D_CUDA(cudaGetLastError());
+    return slabAllGather(ctx, zero, all);
+}
+
 extern "C" {
 
 int fs2d_slab_configure(fs2d_handle ctx, int rank, int world, int device_share)

@@ -194,12 +194,12 @@ __global__ void viscBoxResetKernel(int *box)
 }
 
 // Bounding box of the cells whose right-hand side (density * field, zero exactly when the field is) or viscosity is not zero.
-__global__ void __launch_bounds__(NT) viscBoxKernel(const float *__restrict__ field, int fieldStride, const float *__restrict__ mu, int I, int J,
-                                                    int *__restrict__ box)
+__global__ void __launch_bounds__(NT) viscBoxKernel(const float *__restrict__ field, int fieldStride, const float *__restrict__ mu, int rowLo, int rowHi,
+                                                    int J, int *__restrict__ box)
 {
-    // a CTA takes whole rows, its threads stride over the columns (no index division)
+    // a CTA takes whole rows (of [rowLo, rowHi)), its threads stride over the columns (no index division)
     int iMin = 0x7fffffff, iMax = -1, jMin = 0x7fffffff, jMax = -1;
-    for (int i = blockIdx.x; i < I; i += gridDim.x)
+    for (int i = rowLo + blockIdx.x; i < rowHi; i += gridDim.x)
         for (int j = threadIdx.x; j < J; j += NT)
             if (field[static_cast<long long>(i) * fieldStride + j] != 0.f || mu[static_cast<long long>(i) * J + j] != 0.f)
             {
@@ -575,13 +575,15 @@ __global__ void __launch_bounds__(NT) heavyWriteBackKernel(HeavyArgs a, float *_
 
 // One Eigen-style solve for `field` (U: stride J; V: stride J + 1). *iters = Eigen's iterations(); returns
 // FS2D_OK with *failed = 1 when the solver did not reach the tolerance (the reference prints and gives up).
-static int viscSolve(Ctx *ctx, ViscArgs &a, float *field, int stride, float density, int *iters, int *failed)
+static int viscSolve(Ctx *ctx, ViscArgs &a, float *field, int stride, float density, int *iters, int *failed, int rowLo, int rowHi)
 {
     cudaStream_t st = ctx->stream;
     const int blocks = std::min<long long>(divUp(ctx->N, NT), static_cast<long long>(ctx->smCount) * 8);
     int *box = reinterpret_cast<int *>(static_cast<unsigned char *>(ctx->viscScalars) + 128);
     viscBoxResetKernel<<<1, 1, 0, st>>>(box);
-    viscBoxKernel<<<std::min(ctx->I, ctx->smCount * 8), NT, 0, st>>>(field, stride, a.mu, ctx->I, ctx->J, box);
+    // row slabs: only the rows [rowLo, rowHi) gathered from all ranks are exact copies; every row outside them has a zero
+    // right-hand side and a zero viscosity on the rank that owns it (that is how the band was chosen)
+    viscBoxKernel<<<std::max(1, std::min(rowHi - rowLo, ctx->smCount * 8)), NT, 0, st>>>(field, stride, a.mu, rowLo, rowHi, ctx->J, box);
     a.box = box;
     viscInitKernel<<<blocks, NT, 0, st>>>(a, field, stride, density);
     ctx->launches += 3;
@@ -677,17 +679,37 @@ static int gridViscosityHeavy(Ctx *ctx, int *iters)
 
 int gridViscosity(Ctx *ctx, int *iters)
 {
+    int bandLo = 0, bandHi = ctx->I;  // rows the solve may look at (row slabs: the gathered band)
     if (ctx->slab.enabled && ctx->slab.world > 1)
     {
         // Row slabs: the solve is REPLICATED. Every rank pushes its rows of U, V, the viscosity grid and the material grid
         // to all the others (one collective) and then solves the whole system itself -- same kernels, same reduction
-        // order, hence bit-identical to a single handle on every rank, and U / V come out valid on all rows. The stage
-        // is a handful of iterations of grid-only passes; distributing it would add two all-reduces
-        // and a halo exchange per iteration for a stage that is ~2 ms at 4096^2.
+        // order, hence bit-identical to a single handle on every rank. The stage is a handful of iterations of grid-only
+        // passes; distributing it would add two all-reduces and a halo exchange per iteration for a
+        // stage that is ~2 ms at 4096^2.
         void *arr[4] = {ctx->U, ctx->V, ctx->viscosity, ctx->material};
         const size_t rb[4] = {sizeof(float) * ctx->J, sizeof(float) * (ctx->J + 1), sizeof(float) * ctx->J, static_cast<size_t>(ctx->J)};
         const int rt[4] = {ctx->I + 1, ctx->I, ctx->I, ctx->I};
-        FS2D_TRY(slabGatherMany(ctx, arr, rb, rt, 4));
+        if (ctx->p.heavy_viscosity)
+            FS2D_TRY(slabGatherMany(ctx, arr, rb, rt, 4));  // the coupled model runs on every sample: all rows
+        else
+        {
+            // The light model only touches the box of cells with a non-zero right-hand side or viscosity, grown by two
+            // cells (viscBox): only the band of rows around it travels -- 44 % of the rows of the 4096^2 dam break, and none
+            // of the 2500 empty rows the first slab of a balanced split owns (the full gather cost 3.8 ms of NVLink
+            // pushes per substep on 4 GPUs). Each rank looks at its own rows; the opening handshake carries the result.
+            if (!ctx->viscScalars) FS2D_CUDA(cudaMalloc(&ctx->viscScalars, 256));
+            int *box = reinterpret_cast<int *>(static_cast<unsigned char *>(ctx->viscScalars) + 128);
+            const SlabRows own = slabOwn(ctx);
+            viscBoxResetKernel<<<1, 1, 0, ctx->stream>>>(box);
+            const int grid = std::max(1, std::min(own.hi - own.lo, ctx->smCount * 8));
+            viscBoxKernel<<<grid, NT, 0, ctx->stream>>>(ctx->U, ctx->J, ctx->viscosity, own.lo, own.hi, ctx->J, box);
+            viscBoxKernel<<<grid, NT, 0, ctx->stream>>>(ctx->V, ctx->J + 1, ctx->viscosity, own.lo, own.hi, ctx->J, box);
+            ctx->launches += 3;
+            int rows[2] = {0, -1};
+            FS2D_CUDA(fs2dCopyToHost(ctx, rows, box, sizeof(rows)));
+            FS2D_TRY(slabGatherBand(ctx, arr, rb, rt, 4, rows[0], rows[1], 3, &bandLo, &bandHi));
+        }
     }
     if (ctx->p.heavy_viscosity) return gridViscosityHeavy(ctx, iters);
     if (!ctx->viscScalars) FS2D_CUDA(cudaMalloc(&ctx->viscScalars, 256));
@@ -711,7 +733,7 @@ int gridViscosity(Ctx *ctx, int *iters)
     const float density = static_cast<float>(ctx->p.fluid_density);  // apply(..., float density)
     const int blocks = std::min<long long>(divUp(ctx->N, NT), static_cast<long long>(ctx->smCount) * 8);
     int itU = 0, itV = 0, failed = 0;
-    FS2D_TRY(viscSolve(ctx, a, ctx->U, ctx->J, density, &itU, &failed));
+    FS2D_TRY(viscSolve(ctx, a, ctx->U, ctx->J, density, &itU, &failed, bandLo, bandHi));
     if (failed)
     {
         if (iters) *iters = -1;  // "Viscosity solver U solving failed!" -> return -1 before anything is applied
@@ -719,7 +741,7 @@ int gridViscosity(Ctx *ctx, int *iters)
     }
     viscWriteBackKernel<<<blocks, NT, 0, ctx->stream>>>(a, ctx->U, ctx->J, density);
     ctx->launches++;
-    FS2D_TRY(viscSolve(ctx, a, ctx->V, ctx->J + 1, density, &itV, &failed));
+    FS2D_TRY(viscSolve(ctx, a, ctx->V, ctx->J + 1, density, &itV, &failed, bandLo, bandHi));
     if (failed)
     {
         if (iters) *iters = -1;
