@@ -729,14 +729,49 @@ __global__ void __launch_bounds__(NT) solidFrictionKernel(const int32_t *__restr
 // ------------------------------------------------------------------ semi-Lagrangian advection
 // eulerAdvectionThread (flipsolver2d.cpp:340-351): back-trace RK4(-dt) from the INTEGER sample index
 // (not the staggered sample position) and interpolate the input grid with its own offset / OOB policy.
-__global__ void __launch_bounds__(NT) eulerAdvectKernel(GridView in, VelocityView vel, float dt, float *__restrict__ out,
-                                                        long long nBegin = 0, long long nEnd = -1)
+// (One value = gridLerp(grid, rk4(velocity, (i, j), -dt)); the kernels below evaluate the trace once for all the grids
+// that are advected from the same start point.)
+// The smoke / fire parameter grids (soot, temperature, fuel) in one pass: same cells, same integer start points, one trace.
+__global__ void __launch_bounds__(NT) smokeAdvectKernel(GridView concentration, GridView temperature, GridView fuel, int withFuel, VelocityView vel,
+                                                        float dt, float *__restrict__ outC, float *__restrict__ outT, float *__restrict__ outF,
+                                                        long long nBegin, long long nEnd)
 {
     const long long n = nBegin + blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
-    if (n >= (nEnd >= 0 ? nEnd : static_cast<long long>(in.sizeI) * in.sizeJ)) return;
-    const int i = rowOfCell(n, in.sizeJ), j = static_cast<int>(n - static_cast<long long>(i) * in.sizeJ);
+    if (n >= nEnd) return;
+    const int i = rowOfCell(n, concentration.sizeJ), j = static_cast<int>(n - static_cast<long long>(i) * concentration.sizeJ);
     const float2 prev = rk4(vel, make_float2(static_cast<float>(i), static_cast<float>(j)), -dt);
-    out[n] = gridLerp(in, prev.x, prev.y);
+    outC[n] = gridLerp(concentration, prev.x, prev.y);
+    outT[n] = gridLerp(temperature, prev.x, prev.y);
+    if (withFuel) outF[n] = gridLerp(fuel, prev.x, prev.y);
+}
+
+// NBFlipSolver::advect, the four grids in one pass (nbflipsolver.cpp:83-103). eulerAdvectionThread back-traces from the INTEGER
+// sample index whatever the offset of the grid it is called for, so the U, V, level-set and viscosity samples with the same
+// (i, j) share one and the same RK4 trace -- 16 bilinear velocity look-ups, against one look-up per advected value. Sample
+// (i, j) of the (I + 1) x (J + 1) index space: U for j < J, V / level set / viscosity for cell rows below rowHi. Same
+// arithmetic per value as one pass per grid, hence the same bits.
+__global__ void __launch_bounds__(NT) nbflipAdvectKernel(VelocityView vel, GridView sdf, GridView visc, float dt, int J, int rowLo,
+                                                         int rowHiU, int rowHi, float *__restrict__ advU, float *__restrict__ advV,
+                                                         float *__restrict__ advSdf, float *__restrict__ advVisc)
+{
+    const long long t = blockIdx.x * static_cast<long long>(NT) + threadIdx.x;
+    const int W = J + 1;
+    if (t >= static_cast<long long>(rowHiU - rowLo) * W) return;
+    const int r = rowOfCell(t, W), j = static_cast<int>(t - static_cast<long long>(r) * W), i = rowLo + r;
+    const bool cellRow = i < rowHi;
+    if (j == J && !cellRow) return;  // the corner sample belongs to no grid
+    const float2 prev = rk4(vel, make_float2(static_cast<float>(i), static_cast<float>(j)), -dt);
+    if (j < J) advU[static_cast<long long>(i) * J + j] = gridLerp(vel.u, prev.x, prev.y);
+    if (cellRow)
+    {
+        advV[static_cast<long long>(i) * W + j] = gridLerp(vel.v, prev.x, prev.y);
+        if (j < J)
+        {
+            const long long n = static_cast<long long>(i) * J + j;
+            advSdf[n] = gridLerp(sdf, prev.x, prev.y);
+            advVisc[n] = gridLerp(visc, prev.x, prev.y);
+        }
+    }
 }
 
 // NBFlipSolver::updateGridFromSources + combineLevelset (nbflipsolver.cpp:329-376)
@@ -1171,15 +1206,11 @@ int gridEulerAdvectParameters(Ctx *ctx)
     const VelocityView vel = makeVelocityView(ctx->U, ctx->V, ctx->I, ctx->J);
     const CellRange cr = cellRange(ctx, slabOwn(ctx));
     const int blocks = divUp(cr.count(), NT);
-    eulerAdvectKernel<<<blocks, NT, 0, ctx->stream>>>(concentrationView(ctx), vel, ctx->stepDt, ctx->scratchA, cr.begin, cr.end);
-    eulerAdvectKernel<<<blocks, NT, 0, ctx->stream>>>(temperatureView(ctx), vel, ctx->stepDt, ctx->scratchB, cr.begin, cr.end);
-    ctx->launches += 2;
-    if (ctx->p.sim_type == FS2D_SIM_FIRE)
-    {
-        eulerAdvectKernel<<<blocks, NT, 0, ctx->stream>>>(fuelView(ctx), vel, ctx->stepDt, ctx->scratchC, cr.begin, cr.end);
-        ctx->launches++;
-        std::swap(ctx->fuel, ctx->scratchC);
-    }
+    const bool fire = ctx->p.sim_type == FS2D_SIM_FIRE;
+    smokeAdvectKernel<<<blocks, NT, 0, ctx->stream>>>(concentrationView(ctx), temperatureView(ctx), fire ? fuelView(ctx) : concentrationView(ctx),
+                                                      fire ? 1 : 0, vel, ctx->stepDt, ctx->scratchA, ctx->scratchB, ctx->scratchC, cr.begin, cr.end);
+    ctx->launches++;
+    if (fire) std::swap(ctx->fuel, ctx->scratchC);
     std::swap(ctx->concentration, ctx->scratchA);
     std::swap(ctx->temperature, ctx->scratchB);
     ctx->smokeGridsAdvected = true;  // the members now carry OOB_EXTEND and offset (1/2,1/2)
@@ -1208,11 +1239,9 @@ int gridNbflipAdvect(Ctx *ctx)
     const long long J = ctx->J;
     const VelocityView vel = makeVelocityView(ctx->U, ctx->V, ctx->I, ctx->J);
     cudaStream_t st = ctx->stream;
-    eulerAdvectKernel<<<divUp((rowHiU - own.lo) * J, NT), NT, 0, st>>>(vel.u, vel, ctx->stepDt, ctx->advU, own.lo * J, rowHiU * J);
-    eulerAdvectKernel<<<divUp((own.hi - own.lo) * (J + 1), NT), NT, 0, st>>>(vel.v, vel, ctx->stepDt, ctx->advV, own.lo * (J + 1), own.hi * (J + 1));
-    eulerAdvectKernel<<<divUp((own.hi - own.lo) * J, NT), NT, 0, st>>>(fluidSdfView(ctx), vel, ctx->stepDt, ctx->advSdf, own.lo * J, own.hi * J);
-    eulerAdvectKernel<<<divUp((own.hi - own.lo) * J, NT), NT, 0, st>>>(viscosityView(ctx), vel, ctx->stepDt, ctx->advViscosity, own.lo * J, own.hi * J);
-    ctx->launches += 4;
+    nbflipAdvectKernel<<<divUp((rowHiU - own.lo) * (J + 1), NT), NT, 0, st>>>(vel, fluidSdfView(ctx), viscosityView(ctx), ctx->stepDt, ctx->J, own.lo,
+                                                                             rowHiU, own.hi, ctx->advU, ctx->advV, ctx->advSdf, ctx->advViscosity);
+    ctx->launches++;
     FS2D_CUDA(cudaGetLastError());
     return FS2D_OK;
 }
