@@ -31,6 +31,8 @@ def main():
     ap.add_argument("--check-res", type=int, default=512)
     ap.add_argument("--check-steps", type=int, default=6)
     ap.add_argument("--no-viscosity", action="store_true")
+    ap.add_argument("--scene", default="nbflip", choices=["nbflip", "smoke", "fire"],
+                    help="smoke / fire: BASELINE config 3's scene (grid-advected parameters) over the same row slabs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -49,7 +51,10 @@ def main():
         return type(v)(t.item())
 
     def make(res, tag, slab=True):
-        sc = scenes.dam_break(res, "nbflip", viscosity_enabled=not args.no_viscosity)
+        if args.scene == "nbflip":
+            sc = scenes.dam_break(res, "nbflip", viscosity_enabled=not args.no_viscosity)
+        else:
+            sc = scenes.smoke_test(res, ppc=4, parameter_handling="grid", sim_type=args.scene)
         path = scenes.write_scene(sc, os.path.join(tmp, "%s_r%d.json" % (tag, rank)))
         sv = host_api.Solver(path, quiet=True, device=local, slab=(rank, world) if (world > 1 and slab) else None)
         if world > 1 and slab:
@@ -119,7 +124,8 @@ def main():
     ms = float(ms.item())
     st = sv.stats()
     per = max(st["substeps"], 1)
-    out = {"config": "c4_nbflip%d_%s" % (args.res, "inviscid" if args.no_viscosity else "viscous"), "n_gpus": world,
+    name = "c4_nbflip%d_%s" % (args.res, "inviscid" if args.no_viscosity else "viscous") if args.scene == "nbflip" else "c3_%s%d_grid" % (args.scene, args.res)
+    out = {"config": name, "n_gpus": world,
            "cells": sv.N, "particles": total(sv.particle_count()), "substeps_per_s": args.steps / (ms * 1e-3),
            "ms_per_substep": ms / args.steps, "steps": args.steps, "warmup": args.warmup, "setup_s": round(setup_s, 1),
            "iterations_last_frame": {"pressure": st["pressure_iters"], "viscosity": st["viscosity_iters"]},
