@@ -450,6 +450,8 @@ int fs2d_set_obstacles(fs2d_handle ctx, int count, const float *host_friction)
     if (ctx->obstacleFriction) cudaFree(ctx->obstacleFriction);
     ctx->obstacleFriction = nullptr;
     ctx->numObstacles = count;
+    ctx->obstaclesFrictionless = true;
+    for (int k = 0; k < count; k++) ctx->obstaclesFrictionless = ctx->obstaclesFrictionless && host_friction[k] == 0.f;
     FS2D_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->obstacleFriction), sizeof(float) * std::max(count, 1)));
     if (count > 0)
         FS2D_CUDA(cudaMemcpy(ctx->obstacleFriction, host_friction, sizeof(float) * count, cudaMemcpyHostToDevice));

@@ -281,6 +281,7 @@ struct fs2d_context
     // ---- scene tables
     float *obstacleFriction = nullptr;
     int numObstacles = 0;
+    bool obstaclesFrictionless = true;  // every friction coefficient is 0: updateVelocityFromSolids multiplies by exactly 1
     fs2d_source *sources = nullptr;
     int numSources = 0;
     std::vector<fs2d_source> hostSources;

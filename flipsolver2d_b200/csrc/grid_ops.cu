@@ -1187,6 +1187,10 @@ int gridApplyPressure(Ctx *ctx)
 int gridVelocityFromSolids(Ctx *ctx)
 {
     if (ctx->numObstacles == 0) return FS2D_OK;
+    // every coefficient 0 (the default of a solid in the scene file): the average is 0 / count = 0 and every affected sample
+    // is multiplied by 1 - 0 = 1, which leaves every float as it is -- the pass (9 look-ups per cell over the whole grid) is
+    // skipped
+    if (ctx->obstaclesFrictionless) return FS2D_OK;
     const CellRange cr = cellRange(ctx, slabOwn(ctx));
     solidFrictionKernel<<<divUp(cr.count(), NT), NT, 0, ctx->stream>>>(ctx->solidId, ctx->obstacleFriction, ctx->material, ctx->I, ctx->J,
                                                                       ctx->U, ctx->V, cr.begin, cr.end);
